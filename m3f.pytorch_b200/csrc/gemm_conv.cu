@@ -1,0 +1,205 @@
+// Host launchers + C-ABI entry points for the tcgen05 pipeline (umma_kernel.cuh):
+//   m3t_gemm_bf16, m3t_conv_fprop_bf16, m3t_conv_wgrad_bf16.
+#include "../../include/m3t_b200.h"
+#include "common.cuh"
+#include "tmap.cuh"
+#include "umma_kernel.cuh"
+
+namespace m3t {
+
+template <int BN, int MT, int STAGES, int AKIND, bool A_MN, bool B_MN, int EPI>
+static int launch_umma(const CUtensorMap& tmA, const CUtensorMap& tmB, const UmmaParams& p, int tiles_m, int splits,
+                       cudaStream_t st) {
+  auto kern = umma_kernel<BN, MT, STAGES, AKIND, A_MN, B_MN, EPI>;
+  constexpr int smem = umma_smem_bytes<BN, MT, STAGES>();
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return -20;
+    attr_done = true;
+  }
+  dim3 grid((unsigned)(tiles_m * p.tiles_n), (unsigned)splits, 1);
+  kern<<<grid, kUmmaThreads, smem, st>>>(tmA, tmB, p);
+  count_launch();
+  return launch_status();
+}
+
+static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+}  // namespace m3t
+
+using namespace m3t;
+
+extern "C" int m3t_gemm_bf16(const void* A, long long lda, int a_mn, const void* B, long long ldb, int b_mn, void* D,
+                             long long ldd, int d_f32, int M, int N, int K, const float* scale, const float* shift,
+                             const void* residual, long long ldr, int relu, float* stats, void* stream) {
+  if (M <= 0 || N <= 0 || K <= 0) return -1;
+  if (a_mn && !b_mn) return -2;  // (MN, K) never occurs on the hot path
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  UmmaParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = M; p.N = N;
+  p.k_iters = ceil_div(K, kBlockK);
+  p.out = D; p.ldc = ldd; p.out_f32 = d_f32;
+  p.scale = scale; p.shift = shift;
+  p.residual = reinterpret_cast<const __nv_bfloat16*>(residual); p.ldr = ldr;
+  p.relu = relu; p.stats = stats;
+  const int tiles_m = ceil_div(M, 128);
+  const int bn = (N <= 32 && !b_mn) ? 32 : (N <= 64 ? 64 : 128);
+  p.tiles_n = ceil_div(N, bn);
+  CUtensorMap tmA, tmB;
+  int rc;
+  if (!a_mn) rc = make_tmap_2d_bf16(&tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, 64, 128);
+  else rc = make_tmap_2d_bf16(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 64, 64);
+  if (rc) return rc;
+  if (!b_mn) rc = make_tmap_2d_bf16(&tmB, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, 64, (uint32_t)bn);
+  else rc = make_tmap_2d_bf16(&tmB, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 64, 64);
+  if (rc) return rc;
+#define GEMM_CASE(BN_, AMN_, BMN_)                                                                         \
+  if (bn == BN_ && (bool)a_mn == AMN_ && (bool)b_mn == BMN_)                                               \
+    return launch_umma<BN_, 1, (BN_ >= 128 ? 4 : 4), A_TILED, AMN_, BMN_, EPI_STORE>(tmA, tmB, p, tiles_m, 1, st);
+  GEMM_CASE(32, false, false)
+  GEMM_CASE(64, false, false)
+  GEMM_CASE(128, false, false)
+  GEMM_CASE(64, false, true)
+  GEMM_CASE(128, false, true)
+  GEMM_CASE(64, true, true)
+  GEMM_CASE(128, true, true)
+#undef GEMM_CASE
+  return -3;
+}
+
+namespace {
+
+struct ConvGeom {
+  int nd;                 // spatial dims 1..3
+  int N, D, H, W, Cin, Cout;
+  int kd, kh, kw, sd, sh, sw, dd, dh, dw;
+  int pdl, pdu, phl, phu, pwl, pwu;
+  int Z, P, Q;
+};
+
+int conv_geom(ConvGeom& g, const int* v) {
+  // v: nd, N, D, H, W, Cin, Cout, kd, kh, kw, sd, sh, sw, pdl, pdu, phl, phu, pwl, pwu, dd, dh, dw
+  g.nd = v[0]; g.N = v[1]; g.D = v[2]; g.H = v[3]; g.W = v[4]; g.Cin = v[5]; g.Cout = v[6];
+  g.kd = v[7]; g.kh = v[8]; g.kw = v[9]; g.sd = v[10]; g.sh = v[11]; g.sw = v[12];
+  g.pdl = v[13]; g.pdu = v[14]; g.phl = v[15]; g.phu = v[16]; g.pwl = v[17]; g.pwu = v[18];
+  g.dd = v[19]; g.dh = v[20]; g.dw = v[21];
+  if (g.nd < 1 || g.nd > 3) return -1;
+  if (g.nd < 3) { if (g.D != 1 || g.kd != 1) return -1; g.sd = 1; g.dd = 1; g.pdl = g.pdu = 0; }
+  if (g.nd < 2) { if (g.H != 1 || g.kh != 1) return -1; g.sh = 1; g.dh = 1; g.phl = g.phu = 0; }
+  if (g.Cin % 64 != 0 || g.Cout % 8 != 0) return -4;
+  g.Q = (g.W + g.pwl + g.pwu - g.dw * (g.kw - 1) - 1) / g.sw + 1;
+  g.P = (g.H + g.phl + g.phu - g.dh * (g.kh - 1) - 1) / g.sh + 1;
+  g.Z = (g.D + g.pdl + g.pdu - g.dd * (g.kd - 1) - 1) / g.sd + 1;
+  if (g.Q <= 0 || g.P <= 0 || g.Z <= 0) return -5;
+  return 0;
+}
+
+int conv_tmap(CUtensorMap* tm, const void* x, const ConvGeom& g, uint32_t pixels_per_column) {
+  const int rank = g.nd + 2;
+  uint64_t dims[5];
+  int lower[3], upper[3], cs[3];
+  dims[0] = (uint64_t)g.Cin;
+  dims[1] = (uint64_t)g.W; lower[0] = -g.pwl; upper[0] = g.pwu - (g.kw - 1) * g.dw; cs[0] = g.sw;
+  int i = 2;
+  if (g.nd >= 2) { dims[i] = (uint64_t)g.H; lower[1] = -g.phl; upper[1] = g.phu - (g.kh - 1) * g.dh; cs[1] = g.sh; ++i; }
+  if (g.nd >= 3) { dims[i] = (uint64_t)g.D; lower[2] = -g.pdl; upper[2] = g.pdu - (g.kd - 1) * g.dd; cs[2] = g.sd; ++i; }
+  dims[i] = (uint64_t)g.N;
+  return make_tmap_im2col_bf16(tm, x, rank, dims, lower, upper, cs, 64, pixels_per_column);
+}
+
+void conv_fill_params(UmmaParams& p, const ConvGeom& g) {
+  p.rank = g.nd + 2;
+  p.Q = g.Q; p.P = g.P; p.Z = g.Z;
+  p.sw = g.sw; p.sh = g.sh; p.sd = g.sd;
+  p.pw = g.pwl; p.ph = g.phl; p.pd = g.pdl;
+  p.dw = g.dw; p.dh = g.dh; p.dd = g.dd;
+  p.S = g.kw; p.R = g.kh; p.T = g.kd;
+  p.Cin = g.Cin;
+  p.cblocks = g.Cin / 64;
+}
+
+}  // namespace
+
+extern "C" int m3t_conv_fprop_bf16(const void* x, const void* w_packed, void* y, const int* geom, const float* scale,
+                                   const float* shift, const void* residual, int relu, float* stats, int tile_hint,
+                                   void* stream) {
+  ConvGeom g;
+  int rc = conv_geom(g, geom);
+  if (rc) return rc;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const long long Mpix = (long long)g.N * g.Z * g.P * g.Q;
+  const int taps = g.kd * g.kh * g.kw;
+  UmmaParams p;
+  memset(&p, 0, sizeof(p));
+  conv_fill_params(p, g);
+  p.M = (int)Mpix; p.N = g.Cout;
+  p.k_iters = taps * p.cblocks;
+  p.out = y; p.ldc = g.Cout; p.out_f32 = 0;
+  p.scale = scale; p.shift = shift;
+  p.residual = reinterpret_cast<const __nv_bfloat16*>(residual); p.ldr = g.Cout;
+  p.relu = relu; p.stats = stats;
+  // tile selection: BN = 64 / 128 / 256 ; MT = 2 when there is enough M to still fill the machine
+  int bn = g.Cout <= 64 ? 64 : (g.Cout % 256 == 0 && (tile_hint & 4) ? 256 : 128);
+  int mt = 1;
+  if (tile_hint & 2) mt = 2;
+  else if (!(tile_hint & 1)) {
+    const long long ctas_mt2 = (Mpix / 256) * ((g.Cout + bn - 1) / bn);
+    if (ctas_mt2 >= 2 * 148 * 2) mt = 2;
+  }
+  if (bn == 256) mt = 1;
+  p.tiles_n = ceil_div(g.Cout, bn);
+  const int tiles_m = ceil_div(Mpix, 128 * mt);
+  CUtensorMap tmA, tmB;
+  rc = conv_tmap(&tmA, x, g, 128);
+  if (rc) return rc;
+  rc = make_tmap_2d_bf16(&tmB, w_packed, (uint64_t)taps * g.Cin, (uint64_t)g.Cout, (uint64_t)taps * g.Cin, 64,
+                         (uint32_t)bn);
+  if (rc) return rc;
+  if (bn == 64 && mt == 1) return launch_umma<64, 1, 4, A_IM2COL, false, false, EPI_STORE>(tmA, tmB, p, tiles_m, 1, st);
+  if (bn == 64 && mt == 2) return launch_umma<64, 2, 2, A_IM2COL, false, false, EPI_STORE>(tmA, tmB, p, tiles_m, 1, st);
+  if (bn == 128 && mt == 1) return launch_umma<128, 1, 3, A_IM2COL, false, false, EPI_STORE>(tmA, tmB, p, tiles_m, 1, st);
+  if (bn == 128 && mt == 2) return launch_umma<128, 2, 2, A_IM2COL, false, false, EPI_STORE>(tmA, tmB, p, tiles_m, 1, st);
+  if (bn == 256) return launch_umma<256, 1, 2, A_IM2COL, false, false, EPI_STORE>(tmA, tmB, p, tiles_m, 1, st);
+  return -3;
+}
+
+extern "C" int m3t_conv_wgrad_bf16(const void* x, const void* dy, float* dw_packed, const int* geom, int splits_hint,
+                                   void* stream) {
+  ConvGeom g;
+  int rc = conv_geom(g, geom);
+  if (rc) return rc;
+  if (g.Cout % 64 != 0) return -4;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const long long Mpix = (long long)g.N * g.Z * g.P * g.Q;
+  const int taps = g.kd * g.kh * g.kw;
+  UmmaParams p;
+  memset(&p, 0, sizeof(p));
+  conv_fill_params(p, g);
+  p.atoms = taps * p.cblocks;
+  p.M = taps * g.Cin;  // rows of D = (tap, ci)
+  p.N = g.Cout;
+  const int bn = g.Cout <= 64 ? 64 : 128;
+  p.tiles_n = ceil_div(g.Cout, bn);
+  const int tiles_m = ceil_div(p.atoms, 2);
+  const int kblocks = ceil_div(Mpix, kBlockK);
+  int splits = splits_hint;
+  if (splits <= 0) {
+    const int tiles = tiles_m * p.tiles_n;
+    splits = ceil_div(148 * 4, tiles);
+    const int max_splits = kblocks / 4 > 0 ? kblocks / 4 : 1;
+    if (splits > max_splits) splits = max_splits;
+    if (splits < 1) splits = 1;
+  }
+  p.k_iters = ceil_div(kblocks, splits);
+  splits = ceil_div(kblocks, p.k_iters);
+  p.out = dw_packed; p.ldc = (long long)taps * g.Cin; p.out_f32 = 1;
+  CUtensorMap tmA, tmB;
+  rc = conv_tmap(&tmA, x, g, 64);
+  if (rc) return rc;
+  rc = make_tmap_2d_bf16(&tmB, dy, (uint64_t)g.Cout, (uint64_t)Mpix, (uint64_t)g.Cout, 64, 64);
+  if (rc) return rc;
+  if (bn == 64) return launch_umma<64, 1, 4, A_WGRAD, false, true, EPI_ATOMIC_T>(tmA, tmB, p, tiles_m, splits, st);
+  return launch_umma<128, 1, 3, A_WGRAD, false, true, EPI_ATOMIC_T>(tmA, tmB, p, tiles_m, splits, st);
+}
