@@ -1,0 +1,47 @@
+"""Helpers shared by the golden-fixture tests."""
+import argparse
+import os
+
+import torch
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def load(name):
+    return torch.load(os.path.join(GOLDEN_DIR, name + ".pt"), weights_only=False)
+
+
+def rel_err(y, ref):
+    """Range-normalised max error."""
+    y = y.detach().float().cpu()
+    ref = ref.detach().float().cpu()
+    return float((y - ref).abs().max() / ref.abs().max().clamp_min(1e-12))
+
+
+def grad_err(g, packed):
+    """Compare a gradient tensor with a packed golden gradient (full tensor or strided sample + norm)."""
+    g = g.detach().float().cpu().contiguous().view(-1)
+    if "full" in packed:
+        ref = packed["full"]
+        got = g
+    else:
+        ref = packed["sample"]
+        got = g[::packed["stride"]][: ref.numel()]
+    scale = max(float(ref.abs().max()), 1e-12)
+    e = float((got - ref).abs().max()) / scale
+    n = abs(float(g.norm()) - packed["norm"]) / max(packed["norm"], 1e-12)
+    return max(e, n)
+
+
+def hparams_ns(d):
+    return argparse.Namespace(**d)
+
+
+def ref_batch(inputs, device="cpu"):
+    b = {}
+    for k, v in inputs.items():
+        if k == "video_u8":
+            b["video"] = v.float().to(device)
+        else:
+            b[k] = v.to(device)
+    return b

@@ -1,0 +1,136 @@
+"""CPU: pin oracle/ref_torch.py against the golden vectors produced by the unmodified reference modules
+(oracle/make_golden.py).  fp32 vs fp32 on the same ATen kernels: tolerance 2e-5 range-normalised on outputs,
+5e-4 on gradients (summation order differs between the explicit GRU loop and nn.GRU)."""
+import pytest
+import torch
+
+from oracle import ref_torch as R
+from oracle.ref_torch import synth_state_dict
+from tests.golden_util import grad_err, hparams_ns, load, ref_batch, rel_err
+
+TOL_OUT = 2e-5
+TOL_GRAD = 5e-4
+
+
+def _sd(fx, requires_grad=False):
+    sd = synth_state_dict(fx["spec"], fx["seed"])
+    if requires_grad:
+        for k, v in sd.items():
+            if v.is_floating_point() and not k.endswith(("running_mean", "running_var")):
+                v.requires_grad_(True)
+    return sd
+
+
+def _check_grads(fx, sd, out, inputs):
+    (out * fx["cot"]).sum().backward()
+    worst = 0.0
+    for k, packed in fx["grads"].items():
+        kind, name = k.split(".", 1)
+        t = sd[name] if kind == "param" else inputs[name]
+        assert t.grad is not None, k
+        worst = max(worst, grad_err(t.grad, packed))
+    assert worst < TOL_GRAD, worst
+
+
+@pytest.mark.parametrize("name", ["gru_audio", "gru_scorer", "gru_nohead"])
+def test_gru(name):
+    fx = load(name)
+    sd = _sd(fx, True)
+    x = fx["inputs"]["x"].clone().requires_grad_(True)
+    out = R.gru_module(x, {"m." + k: v for k, v in sd.items()}, "m")
+    assert rel_err(out, fx["out"]) < TOL_OUT
+    _check_grads(fx, sd, out, {"x": x})
+
+
+def test_attfusion():
+    fx = load("attfusion")
+    sd = _sd(fx, True)
+    xa = fx["inputs"]["x_a"].clone().requires_grad_(True)
+    xv = fx["inputs"]["x_v"].clone().requires_grad_(True)
+    out = R.att_fusion(xa, xv, {"att_fuse." + k: v for k, v in sd.items()})
+    assert rel_err(out, fx["out"]) < TOL_OUT
+    _check_grads(fx, sd, out, {"x_a": xa, "x_v": xv})
+
+
+def test_tcn():
+    fx = load("tcn")
+    sd = _sd(fx, True)
+    x = fx["inputs"]["x"].clone().requires_grad_(True)
+    out = R.temporal_conv_net(x, sd, "", 2)
+    assert rel_err(out, fx["out"]) < TOL_OUT
+    _check_grads(fx, sd, out, {"x": x})
+
+
+@pytest.mark.parametrize("mode", ["eval", "train"])
+def test_resnet_trunk(mode):
+    fx = load("resnet_trunk_" + mode)
+    sd = _sd(fx, True)
+    x = fx["inputs"]["x"].clone().requires_grad_(True)
+    out = R.resnet_trunk(x, {"resnet." + k: v for k, v in sd.items()}, train=(mode == "train"))
+    assert rel_err(out, fx["out"]) < TOL_OUT
+    _check_grads(fx, sd, out, {"x": x})
+
+
+def test_va3dresnet_eval():
+    fx = load("va3dresnet_eval")
+    sd = _sd(fx)
+    x = (fx["inputs"]["video_u8"].float() - 127.5) / 127.5
+    with torch.no_grad():
+        out = R.va_3dresnet(x, sd, fx["ctor"]["frameLen"])
+    assert rel_err(out, fx["out"]) < TOL_OUT
+
+
+def test_va3dresnet_train_grads():
+    """Train-mode BN over 8 frames makes early-layer gradients ill-conditioned in fp32: the fp32 reference itself
+    is 4e-3 away from the fp64 reference, while this oracle run in fp64 matches the fp64 reference to 3e-14
+    (measured on the build box).  So the oracle is evaluated in fp64 here and compared with the golden (fp32
+    reference) gradients at the fp32 noise floor."""
+    fx = load("va3dresnet_train")
+    sd = {k: (v.double().requires_grad_(True) if v.is_floating_point() else v) for k, v in _sd(fx).items()}
+    x = (fx["inputs"]["video_u8"].double() - 127.5) / 127.5
+    out = R.va_3dresnet(x, sd, fx["ctor"]["frameLen"], train=True)
+    assert rel_err(out, fx["out"]) < TOL_OUT
+    (out * fx["cot"].double()).sum().backward()
+    worst = max(grad_err(sd[k.split(".", 1)[1]].grad, p) for k, p in fx["grads"].items())
+    assert worst < 1e-2, worst
+
+
+def test_vggm_split_eval():
+    fx = load("vggm_split3_eval")
+    sd = _sd(fx)
+    x = (fx["inputs"]["video_u8"].float() - 127.5) / 127.5
+    se = fx["inputs"]["se_features"]
+    with torch.no_grad():
+        out = R.va_3dvggm_split(x, se, se, sd, "", fx["ctor"]["split_layer"], fx["ctor"]["backend"])
+    assert rel_err(out, fx["out"]) < TOL_OUT
+
+
+@pytest.mark.parametrize("name", ["av_resnet_attention_eval", "av_v2psplit_attention_eval"])
+def test_affwild2va_eval(name):
+    fx = load(name)
+    sd = _sd(fx)
+    with torch.no_grad():
+        out = R.affwild2va_forward(ref_batch(fx["inputs"]), sd, hparams_ns(fx["hparams"]))
+    assert rel_err(out, fx["out"]) < TOL_OUT
+
+
+def test_affwild2va_training_step():
+    fx = load("av_resnet_attention_train")
+    sd = {k: (v.double().requires_grad_(True) if v.is_floating_point() else v) for k, v in _sd(fx).items()}
+    b = {k: (v.double() if v.is_floating_point() else v) for k, v in ref_batch(fx["inputs"]).items()}
+    hp = hparams_ns(fx["hparams"])
+    y = R.affwild2va_forward(b, sd, hp, train=True)
+    loss = R.training_loss(y, b, hp.loss, hp.loss_lambda)
+    assert abs(float(loss) - fx["loss"]) < 1e-4 * max(1.0, abs(fx["loss"]))
+    loss.backward()
+    worst = 0.0
+    for k, packed in fx["grads"].items():
+        name = k.split(".", 1)[1]
+        worst = max(worst, grad_err(sd[name].grad, packed))
+    assert worst < 2e-2, worst  # fp32-reference noise floor through 20 train-mode BN layers (see above)
+
+
+def test_ccc():
+    fx = load("ccc")
+    out = torch.stack([R.concordance_cc2(fx["inputs"]["r1"][i], fx["inputs"]["r2"][i]) for i in range(3)])
+    assert rel_err(out, fx["out"]) < 1e-6
