@@ -63,6 +63,100 @@ int m3t_conv_fprop_bf16(const void* x, const void* w_packed, void* y, const int*
 int m3t_conv_wgrad_bf16(const void* x, const void* dy, float* dw_packed, const int* geom, int splits_hint,
                         void* stream);
 
+
+/* ------------------------------------------------------------------------------------------------------------
+ * HBM-bound passes of the visual stream (elementwise.cu).  Algorithmic bytes per element are given per entry; all
+ * tensors are channels-last bf16 unless noted, C % 8 == 0.
+ * ---------------------------------------------------------------------------------------------------------- */
+
+/* Input pass of the stem: video (B,3,T,H,W) fp32 or uint8 -> out bf16 (B,T,H/2,W/2,16), 2x2 space-to-depth with
+ * channel (ph*2+pw)*3+c (12..15 zero) and value x*mul+add.  mul=1/127.5, add=-1 reproduces
+ * `(batch['video'] - 127.5) / 127.5` (models/model.py:106); the reference's transpose(1,2).contiguous()
+ * (models/backbone.py:349-350) disappears because the layout is already frame-major.  Bytes/pixel: 12|3 in, 8 out. */
+int m3t_video_prep_s2d(const void* video, int is_u8, void* out, int B, int T, int H, int W, float mul, float add,
+                       void* stream);
+
+/* Train-mode BatchNorm statistics -> per-channel scale/shift (+ running-stat update, momentum, unbiased variance).
+ * stats = [2][C] column (sum, sum of squares) produced by the conv epilogue.  Replaces the statistics half of
+ * nn.BatchNorm2d/3d in training (models/resnet.py:25,28; models/backbone.py:329). */
+int m3t_bn_finalize(const float* stats, int C, double count, const float* gamma, const float* beta, float eps,
+                    float momentum, float* running_mean, float* running_var, float* mean, float* invstd, float* scale,
+                    float* shift, void* stream);
+/* Eval-mode BatchNorm folded to scale/shift (optionally absorbing a conv bias). */
+int m3t_bn_fold(int C, const float* gamma, const float* beta, const float* running_mean, const float* running_var,
+                const float* conv_bias, float eps, float* scale, float* shift, void* stream);
+/* out = act(y*scale + shift + (res*res_scale + res_shift)) over [rows][C]: BN apply + residual add + ReLU of a
+ * BasicBlock in ONE pass (models/resnet.py:41-54: bn -> (+identity) -> relu).  Bytes/element: 2 (+2) in, 2 out. */
+int m3t_bn_act(const void* y, const float* scale, const float* shift, const void* res, const float* res_scale,
+               const float* res_shift, int relu, void* out, long long rows, int C, void* stream);
+/* Backward of m3t_bn_act with batch statistics, two passes: reduce (sum dz, sum dz*xhat; optionally materialises
+ * dz = dout*(out>0) for the residual branch) and apply (dy = scale*(dz - s0/n - xhat*s1/n)). */
+int m3t_bn_bwd_reduce(const void* dout, const void* out, const void* y, const float* mean, const float* invstd,
+                      int relu, void* dz_out, float* sums, long long rows, int C, void* stream);
+int m3t_bn_bwd_apply(const void* dout, const void* out, const void* y, const float* mean, const float* invstd,
+                     const float* scale, const float* sums, double count, int relu, void* dy, long long rows, int C,
+                     void* stream);
+/* Stem tail: out = maxpool3x3/s2/p1( relu(y*scale+shift) ) over (H,W) of [F][H][W][C]; idx (uint8, optional) is the
+ * arg-max tap.  Replaces BatchNorm3d apply + ReLU + MaxPool3d((1,3,3),(1,2,2),(0,1,1)) (models/backbone.py:329-331). */
+int m3t_bn_relu_maxpool(const void* y, const float* scale, const float* shift, void* out, void* idx, int F, int H,
+                        int W, int C, void* stream);
+/* Backward of the stem tail; mode 0 accumulates (sum dz, sum dz*xhat) into sums, mode 1 writes dy. */
+int m3t_maxpool_bn_bwd(int mode, const void* dout, const void* idx, const void* y, const float* mean,
+                       const float* invstd, const float* scale, const float* shift, float* sums, double count,
+                       void* dy, int F, int H, int W, int C, void* stream);
+/* AdaptiveAvgPool2d(1)+flatten (models/resnet.py:117-119) over [F][HW][C] and its backward. */
+int m3t_avgpool(const void* x, void* out_bf16, float* out_f32, int F, int HW, int C, void* stream);
+int m3t_avgpool_bwd(const void* dout, int dout_f32, void* dx, int F, int HW, int C, void* stream);
+/* Module-boundary layout changes: fp32 [N][C][S] <-> channels-last [N][S][Cpad] (bf16, or fp32 on the way back). */
+int m3t_ncs_f32_to_nsc_bf16(const float* in, void* out, int N, int C, int S, int Cpad, void* stream);
+int m3t_nsc_to_ncs_f32(const void* in, int in_f32, float* out, int N, int C, int S, int Cpad, void* stream);
+/* Row-wise dtype casts with leading dimensions (pad columns of the bf16 side are zero-filled). */
+int m3t_cast_f32_bf16(const float* in, long long ld_in, void* out, long long ld_out, long long rows, int cols,
+                      void* stream);
+int m3t_cast_bf16_f32(const void* in, long long ld_in, float* out, long long ld_out, long long rows, int cols,
+                      void* stream);
+/* Filter packing fp32 [Cout][Cin][taps] -> bf16 [Cout][taps][Cin] (fprop) and [Cin][taps reversed][Cout] (dgrad);
+ * and the inverse re-layout of a packed fp32 weight gradient. */
+int m3t_pack_filter(const float* w, void* w_fprop, void* w_dgrad, int Cout, int Cin, int taps, void* stream);
+int m3t_unpack_filter_grad(const float* dw_packed, float* dw, int Cout, int Cin, int taps, void* stream);
+/* Index-driven filter re-layout (space-to-depth stem): out[r][k] = idx[k] >= 0 ? w[r*row_stride+idx[k]] : 0, and
+ * the scatter of a packed gradient back. */
+int m3t_gather_pack_bf16(const float* w, const int* idx, void* out, int rows, long long row_stride, int K,
+                         void* stream);
+int m3t_scatter_unpack_f32(const float* dwp, const int* idx, float* dw, int rows, long long row_stride, int K,
+                           void* stream);
+/* Stride-2 dgrad helper: up[n][2p][2q][c] = dy[n][p][q][c], zeros elsewhere. */
+int m3t_zero_insert2(const void* dy, void* up, int N, int P, int Q, int Hup, int Wup, int C, void* stream);
+/* Small helpers: bf16 add (gradient fan-in), bias gradient (column sums), ReLU backward. */
+int m3t_add_bf16(const void* a, const void* b, void* out, long long n, void* stream);
+int m3t_colsum_bf16(const void* x, long long ld, long long rows, int cols, float* out, void* stream);
+int m3t_relu_bwd_bf16(const void* dy, const void* out, void* dz, long long n, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Bidirectional GRU layer recurrence (gru.cu), persistent kernel, both directions in one launch.
+ *   gi        fp32 [B*T][2][3H]  x . W_ih^T + b_ih (one m3t_gemm_bf16), gate order r,z,n
+ *   w_hh_bf16 bf16 [2][3H][H];  b_hh fp32 [2][3H]
+ *   out_bf16  bf16 [B][T][2H] (forward | reverse halves);  out_f32 optional fp32 copy
+ *   saved     fp32 [B*T][2][4][H] (r, z, n, W_hn h + b_hn) or NULL (inference)
+ *   counters  uint32 scratch, >= 2*ceil(B/32) entries (zeroed by the call)
+ * Replaces nn.GRU(batch_first=True, bidirectional=True) (models/rnn.py:17,72-75) = cuDNN RNN in the reference. */
+int m3t_gru_fwd(const float* gi, const void* w_hh_bf16, const float* b_hh, void* out_bf16, float* out_f32,
+                float* saved, unsigned* counters, int B, int T, int H, void* stream);
+/* BPTT: dgi, dgh bf16 [B*T][2][3H] (gradients wrt the input / hidden pre-activations) and hprev bf16 [B*T][2][H]
+ * (h_{t-1}, zero at the sequence start); w_hh_t_bf16 = bf16 [2][H][3H] (W_hh transposed).  The weight / bias /
+ * input gradients follow as GEMMs and column sums over these. */
+int m3t_gru_bwd(const void* dout_bf16, const void* out_bf16, const float* saved, const void* w_hh_t_bf16,
+                void* dgi_bf16, void* dgh_bf16, void* hprev_bf16, unsigned* counters, int B, int T, int H,
+                void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Attention-fusion mix (fusion.cu): f = softmax(sigmoid(s_v), sigmoid(s_a)) . (x_v, x_a) per (b,t) row of C
+ * channels, and its backward.  Replaces sigmoid/cat/softmax/mul/add (models/att_fusion.py:21-25, six ATen kernels). */
+int m3t_att_mix_fwd(const void* x_a, const void* x_v, const float* s_a, const float* s_v, void* f, float* w_v,
+                    long long rows, int C, void* stream);
+int m3t_att_mix_bwd(const void* df, const void* x_a, const void* x_v, const float* s_a, const float* s_v, void* dx_a,
+                    void* dx_v, float* ds_a, float* ds_v, long long rows, int C, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

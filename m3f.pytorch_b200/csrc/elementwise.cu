@@ -1,0 +1,842 @@
+// HBM-bound passes of the visual stream: input preparation, BatchNorm finalize/apply (+residual, +ReLU, +max-pool),
+// their backward passes, average pooling, layout/dtype conversion and filter packing.  All activations are
+// channels-last bf16; every thread moves 16-byte vectors (8 channels); grids are sized in multiples of the SM count.
+#include "../../include/m3t_b200.h"
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace m3t {
+
+constexpr int kEwThreads = 256;
+static inline int ew_blocks(long long work_items) {
+  long long b = (work_items + kEwThreads - 1) / kEwThreads;
+  const long long cap = 148LL * 16;  // persistent-ish: at most 16 CTAs per SM, grid-stride beyond that
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+struct bf16x8 {
+  uint4 v;
+};
+__device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    f[2 * j] = bf16lo(w[j]);
+    f[2 * j + 1] = bf16hi(w[j]);
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  return make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
+                    pack_bf16x2(f[6], f[7]));
+}
+__device__ __forceinline__ void load8f(const float* p, float (&f)[8]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+  const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// video -> normalised, space-to-depth(2x2), channel-padded bf16:  out[b][t][h2][w2][(ph*2+pw)*3 + c], 12..15 = 0
+// ------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void video_prep_s2d_kernel(const T* __restrict__ in, __nv_bfloat16* __restrict__ out, int B, int Tn, int H,
+                                      int W, float mul, float add) {
+  const int H2 = H / 2, W2 = W / 2;
+  const long long total = (long long)B * Tn * H2 * W2;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int w2 = (int)(i % W2);
+    long long r = i / W2;
+    const int h2 = (int)(r % H2);
+    r /= H2;
+    const int t = (int)(r % Tn);
+    const int b = (int)(r / Tn);
+    float f[16];
+#pragma unroll
+    for (int j = 12; j < 16; ++j) f[j] = 0.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+#pragma unroll
+      for (int ph = 0; ph < 2; ++ph) {
+        const T* p = in + ((((long long)b * 3 + c) * Tn + t) * H + (2 * h2 + ph)) * W + 2 * w2;
+        float x0, x1;
+        if constexpr (sizeof(T) == 4) {
+          const float2 v = __ldg(reinterpret_cast<const float2*>(p));
+          x0 = v.x; x1 = v.y;
+        } else {
+          const uchar2 v = *reinterpret_cast<const uchar2*>(p);
+          x0 = (float)v.x; x1 = (float)v.y;
+        }
+        f[(ph * 2 + 0) * 3 + c] = fmaf(x0, mul, add);
+        f[(ph * 2 + 1) * 3 + c] = fmaf(x1, mul, add);
+      }
+    }
+    float lo[8], hi[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { lo[j] = f[j]; hi[j] = f[8 + j]; }
+    uint4* o = reinterpret_cast<uint4*>(out + i * 16);
+    o[0] = pack8(lo);
+    o[1] = pack8(hi);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// BatchNorm finalize: (sum, sumsq) -> mean, invstd, scale = gamma*invstd, shift = beta - mean*scale; running stats
+// ------------------------------------------------------------------------------------------------------------
+__global__ void bn_finalize_kernel(const float* __restrict__ stats, int C, float count, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float eps, float momentum,
+                                   float* __restrict__ running_mean, float* __restrict__ running_var,
+                                   float* __restrict__ mean_out, float* __restrict__ invstd_out,
+                                   float* __restrict__ scale_out, float* __restrict__ shift_out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float mean = stats[c] / count;
+  float var = stats[C + c] / count - mean * mean;
+  var = fmaxf(var, 0.f);
+  const float invstd = rsqrtf(var + eps);
+  const float sc = gamma[c] * invstd;
+  mean_out[c] = mean;
+  invstd_out[c] = invstd;
+  scale_out[c] = sc;
+  shift_out[c] = beta[c] - mean * sc;
+  if (running_mean) {
+    const float unbiased = count > 1.f ? var * (count / (count - 1.f)) : var;
+    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * unbiased;
+  }
+}
+
+// eval-mode fold: scale = gamma / sqrt(running_var + eps), shift = beta - running_mean * scale (+ conv bias * scale)
+__global__ void bn_fold_kernel(int C, const float* __restrict__ gamma, const float* __restrict__ beta,
+                               const float* __restrict__ running_mean, const float* __restrict__ running_var,
+                               const float* __restrict__ conv_bias, float eps, float* __restrict__ scale_out,
+                               float* __restrict__ shift_out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float sc = gamma[c] * rsqrtf(running_var[c] + eps);
+  const float b = conv_bias ? conv_bias[c] : 0.f;
+  scale_out[c] = sc;
+  shift_out[c] = beta[c] + (b - running_mean[c]) * sc;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// out = act( y*scale + shift + (res*res_scale + res_shift) )      [rows][C] bf16, C % 8 == 0
+// ------------------------------------------------------------------------------------------------------------
+__global__ void bn_act_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ scale,
+                              const float* __restrict__ shift, const __nv_bfloat16* __restrict__ res,
+                              const float* __restrict__ res_scale, const float* __restrict__ res_shift, int relu,
+                              __nv_bfloat16* __restrict__ out, long long nvec, int C) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)((i * 8) % C);
+    float v[8], s[8], b[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(y) + i), v);
+    load8f(scale + c, s);
+    load8f(shift + c, b);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], s[j], b[j]);
+    if (res) {
+      float r[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(res) + i), r);
+      if (res_scale) {
+        load8f(res_scale + c, s);
+        load8f(res_shift + c, b);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] = fmaf(r[j], s[j], b[j]);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] += r[j];
+    }
+    if (relu) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+    }
+    reinterpret_cast<uint4*>(out)[i] = pack8(v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Backward of  out = act(y*scale + shift + resid)  with train-mode BN (batch statistics).
+//   dz = dout * (out > 0)                                  (relu)   |  dz = dout   (no relu)
+//   pass 1: sums[0][c] += dz, sums[1][c] += dz * xhat,  xhat = (y - mean) * invstd ; optionally writes dz (bf16)
+//   pass 2: dy = scale * (dz - sums0/n - xhat * sums1/n)
+// `dz_in` (pass 1 input override): when the same dz feeds a second BN (downsample branch) it is read, not recomputed.
+// ------------------------------------------------------------------------------------------------------------
+__global__ void bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ out,
+                                     const __nv_bfloat16* __restrict__ y, const float* __restrict__ mean,
+                                     const float* __restrict__ invstd, int relu, __nv_bfloat16* __restrict__ dz_out,
+                                     float* __restrict__ sums, long long rows, int C) {
+  // block handles a strip of rows for all channels: thread -> (channel group cg = tid % (C/8), row lane)
+  extern __shared__ float sh[];  // [2][C]
+  const int cgs = C / 8;
+  const int rows_per_iter = blockDim.x / cgs;
+  const int cg = threadIdx.x % cgs;
+  const int rl = threadIdx.x / cgs;
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sh[i] = 0.f;
+  __syncthreads();
+  float a0[8], a1[8], mu[8], is[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) a0[j] = a1[j] = 0.f;
+  load8f(mean + cg * 8, mu);
+  load8f(invstd + cg * 8, is);
+  if (rl < rows_per_iter) {
+    for (long long r = (long long)blockIdx.x * rows_per_iter + rl; r < rows; r += (long long)gridDim.x * rows_per_iter) {
+      const long long i = r * cgs + cg;
+      float d[8], yy[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(dout) + i), d);
+      unpack8(__ldg(reinterpret_cast<const uint4*>(y) + i), yy);
+      if (relu) {
+        float o[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(out) + i), o);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) d[j] = o[j] > 0.f ? d[j] : 0.f;
+      }
+      if (dz_out) reinterpret_cast<uint4*>(dz_out)[i] = pack8(d);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        a0[j] += d[j];
+        a1[j] += d[j] * (yy[j] - mu[j]) * is[j];
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      atomicAdd(&sh[cg * 8 + j], a0[j]);
+      atomicAdd(&sh[C + cg * 8 + j], a1[j]);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(sums + i, sh[i]);
+}
+
+__global__ void bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ out,
+                                    const __nv_bfloat16* __restrict__ y, const float* __restrict__ mean,
+                                    const float* __restrict__ invstd, const float* __restrict__ scale,
+                                    const float* __restrict__ sums, float inv_count, int relu,
+                                    __nv_bfloat16* __restrict__ dy, long long nvec, int C) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)((i * 8) % C);
+    float d[8], yy[8], mu[8], is[8], sc[8], s0[8], s1[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(dout) + i), d);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(y) + i), yy);
+    if (relu) {
+      float o[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(out) + i), o);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) d[j] = o[j] > 0.f ? d[j] : 0.f;
+    }
+    load8f(mean + c, mu);
+    load8f(invstd + c, is);
+    load8f(scale + c, sc);
+    load8f(sums + c, s0);
+    load8f(sums + C + c, s1);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float xh = (yy[j] - mu[j]) * is[j];
+      d[j] = sc[j] * (d[j] - s0[j] * inv_count - xh * s1[j] * inv_count);
+    }
+    reinterpret_cast<uint4*>(dy)[i] = pack8(d);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Stem tail: out = maxpool_{3x3,s2,p1}( relu(y*scale + shift) ) over (H,W) of [F][H][W][C]; idx = argmax (0..8)
+// ------------------------------------------------------------------------------------------------------------
+__global__ void bn_relu_maxpool_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ scale,
+                                       const float* __restrict__ shift, __nv_bfloat16* __restrict__ out,
+                                       uint8_t* __restrict__ idx, int F, int H, int W, int C) {
+  const int P = (H + 2 - 3) / 2 + 1, Q = (W + 2 - 3) / 2 + 1;
+  const int cgs = C / 8;
+  const long long total = (long long)F * P * Q * cgs;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % cgs);
+    long long r = i / cgs;
+    const int q = (int)(r % Q);
+    r /= Q;
+    const int p = (int)(r % P);
+    const int f = (int)(r / P);
+    float s[8], b[8], best[8];
+    int bi[8];
+    load8f(scale + cg * 8, s);
+    load8f(shift + cg * 8, b);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { best[j] = -INFINITY; bi[j] = 0; }
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+      const int h = 2 * p - 1 + kh;
+      if (h < 0 || h >= H) continue;
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const int w = 2 * q - 1 + kw;
+        if (w < 0 || w >= W) continue;
+        float v[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(y + (((long long)f * H + h) * W + w) * C) + cg), v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float a = fmaxf(fmaf(v[j], s[j], b[j]), 0.f);
+          if (a > best[j]) { best[j] = a; bi[j] = kh * 3 + kw; }
+        }
+      }
+    }
+    reinterpret_cast<uint4*>(out)[i] = pack8(best);
+    if (idx) {
+      uint2 pk;
+      pk.x = bi[0] | (bi[1] << 8) | (bi[2] << 16) | (bi[3] << 24);
+      pk.y = bi[4] | (bi[5] << 8) | (bi[6] << 16) | (bi[7] << 24);
+      reinterpret_cast<uint2*>(idx)[i] = pk;
+    }
+  }
+}
+
+// Backward of the stem tail.  dz[f][h][w][c] = relu'(a) * sum_{windows (p,q) containing (h,w) with argmax == (h,w)}
+// dout[f][p][q][c];  MODE 0: accumulate (sum dz, sum dz*xhat) ;  MODE 1: write dy = scale*(dz - s0/n - xhat*s1/n).
+template <int MODE>
+__global__ void maxpool_bn_bwd_kernel(const __nv_bfloat16* __restrict__ dout, const uint8_t* __restrict__ idx,
+                                      const __nv_bfloat16* __restrict__ y, const float* __restrict__ mean,
+                                      const float* __restrict__ invstd, const float* __restrict__ scale,
+                                      const float* __restrict__ shift, float* __restrict__ sums, float inv_count,
+                                      __nv_bfloat16* __restrict__ dy, int F, int H, int W, int C) {
+  const int P = (H + 2 - 3) / 2 + 1, Q = (W + 2 - 3) / 2 + 1;
+  const int cgs = C / 8;
+  extern __shared__ float sh[];  // MODE 0: [2][C]
+  if (MODE == 0) {
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sh[i] = 0.f;
+    __syncthreads();
+  }
+  const int cg = threadIdx.x % cgs;        // blockDim.x % cgs == 0 -> a thread keeps its channel group
+  float s[8], b[8], mu[8], is[8], s0[8], s1[8], a0[8], a1[8];
+  load8f(scale + cg * 8, s);
+  load8f(shift + cg * 8, b);
+  load8f(mean + cg * 8, mu);
+  load8f(invstd + cg * 8, is);
+  if (MODE == 1) {
+    load8f(sums + cg * 8, s0);
+    load8f(sums + C + cg * 8, s1);
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) a0[j] = a1[j] = 0.f;
+  const long long total = (long long)F * H * W * cgs;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    long long r = i / cgs;
+    const int w = (int)(r % W);
+    r /= W;
+    const int h = (int)(r % H);
+    const int f = (int)(r / H);
+    float yy[8], dz[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(y) + i), yy);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dz[j] = 0.f;
+    // windows p with 2p-1 <= h <= 2p+1  ->  p in [ceil((h-1)/2), floor((h+1)/2)]
+    const int p_lo = h >> 1, p_hi = (h + 1) >> 1;   // (h-1+1)/2 .. (h+1)/2 ; p_lo == ceil((h-1)/2)
+    const int q_lo = w >> 1, q_hi = (w + 1) >> 1;
+    for (int p = p_lo; p <= p_hi; ++p) {
+      if (p >= P) continue;
+      const int kh = h - (2 * p - 1);
+      for (int q = q_lo; q <= q_hi; ++q) {
+        if (q >= Q) continue;
+        const int kw = w - (2 * q - 1);
+        const int me = kh * 3 + kw;
+        const long long o = (((long long)f * P + p) * Q + q) * cgs + cg;
+        const uint2 pk = __ldg(reinterpret_cast<const uint2*>(idx) + o);
+        float d[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(dout) + o), d);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int sel = ((j < 4 ? pk.x : pk.y) >> (8 * (j & 3))) & 0xFF;
+          if (sel == me) dz[j] += d[j];
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float act = fmaf(yy[j], s[j], b[j]);
+      if (!(act > 0.f)) dz[j] = 0.f;
+    }
+    if (MODE == 0) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        a0[j] += dz[j];
+        a1[j] += dz[j] * (yy[j] - mu[j]) * is[j];
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float xh = (yy[j] - mu[j]) * is[j];
+        dz[j] = s[j] * (dz[j] - s0[j] * inv_count - xh * s1[j] * inv_count);
+      }
+      reinterpret_cast<uint4*>(dy)[i] = pack8(dz);
+    }
+  }
+  if (MODE == 0) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      atomicAdd(&sh[cg * 8 + j], a0[j]);
+      atomicAdd(&sh[C + cg * 8 + j], a1[j]);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(sums + i, sh[i]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Global average pool over HW of [F][HW][C] bf16 -> [F][C] (bf16 and/or fp32); and its backward.
+// ------------------------------------------------------------------------------------------------------------
+__global__ void avgpool_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out_bf16,
+                               float* __restrict__ out_f32, int F, int HW, int C) {
+  const int cgs = C / 8;
+  const long long total = (long long)F * cgs;
+  const float inv = 1.f / HW;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % cgs);
+    const long long f = i / cgs;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int s = 0; s < HW; ++s) {
+      float v[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(x + (f * HW + s) * C) + cg), v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += v[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] *= inv;
+    if (out_bf16) reinterpret_cast<uint4*>(out_bf16)[i] = pack8(acc);
+    if (out_f32) {
+      float4* o = reinterpret_cast<float4*>(out_f32 + i * 8);
+      o[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      o[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    }
+  }
+}
+// dx[f][s][c] = dout[f][c] / HW   (dout fp32 or bf16 -> dx bf16)
+template <typename T>
+__global__ void avgpool_bwd_kernel(const T* __restrict__ dout, __nv_bfloat16* __restrict__ dx, int F, int HW, int C) {
+  const int cgs = C / 8;
+  const long long total = (long long)F * HW * cgs;
+  const float inv = 1.f / HW;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % cgs);
+    const long long f = i / cgs / HW;
+    float v[8];
+    if constexpr (sizeof(T) == 4) load8f(reinterpret_cast<const float*>(dout) + f * C + cg * 8, v);
+    else unpack8(__ldg(reinterpret_cast<const uint4*>(dout + f * C) + cg), v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] *= inv;
+    reinterpret_cast<uint4*>(dx)[i] = pack8(v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Layout / dtype conversion.  [N][C][S] fp32  <->  [N][S][C] bf16 through a 32x32 smem transpose tile.
+// ------------------------------------------------------------------------------------------------------------
+__global__ void ncs_f32_to_nsc_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int C, int S,
+                                           int Cpad) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const int c0 = blockIdx.y * 32, s0 = blockIdx.x * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int c = c0 + j, s = s0 + threadIdx.x;
+    tile[j][threadIdx.x] = (c < C && s < S) ? in[((long long)n * C + c) * S + s] : 0.f;
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int s = s0 + j, c = c0 + threadIdx.x;
+    if (s < S && c < Cpad) out[((long long)n * S + s) * Cpad + c] = __float2bfloat16(tile[threadIdx.x][j]);
+  }
+}
+template <typename TIN>
+__global__ void nsc_to_ncs_f32_kernel(const TIN* __restrict__ in, float* __restrict__ out, int C, int S, int Cpad) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const int c0 = blockIdx.y * 32, s0 = blockIdx.x * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int s = s0 + j, c = c0 + threadIdx.x;
+    float v = 0.f;
+    if (s < S && c < C) {
+      if constexpr (sizeof(TIN) == 4) v = in[((long long)n * S + s) * Cpad + c];
+      else v = __bfloat162float(in[((long long)n * S + s) * Cpad + c]);
+    }
+    tile[j][threadIdx.x] = v;
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int c = c0 + j, s = s0 + threadIdx.x;
+    if (c < C && s < S) out[((long long)n * C + c) * S + s] = tile[threadIdx.x][j];
+  }
+}
+
+// rows x cols fp32 (row stride ld_in) -> bf16 (row stride ld_out >= cols, pad columns zero-filled)
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ in, long long ld_in, __nv_bfloat16* __restrict__ out,
+                                     long long ld_out, long long rows, int cols) {
+  const long long total = rows * ld_out;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / ld_out;
+    const int c = (int)(i - r * ld_out);
+    out[i] = __float2bfloat16(c < cols ? in[r * ld_in + c] : 0.f);
+  }
+}
+__global__ void cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ in, long long ld_in, float* __restrict__ out,
+                                     long long ld_out, long long rows, int cols) {
+  const long long total = rows * cols;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / cols;
+    const int c = (int)(i - r * cols);
+    out[r * ld_out + c] = __bfloat162float(in[r * ld_in + c]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Filter packing:  w fp32 [Cout][Cin][taps]  ->  fprop pack bf16 [Cout][taps][Cin]
+//                                              dgrad pack bf16 [Cin][taps (flipped)][Cout]     (stride-1 dgrad)
+// and the inverse for gradients: dw_packed fp32 [Cout][taps][Cin] -> dw fp32 [Cout][Cin][taps].
+// ------------------------------------------------------------------------------------------------------------
+__global__ void pack_filter_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wf,
+                                   __nv_bfloat16* __restrict__ wd, int Cout, int Cin, int taps) {
+  const long long total = (long long)Cout * Cin * taps;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int t = (int)(i % taps);
+    long long r = i / taps;
+    const int ci = (int)(r % Cin);
+    const int co = (int)(r / Cin);
+    const __nv_bfloat16 v = __float2bfloat16(w[i]);
+    if (wf) wf[((long long)co * taps + t) * Cin + ci] = v;
+    if (wd) wd[((long long)ci * taps + (taps - 1 - t)) * Cout + co] = v;
+  }
+}
+__global__ void unpack_filter_grad_kernel(const float* __restrict__ dwp, float* __restrict__ dw, int Cout, int Cin,
+                                          int taps) {
+  const long long total = (long long)Cout * Cin * taps;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int t = (int)(i % taps);
+    long long r = i / taps;
+    const int ci = (int)(r % Cin);
+    const int co = (int)(r / Cin);
+    dw[i] = dwp[((long long)co * taps + t) * Cin + ci];
+  }
+}
+
+// Stride-2 dgrad helper: dy_up[n][2p][2q][c] = dy[n][p][q][c], zero elsewhere (Hup x Wup spatial extent).
+__global__ void zero_insert2_kernel(const __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__ up, int N, int P,
+                                    int Q, int Hup, int Wup, int C) {
+  const int cgs = C / 8;
+  const long long total = (long long)N * Hup * Wup * cgs;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % cgs);
+    long long r = i / cgs;
+    const int w = (int)(r % Wup);
+    r /= Wup;
+    const int h = (int)(r % Hup);
+    const int n = (int)(r / Hup);
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (!(h & 1) && !(w & 1) && (h >> 1) < P && (w >> 1) < Q)
+      v = __ldg(reinterpret_cast<const uint4*>(dy + (((long long)n * P + (h >> 1)) * Q + (w >> 1)) * C) + cg);
+    reinterpret_cast<uint4*>(up)[i] = v;
+  }
+}
+
+// out = a + b (bf16, vectors of 8) — gradient fan-in at residual forks
+__global__ void add_bf16_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b,
+                                __nv_bfloat16* __restrict__ out, long long nvec) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec;
+       i += (long long)gridDim.x * blockDim.x) {
+    float x[8], y[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(a) + i), x);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(b) + i), y);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) x[j] += y[j];
+    reinterpret_cast<uint4*>(out)[i] = pack8(x);
+  }
+}
+
+// out_bf16[r][k] = idx[k] >= 0 ? w[r*row_stride + idx[k]] : 0      (filter re-layout, e.g. the space-to-depth stem)
+__global__ void gather_pack_kernel(const float* __restrict__ w, const int* __restrict__ idx,
+                                   __nv_bfloat16* __restrict__ out, int rows, long long row_stride, int K) {
+  const long long total = (long long)rows * K;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(i % K);
+    const long long r = i / K;
+    const int s = idx[k];
+    out[i] = __float2bfloat16(s >= 0 ? w[r * row_stride + s] : 0.f);
+  }
+}
+// dw[r*row_stride + idx[k]] = dwp[r][k] for idx[k] >= 0 (each target written once; the caller zero-fills dw)
+__global__ void scatter_unpack_kernel(const float* __restrict__ dwp, const int* __restrict__ idx,
+                                      float* __restrict__ dw, int rows, long long row_stride, int K) {
+  const long long total = (long long)rows * K;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(i % K);
+    const long long r = i / K;
+    const int s = idx[k];
+    if (s >= 0) dw[r * row_stride + s] = dwp[i];
+  }
+}
+
+// column sums of a [rows][ld] bf16 matrix (bias gradients): out[c] = sum_r x[r][c], c < cols
+__global__ void colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, long long ld, long long rows, int cols,
+                                   float* __restrict__ out) {
+  // block: 32 columns x 8 row lanes
+  __shared__ float part[8][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  float acc = 0.f;
+  if (c < cols)
+    for (long long r = blockIdx.y * 8 + threadIdx.y; r < rows; r += (long long)gridDim.y * 8)
+      acc += __bfloat162float(x[r * ld + c]);
+  part[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < cols) {
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += part[j][threadIdx.x];
+    atomicAdd(out + c, s);
+  }
+}
+
+// dz = dy * (out > 0)   (ReLU backward on bf16 vectors of 8)
+__global__ void relu_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ out,
+                                __nv_bfloat16* __restrict__ dz, long long nvec) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec;
+       i += (long long)gridDim.x * blockDim.x) {
+    float d[8], o[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(dy) + i), d);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(out) + i), o);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) d[j] = o[j] > 0.f ? d[j] : 0.f;
+    reinterpret_cast<uint4*>(dz)[i] = pack8(d);
+  }
+}
+
+}  // namespace m3t
+
+using namespace m3t;
+#define ST(s) reinterpret_cast<cudaStream_t>(s)
+#define BF(p) reinterpret_cast<__nv_bfloat16*>(p)
+#define CBF(p) reinterpret_cast<const __nv_bfloat16*>(p)
+
+extern "C" int m3t_video_prep_s2d(const void* video, int is_u8, void* out, int B, int T, int H, int W, float mul,
+                                  float add, void* stream) {
+  if ((H | W) & 1) return -1;
+  const long long items = (long long)B * T * (H / 2) * (W / 2);
+  if (is_u8)
+    video_prep_s2d_kernel<uint8_t><<<ew_blocks(items), kEwThreads, 0, ST(stream)>>>(
+        reinterpret_cast<const uint8_t*>(video), BF(out), B, T, H, W, mul, add);
+  else
+    video_prep_s2d_kernel<float><<<ew_blocks(items), kEwThreads, 0, ST(stream)>>>(
+        reinterpret_cast<const float*>(video), BF(out), B, T, H, W, mul, add);
+  count_launch();
+  return launch_status();
+}
+
+extern "C" int m3t_bn_finalize(const float* stats, int C, double count, const float* gamma, const float* beta,
+                               float eps, float momentum, float* running_mean, float* running_var, float* mean,
+                               float* invstd, float* scale, float* shift, void* stream) {
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, ST(stream)>>>(stats, C, (float)count, gamma, beta, eps, momentum,
+                                                              running_mean, running_var, mean, invstd, scale, shift);
+  count_launch();
+  return launch_status();
+}
+
+extern "C" int m3t_bn_fold(int C, const float* gamma, const float* beta, const float* running_mean,
+                           const float* running_var, const float* conv_bias, float eps, float* scale, float* shift,
+                           void* stream) {
+  bn_fold_kernel<<<(C + 127) / 128, 128, 0, ST(stream)>>>(C, gamma, beta, running_mean, running_var, conv_bias, eps,
+                                                          scale, shift);
+  count_launch();
+  return launch_status();
+}
+
+extern "C" int m3t_bn_act(const void* y, const float* scale, const float* shift, const void* res,
+                          const float* res_scale, const float* res_shift, int relu, void* out, long long rows, int C,
+                          void* stream) {
+  if (C % 8) return -1;
+  const long long nvec = rows * C / 8;
+  bn_act_kernel<<<ew_blocks(nvec), kEwThreads, 0, ST(stream)>>>(CBF(y), scale, shift, CBF(res), res_scale, res_shift,
+                                                                relu, BF(out), nvec, C);
+  count_launch();
+  return launch_status();
+}
+
+extern "C" int m3t_bn_bwd_reduce(const void* dout, const void* out, const void* y, const float* mean,
+                                 const float* invstd, int relu, void* dz_out, float* sums, long long rows, int C,
+                                 void* stream) {
+  if (C % 8 || (kEwThreads % (C / 8)) != 0) return -1;
+  const int cgs = C / 8;
+  const int rows_per_iter = kEwThreads / cgs;
+  long long blocks = (rows + rows_per_iter - 1) / rows_per_iter;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  bn_bwd_reduce_kernel<<<(int)blocks, kEwThreads, 2 * C * sizeof(float), ST(stream)>>>(
+      CBF(dout), CBF(out), CBF(y), mean, invstd, relu, BF(dz_out), sums, rows, C);
+  count_launch();
+  return launch_status();
+}
+
+extern "C" int m3t_bn_bwd_apply(const void* dout, const void* out, const void* y, const float* mean,
+                                const float* invstd, const float* scale, const float* sums, double count, int relu,
+                                void* dy, long long rows, int C, void* stream) {
+  if (C % 8) return -1;
+  const long long nvec = rows * C / 8;
+  bn_bwd_apply_kernel<<<ew_blocks(nvec), kEwThreads, 0, ST(stream)>>>(CBF(dout), CBF(out), CBF(y), mean, invstd, scale,
+                                                                      sums, (float)(1.0 / count), relu, BF(dy), nvec,
+                                                                      C);
+  count_launch();
+  return launch_status();
+}
+
+extern "C" int m3t_bn_relu_maxpool(const void* y, const float* scale, const float* shift, void* out, void* idx, int F,
+                                   int H, int W, int C, void* stream) {
+  if (C % 8) return -1;
+  const int P = (H - 1) / 2 + 1, Q = (W - 1) / 2 + 1;
+  const long long items = (long long)F * P * Q * (C / 8);
+  bn_relu_maxpool_kernel<<<ew_blocks(items), kEwThreads, 0, ST(stream)>>>(CBF(y), scale, shift, BF(out),
+                                                                          reinterpret_cast<uint8_t*>(idx), F, H, W, C);
+  count_launch();
+  return launch_status();
+}
+
+extern "C" int m3t_maxpool_bn_bwd(int mode, const void* dout, const void* idx, const void* y, const float* mean,
+                                  const float* invstd, const float* scale, const float* shift, float* sums,
+                                  double count, void* dy, int F, int H, int W, int C, void* stream) {
+  if (C % 8 || kEwThreads % (C / 8)) return -1;
+  const long long items = (long long)F * H * W * (C / 8);
+  const int blocks = ew_blocks(items);
+  if (mode == 0)
+    maxpool_bn_bwd_kernel<0><<<blocks, kEwThreads, 2 * C * sizeof(float), ST(stream)>>>(
+        CBF(dout), reinterpret_cast<const uint8_t*>(idx), CBF(y), mean, invstd, scale, shift, sums, 0.f, nullptr, F, H,
+        W, C);
+  else
+    maxpool_bn_bwd_kernel<1><<<blocks, kEwThreads, 0, ST(stream)>>>(CBF(dout), reinterpret_cast<const uint8_t*>(idx),
+                                                                   CBF(y), mean, invstd, scale, shift, sums,
+                                                                   (float)(1.0 / count), BF(dy), F, H, W, C);
+  count_launch();
+  return launch_status();
+}
+
+extern "C" int m3t_avgpool(const void* x, void* out_bf16, float* out_f32, int F, int HW, int C, void* stream) {
+  if (C % 8) return -1;
+  avgpool_kernel<<<ew_blocks((long long)F * C / 8), kEwThreads, 0, ST(stream)>>>(CBF(x), BF(out_bf16), out_f32, F, HW,
+                                                                                 C);
+  count_launch();
+  return launch_status();
+}
+
+extern "C" int m3t_avgpool_bwd(const void* dout, int dout_f32, void* dx, int F, int HW, int C, void* stream) {
+  if (C % 8) return -1;
+  const long long items = (long long)F * HW * C / 8;
+  if (dout_f32)
+    avgpool_bwd_kernel<float><<<ew_blocks(items), kEwThreads, 0, ST(stream)>>>(reinterpret_cast<const float*>(dout),
+                                                                               BF(dx), F, HW, C);
+  else
+    avgpool_bwd_kernel<__nv_bfloat16><<<ew_blocks(items), kEwThreads, 0, ST(stream)>>>(CBF(dout), BF(dx), F, HW, C);
+  count_launch();
+  return launch_status();
+}
+
+extern "C" int m3t_ncs_f32_to_nsc_bf16(const float* in, void* out, int N, int C, int S, int Cpad, void* stream) {
+  dim3 grid((S + 31) / 32, (Cpad + 31) / 32, N), block(32, 8);
+  ncs_f32_to_nsc_bf16_kernel<<<grid, block, 0, ST(stream)>>>(in, BF(out), C, S, Cpad);
+  count_launch();
+  return launch_status();
+}
+
+extern "C" int m3t_nsc_to_ncs_f32(const void* in, int in_f32, float* out, int N, int C, int S, int Cpad,
+                                  void* stream) {
+  dim3 grid((S + 31) / 32, (C + 31) / 32, N), block(32, 8);
+  if (in_f32)
+    nsc_to_ncs_f32_kernel<float><<<grid, block, 0, ST(stream)>>>(reinterpret_cast<const float*>(in), out, C, S, Cpad);
+  else
+    nsc_to_ncs_f32_kernel<__nv_bfloat16><<<grid, block, 0, ST(stream)>>>(CBF(in), out, C, S, Cpad);
+  count_launch();
+  return launch_status();
+}
+
+extern "C" int m3t_cast_f32_bf16(const float* in, long long ld_in, void* out, long long ld_out, long long rows,
+                                 int cols, void* stream) {
+  cast_f32_bf16_kernel<<<ew_blocks(rows * ld_out), kEwThreads, 0, ST(stream)>>>(in, ld_in, BF(out), ld_out, rows,
+                                                                                cols);
+  count_launch();
+  return launch_status();
+}
+
+extern "C" int m3t_cast_bf16_f32(const void* in, long long ld_in, float* out, long long ld_out, long long rows,
+                                 int cols, void* stream) {
+  cast_bf16_f32_kernel<<<ew_blocks(rows * cols), kEwThreads, 0, ST(stream)>>>(CBF(in), ld_in, out, ld_out, rows, cols);
+  count_launch();
+  return launch_status();
+}
+
+extern "C" int m3t_pack_filter(const float* w, void* w_fprop, void* w_dgrad, int Cout, int Cin, int taps,
+                               void* stream) {
+  pack_filter_kernel<<<ew_blocks((long long)Cout * Cin * taps), kEwThreads, 0, ST(stream)>>>(w, BF(w_fprop),
+                                                                                           BF(w_dgrad), Cout, Cin,
+                                                                                           taps);
+  count_launch();
+  return launch_status();
+}
+
+extern "C" int m3t_unpack_filter_grad(const float* dw_packed, float* dw, int Cout, int Cin, int taps, void* stream) {
+  unpack_filter_grad_kernel<<<ew_blocks((long long)Cout * Cin * taps), kEwThreads, 0, ST(stream)>>>(dw_packed, dw,
+                                                                                                  Cout, Cin, taps);
+  count_launch();
+  return launch_status();
+}
+
+extern "C" int m3t_zero_insert2(const void* dy, void* up, int N, int P, int Q, int Hup, int Wup, int C,
+                                void* stream) {
+  if (C % 8) return -1;
+  zero_insert2_kernel<<<ew_blocks((long long)N * Hup * Wup * C / 8), kEwThreads, 0, ST(stream)>>>(CBF(dy), BF(up), N,
+                                                                                                 P, Q, Hup, Wup, C);
+  count_launch();
+  return launch_status();
+}
+
+extern "C" int m3t_add_bf16(const void* a, const void* b, void* out, long long n, void* stream) {
+  if (n % 8) return -1;
+  add_bf16_kernel<<<ew_blocks(n / 8), kEwThreads, 0, ST(stream)>>>(CBF(a), CBF(b), BF(out), n / 8);
+  count_launch();
+  return launch_status();
+}
+
+extern "C" int m3t_gather_pack_bf16(const float* w, const int* idx, void* out, int rows, long long row_stride, int K,
+                                    void* stream) {
+  gather_pack_kernel<<<ew_blocks((long long)rows * K), kEwThreads, 0, ST(stream)>>>(w, idx, BF(out), rows, row_stride,
+                                                                                  K);
+  count_launch();
+  return launch_status();
+}
+
+extern "C" int m3t_scatter_unpack_f32(const float* dwp, const int* idx, float* dw, int rows, long long row_stride,
+                                      int K, void* stream) {
+  scatter_unpack_kernel<<<ew_blocks((long long)rows * K), kEwThreads, 0, ST(stream)>>>(dwp, idx, dw, rows, row_stride,
+                                                                                     K);
+  count_launch();
+  return launch_status();
+}
+
+extern "C" int m3t_colsum_bf16(const void* x, long long ld, long long rows, int cols, float* out, void* stream) {
+  long long gy = (rows + 8 * 64 - 1) / (8 * 64);
+  if (gy > 148) gy = 148;
+  if (gy < 1) gy = 1;
+  dim3 grid((cols + 31) / 32, (unsigned)gy), block(32, 8);
+  colsum_bf16_kernel<<<grid, block, 0, ST(stream)>>>(CBF(x), ld, rows, cols, out);
+  count_launch();
+  return launch_status();
+}
+
+extern "C" int m3t_relu_bwd_bf16(const void* dy, const void* out, void* dz, long long n, void* stream) {
+  if (n % 8) return -1;
+  relu_bwd_kernel<<<ew_blocks(n / 8), kEwThreads, 0, ST(stream)>>>(CBF(dy), CBF(out), BF(dz), n / 8);
+  count_launch();
+  return launch_status();
+}

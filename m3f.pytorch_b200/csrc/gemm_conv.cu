@@ -7,10 +7,10 @@
 
 namespace m3t {
 
-template <int BN, int MT, int STAGES, int AKIND, bool A_MN, bool B_MN, int EPI>
+template <int BN, int MT, int STAGES, int AKIND, bool A_MN, bool B_MN, int EPI, int CK = 64>
 static int launch_umma(const CUtensorMap& tmA, const CUtensorMap& tmB, const UmmaParams& p, int tiles_m, int splits,
                        cudaStream_t st) {
-  auto kern = umma_kernel<BN, MT, STAGES, AKIND, A_MN, B_MN, EPI>;
+  auto kern = umma_kernel<BN, MT, STAGES, AKIND, A_MN, B_MN, EPI, CK>;
   constexpr int smem = umma_smem_bytes<BN, MT, STAGES>();
   static bool attr_done = false;
   if (!attr_done) {
@@ -88,13 +88,16 @@ int conv_geom(ConvGeom& g, const int* v) {
   if (g.nd < 1 || g.nd > 3) return -1;
   if (g.nd < 3) { if (g.D != 1 || g.kd != 1) return -1; g.sd = 1; g.dd = 1; g.pdl = g.pdu = 0; }
   if (g.nd < 2) { if (g.H != 1 || g.kh != 1) return -1; g.sh = 1; g.dh = 1; g.phl = g.phu = 0; }
-  if (g.Cin % 64 != 0 || g.Cout % 8 != 0) return -4;
+  if ((g.Cin % 64 != 0 && g.Cin != 16) || g.Cout % 8 != 0) return -4;
+  if (g.Cin == 16 && (g.kd * g.kh * g.kw) % 4 != 0) return -4;  // 16-channel mode packs 4 taps per stage
   g.Q = (g.W + g.pwl + g.pwu - g.dw * (g.kw - 1) - 1) / g.sw + 1;
   g.P = (g.H + g.phl + g.phu - g.dh * (g.kh - 1) - 1) / g.sh + 1;
   g.Z = (g.D + g.pdl + g.pdu - g.dd * (g.kd - 1) - 1) / g.sd + 1;
   if (g.Q <= 0 || g.P <= 0 || g.Z <= 0) return -5;
   return 0;
 }
+
+int conv_ck(const ConvGeom& g) { return g.Cin == 16 ? 16 : 64; }
 
 int conv_tmap(CUtensorMap* tm, const void* x, const ConvGeom& g, uint32_t pixels_per_column) {
   const int rank = g.nd + 2;
@@ -106,7 +109,9 @@ int conv_tmap(CUtensorMap* tm, const void* x, const ConvGeom& g, uint32_t pixels
   if (g.nd >= 2) { dims[i] = (uint64_t)g.H; lower[1] = -g.phl; upper[1] = g.phu - (g.kh - 1) * g.dh; cs[1] = g.sh; ++i; }
   if (g.nd >= 3) { dims[i] = (uint64_t)g.D; lower[2] = -g.pdl; upper[2] = g.pdu - (g.kd - 1) * g.dd; cs[2] = g.sd; ++i; }
   dims[i] = (uint64_t)g.N;
-  return make_tmap_im2col_bf16(tm, x, rank, dims, lower, upper, cs, 64, pixels_per_column);
+  const int ck = conv_ck(g);
+  return make_tmap_im2col_bf16(tm, x, rank, dims, lower, upper, cs, (uint32_t)ck, pixels_per_column,
+                               ck == 64 ? 128 : 32);
 }
 
 void conv_fill_params(UmmaParams& p, const ConvGeom& g) {
@@ -117,7 +122,7 @@ void conv_fill_params(UmmaParams& p, const ConvGeom& g) {
   p.dw = g.dw; p.dh = g.dh; p.dd = g.dd;
   p.S = g.kw; p.R = g.kh; p.T = g.kd;
   p.Cin = g.Cin;
-  p.cblocks = g.Cin / 64;
+  p.cblocks = g.Cin / conv_ck(g);
 }
 
 }  // namespace
@@ -135,7 +140,8 @@ extern "C" int m3t_conv_fprop_bf16(const void* x, const void* w_packed, void* y,
   memset(&p, 0, sizeof(p));
   conv_fill_params(p, g);
   p.M = (int)Mpix; p.N = g.Cout;
-  p.k_iters = taps * p.cblocks;
+  const int ck = conv_ck(g);
+  p.k_iters = taps * g.Cin / kBlockK;
   p.out = y; p.ldc = g.Cout; p.out_f32 = 0;
   p.scale = scale; p.shift = shift;
   p.residual = reinterpret_cast<const __nv_bfloat16*>(residual); p.ldr = g.Cout;
@@ -154,9 +160,14 @@ extern "C" int m3t_conv_fprop_bf16(const void* x, const void* w_packed, void* y,
   CUtensorMap tmA, tmB;
   rc = conv_tmap(&tmA, x, g, 128);
   if (rc) return rc;
-  rc = make_tmap_2d_bf16(&tmB, w_packed, (uint64_t)taps * g.Cin, (uint64_t)g.Cout, (uint64_t)taps * g.Cin, 64,
-                         (uint32_t)bn);
+  rc = make_tmap_2d_bf16(&tmB, w_packed, (uint64_t)taps * g.Cin, (uint64_t)g.Cout, (uint64_t)taps * g.Cin,
+                         (uint32_t)ck, (uint32_t)bn, ck == 64 ? 128 : 32);
   if (rc) return rc;
+  if (ck == 16) {
+    if (bn != 64) return -4;
+    if (mt == 2) return launch_umma<64, 2, 2, A_IM2COL, false, false, EPI_STORE, 16>(tmA, tmB, p, tiles_m, 1, st);
+    return launch_umma<64, 1, 4, A_IM2COL, false, false, EPI_STORE, 16>(tmA, tmB, p, tiles_m, 1, st);
+  }
   if (bn == 64 && mt == 1) return launch_umma<64, 1, 4, A_IM2COL, false, false, EPI_STORE>(tmA, tmB, p, tiles_m, 1, st);
   if (bn == 64 && mt == 2) return launch_umma<64, 2, 2, A_IM2COL, false, false, EPI_STORE>(tmA, tmB, p, tiles_m, 1, st);
   if (bn == 128 && mt == 1) return launch_umma<128, 1, 3, A_IM2COL, false, false, EPI_STORE>(tmA, tmB, p, tiles_m, 1, st);
@@ -181,8 +192,9 @@ extern "C" int m3t_conv_wgrad_bf16(const void* x, const void* dy, float* dw_pack
   p.M = taps * g.Cin;  // rows of D = (tap, ci)
   p.N = g.Cout;
   const int bn = g.Cout <= 64 ? 64 : 128;
+  const int ck = conv_ck(g);
   p.tiles_n = ceil_div(g.Cout, bn);
-  const int tiles_m = ceil_div(p.atoms, 2);
+  const int tiles_m = ceil_div(p.atoms, 128 / ck);
   const int kblocks = ceil_div(Mpix, kBlockK);
   int splits = splits_hint;
   if (splits <= 0) {
@@ -200,6 +212,10 @@ extern "C" int m3t_conv_wgrad_bf16(const void* x, const void* dy, float* dw_pack
   if (rc) return rc;
   rc = make_tmap_2d_bf16(&tmB, dy, (uint64_t)g.Cout, (uint64_t)Mpix, (uint64_t)g.Cout, 64, 64);
   if (rc) return rc;
+  if (ck == 16) {
+    if (bn != 64) return -4;
+    return launch_umma<64, 1, 4, A_WGRAD, false, true, EPI_ATOMIC_T, 16>(tmA, tmB, p, tiles_m, splits, st);
+  }
   if (bn == 64) return launch_umma<64, 1, 4, A_WGRAD, false, true, EPI_ATOMIC_T>(tmA, tmB, p, tiles_m, splits, st);
   return launch_umma<128, 1, 3, A_WGRAD, false, true, EPI_ATOMIC_T>(tmA, tmB, p, tiles_m, splits, st);
 }

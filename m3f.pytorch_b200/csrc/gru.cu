@@ -1,0 +1,364 @@
+// Bidirectional GRU recurrence as persistent kernels (forward and BPTT).
+//
+// The input projection  gi = x . W_ih^T + b_ih  of all time steps is one tcgen05 GEMM (m3t_gemm_bf16); what is
+// left is the serial part.  One launch runs a whole layer, both directions:
+//   grid = (H/32 hidden slices, batch-slice lanes, 2 directions), 256 threads, one CTA per SM (cooperative launch).
+//   A CTA keeps its slice of W_hh (3 gates x 32 units x H, bf16) in shared memory for the whole sequence, and per
+//   step multiplies the previous hidden state of its batch slice (re-read from the layer output in L2, bf16) with
+//   it on the legacy tensor path (mma.sync m16n8k16, fp32 accumulate) -- the step is latency/sync bound, not
+//   throughput bound, so the 128-row tcgen05 tile would only add TMEM round trips.  The fp32 hidden state of the
+//   (batch, unit) elements a thread owns never leaves its registers.  CTAs that share a (direction, batch slice)
+//   synchronise once per step through a global arrival counter.
+// Gate order and arithmetic follow nn.GRU (reference: models/rnn.py:17,72-75):
+//   r = s(gi_r + W_hr h + b_hr), z = s(gi_z + W_hz h + b_hz), n = tanh(gi_n + r*(W_hn h + b_hn)), h' = (1-z)n + z h.
+#include "../../include/m3t_b200.h"
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace m3t {
+
+constexpr int kGruThreads = 256;
+constexpr int kJS = 32;          // hidden units per CTA
+constexpr int kFwdBS = 64;       // batch rows per slice (forward)
+constexpr int kBwdBS = 32;       // batch rows per slice (backward)
+constexpr int kMaxSlicesPerCta = 8;
+
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], uint32_t saddr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(saddr));
+}
+__device__ __forceinline__ void ldmatrix_x2(uint32_t (&r)[2], uint32_t saddr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0, %1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(saddr));
+}
+__device__ __forceinline__ void mma_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+      "{%0, %1, %2, %3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint4 ld_cg_u4(const void* p) {
+  uint4 v;
+  asm volatile("ld.global.cg.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float ld_cg_bf16(const __nv_bfloat16* p) {
+  unsigned short v;
+  asm volatile("ld.global.cg.u16 %0, [%1];" : "=h"(v) : "l"(p));
+  return __uint_as_float(((uint32_t)v) << 16);
+}
+__device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// all threads of the CTA call; thread 0 arrives / polls
+__device__ __forceinline__ void group_arrive(unsigned* counter) {
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) atomicAdd(counter, 1u);
+}
+__device__ __forceinline__ void group_wait(const unsigned* counter, unsigned target) {
+  if (threadIdx.x == 0) {
+    const long long t0 = clock64();
+    while (ld_acquire(counter) < target) {
+      if (clock64() - t0 > 4000000000LL) {
+        printf("m3t: gru group barrier timeout block=(%d,%d,%d) target=%u have=%u\n", blockIdx.x, blockIdx.y,
+               blockIdx.z, target, ld_acquire(counter));
+        __trap();
+      }
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
+
+struct GruParams {
+  int B, T, H;
+  const float* gi;              // [B*T][2][3H]   x-projection incl. b_ih
+  const __nv_bfloat16* w;       // fwd: [2][3H][H] (W_hh)      bwd: [2][H][3H] (W_hh^T)
+  const float* b_hh;            // [2][3H]
+  __nv_bfloat16* out;           // [B][T][2H]     hidden states (bf16)
+  float* out_f32;               // optional fp32 copy of out (API boundary) or null
+  float* saved;                 // [B*T][2][4][H] r, z, n, hn  (fwd writes when non-null; bwd reads)
+  // backward only
+  const __nv_bfloat16* dout;    // [B][T][2H] gradient wrt out
+  __nv_bfloat16* dgi;           // [B*T][2][3H]
+  __nv_bfloat16* dgh;           // [B*T][2][3H]
+  __nv_bfloat16* hprev;         // [B*T][2][H]   h_{t-1} copy (zero at sequence start) for the dW_hh GEMM
+  unsigned* counters;           // [2][nslices_b] zero-initialised
+  int nbslices;                 // number of batch slices
+};
+
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kGruThreads, 1) gru_fwd_kernel(const GruParams p) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int H = p.H, T = p.T, B = p.B;
+  const int ldk = H + 8;  // padded row (elements): rows shift by 16 B -> conflict-free ldmatrix
+  __nv_bfloat16* Wsm = reinterpret_cast<__nv_bfloat16*>(smem);   // [96][ldk]
+  __nv_bfloat16* hsm = Wsm + 96 * ldk;                           // [64][ldk]
+  const int js = blockIdx.x, dir = blockIdx.z;
+  const int nsl = gridDim.x;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int vec_per_row = H / 8;
+
+  // resident W_hh slice: smem row g*32 + j  <-  W_hh[dir][g*H + js*32 + j][:]
+  for (int i = tid; i < 96 * vec_per_row; i += kGruThreads) {
+    const int row = i / vec_per_row, v = i - row * vec_per_row;
+    const int g = row >> 5, j = row & 31;
+    const uint4 val =
+        __ldg(reinterpret_cast<const uint4*>(p.w + ((long long)dir * 3 * H + g * H + js * kJS + j) * H) + v);
+    *reinterpret_cast<uint4*>(Wsm + row * ldk + v * 8) = val;
+  }
+  const int mrow = (warp & 3) * 16, jhalf = warp >> 2;
+  // per-thread owned elements: (half, e): row = mrow + lane/4 + (e>>1)*8 ; j = 16*jhalf + 8*half + (lane%4)*2 + (e&1)
+  float bhh[3][4];  // [gate][half*2 + (e&1)]
+#pragma unroll
+  for (int g = 0; g < 3; ++g)
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh)
+#pragma unroll
+      for (int e = 0; e < 2; ++e)
+        bhh[g][hh * 2 + e] =
+            p.b_hh[dir * 3 * H + g * H + js * kJS + 16 * jhalf + 8 * hh + (lane & 3) * 2 + e];
+  float hreg[kMaxSlicesPerCta][8];
+#pragma unroll
+  for (int s = 0; s < kMaxSlicesPerCta; ++s)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) hreg[s][e] = 0.f;
+  __syncthreads();
+
+  for (int step = 0; step < T; ++step) {
+    const int t = dir == 0 ? step : T - 1 - step;
+    const int tprev = dir == 0 ? t - 1 : t + 1;
+#pragma unroll
+    for (int si = 0; si < kMaxSlicesPerCta; ++si) {
+      const int bs = blockIdx.y + si * gridDim.y;
+      if (bs >= p.nbslices) break;
+      const int b0 = bs * kFwdBS;
+      unsigned* counter = p.counters + dir * p.nbslices + bs;
+      float acc[6][4];
+#pragma unroll
+      for (int i = 0; i < 6; ++i)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[i][e] = 0.f;
+      if (step > 0) {
+        group_wait(counter, (unsigned)(step * nsl));
+        // stage h_{t-1} of this batch slice (bf16, written by the nsl CTAs of the group) -> smem
+        for (int i = tid; i < kFwdBS * vec_per_row; i += kGruThreads) {
+          const int row = i / vec_per_row, v = i - row * vec_per_row;
+          const int b = b0 + row;
+          uint4 val = make_uint4(0, 0, 0, 0);
+          if (b < B) val = ld_cg_u4(p.out + ((long long)b * T + tprev) * 2 * H + dir * H + v * 8);
+          *reinterpret_cast<uint4*>(hsm + row * ldk + v * 8) = val;
+        }
+        __syncthreads();
+        const uint32_t a_base = smem_u32(hsm + (mrow + (lane & 7) + ((lane >> 3) & 1) * 8) * ldk + (lane >> 4) * 8);
+        const uint32_t b_base =
+            smem_u32(Wsm + (16 * jhalf + (lane & 7) + (lane >> 4) * 8) * ldk + ((lane >> 3) & 1) * 8);
+        for (int kk = 0; kk < H / 16; ++kk) {
+          uint32_t a[4];
+          ldmatrix_x4(a, a_base + kk * 32);
+#pragma unroll
+          for (int g = 0; g < 3; ++g) {
+            uint32_t bb[4];
+            ldmatrix_x4(bb, b_base + (g * 32 * ldk) * 2 + kk * 32);
+            mma_16816(acc[g * 2 + 0], a, bb[0], bb[1]);
+            mma_16816(acc[g * 2 + 1], a, bb[2], bb[3]);
+          }
+        }
+      }
+      // gate math on the 8 owned (b, j) elements
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int b = b0 + mrow + (lane >> 2) + (e >> 1) * 8;
+          const int jl = 16 * jhalf + 8 * hh + (lane & 3) * 2 + (e & 1);
+          const int j = js * kJS + jl;
+          if (b < B) {
+            const long long row = (long long)b * T + t;
+            const float* gi = p.gi + row * 6 * H + dir * 3 * H + j;
+            const float hp = hreg[si][hh * 4 + e];
+            const float hr = acc[0 + hh][e] + bhh[0][hh * 2 + (e & 1)];
+            const float hz = acc[2 + hh][e] + bhh[1][hh * 2 + (e & 1)];
+            const float hn = acc[4 + hh][e] + bhh[2][hh * 2 + (e & 1)];
+            const float r = sigmoidf_(__ldg(gi) + hr);
+            const float z = sigmoidf_(__ldg(gi + H) + hz);
+            const float n = tanhf(__ldg(gi + 2 * H) + r * hn);
+            const float hnew = (1.f - z) * n + z * hp;
+            hreg[si][hh * 4 + e] = hnew;
+            p.out[row * 2 * H + dir * H + j] = __float2bfloat16(hnew);
+            if (p.out_f32) p.out_f32[row * 2 * H + dir * H + j] = hnew;
+            if (p.saved) {
+              float* sv = p.saved + (row * 2 + dir) * 4 * H + j;
+              sv[0] = r; sv[H] = z; sv[2 * H] = n; sv[3 * H] = hn;
+            }
+          }
+        }
+      }
+      group_arrive(counter);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// BPTT.  Per step and batch slice (32 rows):
+//   phase A (elementwise, owned (b, j)):  dh = dout_t + dh_rec ; gate gradients ; write dgi, dgh (bf16), hprev copy
+//   group barrier
+//   phase B: dh_rec[b][k in own slice] = dh*z + sum_{g,j} dgh[b][g][j] * W_hh[g][j][k]   (mma.sync over 3H)
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kGruThreads, 1) gru_bwd_kernel(const GruParams p) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int H = p.H, T = p.T, B = p.B;
+  const int K3 = 3 * H;
+  const int ldk = K3 + 8;
+  __nv_bfloat16* Wsm = reinterpret_cast<__nv_bfloat16*>(smem);  // [32][ldk] rows = own k, cols = (g, j)
+  __nv_bfloat16* gsm = Wsm + 32 * ldk;                          // [32][ldk] dgh tile of the batch slice
+  const int js = blockIdx.x, dir = blockIdx.z;
+  const int nsl = gridDim.x;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int vec_per_row = K3 / 8;
+  for (int i = tid; i < 32 * vec_per_row; i += kGruThreads) {
+    const int row = i / vec_per_row, v = i - row * vec_per_row;
+    const uint4 val = __ldg(reinterpret_cast<const uint4*>(p.w + ((long long)dir * H + js * kJS + row) * K3) + v);
+    *reinterpret_cast<uint4*>(Wsm + row * ldk + v * 8) = val;
+  }
+  const int mrow = (warp & 1) * 16, ncol = (warp >> 1) * 8;
+  float dhrec[kMaxSlicesPerCta][4];
+#pragma unroll
+  for (int s = 0; s < kMaxSlicesPerCta; ++s)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) dhrec[s][e] = 0.f;
+  __syncthreads();
+
+  for (int step = 0; step < T; ++step) {
+    const int t = dir == 0 ? T - 1 - step : step;       // reverse of the forward order
+    const int tprev = dir == 0 ? t - 1 : t + 1;         // time index of h_{prev} in forward order
+    const bool has_prev = tprev >= 0 && tprev < T;
+#pragma unroll
+    for (int si = 0; si < kMaxSlicesPerCta; ++si) {
+      const int bs = blockIdx.y + si * gridDim.y;
+      if (bs >= p.nbslices) break;
+      const int b0 = bs * kBwdBS;
+      unsigned* counter = p.counters + dir * p.nbslices + bs;
+      float dh_direct[4];
+      // ---- phase A ----
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int b = b0 + mrow + (lane >> 2) + (e >> 1) * 8;
+        const int j = js * kJS + ncol + (lane & 3) * 2 + (e & 1);
+        dh_direct[e] = 0.f;
+        if (b < B) {
+          const long long row = (long long)b * T + t;
+          const float dh = __bfloat162float(p.dout[row * 2 * H + dir * H + j]) + dhrec[si][e];
+          const float* sv = p.saved + (row * 2 + dir) * 4 * H + j;
+          const float r = __ldg(sv), z = __ldg(sv + H), n = __ldg(sv + 2 * H), hn = __ldg(sv + 3 * H);
+          const float hp =
+              has_prev ? __bfloat162float(p.out[((long long)b * T + tprev) * 2 * H + dir * H + j]) : 0.f;
+          const float dn = dh * (1.f - z);
+          const float dz = dh * (hp - n);
+          const float dan = dn * (1.f - n * n);
+          const float daz = dz * z * (1.f - z);
+          const float dar = dan * hn * r * (1.f - r);
+          const long long g0 = row * 6 * H + dir * 3 * H + j;
+          p.dgi[g0] = __float2bfloat16(dar);
+          p.dgi[g0 + H] = __float2bfloat16(daz);
+          p.dgi[g0 + 2 * H] = __float2bfloat16(dan);
+          p.dgh[g0] = __float2bfloat16(dar);
+          p.dgh[g0 + H] = __float2bfloat16(daz);
+          p.dgh[g0 + 2 * H] = __float2bfloat16(dan * r);
+          p.hprev[(row * 2 + dir) * H + j] = __float2bfloat16(hp);
+          dh_direct[e] = dh * z;
+        }
+      }
+      if (step + 1 == T) continue;  // gradient wrt h_0 is not needed
+      group_arrive(counter);
+      group_wait(counter, (unsigned)((step + 1) * nsl));
+      // ---- phase B ----
+      for (int i = tid; i < kBwdBS * vec_per_row; i += kGruThreads) {
+        const int row = i / vec_per_row, v = i - row * vec_per_row;
+        const int b = b0 + row;
+        uint4 val = make_uint4(0, 0, 0, 0);
+        if (b < B) val = ld_cg_u4(p.dgh + ((long long)b * T + t) * 6 * H + dir * 3 * H + v * 8);
+        *reinterpret_cast<uint4*>(gsm + row * ldk + v * 8) = val;
+      }
+      __syncthreads();
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+      const uint32_t a_base = smem_u32(gsm + (mrow + (lane & 7) + ((lane >> 3) & 1) * 8) * ldk + (lane >> 4) * 8);
+      const uint32_t b_base = smem_u32(Wsm + (ncol + (lane & 7)) * ldk + ((lane >> 3) & 1) * 8);
+      for (int kk = 0; kk < K3 / 16; ++kk) {
+        uint32_t a[4], bb[2];
+        ldmatrix_x4(a, a_base + kk * 32);
+        ldmatrix_x2(bb, b_base + kk * 32);
+        mma_16816(acc, a, bb[0], bb[1]);
+      }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) dhrec[si][e] = dh_direct[e] + acc[e];
+      __syncthreads();  // gsm is rewritten by the next slice / step
+    }
+  }
+}
+
+}  // namespace m3t
+
+using namespace m3t;
+
+static int gru_launch(bool fwd, GruParams& p, void* stream) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (p.H % 32 != 0 || p.H > 512 || p.B <= 0 || p.T <= 0) return -1;
+  const int bs_rows = fwd ? kFwdBS : kBwdBS;
+  p.nbslices = (p.B + bs_rows - 1) / bs_rows;
+  const int nsl = p.H / kJS;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int gy = sms / (2 * nsl);   // all CTAs must be co-resident (1 CTA per SM)
+  if (gy < 1) return -2;
+  if (gy > p.nbslices) gy = p.nbslices;
+  if ((p.nbslices + gy - 1) / gy > kMaxSlicesPerCta) return -3;
+  const size_t smem = fwd ? (size_t)(96 + 64) * (p.H + 8) * 2 : (size_t)64 * (3 * p.H + 8) * 2;
+  auto kern = fwd ? gru_fwd_kernel : gru_bwd_kernel;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -20;
+  if (cudaMemsetAsync(p.counters, 0, sizeof(unsigned) * 2 * p.nbslices, st) != cudaSuccess) return -22;
+  dim3 grid(nsl, gy, 2);
+  void* args[] = {&p};
+  cudaError_t e = cudaLaunchCooperativeKernel((void*)kern, grid, dim3(kGruThreads), args, smem, st);
+  count_launch();
+  if (e != cudaSuccess) return -21;
+  return launch_status();
+}
+
+extern "C" int m3t_gru_fwd(const float* gi, const void* w_hh_bf16, const float* b_hh, void* out_bf16, float* out_f32,
+                           float* saved, unsigned* counters, int B, int T, int H, void* stream) {
+  GruParams p;
+  memset(&p, 0, sizeof(p));
+  p.B = B; p.T = T; p.H = H;
+  p.gi = gi;
+  p.w = reinterpret_cast<const __nv_bfloat16*>(w_hh_bf16);
+  p.b_hh = b_hh;
+  p.out = reinterpret_cast<__nv_bfloat16*>(out_bf16);
+  p.out_f32 = out_f32;
+  p.saved = saved;
+  p.counters = counters;
+  return gru_launch(true, p, stream);
+}
+
+extern "C" int m3t_gru_bwd(const void* dout_bf16, const void* out_bf16, const float* saved, const void* w_hh_t_bf16,
+                           void* dgi_bf16, void* dgh_bf16, void* hprev_bf16, unsigned* counters, int B, int T, int H,
+                           void* stream) {
+  GruParams p;
+  memset(&p, 0, sizeof(p));
+  p.B = B; p.T = T; p.H = H;
+  p.dout = reinterpret_cast<const __nv_bfloat16*>(dout_bf16);
+  p.out = reinterpret_cast<__nv_bfloat16*>(const_cast<void*>(out_bf16));
+  p.saved = const_cast<float*>(saved);
+  p.w = reinterpret_cast<const __nv_bfloat16*>(w_hh_t_bf16);
+  p.dgi = reinterpret_cast<__nv_bfloat16*>(dgi_bf16);
+  p.dgh = reinterpret_cast<__nv_bfloat16*>(dgh_bf16);
+  p.hprev = reinterpret_cast<__nv_bfloat16*>(hprev_bf16);
+  p.counters = counters;
+  return gru_launch(false, p, stream);
+}

@@ -104,7 +104,7 @@ inline int make_tmap_2d_bf16(CUtensorMap* tm, const void* base, uint64_t inner, 
 // lower/upper: bounding-box corners per spatial dim in (W, H, D) order; conv_stride likewise.
 inline int make_tmap_im2col_bf16(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims,
                                  const int* lower, const int* upper, const int* conv_stride,
-                                 uint32_t channels_per_pixel, uint32_t pixels_per_column) {
+                                 uint32_t channels_per_pixel, uint32_t pixels_per_column, int swizzle_bytes = 128) {
   const TmapApi& api = tmap_api();
   if (!api.ok) return -10;
   cuuint64_t gdim[5];
@@ -123,7 +123,7 @@ inline int make_tmap_im2col_bf16(CUtensorMap* tm, const void* base, int rank, co
   if (reinterpret_cast<uintptr_t>(base) % 16) return -12;
   CUresult r = api.im2col(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim,
                           gstr, lower, upper, channels_per_pixel, pixels_per_column, es,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_enum(swizzle_bytes),
                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     fprintf(stderr, "m3t: cuTensorMapEncodeIm2col failed (%d) rank=%d dims=[%llu,%llu,%llu,..] lower=%d upper=%d\n",

@@ -31,9 +31,9 @@ struct UmmaParams {
   int pw, ph, pd;     // paddings (lower)
   int dw, dh, dd;     // dilations
   int S, R, T;        // filter extents along w, h, d
-  int cblocks;        // Cin / 64
+  int cblocks;        // Cin / CK
   int Cin;
-  int atoms;          // A_WGRAD: taps * cblocks (number of 64-wide M atoms)
+  int atoms;          // A_WGRAD: taps * cblocks (number of CK-wide M atoms)
   // ---- epilogue ----
   void* out;
   long long ldc;      // row stride of out (elements)
@@ -106,13 +106,22 @@ __device__ __forceinline__ void butterfly_colsum(float (&v)[32], uint32_t lane) 
 template <>
 __device__ __forceinline__ void butterfly_colsum<0>(float (&)[32], uint32_t) {}
 
-template <int BN, int MT, int STAGES, int AKIND, bool A_MN, bool B_MN, int EPI>
+// CK = channels per filter-tap chunk of the implicit-GEMM operand: 64 (one 128B swizzle row per pixel) for the
+// trunk, 16 (32B rows, SWIZZLE_32B, four taps per pipeline stage) for the space-to-depth stem whose Cin is 16.
+template <int BN, int MT, int STAGES, int AKIND, bool A_MN, bool B_MN, int EPI, int CK = 64>
 __global__ void __launch_bounds__(kUmmaThreads, 1)
 umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const UmmaParams p) {
   static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N");
   static_assert(MT == 1 || MT == 2, "MT");
   static_assert(!(A_MN && MT != 1), "MN-major A supports MT == 1");
   static_assert(!B_MN || BN % 64 == 0, "MN-major B needs 64-wide atoms");
+  static_assert(CK == 64 || CK == 16, "CK");
+  static_assert(CK == 64 || AKIND != A_TILED, "CK=16 is an implicit-GEMM mode");
+  constexpr int TPS = kBlockK / CK;              // filter taps per pipeline stage (1 or 4)
+  constexpr int ATOMS_PER_TILE = 128 / CK;       // A_WGRAD: CK-wide M atoms per 128-row tile (2 or 8)
+  constexpr int ATOM_BYTES = kBlockK * CK * 2;   // A_WGRAD: one atom = 64 pixels x CK channels
+  constexpr uint32_t A_SWZ = CK == 64 ? SWZ_128B : SWZ_32B;
+  constexpr uint32_t A_SBO = 8 * CK * 2;         // 8 rows of CK bf16
   constexpr int A_STAGE = MT * 128 * 128;                 // bytes
   constexpr int B_STAGE = (BN < 8 ? 8 : BN) * 128;        // bytes
   constexpr int STAGE = A_STAGE + B_STAGE;
@@ -162,7 +171,8 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       uint32_t tx_bytes = STAGE;
       if constexpr (AKIND == A_WGRAD) {
         // the second 64-wide atom of the last M tile may not exist
-        if (m_tile * 2 + 1 >= p.atoms) tx_bytes -= 64 * 128;
+        const int missing = (m_tile + 1) * ATOMS_PER_TILE - p.atoms;
+        if (missing > 0) tx_bytes -= missing * ATOM_BYTES;
       }
       int stage = 0;
       uint32_t phase = 0;
@@ -189,22 +199,33 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               tma_load_2d(&tmB, &full_bar[stage], sB + j * 8192, n_tile * BN + j * 64, kglob * kBlockK);
           }
         } else if constexpr (AKIND == A_IM2COL) {
-          const int tap = kglob / p.cblocks;
-          const int cb = kglob - tap * p.cblocks;
+          if constexpr (CK == 64) {
+            const int tap = kglob / p.cblocks;
+            const int cb = kglob - tap * p.cblocks;
 #pragma unroll
-          for (int mt = 0; mt < MT; ++mt)
-            im2col_load(&tmA, &full_bar[stage], sA + mt * 16384, p, pc[mt], cb * 64, tap);
-          tma_load_2d(&tmB, &full_bar[stage], sB, tap * p.Cin + cb * 64, n_tile * BN);
+            for (int mt = 0; mt < MT; ++mt)
+              im2col_load(&tmA, &full_bar[stage], sA + mt * 16384, p, pc[mt], cb * 64, tap);
+            tma_load_2d(&tmB, &full_bar[stage], sB, tap * p.Cin + cb * 64, n_tile * BN);
+          } else {
+#pragma unroll
+            for (int j = 0; j < TPS; ++j) {
+              const int tap = kglob * TPS + j;
+#pragma unroll
+              for (int mt = 0; mt < MT; ++mt)
+                im2col_load(&tmA, &full_bar[stage], sA + mt * 16384 + j * (128 * CK * 2), p, pc[mt], 0, tap);
+              tma_load_2d(&tmB, &full_bar[stage], sB + j * (BN * CK * 2), tap * CK, n_tile * BN);
+            }
+          }
         } else {  // A_WGRAD: contraction over pixels, 64 pixels per stage
           const int pix0 = kglob * kBlockK;
           const PixCoord c = pixel_base(p, pix0);
 #pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            const int atom = m_tile * 2 + j;
+          for (int j = 0; j < ATOMS_PER_TILE; ++j) {
+            const int atom = m_tile * ATOMS_PER_TILE + j;
             if (atom < p.atoms) {
               const int tap = atom / p.cblocks;
               const int cb = atom - tap * p.cblocks;
-              im2col_load(&tmA, &full_bar[stage], sA + j * 8192, p, c, cb * 64, tap);
+              im2col_load(&tmA, &full_bar[stage], sA + j * ATOM_BYTES, p, c, cb * CK, tap);
             }
           }
 #pragma unroll
@@ -219,8 +240,13 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     if (lane == 0) {
       constexpr bool a_mn = A_MN || (AKIND == A_WGRAD);
       constexpr uint32_t idesc = make_idesc_bf16(128, BN, a_mn ? 1u : 0u, B_MN ? 1u : 0u);
-      constexpr uint32_t a_lbo = a_mn ? 8192u : 16u, b_lbo = B_MN ? 8192u : 16u;
-      constexpr uint32_t a_kstep = a_mn ? 2048u : 32u, b_kstep = B_MN ? 2048u : 32u;
+      // K-major: LBO unused (16), SBO = 8 rows; k-step = 16 elements along the row (CK=64) or the next tap
+      // sub-tile (CK=16).  MN-major: LBO = one atom (64 k-rows x CK), SBO = 8 k-rows, k-step = 16 k-rows.
+      constexpr uint32_t a_lbo = a_mn ? (uint32_t)ATOM_BYTES : 16u, b_lbo = B_MN ? 8192u : 16u;
+      constexpr uint32_t a_kstep = a_mn ? 16u * CK * 2 : (CK == 64 ? 32u : 128u * CK * 2);
+      constexpr uint32_t b_kstep = B_MN ? 2048u : (CK == 64 ? 32u : (uint32_t)BN * CK * 2);
+      constexpr uint32_t B_SWZ = B_MN ? SWZ_128B : A_SWZ;
+      constexpr uint32_t B_SBO = B_MN ? 1024u : A_SBO;
       int stage = 0;
       uint32_t phase = 0;
       for (int it = 0; it < p.k_iters; ++it) {
@@ -230,10 +256,10 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const uint32_t sB = sA + A_STAGE;
 #pragma unroll
         for (int k = 0; k < kBlockK / 16; ++k) {
-          const uint64_t bdesc = make_smem_desc(sB + k * b_kstep, b_lbo, 1024, SWZ_128B);
+          const uint64_t bdesc = make_smem_desc(sB + k * b_kstep, b_lbo, B_SBO, B_SWZ);
 #pragma unroll
           for (int mt = 0; mt < MT; ++mt) {
-            const uint64_t adesc = make_smem_desc(sA + mt * 16384 + k * a_kstep, a_lbo, 1024, SWZ_128B);
+            const uint64_t adesc = make_smem_desc(sA + mt * 16384 + k * a_kstep, a_lbo, A_SBO, A_SWZ);
             umma_bf16(tmem_base + mt * BN, adesc, bdesc, idesc, (it | k) != 0 ? 1u : 0u);
           }
         }

@@ -1,0 +1,77 @@
+"""Visual backbones (reference: models/backbone.py).
+
+VA_3DResNet  (reference :314-372): Conv3d spatio-temporal stem + per-frame ResNet-18 trunk + BiGRU head.
+The NCDHW -> (B*T)CHW transpose/copy of the reference (:349-350) does not exist here: the stem writes
+channels-last (B*T, 28, 28, 64) bf16, which *is* the trunk's input layout.
+"""
+import math
+
+import torch
+import torch.nn as nn
+
+from .. import ops
+from .resnet import BasicBlock, ResNet
+from .rnn import GRU
+
+
+def _init_like_reference(module):
+    """Conv3d ~ N(0, sqrt(2/(kt*kh*kw*Cout))), Conv1d kaiming-normal, BN3d/BN1d gamma=1 beta=0
+    (reference: models/backbone.py:357-372)."""
+    for m in module.modules():
+        if isinstance(m, nn.Conv3d):
+            fan = m.kernel_size[0] * m.kernel_size[1] * m.kernel_size[2] * m.out_channels
+            m.weight.data.normal_(0, math.sqrt(2.0 / fan))
+            if m.bias is not None:
+                m.bias.data.zero_()
+        elif isinstance(m, nn.Conv1d):
+            nn.init.kaiming_normal_(m.weight)
+        elif isinstance(m, (nn.BatchNorm3d, nn.BatchNorm1d)):
+            m.weight.data.fill_(1)
+            m.bias.data.zero_()
+
+
+class VA_3DResNet(nn.Module):
+    def __init__(self, inputDim=512, hiddenDim=512, nLayers=2, nClasses=2, frameLen=16, backend='gru', use_cbam=False,
+                 resnet_ver='v2', resnet_depth=18, frontend_agg_mode='ap', nFCs=1):
+        super().__init__()
+        self.inputDim, self.hiddenDim, self.nClasses = inputDim, hiddenDim, nClasses
+        self.frameLen, self.nLayers, self.backend, self.nFCs = frameLen, nLayers, backend, nFCs
+        assert resnet_depth in (18, 34) and resnet_ver in ('v1', 'v2'), \
+            'unsupported ResNet configuration: {}, {}'.format(resnet_depth, resnet_ver)
+        if resnet_ver != 'v1':
+            raise NotImplementedError("pre-activation ResNetV2 is selected by no caller of the reference "
+                                      "(models/model.py:47, models/vox2_model.py:35 pass 'v1')")
+        self.c3d = nn.Sequential(
+            nn.Conv3d(3, 64, kernel_size=(5, 7, 7), stride=(1, 2, 2), padding=(2, 3, 3), bias=False),
+            nn.BatchNorm3d(64),
+            nn.ReLU(True),
+            nn.MaxPool3d(kernel_size=(1, 3, 3), stride=(1, 2, 2), padding=(0, 1, 1)))
+        blocks = [2, 2, 2, 2] if resnet_depth == 18 else [3, 4, 6, 3]
+        self.resnet = ResNet(BasicBlock, blocks, inputDim, zero_init_residual=True, agg_mode=frontend_agg_mode,
+                             fmap_out_size=3, use_cbam=use_cbam)
+        if backend == 'gru':
+            self.gru = GRU(inputDim, hiddenDim, nLayers, nClasses, nFCs)
+        _init_like_reference(self)
+
+    def features_cl(self, video, normalise):
+        """video (B,3,T,112,112) fp32/uint8 -> per-frame trunk features bf16 (B, T, 512)."""
+        conv, bn = self.c3d[0], self.c3d[1]
+        B, T = video.shape[0], video.shape[2]
+        x = ops.Stem3D.apply(video, conv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var, normalise,
+                             bn.training)
+        if bn.training:
+            bn.num_batches_tracked.add_(1)
+        f = self.resnet.forward_cl(x)                     # (B*T, 512)
+        return f.view(B, T, -1)
+
+    def forward_bf16(self, x, normalise=False):
+        f = self.features_cl(x, normalise)
+        if f.shape[1] != self.frameLen:
+            raise RuntimeError("VA_3DResNet: T (%d) must equal frameLen (%d)" % (f.shape[1], self.frameLen))
+        if self.backend == 'gru':
+            return self.gru.forward_bf16(f)
+        return f
+
+    def forward(self, x, *unused):
+        # `*unused` tolerates AffWild2VA.forward's 3-argument call (reference models/model.py:111,130)
+        return ops.as_f32(self.forward_bf16(x))

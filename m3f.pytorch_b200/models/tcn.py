@@ -1,0 +1,89 @@
+"""Temporal convolutional network (reference: models/tcn.py).
+
+Same module tree and state_dict keys as the reference (`network.{i}.conv{1,2}.{bias,weight_g,weight_v}`, their
+aliases under `net.{0,4}`, `downsample.*`).  Each weight-normed dilated causal Conv1d runs as an implicit-GEMM
+conv over channels-last (B,T,C) with left-only zero padding -- Chomp1d becomes index math -- and bias + ReLU in the
+epilogue; the block's residual add + ReLU is one more streaming pass.
+"""
+import warnings
+
+import torch
+import torch.nn as nn
+from torch.nn.utils import weight_norm
+
+from .. import ops
+
+
+class Chomp1d(nn.Module):
+    def __init__(self, chomp_size):
+        super().__init__()
+        self.chomp_size = chomp_size
+
+    def forward(self, x):
+        return x[:, :, :-self.chomp_size].contiguous()
+
+
+def _wn_weight(conv):
+    return torch._weight_norm(conv.weight_v, conv.weight_g, 0)
+
+
+class TemporalBlock(nn.Module):
+    def __init__(self, n_inputs, n_outputs, kernel_size, stride, dilation, padding, dropout=0.2):
+        super().__init__()
+        assert stride == 1, "the reference only builds stride-1 temporal blocks"
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            self.conv1 = weight_norm(nn.Conv1d(n_inputs, n_outputs, kernel_size, stride=stride, padding=padding,
+                                               dilation=dilation))
+            self.conv2 = weight_norm(nn.Conv1d(n_outputs, n_outputs, kernel_size, stride=stride, padding=padding,
+                                               dilation=dilation))
+        self.chomp1, self.relu1, self.dropout1 = Chomp1d(padding), nn.ReLU(), nn.Dropout(dropout)
+        self.chomp2, self.relu2, self.dropout2 = Chomp1d(padding), nn.ReLU(), nn.Dropout(dropout)
+        self.net = nn.Sequential(self.conv1, self.chomp1, self.relu1, self.dropout1,
+                                 self.conv2, self.chomp2, self.relu2, self.dropout2)
+        self.downsample = nn.Conv1d(n_inputs, n_outputs, 1) if n_inputs != n_outputs else None
+        self.relu = nn.ReLU()
+        self.dilation, self.padding = dilation, padding
+        self.init_weights()
+
+    def init_weights(self):
+        # as in the reference, this writes the derived `.weight`, which weight_norm recomputes at the next forward
+        self.conv1.weight.data.normal_(0, 0.01)
+        self.conv2.weight.data.normal_(0, 0.01)
+        if self.downsample is not None:
+            self.downsample.weight.data.normal_(0, 0.01)
+
+    def forward_cl(self, x):
+        h = x
+        for conv, drop in ((self.conv1, self.dropout1), (self.conv2, self.dropout2)):
+            h = ops.Conv1dBiasAct.apply(h, _wn_weight(conv), conv.bias, self.dilation, self.padding, 0, True)
+            if self.training and drop.p > 0:
+                h = torch.nn.functional.dropout(h, drop.p, True)
+        if self.downsample is None:
+            res = x
+        else:
+            res = ops.Conv1dBiasAct.apply(x, self.downsample.weight, self.downsample.bias, 1, 0, 0, False)
+        return ops.AddReLU.apply(h, res)
+
+    def forward(self, x):
+        return ops.FromCL.apply(self.forward_cl(ops.ToCL.apply(x)))
+
+
+class TemporalConvNet(nn.Module):
+    def __init__(self, num_inputs, num_channels, kernel_size=2, dropout=0.2):
+        super().__init__()
+        layers = []
+        for i, out_ch in enumerate(num_channels):
+            d = 2 ** i
+            in_ch = num_inputs if i == 0 else num_channels[i - 1]
+            layers.append(TemporalBlock(in_ch, out_ch, kernel_size, stride=1, dilation=d,
+                                        padding=(kernel_size - 1) * d, dropout=dropout))
+        self.network = nn.Sequential(*layers)
+
+    def forward_cl(self, x):
+        for blk in self.network:
+            x = blk.forward_cl(x)
+        return x
+
+    def forward(self, x):
+        return ops.FromCL.apply(self.forward_cl(ops.ToCL.apply(x)))

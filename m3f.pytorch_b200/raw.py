@@ -6,10 +6,52 @@ import torch
 from . import lib as L
 
 
+# Optional per-call CUDA-event timing of the tensor-core kernels (bench.py's roofline leg).  Events are recorded on
+# the current stream, i.e. the stream the kernels are launched on.
+_prof = None
+
+
+class KernelProfiler:
+    def __init__(self):
+        self.records = []          # (key, algorithmic flops, start event, end event)
+
+    def add(self, key, flops, e0, e1):
+        self.records.append((key, flops, e0, e1))
+
+    def summary(self):
+        """key -> dict(calls, ms_total, flops_total, tflops) (call after torch.cuda.synchronize())."""
+        out = {}
+        for key, flops, e0, e1 in self.records:
+            d = out.setdefault(key, {"calls": 0, "ms_total": 0.0, "flops_total": 0.0})
+            d["calls"] += 1
+            d["ms_total"] += e0.elapsed_time(e1)
+            d["flops_total"] += flops
+        for d in out.values():
+            d["tflops"] = d["flops_total"] / (d["ms_total"] * 1e-3) / 1e12 if d["ms_total"] > 0 else 0.0
+        return out
+
+
+def set_profiler(p):
+    global _prof
+    _prof = p
+
+
+def _timed(key, flops, fn):
+    if _prof is None:
+        return fn()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    r = fn()
+    e1.record()
+    _prof.add(key, flops, e0, e1)
+    return r
+
+
 def _chk_bf16(*ts):
     for t in ts:
         if t is not None:
-            assert t.is_cuda and t.dtype == torch.bfloat16 and t.is_contiguous(), (t.dtype, t.shape, t.is_contiguous())
+            assert t.is_cuda and t.dtype == torch.bfloat16 and t.stride(-1) == 1, (t.dtype, t.shape, t.stride())
 
 
 def gemm(A, B, a_mn=False, b_mn=False, out_dtype=torch.bfloat16, scale=None, shift=None, residual=None,
@@ -58,26 +100,315 @@ def conv_out_dims(g):
     return Z, P, Q
 
 
-def conv_fprop(x, w_packed, g, scale=None, shift=None, residual=None, relu=False, stats=None, tile_hint=0):
+def conv_key(kind, g):
+    return "%s nd%d %dx%dx%d c%d->%d k%dx%dx%d s%d" % (kind, g[0], g[2], g[3], g[4], g[5], g[6], g[7], g[8], g[9],
+                                                        g[12])
+
+
+def conv_fprop(x, w_packed, g, scale=None, shift=None, residual=None, relu=False, stats=None, tile_hint=0,
+               algo_flops=None, tag="fprop"):
     """x: bf16 [N,D,H,W,Cin] contiguous (any view with that element order), w_packed: bf16 [Cout, taps*Cin].
-    Returns bf16 [N,Z,P,Q,Cout]."""
+    Returns bf16 [N,Z,P,Q,Cout].  algo_flops overrides the algorithmic FLOP count credited to this launch
+    (e.g. the space-to-depth stem computes padded taps; a stride-2 dgrad runs over a zero-inserted map)."""
     _chk_bf16(x, w_packed, residual)
     Z, P, Q = conv_out_dims(g)
     N, Cout = g[1], g[6]
     y = torch.empty((N, Z, P, Q, Cout), device=x.device, dtype=torch.bfloat16)
-    rc = L.load().m3t_conv_fprop_bf16(L.ptr(x), L.ptr(w_packed), L.ptr(y), L.int_array(g), L.ptr(scale),
-                                      L.ptr(shift), L.ptr(residual), L.i32(relu), L.ptr(stats), L.i32(tile_hint),
-                                      L.stream_ptr())
-    L.check(rc, "m3t_conv_fprop_bf16")
+
+    def run():
+        rc = L.load().m3t_conv_fprop_bf16(L.ptr(x), L.ptr(w_packed), L.ptr(y), L.int_array(g), L.ptr(scale),
+                                          L.ptr(shift), L.ptr(residual), L.i32(relu), L.ptr(stats), L.i32(tile_hint),
+                                          L.stream_ptr())
+        L.check(rc, "m3t_conv_fprop_bf16")
+
+    if _prof is not None and algo_flops is None:
+        algo_flops = 2.0 * N * Z * P * Q * Cout * g[5] * g[7] * g[8] * g[9]
+    _timed(conv_key(tag, g), algo_flops, run)
     return y
 
 
-def conv_wgrad(x, dy, g, splits=0):
+def conv_wgrad(x, dy, g, splits=0, algo_flops=None):
     """Returns fp32 [Cout, taps*Cin] (packed, tap-major / channel-minor)."""
     _chk_bf16(x, dy)
     Cin, Cout = g[5], g[6]
     taps = g[7] * g[8] * g[9]
     dw = torch.zeros((Cout, taps * Cin), device=x.device, dtype=torch.float32)
-    rc = L.load().m3t_conv_wgrad_bf16(L.ptr(x), L.ptr(dy), L.ptr(dw), L.int_array(g), L.i32(splits), L.stream_ptr())
-    L.check(rc, "m3t_conv_wgrad_bf16")
+
+    def run():
+        rc = L.load().m3t_conv_wgrad_bf16(L.ptr(x), L.ptr(dy), L.ptr(dw), L.int_array(g), L.i32(splits),
+                                          L.stream_ptr())
+        L.check(rc, "m3t_conv_wgrad_bf16")
+
+    flops = None
+    if _prof is not None:
+        Z, P, Q = conv_out_dims(g)
+        flops = algo_flops if algo_flops is not None else 2.0 * g[1] * Z * P * Q * Cout * Cin * taps
+    _timed(conv_key("wgrad", g), flops, run)
     return dw
+
+
+# ----------------------------------------------------------------------------------------------------------
+# HBM-bound passes (elementwise.cu), GRU recurrence (gru.cu), attention mix (fusion.cu)
+# ----------------------------------------------------------------------------------------------------------
+def _lib():
+    return L.load()
+
+
+def video_prep_s2d(video, normalise):
+    """video: (B,3,T,H,W) float32 or uint8 -> bf16 (B,T,H/2,W/2,16) space-to-depth, channel (ph*2+pw)*3+c.
+    normalise=True applies (x-127.5)/127.5 (models/model.py:106); False passes values through."""
+    assert video.is_cuda and video.is_contiguous() and video.dtype in (torch.float32, torch.uint8)
+    B, C, T, H, W = video.shape
+    assert C == 3
+    out = torch.empty((B, T, H // 2, W // 2, 16), device=video.device, dtype=torch.bfloat16)
+    mul, add = (1.0 / 127.5, -1.0) if normalise else (1.0, 0.0)
+    L.check(_lib().m3t_video_prep_s2d(L.ptr(video), L.i32(video.dtype == torch.uint8), L.ptr(out), L.i32(B), L.i32(T),
+                                      L.i32(H), L.i32(W), L.f32(mul), L.f32(add), L.stream_ptr()), "video_prep_s2d")
+    return out
+
+
+def bn_finalize(stats, count, gamma, beta, eps, momentum, running_mean, running_var):
+    C = gamma.numel()
+    buf = torch.empty((4, C), device=gamma.device, dtype=torch.float32)  # mean, invstd, scale, shift
+    L.check(_lib().m3t_bn_finalize(L.ptr(stats), L.i32(C), ctypes_double(count), L.ptr(gamma), L.ptr(beta), L.f32(eps),
+                                   L.f32(momentum), L.ptr(running_mean), L.ptr(running_var), L.ptr(buf[0]),
+                                   L.ptr(buf[1]), L.ptr(buf[2]), L.ptr(buf[3]), L.stream_ptr()), "bn_finalize")
+    return buf
+
+
+def bn_fold(gamma, beta, running_mean, running_var, conv_bias, eps):
+    C = gamma.numel()
+    buf = torch.empty((2, C), device=gamma.device, dtype=torch.float32)  # scale, shift
+    L.check(_lib().m3t_bn_fold(L.i32(C), L.ptr(gamma), L.ptr(beta), L.ptr(running_mean), L.ptr(running_var),
+                               L.ptr(conv_bias), L.f32(eps), L.ptr(buf[0]), L.ptr(buf[1]), L.stream_ptr()), "bn_fold")
+    return buf
+
+
+def ctypes_double(v):
+    import ctypes
+    return ctypes.c_double(float(v))
+
+
+def bn_act(y, scale, shift, res=None, res_scale=None, res_shift=None, relu=True):
+    C = y.shape[-1]
+    rows = y.numel() // C
+    out = torch.empty_like(y)
+    L.check(_lib().m3t_bn_act(L.ptr(y), L.ptr(scale), L.ptr(shift), L.ptr(res), L.ptr(res_scale), L.ptr(res_shift),
+                              L.i32(relu), L.ptr(out), L.i64(rows), L.i32(C), L.stream_ptr()), "bn_act")
+    return out
+
+
+def bn_bwd_reduce(dout, out, y, mean, invstd, relu, want_dz):
+    C = y.shape[-1]
+    rows = y.numel() // C
+    sums = torch.zeros((2, C), device=y.device, dtype=torch.float32)
+    dz = torch.empty_like(y) if want_dz else None
+    L.check(_lib().m3t_bn_bwd_reduce(L.ptr(dout), L.ptr(out), L.ptr(y), L.ptr(mean), L.ptr(invstd), L.i32(relu),
+                                     L.ptr(dz), L.ptr(sums), L.i64(rows), L.i32(C), L.stream_ptr()), "bn_bwd_reduce")
+    return sums, dz
+
+
+def bn_bwd_apply(dout, out, y, mean, invstd, scale, sums, count, relu):
+    C = y.shape[-1]
+    rows = y.numel() // C
+    dy = torch.empty_like(y)
+    L.check(_lib().m3t_bn_bwd_apply(L.ptr(dout), L.ptr(out), L.ptr(y), L.ptr(mean), L.ptr(invstd), L.ptr(scale),
+                                    L.ptr(sums), ctypes_double(count), L.i32(relu), L.ptr(dy), L.i64(rows), L.i32(C),
+                                    L.stream_ptr()), "bn_bwd_apply")
+    return dy
+
+
+def bn_relu_maxpool(y, scale, shift, want_idx):
+    F_, H, W, C = y.shape
+    P, Q = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    out = torch.empty((F_, P, Q, C), device=y.device, dtype=torch.bfloat16)
+    idx = torch.empty((F_, P, Q, C), device=y.device, dtype=torch.uint8) if want_idx else None
+    L.check(_lib().m3t_bn_relu_maxpool(L.ptr(y), L.ptr(scale), L.ptr(shift), L.ptr(out), L.ptr(idx), L.i32(F_),
+                                       L.i32(H), L.i32(W), L.i32(C), L.stream_ptr()), "bn_relu_maxpool")
+    return out, idx
+
+
+def maxpool_bn_bwd(dout, idx, y, mean, invstd, scale, shift, count):
+    F_, H, W, C = y.shape
+    sums = torch.zeros((2, C), device=y.device, dtype=torch.float32)
+    fn = _lib().m3t_maxpool_bn_bwd
+    L.check(fn(L.i32(0), L.ptr(dout), L.ptr(idx), L.ptr(y), L.ptr(mean), L.ptr(invstd), L.ptr(scale), L.ptr(shift),
+               L.ptr(sums), ctypes_double(count), L.ptr(None), L.i32(F_), L.i32(H), L.i32(W), L.i32(C),
+               L.stream_ptr()), "maxpool_bn_bwd(reduce)")
+    dy = torch.empty_like(y)
+    L.check(fn(L.i32(1), L.ptr(dout), L.ptr(idx), L.ptr(y), L.ptr(mean), L.ptr(invstd), L.ptr(scale), L.ptr(shift),
+               L.ptr(sums), ctypes_double(count), L.ptr(dy), L.i32(F_), L.i32(H), L.i32(W), L.i32(C),
+               L.stream_ptr()), "maxpool_bn_bwd(apply)")
+    return dy, sums
+
+
+def avgpool(x, out_f32=False):
+    F_, C = x.shape[0], x.shape[-1]
+    HW = x.numel() // (F_ * C)
+    ob = torch.empty((F_, C), device=x.device, dtype=torch.bfloat16)
+    of = torch.empty((F_, C), device=x.device, dtype=torch.float32) if out_f32 else None
+    L.check(_lib().m3t_avgpool(L.ptr(x), L.ptr(ob), L.ptr(of), L.i32(F_), L.i32(HW), L.i32(C), L.stream_ptr()),
+            "avgpool")
+    return ob, of
+
+
+def avgpool_bwd(dout, shape):
+    F_, C = shape[0], shape[-1]
+    HW = 1
+    for d in shape[1:-1]:
+        HW *= d
+    dx = torch.empty(shape, device=dout.device, dtype=torch.bfloat16)
+    L.check(_lib().m3t_avgpool_bwd(L.ptr(dout), L.i32(dout.dtype == torch.float32), L.ptr(dx), L.i32(F_), L.i32(HW),
+                                   L.i32(C), L.stream_ptr()), "avgpool_bwd")
+    return dx
+
+
+def ncs_to_nsc_bf16(x, cpad=None):
+    """fp32 [N,C,*S] -> bf16 [N,*S,Cpad] (channels-last)."""
+    N, C = x.shape[:2]
+    S = x.numel() // (N * C)
+    cpad = cpad or C
+    out = torch.empty([N] + list(x.shape[2:]) + [cpad], device=x.device, dtype=torch.bfloat16)
+    L.check(_lib().m3t_ncs_f32_to_nsc_bf16(L.ptr(x), L.ptr(out), L.i32(N), L.i32(C), L.i32(S), L.i32(cpad),
+                                           L.stream_ptr()), "ncs_to_nsc")
+    return out
+
+
+def nsc_to_ncs_f32(x, C=None):
+    """bf16/fp32 [N,*S,Cpad] -> fp32 [N,C,*S]."""
+    N, cpad = x.shape[0], x.shape[-1]
+    C = C or cpad
+    S = x.numel() // (N * cpad)
+    out = torch.empty([N, C] + list(x.shape[1:-1]), device=x.device, dtype=torch.float32)
+    L.check(_lib().m3t_nsc_to_ncs_f32(L.ptr(x), L.i32(x.dtype == torch.float32), L.ptr(out), L.i32(N), L.i32(C),
+                                      L.i32(S), L.i32(cpad), L.stream_ptr()), "nsc_to_ncs")
+    return out
+
+
+def cast_bf16(x2d, ld_out=None, out=None):
+    """fp32 [rows, cols] (row stride = stride(0)) -> bf16 [rows, ld_out] (pad columns zero)."""
+    rows, cols = x2d.shape
+    assert x2d.dtype == torch.float32 and x2d.stride(1) == 1
+    ld_out = ld_out or (cols + 7) // 8 * 8
+    if out is None:
+        out = torch.empty((rows, ld_out), device=x2d.device, dtype=torch.bfloat16)
+    L.check(_lib().m3t_cast_f32_bf16(L.ptr(x2d), L.i64(x2d.stride(0)), L.ptr(out), L.i64(out.stride(0)), L.i64(rows),
+                                     L.i32(cols), L.stream_ptr()), "cast_f32_bf16")
+    return out
+
+
+def cast_f32(x2d, cols=None):
+    rows = x2d.shape[0]
+    cols = cols or x2d.shape[1]
+    out = torch.empty((rows, cols), device=x2d.device, dtype=torch.float32)
+    L.check(_lib().m3t_cast_bf16_f32(L.ptr(x2d), L.i64(x2d.stride(0)), L.ptr(out), L.i64(cols), L.i64(rows),
+                                     L.i32(cols), L.stream_ptr()), "cast_bf16_f32")
+    return out
+
+
+def pack_filter(w, want_dgrad):
+    """fp32 [Cout, Cin, *k] -> bf16 [Cout, taps*Cin] (+ dgrad pack [Cin, taps(flipped)*Cout])."""
+    Cout, Cin = w.shape[:2]
+    taps = w.numel() // (Cout * Cin)
+    wf = torch.empty((Cout, taps * Cin), device=w.device, dtype=torch.bfloat16)
+    wd = torch.empty((Cin, taps * Cout), device=w.device, dtype=torch.bfloat16) if want_dgrad else None
+    L.check(_lib().m3t_pack_filter(L.ptr(w), L.ptr(wf), L.ptr(wd), L.i32(Cout), L.i32(Cin), L.i32(taps),
+                                   L.stream_ptr()), "pack_filter")
+    return wf, wd
+
+
+def unpack_filter_grad(dwp, shape):
+    Cout, Cin = shape[:2]
+    taps = 1
+    for d in shape[2:]:
+        taps *= d
+    dw = torch.empty(shape, device=dwp.device, dtype=torch.float32)
+    L.check(_lib().m3t_unpack_filter_grad(L.ptr(dwp), L.ptr(dw), L.i32(Cout), L.i32(Cin), L.i32(taps),
+                                          L.stream_ptr()), "unpack_filter_grad")
+    return dw
+
+
+def zero_insert2(dy, H, W):
+    N, P, Q, C = dy.shape
+    up = torch.empty((N, H, W, C), device=dy.device, dtype=torch.bfloat16)
+    L.check(_lib().m3t_zero_insert2(L.ptr(dy), L.ptr(up), L.i32(N), L.i32(P), L.i32(Q), L.i32(H), L.i32(W), L.i32(C),
+                                    L.stream_ptr()), "zero_insert2")
+    return up
+
+
+def add_bf16(a, b):
+    out = torch.empty_like(a)
+    L.check(_lib().m3t_add_bf16(L.ptr(a), L.ptr(b), L.ptr(out), L.i64(a.numel()), L.stream_ptr()), "add_bf16")
+    return out
+
+
+def gather_pack(w2d, idx, K):
+    rows = w2d.shape[0]
+    out = torch.empty((rows, K), device=w2d.device, dtype=torch.bfloat16)
+    L.check(_lib().m3t_gather_pack_bf16(L.ptr(w2d), L.ptr(idx), L.ptr(out), L.i32(rows), L.i64(w2d.stride(0)), L.i32(K),
+                                        L.stream_ptr()), "gather_pack")
+    return out
+
+
+def scatter_unpack(dwp, idx, shape2d):
+    rows, K = dwp.shape
+    dw = torch.zeros(shape2d, device=dwp.device, dtype=torch.float32)
+    L.check(_lib().m3t_scatter_unpack_f32(L.ptr(dwp), L.ptr(idx), L.ptr(dw), L.i32(rows), L.i64(dw.stride(0)), L.i32(K),
+                                          L.stream_ptr()), "scatter_unpack")
+    return dw
+
+
+def colsum(x2d, cols=None):
+    rows = x2d.shape[0]
+    cols = cols or x2d.shape[1]
+    out = torch.zeros((cols,), device=x2d.device, dtype=torch.float32)
+    L.check(_lib().m3t_colsum_bf16(L.ptr(x2d), L.i64(x2d.stride(0)), L.i64(rows), L.i32(cols), L.ptr(out),
+                                   L.stream_ptr()), "colsum")
+    return out
+
+
+def relu_bwd(dy, out):
+    dz = torch.empty_like(dy)
+    L.check(_lib().m3t_relu_bwd_bf16(L.ptr(dy), L.ptr(out), L.ptr(dz), L.i64(dy.numel()), L.stream_ptr()), "relu_bwd")
+    return dz
+
+
+def gru_fwd(gi, w_hh_bf16, b_hh, B, T, H, want_saved, want_f32=False):
+    dev = gi.device
+    out = torch.empty((B, T, 2 * H), device=dev, dtype=torch.bfloat16)
+    out32 = torch.empty((B, T, 2 * H), device=dev, dtype=torch.float32) if want_f32 else None
+    saved = torch.empty((B * T, 2, 4, H), device=dev, dtype=torch.float32) if want_saved else None
+    counters = torch.empty((2 * ((B + 31) // 32) + 2,), device=dev, dtype=torch.int32)
+    L.check(_lib().m3t_gru_fwd(L.ptr(gi), L.ptr(w_hh_bf16), L.ptr(b_hh), L.ptr(out), L.ptr(out32), L.ptr(saved),
+                               L.ptr(counters), L.i32(B), L.i32(T), L.i32(H), L.stream_ptr()), "gru_fwd")
+    return out, out32, saved
+
+
+def gru_bwd(dout, out, saved, w_hh_t_bf16, B, T, H):
+    dev = dout.device
+    dgi = torch.empty((B * T, 6 * H), device=dev, dtype=torch.bfloat16)
+    dgh = torch.empty((B * T, 6 * H), device=dev, dtype=torch.bfloat16)
+    hprev = torch.empty((B * T, 2 * H), device=dev, dtype=torch.bfloat16)
+    counters = torch.empty((2 * ((B + 31) // 32) + 2,), device=dev, dtype=torch.int32)
+    L.check(_lib().m3t_gru_bwd(L.ptr(dout), L.ptr(out), L.ptr(saved), L.ptr(w_hh_t_bf16), L.ptr(dgi), L.ptr(dgh),
+                               L.ptr(hprev), L.ptr(counters), L.i32(B), L.i32(T), L.i32(H), L.stream_ptr()), "gru_bwd")
+    return dgi, dgh, hprev
+
+
+def att_mix_fwd(x_a, x_v, s_a, s_v):
+    C = x_a.shape[-1]
+    rows = x_a.numel() // C
+    f = torch.empty_like(x_a)
+    L.check(_lib().m3t_att_mix_fwd(L.ptr(x_a), L.ptr(x_v), L.ptr(s_a), L.ptr(s_v), L.ptr(f), L.ptr(None), L.i64(rows),
+                                   L.i32(C), L.stream_ptr()), "att_mix_fwd")
+    return f
+
+
+def att_mix_bwd(df, x_a, x_v, s_a, s_v):
+    C = x_a.shape[-1]
+    rows = x_a.numel() // C
+    dxa, dxv = torch.empty_like(x_a), torch.empty_like(x_v)
+    dsa, dsv = torch.empty_like(s_a), torch.empty_like(s_v)
+    L.check(_lib().m3t_att_mix_bwd(L.ptr(df), L.ptr(x_a), L.ptr(x_v), L.ptr(s_a), L.ptr(s_v), L.ptr(dxa), L.ptr(dxv),
+                                   L.ptr(dsa), L.ptr(dsv), L.i64(rows), L.i32(C), L.stream_ptr()), "att_mix_bwd")
+    return dxa, dxv, dsa, dsv
