@@ -227,6 +227,11 @@ def run_b200(args, rank, local_rank, world):
     ksum = prof.summary()
 
     # ---------------- end-to-end timing (host batch -> device every step, loss read back) ----------------
+    if args.no_e2e:
+        if rank == 0:
+            print(json.dumps({"metric": METRIC, "value": value, "ms_per_step": ms / args.steps, "profiling": True,
+                              "gpu_launches": int(launches)}), flush=True)
+        return
     copy_stream = torch.cuda.Stream()
     bufs = [{k: torch.empty_like(v, device=dev) for k, v in host.items()} for _ in range(2)]
     ready = [torch.cuda.Event(), torch.cuda.Event()]
@@ -317,6 +322,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--clips", type=int, default=256, help="clips per GPU (x16 frames)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3

@@ -76,6 +76,12 @@ int m3t_conv_wgrad_bf16(const void* x, const void* dy, float* dw_packed, const i
 int m3t_video_prep_s2d(const void* video, int is_u8, void* out, int B, int T, int H, int W, float mul, float add,
                        void* stream);
 
+/* Same, additionally unrolled over the stem's four horizontal taps: out bf16 (B,T,H/2,W/2,64) with
+ * out[..][w2][jw*16+ch] = s2d[..][w2+jw-2][ch] (zero outside).  Every pixel is then one 128-byte row, and the stem
+ * Conv3d(3,64,(5,7,7),s(1,2,2),p(2,3,3)) (models/backbone.py:328) becomes a (5,4,1) filter over 64 channels. */
+int m3t_video_prep_s2d_w4(const void* video, int is_u8, void* out, int B, int T, int H, int W, float mul, float add,
+                          void* stream);
+
 /* Train-mode BatchNorm statistics -> per-channel scale/shift (+ running-stat update, momentum, unbiased variance).
  * stats = [2][C] column (sum, sum of squares) produced by the conv epilogue.  Replaces the statistics half of
  * nn.BatchNorm2d/3d in training (models/resnet.py:25,28; models/backbone.py:329). */
@@ -96,14 +102,16 @@ int m3t_bn_bwd_reduce(const void* dout, const void* out, const void* y, const fl
 int m3t_bn_bwd_apply(const void* dout, const void* out, const void* y, const float* mean, const float* invstd,
                      const float* scale, const float* sums, double count, int relu, void* dy, long long rows, int C,
                      void* stream);
-/* Stem tail: out = maxpool3x3/s2/p1( relu(y*scale+shift) ) over (H,W) of [F][H][W][C]; idx (uint8, optional) is the
- * arg-max tap.  Replaces BatchNorm3d apply + ReLU + MaxPool3d((1,3,3),(1,2,2),(0,1,1)) (models/backbone.py:329-331). */
+/* BN apply + ReLU + spatial max-pool in one pass: out = maxpool_{KxK, stride S, pad PAD}( relu(y*scale+shift) ) over
+ * (H,W) of [F][H][W][C]; idx (uint8, optional) is the arg-max tap kh*K+kw.  Replaces BatchNorm3d apply + ReLU +
+ * MaxPool3d((1,3,3),(1,2,2),(0,1,1)) of the ResNet stem (models/backbone.py:329-331) and + MaxPool3d((1,2,2))
+ * of the VGG-M stacks (models/backbone.py:74-92,180-183,218-231). */
 int m3t_bn_relu_maxpool(const void* y, const float* scale, const float* shift, void* out, void* idx, int F, int H,
-                        int W, int C, void* stream);
+                        int W, int C, int K, int S, int PAD, void* stream);
 /* Backward of the stem tail; mode 0 accumulates (sum dz, sum dz*xhat) into sums, mode 1 writes dy. */
 int m3t_maxpool_bn_bwd(int mode, const void* dout, const void* idx, const void* y, const float* mean,
                        const float* invstd, const float* scale, const float* shift, float* sums, double count,
-                       void* dy, int F, int H, int W, int C, void* stream);
+                       void* dy, int F, int H, int W, int C, int K, int S, int PAD, void* stream);
 /* AdaptiveAvgPool2d(1)+flatten (models/resnet.py:117-119) over [F][HW][C] and its backward. */
 int m3t_avgpool(const void* x, void* out_bf16, float* out_f32, int F, int HW, int C, void* stream);
 int m3t_avgpool_bwd(const void* dout, int dout_f32, void* dx, int F, int HW, int C, void* stream);

@@ -82,6 +82,70 @@ __global__ void video_prep_s2d_kernel(const T* __restrict__ in, __nv_bfloat16* _
   }
 }
 
+// Same normalised space-to-depth image, additionally unrolled over the 4 horizontal filter taps so that every pixel
+// carries 64 channels (one 128-byte swizzle row):  out[b][t][h2][w2][jw*16 + ch] = s2d[b][t][h2][w2 + jw - 2][ch]
+// (zero outside the image).  The stem conv then is a (5,4,1) filter over 64 channels: the standard CK=64 im2col path.
+template <typename T>
+__global__ void video_prep_s2d_w4_kernel(const T* __restrict__ in, __nv_bfloat16* __restrict__ out, int B, int Tn,
+                                         int H, int W, float mul, float add) {
+  const int H2 = H / 2, W2 = W / 2;
+  const long long total = (long long)B * Tn * H2 * W2;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int w2 = (int)(i % W2);
+    long long r = i / W2;
+    const int h2 = (int)(r % H2);
+    r /= H2;
+    const int t = (int)(r % Tn);
+    const int b = (int)(r / Tn);
+    float f[16];
+#pragma unroll
+    for (int j = 12; j < 16; ++j) f[j] = 0.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+#pragma unroll
+      for (int ph = 0; ph < 2; ++ph) {
+        const T* p = in + ((((long long)b * 3 + c) * Tn + t) * H + (2 * h2 + ph)) * W + 2 * w2;
+        float x0, x1;
+        if constexpr (sizeof(T) == 4) {
+          const float2 v = __ldg(reinterpret_cast<const float2*>(p));
+          x0 = v.x; x1 = v.y;
+        } else {
+          const uchar2 v = *reinterpret_cast<const uchar2*>(p);
+          x0 = (float)v.x; x1 = (float)v.y;
+        }
+        f[(ph * 2 + 0) * 3 + c] = fmaf(x0, mul, add);
+        f[(ph * 2 + 1) * 3 + c] = fmaf(x1, mul, add);
+      }
+    }
+    float lo[8], hi[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { lo[j] = f[j]; hi[j] = f[8 + j]; }
+    const uint4 vlo = pack8(lo), vhi = pack8(hi);
+    // source pixel w2 is tap jw of destination pixel wd = w2 - jw + 2
+    const long long rowbase = (i - w2) * 64;
+#pragma unroll
+    for (int jw = 0; jw < 4; ++jw) {
+      const int wd = w2 - jw + 2;
+      if (wd >= 0 && wd < W2) {
+        uint4* o = reinterpret_cast<uint4*>(out + rowbase + (long long)wd * 64 + jw * 16);
+        o[0] = vlo;
+        o[1] = vhi;
+      }
+    }
+    // taps that fall outside the image are zero: destination w2 has missing taps jw with w2 + jw - 2 outside [0,W2)
+#pragma unroll
+    for (int jw = 0; jw < 4; ++jw) {
+      const int ws = w2 + jw - 2;
+      if (ws < 0 || ws >= W2) {
+        uint4* o = reinterpret_cast<uint4*>(out + rowbase + (long long)w2 * 64 + jw * 16);
+        o[0] = make_uint4(0, 0, 0, 0);
+        o[1] = make_uint4(0, 0, 0, 0);
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // BatchNorm finalize: (sum, sumsq) -> mean, invstd, scale = gamma*invstd, shift = beta - mean*scale; running stats
 // ------------------------------------------------------------------------------------------------------------
@@ -246,8 +310,8 @@ __global__ void bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout, cons
 // ------------------------------------------------------------------------------------------------------------
 __global__ void bn_relu_maxpool_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ scale,
                                        const float* __restrict__ shift, __nv_bfloat16* __restrict__ out,
-                                       uint8_t* __restrict__ idx, int F, int H, int W, int C) {
-  const int P = (H + 2 - 3) / 2 + 1, Q = (W + 2 - 3) / 2 + 1;
+                                       uint8_t* __restrict__ idx, int F, int H, int W, int C, int K, int S, int PAD) {
+  const int P = (H + 2 * PAD - K) / S + 1, Q = (W + 2 * PAD - K) / S + 1;
   const int cgs = C / 8;
   const long long total = (long long)F * P * Q * cgs;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -264,20 +328,18 @@ __global__ void bn_relu_maxpool_kernel(const __nv_bfloat16* __restrict__ y, cons
     load8f(shift + cg * 8, b);
 #pragma unroll
     for (int j = 0; j < 8; ++j) { best[j] = -INFINITY; bi[j] = 0; }
-#pragma unroll
-    for (int kh = 0; kh < 3; ++kh) {
-      const int h = 2 * p - 1 + kh;
+    for (int kh = 0; kh < K; ++kh) {
+      const int h = S * p - PAD + kh;
       if (h < 0 || h >= H) continue;
-#pragma unroll
-      for (int kw = 0; kw < 3; ++kw) {
-        const int w = 2 * q - 1 + kw;
+      for (int kw = 0; kw < K; ++kw) {
+        const int w = S * q - PAD + kw;
         if (w < 0 || w >= W) continue;
         float v[8];
         unpack8(__ldg(reinterpret_cast<const uint4*>(y + (((long long)f * H + h) * W + w) * C) + cg), v);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float a = fmaxf(fmaf(v[j], s[j], b[j]), 0.f);
-          if (a > best[j]) { best[j] = a; bi[j] = kh * 3 + kw; }
+          if (a > best[j]) { best[j] = a; bi[j] = kh * K + kw; }
         }
       }
     }
@@ -294,12 +356,13 @@ __global__ void bn_relu_maxpool_kernel(const __nv_bfloat16* __restrict__ y, cons
 // Backward of the stem tail.  dz[f][h][w][c] = relu'(a) * sum_{windows (p,q) containing (h,w) with argmax == (h,w)}
 // dout[f][p][q][c];  MODE 0: accumulate (sum dz, sum dz*xhat) ;  MODE 1: write dy = scale*(dz - s0/n - xhat*s1/n).
 template <int MODE>
-__global__ void maxpool_bn_bwd_kernel(const __nv_bfloat16* __restrict__ dout, const uint8_t* __restrict__ idx,
+__global__ void __launch_bounds__(256, 2) maxpool_bn_bwd_kernel(const __nv_bfloat16* __restrict__ dout, const uint8_t* __restrict__ idx,
                                       const __nv_bfloat16* __restrict__ y, const float* __restrict__ mean,
                                       const float* __restrict__ invstd, const float* __restrict__ scale,
                                       const float* __restrict__ shift, float* __restrict__ sums, float inv_count,
-                                      __nv_bfloat16* __restrict__ dy, int F, int H, int W, int C) {
-  const int P = (H + 2 - 3) / 2 + 1, Q = (W + 2 - 3) / 2 + 1;
+                                      __nv_bfloat16* __restrict__ dy, int F, int H, int W, int C, int K, int S,
+                                      int PAD) {
+  const int P = (H + 2 * PAD - K) / S + 1, Q = (W + 2 * PAD - K) / S + 1;
   const int cgs = C / 8;
   extern __shared__ float sh[];  // MODE 0: [2][C]
   if (MODE == 0) {
@@ -327,28 +390,39 @@ __global__ void maxpool_bn_bwd_kernel(const __nv_bfloat16* __restrict__ dout, co
     const int h = (int)(r % H);
     const int f = (int)(r / H);
     float yy[8], dz[8];
-    unpack8(__ldg(reinterpret_cast<const uint4*>(y) + i), yy);
+    const uint4 yraw = __ldg(reinterpret_cast<const uint4*>(y) + i);
 #pragma unroll
     for (int j = 0; j < 8; ++j) dz[j] = 0.f;
-    // windows p with 2p-1 <= h <= 2p+1  ->  p in [ceil((h-1)/2), floor((h+1)/2)]
-    const int p_lo = h >> 1, p_hi = (h + 1) >> 1;   // (h-1+1)/2 .. (h+1)/2 ; p_lo == ceil((h-1)/2)
-    const int q_lo = w >> 1, q_hi = (w + 1) >> 1;
-    for (int p = p_lo; p <= p_hi; ++p) {
-      if (p >= P) continue;
-      const int kh = h - (2 * p - 1);
-      for (int q = q_lo; q <= q_hi; ++q) {
-        if (q >= Q) continue;
-        const int kw = w - (2 * q - 1);
-        const int me = kh * 3 + kw;
-        const long long o = (((long long)f * P + p) * Q + q) * cgs + cg;
-        const uint2 pk = __ldg(reinterpret_cast<const uint2*>(idx) + o);
-        float d[8];
-        unpack8(__ldg(reinterpret_cast<const uint4*>(dout) + o), d);
+    // windows p with S*p-PAD <= h <= S*p-PAD+K-1  ->  p in [ceil((h+PAD-K+1)/S), floor((h+PAD)/S)]; at most two per
+    // dimension for the supported pools (K <= 3, S == 2 or K == S).  All (idx, dout) loads are issued before use.
+    const int hn = h + PAD - K + 1, wn = w + PAD - K + 1;
+    const int p_lo = hn > 0 ? (hn + S - 1) / S : 0, p_hi = min((h + PAD) / S, P - 1);
+    const int q_lo = wn > 0 ? (wn + S - 1) / S : 0, q_hi = min((w + PAD) / S, Q - 1);
+    uint2 pk[4];
+    uint4 dv[4];
+    int me[4];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int sel = ((j < 4 ? pk.x : pk.y) >> (8 * (j & 3))) & 0xFF;
-          if (sel == me) dz[j] += d[j];
-        }
+    for (int a = 0; a < 2; ++a) {
+#pragma unroll
+      for (int bq = 0; bq < 2; ++bq) {
+        const int p = p_lo + a, q = q_lo + bq;
+        const bool ok = p <= p_hi && q <= q_hi;
+        const int pp = ok ? p : p_lo, qq = ok ? q : q_lo;
+        const long long o = (((long long)f * P + min(pp, P - 1)) * Q + min(qq, Q - 1)) * cgs + cg;
+        me[a * 2 + bq] = ok ? (h - (S * p - PAD)) * K + (w - (S * q - PAD)) : -1;
+        pk[a * 2 + bq] = __ldg(reinterpret_cast<const uint2*>(idx) + o);
+        dv[a * 2 + bq] = __ldg(reinterpret_cast<const uint4*>(dout) + o);
+      }
+    }
+    unpack8(yraw, yy);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float d[8];
+      unpack8(dv[k], d);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int sel = ((j < 4 ? pk[k].x : pk[k].y) >> (8 * (j & 3))) & 0xFF;
+        if (sel == me[k]) dz[j] += d[j];
       }
     }
 #pragma unroll
@@ -639,6 +713,20 @@ extern "C" int m3t_video_prep_s2d(const void* video, int is_u8, void* out, int B
   return launch_status();
 }
 
+extern "C" int m3t_video_prep_s2d_w4(const void* video, int is_u8, void* out, int B, int T, int H, int W, float mul,
+                                     float add, void* stream) {
+  if ((H | W) & 1) return -1;
+  const long long items = (long long)B * T * (H / 2) * (W / 2);
+  if (is_u8)
+    video_prep_s2d_w4_kernel<uint8_t><<<ew_blocks(items), kEwThreads, 0, ST(stream)>>>(
+        reinterpret_cast<const uint8_t*>(video), BF(out), B, T, H, W, mul, add);
+  else
+    video_prep_s2d_w4_kernel<float><<<ew_blocks(items), kEwThreads, 0, ST(stream)>>>(
+        reinterpret_cast<const float*>(video), BF(out), B, T, H, W, mul, add);
+  count_launch();
+  return launch_status();
+}
+
 extern "C" int m3t_bn_finalize(const float* stats, int C, double count, const float* gamma, const float* beta,
                                float eps, float momentum, float* running_mean, float* running_var, float* mean,
                                float* invstd, float* scale, float* shift, void* stream) {
@@ -695,30 +783,32 @@ extern "C" int m3t_bn_bwd_apply(const void* dout, const void* out, const void* y
 }
 
 extern "C" int m3t_bn_relu_maxpool(const void* y, const float* scale, const float* shift, void* out, void* idx, int F,
-                                   int H, int W, int C, void* stream) {
-  if (C % 8) return -1;
-  const int P = (H - 1) / 2 + 1, Q = (W - 1) / 2 + 1;
+                                   int H, int W, int C, int K, int S, int PAD, void* stream) {
+  if (C % 8 || K < 1 || K > 3 || S < 1) return -1;
+  const int P = (H + 2 * PAD - K) / S + 1, Q = (W + 2 * PAD - K) / S + 1;
   const long long items = (long long)F * P * Q * (C / 8);
   bn_relu_maxpool_kernel<<<ew_blocks(items), kEwThreads, 0, ST(stream)>>>(CBF(y), scale, shift, BF(out),
-                                                                          reinterpret_cast<uint8_t*>(idx), F, H, W, C);
+                                                                          reinterpret_cast<uint8_t*>(idx), F, H, W, C,
+                                                                          K, S, PAD);
   count_launch();
   return launch_status();
 }
 
 extern "C" int m3t_maxpool_bn_bwd(int mode, const void* dout, const void* idx, const void* y, const float* mean,
                                   const float* invstd, const float* scale, const float* shift, float* sums,
-                                  double count, void* dy, int F, int H, int W, int C, void* stream) {
-  if (C % 8 || kEwThreads % (C / 8)) return -1;
+                                  double count, void* dy, int F, int H, int W, int C, int K, int S, int PAD,
+                                  void* stream) {
+  if (C % 8 || kEwThreads % (C / 8) || K < 1 || K > 3 || S < 1) return -1;
   const long long items = (long long)F * H * W * (C / 8);
   const int blocks = ew_blocks(items);
   if (mode == 0)
     maxpool_bn_bwd_kernel<0><<<blocks, kEwThreads, 2 * C * sizeof(float), ST(stream)>>>(
         CBF(dout), reinterpret_cast<const uint8_t*>(idx), CBF(y), mean, invstd, scale, shift, sums, 0.f, nullptr, F, H,
-        W, C);
+        W, C, K, S, PAD);
   else
     maxpool_bn_bwd_kernel<1><<<blocks, kEwThreads, 0, ST(stream)>>>(CBF(dout), reinterpret_cast<const uint8_t*>(idx),
                                                                    CBF(y), mean, invstd, scale, shift, sums,
-                                                                   (float)(1.0 / count), BF(dy), F, H, W, C);
+                                                                   (float)(1.0 / count), BF(dy), F, H, W, C, K, S, PAD);
   count_launch();
   return launch_status();
 }

@@ -195,10 +195,12 @@ class Stem3D(torch.autograd.Function):
     @staticmethod
     def forward(ctx, video, w, gamma, beta, running_mean, running_var, normalise, training):
         B, _, T, H, W = video.shape
-        xs = raw.video_prep_s2d(video.contiguous(), normalise)
+        xs = raw.video_prep_s2d_w4(video.contiguous(), normalise)
         idx = stem_s2d_index(w.device)
         wp = _cached(w, "stem", lambda: raw.gather_pack(w.detach().view(64, -1), idx, 80 * 16))
-        geom = raw.conv_geom(3, B, T, H // 2, W // 2, 16, 64, (5, 4, 4), (1, 1, 1), (2, 2, 2), (2, 1, 1), (1, 1, 1))
+        # (5,4,1) filter over the 64 = 4 taps x 16 channels of the W-unrolled space-to-depth image; the packed
+        # filter [64][(kt,jh,jw,ch)] is the same buffer either way
+        geom = raw.conv_geom(3, B, T, H // 2, W // 2, 64, 64, (5, 4, 1), (1, 1, 1), (2, 2, 0), (2, 1, 0), (1, 1, 1))
         flops = 2.0 * B * T * (H // 2) * (W // 2) * 64 * 3 * 5 * 7 * 7     # unpadded 5x7x7x3 filter
         ctx.flops = flops
         if training:
@@ -471,3 +473,114 @@ class AddReLU(torch.autograd.Function):
         (out,) = ctx.saved_tensors
         dz = raw.relu_bwd(dout.contiguous(), out)
         return dz, dz
+
+
+# ------------------------------------------------------------------------------------------------------------
+# General conv + bias + BatchNorm (+ ReLU) (+ spatial max-pool) unit for the VGG-M 3-D stacks and tcn_simple
+# ------------------------------------------------------------------------------------------------------------
+_vggm_idx = {}
+
+
+def vggm_s2d_index(device):
+    """First VGG-M conv (Conv3d(3,64,3,stride=(1,2,2),padding=(1,0,0)), models/backbone.py:73) evaluated as a
+    (3,2,2) stride-1 filter over the 2x2 space-to-depth image: idx[((kt*2+jh)*2+jw)*16 + (ph*2+pw)*3 + c] = flat
+    offset of W[c, kt, kh=2jh+ph, kw=2jw+pw] inside one filter (kh or kw == 3 and the 4 pad channels -> -1)."""
+    key = str(device)
+    if key not in _vggm_idx:
+        idx = torch.full((3, 2, 2, 16), -1, dtype=torch.int32)
+        for kt in range(3):
+            for jh in range(2):
+                for jw in range(2):
+                    for ph in range(2):
+                        for pw in range(2):
+                            kh, kw = 2 * jh + ph, 2 * jw + pw
+                            if kh < 3 and kw < 3:
+                                for c in range(3):
+                                    idx[kt, jh, jw, (ph * 2 + pw) * 3 + c] = ((c * 3 + kt) * 3 + kh) * 3 + kw
+        _vggm_idx[key] = idx.view(-1).to(device)
+    return _vggm_idx[key]
+
+
+class ConvNdBNAct(torch.autograd.Function):
+    """out = [maxpool_(H,W)] relu( BN( convNd(x, w) + b ) ) on channels-last bf16, nd in {1, 3}, stride 1.
+    cfg: dict(nd, k=(d,h,w), pad_lo, pad_hi, relu, pool=None|(K,S,PAD), s2d_first=bool)."""
+
+    @staticmethod
+    def forward(ctx, x, w, cbias, gamma, beta, running_mean, running_var, cfg, training):
+        nd, k = cfg["nd"], cfg["k"]
+        Cout = w.shape[0]
+        if nd == 3:
+            N, D, H, W, Cin = x.shape
+        else:
+            N, W, Cin = x.shape
+            D = H = 1
+        geom = raw.conv_geom(nd, N, D, H, W, Cin, Cout, k, (1, 1, 1), cfg["pad_lo"], cfg["pad_hi"], (1, 1, 1))
+        if cfg.get("s2d_first"):
+            idx = vggm_s2d_index(w.device)
+            wf = _cached(w, "vggm1", lambda: raw.gather_pack(w.detach().view(Cout, -1), idx, 12 * 16))
+            flops = 2.0 * N * D * (H - 1) * (W - 1) * Cout * 3 * 27
+        else:
+            wf, _ = packed_filter(w, True)
+            flops = None
+        pool = cfg.get("pool")
+        relu = cfg["relu"]
+        Z, P, Q = raw.conv_out_dims(geom)
+        if not training:
+            ss = raw.bn_fold(gamma.detach(), beta.detach(), running_mean, running_var,
+                             cbias.detach() if cbias is not None else None, BN_EPS)
+            if pool:
+                y = raw.conv_fprop(x, wf, geom, algo_flops=flops)
+                out, _ = raw.bn_relu_maxpool(y.view(N * Z, P, Q, Cout), ss[0], ss[1], False, pool)
+                out = out.view(N, Z, out.shape[1], out.shape[2], Cout)
+            else:
+                out = raw.conv_fprop(x, wf, geom, scale=ss[0], shift=ss[1], relu=relu, algo_flops=flops)
+            return out if nd == 3 else out.view(N, Q, Cout)
+        stats = torch.zeros((2, Cout), device=x.device, dtype=torch.float32)
+        y = raw.conv_fprop(x, wf, geom, stats=stats, algo_flops=flops)
+        count = y.numel() // Cout
+        fin = raw.bn_finalize(stats, count, gamma.detach(), beta.detach(), BN_EPS, BN_MOMENTUM, running_mean,
+                              running_var)
+        if cbias is not None:   # BN(conv + b): the bias only shifts the batch mean that enters running_mean
+            running_mean.add_(cbias.detach(), alpha=BN_MOMENTUM)
+        pidx = None
+        if pool:
+            out, pidx = raw.bn_relu_maxpool(y.view(N * Z, P, Q, Cout), fin[2], fin[3], True, pool)
+            out = out.view(N, Z, out.shape[1], out.shape[2], Cout)
+        else:
+            out = raw.bn_act(y, fin[2], fin[3], relu=relu)
+        ctx.save_for_backward(x, w, y, pidx, out if (relu and not pool) else None, fin)
+        ctx.cfg, ctx.geom, ctx.count, ctx.flops = cfg, geom, count, flops
+        ctx.has_bias = cbias is not None
+        return out if nd == 3 else out.view(N, Q, Cout)
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, w, y, pidx, out, fin = ctx.saved_tensors
+        cfg, geom = ctx.cfg, ctx.geom
+        nd, k, pool, relu = cfg["nd"], cfg["k"], cfg.get("pool"), cfg["relu"]
+        Cout = w.shape[0]
+        N, Z, P, Q = y.shape[0], y.shape[1], y.shape[2], y.shape[3]
+        dout = dout.contiguous()
+        if pool:
+            dy, sums = raw.maxpool_bn_bwd(dout.view(N * Z, -1, dout.shape[-2], Cout) if nd == 3 else dout, pidx,
+                                          y.view(N * Z, P, Q, Cout), fin[0], fin[1], fin[2], fin[3], ctx.count, pool)
+            dy = dy.view(y.shape)
+        else:
+            d5 = dout.view(y.shape)
+            sums, _ = raw.bn_bwd_reduce(d5, out, y, fin[0], fin[1], relu, False)
+            dy = raw.bn_bwd_apply(d5, out, y, fin[0], fin[1], fin[2], sums, ctx.count, relu)
+        dwp = raw.conv_wgrad(x, dy, geom, algo_flops=ctx.flops)
+        if cfg.get("s2d_first"):
+            dw = raw.scatter_unpack(dwp, vggm_s2d_index(w.device), (Cout, w[0].numel())).view(w.shape)
+        else:
+            dw = raw.unpack_filter_grad(dwp, tuple(w.shape))
+        dx = None
+        if ctx.needs_input_grad[0]:
+            _, wd = packed_filter(w, True)
+            lo = tuple(k[i] - 1 - cfg["pad_lo"][i] for i in range(3))
+            hi = tuple(k[i] - 1 - cfg["pad_hi"][i] for i in range(3))
+            Cin = x.shape[-1]
+            g2 = raw.conv_geom(nd, N, Z, P, Q, Cout, Cin, k, (1, 1, 1), lo, hi, (1, 1, 1))
+            dx = raw.conv_fprop(dy, wd, g2, tag="dgrad").view(x.shape)
+        dcb = torch.zeros_like(fin[0]) if ctx.has_bias else None   # exact: batch-norm removes the bias
+        return dx, dw, dcb, sums[1].clone(), sums[0].clone(), None, None, None, None

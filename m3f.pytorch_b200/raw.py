@@ -167,6 +167,19 @@ def video_prep_s2d(video, normalise):
     return out
 
 
+def video_prep_s2d_w4(video, normalise):
+    """As video_prep_s2d, unrolled over the 4 horizontal stem taps: bf16 (B,T,H/2,W/2,64)."""
+    assert video.is_cuda and video.is_contiguous() and video.dtype in (torch.float32, torch.uint8)
+    B, C, T, H, W = video.shape
+    assert C == 3
+    out = torch.empty((B, T, H // 2, W // 2, 64), device=video.device, dtype=torch.bfloat16)
+    mul, add = (1.0 / 127.5, -1.0) if normalise else (1.0, 0.0)
+    L.check(_lib().m3t_video_prep_s2d_w4(L.ptr(video), L.i32(video.dtype == torch.uint8), L.ptr(out), L.i32(B),
+                                         L.i32(T), L.i32(H), L.i32(W), L.f32(mul), L.f32(add), L.stream_ptr()),
+            "video_prep_s2d_w4")
+    return out
+
+
 def bn_finalize(stats, count, gamma, beta, eps, momentum, running_mean, running_var):
     C = gamma.numel()
     buf = torch.empty((4, C), device=gamma.device, dtype=torch.float32)  # mean, invstd, scale, shift
@@ -218,27 +231,30 @@ def bn_bwd_apply(dout, out, y, mean, invstd, scale, sums, count, relu):
     return dy
 
 
-def bn_relu_maxpool(y, scale, shift, want_idx):
+def bn_relu_maxpool(y, scale, shift, want_idx, pool=(3, 2, 1)):
     F_, H, W, C = y.shape
-    P, Q = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    K, S, PAD = pool
+    P, Q = (H + 2 * PAD - K) // S + 1, (W + 2 * PAD - K) // S + 1
     out = torch.empty((F_, P, Q, C), device=y.device, dtype=torch.bfloat16)
     idx = torch.empty((F_, P, Q, C), device=y.device, dtype=torch.uint8) if want_idx else None
     L.check(_lib().m3t_bn_relu_maxpool(L.ptr(y), L.ptr(scale), L.ptr(shift), L.ptr(out), L.ptr(idx), L.i32(F_),
-                                       L.i32(H), L.i32(W), L.i32(C), L.stream_ptr()), "bn_relu_maxpool")
+                                       L.i32(H), L.i32(W), L.i32(C), L.i32(K), L.i32(S), L.i32(PAD), L.stream_ptr()),
+            "bn_relu_maxpool")
     return out, idx
 
 
-def maxpool_bn_bwd(dout, idx, y, mean, invstd, scale, shift, count):
+def maxpool_bn_bwd(dout, idx, y, mean, invstd, scale, shift, count, pool=(3, 2, 1)):
     F_, H, W, C = y.shape
+    K, S, PAD = pool
     sums = torch.zeros((2, C), device=y.device, dtype=torch.float32)
     fn = _lib().m3t_maxpool_bn_bwd
     L.check(fn(L.i32(0), L.ptr(dout), L.ptr(idx), L.ptr(y), L.ptr(mean), L.ptr(invstd), L.ptr(scale), L.ptr(shift),
-               L.ptr(sums), ctypes_double(count), L.ptr(None), L.i32(F_), L.i32(H), L.i32(W), L.i32(C),
-               L.stream_ptr()), "maxpool_bn_bwd(reduce)")
+               L.ptr(sums), ctypes_double(count), L.ptr(None), L.i32(F_), L.i32(H), L.i32(W), L.i32(C), L.i32(K),
+               L.i32(S), L.i32(PAD), L.stream_ptr()), "maxpool_bn_bwd(reduce)")
     dy = torch.empty_like(y)
     L.check(fn(L.i32(1), L.ptr(dout), L.ptr(idx), L.ptr(y), L.ptr(mean), L.ptr(invstd), L.ptr(scale), L.ptr(shift),
-               L.ptr(sums), ctypes_double(count), L.ptr(dy), L.i32(F_), L.i32(H), L.i32(W), L.i32(C),
-               L.stream_ptr()), "maxpool_bn_bwd(apply)")
+               L.ptr(sums), ctypes_double(count), L.ptr(dy), L.i32(F_), L.i32(H), L.i32(W), L.i32(C), L.i32(K),
+               L.i32(S), L.i32(PAD), L.stream_ptr()), "maxpool_bn_bwd(apply)")
     return dy, sums
 
 
