@@ -165,6 +165,19 @@ int m3t_att_mix_fwd(const void* x_a, const void* x_v, const float* s_a, const fl
 int m3t_att_mix_bwd(const void* df, const void* x_a, const void* x_v, const float* s_a, const float* s_v, void* dx_a,
                     void* dx_v, float* ds_a, float* ds_v, long long rows, int C, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Fused log-Mel front end (melspec.cu).  wav: fp32 mono 16 kHz [n_samples]; out_db: fp32 [1 + n_samples/hop][n_mels].
+ * Framing (centre padding n_fft/2, pad_mode 0 = zeros / 1 = reflect), periodic Hann(win_length) zero-padded to
+ * n_fft = 512, FFT, power, mel projection with the caller's filterbank mel_fb [n_mels][257], 10*log10(max(S,1e-10)),
+ * clip to (global max - top_db) when top_db > 0.  scratch: one int.  Replaces librosa.feature.melspectrogram +
+ * librosa.power_to_db at process/extract_melspec.py:15-19 (CPU, offline in the reference). */
+int m3t_logmel(const float* wav, long long n_samples, int hop, int win_length, int n_mels, const float* mel_fb,
+               int pad_mode, float top_db, float* out_db, int* scratch, void* stream);
+/* 200-d stacked audio features: out[t][j*n_mels+m] = mel[3*(start+t)+j][m] for j < 5, zero past the end
+ * (models/dataset.py:83-95 `load_audio`). */
+int m3t_mel_stack(const float* mel, long long n_frames, int n_mels, long long start, int w_len, float* out,
+                  void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -8,6 +8,7 @@ through the C ABI and compares with a plain fp32 PyTorch CPU evaluation of the s
 Metric: max|y - ref| / max|ref| (range-normalised).
 """
 import json
+import math
 import sys
 
 import torch
@@ -662,6 +663,31 @@ CASES.update({
 })
 for _k in ("d_conv_w", "d_bn_w", "d_bn_b"):
     TOLS[_k] = 3e-2
+
+
+
+def case_logmel(seed=0):
+    """Fused log-Mel kernel vs the numpy oracle (oracle/melspec.py; parity unpinned w.r.t. librosa itself)."""
+    import numpy as np
+    from m3t_b200.process import extract_melspec as P
+    from oracle import melspec as OM
+    g = torch.Generator().manual_seed(seed)
+    errs = {}
+    for name, fps, n, mode in (("fps30", 30.0, 16000 * 3 + 123, "constant"), ("fps25_reflect", 25.0, 16000 * 2, "reflect")):
+        t = torch.arange(n) / 16000.0
+        y = 0.3 * torch.sin(2 * math.pi * 440 * t) + 0.05 * torch.randn(n, generator=g) * (t > 0.5) + 1e-4
+        ref = OM.logmel(y.numpy(), fps, pad_mode=mode)
+        got = P.melspectrogram_db(y.cuda(), fps, pad_mode=mode).cpu().numpy()
+        assert got.shape == ref.shape, (got.shape, ref.shape)
+        errs[name + "_db_abs"] = float(np.abs(got - ref).max())
+        st = P.stack_audio_windows(torch.from_numpy(got).cuda(), 5, 40).cpu().numpy()
+        errs[name + "_stack"] = float(np.abs(st - OM.stack_windows(got, 5, 40)).max())
+    return errs
+
+
+CASES["logmel"] = (case_logmel, _c())
+for _k in ("fps30_db_abs", "fps25_reflect_db_abs"):
+    TOLS[_k] = 2e-2      # dB
 
 
 if __name__ == "__main__":
