@@ -1,0 +1,81 @@
+// Optimiser pass over the flat parameter / gradient arena: global-norm clip (train.py:35 gradient_clip_val=1.0) +
+// Adam with coupled L2 weight decay (models/model.py:388-390) in two streaming kernels, no host synchronisation
+// (the clip coefficient is computed on the device from the squared norm).  HBM-bound: the step reads p, g, m, v and
+// writes p, m, v (28 B per parameter); the norm pass reads g (4 B per parameter).
+#include "../../include/m3t_b200.h"
+#include "common.cuh"
+
+namespace m3t {
+
+__global__ void sumsq_kernel(const float* __restrict__ g, long long n, float* __restrict__ out) {
+  float acc = 0.f;
+  const long long n4 = n / 4;
+  const float4* g4 = reinterpret_cast<const float4*>(g);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = __ldg(g4 + i);
+    acc += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    for (long long i = n4 * 4; i < n; ++i) acc += g[i] * g[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  __shared__ float red[32];
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float s = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (threadIdx.x == 0) atomicAdd(out, s);
+  }
+}
+
+__global__ void adam_clip_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                 float* __restrict__ v, long long n, float lr, float beta1, float beta2, float eps,
+                                 float wd, float bc1, float bc2_sqrt, float max_norm, float grad_scale,
+                                 const float* __restrict__ gnorm_sq) {
+  float coef = grad_scale;
+  if (max_norm > 0.f) {
+    const float total = sqrtf(__ldg(gnorm_sq)) * grad_scale;
+    coef *= fminf(1.f, max_norm / (total + 1e-6f));
+  }
+  const float step = lr / bc1;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float pi = p[i];
+    const float gi = fmaf(wd, pi, g[i] * coef);
+    const float mi = fmaf(beta1, m[i], (1.f - beta1) * gi);
+    const float vi = fmaf(beta2, v[i], (1.f - beta2) * gi * gi);
+    m[i] = mi;
+    v[i] = vi;
+    p[i] = pi - step * mi / (sqrtf(vi) / bc2_sqrt + eps);
+  }
+}
+
+}  // namespace m3t
+
+using namespace m3t;
+
+extern "C" int m3t_sumsq_f32(const float* g, long long n, float* out, void* stream) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (cudaMemsetAsync(out, 0, sizeof(float), st) != cudaSuccess) return -22;
+  long long blocks = (n / 4 + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks < 1) blocks = 1;
+  sumsq_kernel<<<(int)blocks, 256, 0, st>>>(g, n, out);
+  count_launch();
+  return launch_status();
+}
+
+extern "C" int m3t_adam_clip_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1,
+                                  float beta2, float eps, float weight_decay, int step, float max_norm,
+                                  float grad_scale, const float* gnorm_sq, void* stream) {
+  if (step < 1) return -1;
+  const float bc1 = 1.f - powf(beta1, (float)step);
+  const float bc2_sqrt = sqrtf(1.f - powf(beta2, (float)step));
+  long long blocks = (n + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  adam_clip_kernel<<<(int)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, bc1, bc2_sqrt, max_norm, grad_scale, gnorm_sq);
+  count_launch();
+  return launch_status();
+}

@@ -690,6 +690,45 @@ for _k in ("fps30_db_abs", "fps25_reflect_db_abs"):
     TOLS[_k] = 2e-2      # dB
 
 
+
+def case_optim(seed=0):
+    """Flat-arena clip + Adam (optim.cu) vs torch.nn.utils.clip_grad_norm_ + torch.optim.Adam over 3 steps."""
+    import torch.nn as nn
+    from m3t_b200.engine import TrainEngine
+
+    class Net(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.l1, self.l2 = nn.Linear(37, 53), nn.Linear(53, 5)
+
+        def forward(self, batch):
+            return self.l2(torch.tanh(self.l1(batch["x"])))
+
+        def compute_loss(self, y, batch, sync_free=False):
+            return ((y - batch["t"]) ** 2).sum(), {}
+
+    torch.manual_seed(seed)
+    a, b = Net().cuda(), Net().cuda()
+    b.load_state_dict(a.state_dict())
+    eng = TrainEngine(a, lr=1e-2, weight_decay=1e-4, clip=1.0)
+    opt = torch.optim.Adam(b.parameters(), lr=1e-2, weight_decay=1e-4)
+    g = torch.Generator().manual_seed(seed)
+    for _ in range(3):
+        batch = {"x": torch.randn(64, 37, generator=g).cuda() * 3, "t": torch.randn(64, 5, generator=g).cuda()}
+        eng.step(batch)
+        opt.zero_grad()
+        b.compute_loss(b(batch), batch)[0].backward()
+        nn.utils.clip_grad_norm_(b.parameters(), 1.0)
+        opt.step()
+    torch.cuda.synchronize()
+    return {"p_" + n: _err(p, dict(b.named_parameters())[n]) for n, p in a.named_parameters()}
+
+
+CASES["optim_adam_clip"] = (case_optim, _c())
+for _k in ("p_l1.weight", "p_l1.bias", "p_l2.weight", "p_l2.bias"):
+    TOLS[_k] = 1e-4
+
+
 if __name__ == "__main__":
     name = sys.argv[1]
     errs = run_case(name)

@@ -1,0 +1,128 @@
+"""CPU-only checks of the host side: the C-ABI library loads and exports every symbol include/m3t_b200.h declares (no
+compute calls), the module mirrors carry the reference's state_dict contract, the product never imports the oracle,
+and the data-parallel gradient reduction is correct under gloo with world_size 2."""
+import argparse
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_abi_symbols_exported():
+    from m3t_b200 import lib as L
+    h = L.load()
+    syms = L.header_symbols()
+    assert len(syms) >= 30
+    missing = [s for s in syms if not hasattr(h, s)]
+    assert not missing, missing
+    assert h.m3t_abi_version() == 1
+
+
+def test_header_cites_reference():
+    txt = open(os.path.join(ROOT, "include", "m3t_b200.h")).read()
+    assert len(re.findall(r"models/[a-z_]+\.py:\d+", txt)) >= 15
+
+
+@pytest.mark.parametrize("name", ["gru_audio", "gru_scorer", "gru_nohead", "attfusion", "tcn", "resnet_trunk_eval",
+                                  "va3dresnet_eval", "vggm_split3_eval", "av_resnet_attention_eval",
+                                  "av_v2psplit_attention_eval"])
+def test_state_dict_contract(name):
+    """Same keys and shapes as the reference module the fixture was generated from (strict load both ways)."""
+    from oracle.ref_torch import synth_state_dict
+    from tests.golden_util import load
+    fx = load(name)
+    kind = fx["kind"]
+    if kind == "GRU":
+        from m3t_b200.models.rnn import GRU
+        m = GRU(**fx["ctor"])
+    elif kind == "AttFusion":
+        from m3t_b200.models.att_fusion import AttFusion
+        m = AttFusion(**fx["ctor"])
+    elif kind == "TemporalConvNet":
+        from m3t_b200.models.tcn import TemporalConvNet
+        m = TemporalConvNet(**fx["ctor"])
+    elif kind == "ResNet":
+        from m3t_b200.models.resnet import BasicBlock, ResNet
+        m = ResNet(BasicBlock, [2, 2, 2, 2], 512, zero_init_residual=True, agg_mode="ap", fmap_out_size=3)
+    elif kind == "VA_3DResNet":
+        from m3t_b200.models.backbone import VA_3DResNet
+        m = VA_3DResNet(**fx["ctor"])
+    elif kind == "VA_3DVGGM_Split":
+        from m3t_b200.models.vggm import VA_3DVGGM_Split
+        m = VA_3DVGGM_Split(**fx["ctor"])
+    else:
+        from m3t_b200.models.model import AffWild2VA
+        m = AffWild2VA(argparse.Namespace(**fx["hparams"]))
+    assert {k: tuple(v.shape) for k, v in m.state_dict().items()} == fx["spec"]
+    m.load_state_dict(synth_state_dict(fx["spec"], fx["seed"]), strict=True)
+
+
+def test_reference_init_distributions():
+    """zero_init_residual zeroes bn2.weight; GRU biases are zero and W_hh blocks orthogonal (models/rnn.py:57-69)."""
+    from m3t_b200.models.backbone import VA_3DResNet
+    m = VA_3DResNet(nClasses=9, nFCs=2, frameLen=4, resnet_ver="v1")
+    assert float(m.resnet.layer1[0].bn2.weight.abs().max()) == 0.0
+    assert float(m.resnet.layer1[0].bn1.weight.min()) == 1.0
+    w = m.gru.gru.weight_hh_l0[:512]
+    assert torch.allclose(w @ w.t(), torch.eye(512), atol=1e-4)
+    assert float(m.gru.gru.bias_ih_l0.abs().max()) == 0.0
+    c = m.c3d[0].weight
+    assert abs(float(c.std()) - (2.0 / (5 * 7 * 7 * 64)) ** 0.5) < 2e-3
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "m3f.pytorch_b200")
+    for dp, _, fns in os.walk(pkg):
+        for fn in fns:
+            if fn.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dp, fn)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", txt, flags=re.M), fn
+
+
+def test_ops_fail_loudly_without_gpu():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from m3t_b200.models.rnn import GRU
+    m = GRU(200, 256, 1, 2)
+    with pytest.raises(Exception):
+        m(torch.randn(1, 3, 200))
+
+
+def test_stem_index_maps():
+    from m3t_b200 import ops
+    idx = ops.stem_s2d_index("cpu")
+    valid = idx[idx >= 0]
+    assert idx.numel() == 80 * 16 and valid.numel() == 3 * 5 * 7 * 7 and valid.unique().numel() == valid.numel()
+    v = ops.vggm_s2d_index("cpu")
+    vv = v[v >= 0]
+    assert v.numel() == 12 * 16 and vv.numel() == 81 and vv.unique().numel() == 81
+
+
+def test_logmel_oracle_vs_torchaudio():
+    ta = pytest.importorskip("torchaudio")
+    import numpy as np
+    from oracle import melspec as OM
+    from m3t_b200.process.extract_melspec import mel_filterbank
+    assert np.abs(mel_filterbank() - OM.mel_filters()).max() < 1e-6
+    fps = 30.0
+    hop = int(1 / 3 * 1 / fps * 16000)
+    y = torch.randn(32000, generator=torch.Generator().manual_seed(0)) * 0.1
+    ms = ta.transforms.MelSpectrogram(16000, n_fft=512, win_length=400, hop_length=hop, f_min=0, f_max=8000, n_mels=40,
+                                      power=2.0, norm="slaney", mel_scale="slaney", center=True, pad_mode="constant")
+    ref = ta.transforms.AmplitudeToDB("power", top_db=80)(ms(y)).t().numpy()
+    assert np.abs(ref - OM.logmel(y.numpy(), fps)).max() < 1e-3
+
+
+def test_data_parallel_gradient_allreduce_gloo():
+    """world_size 2 on CPU/gloo: after TrainEngine's reduction every rank holds the mean of the per-rank gradients."""
+    script = os.path.join(ROOT, "tests", "dp_gloo_worker.py")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29541", script], cwd=ROOT, capture_output=True,
+                       text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.stdout.count("DP_OK") == 2, r.stdout[-2000:]
