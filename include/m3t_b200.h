@@ -189,6 +189,16 @@ int m3t_adam_clip_step(float* p, const float* g, float* m, float* v, long long n
                        float eps, float weight_decay, int step, float max_norm, float grad_scale,
                        const float* gnorm_sq, void* stream);
 
+/* 3x3/pad-1 patches of a 1-channel fp32 image [N][H][W] as bf16 GEMM rows [N*H*W][16] (9 taps + 7 zero columns):
+ * the 1->64 channel stem of the builder-declared audio ResNet composition (BASELINE config 2; no reference symbol,
+ * SURVEY F6) then is one m3t_gemm_bf16 with K = 16. */
+int m3t_patch3x3_c1(const float* x, void* out, int N, int H, int W, void* stream);
+
+/* Hardware probe (debug.cu), not on the product path: out[128][64] = A[shift_rows : shift_rows+128] . B^T with the
+ * K-major SWIZZLE_128B A operand starting at an arbitrary 128-byte row of a TMA-written [256][64] tile;
+ * mode 1 additionally sets the descriptor base_offset to (addr >> 7) & 7. */
+int m3t_debug_rowshift(const void* A, const void* B, float* out, int shift_rows, int mode, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

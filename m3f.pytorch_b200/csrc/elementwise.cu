@@ -308,29 +308,32 @@ __global__ void bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout, cons
 // ------------------------------------------------------------------------------------------------------------
 // Stem tail: out = maxpool_{3x3,s2,p1}( relu(y*scale + shift) ) over (H,W) of [F][H][W][C]; idx = argmax (0..8)
 // ------------------------------------------------------------------------------------------------------------
+template <int K, int S, int PAD>
 __global__ void bn_relu_maxpool_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ scale,
                                        const float* __restrict__ shift, __nv_bfloat16* __restrict__ out,
-                                       uint8_t* __restrict__ idx, int F, int H, int W, int C, int K, int S, int PAD) {
+                                       uint8_t* __restrict__ idx, int F, int H, int W, int C, int cg_shift) {
+  // index math in 32 bits (the host checks the element counts fit); C/8 is a power of two on this path
   const int P = (H + 2 * PAD - K) / S + 1, Q = (W + 2 * PAD - K) / S + 1;
-  const int cgs = C / 8;
-  const long long total = (long long)F * P * Q * cgs;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int cg = (int)(i % cgs);
-    long long r = i / cgs;
-    const int q = (int)(r % Q);
-    r /= Q;
-    const int p = (int)(r % P);
-    const int f = (int)(r / P);
+  const unsigned cgs = (unsigned)C / 8;
+  const unsigned total = (unsigned)F * P * Q * cgs;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int cg = (int)(i & (cgs - 1));
+    unsigned r = i >> cg_shift;
+    const int q = (int)(r % (unsigned)Q);
+    r /= (unsigned)Q;
+    const int p = (int)(r % (unsigned)P);
+    const int f = (int)(r / (unsigned)P);
     float s[8], b[8], best[8];
     int bi[8];
     load8f(scale + cg * 8, s);
     load8f(shift + cg * 8, b);
 #pragma unroll
     for (int j = 0; j < 8; ++j) { best[j] = -INFINITY; bi[j] = 0; }
+#pragma unroll
     for (int kh = 0; kh < K; ++kh) {
       const int h = S * p - PAD + kh;
       if (h < 0 || h >= H) continue;
+#pragma unroll
       for (int kw = 0; kw < K; ++kw) {
         const int w = S * q - PAD + kw;
         if (w < 0 || w >= W) continue;
@@ -355,13 +358,12 @@ __global__ void bn_relu_maxpool_kernel(const __nv_bfloat16* __restrict__ y, cons
 
 // Backward of the stem tail.  dz[f][h][w][c] = relu'(a) * sum_{windows (p,q) containing (h,w) with argmax == (h,w)}
 // dout[f][p][q][c];  MODE 0: accumulate (sum dz, sum dz*xhat) ;  MODE 1: write dy = scale*(dz - s0/n - xhat*s1/n).
-template <int MODE>
+template <int MODE, int K, int S, int PAD>
 __global__ void __launch_bounds__(256, 2) maxpool_bn_bwd_kernel(const __nv_bfloat16* __restrict__ dout, const uint8_t* __restrict__ idx,
                                       const __nv_bfloat16* __restrict__ y, const float* __restrict__ mean,
                                       const float* __restrict__ invstd, const float* __restrict__ scale,
                                       const float* __restrict__ shift, float* __restrict__ sums, float inv_count,
-                                      __nv_bfloat16* __restrict__ dy, int F, int H, int W, int C, int K, int S,
-                                      int PAD) {
+                                      __nv_bfloat16* __restrict__ dy, int F, int H, int W, int C, int cg_shift) {
   const int P = (H + 2 * PAD - K) / S + 1, Q = (W + 2 * PAD - K) / S + 1;
   const int cgs = C / 8;
   extern __shared__ float sh[];  // MODE 0: [2][C]
@@ -381,14 +383,13 @@ __global__ void __launch_bounds__(256, 2) maxpool_bn_bwd_kernel(const __nv_bfloa
   }
 #pragma unroll
   for (int j = 0; j < 8; ++j) a0[j] = a1[j] = 0.f;
-  const long long total = (long long)F * H * W * cgs;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    long long r = i / cgs;
-    const int w = (int)(r % W);
-    r /= W;
-    const int h = (int)(r % H);
-    const int f = (int)(r / H);
+  const unsigned total = (unsigned)F * H * W * cgs;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    unsigned r = i >> cg_shift;
+    const int w = (int)(r % (unsigned)W);
+    r /= (unsigned)W;
+    const int h = (int)(r % (unsigned)H);
+    const int f = (int)(r / (unsigned)H);
     float yy[8], dz[8];
     const uint4 yraw = __ldg(reinterpret_cast<const uint4*>(y) + i);
 #pragma unroll
@@ -408,7 +409,7 @@ __global__ void __launch_bounds__(256, 2) maxpool_bn_bwd_kernel(const __nv_bfloa
         const int p = p_lo + a, q = q_lo + bq;
         const bool ok = p <= p_hi && q <= q_hi;
         const int pp = ok ? p : p_lo, qq = ok ? q : q_lo;
-        const long long o = (((long long)f * P + min(pp, P - 1)) * Q + min(qq, Q - 1)) * cgs + cg;
+        const unsigned o = ((((unsigned)f * P + min(pp, P - 1)) * Q + min(qq, Q - 1)) << cg_shift) + cg;
         me[a * 2 + bq] = ok ? (h - (S * p - PAD)) * K + (w - (S * q - PAD)) : -1;
         pk[a * 2 + bq] = __ldg(reinterpret_cast<const uint2*>(idx) + o);
         dv[a * 2 + bq] = __ldg(reinterpret_cast<const uint4*>(dout) + o);
@@ -692,6 +693,35 @@ __global__ void relu_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv
   }
 }
 
+// 3x3 / pad 1 patches of a single-channel image as GEMM rows: out[(n*H + h)*W + w][kh*3 + kw] (9 taps, zero padded
+// to 16 columns) in bf16.  Feeds the 1-channel stem of the audio ResNet composition (BASELINE config 2).
+__global__ void patch3x3_c1_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int N, int H, int W) {
+  const long long total = (long long)N * H * W;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int w = (int)(i % W);
+    const long long r = i / W;
+    const int h = (int)(r % H);
+    const long long n = r / H;
+    float f[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) f[j] = 0.f;
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const int hh = h + kh - 1, ww = w + kw - 1;
+        if (hh >= 0 && hh < H && ww >= 0 && ww < W) f[kh * 3 + kw] = __ldg(x + (n * H + hh) * W + ww);
+      }
+    float lo[8], hi[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { lo[j] = f[j]; hi[j] = f[8 + j]; }
+    uint4* o = reinterpret_cast<uint4*>(out + i * 16);
+    o[0] = pack8(lo);
+    o[1] = pack8(hi);
+  }
+}
+
 }  // namespace m3t
 
 using namespace m3t;
@@ -782,33 +812,63 @@ extern "C" int m3t_bn_bwd_apply(const void* dout, const void* out, const void* y
   return launch_status();
 }
 
+static int ilog2_exact(int v) {
+  int s = 0;
+  while ((1 << s) < v) ++s;
+  return (1 << s) == v ? s : -1;
+}
+
 extern "C" int m3t_bn_relu_maxpool(const void* y, const float* scale, const float* shift, void* out, void* idx, int F,
                                    int H, int W, int C, int K, int S, int PAD, void* stream) {
-  if (C % 8 || K < 1 || K > 3 || S < 1) return -1;
+  const int sh = C % 8 ? -1 : ilog2_exact(C / 8);
+  if (sh < 0) return -1;
   const int P = (H + 2 * PAD - K) / S + 1, Q = (W + 2 * PAD - K) / S + 1;
   const long long items = (long long)F * P * Q * (C / 8);
-  bn_relu_maxpool_kernel<<<ew_blocks(items), kEwThreads, 0, ST(stream)>>>(CBF(y), scale, shift, BF(out),
-                                                                          reinterpret_cast<uint8_t*>(idx), F, H, W, C,
-                                                                          K, S, PAD);
+  if ((long long)F * H * W * (C / 8) >= (1LL << 31)) return -6;
+  const int blocks = ew_blocks(items);
+  if (K == 3 && S == 2 && PAD == 1)
+    bn_relu_maxpool_kernel<3, 2, 1><<<blocks, kEwThreads, 0, ST(stream)>>>(CBF(y), scale, shift, BF(out),
+                                                                         reinterpret_cast<uint8_t*>(idx), F, H, W, C, sh);
+  else if (K == 2 && S == 2 && PAD == 0)
+    bn_relu_maxpool_kernel<2, 2, 0><<<blocks, kEwThreads, 0, ST(stream)>>>(CBF(y), scale, shift, BF(out),
+                                                                         reinterpret_cast<uint8_t*>(idx), F, H, W, C, sh);
+  else
+    return -1;
   count_launch();
   return launch_status();
+}
+
+template <int K, int S, int PAD>
+static void launch_pool_bwd(int mode, const void* dout, const void* idx, const void* y, const float* mean,
+                            const float* invstd, const float* scale, const float* shift, float* sums, double count,
+                            void* dy, int F, int H, int W, int C, int sh, int blocks, cudaStream_t st) {
+  if (mode == 0)
+    maxpool_bn_bwd_kernel<0, K, S, PAD><<<blocks, kEwThreads, 2 * C * sizeof(float), st>>>(
+        CBF(dout), reinterpret_cast<const uint8_t*>(idx), CBF(y), mean, invstd, scale, shift, sums, 0.f, nullptr, F, H,
+        W, C, sh);
+  else
+    maxpool_bn_bwd_kernel<1, K, S, PAD><<<blocks, kEwThreads, 0, st>>>(
+        CBF(dout), reinterpret_cast<const uint8_t*>(idx), CBF(y), mean, invstd, scale, shift, sums,
+        (float)(1.0 / count), BF(dy), F, H, W, C, sh);
 }
 
 extern "C" int m3t_maxpool_bn_bwd(int mode, const void* dout, const void* idx, const void* y, const float* mean,
                                   const float* invstd, const float* scale, const float* shift, float* sums,
                                   double count, void* dy, int F, int H, int W, int C, int K, int S, int PAD,
                                   void* stream) {
-  if (C % 8 || kEwThreads % (C / 8) || K < 1 || K > 3 || S < 1) return -1;
+  const int sh = C % 8 ? -1 : ilog2_exact(C / 8);
+  if (sh < 0 || kEwThreads % (C / 8)) return -1;
   const long long items = (long long)F * H * W * (C / 8);
+  if (items >= (1LL << 31)) return -6;
   const int blocks = ew_blocks(items);
-  if (mode == 0)
-    maxpool_bn_bwd_kernel<0><<<blocks, kEwThreads, 2 * C * sizeof(float), ST(stream)>>>(
-        CBF(dout), reinterpret_cast<const uint8_t*>(idx), CBF(y), mean, invstd, scale, shift, sums, 0.f, nullptr, F, H,
-        W, C, K, S, PAD);
+  if (K == 3 && S == 2 && PAD == 1)
+    launch_pool_bwd<3, 2, 1>(mode, dout, idx, y, mean, invstd, scale, shift, sums, count, dy, F, H, W, C, sh, blocks,
+                             ST(stream));
+  else if (K == 2 && S == 2 && PAD == 0)
+    launch_pool_bwd<2, 2, 0>(mode, dout, idx, y, mean, invstd, scale, shift, sums, count, dy, F, H, W, C, sh, blocks,
+                             ST(stream));
   else
-    maxpool_bn_bwd_kernel<1><<<blocks, kEwThreads, 0, ST(stream)>>>(CBF(dout), reinterpret_cast<const uint8_t*>(idx),
-                                                                   CBF(y), mean, invstd, scale, shift, sums,
-                                                                   (float)(1.0 / count), BF(dy), F, H, W, C, K, S, PAD);
+    return -1;
   count_launch();
   return launch_status();
 }
@@ -927,6 +987,12 @@ extern "C" int m3t_colsum_bf16(const void* x, long long ld, long long rows, int 
 extern "C" int m3t_relu_bwd_bf16(const void* dy, const void* out, void* dz, long long n, void* stream) {
   if (n % 8) return -1;
   relu_bwd_kernel<<<ew_blocks(n / 8), kEwThreads, 0, ST(stream)>>>(CBF(dy), CBF(out), BF(dz), n / 8);
+  count_launch();
+  return launch_status();
+}
+
+extern "C" int m3t_patch3x3_c1(const float* x, void* out, int N, int H, int W, void* stream) {
+  patch3x3_c1_kernel<<<ew_blocks((long long)N * H * W), kEwThreads, 0, ST(stream)>>>(x, BF(out), N, H, W);
   count_launch();
   return launch_status();
 }

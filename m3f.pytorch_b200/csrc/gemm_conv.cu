@@ -194,7 +194,10 @@ extern "C" int m3t_conv_wgrad_bf16(const void* x, const void* dy, float* dw_pack
   const int bn = g.Cout <= 64 ? 64 : 128;
   const int ck = conv_ck(g);
   p.tiles_n = ceil_div(g.Cout, bn);
-  const int tiles_m = ceil_div(p.atoms, 128 / ck);
+  // 256-row CTA tiles (two accumulators share every dY stage) whenever there are enough M atoms
+  const int mt = (ck == 64 && p.atoms >= 4 && bn == 64 && !(splits_hint & (1 << 30))) ? 2 : 1;
+  splits_hint &= ~(1 << 30);
+  const int tiles_m = ceil_div(p.atoms, mt * 128 / ck);
   const int kblocks = ceil_div(Mpix, kBlockK);
   int splits = splits_hint;
   if (splits <= 0) {
@@ -216,6 +219,8 @@ extern "C" int m3t_conv_wgrad_bf16(const void* x, const void* dy, float* dw_pack
     if (bn != 64) return -4;
     return launch_umma<64, 1, 4, A_WGRAD, false, true, EPI_ATOMIC_T, 16>(tmA, tmB, p, tiles_m, splits, st);
   }
+  if (bn == 64 && mt == 2)
+    return launch_umma<64, 2, 2, A_WGRAD, false, true, EPI_ATOMIC_T>(tmA, tmB, p, tiles_m, splits, st);
   if (bn == 64) return launch_umma<64, 1, 4, A_WGRAD, false, true, EPI_ATOMIC_T>(tmA, tmB, p, tiles_m, splits, st);
   return launch_umma<128, 1, 3, A_WGRAD, false, true, EPI_ATOMIC_T>(tmA, tmB, p, tiles_m, splits, st);
 }

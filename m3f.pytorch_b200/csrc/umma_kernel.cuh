@@ -118,7 +118,7 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   static_assert(CK == 64 || CK == 16, "CK");
   static_assert(CK == 64 || AKIND != A_TILED, "CK=16 is an implicit-GEMM mode");
   constexpr int TPS = kBlockK / CK;              // filter taps per pipeline stage (1 or 4)
-  constexpr int ATOMS_PER_TILE = 128 / CK;       // A_WGRAD: CK-wide M atoms per 128-row tile (2 or 8)
+  constexpr int ATOMS_PER_TILE = MT * 128 / CK;  // A_WGRAD: CK-wide M atoms per (128*MT)-row CTA tile
   constexpr int ATOM_BYTES = kBlockK * CK * 2;   // A_WGRAD: one atom = 64 pixels x CK channels
   constexpr uint32_t A_SWZ = CK == 64 ? SWZ_128B : SWZ_32B;
   constexpr uint32_t A_SBO = 8 * CK * 2;         // 8 rows of CK bf16
@@ -401,19 +401,22 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
       }
     } else {  // EPI_ATOMIC_T : out_f32[n][m] += acc  (rows of D are contiguous in the output)
-      const long long m = (long long)m_tile * 128 + row;
-      const bool row_ok = m < p.M;
       float* outp = reinterpret_cast<float*>(p.out);
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 16) {
-        uint32_t r[16];
-        tmem_ld16(t_lane + c0, r);
-        tmem_ld_wait();
-        if (row_ok) {
+      for (int mt = 0; mt < MT; ++mt) {
+        const long long m = (long long)(m_tile * MT + mt) * 128 + row;
+        const bool row_ok = m < p.M;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 16) {
+          uint32_t r[16];
+          tmem_ld16(t_lane + mt * BN + c0, r);
+          tmem_ld_wait();
+          if (row_ok) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const int n = n0 + c0 + i;
-            if (n < p.N) atomicAdd(outp + (long long)n * p.ldc + m, __uint_as_float(r[i]));
+            for (int i = 0; i < 16; ++i) {
+              const int n = n0 + c0 + i;
+              if (n < p.N) atomicAdd(outp + (long long)n * p.ldc + m, __uint_as_float(r[i]));
+            }
           }
         }
       }

@@ -584,3 +584,40 @@ class ConvNdBNAct(torch.autograd.Function):
             dx = raw.conv_fprop(dy, wd, g2, tag="dgrad").view(x.shape)
         dcb = torch.zeros_like(fin[0]) if ctx.has_bias else None   # exact: batch-norm removes the bias
         return dx, dw, dcb, sums[1].clone(), sums[0].clone(), None, None, None, None
+
+
+# ------------------------------------------------------------------------------------------------------------
+# 1-channel 3x3 conv + BN + ReLU (stem of the audio ResNet composition, BASELINE config 2)
+# ------------------------------------------------------------------------------------------------------------
+class Conv3x3C1BNReLU(torch.autograd.Function):
+    """relu(BN(conv2d(x, w, padding=1))) for a single input channel: x fp32 [N,H,W] -> CL bf16 [N,H,W,Cout].
+    The 9-tap patches become 16-wide bf16 GEMM rows (m3t_patch3x3_c1) and the conv is one tcgen05 GEMM with K = 16;
+    BN statistics come out of its epilogue."""
+
+    @staticmethod
+    def forward(ctx, x, w, gamma, beta, running_mean, running_var, training):
+        N, H, W = x.shape
+        Cout = w.shape[0]
+        patches = raw.patch3x3_c1(x)
+        wb = _cached(w, "c1", lambda: raw.cast_bf16(w.detach().view(Cout, 9), 16))
+        if not training:
+            ss = raw.bn_fold(gamma.detach(), beta.detach(), running_mean, running_var, None, BN_EPS)
+            out = raw.gemm(patches, wb, scale=ss[0], shift=ss[1], relu=True)
+            return out.view(N, H, W, Cout)
+        stats = torch.zeros((2, Cout), device=x.device, dtype=torch.float32)
+        y = raw.gemm(patches, wb, stats=stats)
+        fin = raw.bn_finalize(stats, y.shape[0], gamma.detach(), beta.detach(), BN_EPS, BN_MOMENTUM, running_mean,
+                              running_var)
+        out = raw.bn_act(y, fin[2], fin[3], relu=True)
+        ctx.save_for_backward(patches, w, y, out, fin)
+        return out.view(N, H, W, Cout)
+
+    @staticmethod
+    def backward(ctx, dout):
+        patches, w, y, out, fin = ctx.saved_tensors
+        d2 = dout.contiguous().view(y.shape)
+        sums, _ = raw.bn_bwd_reduce(d2, out, y, fin[0], fin[1], True, False)
+        dy = raw.bn_bwd_apply(d2, out, y, fin[0], fin[1], fin[2], sums, y.shape[0], True)
+        dwp = raw.gemm(dy, patches, a_mn=True, b_mn=True, out_dtype=torch.float32)     # [Cout, 16]
+        dw = dwp[:, :9].reshape(w.shape)
+        return None, dw, sums[1].clone(), sums[0].clone(), None, None, None

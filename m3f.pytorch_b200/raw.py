@@ -428,3 +428,12 @@ def att_mix_bwd(df, x_a, x_v, s_a, s_v):
     L.check(_lib().m3t_att_mix_bwd(L.ptr(df), L.ptr(x_a), L.ptr(x_v), L.ptr(s_a), L.ptr(s_v), L.ptr(dxa), L.ptr(dxv),
                                    L.ptr(dsa), L.ptr(dsv), L.i64(rows), L.i32(C), L.stream_ptr()), "att_mix_bwd")
     return dxa, dxv, dsa, dsv
+
+
+def patch3x3_c1(x):
+    """fp32 [N,H,W] -> bf16 [N*H*W, 16] (3x3 / pad 1 patches, 9 taps + zero pad)."""
+    N, H, W = x.shape
+    out = torch.empty((N * H * W, 16), device=x.device, dtype=torch.bfloat16)
+    L.check(_lib().m3t_patch3x3_c1(L.ptr(x.contiguous()), L.ptr(out), L.i32(N), L.i32(H), L.i32(W), L.stream_ptr()),
+            "patch3x3_c1")
+    return out

@@ -62,6 +62,20 @@ def rnd(shape, seed, scale=1.0):
     return torch.randn(shape, generator=torch.Generator().manual_seed(seed)) * scale
 
 
+def materialise(gen):
+    """Inputs too large to commit are stored as (kind, shape, seed) recipes (tests/golden_util.py mirrors this)."""
+    out = {}
+    for k, d in gen.items():
+        g = torch.Generator().manual_seed(d["seed"])
+        if d["kind"] == "randn_relu":
+            out[k] = torch.randn(d["shape"], generator=g).relu_()
+        elif d["kind"] == "randint_u8":
+            out[k] = torch.randint(0, 256, d["shape"], generator=g, dtype=torch.uint8)
+        else:
+            raise KeyError(d["kind"])
+    return out
+
+
 def video(B, T, seed):
     return torch.randint(0, 256, (B, 3, T, 112, 112), generator=torch.Generator().manual_seed(seed), dtype=torch.uint8)
 
@@ -118,9 +132,10 @@ def main():
                           fmap_out_size=3)
         spec = load_synth(m, 14)
         m.train(mode == "train")
-        x = rnd((3, 64, 28, 28), 8).relu_().requires_grad_(True)
+        gen = {"x": dict(kind="randn_relu", shape=(16, 64, 28, 28), seed=8)}
+        x = materialise(gen)["x"].requires_grad_(True)
         out, cot, grads = run_with_grads(m, lambda: m(x), {"x": x}, 9)
-        save("resnet_trunk_" + mode, dict(kind="ResNet", mode=mode, seed=14, spec=spec, inputs={"x": x.detach()},
+        save("resnet_trunk_" + mode, dict(kind="ResNet", mode=mode, seed=14, spec=spec, inputs_gen=gen,
                                           out=out, cot=cot, grads=grads))
 
     # ---- VA_3DResNet (config-1 model at reduced T), eval forward and train forward+backward ----
@@ -133,12 +148,16 @@ def main():
         out = m((v.float() - 127.5) / 127.5)
     save("va3dresnet_eval", dict(kind="VA_3DResNet", ctor=ctor, mode="eval", seed=15, spec=spec,
                                  inputs={"video_u8": v}, out=out))
+    ctor = dict(hiddenDim=512, frameLen=8, backend="gru", resnet_ver="v1", nClasses=9, nFCs=2)
+    m = backbone.VA_3DResNet(**ctor)
+    spec = load_synth(m, 15)
     m.train()
-    v = video(2, 4, 11)
+    gen = {"video_u8": dict(kind="randint_u8", shape=(2, 3, 8, 112, 112), seed=11)}
+    v = materialise(gen)["video_u8"]
     x = ((v.float() - 127.5) / 127.5)
     out, cot, grads = run_with_grads(m, lambda: m(x), {}, 12)
     save("va3dresnet_train", dict(kind="VA_3DResNet", ctor=ctor, mode="train", seed=15, spec=spec,
-                                  inputs={"video_u8": v}, out=out, cot=cot, grads=grads))
+                                  inputs_gen=gen, out=out, cot=cot, grads=grads))
 
     # ---- VA_3DVGGM_Split (the AV visual stream model.py really runs), eval ----
     ctor = dict(hiddenDim=512, frameLen=4, backend="gru", split_layer=3, nClasses=-1, nFCs=2, use_mtl=True)
@@ -184,16 +203,22 @@ def main():
             out = m(to_ref_batch(b))
         save("av_resnet_attention_eval", dict(kind="AffWild2VA", hparams=vars(hp), mode="eval", seed=17, spec=spec,
                                               inputs=b, out=out))
+        # training_step on 2 clips x 8 frames (16 frames: BatchNorm statistics over >= 256 samples everywhere)
+        hp_tr = _refload.hparams(modality="audiovisual", fusion_type="attention", backbone="resnet", split_layer=5,
+                                 window=8, loss="ccc_mtl")
+        m = model.AffWild2VA(hp_tr)
+        spec = load_synth(m, 17)
         m.train()
-        m.zero_grad()
+        b = av_batch(2, 8, 19)
         res = m.training_step(to_ref_batch(b), 0)
         loss = res["loss"]
         loss.backward()
         grads = {"param." + n: pack_grad(p.grad) for n, p in m.named_parameters() if p.grad is not None}
         with torch.no_grad():
             out_tr = m(to_ref_batch(b))
-        save("av_resnet_attention_train", dict(kind="AffWild2VA", hparams=vars(hp), mode="train", seed=17, spec=spec,
-                                               inputs=b, out=out_tr, loss=float(loss), grads=grads))
+        save("av_resnet_attention_train", dict(kind="AffWild2VA", hparams=vars(hp_tr), mode="train", seed=17,
+                                               spec=spec, inputs=b, out=out_tr, loss=float(loss.detach()),
+                                               grads=grads))
     finally:
         backbone.VA_3DResNet.forward = orig_fwd
 

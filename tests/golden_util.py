@@ -8,7 +8,18 @@ GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
 def load(name):
-    return torch.load(os.path.join(GOLDEN_DIR, name + ".pt"), weights_only=False)
+    fx = torch.load(os.path.join(GOLDEN_DIR, name + ".pt"), weights_only=False)
+    if "inputs_gen" in fx:      # inputs too large to commit: regenerate from (kind, shape, seed)
+        fx["inputs"] = {}
+        for k, d in fx["inputs_gen"].items():
+            g = torch.Generator().manual_seed(d["seed"])
+            if d["kind"] == "randn_relu":
+                fx["inputs"][k] = torch.randn(d["shape"], generator=g).relu_()
+            elif d["kind"] == "randint_u8":
+                fx["inputs"][k] = torch.randint(0, 256, d["shape"], generator=g, dtype=torch.uint8)
+            else:
+                raise KeyError(d["kind"])
+    return fx
 
 
 def rel_err(y, ref):

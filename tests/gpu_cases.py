@@ -531,7 +531,7 @@ CASES.update({
     "golden_av_v2psplit_attention_eval": (case_golden, _c(name="av_v2psplit_attention_eval")),
 })
 
-TOLS = {"out_ref": 4e-2, "va_ref": 4e-2, "floor": 1.0, "out_emu": 1.5e-2, "loss_ref": 2e-2, "loss_emu": 1e-2,
+TOLS = {"out_ref": 3e-2, "va_ref": 2e-2, "floor": 1.0, "out_emu": 1.5e-2, "loss_ref": 2e-2, "loss_emu": 1e-2,
         "grad_emu": 0.12, "grad_all_l2": 0.05, "dx": 3e-2}
 for _k in ("conv1.weight", "conv2.weight", "bn1.weight", "bn1.bias", "bn2.weight", "bn2.bias", "downsample.0.weight",
            "downsample.1.weight", "downsample.1.bias"):
@@ -727,6 +727,64 @@ def case_optim(seed=0):
 CASES["optim_adam_clip"] = (case_optim, _c())
 for _k in ("p_l1.weight", "p_l1.bias", "p_l2.weight", "p_l2.bias"):
     TOLS[_k] = 1e-4
+
+
+
+def case_rowshift():
+    """Probe: UMMA K-major SW128 operand starting at a non-1024-aligned row of a TMA-written tile (round-2 halo conv).
+    Reports, per shift, the error with base_offset = 0 (m0_*) and base_offset = (addr>>7)&7 (m1_*)."""
+    from m3t_b200 import lib as L
+    g = torch.Generator().manual_seed(0)
+    A = _rnd((256, 64), g)
+    B = _rnd((64, 64), g)
+    Ad, Bd = A.cuda(), B.cuda()
+    errs = {}
+    for shift in (0, 8, 1, 2, 3, 7, 30, 31, 61):
+        ref = A[shift:shift + 128].float() @ B.float().t()
+        for mode in (0, 1):
+            out = torch.zeros((128, 64), device="cuda")
+            L.check(L.load().m3t_debug_rowshift(L.ptr(Ad), L.ptr(Bd), L.ptr(out), L.i32(shift), L.i32(mode),
+                                                L.stream_ptr()), "rowshift")
+            torch.cuda.synchronize()
+            errs["m%d_s%d" % (mode, shift)] = _err(out, ref)
+    return errs
+
+
+CASES["probe_rowshift"] = (case_rowshift, _c())
+
+
+
+def case_audio_resnet(train, seed=0):
+    """BASELINE config 2 composition (audio ResNet over log-Mel windows + TCN head) vs the same composition built
+    from the oracle's functions (bf16-emulated) — there is no reference class for it."""
+    from m3t_b200.models.audio_resnet import AudioResNetTCN
+    from oracle import ref_torch as R
+    torch.manual_seed(seed)
+    m = AudioResNetTCN(dropout=0.0)
+    spec = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    sd = R.synth_state_dict(spec, 41 + seed)
+    m.load_state_dict(sd)
+    m = m.cuda().train(train)
+    g = torch.Generator().manual_seed(seed + 1)
+    B, T = 8, 16
+    audio = torch.randn((B, T, 200), generator=g) * 20 - 40
+    out = m(audio.cuda())
+
+    def oracle(emulate):
+        import contextlib
+        with (R.bf16_emulation() if emulate else contextlib.nullcontext()), torch.no_grad():
+            x = audio.reshape(B * T, 1, 5, 40)
+            h = R.q(R._conv_bn(R.q(x), sd["stem.0.weight"], sd, "stem.1", train, 1, 1).relu())
+            f = R.resnet_trunk(h, sd, "resnet", train=train).view(B, T, 512)
+            f = R.temporal_conv_net(f.transpose(1, 2), sd, "tcn", 2).transpose(1, 2)
+            return R._linear(f, sd["fc.weight"], sd["fc.bias"], keep_f32=True)
+
+    o32, oemu = oracle(False), oracle(True)
+    return {"out_ref": _err(out, o32), "floor": _err(oemu, o32), "out_emu": _err(out, oemu)}
+
+
+CASES["audio_resnet_tcn_eval"] = (case_audio_resnet, _c(train=False))
+CASES["audio_resnet_tcn_train_fwd"] = (case_audio_resnet, _c(train=True))
 
 
 if __name__ == "__main__":
