@@ -1,0 +1,295 @@
+// 3x3 / stride 1 / pad 1 convolution for the 64 -> 64 channel layers (ResNet layer1 fprop and dgrad): persistent,
+// filter-resident, halo-tile implicit GEMM.
+//
+// Why: with one im2col load per filter tap (umma_kernel.cuh) a 128x64 tile moves 9 x (16 KB + 8 KB) through L2 for
+// 4.7 MMAC - 192 B/cycle/SM demanded against ~42 B/cycle/SM of L2->SM bandwidth, i.e. L2-bound at ~20 % of the MMA
+// rate (measured 251 TFLOP/s).  Here
+//   * the 9 filter taps (9 x [64 co][64 ci] bf16 = 72 KB) are loaded ONCE per CTA and stay in shared memory;
+//   * per tile ONE tiled-TMA box brings the input halo: (TR+3) rows x (W+2) columns x 64 channels of one image, with
+//     the zero padding produced by TMA out-of-bounds fill (coordinates start at -1);
+//   * an output tile is 128 consecutive positions of the W-padded row-major pixel space, so filter tap (r,s) is the
+//     SAME smem tile read from row offset r*(W+2)+s: the UMMA descriptor start address simply moves by that many
+//     128-byte rows (the SWIZZLE_128B pattern is a function of the absolute smem address, so any row offset is
+//     legal with base_offset = 0 - verified on hardware by m3t_debug_rowshift);
+//   * CTAs are persistent (one per SM) with a double-buffered TMEM accumulator, so the epilogue of tile i overlaps
+//     the MMAs of tile i+1; BatchNorm statistics are accumulated across all tiles of a CTA and flushed once.
+// L2->SM traffic per tile drops from 216 KB to 26 KB; 2 of every W+2 positions (and the tail of the last row block)
+// are computed and discarded.
+#include "../../include/m3t_b200.h"
+#include "common.cuh"
+#include "tmap.cuh"
+#include "ptx.cuh"
+
+namespace m3t {
+
+constexpr int kHaloThreads = 192;
+constexpr int kHaloStages = 4;
+
+struct HaloParams {
+  int F, H, W;     // images, height, width; Cin = Cout = 64
+  int Wp;          // W + 2
+  int TR;          // output rows per tile (TR * Wp <= 128)
+  int tiles_per_img, num_tiles;
+  int a_stage;     // bytes per A stage (1024-aligned)
+  int box_bytes;   // bytes one halo box delivers
+  __nv_bfloat16* y;
+  const float* scale;
+  const float* shift;
+  const __nv_bfloat16* residual;
+  int relu;
+  float* stats;    // [2][64] or null
+};
+
+template <int N>
+__device__ __forceinline__ void halo_butterfly(float (&v)[32], uint32_t lane) {
+  if constexpr (N >= 1) {
+    const bool upper = (lane & N) != 0;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      const float send = upper ? v[i] : v[i + N];
+      const float keep = upper ? v[i + N] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, N);
+    }
+    halo_butterfly<N / 2>(v, lane);
+  }
+}
+template <>
+__device__ __forceinline__ void halo_butterfly<0>(float (&)[32], uint32_t) {}
+
+__global__ void __launch_bounds__(kHaloThreads, 1)
+conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
+                    const HaloParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sW = smem;                                   // 9 x 8 KB
+  uint8_t* sA = smem + 9 * 8192;                        // kHaloStages x a_stage
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sA + kHaloStages * p.a_stage);
+  uint64_t* empty_bar = full_bar + kHaloStages;
+  uint64_t* w_bar = empty_bar + kHaloStages;
+  uint64_t* tmem_full = w_bar + 1;                      // [2]
+  uint64_t* tmem_empty = tmem_full + 2;                 // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  float* stat_smem = reinterpret_cast<float*>(tmem_slot + 2);   // [4 warps][2][64]
+
+  const int warp = threadIdx.x >> 5;
+  const uint32_t lane = lane_id();
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmW);
+    for (int i = 0; i < kHaloStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    mbar_init(w_bar, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 128);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 128);
+  for (int i = threadIdx.x; i < 4 * 2 * 64; i += kHaloThreads) stat_smem[i] = 0.f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(w_bar, 9 * 8192);
+      for (int t = 0; t < 9; ++t) tma_load_2d(&tmW, w_bar, sW + t * 8192, t * 64, 0);
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+        const int stage = it % kHaloStages;
+        const uint32_t phase = (it / kHaloStages) & 1;
+        mbar_wait(&empty_bar[stage], phase ^ 1, 400 + stage);
+        const int f = tile / p.tiles_per_img;
+        const int h0 = (tile - f * p.tiles_per_img) * p.TR;
+        mbar_arrive_expect_tx(&full_bar[stage], p.box_bytes);
+        tma_load_4d(&tmX, &full_bar[stage], sA + stage * p.a_stage, 0, -1, h0 - 1, f);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, 64, 0, 0);
+      mbar_wait(w_bar, 0, 410);
+      const uint32_t w_base = smem_u32(sW);
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+        const int stage = it % kHaloStages;
+        const uint32_t phase = (it / kHaloStages) & 1;
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1, 420 + acc);
+        mbar_wait(&full_bar[stage], phase, 430 + stage);
+        tc_fence_after();
+        const uint32_t a_base = smem_u32(sA + stage * p.a_stage);
+#pragma unroll 1
+        for (int r = 0; r < 3; ++r) {
+#pragma unroll
+          for (int s = 0; s < 3; ++s) {
+            const uint32_t a_tap = a_base + (uint32_t)(r * p.Wp + s) * 128u;
+            const uint32_t b_tap = w_base + (uint32_t)(r * 3 + s) * 8192u;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t adesc = make_smem_desc(a_tap + k * 32, 16, 1024, SWZ_128B);
+              const uint64_t bdesc = make_smem_desc(b_tap + k * 32, 16, 1024, SWZ_128B);
+              umma_bf16(tmem_base + acc * 64, adesc, bdesc, idesc, (r | s | k) != 0 ? 1u : 0u);
+            }
+          }
+        }
+        umma_commit(&empty_bar[stage]);
+        umma_commit(&tmem_full[acc]);
+      }
+    }
+  } else {
+    const int quad = warp & 3;
+    const int row = quad * 32 + (int)lane;
+    const int hh = row / p.Wp, ww = row - hh * p.Wp;
+    const bool want_stats = p.stats != nullptr;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const int f = tile / p.tiles_per_img;
+      const int h0 = (tile - f * p.tiles_per_img) * p.TR;
+      const bool ok = hh < p.TR && ww < p.W && (h0 + hh) < p.H;
+      const long long pix = ((long long)f * p.H + h0 + hh) * p.W + ww;
+      mbar_wait(&tmem_full[acc], acc_phase, 440 + acc);
+      tc_fence_after();
+      const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * 64;
+#pragma unroll 1
+      for (int c0 = 0; c0 < 64; c0 += 32) {
+        float v[32];
+        {
+          uint32_t r[16];
+          tmem_ld16(t_lane + c0, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+          tmem_ld16(t_lane + c0 + 16, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[16 + i] = __uint_as_float(r[i]);
+        }
+        if (c0 == 32) {   // accumulator fully read: hand the TMEM buffer back to the MMA warp
+          tc_fence_before();
+          mbar_arrive(&tmem_empty[acc]);
+        }
+        if (ok) {
+          float o[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            float x = v[i];
+            if (p.scale) x *= __ldg(p.scale + c0 + i);
+            if (p.shift) x += __ldg(p.shift + c0 + i);
+            o[i] = x;
+          }
+          if (p.residual) {
+            const uint4* rp = reinterpret_cast<const uint4*>(p.residual + pix * 64 + c0);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const uint4 rv = __ldg(rp + g);
+              const uint32_t w4[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                o[g * 8 + 2 * j] += bf16lo(w4[j]);
+                o[g * 8 + 2 * j + 1] += bf16hi(w4[j]);
+              }
+            }
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = fmaxf(o[i], 0.f);
+          }
+          uint4* op = reinterpret_cast<uint4*>(p.y + pix * 64 + c0);
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+            op[g] = make_uint4(pack_bf16x2(o[8 * g], o[8 * g + 1]), pack_bf16x2(o[8 * g + 2], o[8 * g + 3]),
+                               pack_bf16x2(o[8 * g + 4], o[8 * g + 5]), pack_bf16x2(o[8 * g + 6], o[8 * g + 7]));
+        }
+        if (want_stats) {
+          float s1[32], s2[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float x = ok ? v[i] : 0.f;
+            s1[i] = x;
+            s2[i] = x * x;
+          }
+          halo_butterfly<16>(s1, lane);
+          halo_butterfly<16>(s2, lane);
+          stat_smem[(quad * 2 + 0) * 64 + c0 + lane] += s1[0];
+          stat_smem[(quad * 2 + 1) * 64 + c0 + lane] += s2[0];
+        }
+      }
+    }
+    if (want_stats) {
+      named_bar_sync(1, 128);
+      for (int i = threadIdx.x - 64; i < 2 * 64; i += 128) {
+        const int which = i / 64, c = i - which * 64;
+        const float s = stat_smem[(0 * 2 + which) * 64 + c] + stat_smem[(1 * 2 + which) * 64 + c] +
+                        stat_smem[(2 * 2 + which) * 64 + c] + stat_smem[(3 * 2 + which) * 64 + c];
+        atomicAdd(p.stats + which * 64 + c, s);
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 128);
+  }
+}
+
+}  // namespace m3t
+
+using namespace m3t;
+
+// x: bf16 [F][H][W][64], w_packed: bf16 [64][9*64] (tap-major), y: bf16 [F][H][W][64]
+extern "C" int m3t_conv3x3_c64_halo(const void* x, const void* w_packed, void* y, int F, int H, int W,
+                                    const float* scale, const float* shift, const void* residual, int relu,
+                                    float* stats, void* stream) {
+  if (F <= 0 || H <= 0 || W <= 0 || W + 2 > 64) return -1;
+  HaloParams p;
+  memset(&p, 0, sizeof(p));
+  p.F = F; p.H = H; p.W = W;
+  p.Wp = W + 2;
+  p.TR = 128 / p.Wp;
+  if (p.TR < 1) return -1;
+  if (p.TR > H) p.TR = H;
+  p.tiles_per_img = (H + p.TR - 1) / p.TR;
+  p.num_tiles = F * p.tiles_per_img;
+  // rows of the halo box: enough for the largest row offset (2*Wp + 2) plus 128 positions
+  const int box_rows = (2 * p.Wp + 2 + 128 + p.Wp - 1) / p.Wp;
+  if (box_rows > 256 || p.Wp > 256) return -1;
+  p.box_bytes = box_rows * p.Wp * 128;
+  p.a_stage = (p.box_bytes + 1023) / 1024 * 1024;
+  p.y = reinterpret_cast<__nv_bfloat16*>(y);
+  p.scale = scale; p.shift = shift;
+  p.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
+  p.relu = relu; p.stats = stats;
+  CUtensorMap tmX, tmW;
+  uint64_t dims[4] = {64, (uint64_t)W, (uint64_t)H, (uint64_t)F};
+  uint64_t strides[3] = {128, (uint64_t)W * 128, (uint64_t)H * W * 128};
+  uint32_t box[4] = {64, (uint32_t)p.Wp, (uint32_t)box_rows, 1};
+  int rc = make_tmap_tiled_bf16(&tmX, x, 4, dims, strides, box, 128);
+  if (rc) return rc;
+  rc = make_tmap_2d_bf16(&tmW, w_packed, 576, 64, 576, 64, 64);
+  if (rc) return rc;
+  const int smem = 9 * 8192 + kHaloStages * p.a_stage + (2 * kHaloStages + 5) * 8 + 16 + 4 * 2 * 64 * 4 + 1024;
+  if (smem > 227 * 1024) return -7;
+  static bool attr_done = false;
+  if (!attr_done) {
+    if (cudaFuncSetAttribute(conv3x3_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) !=
+        cudaSuccess)
+      return -20;
+    attr_done = true;
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = p.num_tiles < sms ? p.num_tiles : sms;
+  conv3x3_halo_kernel<<<grid, kHaloThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(tmX, tmW, p);
+  count_launch();
+  return launch_status();
+}

@@ -6,6 +6,8 @@ are sequences of C-ABI calls (raw.py -> libm3t_b200.so).  Activations between un
 Nothing here falls back to stock PyTorch kernels for the ops the library implements; torch is used for memory
 (torch.empty / zeros on the current stream), autograd bookkeeping and tiny parameter-side glue.
 """
+import weakref
+
 import torch
 
 from . import raw
@@ -17,15 +19,10 @@ _pack_cache = {}
 
 
 def _cached(key_tensor, tag, fn):
-    """Cache derived (packed / bf16) copies of a parameter until it is modified in place (optimizer step)."""
-    key = (key_tensor.data_ptr(), tag)
-    ver = key_tensor._version
-    hit = _pack_cache.get(key)
-    if hit is not None and hit[0] == ver and hit[1] == tuple(key_tensor.shape):
-        return hit[2]
-    val = fn()
-    _pack_cache[key] = (ver, tuple(key_tensor.shape), val)
-    return val
+    """Cache derived (packed / bf16) copies of a parameter until it is modified in place (optimizer step).
+    Entries are keyed by object identity and validated through a weak reference (an address can be recycled by a
+    different tensor), the in-place version counter and the storage pointer (`p.data = ...` re-seats storage)."""
+    return _cached_multi((key_tensor,), tag, fn)
 
 
 def clear_caches():
@@ -362,8 +359,14 @@ class GRULayerFn(torch.autograd.Function):
             t = torch.stack((w_hh.detach().t().contiguous(), w_hh_r.detach().t().contiguous()))
             return raw.cast_bf16(t.view(2 * H, 3 * H)).view(2, H, 3 * H)
 
+        def make_ih():
+            buf = torch.empty((6 * H, (I + 7) // 8 * 8), device=dout.device, dtype=torch.bfloat16)
+            raw.cast_bf16(w_ih.detach(), out=buf[:3 * H])
+            raw.cast_bf16(w_ih_r.detach(), out=buf[3 * H:])
+            return buf
+
         whht = _cached_multi((w_hh, w_hh_r), "gru_hht", make_hht)
-        wih = _cached_multi((w_ih, w_ih_r), "gru_ih", lambda: None)
+        wih = _cached_multi((w_ih, w_ih_r), "gru_ih", make_ih)
         dgi, dgh, hprev = raw.gru_bwd(dout.contiguous(), out, saved, whht, B, T, H)
         dx = None
         if ctx.needs_input_grad[0]:
@@ -381,15 +384,18 @@ class GRULayerFn(torch.autograd.Function):
 
 
 def _cached_multi(tensors, tag, fn):
-    key = (tuple(t.data_ptr() for t in tensors), tag)
-    ver = tuple(t._version for t in tensors)
+    key = (tuple(id(t) for t in tensors), tag)
+    ver = tuple((t._version, t.data_ptr()) for t in tensors)
     hit = _pack_cache.get(key)
-    if hit is not None and hit[0] == ver:
+    if hit is not None and hit[0] == ver and all(r() is t for r, t in zip(hit[1], tensors)):
         return hit[2]
     val = fn()
     if val is None:
         raise RuntimeError("derived weight cache miss for %s" % tag)
-    _pack_cache[key] = (ver, None, val)
+    if len(_pack_cache) > 4096:          # dead entries of discarded models
+        for k in [k for k, v in _pack_cache.items() if any(r() is None for r in v[1])]:
+            del _pack_cache[k]
+    _pack_cache[key] = (ver, tuple(weakref.ref(t) for t in tensors), val)
     return val
 
 
