@@ -48,7 +48,7 @@ int m3t_gemm_bf16(const void* A, long long lda, int a_mn, const void* B, long lo
  *   w_packed bf16 [Cout][kd*kh*kw*Cin]                 (tap-major, channel-minor)
  *   y        bf16 channels-last [N][Z][P][Q][Cout]
  *   y = act( conv(x,w) * scale[c] + shift[c] + residual ), all optional; stats as in m3t_gemm_bf16.
- *   tile_hint: 0 = auto; bit0 force 128-row tiles, bit1 force 256-row tiles, bit2 allow 256-column tiles.
+ *   tile_hint: 0 = auto; bit0 force 128-row tiles, bit1 force 256-row tiles, bit3 force 128-column tiles.
  * Replaces: nn.Conv2d 3x3 / 1x1 in BasicBlock (models/resnet.py:7-15,24-27,40-54,98-101), nn.Conv3d 3x3x3 in
  * VA_3DVGGM(_Split) (models/backbone.py:73-103,179-195,243-271), weight-normed dilated causal nn.Conv1d in
  * TemporalBlock (models/tcn.py:19-33) and Conv1d k5 in tcn_simple (models/backbone.py:214-231), with the
@@ -56,6 +56,23 @@ int m3t_gemm_bf16(const void* A, long long lda, int a_mn, const void* B, long lo
 int m3t_conv_fprop_bf16(const void* x, const void* w_packed, void* y, const int* geom, const float* scale,
                         const float* shift, const void* residual, int relu, float* stats, int tile_hint,
                         void* stream);
+
+/* 3x3 / stride 1 / pad 1 convolution for Cin = Cout = 64 (ResNet layer1 fprop; its dgrad with the flipped filter):
+ * persistent CTAs, the 9 filter taps resident in shared memory, ONE halo box per 128-position tile (zero padding by
+ * TMA out-of-bounds fill), the taps read as row-shifted views of that box, double-buffered TMEM accumulators.
+ * Same epilogue contract as m3t_conv_fprop_bf16.  x, y: bf16 [F][H][W][64]; w_packed: bf16 [64][9*64].
+ * Replaces the same call sites as m3t_conv_fprop_bf16 for models/resnet.py layer1 (4 convs of 64->64 at 28x28). */
+int m3t_conv3x3_c64_halo(const void* x, const void* w_packed, void* y, int F, int H, int W, const float* scale,
+                         const float* shift, const void* residual, int relu, float* stats, void* stream);
+
+/* Halo-tile weight gradients for the 64-channel layers (wgrad_halo.cu): persistent CTAs, one activation halo box and
+ * one dY box per K-block of whole image rows, filter taps as row-shifted MN-major views, accumulators resident in
+ * TMEM, one atomic flush.  dw_packed is fp32, caller-zeroed, same packed layout as m3t_conv_wgrad_bf16.
+ *   m3t_wgrad3x3_c64_halo : 3x3/s1/p1, 64->64, x/dy bf16 [F][H][W][64], dw_packed [64][9*64]   (ResNet layer1)
+ *   m3t_wgrad_stem_halo   : stem over the W-unrolled s2d image xs [B][T][H2][W2][64], dy [B*T][H2][W2][64],
+ *                           dw_packed [64][20*64] with tap = kt*4 + jh                         (models/backbone.py:328) */
+int m3t_wgrad3x3_c64_halo(const void* x, const void* dy, float* dw_packed, int F, int H, int W, void* stream);
+int m3t_wgrad_stem_halo(const void* xs, const void* dy, float* dw_packed, int B, int T, int H2, int W2, void* stream);
 
 /* Convolution weight gradient: dw_packed[Cout][taps*Cin] (fp32) += sum over output pixels of dy (x) patch(x).
  * The caller zero-fills dw_packed; split-K partial tiles are combined with fp32 atomics.

@@ -147,6 +147,11 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     const int row = quad * 32 + (int)lane;
     const int hh = row / p.Wp, ww = row - hh * p.Wp;
     const bool want_stats = p.stats != nullptr;
+    // BatchNorm statistics: every thread owns one accumulator row, so it keeps running per-column sums of ITS rows
+    // over all tiles of this persistent CTA (2 x 64 registers); rows are reduced across lanes once, at the end.
+    float st1[64], st2[64];
+#pragma unroll
+    for (int i = 0; i < 64; ++i) st1[i] = st2[i] = 0.f;
     int it = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
@@ -158,7 +163,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
       mbar_wait(&tmem_full[acc], acc_phase, 440 + acc);
       tc_fence_after();
       const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * 64;
-#pragma unroll 1
+#pragma unroll
       for (int c0 = 0; c0 < 64; c0 += 32) {
         float v[32];
         {
@@ -208,22 +213,29 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
             op[g] = make_uint4(pack_bf16x2(o[8 * g], o[8 * g + 1]), pack_bf16x2(o[8 * g + 2], o[8 * g + 3]),
                                pack_bf16x2(o[8 * g + 4], o[8 * g + 5]), pack_bf16x2(o[8 * g + 6], o[8 * g + 7]));
         }
-        if (want_stats) {
-          float s1[32], s2[32];
+        if (want_stats && ok) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
-            const float x = ok ? v[i] : 0.f;
-            s1[i] = x;
-            s2[i] = x * x;
+            st1[c0 + i] += v[i];
+            st2[c0 + i] = fmaf(v[i], v[i], st2[c0 + i]);
           }
-          halo_butterfly<16>(s1, lane);
-          halo_butterfly<16>(s2, lane);
-          stat_smem[(quad * 2 + 0) * 64 + c0 + lane] += s1[0];
-          stat_smem[(quad * 2 + 1) * 64 + c0 + lane] += s2[0];
         }
       }
     }
     if (want_stats) {
+#pragma unroll
+      for (int c0 = 0; c0 < 64; c0 += 32) {
+        float s1[32], s2[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          s1[i] = st1[c0 + i];
+          s2[i] = st2[c0 + i];
+        }
+        halo_butterfly<16>(s1, lane);
+        halo_butterfly<16>(s2, lane);
+        stat_smem[(quad * 2 + 0) * 64 + c0 + lane] = s1[0];
+        stat_smem[(quad * 2 + 1) * 64 + c0 + lane] = s2[0];
+      }
       named_bar_sync(1, 128);
       for (int i = threadIdx.x - 64; i < 2 * 64; i += 128) {
         const int which = i / 64, c = i - which * 64;

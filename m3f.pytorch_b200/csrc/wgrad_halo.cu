@@ -1,0 +1,256 @@
+// Weight gradient of the 64-channel convolutions as a persistent, halo-tile tcgen05 kernel:
+//   * ResNet layer1  3x3/s1/p1  64 -> 64  over [F][H][W][64]                      (9 taps, one launch)
+//   * the stem over the W-unrolled space-to-depth image  (5,4,1) x 64 -> 64        (5 launches: one per temporal tap,
+//     4 vertical taps each)
+// The generic wgrad (umma_kernel.cuh, A_WGRAD) re-reads a 64-pixel activation tile from L2 once per filter tap: 200 KB
+// of L2->SM traffic per 64 pixels for the stem, i.e. L2-bound at ~150 TFLOP/s.  Here a K-block is TR whole image rows;
+// ONE TMA box brings the activation halo (TR+3 rows, zero padding by out-of-bounds fill) and ONE box brings dY in the
+// same W-padded pixel space (its padding columns are zero-filled, so they contribute nothing); every filter tap is a
+// row-shifted view of the activation box used as an MN-major A operand, and two taps 64 channels wide form one
+// 128-row operand whose leading-dimension offset is simply the distance between the two views.  All accumulators of a
+// CTA ([taps*64] x 64 fp32) stay in TMEM over all its K-blocks and are flushed once with fp32 atomics.
+#include "../../include/m3t_b200.h"
+#include "common.cuh"
+#include "tmap.cuh"
+#include "ptx.cuh"
+
+namespace m3t {
+
+constexpr int kWgThreads = 192;
+constexpr int kWgMaxAcc = 5;
+
+struct WgHaloParams {
+  int n_img;            // images (frames) the K loop runs over
+  int H, TR;            // image rows, rows per K-block
+  int Wq;               // positions per row in the padded pixel space
+  int blocks_per_img, num_kblocks;
+  int ksteps;           // TR * Wq / 16
+  int x_bytes, dy_bytes, stage_bytes;
+  int x_w0, x_h0;       // box start offsets relative to (0, h0): (-1,-1) for 3x3/p1, (0,-2) for the stem
+  int t_frames, dt;     // stem: frames per clip and temporal tap offset (image n = b*T + t reads frame t + dt); else T=0
+  int n_acc;
+  int shiftA[kWgMaxAcc], shiftB[kWgMaxAcc];   // row shifts of the two 64-wide atoms of accumulator a
+  int tapA[kWgMaxAcc], tapB[kWgMaxAcc];       // output tap index of each atom (-1: atom unused)
+  float* out;           // fp32 [64][ldo], accumulated atomically
+  int ldo;
+};
+
+template <int STAGES>
+__global__ void __launch_bounds__(kWgThreads, 1)
+wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY,
+                  const WgHaloParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * p.stage_bytes);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  const int warp = threadIdx.x >> 5;
+  const uint32_t lane = lane_id();
+  const uint32_t tm_cols = p.n_acc * 64 <= 128 ? 128 : (p.n_acc * 64 <= 256 ? 256 : 512);
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmDY);
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    mbar_init(tmem_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, tm_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int x_stage_bytes = (p.x_bytes + 1023) / 1024 * 1024;
+  int my_blocks = 0;
+  for (int kb = blockIdx.x; kb < p.num_kblocks; kb += gridDim.x) ++my_blocks;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int it = 0;
+      for (int kb = blockIdx.x; kb < p.num_kblocks; kb += gridDim.x, ++it) {
+        const int stage = it % STAGES;
+        const uint32_t phase = (it / STAGES) & 1;
+        mbar_wait(&empty_bar[stage], phase ^ 1, 500 + stage);
+        const int n = kb / p.blocks_per_img;
+        const int h0 = (kb - n * p.blocks_per_img) * p.TR;
+        uint8_t* sX = smem + stage * p.stage_bytes;
+        uint8_t* sD = sX + x_stage_bytes;
+        mbar_arrive_expect_tx(&full_bar[stage], p.x_bytes + p.dy_bytes);
+        if (p.t_frames > 0) {
+          const int b = n / p.t_frames, t = n - b * p.t_frames;
+          tma_load_5d(&tmX, &full_bar[stage], sX, 0, p.x_w0, h0 + p.x_h0, t + p.dt, b);
+        } else {
+          tma_load_5d(&tmX, &full_bar[stage], sX, 0, p.x_w0, h0 + p.x_h0, 0, n);
+        }
+        tma_load_4d(&tmDY, &full_bar[stage], sD, 0, 0, h0, n);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, 64, 1, 1);
+      int it = 0;
+      for (int kb = blockIdx.x; kb < p.num_kblocks; kb += gridDim.x, ++it) {
+        const int stage = it % STAGES;
+        const uint32_t phase = (it / STAGES) & 1;
+        mbar_wait(&full_bar[stage], phase, 510 + stage);
+        tc_fence_after();
+        const uint32_t sX = smem_u32(smem + stage * p.stage_bytes);
+        const uint32_t sD = sX + x_stage_bytes;
+        for (int ks = 0; ks < p.ksteps; ++ks) {
+          const uint64_t bdesc = make_smem_desc(sD + ks * 2048, 8192, 1024, SWZ_128B);
+          for (int a = 0; a < p.n_acc; ++a) {
+            const uint32_t lbo = (uint32_t)(p.shiftB[a] - p.shiftA[a]) * 128u;
+            const uint64_t adesc = make_smem_desc(sX + (uint32_t)(p.shiftA[a] + ks * 16) * 128u, lbo, 1024, SWZ_128B);
+            umma_bf16(tmem_base + a * 64, adesc, bdesc, idesc, (it | ks) != 0 ? 1u : 0u);
+          }
+        }
+        umma_commit(&empty_bar[stage]);
+      }
+      umma_commit(tmem_full);
+    }
+  } else if (my_blocks > 0) {
+    const int quad = warp & 3;
+    const int row = quad * 32 + (int)lane;
+    mbar_wait(tmem_full, 0, 520);
+    tc_fence_after();
+    for (int a = 0; a < p.n_acc; ++a) {
+      const int tap = row < 64 ? p.tapA[a] : p.tapB[a];
+      const long long m = (long long)tap * 64 + (row & 63);
+      const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + a * 64;
+#pragma unroll 1
+      for (int c0 = 0; c0 < 64; c0 += 16) {
+        uint32_t r[16];
+        tmem_ld16(t_lane + c0, r);
+        tmem_ld_wait();
+        if (tap >= 0) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) atomicAdd(p.out + (long long)(c0 + i) * p.ldo + m, __uint_as_float(r[i]));
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tm_cols);
+  }
+}
+
+static int wg_launch(const CUtensorMap& tmX, const CUtensorMap& tmDY, WgHaloParams& p, cudaStream_t st) {
+  const int x_stage = (p.x_bytes + 1023) / 1024 * 1024;
+  const int dy_stage = (p.dy_bytes + 1023) / 1024 * 1024;
+  p.stage_bytes = x_stage + dy_stage;
+  constexpr int STAGES = 2;
+  const int smem = STAGES * p.stage_bytes + (2 * STAGES + 1) * 8 + 16 + 1024;
+  if (smem > 227 * 1024) return -7;
+  static bool attr_done = false;
+  if (!attr_done) {
+    if (cudaFuncSetAttribute(wgrad_halo_kernel<STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) !=
+        cudaSuccess)
+      return -20;
+    attr_done = true;
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = p.num_kblocks < sms ? p.num_kblocks : sms;
+  wgrad_halo_kernel<STAGES><<<grid, kWgThreads, smem, st>>>(tmX, tmDY, p);
+  count_launch();
+  return launch_status();
+}
+
+}  // namespace m3t
+
+using namespace m3t;
+
+// 3x3 / stride 1 / pad 1, Cin = Cout = 64.  x, dy: bf16 [F][H][W][64]; dw_packed: fp32 [64][9*64] += (caller zero-fills)
+extern "C" int m3t_wgrad3x3_c64_halo(const void* x, const void* dy, float* dw_packed, int F, int H, int W,
+                                     void* stream) {
+  const int Wp = W + 2;
+  if (F <= 0 || H <= 0 || W <= 0 || Wp > 64) return -1;
+  // rows per K-block: TR*Wp must be a multiple of 16 and the boxes must fit two pipeline stages
+  int TR = 0;
+  for (int t = 16; t >= 1; --t)
+    if ((t * Wp) % 16 == 0 && (t + 3) * Wp * 128 + t * Wp * 128 <= 100 * 1024) { TR = t; break; }
+  if (TR == 0) return -8;
+  WgHaloParams p;
+  memset(&p, 0, sizeof(p));
+  p.n_img = F; p.H = H; p.TR = TR; p.Wq = Wp;
+  p.blocks_per_img = (H + TR - 1) / TR;
+  p.num_kblocks = F * p.blocks_per_img;
+  p.ksteps = TR * Wp / 16;
+  const int RX = TR + 3;
+  p.x_bytes = RX * Wp * 128;
+  p.dy_bytes = TR * Wp * 128;
+  p.x_w0 = -1; p.x_h0 = -1;
+  p.t_frames = 0; p.dt = 0;
+  p.n_acc = 5;
+  for (int a = 0; a < 5; ++a) {
+    const int t0 = 2 * a, t1 = 2 * a + 1;
+    p.tapA[a] = t0;
+    p.shiftA[a] = (t0 / 3) * Wp + (t0 % 3);
+    if (t1 < 9) { p.tapB[a] = t1; p.shiftB[a] = (t1 / 3) * Wp + (t1 % 3); }
+    else { p.tapB[a] = -1; p.shiftB[a] = p.shiftA[a]; }
+  }
+  p.out = dw_packed; p.ldo = 576;
+  CUtensorMap tmX, tmDY;
+  uint64_t xd[5] = {64, (uint64_t)W, (uint64_t)H, 1, (uint64_t)F};
+  uint64_t xs[4] = {128, (uint64_t)W * 128, (uint64_t)H * W * 128, (uint64_t)H * W * 128};
+  uint32_t xb[5] = {64, (uint32_t)Wp, (uint32_t)RX, 1, 1};
+  int rc = make_tmap_tiled_bf16(&tmX, x, 5, xd, xs, xb, 128);
+  if (rc) return rc;
+  uint64_t dd[4] = {64, (uint64_t)W, (uint64_t)H, (uint64_t)F};
+  uint64_t ds[3] = {128, (uint64_t)W * 128, (uint64_t)H * W * 128};
+  uint32_t db[4] = {64, (uint32_t)Wp, (uint32_t)TR, 1};
+  rc = make_tmap_tiled_bf16(&tmDY, dy, 4, dd, ds, db, 128);
+  if (rc) return rc;
+  return wg_launch(tmX, tmDY, p, reinterpret_cast<cudaStream_t>(stream));
+}
+
+// Stem: xs bf16 [B][T][H2][W2][64] (W-unrolled space-to-depth), dy bf16 [B*T][H2][W2][64];
+// dw_packed fp32 [64][20*64] (tap = kt*4 + jh) += .  Five launches, one per temporal tap kt.
+extern "C" int m3t_wgrad_stem_halo(const void* xs, const void* dy, float* dw_packed, int B, int T, int H2, int W2,
+                                   void* stream) {
+  if (B <= 0 || T <= 0 || H2 <= 0 || W2 <= 0 || W2 > 256) return -1;
+  int TR = 0;
+  for (int t = 8; t >= 1; --t)
+    if ((t * W2) % 16 == 0 && (t + 3) * W2 * 128 + t * W2 * 128 <= 100 * 1024) { TR = t; break; }
+  if (TR == 0) return -8;
+  const int RX = TR + 3;
+  CUtensorMap tmX, tmDY;
+  uint64_t xd[5] = {64, (uint64_t)W2, (uint64_t)H2, (uint64_t)T, (uint64_t)B};
+  uint64_t xst[4] = {128, (uint64_t)W2 * 128, (uint64_t)H2 * W2 * 128, (uint64_t)T * H2 * W2 * 128};
+  uint32_t xb[5] = {64, (uint32_t)W2, (uint32_t)RX, 1, 1};
+  int rc = make_tmap_tiled_bf16(&tmX, xs, 5, xd, xst, xb, 128);
+  if (rc) return rc;
+  uint64_t dd[4] = {64, (uint64_t)W2, (uint64_t)H2, (uint64_t)B * T};
+  uint64_t dst[3] = {128, (uint64_t)W2 * 128, (uint64_t)H2 * W2 * 128};
+  uint32_t db[4] = {64, (uint32_t)W2, (uint32_t)TR, 1};
+  rc = make_tmap_tiled_bf16(&tmDY, dy, 4, dd, dst, db, 128);
+  if (rc) return rc;
+  for (int kt = 0; kt < 5; ++kt) {
+    WgHaloParams p;
+    memset(&p, 0, sizeof(p));
+    p.n_img = B * T; p.H = H2; p.TR = TR; p.Wq = W2;
+    p.blocks_per_img = (H2 + TR - 1) / TR;
+    p.num_kblocks = p.n_img * p.blocks_per_img;
+    p.ksteps = TR * W2 / 16;
+    p.x_bytes = RX * W2 * 128;
+    p.dy_bytes = TR * W2 * 128;
+    p.x_w0 = 0; p.x_h0 = -2;
+    p.t_frames = T; p.dt = kt - 2;
+    p.n_acc = 2;
+    for (int a = 0; a < 2; ++a) {
+      p.tapA[a] = kt * 4 + 2 * a;     p.shiftA[a] = (2 * a) * W2;
+      p.tapB[a] = kt * 4 + 2 * a + 1; p.shiftB[a] = (2 * a + 1) * W2;
+    }
+    p.out = dw_packed; p.ldo = 20 * 64;
+    rc = wg_launch(tmX, tmDY, p, reinterpret_cast<cudaStream_t>(stream));
+    if (rc) return rc;
+  }
+  return 0;
+}

@@ -222,7 +222,10 @@ class Stem3D(torch.autograd.Function):
     def backward(ctx, dout):
         xs, w, y, pidx, fin = ctx.saved_tensors
         dy, sums = raw.maxpool_bn_bwd(dout.contiguous(), pidx, y, fin[0], fin[1], fin[2], fin[3], ctx.count)
-        dwp = raw.conv_wgrad(xs, dy, ctx.geom, algo_flops=ctx.flops)
+        if raw.USE_HALO_WGRAD:
+            dwp = raw.wgrad_stem_halo(xs, dy, algo_flops=ctx.flops)
+        else:
+            dwp = raw.conv_wgrad(xs, dy, ctx.geom, algo_flops=ctx.flops)
         dw = raw.scatter_unpack(dwp, stem_s2d_index(w.device), (64, 3 * 5 * 7 * 7)).view(w.shape)
         return None, dw, sums[1].clone(), sums[0].clone(), None, None, None, None
 

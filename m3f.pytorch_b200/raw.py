@@ -113,6 +113,12 @@ def conv_fprop(x, w_packed, g, scale=None, shift=None, residual=None, relu=False
     _chk_bf16(x, w_packed, residual)
     Z, P, Q = conv_out_dims(g)
     N, Cout = g[1], g[6]
+    if (USE_HALO and tile_hint == 0 and g[0] == 2 and g[5] == 64 and Cout == 64 and tuple(g[7:10]) == (1, 3, 3)
+            and tuple(g[10:13]) == (1, 1, 1) and tuple(g[13:19]) == (0, 0, 1, 1, 1, 1)
+            and tuple(g[19:22]) == (1, 1, 1) and g[4] + 2 <= 48):
+        y = conv3x3_c64_halo(x.view(N, g[3], g[4], 64), w_packed, scale, shift,
+                             residual.view(N, g[3], g[4], 64) if residual is not None else None, relu, stats, tag)
+        return y.view(N, 1, g[3], g[4], 64)
     y = torch.empty((N, Z, P, Q, Cout), device=x.device, dtype=torch.bfloat16)
 
     def run():
@@ -127,12 +133,61 @@ def conv_fprop(x, w_packed, g, scale=None, shift=None, residual=None, relu=False
     return y
 
 
+USE_HALO = True   # route 64->64 3x3/s1/p1 convolutions to the persistent halo-tile kernel
+
+
+def conv3x3_c64_halo(x, w_packed, scale=None, shift=None, residual=None, relu=False, stats=None, tag="fprop"):
+    """x: bf16 [F,H,W,64]; w_packed bf16 [64, 576] -> bf16 [F,H,W,64]."""
+    _chk_bf16(x, w_packed, residual)
+    F_, H, W, C = x.shape
+    assert C == 64 and w_packed.shape == (64, 576)
+    y = torch.empty((F_, H, W, 64), device=x.device, dtype=torch.bfloat16)
+
+    def run():
+        rc = L.load().m3t_conv3x3_c64_halo(L.ptr(x), L.ptr(w_packed), L.ptr(y), L.i32(F_), L.i32(H), L.i32(W),
+                                           L.ptr(scale), L.ptr(shift), L.ptr(residual), L.i32(relu), L.ptr(stats),
+                                           L.stream_ptr())
+        L.check(rc, "m3t_conv3x3_c64_halo")
+
+    _timed("%s-halo nd2 1x%dx%d c64->64 k1x3x3 s1" % (tag, H, W), 2.0 * F_ * H * W * 64 * 576, run)
+    return y
+
+
+USE_HALO_WGRAD = True
+
+
+def wgrad_stem_halo(xs, dy, algo_flops=None):
+    """Stem weight gradient over the W-unrolled s2d image: xs bf16 [B,T,H2,W2,64], dy bf16 [B*T,H2,W2,64] ->
+    fp32 [64, 1280] (packed (kt,jh,jw,ch))."""
+    _chk_bf16(xs, dy)
+    B, T, H2, W2, _ = xs.shape
+    dw = torch.zeros((64, 1280), device=xs.device, dtype=torch.float32)
+
+    def run():
+        L.check(L.load().m3t_wgrad_stem_halo(L.ptr(xs), L.ptr(dy), L.ptr(dw), L.i32(B), L.i32(T), L.i32(H2),
+                                             L.i32(W2), L.stream_ptr()), "m3t_wgrad_stem_halo")
+
+    _timed("wgrad-halo stem %dx%dx%d" % (T, H2, W2), algo_flops or 2.0 * B * T * H2 * W2 * 64 * 1280, run)
+    return dw
+
+
 def conv_wgrad(x, dy, g, splits=0, algo_flops=None):
     """Returns fp32 [Cout, taps*Cin] (packed, tap-major / channel-minor)."""
     _chk_bf16(x, dy)
     Cin, Cout = g[5], g[6]
     taps = g[7] * g[8] * g[9]
     dw = torch.zeros((Cout, taps * Cin), device=x.device, dtype=torch.float32)
+    if (USE_HALO_WGRAD and splits == 0 and g[0] == 2 and Cin == 64 and Cout == 64 and tuple(g[7:10]) == (1, 3, 3)
+            and tuple(g[10:13]) == (1, 1, 1) and tuple(g[13:19]) == (0, 0, 1, 1, 1, 1)
+            and tuple(g[19:22]) == (1, 1, 1) and g[4] + 2 <= 48):
+        N, H, W = g[1], g[3], g[4]
+
+        def run_h():
+            L.check(L.load().m3t_wgrad3x3_c64_halo(L.ptr(x), L.ptr(dy), L.ptr(dw), L.i32(N), L.i32(H), L.i32(W),
+                                                   L.stream_ptr()), "m3t_wgrad3x3_c64_halo")
+
+        _timed("wgrad-halo nd2 1x%dx%d c64->64 k1x3x3 s1" % (H, W), 2.0 * N * H * W * 64 * 576, run_h)
+        return dw
 
     def run():
         rc = L.load().m3t_conv_wgrad_bf16(L.ptr(x), L.ptr(dy), L.ptr(dw), L.int_array(g), L.i32(splits),

@@ -185,8 +185,8 @@ CASES = {
                                    stride=(1, 1, 1), pad_lo=(0, 1, 1), stats=True)),
     "conv2d_mt2": (case_conv, _c(nd=2, N=3, D=1, H=28, W=28, Cin=64, Cout=64, k=(1, 3, 3), stride=(1, 1, 1),
                                  pad_lo=(0, 1, 1), tile_hint=2, stats=True)),
-    "conv2d_bn256": (case_conv, _c(nd=2, N=9, D=1, H=4, W=4, Cin=512, Cout=512, k=(1, 3, 3), stride=(1, 1, 1),
-                                   pad_lo=(0, 1, 1), tile_hint=4)),
+    "conv2d_bn128_forced": (case_conv, _c(nd=2, N=9, D=1, H=4, W=4, Cin=512, Cout=512, k=(1, 3, 3), stride=(1, 1, 1),
+                                   pad_lo=(0, 1, 1), tile_hint=8)),
     "conv1d_causal_dil2": (case_conv, _c(nd=1, N=4, D=1, H=1, W=32, Cin=512, Cout=512, k=(1, 1, 3),
                                          stride=(1, 1, 1), pad_lo=(0, 0, 4), pad_hi=(0, 0, 0), dil=(1, 1, 2))),
     "conv1d_k5": (case_conv, _c(nd=1, N=4, D=1, H=1, W=32, Cin=1024, Cout=512, k=(1, 1, 5), stride=(1, 1, 1),
@@ -725,6 +725,21 @@ def case_optim(seed=0):
 
 
 CASES["optim_adam_clip"] = (case_optim, _c())
+# the halo-tile kernel is selected automatically for 64->64 3x3/s1/p1 (conv2d_3x3_s1_64 above); more shapes:
+CASES["halo_28_fused"] = (case_conv, _c(nd=2, N=5, D=1, H=28, W=28, Cin=64, Cout=64, k=(1, 3, 3), stride=(1, 1, 1),
+                                        pad_lo=(0, 1, 1), fused=True))
+CASES["halo_28_stats_big"] = (case_conv, _c(nd=2, N=67, D=1, H=28, W=28, Cin=64, Cout=64, k=(1, 3, 3),
+                                            stride=(1, 1, 1), pad_lo=(0, 1, 1), stats=True))
+CASES["halo_odd_13x9"] = (case_conv, _c(nd=2, N=3, D=1, H=13, W=9, Cin=64, Cout=64, k=(1, 3, 3), stride=(1, 1, 1),
+                                        pad_lo=(0, 1, 1), stats=True))
+CASES["wgrad_halo_28"] = (case_conv, _c(nd=2, N=5, D=1, H=28, W=28, Cin=64, Cout=64, k=(1, 3, 3), stride=(1, 1, 1),
+                                        pad_lo=(0, 1, 1), wgrad=True))
+CASES["wgrad_halo_13x9"] = (case_conv, _c(nd=2, N=3, D=1, H=13, W=9, Cin=64, Cout=64, k=(1, 3, 3), stride=(1, 1, 1),
+                                          pad_lo=(0, 1, 1), wgrad=True))
+CASES["wgrad_halo_5x40_big"] = (case_conv, _c(nd=2, N=301, D=1, H=5, W=40, Cin=64, Cout=64, k=(1, 3, 3),
+                                              stride=(1, 1, 1), pad_lo=(0, 1, 1), wgrad=True))
+CASES["halo_5x40"] = (case_conv, _c(nd=2, N=7, D=1, H=5, W=40, Cin=64, Cout=64, k=(1, 3, 3), stride=(1, 1, 1),
+                                    pad_lo=(0, 1, 1)))
 for _k in ("p_l1.weight", "p_l1.bias", "p_l2.weight", "p_l2.bias"):
     TOLS[_k] = 1e-4
 
@@ -785,6 +800,32 @@ def case_audio_resnet(train, seed=0):
 
 CASES["audio_resnet_tcn_eval"] = (case_audio_resnet, _c(train=False))
 CASES["audio_resnet_tcn_train_fwd"] = (case_audio_resnet, _c(train=True))
+
+
+
+def case_stem_wgrad_halo(seed=0):
+    """Halo-tile stem wgrad (5 launches, one per temporal tap) vs the generic im2col wgrad and vs autograd."""
+    from m3t_b200 import raw
+    g = torch.Generator().manual_seed(seed)
+    B, T, H2, W2 = 2, 5, 56, 56
+    xs = _rnd((B, T, H2, W2, 64), g).cuda()
+    dy = _rnd((B * T, H2, W2, 64), g).cuda()
+    geom = raw.conv_geom(3, B, T, H2, W2, 64, 64, (5, 4, 1), (1, 1, 1), (2, 2, 0), (2, 1, 0), (1, 1, 1))
+    ref = raw.conv_wgrad(xs, dy.view(B, T, H2, W2, 64), geom)
+    got = raw.wgrad_stem_halo(xs, dy)
+    torch.cuda.synchronize()
+    # independent CPU check on one output channel block via conv3d autograd
+    x_nc = xs.float().cpu().permute(0, 4, 1, 2, 3)
+    w = torch.zeros((64, 64, 5, 4, 1), requires_grad=True)
+    y = F.conv3d(F.pad(x_nc, (0, 0, 2, 1, 2, 2)), w)
+    y.backward(dy.float().cpu().view(B, T, H2, W2, 64).permute(0, 4, 1, 2, 3))
+    dw_cpu = w.grad.permute(0, 2, 3, 4, 1).reshape(64, -1)
+    return {"vs_generic": _err(got, ref), "vs_cpu": _err(got, dw_cpu)}
+
+
+CASES["stem_wgrad_halo"] = (case_stem_wgrad_halo, _c())
+TOLS["vs_generic"] = 1e-4
+TOLS["vs_cpu"] = 1e-4
 
 
 if __name__ == "__main__":
