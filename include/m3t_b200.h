@@ -65,6 +65,13 @@ int m3t_conv_fprop_bf16(const void* x, const void* w_packed, void* y, const int*
 int m3t_conv3x3_c64_halo(const void* x, const void* w_packed, void* y, int F, int H, int W, const float* scale,
                          const float* shift, const void* residual, int relu, float* stats, void* stream);
 
+/* Stem forward as a halo-tile kernel over the W-unrolled space-to-depth image xs [B][T][H2][W2][64] with the packed
+ * (5,4,1)x64 filter [64][20*64]: per temporal tap one box of TR+3 rows plus that tap's filter slices, the 4 vertical
+ * taps as row-shifted views; y bf16 [B*T][H2][W2][64]; epilogue contract as m3t_conv_fprop_bf16 (no residual).
+ * Replaces nn.Conv3d(3,64,(5,7,7),(1,2,2),(2,3,3)) at models/backbone.py:328. */
+int m3t_stem_fprop_halo(const void* xs, const void* w_packed, void* y, int B, int T, int H2, int W2,
+                        const float* scale, const float* shift, int relu, float* stats, void* stream);
+
 /* Halo-tile weight gradients for the 64-channel layers (wgrad_halo.cu): persistent CTAs, one activation halo box and
  * one dY box per K-block of whole image rows, filter taps as row-shifted MN-major views, accumulators resident in
  * TMEM, one atomic flush.  dw_packed is fp32, caller-zeroed, same packed layout as m3t_conv_wgrad_bf16.

@@ -253,6 +253,213 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------
+// Stem forward over the W-unrolled space-to-depth image: (5,4,1) filter, 64 -> 64 channels (reference:
+// models/backbone.py:328).  Same halo idea along H: a tile is TR = 8 whole image rows (448 positions = four 128-row
+// accumulators, the last one overlapping the third); per temporal tap kt ONE box brings rows h0-2 .. h0+TR of frame
+// t+kt-2 (zero-filled outside the image / clip) together with that tap's 4 x [64][64] filter slices, and the four
+// vertical taps jh are row-shifted views (jh * W2 rows) of the box.  L2->SM traffic per 128 positions drops from
+// 480 KB (20 taps x (16 + 8) KB) to 159 KB.  Persistent CTAs, double-buffered TMEM (2 x 256 columns).
+// ------------------------------------------------------------------------------------------------------------
+struct StemHaloParams {
+  int B, T, H2, W2;
+  int TR, npos, nsub;           // rows per tile, positions per tile, 128-row accumulators per tile
+  int tiles_per_img, num_tiles;
+  int a_bytes, stage_bytes;
+  __nv_bfloat16* y;
+  const float* scale;
+  const float* shift;
+  int relu;
+  float* stats;
+};
+
+__global__ void __launch_bounds__(kHaloThreads, 1)
+stem_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
+                 const StemHaloParams p) {
+  constexpr int STAGES = 2;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * p.stage_bytes);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;   // [2]
+  uint64_t* tmem_empty = tmem_full + 2;       // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  float* stat_smem = reinterpret_cast<float*>(tmem_slot + 2);   // [4 warps][2][64]
+  const int warp = threadIdx.x >> 5;
+  const uint32_t lane = lane_id();
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmW);
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 128);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  for (int i = threadIdx.x; i < 4 * 2 * 64; i += kHaloThreads) stat_smem[i] = 0.f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const int f = tile / p.tiles_per_img;
+        const int h0 = (tile - f * p.tiles_per_img) * p.TR;
+        const int b = f / p.T, t = f - b * p.T;
+        for (int kt = 0; kt < 5; ++kt, ++it) {
+          const int stage = it % STAGES;
+          const uint32_t phase = (it / STAGES) & 1;
+          mbar_wait(&empty_bar[stage], phase ^ 1, 600 + stage);
+          uint8_t* sA = smem + stage * p.stage_bytes;
+          uint8_t* sB = sA + p.a_bytes;
+          mbar_arrive_expect_tx(&full_bar[stage], p.a_bytes + 4 * 8192);
+          tma_load_5d(&tmX, &full_bar[stage], sA, 0, 0, h0 - 2, t + kt - 2, b);
+#pragma unroll
+          for (int jh = 0; jh < 4; ++jh) tma_load_2d(&tmW, &full_bar[stage], sB + jh * 8192, (kt * 4 + jh) * 64, 0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, 64, 0, 0);
+      int it = 0, tcount = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tcount) {
+        const int acc = tcount & 1;
+        const uint32_t acc_phase = (tcount >> 1) & 1;
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1, 620 + acc);
+        for (int kt = 0; kt < 5; ++kt, ++it) {
+          const int stage = it % STAGES;
+          const uint32_t phase = (it / STAGES) & 1;
+          mbar_wait(&full_bar[stage], phase, 630 + stage);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(smem + stage * p.stage_bytes);
+          const uint32_t b_base = a_base + p.a_bytes;
+#pragma unroll 1
+          for (int jh = 0; jh < 4; ++jh) {
+#pragma unroll 1
+            for (int j = 0; j < p.nsub; ++j) {
+              const int sub_start = min(128 * j, p.npos - 128);
+              const uint32_t a_tap = a_base + (uint32_t)(jh * p.W2 + sub_start) * 128u;
+              const uint32_t b_tap = b_base + (uint32_t)jh * 8192u;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const uint64_t adesc = make_smem_desc(a_tap + k * 32, 16, 1024, SWZ_128B);
+                const uint64_t bdesc = make_smem_desc(b_tap + k * 32, 16, 1024, SWZ_128B);
+                umma_bf16(tmem_base + acc * 256 + j * 64, adesc, bdesc, idesc, (kt | jh | k) != 0 ? 1u : 0u);
+              }
+            }
+          }
+          umma_commit(&empty_bar[stage]);
+        }
+        umma_commit(&tmem_full[acc]);
+      }
+    }
+  } else {
+    const int quad = warp & 3;
+    const int row = quad * 32 + (int)lane;
+    const bool want_stats = p.stats != nullptr;
+    float st1[64], st2[64];
+#pragma unroll
+    for (int i = 0; i < 64; ++i) st1[i] = st2[i] = 0.f;
+    int tcount = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tcount) {
+      const int acc = tcount & 1;
+      const uint32_t acc_phase = (tcount >> 1) & 1;
+      const int f = tile / p.tiles_per_img;
+      const int h0 = (tile - f * p.tiles_per_img) * p.TR;
+      mbar_wait(&tmem_full[acc], acc_phase, 640 + acc);
+      tc_fence_after();
+#pragma unroll 1
+      for (int j = 0; j < p.nsub; ++j) {
+        const int sub_start = min(128 * j, p.npos - 128);
+        const int q = sub_start + row;
+        const int hh = q / p.W2, ww = q - hh * p.W2;
+        const bool ok = q >= 128 * j && (h0 + hh) < p.H2;
+        const long long pix = ((long long)f * p.H2 + h0 + hh) * p.W2 + ww;
+        const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * 256 + j * 64;
+#pragma unroll
+        for (int c0 = 0; c0 < 64; c0 += 32) {
+          float v[32];
+          {
+            uint32_t r[16];
+            tmem_ld16(t_lane + c0, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+            tmem_ld16(t_lane + c0 + 16, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[16 + i] = __uint_as_float(r[i]);
+          }
+          if (j == p.nsub - 1 && c0 == 32) {   // whole tile read: release the TMEM buffer
+            tc_fence_before();
+            mbar_arrive(&tmem_empty[acc]);
+          }
+          if (ok) {
+            float o[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              float x = v[i];
+              if (p.scale) x *= __ldg(p.scale + c0 + i);
+              if (p.shift) x += __ldg(p.shift + c0 + i);
+              o[i] = p.relu ? fmaxf(x, 0.f) : x;
+            }
+            uint4* op = reinterpret_cast<uint4*>(p.y + pix * 64 + c0);
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+              op[g] = make_uint4(pack_bf16x2(o[8 * g], o[8 * g + 1]), pack_bf16x2(o[8 * g + 2], o[8 * g + 3]),
+                                 pack_bf16x2(o[8 * g + 4], o[8 * g + 5]), pack_bf16x2(o[8 * g + 6], o[8 * g + 7]));
+            if (want_stats) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                st1[c0 + i] += v[i];
+                st2[c0 + i] = fmaf(v[i], v[i], st2[c0 + i]);
+              }
+            }
+          }
+        }
+      }
+    }
+    if (want_stats) {
+#pragma unroll
+      for (int c0 = 0; c0 < 64; c0 += 32) {
+        float s1[32], s2[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          s1[i] = st1[c0 + i];
+          s2[i] = st2[c0 + i];
+        }
+        halo_butterfly<16>(s1, lane);
+        halo_butterfly<16>(s2, lane);
+        stat_smem[(quad * 2 + 0) * 64 + c0 + lane] = s1[0];
+        stat_smem[(quad * 2 + 1) * 64 + c0 + lane] = s2[0];
+      }
+      named_bar_sync(1, 128);
+      for (int i = threadIdx.x - 64; i < 2 * 64; i += 128) {
+        const int which = i / 64, c = i - which * 64;
+        const float s = stat_smem[(0 * 2 + which) * 64 + c] + stat_smem[(1 * 2 + which) * 64 + c] +
+                        stat_smem[(2 * 2 + which) * 64 + c] + stat_smem[(3 * 2 + which) * 64 + c];
+        atomicAdd(p.stats + which * 64 + c, s);
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 }  // namespace m3t
 
 using namespace m3t;
@@ -302,6 +509,57 @@ extern "C" int m3t_conv3x3_c64_halo(const void* x, const void* w_packed, void* y
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = p.num_tiles < sms ? p.num_tiles : sms;
   conv3x3_halo_kernel<<<grid, kHaloThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(tmX, tmW, p);
+  count_launch();
+  return launch_status();
+}
+
+// xs: bf16 [B][T][H2][W2][64] (W-unrolled s2d), w_packed: bf16 [64][20*64] ((kt,jh) taps), y: bf16 [B*T][H2][W2][64]
+extern "C" int m3t_stem_fprop_halo(const void* xs, const void* w_packed, void* y, int B, int T, int H2, int W2,
+                                   const float* scale, const float* shift, int relu, float* stats, void* stream) {
+  if (B <= 0 || T <= 0 || H2 <= 0 || W2 <= 0 || W2 > 256) return -1;
+  StemHaloParams p;
+  memset(&p, 0, sizeof(p));
+  p.B = B; p.T = T; p.H2 = H2; p.W2 = W2;
+  // rows per tile: as many as fit (box + 4 filter slices) x 2 stages in shared memory, at most 4 accumulators
+  int TR = 0;
+  for (int t = 16; t >= 1; --t) {
+    const int npos = t * W2;
+    const int abytes = ((t + 3) * W2 * 128 + 1023) / 1024 * 1024;
+    if (npos >= 128 && (npos + 127) / 128 <= 4 && 2 * (abytes + 4 * 8192) + 4096 <= 227 * 1024 - 1024) { TR = t; break; }
+  }
+  if (TR == 0) return -8;
+  if (TR > H2) return -8;
+  p.TR = TR;
+  p.npos = TR * W2;
+  p.nsub = (p.npos + 127) / 128;
+  p.tiles_per_img = (H2 + TR - 1) / TR;
+  p.num_tiles = B * T * p.tiles_per_img;
+  p.a_bytes = ((TR + 3) * W2 * 128 + 1023) / 1024 * 1024;
+  p.stage_bytes = p.a_bytes + 4 * 8192;
+  p.y = reinterpret_cast<__nv_bfloat16*>(y);
+  p.scale = scale; p.shift = shift; p.relu = relu; p.stats = stats;
+  if ((TR + 3) * W2 * 128 != p.a_bytes) return -8;   // the box must fill the stage exactly (expect_tx accounting)
+  CUtensorMap tmX, tmW;
+  uint64_t xd[5] = {64, (uint64_t)W2, (uint64_t)H2, (uint64_t)T, (uint64_t)B};
+  uint64_t xst[4] = {128, (uint64_t)W2 * 128, (uint64_t)H2 * W2 * 128, (uint64_t)T * H2 * W2 * 128};
+  uint32_t xb[5] = {64, (uint32_t)W2, (uint32_t)(TR + 3), 1, 1};
+  int rc = make_tmap_tiled_bf16(&tmX, xs, 5, xd, xst, xb, 128);
+  if (rc) return rc;
+  rc = make_tmap_2d_bf16(&tmW, w_packed, 1280, 64, 1280, 64, 64);
+  if (rc) return rc;
+  const int smem = 2 * p.stage_bytes + (2 * 2 + 4) * 8 + 16 + 4 * 2 * 64 * 4 + 1024;
+  if (smem > 227 * 1024) return -7;
+  static bool attr_done = false;
+  if (!attr_done) {
+    if (cudaFuncSetAttribute(stem_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+      return -20;
+    attr_done = true;
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = p.num_tiles < sms ? p.num_tiles : sms;
+  stem_halo_kernel<<<grid, kHaloThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(tmX, tmW, p);
   count_launch();
   return launch_status();
 }

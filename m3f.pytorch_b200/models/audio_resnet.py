@@ -35,7 +35,7 @@ class AudioResNetTCN(nn.Module):
         conv, bn = self.stem[0], self.stem[1]
         h = ops.Conv3x3C1BNReLU.apply(x, conv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.training)
         if bn.training:
-            bn.num_batches_tracked.add_(1)
+            ops.bump_num_batches_tracked(bn)
         f = self.resnet.forward_cl(h).view(B, T, -1)          # (B,T,512) bf16
         f = self.tcn.forward_cl(f)
         return ops.linear(f, self.fc.weight, self.fc.bias, out_f32=True)

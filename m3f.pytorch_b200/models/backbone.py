@@ -60,7 +60,7 @@ class VA_3DResNet(nn.Module):
         x = ops.Stem3D.apply(video, conv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var, normalise,
                              bn.training)
         if bn.training:
-            bn.num_batches_tracked.add_(1)
+            ops.bump_num_batches_tracked(bn)
         f = self.resnet.forward_cl(x)                     # (B*T, 512)
         return f.view(B, T, -1)
 

@@ -14,8 +14,8 @@ def _conv_bn_act(x, conv, bn, residual, relu):
     training = bn.training
     out = ops.ConvBNAct.apply(x, conv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var, residual,
                               conv.stride[0], conv.padding[0], relu, training)
-    if training and bn.num_batches_tracked is not None:
-        bn.num_batches_tracked.add_(1)
+    if training:
+        ops.bump_num_batches_tracked(bn)
     return out
 
 

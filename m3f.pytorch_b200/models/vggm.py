@@ -45,7 +45,7 @@ def _run_stack(seq, x, first_is_s2d):
         x = ops.ConvNdBNAct.apply(x, conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var, cfg,
                                   bn.training)
         if bn.training:
-            bn.num_batches_tracked.add_(1)
+            ops.bump_num_batches_tracked(bn)
         i += 4 if pool else 3
     return x
 
@@ -60,7 +60,7 @@ def _tcn_simple(mlist, x):
         x = ops.ConvNdBNAct.apply(x, conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var, cfg,
                                   bn.training)
         if bn.training:
-            bn.num_batches_tracked.add_(1)
+            ops.bump_num_batches_tracked(bn)
     if len(mlist) > 1:
         x = ops.linear(x, mlist[1].weight, mlist[1].bias, out_f32=True)
     return x

@@ -15,6 +15,15 @@ from . import raw
 BN_EPS = 1e-5
 BN_MOMENTUM = 0.1
 
+# When a TrainEngine drives the step it bumps every BatchNorm's num_batches_tracked with ONE multi-tensor op per step
+# instead of one tiny kernel per layer.
+DEFER_NUM_BATCHES_TRACKED = False
+
+
+def bump_num_batches_tracked(bn):
+    if not DEFER_NUM_BATCHES_TRACKED and bn.num_batches_tracked is not None:
+        bn.num_batches_tracked.add_(1)
+
 _pack_cache = {}
 
 
@@ -155,7 +164,7 @@ class ConvBNAct(torch.autograd.Function):
         dres = None
         if ctx.has_res:
             dres = dz if relu else dout
-        dgamma, dbeta = sums[1].clone(), sums[0].clone()
+        dgamma, dbeta = sums[1], sums[0]
         # weight gradient
         dwp = raw.conv_wgrad(x, dy, ctx.geom)
         dw = raw.unpack_filter_grad(dwp, tuple(w.shape))
@@ -200,16 +209,23 @@ class Stem3D(torch.autograd.Function):
         geom = raw.conv_geom(3, B, T, H // 2, W // 2, 64, 64, (5, 4, 1), (1, 1, 1), (2, 2, 0), (2, 1, 0), (1, 1, 1))
         flops = 2.0 * B * T * (H // 2) * (W // 2) * 64 * 3 * 5 * 7 * 7     # unpadded 5x7x7x3 filter
         ctx.flops = flops
+        halo = raw.USE_HALO_STEM and (H // 2) % 8 == 0 and (W // 2) == 56
         if training:
             stats = torch.zeros((2, 64), device=video.device, dtype=torch.float32)
-            y = raw.conv_fprop(xs, wp, geom, stats=stats, algo_flops=flops, tag="stem")
+            if halo:
+                y = raw.stem_fprop_halo(xs, wp, stats=stats, algo_flops=flops)
+            else:
+                y = raw.conv_fprop(xs, wp, geom, stats=stats, algo_flops=flops, tag="stem")
             y = y.view(B * T, H // 2, W // 2, 64)
             count = y.numel() // 64
             fin = raw.bn_finalize(stats, count, gamma.detach(), beta.detach(), BN_EPS, BN_MOMENTUM, running_mean,
                                   running_var)
             scale, shift = fin[2], fin[3]
         else:
-            y = raw.conv_fprop(xs, wp, geom, algo_flops=flops, tag="stem").view(B * T, H // 2, W // 2, 64)
+            if halo:
+                y = raw.stem_fprop_halo(xs, wp, algo_flops=flops)
+            else:
+                y = raw.conv_fprop(xs, wp, geom, algo_flops=flops, tag="stem").view(B * T, H // 2, W // 2, 64)
             ss = raw.bn_fold(gamma.detach(), beta.detach(), running_mean, running_var, None, BN_EPS)
             scale, shift = ss[0], ss[1]
         out, pidx = raw.bn_relu_maxpool(y, scale, shift, training)
@@ -227,7 +243,7 @@ class Stem3D(torch.autograd.Function):
         else:
             dwp = raw.conv_wgrad(xs, dy, ctx.geom, algo_flops=ctx.flops)
         dw = raw.scatter_unpack(dwp, stem_s2d_index(w.device), (64, 3 * 5 * 7 * 7)).view(w.shape)
-        return None, dw, sums[1].clone(), sums[0].clone(), None, None, None, None
+        return None, dw, sums[1], sums[0], None, None, None, None
 
 
 _stem_idx = {}
@@ -592,7 +608,7 @@ class ConvNdBNAct(torch.autograd.Function):
             g2 = raw.conv_geom(nd, N, Z, P, Q, Cout, Cin, k, (1, 1, 1), lo, hi, (1, 1, 1))
             dx = raw.conv_fprop(dy, wd, g2, tag="dgrad").view(x.shape)
         dcb = torch.zeros_like(fin[0]) if ctx.has_bias else None   # exact: batch-norm removes the bias
-        return dx, dw, dcb, sums[1].clone(), sums[0].clone(), None, None, None, None
+        return dx, dw, dcb, sums[1], sums[0], None, None, None, None
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -629,4 +645,4 @@ class Conv3x3C1BNReLU(torch.autograd.Function):
         dy = raw.bn_bwd_apply(d2, out, y, fin[0], fin[1], fin[2], sums, y.shape[0], True)
         dwp = raw.gemm(dy, patches, a_mn=True, b_mn=True, out_dtype=torch.float32)     # [Cout, 16]
         dw = dwp[:, :9].reshape(w.shape)
-        return None, dw, sums[1].clone(), sums[0].clone(), None, None, None
+        return None, dw, sums[1], sums[0], None, None, None

@@ -154,6 +154,22 @@ def conv3x3_c64_halo(x, w_packed, scale=None, shift=None, residual=None, relu=Fa
 
 
 USE_HALO_WGRAD = True
+USE_HALO_STEM = True
+
+
+def stem_fprop_halo(xs, w_packed, stats=None, algo_flops=None):
+    """xs bf16 [B,T,H2,W2,64], w_packed bf16 [64,1280] -> raw conv output bf16 [B*T,H2,W2,64] (+ column stats)."""
+    _chk_bf16(xs, w_packed)
+    B, T, H2, W2, _ = xs.shape
+    y = torch.empty((B * T, H2, W2, 64), device=xs.device, dtype=torch.bfloat16)
+
+    def run():
+        L.check(L.load().m3t_stem_fprop_halo(L.ptr(xs), L.ptr(w_packed), L.ptr(y), L.i32(B), L.i32(T), L.i32(H2),
+                                             L.i32(W2), L.ptr(None), L.ptr(None), L.i32(0), L.ptr(stats),
+                                             L.stream_ptr()), "m3t_stem_fprop_halo")
+
+    _timed("stem-halo %dx%dx%d" % (T, H2, W2), algo_flops or 2.0 * B * T * H2 * W2 * 64 * 1280, run)
+    return y
 
 
 def wgrad_stem_halo(xs, dy, algo_flops=None):

@@ -46,9 +46,10 @@ def main():
     y = m(batch)
     loss, _ = m.compute_loss(y, batch)
     loss.backward()
+    eng._gather_grads()
     eng._allreduce_grads()
-    for p, e in zip(m.parameters(), exp):
-        assert torch.allclose(p.grad, e, atol=1e-6), (rank, (p.grad - e).abs().max())
+    for v, e in zip(eng.grad_views, exp):
+        assert torch.allclose(v, e, atol=1e-6), (rank, (v - e).abs().max())
     print("DP_OK rank %d" % rank, flush=True)
     dist.destroy_process_group()
 
