@@ -120,12 +120,14 @@ int m3t_bn_fold(int C, const float* gamma, const float* beta, const float* runni
 int m3t_bn_act(const void* y, const float* scale, const float* shift, const void* res, const float* res_scale,
                const float* res_shift, int relu, void* out, long long rows, int C, void* stream);
 /* Backward of m3t_bn_act with batch statistics, two passes: reduce (sum dz, sum dz*xhat; optionally materialises
- * dz = dout*(out>0) for the residual branch) and apply (dy = scale*(dz - s0/n - xhat*s1/n)). */
+ * dz for the residual branch) and apply (dy = scale*(dz - s0/n - xhat*s1/n)).  relu: 0 = none, 1 = dz = dout*(out>0)
+ * from the stored activation, 2 = mask recomputed as (y*scale+shift > 0) (no residual: `out` may be NULL). */
 int m3t_bn_bwd_reduce(const void* dout, const void* out, const void* y, const float* mean, const float* invstd,
-                      int relu, void* dz_out, float* sums, long long rows, int C, void* stream);
+                      const float* scale, const float* shift, int relu, void* dz_out, float* sums, long long rows,
+                      int C, void* stream);
 int m3t_bn_bwd_apply(const void* dout, const void* out, const void* y, const float* mean, const float* invstd,
-                     const float* scale, const float* sums, double count, int relu, void* dy, long long rows, int C,
-                     void* stream);
+                     const float* scale, const float* shift, const float* sums, double count, int relu, void* dy,
+                     long long rows, int C, void* stream);
 /* BN apply + ReLU + spatial max-pool in one pass: out = maxpool_{KxK, stride S, pad PAD}( relu(y*scale+shift) ) over
  * (H,W) of [F][H][W][C]; idx (uint8, optional) is the arg-max tap kh*K+kw.  Replaces BatchNorm3d apply + ReLU +
  * MaxPool3d((1,3,3),(1,2,2),(0,1,1)) of the ResNet stem (models/backbone.py:329-331) and + MaxPool3d((1,2,2))

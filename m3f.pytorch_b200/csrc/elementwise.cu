@@ -228,9 +228,12 @@ __global__ void bn_act_kernel(const __nv_bfloat16* __restrict__ y, const float* 
 //   pass 2: dy = scale * (dz - sums0/n - xhat * sums1/n)
 // `dz_in` (pass 1 input override): when the same dz feeds a second BN (downsample branch) it is read, not recomputed.
 // ------------------------------------------------------------------------------------------------------------
+// relu: 0 = none, 1 = mask from the stored activation (out > 0), 2 = mask recomputed from y*scale + shift > 0 (units
+// without a residual input: `out` is then neither stored for backward nor read here)
 __global__ void bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ out,
                                      const __nv_bfloat16* __restrict__ y, const float* __restrict__ mean,
-                                     const float* __restrict__ invstd, int relu, __nv_bfloat16* __restrict__ dz_out,
+                                     const float* __restrict__ invstd, const float* __restrict__ scale,
+                                     const float* __restrict__ shift, int relu, __nv_bfloat16* __restrict__ dz_out,
                                      float* __restrict__ sums, long long rows, int C) {
   // block handles a strip of rows for all channels: thread -> (channel group cg = tid % (C/8), row lane)
   extern __shared__ float sh[];  // [2][C]
@@ -240,22 +243,29 @@ __global__ void bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, con
   const int rl = threadIdx.x / cgs;
   for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sh[i] = 0.f;
   __syncthreads();
-  float a0[8], a1[8], mu[8], is[8];
+  float a0[8], a1[8], mu[8], is[8], sc[8], sft[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) a0[j] = a1[j] = 0.f;
+  for (int j = 0; j < 8; ++j) a0[j] = a1[j] = sc[j] = sft[j] = 0.f;
   load8f(mean + cg * 8, mu);
   load8f(invstd + cg * 8, is);
+  if (relu == 2) {
+    load8f(scale + cg * 8, sc);
+    load8f(shift + cg * 8, sft);
+  }
   if (rl < rows_per_iter) {
     for (long long r = (long long)blockIdx.x * rows_per_iter + rl; r < rows; r += (long long)gridDim.x * rows_per_iter) {
       const long long i = r * cgs + cg;
       float d[8], yy[8];
       unpack8(__ldg(reinterpret_cast<const uint4*>(dout) + i), d);
       unpack8(__ldg(reinterpret_cast<const uint4*>(y) + i), yy);
-      if (relu) {
+      if (relu == 1) {
         float o[8];
         unpack8(__ldg(reinterpret_cast<const uint4*>(out) + i), o);
 #pragma unroll
         for (int j = 0; j < 8; ++j) d[j] = o[j] > 0.f ? d[j] : 0.f;
+      } else if (relu == 2) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) d[j] = fmaf(yy[j], sc[j], sft[j]) > 0.f ? d[j] : 0.f;
       }
       if (dz_out) reinterpret_cast<uint4*>(dz_out)[i] = pack8(d);
 #pragma unroll
@@ -277,23 +287,28 @@ __global__ void bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, con
 __global__ void bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ out,
                                     const __nv_bfloat16* __restrict__ y, const float* __restrict__ mean,
                                     const float* __restrict__ invstd, const float* __restrict__ scale,
-                                    const float* __restrict__ sums, float inv_count, int relu,
-                                    __nv_bfloat16* __restrict__ dy, long long nvec, int C) {
+                                    const float* __restrict__ shift, const float* __restrict__ sums, float inv_count,
+                                    int relu, __nv_bfloat16* __restrict__ dy, long long nvec, int C) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec;
        i += (long long)gridDim.x * blockDim.x) {
     const int c = (int)((i * 8) % C);
     float d[8], yy[8], mu[8], is[8], sc[8], s0[8], s1[8];
     unpack8(__ldg(reinterpret_cast<const uint4*>(dout) + i), d);
     unpack8(__ldg(reinterpret_cast<const uint4*>(y) + i), yy);
-    if (relu) {
+    load8f(scale + c, sc);
+    if (relu == 1) {
       float o[8];
       unpack8(__ldg(reinterpret_cast<const uint4*>(out) + i), o);
 #pragma unroll
       for (int j = 0; j < 8; ++j) d[j] = o[j] > 0.f ? d[j] : 0.f;
+    } else if (relu == 2) {
+      float sh[8];
+      load8f(shift + c, sh);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) d[j] = fmaf(yy[j], sc[j], sh[j]) > 0.f ? d[j] : 0.f;
     }
     load8f(mean + c, mu);
     load8f(invstd + c, is);
-    load8f(scale + c, sc);
     load8f(sums + c, s0);
     load8f(sums + C + c, s1);
 #pragma unroll
@@ -787,27 +802,27 @@ extern "C" int m3t_bn_act(const void* y, const float* scale, const float* shift,
 }
 
 extern "C" int m3t_bn_bwd_reduce(const void* dout, const void* out, const void* y, const float* mean,
-                                 const float* invstd, int relu, void* dz_out, float* sums, long long rows, int C,
-                                 void* stream) {
+                                 const float* invstd, const float* scale, const float* shift, int relu, void* dz_out,
+                                 float* sums, long long rows, int C, void* stream) {
   if (C % 8 || (kEwThreads % (C / 8)) != 0) return -1;
   const int cgs = C / 8;
   const int rows_per_iter = kEwThreads / cgs;
   long long blocks = (rows + rows_per_iter - 1) / rows_per_iter;
   if (blocks > 148 * 8) blocks = 148 * 8;
   bn_bwd_reduce_kernel<<<(int)blocks, kEwThreads, 2 * C * sizeof(float), ST(stream)>>>(
-      CBF(dout), CBF(out), CBF(y), mean, invstd, relu, BF(dz_out), sums, rows, C);
+      CBF(dout), CBF(out), CBF(y), mean, invstd, scale, shift, relu, BF(dz_out), sums, rows, C);
   count_launch();
   return launch_status();
 }
 
 extern "C" int m3t_bn_bwd_apply(const void* dout, const void* out, const void* y, const float* mean,
-                                const float* invstd, const float* scale, const float* sums, double count, int relu,
-                                void* dy, long long rows, int C, void* stream) {
+                                const float* invstd, const float* scale, const float* shift, const float* sums,
+                                double count, int relu, void* dy, long long rows, int C, void* stream) {
   if (C % 8) return -1;
   const long long nvec = rows * C / 8;
   bn_bwd_apply_kernel<<<ew_blocks(nvec), kEwThreads, 0, ST(stream)>>>(CBF(dout), CBF(out), CBF(y), mean, invstd, scale,
-                                                                      sums, (float)(1.0 / count), relu, BF(dy), nvec,
-                                                                      C);
+                                                                      shift, sums, (float)(1.0 / count), relu, BF(dy),
+                                                                      nvec, C);
   count_launch();
   return launch_status();
 }

@@ -21,7 +21,7 @@ constexpr int kGruThreads = 256;
 constexpr int kJS = 32;          // hidden units per CTA
 constexpr int kFwdBS = 64;       // batch rows per slice (forward)
 constexpr int kBwdBS = 32;       // batch rows per slice (backward)
-constexpr int kMaxSlicesPerCta = 8;
+constexpr int kMaxSlicesPerCta = 4;
 
 __device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], uint32_t saddr) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
@@ -144,6 +144,22 @@ __global__ void __launch_bounds__(kGruThreads, 1) gru_fwd_kernel(const GruParams
       for (int i = 0; i < 6; ++i)
 #pragma unroll
         for (int e = 0; e < 4; ++e) acc[i][e] = 0.f;
+      // the x-projection of this step does not depend on h: fetch it before waiting on the other slices
+      // (element pairs (e&1) are adjacent hidden units -> 8-byte loads)
+      float2 gir[4], giz[4], gin[4];
+#pragma unroll
+      for (int pr = 0; pr < 4; ++pr) {
+        const int hh = pr >> 1, rs = pr & 1;
+        const int b = b0 + mrow + (lane >> 2) + rs * 8;
+        const int j = js * kJS + 16 * jhalf + 8 * hh + (lane & 3) * 2;
+        gir[pr] = giz[pr] = gin[pr] = make_float2(0.f, 0.f);
+        if (b < B) {
+          const float* gi = p.gi + ((long long)b * T + t) * 6 * H + dir * 3 * H + j;
+          gir[pr] = __ldg(reinterpret_cast<const float2*>(gi));
+          giz[pr] = __ldg(reinterpret_cast<const float2*>(gi + H));
+          gin[pr] = __ldg(reinterpret_cast<const float2*>(gi + 2 * H));
+        }
+      }
       if (step > 0) {
         group_wait(counter, (unsigned)(step * nsl));
         // stage h_{t-1} of this batch slice (bf16, written by the nsl CTAs of the group) -> smem
@@ -170,32 +186,37 @@ __global__ void __launch_bounds__(kGruThreads, 1) gru_fwd_kernel(const GruParams
           }
         }
       }
-      // gate math on the 8 owned (b, j) elements
+      // gate math on the 8 owned (b, j) elements, as 4 pairs of adjacent hidden units
 #pragma unroll
-      for (int hh = 0; hh < 2; ++hh) {
+      for (int pr = 0; pr < 4; ++pr) {
+        const int hh = pr >> 1, rs = pr & 1;
+        const int b = b0 + mrow + (lane >> 2) + rs * 8;
+        const int j = js * kJS + 16 * jhalf + 8 * hh + (lane & 3) * 2;
+        if (b < B) {
+          const long long row = (long long)b * T + t;
+          float hnew[2], rr[2], zz[2], nn[2], hnn[2];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int b = b0 + mrow + (lane >> 2) + (e >> 1) * 8;
-          const int jl = 16 * jhalf + 8 * hh + (lane & 3) * 2 + (e & 1);
-          const int j = js * kJS + jl;
-          if (b < B) {
-            const long long row = (long long)b * T + t;
-            const float* gi = p.gi + row * 6 * H + dir * 3 * H + j;
+          for (int q = 0; q < 2; ++q) {
+            const int e = rs * 2 + q;
             const float hp = hreg[si][hh * 4 + e];
-            const float hr = acc[0 + hh][e] + bhh[0][hh * 2 + (e & 1)];
-            const float hz = acc[2 + hh][e] + bhh[1][hh * 2 + (e & 1)];
-            const float hn = acc[4 + hh][e] + bhh[2][hh * 2 + (e & 1)];
-            const float r = sigmoidf_(__ldg(gi) + hr);
-            const float z = sigmoidf_(__ldg(gi + H) + hz);
-            const float n = tanhf(__ldg(gi + 2 * H) + r * hn);
-            const float hnew = (1.f - z) * n + z * hp;
-            hreg[si][hh * 4 + e] = hnew;
-            p.out[row * 2 * H + dir * H + j] = __float2bfloat16(hnew);
-            if (p.out_f32) p.out_f32[row * 2 * H + dir * H + j] = hnew;
-            if (p.saved) {
-              float* sv = p.saved + (row * 2 + dir) * 4 * H + j;
-              sv[0] = r; sv[H] = z; sv[2 * H] = n; sv[3 * H] = hn;
-            }
+            const float hr = acc[0 + hh][e] + bhh[0][hh * 2 + q];
+            const float hz = acc[2 + hh][e] + bhh[1][hh * 2 + q];
+            const float hn = acc[4 + hh][e] + bhh[2][hh * 2 + q];
+            const float r = sigmoidf_((q ? gir[pr].y : gir[pr].x) + hr);
+            const float z = sigmoidf_((q ? giz[pr].y : giz[pr].x) + hz);
+            const float n = tanhf((q ? gin[pr].y : gin[pr].x) + r * hn);
+            hnew[q] = (1.f - z) * n + z * hp;
+            hreg[si][hh * 4 + e] = hnew[q];
+            rr[q] = r; zz[q] = z; nn[q] = n; hnn[q] = hn;
+          }
+          *reinterpret_cast<uint32_t*>(p.out + row * 2 * H + dir * H + j) = pack_bf16x2(hnew[0], hnew[1]);
+          if (p.out_f32) *reinterpret_cast<float2*>(p.out_f32 + row * 2 * H + dir * H + j) = make_float2(hnew[0], hnew[1]);
+          if (p.saved) {
+            float* sv = p.saved + (row * 2 + dir) * 4 * H + j;
+            *reinterpret_cast<float2*>(sv) = make_float2(rr[0], rr[1]);
+            *reinterpret_cast<float2*>(sv + H) = make_float2(zz[0], zz[1]);
+            *reinterpret_cast<float2*>(sv + 2 * H) = make_float2(nn[0], nn[1]);
+            *reinterpret_cast<float2*>(sv + 3 * H) = make_float2(hnn[0], hnn[1]);
           }
         }
       }

@@ -147,7 +147,8 @@ class ConvBNAct(torch.autograd.Function):
         fin = raw.bn_finalize(stats, count, gamma.detach(), beta.detach(), BN_EPS, BN_MOMENTUM, running_mean,
                               running_var)
         out = raw.bn_act(y, fin[2], fin[3], res=residual, relu=relu)
-        ctx.save_for_backward(x, w, y, out if relu else None, fin)
+        # the ReLU mask of a unit without residual is recomputed from y in backward: `out` is not kept for it
+        ctx.save_for_backward(x, w, y, out if (relu and residual is not None) else None, fin)
         ctx.geom, ctx.stride, ctx.pad, ctx.relu, ctx.count = geom, stride, pad, relu, count
         ctx.has_res = residual is not None
         return out
@@ -159,8 +160,8 @@ class ConvBNAct(torch.autograd.Function):
         mean, invstd, scale = fin[0], fin[1], fin[2]
         relu = ctx.relu
         need_dz = ctx.has_res and relu
-        sums, dz = raw.bn_bwd_reduce(dout, out, y, mean, invstd, relu, need_dz)
-        dy = raw.bn_bwd_apply(dout, out, y, mean, invstd, scale, sums, ctx.count, relu)
+        sums, dz = raw.bn_bwd_reduce(dout, out, y, mean, invstd, relu, need_dz, scale=scale, shift=fin[3])
+        dy = raw.bn_bwd_apply(dout, out, y, mean, invstd, scale, sums, ctx.count, relu, shift=fin[3])
         dres = None
         if ctx.has_res:
             dres = dz if relu else dout
@@ -573,7 +574,7 @@ class ConvNdBNAct(torch.autograd.Function):
             out = out.view(N, Z, out.shape[1], out.shape[2], Cout)
         else:
             out = raw.bn_act(y, fin[2], fin[3], relu=relu)
-        ctx.save_for_backward(x, w, y, pidx, out if (relu and not pool) else None, fin)
+        ctx.save_for_backward(x, w, y, pidx, None, fin)      # ReLU mask recomputed from y in backward
         ctx.cfg, ctx.geom, ctx.count, ctx.flops = cfg, geom, count, flops
         ctx.has_bias = cbias is not None
         return out if nd == 3 else out.view(N, Q, Cout)
@@ -592,8 +593,8 @@ class ConvNdBNAct(torch.autograd.Function):
             dy = dy.view(y.shape)
         else:
             d5 = dout.view(y.shape)
-            sums, _ = raw.bn_bwd_reduce(d5, out, y, fin[0], fin[1], relu, False)
-            dy = raw.bn_bwd_apply(d5, out, y, fin[0], fin[1], fin[2], sums, ctx.count, relu)
+            sums, _ = raw.bn_bwd_reduce(d5, None, y, fin[0], fin[1], relu, False, scale=fin[2], shift=fin[3])
+            dy = raw.bn_bwd_apply(d5, None, y, fin[0], fin[1], fin[2], sums, ctx.count, relu, shift=fin[3])
         dwp = raw.conv_wgrad(x, dy, geom, algo_flops=ctx.flops)
         if cfg.get("s2d_first"):
             dw = raw.scatter_unpack(dwp, vggm_s2d_index(w.device), (Cout, w[0].numel())).view(w.shape)
@@ -634,15 +635,15 @@ class Conv3x3C1BNReLU(torch.autograd.Function):
         fin = raw.bn_finalize(stats, y.shape[0], gamma.detach(), beta.detach(), BN_EPS, BN_MOMENTUM, running_mean,
                               running_var)
         out = raw.bn_act(y, fin[2], fin[3], relu=True)
-        ctx.save_for_backward(patches, w, y, out, fin)
+        ctx.save_for_backward(patches, w, y, None, fin)
         return out.view(N, H, W, Cout)
 
     @staticmethod
     def backward(ctx, dout):
         patches, w, y, out, fin = ctx.saved_tensors
         d2 = dout.contiguous().view(y.shape)
-        sums, _ = raw.bn_bwd_reduce(d2, out, y, fin[0], fin[1], True, False)
-        dy = raw.bn_bwd_apply(d2, out, y, fin[0], fin[1], fin[2], sums, y.shape[0], True)
+        sums, _ = raw.bn_bwd_reduce(d2, None, y, fin[0], fin[1], True, False, scale=fin[2], shift=fin[3])
+        dy = raw.bn_bwd_apply(d2, None, y, fin[0], fin[1], fin[2], sums, y.shape[0], True, shift=fin[3])
         dwp = raw.gemm(dy, patches, a_mn=True, b_mn=True, out_dtype=torch.float32)     # [Cout, 16]
         dw = dwp[:, :9].reshape(w.shape)
         return None, dw, sums[1], sums[0], None, None, None

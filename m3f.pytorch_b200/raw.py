@@ -282,23 +282,35 @@ def bn_act(y, scale, shift, res=None, res_scale=None, res_shift=None, relu=True)
     return out
 
 
-def bn_bwd_reduce(dout, out, y, mean, invstd, relu, want_dz):
+def _relu_mode(relu, out):
+    """0 = no ReLU, 1 = mask from the stored activation, 2 = mask recomputed from y*scale+shift (out is None)."""
+    if not relu:
+        return 0
+    return 1 if out is not None else 2
+
+
+def bn_bwd_reduce(dout, out, y, mean, invstd, relu, want_dz, scale=None, shift=None):
     C = y.shape[-1]
     rows = y.numel() // C
     sums = torch.zeros((2, C), device=y.device, dtype=torch.float32)
     dz = torch.empty_like(y) if want_dz else None
-    L.check(_lib().m3t_bn_bwd_reduce(L.ptr(dout), L.ptr(out), L.ptr(y), L.ptr(mean), L.ptr(invstd), L.i32(relu),
-                                     L.ptr(dz), L.ptr(sums), L.i64(rows), L.i32(C), L.stream_ptr()), "bn_bwd_reduce")
+    mode = _relu_mode(relu, out)
+    assert mode != 2 or (scale is not None and shift is not None)
+    L.check(_lib().m3t_bn_bwd_reduce(L.ptr(dout), L.ptr(out), L.ptr(y), L.ptr(mean), L.ptr(invstd), L.ptr(scale),
+                                     L.ptr(shift), L.i32(mode), L.ptr(dz), L.ptr(sums), L.i64(rows), L.i32(C),
+                                     L.stream_ptr()), "bn_bwd_reduce")
     return sums, dz
 
 
-def bn_bwd_apply(dout, out, y, mean, invstd, scale, sums, count, relu):
+def bn_bwd_apply(dout, out, y, mean, invstd, scale, sums, count, relu, shift=None):
     C = y.shape[-1]
     rows = y.numel() // C
     dy = torch.empty_like(y)
+    mode = _relu_mode(relu, out)
+    assert mode != 2 or shift is not None
     L.check(_lib().m3t_bn_bwd_apply(L.ptr(dout), L.ptr(out), L.ptr(y), L.ptr(mean), L.ptr(invstd), L.ptr(scale),
-                                    L.ptr(sums), ctypes_double(count), L.i32(relu), L.ptr(dy), L.i64(rows), L.i32(C),
-                                    L.stream_ptr()), "bn_bwd_apply")
+                                    L.ptr(shift), L.ptr(sums), ctypes_double(count), L.i32(mode), L.ptr(dy),
+                                    L.i64(rows), L.i32(C), L.stream_ptr()), "bn_bwd_apply")
     return dy
 
 

@@ -311,6 +311,18 @@ def case_elementwise(seed=0):
     sums, dz = raw.bn_bwd_reduce(dout.cuda(), o, y.cuda(), mean.cuda(), invstd.cuda(), True, True)
     dy = raw.bn_bwd_apply(dout.cuda(), o, y.cuda(), mean.cuda(), invstd.cuda(), scale.cuda(), sums, y.numel() // C,
                           True)
+    # mask recomputed from y (unit without residual)
+    o2 = raw.bn_act(y.cuda(), scale.cuda(), shift.cuda(), None, None, None, True)
+    sums2, _ = raw.bn_bwd_reduce(dout.cuda(), None, y.cuda(), mean.cuda(), invstd.cuda(), True, False,
+                                 scale=scale.cuda(), shift=shift.cuda())
+    dy2 = raw.bn_bwd_apply(dout.cuda(), None, y.cuda(), mean.cuda(), invstd.cuda(), scale.cuda(), sums2,
+                           y.numel() // C, True, shift=shift.cuda())
+    yq = y.float().permute(0, 3, 1, 2).clone().requires_grad_(True)
+    gq, bq = gam.clone().requires_grad_(True), bet.clone().requires_grad_(True)
+    F.batch_norm(yq, None, None, gq, bq, True, 0.1, 1e-5).relu().backward(dout.float().permute(0, 3, 1, 2))
+    errs["bn_bwd2_dy"] = _err(dy2.float().cpu().permute(0, 3, 1, 2), yq.grad)
+    errs["bn_bwd2_dgamma"] = _err(sums2[1], gq.grad)
+    errs["bn_bwd2_dbeta"] = _err(sums2[0], bq.grad)
     yr = y.float().permute(0, 3, 1, 2).clone().requires_grad_(True)
     rr = res.float().permute(0, 3, 1, 2).clone().requires_grad_(True)
     gp, bp = gam.clone().requires_grad_(True), bet.clone().requires_grad_(True)

@@ -38,7 +38,7 @@ def main():
     raw.conv_wgrad(x, y1.view(F, 28, 28, 64), g1)
     o = raw.bn_act(y1, ss[2], ss[3], res=x, relu=True)
     sums, dz = raw.bn_bwd_reduce(o, o, y1, ss[0], ss[1], True, True)
-    raw.bn_bwd_apply(o, o, y1, ss[0], ss[1], ss[2], sums, F * 784, True)
+    raw.bn_bwd_apply(o, o, y1, ss[0], ss[1], ss[2], sums, F * 784, True, shift=ss[3])
     del x, y1, o, dz
     # layer2 / layer4 fprop
     x = rb(F, 14, 14, 128)
