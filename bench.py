@@ -22,6 +22,18 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# dram__bytes_read.sum + dram__bytes_write.sum per call of the kernels that can be the dominant one, from the
+# `ncu --set full` capture at this workload (profiles/r1_ncu_full_summary.md; 256 clips x 16 frames per GPU)
+NCU_DRAM_TRAFFIC_256 = {
+    "wgrad-halo stem 16x56x56": 15.85e9,        # sum over its 5 launches (one per temporal tap)
+    "stem-halo 16x56x56": 3.244e9,
+    "stem nd3 16x56x56 c64->64 k5x4x1 s1": 3.248e9,
+    "wgrad nd3 16x56x56 c64->64 k5x4x1 s1": 8.788e9,
+    "fprop-halo nd2 1x28x28 c64->64 k1x3x3 s1": 0.772e9,
+    "dgrad-halo nd2 1x28x28 c64->64 k1x3x3 s1": 0.772e9,
+    "wgrad-halo nd2 1x28x28 c64->64 k1x3x3 s1": 0.826e9,
+}
+
 METRIC = "av_m3t_train_frames_per_sec"
 UNIT = "frames/s"
 T_FRAMES = 16
@@ -287,7 +299,8 @@ def run_b200(args, rank, local_rank, world):
             d = conv[dom_key]
             roof = {"bound": "tensor", "kernel": "umma_kernel (tcgen05 implicit GEMM): " + dom_key,
                     "achieved": d["tflops"], "peak": peak, "unit": "TFLOP/s", "frac": d["tflops"] / peak,
-                    "traffic": None, "peak_source": peak_src,
+                    "traffic": NCU_DRAM_TRAFFIC_256.get(dom_key) if args.clips == 256 else None,
+                    "peak_source": peak_src,
                     "avg_launch_ms": d["ms_total"] / d["calls"], "launches_timed": d["calls"],
                     "all_conv_kernels": {"tflops": tot_fl / (tot_ms * 1e-3) / 1e12 if tot_ms else None,
                                          "share_of_step": tot_ms / ms if ms else None}}

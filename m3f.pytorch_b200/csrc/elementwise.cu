@@ -230,11 +230,13 @@ __global__ void bn_act_kernel(const __nv_bfloat16* __restrict__ y, const float* 
 // ------------------------------------------------------------------------------------------------------------
 // relu: 0 = none, 1 = mask from the stored activation (out > 0), 2 = mask recomputed from y*scale + shift > 0 (units
 // without a residual input: `out` is then neither stored for backward nor read here)
-__global__ void bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ out,
-                                     const __nv_bfloat16* __restrict__ y, const float* __restrict__ mean,
-                                     const float* __restrict__ invstd, const float* __restrict__ scale,
-                                     const float* __restrict__ shift, int relu, __nv_bfloat16* __restrict__ dz_out,
-                                     float* __restrict__ sums, long long rows, int C) {
+template <int relu>
+__global__ void __launch_bounds__(256, relu == 2 ? 3 : 4)
+bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ out,
+                     const __nv_bfloat16* __restrict__ y, const float* __restrict__ mean,
+                     const float* __restrict__ invstd, const float* __restrict__ scale,
+                     const float* __restrict__ shift, __nv_bfloat16* __restrict__ dz_out, float* __restrict__ sums,
+                     long long rows, int C) {
   // block handles a strip of rows for all channels: thread -> (channel group cg = tid % (C/8), row lane)
   extern __shared__ float sh[];  // [2][C]
   const int cgs = C / 8;
@@ -809,8 +811,16 @@ extern "C" int m3t_bn_bwd_reduce(const void* dout, const void* out, const void* 
   const int rows_per_iter = kEwThreads / cgs;
   long long blocks = (rows + rows_per_iter - 1) / rows_per_iter;
   if (blocks > 148 * 8) blocks = 148 * 8;
-  bn_bwd_reduce_kernel<<<(int)blocks, kEwThreads, 2 * C * sizeof(float), ST(stream)>>>(
-      CBF(dout), CBF(out), CBF(y), mean, invstd, scale, shift, relu, BF(dz_out), sums, rows, C);
+  const size_t sm = 2 * C * sizeof(float);
+  if (relu == 0)
+    bn_bwd_reduce_kernel<0><<<(int)blocks, kEwThreads, sm, ST(stream)>>>(CBF(dout), CBF(out), CBF(y), mean, invstd,
+                                                                        scale, shift, BF(dz_out), sums, rows, C);
+  else if (relu == 1)
+    bn_bwd_reduce_kernel<1><<<(int)blocks, kEwThreads, sm, ST(stream)>>>(CBF(dout), CBF(out), CBF(y), mean, invstd,
+                                                                        scale, shift, BF(dz_out), sums, rows, C);
+  else
+    bn_bwd_reduce_kernel<2><<<(int)blocks, kEwThreads, sm, ST(stream)>>>(CBF(dout), CBF(out), CBF(y), mean, invstd,
+                                                                        scale, shift, BF(dz_out), sums, rows, C);
   count_launch();
   return launch_status();
 }

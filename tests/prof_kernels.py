@@ -19,8 +19,10 @@ def main():
     w = (torch.randn(64, 1280, device=dev) * 0.03).bfloat16()
     g = raw.conv_geom(3, B, T, 56, 56, 64, 64, (5, 4, 1), (1, 1, 1), (2, 2, 0), (2, 1, 0), (1, 1, 1))
     st = torch.zeros(2, 64, device=dev)
-    y = raw.conv_fprop(xs, w, g, stats=st, tag="stem")
-    raw.conv_wgrad(xs, y, g)
+    y = raw.stem_fprop_halo(xs, w, stats=st)                 # halo kernels (product path)
+    raw.wgrad_stem_halo(xs, y)
+    y = raw.conv_fprop(xs, w, g, stats=st, tag="stem")       # generic im2col kernels, for comparison
+    raw.conv_wgrad(xs, y, g, splits=59)
     # stem tail fwd/bwd
     ss = torch.rand(4, 64, device=dev) + 0.5
     y4 = y.view(F, 56, 56, 64)
@@ -35,7 +37,8 @@ def main():
     raw.USE_HALO = False
     raw.conv_fprop(x, w1, g1, stats=st)
     raw.USE_HALO = True
-    raw.conv_wgrad(x, y1.view(F, 28, 28, 64), g1)
+    raw.conv_wgrad(x, y1.view(F, 28, 28, 64), g1)             # halo wgrad
+    raw.conv_wgrad(x, y1.view(F, 28, 28, 64), g1, splits=59)  # generic
     o = raw.bn_act(y1, ss[2], ss[3], res=x, relu=True)
     sums, dz = raw.bn_bwd_reduce(o, o, y1, ss[0], ss[1], True, True)
     raw.bn_bwd_apply(o, o, y1, ss[0], ss[1], ss[2], sums, F * 784, True, shift=ss[3])
