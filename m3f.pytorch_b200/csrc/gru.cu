@@ -43,6 +43,14 @@ __device__ __forceinline__ uint4 ld_cg_u4(const void* p) {
   asm volatile("ld.global.cg.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
   return v;
 }
+// 16-byte async copy global(L2) -> shared; src_bytes = 0 zero-fills the destination (rows past the batch)
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(src_bytes)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
 __device__ __forceinline__ float ld_cg_bf16(const __nv_bfloat16* p) {
   unsigned short v;
   asm volatile("ld.global.cg.u16 %0, [%1];" : "=h"(v) : "l"(p));
@@ -166,10 +174,11 @@ __global__ void __launch_bounds__(kGruThreads, 1) gru_fwd_kernel(const GruParams
         for (int i = tid; i < kFwdBS * vec_per_row; i += kGruThreads) {
           const int row = i / vec_per_row, v = i - row * vec_per_row;
           const int b = b0 + row;
-          uint4 val = make_uint4(0, 0, 0, 0);
-          if (b < B) val = ld_cg_u4(p.out + ((long long)b * T + tprev) * 2 * H + dir * H + v * 8);
-          *reinterpret_cast<uint4*>(hsm + row * ldk + v * 8) = val;
+          const bool ok = b < B;
+          cp_async16(hsm + row * ldk + v * 8,
+                     p.out + ((long long)(ok ? b : 0) * T + tprev) * 2 * H + dir * H + v * 8, ok ? 16 : 0);
         }
+        cp_async_wait_all();
         __syncthreads();
         const uint32_t a_base = smem_u32(hsm + (mrow + (lane & 7) + ((lane >> 3) & 1) * 8) * ldk + (lane >> 4) * 8);
         const uint32_t b_base =
@@ -259,19 +268,19 @@ __global__ void __launch_bounds__(kGruThreads, 1) gru_bwd_kernel(const GruParams
     const int t = dir == 0 ? T - 1 - step : step;       // reverse of the forward order
     const int tprev = dir == 0 ? t - 1 : t + 1;         // time index of h_{prev} in forward order
     const bool has_prev = tprev >= 0 && tprev < T;
+    float dh_direct[kMaxSlicesPerCta][4];
+    // ---- phase A for every batch slice of this CTA, each followed by its group arrival: the barrier latency of
+    //      slice i overlaps the element-wise work of slice i+1 ----
 #pragma unroll
     for (int si = 0; si < kMaxSlicesPerCta; ++si) {
       const int bs = blockIdx.y + si * gridDim.y;
       if (bs >= p.nbslices) break;
       const int b0 = bs * kBwdBS;
-      unsigned* counter = p.counters + dir * p.nbslices + bs;
-      float dh_direct[4];
-      // ---- phase A ----
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int b = b0 + mrow + (lane >> 2) + (e >> 1) * 8;
         const int j = js * kJS + ncol + (lane & 3) * 2 + (e & 1);
-        dh_direct[e] = 0.f;
+        dh_direct[si][e] = 0.f;
         if (b < B) {
           const long long row = (long long)b * T + t;
           const float dh = __bfloat162float(p.dout[row * 2 * H + dir * H + j]) + dhrec[si][e];
@@ -292,20 +301,27 @@ __global__ void __launch_bounds__(kGruThreads, 1) gru_bwd_kernel(const GruParams
           p.dgh[g0 + H] = __float2bfloat16(daz);
           p.dgh[g0 + 2 * H] = __float2bfloat16(dan * r);
           p.hprev[(row * 2 + dir) * H + j] = __float2bfloat16(hp);
-          dh_direct[e] = dh * z;
+          dh_direct[si][e] = dh * z;
         }
       }
-      if (step + 1 == T) continue;  // gradient wrt h_0 is not needed
-      group_arrive(counter);
-      group_wait(counter, (unsigned)((step + 1) * nsl));
-      // ---- phase B ----
+      if (step + 1 < T) group_arrive(p.counters + dir * p.nbslices + bs);
+    }
+    if (step + 1 == T) break;  // gradient wrt h_0 is not needed
+    // ---- phase B ----
+#pragma unroll
+    for (int si = 0; si < kMaxSlicesPerCta; ++si) {
+      const int bs = blockIdx.y + si * gridDim.y;
+      if (bs >= p.nbslices) break;
+      const int b0 = bs * kBwdBS;
+      group_wait(p.counters + dir * p.nbslices + bs, (unsigned)((step + 1) * nsl));
       for (int i = tid; i < kBwdBS * vec_per_row; i += kGruThreads) {
         const int row = i / vec_per_row, v = i - row * vec_per_row;
         const int b = b0 + row;
-        uint4 val = make_uint4(0, 0, 0, 0);
-        if (b < B) val = ld_cg_u4(p.dgh + ((long long)b * T + t) * 6 * H + dir * 3 * H + v * 8);
-        *reinterpret_cast<uint4*>(gsm + row * ldk + v * 8) = val;
+        const bool ok = b < B;
+        cp_async16(gsm + row * ldk + v * 8, p.dgh + ((long long)(ok ? b : 0) * T + t) * 6 * H + dir * 3 * H + v * 8,
+                   ok ? 16 : 0);
       }
+      cp_async_wait_all();
       __syncthreads();
       float acc[4] = {0.f, 0.f, 0.f, 0.f};
       const uint32_t a_base = smem_u32(gsm + (mrow + (lane & 7) + ((lane >> 3) & 1) * 8) * ldk + (lane >> 4) * 8);
@@ -317,7 +333,7 @@ __global__ void __launch_bounds__(kGruThreads, 1) gru_bwd_kernel(const GruParams
         mma_16816(acc, a, bb[0], bb[1]);
       }
 #pragma unroll
-      for (int e = 0; e < 4; ++e) dhrec[si][e] = dh_direct[e] + acc[e];
+      for (int e = 0; e < 4; ++e) dhrec[si][e] = dh_direct[si][e] + acc[e];
       __syncthreads();  // gsm is rewritten by the next slice / step
     }
   }
