@@ -9,6 +9,7 @@
 // row-shifted view of the activation box used as an MN-major A operand, and two taps 64 channels wide form one
 // 128-row operand whose leading-dimension offset is simply the distance between the two views.  All accumulators of a
 // CTA ([taps*64] x 64 fp32) stay in TMEM over all its K-blocks and are flushed once with fp32 atomics.
+#include <cstdlib>
 #include "../../include/m3t_b200.h"
 #include "common.cuh"
 #include "tmap.cuh"
@@ -163,6 +164,171 @@ static int wg_launch(const CUtensorMap& tmX, const CUtensorMap& tmDY, WgHaloPara
   return launch_status();
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Stem weight gradient with the ACTIVATION box resident: one K-block = TR rows of one input frame f.  Its halo box is
+// loaded once and multiplied against the dY boxes of every output frame t = f + 2 - kt that reads it (kt in
+// [kt0, kt0+nkt)), so a K-block costs one X box + nkt dY boxes of L2->SM traffic for nkt*2 accumulators instead of
+// nkt * (X + dY).  TMEM holds at most 8 accumulators of 64 columns, so the five temporal taps take two passes.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kXresXStages = 2;
+constexpr int kXresDStages = 4;
+
+struct WgXresParams {
+  int B, T, H, TR, W;
+  int blocks_per_img, num_xblocks, ksteps;
+  int x_bytes, dy_bytes;
+  int kt0, nkt;
+  float* out;
+  int ldo;
+};
+
+__global__ void __launch_bounds__(kWgThreads, 1)
+wgrad_stem_xres_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY,
+                       const WgXresParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smemD = smem + kXresXStages * p.x_bytes;
+  uint64_t* xfull = reinterpret_cast<uint64_t*>(smemD + kXresDStages * p.dy_bytes);
+  uint64_t* xempty = xfull + kXresXStages;
+  uint64_t* dfull = xempty + kXresXStages;
+  uint64_t* dempty = dfull + kXresDStages;
+  uint64_t* tmem_full = dempty + kXresDStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  uint32_t* started_slot = tmem_slot + 1;
+  const int warp = threadIdx.x >> 5;
+  const uint32_t lane = lane_id();
+  const int n_acc = p.nkt * 2;
+  const uint32_t tm_cols = n_acc * 64 <= 128 ? 128 : (n_acc * 64 <= 256 ? 256 : 512);
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmDY);
+    for (int i = 0; i < kXresXStages; ++i) {
+      mbar_init(&xfull[i], 1);
+      mbar_init(&xempty[i], 1);
+    }
+    for (int i = 0; i < kXresDStages; ++i) {
+      mbar_init(&dfull[i], 1);
+      mbar_init(&dempty[i], 1);
+    }
+    mbar_init(tmem_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, tm_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int it = 0, dit = 0;
+      for (int kb = blockIdx.x; kb < p.num_xblocks; kb += gridDim.x, ++it) {
+        const int xs = it % kXresXStages;
+        mbar_wait(&xempty[xs], ((it / kXresXStages) & 1) ^ 1, 600 + xs);
+        const int n = kb / p.blocks_per_img;
+        const int h0 = (kb - n * p.blocks_per_img) * p.TR;
+        const int b = n / p.T, f = n - b * p.T;
+        mbar_arrive_expect_tx(&xfull[xs], p.x_bytes);
+        tma_load_5d(&tmX, &xfull[xs], smem + xs * p.x_bytes, 0, 0, h0 - 2, f, b);
+        for (int k = 0; k < p.nkt; ++k) {
+          const int t = f + 2 - (p.kt0 + k);
+          if (t < 0 || t >= p.T) continue;
+          const int ds = dit % kXresDStages;
+          mbar_wait(&dempty[ds], ((dit / kXresDStages) & 1) ^ 1, 610 + ds);
+          mbar_arrive_expect_tx(&dfull[ds], p.dy_bytes);
+          tma_load_4d(&tmDY, &dfull[ds], smemD + ds * p.dy_bytes, 0, 0, h0, b * p.T + t);
+          ++dit;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, 64, 1, 1);
+      const uint32_t lbo = (uint32_t)p.W * 128u;   // the second 64-channel atom of A is the next vertical tap
+      uint32_t started = 0;
+      int it = 0, dit = 0;
+      for (int kb = blockIdx.x; kb < p.num_xblocks; kb += gridDim.x, ++it) {
+        const int xs = it % kXresXStages;
+        const int n = kb / p.blocks_per_img;
+        const int f = n % p.T;
+        mbar_wait(&xfull[xs], (it / kXresXStages) & 1, 620 + xs);
+        const uint32_t sX = smem_u32(smem + xs * p.x_bytes);
+        for (int k = 0; k < p.nkt; ++k) {
+          const int t = f + 2 - (p.kt0 + k);
+          if (t < 0 || t >= p.T) continue;
+          const int ds = dit % kXresDStages;
+          mbar_wait(&dfull[ds], (dit / kXresDStages) & 1, 630 + ds);
+          tc_fence_after();
+          const uint32_t sD = smem_u32(smemD + ds * p.dy_bytes);
+          const uint32_t first = ((started >> k) & 1u) ^ 1u;
+          for (int ks = 0; ks < p.ksteps; ++ks) {
+            const uint64_t bdesc = make_smem_desc(sD + ks * 2048, 8192, 1024, SWZ_128B);
+#pragma unroll
+            for (int jp = 0; jp < 2; ++jp) {
+              const uint64_t adesc =
+                  make_smem_desc(sX + (uint32_t)(2 * jp * p.W + ks * 16) * 128u, lbo, 1024, SWZ_128B);
+              umma_bf16(tmem_base + (k * 2 + jp) * 64, adesc, bdesc, idesc, (first && ks == 0) ? 0u : 1u);
+            }
+          }
+          started |= 1u << k;
+          umma_commit(&dempty[ds]);
+          ++dit;
+        }
+        umma_commit(&xempty[xs]);
+      }
+      *started_slot = started;
+      __threadfence_block();
+      umma_commit(tmem_full);
+    }
+  } else if (blockIdx.x < p.num_xblocks) {
+    const int quad = warp & 3;
+    const int row = quad * 32 + (int)lane;
+    mbar_wait(tmem_full, 0, 640);
+    tc_fence_after();
+    const uint32_t started = *reinterpret_cast<volatile uint32_t*>(started_slot);
+    for (int a = 0; a < n_acc; ++a) {
+      if (!((started >> (a >> 1)) & 1u)) continue;
+      const int tap = (p.kt0 + (a >> 1)) * 4 + (a & 1) * 2 + (row >> 6);
+      const long long m = (long long)tap * 64 + (row & 63);
+      const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + a * 64;
+#pragma unroll 1
+      for (int c0 = 0; c0 < 64; c0 += 16) {
+        uint32_t r[16];
+        tmem_ld16(t_lane + c0, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) atomicAdd(p.out + (long long)(c0 + i) * p.ldo + m, __uint_as_float(r[i]));
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tm_cols);
+  }
+}
+
+static int wg_xres_launch(const CUtensorMap& tmX, const CUtensorMap& tmDY, const WgXresParams& p, cudaStream_t st) {
+  const int smem = kXresXStages * p.x_bytes + kXresDStages * p.dy_bytes + (2 * kXresXStages + 2 * kXresDStages + 1) * 8 +
+                   16 + 1024;
+  if (smem > 227 * 1024 || p.x_bytes % 1024 || p.dy_bytes % 1024) return -7;
+  static bool attr_done = false;
+  if (!attr_done) {
+    if (cudaFuncSetAttribute(wgrad_stem_xres_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) !=
+        cudaSuccess)
+      return -20;
+    attr_done = true;
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = p.num_xblocks < sms ? p.num_xblocks : sms;
+  wgrad_stem_xres_kernel<<<grid, kWgThreads, smem, st>>>(tmX, tmDY, p);
+  count_launch();
+  return launch_status();
+}
+
 }  // namespace m3t
 
 using namespace m3t;
@@ -232,6 +398,45 @@ extern "C" int m3t_wgrad_stem_halo(const void* xs, const void* dy, float* dw_pac
   uint32_t db[4] = {64, (uint32_t)W2, (uint32_t)TR, 1};
   rc = make_tmap_tiled_bf16(&tmDY, dy, 4, dd, dst, db, 128);
   if (rc) return rc;
+  // Activation-resident passes (see wgrad_stem_xres_kernel) when the boxes are whole 1 KB swizzle atoms and two X
+  // stages + four dY stages fit in shared memory; `split` = temporal taps per pass (TMEM holds four).
+  {
+    int TX = 0;
+    for (int t = 8; t >= 1; --t) {
+      const int xb = (t + 3) * W2 * 128, db = t * W2 * 128;
+      if ((t * W2) % 16 == 0 && xb % 1024 == 0 && db % 1024 == 0 &&
+          kXresXStages * xb + kXresDStages * db <= 220 * 1024) { TX = t; break; }
+    }
+    static int split = -1;
+    if (split < 0) {
+      const char* e = getenv("M3T_STEM_WGRAD_SPLIT");
+      split = e ? atoi(e) : 3;
+      if (split < 0 || split > 4) split = 3;
+    }
+    if (TX > 0 && split > 0) {
+      uint32_t xb2[5] = {64, (uint32_t)W2, (uint32_t)(TX + 3), 1, 1};
+      rc = make_tmap_tiled_bf16(&tmX, xs, 5, xd, xst, xb2, 128);
+      if (rc) return rc;
+      uint32_t db2[4] = {64, (uint32_t)W2, (uint32_t)TX, 1};
+      rc = make_tmap_tiled_bf16(&tmDY, dy, 4, dd, dst, db2, 128);
+      if (rc) return rc;
+      for (int kt0 = 0; kt0 < 5; kt0 += split) {
+        WgXresParams q;
+        memset(&q, 0, sizeof(q));
+        q.B = B; q.T = T; q.H = H2; q.TR = TX; q.W = W2;
+        q.blocks_per_img = (H2 + TX - 1) / TX;
+        q.num_xblocks = B * T * q.blocks_per_img;
+        q.ksteps = TX * W2 / 16;
+        q.x_bytes = (TX + 3) * W2 * 128;
+        q.dy_bytes = TX * W2 * 128;
+        q.kt0 = kt0; q.nkt = 5 - kt0 < split ? 5 - kt0 : split;
+        q.out = dw_packed; q.ldo = 20 * 64;
+        rc = wg_xres_launch(tmX, tmDY, q, reinterpret_cast<cudaStream_t>(stream));
+        if (rc) return rc;
+      }
+      return 0;
+    }
+  }
   for (int kt = 0; kt < 5; ++kt) {
     WgHaloParams p;
     memset(&p, 0, sizeof(p));

@@ -840,11 +840,13 @@ CASES["audio_resnet_tcn_train_fwd"] = (case_audio_resnet, _c(train=True))
 
 
 
-def case_stem_wgrad_halo(seed=0):
-    """Halo-tile stem wgrad (5 launches, one per temporal tap) vs the generic im2col wgrad and vs autograd."""
+def case_stem_wgrad_halo(B=2, T=5, seed=0):
+    """Halo-tile stem wgrad (activation box resident, temporal taps in two passes) vs the generic im2col wgrad and
+    vs autograd.  B*T*14 K-blocks: the small case gives every CTA one block (taps with no valid frame stay unstarted),
+    the large one makes CTAs accumulate over several frames and clips."""
     from m3t_b200 import raw
     g = torch.Generator().manual_seed(seed)
-    B, T, H2, W2 = 2, 5, 56, 56
+    H2, W2 = 56, 56
     xs = _rnd((B, T, H2, W2, 64), g).cuda()
     dy = _rnd((B * T, H2, W2, 64), g).cuda()
     geom = raw.conv_geom(3, B, T, H2, W2, 64, 64, (5, 4, 1), (1, 1, 1), (2, 2, 0), (2, 1, 0), (1, 1, 1))
@@ -861,6 +863,7 @@ def case_stem_wgrad_halo(seed=0):
 
 
 CASES["stem_wgrad_halo"] = (case_stem_wgrad_halo, _c())
+CASES["stem_wgrad_halo_3x16"] = (case_stem_wgrad_halo, _c(B=3, T=16))
 TOLS["vs_generic"] = 5e-3
 TOLS["vs_cpu"] = 1e-4
 
