@@ -475,6 +475,188 @@ __global__ void __launch_bounds__(256, 2) maxpool_bn_bwd_kernel(const __nv_bfloa
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// 3x3 / stride 2 / pad 1 specialisations for even H, W (the ResNet stem tail, 56x56 -> 28x28).  The generic
+// kernels above are instruction-bound (~320 instructions per 8 channels of one input position: index divisions and
+// 4 windows x 8 byte-compares each).  Here a thread owns a 2x2 input block x 8 channels: the block touches exactly
+// the four windows (a..a+1, b..b+1), each (idx, dout) pair is loaded once, and which argmax code of which window
+// names which of the four positions is a compile-time constant (9 compare sets instead of 16).
+// ------------------------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(256, 2)
+maxpool3s2_bn_bwd_kernel(const __nv_bfloat16* __restrict__ dout, const uint8_t* __restrict__ idx,
+                         const __nv_bfloat16* __restrict__ y, const float* __restrict__ mean,
+                         const float* __restrict__ invstd, const float* __restrict__ scale,
+                         const float* __restrict__ shift, float* __restrict__ sums, float inv_count,
+                         __nv_bfloat16* __restrict__ dy, int F, int H, int W, int C, int cg_shift) {
+  const int P = H / 2, Q = W / 2;
+  const int cgs = C / 8;
+  extern __shared__ float sh[];  // MODE 0: [2][C]
+  if (MODE == 0) {
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sh[i] = 0.f;
+    __syncthreads();
+  }
+  const int cg = threadIdx.x % cgs;
+  // MODE 0: a0 = sum dz, a1 = sum dz*y (centred at the end).  MODE 1: dy = kA*dz + kB*y + kC.
+  float s[8], b[8], a0[8], a1[8];
+  load8f(scale + cg * 8, s);
+  load8f(shift + cg * 8, b);
+  if (MODE == 1) {
+    float mu[8], is[8], s0[8], s1[8];
+    load8f(mean + cg * 8, mu);
+    load8f(invstd + cg * 8, is);
+    load8f(sums + cg * 8, s0);
+    load8f(sums + C + cg * 8, s1);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float kb = -s[j] * is[j] * s1[j] * inv_count;     // coefficient of (y - mu)
+      a0[j] = kb;
+      a1[j] = -s[j] * s0[j] * inv_count - kb * mu[j];
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a0[j] = a1[j] = 0.f;
+  }
+  const unsigned total = (unsigned)F * P * Q * cgs;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    unsigned r = i >> cg_shift;
+    const int bq = (int)(r % (unsigned)Q);
+    r /= (unsigned)Q;
+    const int ap = (int)(r % (unsigned)P);
+    const int f = (int)(r / (unsigned)P);
+    // windows (ap,bq) (ap,bq+1) (ap+1,bq) (ap+1,bq+1); missing ones get an argmax code that matches nothing
+    const bool okp = ap + 1 < P, okq = bq + 1 < Q;
+    const unsigned o00 = i;
+    const unsigned o01 = okq ? i + cgs : i;
+    const unsigned o10 = okp ? i + (unsigned)Q * cgs : i;
+    const unsigned o11 = okp ? o01 + (unsigned)Q * cgs : o01;
+    uint2 pk[4];
+    uint4 dv[4], yr[4];
+    pk[0] = __ldg(reinterpret_cast<const uint2*>(idx) + o00);
+    pk[1] = __ldg(reinterpret_cast<const uint2*>(idx) + o01);
+    pk[2] = __ldg(reinterpret_cast<const uint2*>(idx) + o10);
+    pk[3] = __ldg(reinterpret_cast<const uint2*>(idx) + o11);
+    dv[0] = __ldg(reinterpret_cast<const uint4*>(dout) + o00);
+    dv[1] = __ldg(reinterpret_cast<const uint4*>(dout) + o01);
+    dv[2] = __ldg(reinterpret_cast<const uint4*>(dout) + o10);
+    dv[3] = __ldg(reinterpret_cast<const uint4*>(dout) + o11);
+    const unsigned y00 = ((((unsigned)f * H + 2 * ap) * W + 2 * bq) << cg_shift) + cg;
+    const unsigned yoff[4] = {y00, y00 + cgs, y00 + (unsigned)W * cgs, y00 + (unsigned)W * cgs + cgs};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) yr[k] = __ldg(reinterpret_cast<const uint4*>(y) + yoff[k]);
+    if (!okq) { pk[1] = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu); }
+    if (!okp) { pk[2] = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu); }
+    if (!okp || !okq) { pk[3] = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu); }
+    float d[4][8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) unpack8(dv[k], d[k]);
+    // argmax code kh*3+kw of window k that names position (ph,pw) of the block; -1: the window does not cover it
+    constexpr int code[4][4] = {{4, -1, -1, -1}, {5, 3, -1, -1}, {7, -1, 1, -1}, {8, 6, 2, 0}};
+#pragma unroll
+    for (int pos = 0; pos < 4; ++pos) {
+      float dz[8], yy[8];
+      unpack8(yr[pos], yy);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) dz[j] = 0.f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (code[pos][k] < 0) continue;
+        const uint32_t m4 = (uint32_t)code[pos][k] * 0x01010101u;
+        const uint32_t x0 = pk[k].x ^ m4, x1 = pk[k].y ^ m4;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t xx = j < 4 ? x0 : x1;
+          if ((xx & (0xFFu << (8 * (j & 3)))) == 0u) dz[j] += d[k][j];
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float act = fmaf(yy[j], s[j], b[j]);
+        if (!(act > 0.f)) dz[j] = 0.f;
+      }
+      if (MODE == 0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          a0[j] += dz[j];
+          a1[j] = fmaf(dz[j], yy[j], a1[j]);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dz[j] = fmaf(s[j], dz[j], fmaf(a0[j], yy[j], a1[j]));
+        reinterpret_cast<uint4*>(dy)[yoff[pos]] = pack8(dz);
+      }
+    }
+  }
+  if (MODE == 0) {
+    float mu[8], is[8];
+    load8f(mean + cg * 8, mu);
+    load8f(invstd + cg * 8, is);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      atomicAdd(&sh[cg * 8 + j], a0[j]);
+      atomicAdd(&sh[C + cg * 8 + j], (a1[j] - mu[j] * a0[j]) * is[j]);   // sum dz*xhat
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(sums + i, sh[i]);
+  }
+}
+
+// Forward, same specialisation: all nine window loads are issued before the compare chain.
+__global__ void __launch_bounds__(256, 2)
+bn_relu_maxpool3s2_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ scale,
+                          const float* __restrict__ shift, __nv_bfloat16* __restrict__ out, uint8_t* __restrict__ idx,
+                          int F, int H, int W, int C, int cg_shift) {
+  const int P = H / 2, Q = W / 2;
+  const unsigned cgs = (unsigned)C / 8;
+  const unsigned total = (unsigned)F * P * Q * cgs;
+  const int cg = threadIdx.x % cgs;
+  float s[8], b[8];
+  load8f(scale + cg * 8, s);
+  load8f(shift + cg * 8, b);
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    unsigned r = i >> cg_shift;
+    const int q = (int)(r % (unsigned)Q);
+    r /= (unsigned)Q;
+    const int p = (int)(r % (unsigned)P);
+    const int f = (int)(r / (unsigned)P);
+    // rows 2p-1..2p+1, cols 2q-1..2q+1: only the -1 row / column can fall outside (H, W even)
+    const unsigned c00 = ((((unsigned)f * H + 2 * p) * W + 2 * q) << cg_shift) + cg;   // window centre (kh=kw=1)
+    const unsigned rs = (unsigned)W * cgs;
+    uint4 v[9];
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const bool ok = (kh > 0 || p > 0) && (kw > 0 || q > 0);
+        const unsigned o = c00 + (unsigned)(kh - 1) * rs + (unsigned)(kw - 1) * cgs;
+        v[kh * 3 + kw] = __ldg(reinterpret_cast<const uint4*>(y) + (ok ? o : c00));
+      }
+    }
+    float best[8];
+    int bi[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { best[j] = -INFINITY; bi[j] = 0; }
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      const bool ok = (k / 3 > 0 || p > 0) && (k % 3 > 0 || q > 0);
+      float x[8];
+      unpack8(v[k], x);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float a = ok ? fmaxf(fmaf(x[j], s[j], b[j]), 0.f) : -INFINITY;
+        if (a > best[j]) { best[j] = a; bi[j] = k; }
+      }
+    }
+    reinterpret_cast<uint4*>(out)[i] = pack8(best);
+    if (idx) {
+      uint2 pk;
+      pk.x = bi[0] | (bi[1] << 8) | (bi[2] << 16) | (bi[3] << 24);
+      pk.y = bi[4] | (bi[5] << 8) | (bi[6] << 16) | (bi[7] << 24);
+      reinterpret_cast<uint2*>(idx)[i] = pk;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // Global average pool over HW of [F][HW][C] bf16 -> [F][C] (bf16 and/or fp32); and its backward.
 // ------------------------------------------------------------------------------------------------------------
 __global__ void avgpool_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out_bf16,
@@ -851,7 +1033,10 @@ extern "C" int m3t_bn_relu_maxpool(const void* y, const float* scale, const floa
   const long long items = (long long)F * P * Q * (C / 8);
   if ((long long)F * H * W * (C / 8) >= (1LL << 31)) return -6;
   const int blocks = ew_blocks(items);
-  if (K == 3 && S == 2 && PAD == 1)
+  if (K == 3 && S == 2 && PAD == 1 && H % 2 == 0 && W % 2 == 0 && kEwThreads % (C / 8) == 0)
+    bn_relu_maxpool3s2_kernel<<<blocks, kEwThreads, 0, ST(stream)>>>(CBF(y), scale, shift, BF(out),
+                                                                   reinterpret_cast<uint8_t*>(idx), F, H, W, C, sh);
+  else if (K == 3 && S == 2 && PAD == 1)
     bn_relu_maxpool_kernel<3, 2, 1><<<blocks, kEwThreads, 0, ST(stream)>>>(CBF(y), scale, shift, BF(out),
                                                                          reinterpret_cast<uint8_t*>(idx), F, H, W, C, sh);
   else if (K == 2 && S == 2 && PAD == 0)
@@ -886,7 +1071,17 @@ extern "C" int m3t_maxpool_bn_bwd(int mode, const void* dout, const void* idx, c
   const long long items = (long long)F * H * W * (C / 8);
   if (items >= (1LL << 31)) return -6;
   const int blocks = ew_blocks(items);
-  if (K == 3 && S == 2 && PAD == 1)
+  if (K == 3 && S == 2 && PAD == 1 && H % 2 == 0 && W % 2 == 0) {
+    const int blocks4 = ew_blocks(items / 4);
+    if (mode == 0)
+      maxpool3s2_bn_bwd_kernel<0><<<blocks4, kEwThreads, 2 * C * sizeof(float), ST(stream)>>>(
+          CBF(dout), reinterpret_cast<const uint8_t*>(idx), CBF(y), mean, invstd, scale, shift, sums, 0.f, nullptr, F,
+          H, W, C, sh);
+    else
+      maxpool3s2_bn_bwd_kernel<1><<<blocks4, kEwThreads, 0, ST(stream)>>>(
+          CBF(dout), reinterpret_cast<const uint8_t*>(idx), CBF(y), mean, invstd, scale, shift, sums,
+          (float)(1.0 / count), BF(dy), F, H, W, C, sh);
+  } else if (K == 3 && S == 2 && PAD == 1)
     launch_pool_bwd<3, 2, 1>(mode, dout, idx, y, mean, invstd, scale, shift, sums, count, dy, F, H, W, C, sh, blocks,
                              ST(stream));
   else if (K == 2 && S == 2 && PAD == 0)

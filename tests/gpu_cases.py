@@ -273,31 +273,33 @@ def case_elementwise(seed=0):
     errs["bn_shift"] = _err(fin[3], bet - mean * gam / torch.sqrt(var + 1e-5))
     errs["bn_rm"] = _err(rmd, 0.1 * mean)
     errs["bn_rv"] = _err(rvd, 0.9 + 0.1 * var * n / (n - 1))
-    # stem tail: bn + relu + maxpool, forward and backward against autograd
-    F_, H, W, C = 3, 12, 10, 64
-    yy = _rnd((F_, H, W, C), g)
-    sc, sh = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g) * 0.3
-    out, idx = raw.bn_relu_maxpool(yy.cuda(), sc.cuda(), sh.cuda(), True)
-    yr = yy.float().permute(0, 3, 1, 2).clone().requires_grad_(True)
-    act = (yr * sc.view(1, -1, 1, 1) + sh.view(1, -1, 1, 1)).relu()
-    pr = F.max_pool2d(act, 3, 2, 1)
-    errs["maxpool"] = _err(out.float().cpu().permute(0, 3, 1, 2), pr)
-    # backward through pool+relu+BN(train) : use batch stats of yy so BN backward terms are exercised
-    mean, var = yy.float().mean((0, 1, 2)), yy.float().var((0, 1, 2), unbiased=False)
-    invstd = 1 / torch.sqrt(var + 1e-5)
-    gam, bet = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g) * 0.3
-    scale, shift = gam * invstd, bet - mean * gam * invstd
-    out2, idx2 = raw.bn_relu_maxpool(yy.cuda(), scale.cuda(), shift.cuda(), True)
-    dout = _rnd(tuple(out2.shape), g)
-    dy, sums = raw.maxpool_bn_bwd(dout.cuda(), idx2, yy.cuda(), mean.cuda(), invstd.cuda(), scale.cuda(), shift.cuda(),
-                                  F_ * H * W)
-    y3 = yy.float().permute(0, 3, 1, 2).clone().requires_grad_(True)
-    gp, bp = gam.clone().requires_grad_(True), bet.clone().requires_grad_(True)
-    z = F.batch_norm(y3, None, None, gp, bp, True, 0.1, 1e-5).relu()
-    F.max_pool2d(z, 3, 2, 1).backward(dout.float().permute(0, 3, 1, 2))
-    errs["pool_bwd_dy"] = _err(dy.float().cpu().permute(0, 3, 1, 2), y3.grad)
-    errs["pool_bwd_dgamma"] = _err(sums[1], gp.grad)
-    errs["pool_bwd_dbeta"] = _err(sums[0], bp.grad)
+    # stem tail: bn + relu + maxpool, forward and backward against autograd (even sizes take the 2x2-block
+    # specialisation, odd sizes the generic kernels)
+    for H, W, tag in ((12, 10, ""), (11, 9, "_odd")):
+        F_, C = 3, 64
+        yy = _rnd((F_, H, W, C), g)
+        sc, sh = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g) * 0.3
+        out, idx = raw.bn_relu_maxpool(yy.cuda(), sc.cuda(), sh.cuda(), True)
+        yr = yy.float().permute(0, 3, 1, 2).clone().requires_grad_(True)
+        act = (yr * sc.view(1, -1, 1, 1) + sh.view(1, -1, 1, 1)).relu()
+        pr = F.max_pool2d(act, 3, 2, 1)
+        errs["maxpool" + tag] = _err(out.float().cpu().permute(0, 3, 1, 2), pr)
+        # backward through pool+relu+BN(train) : use batch stats of yy so BN backward terms are exercised
+        mean, var = yy.float().mean((0, 1, 2)), yy.float().var((0, 1, 2), unbiased=False)
+        invstd = 1 / torch.sqrt(var + 1e-5)
+        gam, bet = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g) * 0.3
+        scale, shift = gam * invstd, bet - mean * gam * invstd
+        out2, idx2 = raw.bn_relu_maxpool(yy.cuda(), scale.cuda(), shift.cuda(), True)
+        dout = _rnd(tuple(out2.shape), g)
+        dy, sums = raw.maxpool_bn_bwd(dout.cuda(), idx2, yy.cuda(), mean.cuda(), invstd.cuda(), scale.cuda(), shift.cuda(),
+                                      F_ * H * W)
+        y3 = yy.float().permute(0, 3, 1, 2).clone().requires_grad_(True)
+        gp, bp = gam.clone().requires_grad_(True), bet.clone().requires_grad_(True)
+        z = F.batch_norm(y3, None, None, gp, bp, True, 0.1, 1e-5).relu()
+        F.max_pool2d(z, 3, 2, 1).backward(dout.float().permute(0, 3, 1, 2))
+        errs["pool_bwd_dy" + tag] = _err(dy.float().cpu().permute(0, 3, 1, 2), y3.grad)
+        errs["pool_bwd_dgamma" + tag] = _err(sums[1], gp.grad)
+        errs["pool_bwd_dbeta" + tag] = _err(sums[0], bp.grad)
     # bn_act backward (relu + residual)
     C = 64
     y = _rnd((4, 6, 6, C), g)
