@@ -127,12 +127,30 @@ void conv_fill_params(UmmaParams& p, const ConvGeom& g) {
 
 }  // namespace
 
+static int conv_fprop_impl(const void* x, const void* w_packed, void* y, const int* geom, const float* scale,
+                           const float* shift, const void* residual, int relu, float* stats, int tile_hint,
+                           const long long* out_map, void* stream);
+
 extern "C" int m3t_conv_fprop_bf16(const void* x, const void* w_packed, void* y, const int* geom, const float* scale,
                                    const float* shift, const void* residual, int relu, float* stats, int tile_hint,
                                    void* stream) {
+  return conv_fprop_impl(x, w_packed, y, geom, scale, shift, residual, relu, stats, tile_hint, nullptr, stream);
+}
+
+extern "C" int m3t_conv_fprop_scatter_bf16(const void* x, const void* w_packed, void* y, const int* geom,
+                                           long long img_pitch, long long row_pitch, long long px_pitch,
+                                           int tile_hint, void* stream) {
+  const long long map[3] = {img_pitch, row_pitch, px_pitch};
+  return conv_fprop_impl(x, w_packed, y, geom, nullptr, nullptr, nullptr, 0, nullptr, tile_hint, map, stream);
+}
+
+static int conv_fprop_impl(const void* x, const void* w_packed, void* y, const int* geom, const float* scale,
+                           const float* shift, const void* residual, int relu, float* stats, int tile_hint,
+                           const long long* out_map, void* stream) {
   ConvGeom g;
   int rc = conv_geom(g, geom);
   if (rc) return rc;
+  if (out_map && g.Z != 1) return -1;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const long long Mpix = (long long)g.N * g.Z * g.P * g.Q;
   const int taps = g.kd * g.kh * g.kw;
@@ -146,6 +164,10 @@ extern "C" int m3t_conv_fprop_bf16(const void* x, const void* w_packed, void* y,
   p.scale = scale; p.shift = shift;
   p.residual = reinterpret_cast<const __nv_bfloat16*>(residual); p.ldr = g.Cout;
   p.relu = relu; p.stats = stats;
+  if (out_map) {
+    p.oq = g.Q; p.op = g.P;
+    p.o_img = out_map[0]; p.o_row = out_map[1]; p.o_px = out_map[2];
+  }
   // tile selection: BN = 64 / 128 / 256 ; MT = 2 when there is enough M to still fill the machine
   // 256-column tiles halve the A re-reads of the wide layers (measured +3..7 % on the 256/512-channel convs);
   // tile_hint bit3 forces 128 columns.

@@ -44,7 +44,20 @@ struct UmmaParams {
   long long ldr;
   int relu;
   float* stats;       // [2][N] (sum, sum of squares of the raw accumulator over valid rows) or null
+  // ---- optional output row map (stride-2 dgrad by parity): row m = (img, a, b) over [.][op][oq] is stored at pixel
+  //      img*o_img + a*o_row + b*o_px (x ldc elements) instead of m.  oq == 0: linear.
+  int oq, op;
+  long long o_img, o_row, o_px;
 };
+
+__device__ __forceinline__ long long out_row(const UmmaParams& p, long long m) {
+  if (p.oq == 0) return m;
+  const int mi = (int)m;
+  const int b = mi % p.oq;
+  const int t = mi / p.oq;
+  const int a = t % p.op;
+  return (long long)(t / p.op) * p.o_img + (long long)a * p.o_row + (long long)b * p.o_px;
+}
 
 // Decompose a linear output-pixel index into the im2col base coordinates of filter tap 0.
 struct PixCoord {
@@ -287,6 +300,7 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       for (int mt = 0; mt < MT; ++mt) {
         const long long m = (long long)(m_tile * MT + mt) * 128 + row;
         const bool row_ok = m < p.M;
+        const long long mo = row_ok ? out_row(p, m) : 0;
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 32) {
           float v[32];
@@ -345,7 +359,7 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             }
             if (ncols > 0) {
               if (p.out_f32) {
-                float* op = reinterpret_cast<float*>(p.out) + m * p.ldc + n0 + c0;
+                float* op = reinterpret_cast<float*>(p.out) + mo * p.ldc + n0 + c0;
                 if (ncols == 32 && (p.ldc & 3) == 0) {
 #pragma unroll
                   for (int g = 0; g < 8; ++g)
@@ -356,7 +370,7 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     if (i < ncols) op[i] = o[i];
                 }
               } else {
-                __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + m * p.ldc + n0 + c0;
+                __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + mo * p.ldc + n0 + c0;
                 if (ncols == 32 && (p.ldc & 7) == 0) {
 #pragma unroll
                   for (int g = 0; g < 4; ++g)

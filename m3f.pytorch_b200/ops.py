@@ -176,10 +176,79 @@ class ConvBNAct(torch.autograd.Function):
         return dx, dw, dgamma, dbeta, None, None, dres, None, None, None, None
 
 
+_PARITY_TAPS = {}
+
+
+def _parity_taps(K, pad, ph, pw, device):
+    """Stride-2 dgrad by output parity: dX[2a+ph, 2b+pw] only sees the filter taps kh = ph + pad - 2d (d = p - a),
+    i.e. a (nh x nw) stride-1 filter over dY.  Returns (index of those taps in the flipped dgrad pack, nh, nw,
+    pad_lo_h, pad_lo_w) or None if the parity sees no tap (its quarter of dX is zero)."""
+    key = (K, pad, ph, pw, str(device))
+    if key not in _PARITY_TAPS:
+        def rng(par):
+            lo = -((-(par + pad - K + 1)) // 2)
+            hi = (par + pad) // 2
+            return lo, hi
+        (hlo, hhi), (wlo, whi) = rng(ph), rng(pw)
+        if hhi < hlo or whi < wlo:
+            _PARITY_TAPS[key] = None
+        else:
+            taps = K * K
+            idx = [taps - 1 - ((ph + pad - 2 * dh) * K + (pw + pad - 2 * dw))
+                   for dh in range(hlo, hhi + 1) for dw in range(wlo, whi + 1)]
+            _PARITY_TAPS[key] = (torch.tensor(idx, device=device, dtype=torch.long), hhi - hlo + 1, whi - wlo + 1,
+                                 -hlo, -wlo)
+    return _PARITY_TAPS[key]
+
+
+DGRAD_S2_PARITY = True   # stride-2 data gradients as four parity sub-convolutions (False: zero-inserted dY)
+
+
+def _dgrad_s2_parity(dy, w, x_shape, pad):
+    N, H, W, Cin = x_shape
+    Cout, _, K, _ = w.shape
+    _, P, Q, _ = dy.shape
+    plans = []
+    for ph in range(2):
+        for pw in range(2):
+            tp = _parity_taps(K, pad, ph, pw, dy.device)
+            Ha, Wa = (H - ph + 1) // 2, (W - pw + 1) // 2
+            if tp is None or Ha == 0 or Wa == 0:
+                plans.append(None)
+                continue
+            idx, nh, nw, plh, plw = tp
+            phh, pwh = Ha - P - plh + nh - 1, Wa - Q - plw + nw - 1
+            if phh < 0 or pwh < 0 or plh < 0 or plw < 0:
+                return None
+            plans.append((ph, pw, idx, nh, nw, plh, plw, phh, pwh))
+    _, wd = packed_filter(w, True)
+
+    def make():
+        wd3 = wd.view(Cin, K * K, Cout)
+        return tuple(None if pl is None else wd3.index_select(1, pl[2]).reshape(Cin, -1).contiguous() for pl in plans)
+
+    subs = _cached(w, "dgrad_s2", make)
+    full = all(pl is not None for pl in plans)
+    dx = (torch.empty if full else torch.zeros)((N, H, W, Cin), device=dy.device, dtype=torch.bfloat16)
+    flat = dx.view(-1)
+    for pl, wsub in zip(plans, subs):
+        if pl is None:
+            continue
+        ph, pw, _, nh, nw, plh, plw, phh, pwh = pl
+        geom = _geom2d(dy.shape, Cin, (nh, nw), 1, (plh, plw), (phh, pwh))
+        raw.conv_fprop_scatter(dy, wsub, geom, flat[(ph * W + pw) * Cin:], H * W, 2 * W, 2)
+    return dx
+
+
 def conv2d_dgrad(dy, w, x_shape, stride, pad):
-    """dX of conv2d as a stride-1 implicit-GEMM conv of (zero-inserted) dY with the flipped, transposed filter."""
+    """dX of conv2d as stride-1 implicit-GEMM convolutions of dY with the flipped, transposed filter: one for
+    stride 1; one per output parity for stride 2 (fallback: a single one over zero-inserted dY)."""
     N, H, W, Cin = x_shape
     Cout, _, kh, kw = w.shape
+    if stride == 2 and DGRAD_S2_PARITY and kh == kw and Cout % 64 == 0:
+        dx = _dgrad_s2_parity(dy, w, x_shape, pad)
+        if dx is not None:
+            return dx
     _, wd = packed_filter(w, True)
     if stride == 1:
         src = dy

@@ -895,6 +895,33 @@ def case_stem_fprop_halo(seed=0):
 CASES["stem_fprop_halo"] = (case_stem_fprop_halo, _c())
 
 
+def case_dgrad_s2(H, K, pad, Cin, Cout, N=5, seed=0):
+    """Stride-2 data gradient by output parity (four small stride-1 convolutions of dY scattered into dX) vs the
+    zero-inserted formulation and vs conv_transpose on the CPU."""
+    from m3t_b200 import ops
+    g = torch.Generator().manual_seed(seed)
+    P = (H + 2 * pad - K) // 2 + 1
+    w = (torch.randn((Cout, Cin, K, K), generator=g) * 0.05).cuda()
+    dy = _rnd((N, P, P, Cout), g).cuda()
+    ops.DGRAD_S2_PARITY = True
+    dx1 = ops.conv2d_dgrad(dy, w, (N, H, H, Cin), 2, pad)
+    ops.DGRAD_S2_PARITY = False
+    dx0 = ops.conv2d_dgrad(dy, w, (N, H, H, Cin), 2, pad)
+    ops.DGRAD_S2_PARITY = True
+    torch.cuda.synchronize()
+    wq = w.bfloat16().float().cpu()
+    ref = F.conv_transpose2d(dy.float().cpu().permute(0, 3, 1, 2), wq, stride=2, padding=pad,
+                             output_padding=H - ((P - 1) * 2 - 2 * pad + K))
+    return {"vs_zero_insert": _err(dx1, dx0), "out": _err(dx1.float().cpu().permute(0, 3, 1, 2), ref)}
+
+
+TOLS["vs_zero_insert"] = 1e-2
+CASES["dgrad_s2_3x3_28"] = (case_dgrad_s2, _c(H=28, K=3, pad=1, Cin=64, Cout=128))
+CASES["dgrad_s2_3x3_7"] = (case_dgrad_s2, _c(H=7, K=3, pad=1, Cin=256, Cout=512))
+CASES["dgrad_s2_1x1_14"] = (case_dgrad_s2, _c(H=14, K=1, pad=0, Cin=128, Cout=256))
+CASES["dgrad_s2_1x1_7"] = (case_dgrad_s2, _c(H=7, K=1, pad=0, Cin=256, Cout=512))
+
+
 if __name__ == "__main__":
     name = sys.argv[1]
     errs = run_case(name)
