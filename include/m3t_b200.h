@@ -61,10 +61,11 @@ int m3t_conv_fprop_bf16(const void* x, const void* w_packed, void* y, const int*
  * n*img_pitch + p*row_pitch + q*px_pitch (in units of Cout-element pixels) from y instead of densely: the data
  * gradient of a stride-2 convolution is evaluated as one small stride-1 convolution of dY per output parity
  * (h%2, w%2), each writing its quarter of dX in place - no zero-inserted copy of dY, no multiplications by zero.
+ * accumulate != 0 adds to the stored values instead (the 1x1 downsample gradient joins the 3x3 one at the block input).
  * Replaces autograd's conv_backward_input for the stride-2 nn.Conv2d 3x3 / 1x1 of the first BasicBlock of
  * layer2..4 (models/resnet.py:7-15,24-27 via :98-101). */
 int m3t_conv_fprop_scatter_bf16(const void* x, const void* w_packed, void* y, const int* geom, long long img_pitch,
-                                long long row_pitch, long long px_pitch, int tile_hint, void* stream);
+                                long long row_pitch, long long px_pitch, int accumulate, int tile_hint, void* stream);
 
 /* 3x3 / stride 1 / pad 1 convolution for Cin = Cout = 64 (ResNet layer1 fprop; its dgrad with the flipped filter):
  * persistent CTAs, the 9 filter taps resident in shared memory, ONE halo box per 128-position tile (zero padding by

@@ -139,9 +139,10 @@ extern "C" int m3t_conv_fprop_bf16(const void* x, const void* w_packed, void* y,
 
 extern "C" int m3t_conv_fprop_scatter_bf16(const void* x, const void* w_packed, void* y, const int* geom,
                                            long long img_pitch, long long row_pitch, long long px_pitch,
-                                           int tile_hint, void* stream) {
+                                           int accumulate, int tile_hint, void* stream) {
   const long long map[3] = {img_pitch, row_pitch, px_pitch};
-  return conv_fprop_impl(x, w_packed, y, geom, nullptr, nullptr, nullptr, 0, nullptr, tile_hint, map, stream);
+  return conv_fprop_impl(x, w_packed, y, geom, nullptr, nullptr, accumulate ? y : nullptr, 0, nullptr, tile_hint, map,
+                         stream);
 }
 
 static int conv_fprop_impl(const void* x, const void* w_packed, void* y, const int* geom, const float* scale,
@@ -167,6 +168,7 @@ static int conv_fprop_impl(const void* x, const void* w_packed, void* y, const i
   if (out_map) {
     p.oq = g.Q; p.op = g.P;
     p.o_img = out_map[0]; p.o_row = out_map[1]; p.o_px = out_map[2];
+    p.res_mapped = 1;   // a residual here is the output itself (accumulate)
   }
   // tile selection: BN = 64 / 128 / 256 ; MT = 2 when there is enough M to still fill the machine
   // 256-column tiles halve the A re-reads of the wide layers (measured +3..7 % on the 256/512-channel convs);

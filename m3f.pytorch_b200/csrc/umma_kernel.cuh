@@ -48,6 +48,7 @@ struct UmmaParams {
   //      img*o_img + a*o_row + b*o_px (x ldc elements) instead of m.  oq == 0: linear.
   int oq, op;
   long long o_img, o_row, o_px;
+  int res_mapped;     // residual rows follow the same map (in-place accumulation)
 };
 
 __device__ __forceinline__ long long out_row(const UmmaParams& p, long long m) {
@@ -335,7 +336,7 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             }
             const int ncols = min(32, min(BN - c0, p.N - (n0 + c0)));
             if (p.residual) {
-              const __nv_bfloat16* rp = p.residual + m * p.ldr + n0 + c0;
+              const __nv_bfloat16* rp = p.residual + (p.res_mapped ? mo : m) * p.ldr + n0 + c0;
               if (ncols == 32 && (p.ldr & 7) == 0) {
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {

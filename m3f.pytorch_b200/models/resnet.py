@@ -36,6 +36,18 @@ class BasicBlock(nn.Module):
         self.cbam = None
 
     def forward_cl(self, x):
+        if self.training and torch.is_grad_enabled():
+            # one autograd node per block: the gradients meeting at the block input are summed in a dgrad epilogue
+            ds = self.downsample
+            dargs = ((ds[0].weight, ds[1].weight, ds[1].bias, ds[1].running_mean, ds[1].running_var)
+                     if ds is not None else (None,) * 5)
+            out = ops.BasicBlockFn.apply(x, self.stride, self.conv1.weight, self.bn1.weight, self.bn1.bias,
+                                         self.bn1.running_mean, self.bn1.running_var, self.conv2.weight,
+                                         self.bn2.weight, self.bn2.bias, self.bn2.running_mean, self.bn2.running_var,
+                                         *dargs)
+            for bn in (self.bn1, self.bn2) + ((ds[1],) if ds is not None else ()):
+                ops.bump_num_batches_tracked(bn)
+            return out
         h = _conv_bn_act(x, self.conv1, self.bn1, None, True)
         idt = x if self.downsample is None else _conv_bn_act(x, self.downsample[0], self.downsample[1], None, False)
         return _conv_bn_act(h, self.conv2, self.bn2, idt, True)

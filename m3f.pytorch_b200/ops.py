@@ -123,6 +123,44 @@ def _geom2d(x_shape, Cout, k, stride, pad_lo, pad_hi, dil=1, nd=2):
                          (1, 1, dil))
 
 
+def _cba_train_fwd(x, w, gamma, beta, running_mean, running_var, residual, stride, pad, relu):
+    """Train-mode conv + BN (+ residual) (+ ReLU).  Returns (out, saved tensors, meta)."""
+    Cout = w.shape[0]
+    k = (w.shape[2], w.shape[3])
+    geom = _geom2d(x.shape, Cout, k, stride, (pad, pad), (pad, pad))
+    wf, _ = packed_filter(w, True)
+    stats = torch.zeros((2, Cout), device=x.device, dtype=torch.float32)
+    y = raw.conv_fprop(x, wf, geom, stats=stats)
+    y = y.view(y.shape[0], y.shape[2], y.shape[3], y.shape[4])
+    count = y.numel() // Cout
+    fin = raw.bn_finalize(stats, count, gamma.detach(), beta.detach(), BN_EPS, BN_MOMENTUM, running_mean, running_var)
+    out = raw.bn_act(y, fin[2], fin[3], res=residual, relu=relu)
+    # the ReLU mask of a unit without residual is recomputed from y in backward: `out` is not kept for it
+    saved = (x, w, y, out if (relu and residual is not None) else None, fin)
+    meta = (geom, stride, pad, relu, count, residual is not None)
+    return out, saved, meta
+
+
+def _cba_bwd(saved, meta, dout, need_dx, dgrad_residual=None, dx_accum=None):
+    """Backward of _cba_train_fwd.  dgrad_residual: bf16 tensor added to dX in the dgrad epilogue (stride 1);
+    dx_accum: dX tensor the (stride-2) data gradient is accumulated into in place.
+    Returns (dx, dw, dgamma, dbeta, dres)."""
+    x, w, y, out, fin = saved
+    geom, stride, pad, relu, count, has_res = meta
+    dout = dout.contiguous()
+    mean, invstd, scale = fin[0], fin[1], fin[2]
+    need_dz = has_res and relu
+    sums, dz = raw.bn_bwd_reduce(dout, out, y, mean, invstd, relu, need_dz, scale=scale, shift=fin[3])
+    dy = raw.bn_bwd_apply(dout, out, y, mean, invstd, scale, sums, count, relu, shift=fin[3])
+    dres = (dz if relu else dout) if has_res else None
+    dwp = raw.conv_wgrad(x, dy, geom)
+    dw = raw.unpack_filter_grad(dwp, tuple(w.shape))
+    dx = None
+    if need_dx:
+        dx = conv2d_dgrad(dy, w, x.shape, stride, pad, residual=dgrad_residual, accum_into=dx_accum)
+    return dx, dw, sums[1], sums[0], dres
+
+
 class ConvBNAct(torch.autograd.Function):
     """out = act( BN(conv2d(x, w)) + residual )   (models/resnet.py:40-54, one conv of a BasicBlock).
 
@@ -132,48 +170,57 @@ class ConvBNAct(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, w, gamma, beta, running_mean, running_var, residual, stride, pad, relu, training):
-        Cout = w.shape[0]
-        k = (w.shape[2], w.shape[3])
-        geom = _geom2d(x.shape, Cout, k, stride, (pad, pad), (pad, pad))
-        wf, _ = packed_filter(w, True)
         if not training:
+            Cout = w.shape[0]
+            geom = _geom2d(x.shape, Cout, (w.shape[2], w.shape[3]), stride, (pad, pad), (pad, pad))
+            wf, _ = packed_filter(w, True)
             ss = raw.bn_fold(gamma.detach(), beta.detach(), running_mean, running_var, None, BN_EPS)
             out = raw.conv_fprop(x, wf, geom, scale=ss[0], shift=ss[1], residual=residual, relu=relu)
             return out.view(out.shape[0], out.shape[2], out.shape[3], out.shape[4])
-        stats = torch.zeros((2, Cout), device=x.device, dtype=torch.float32)
-        y = raw.conv_fprop(x, wf, geom, stats=stats)
-        y = y.view(y.shape[0], y.shape[2], y.shape[3], y.shape[4])
-        count = y.numel() // Cout
-        fin = raw.bn_finalize(stats, count, gamma.detach(), beta.detach(), BN_EPS, BN_MOMENTUM, running_mean,
-                              running_var)
-        out = raw.bn_act(y, fin[2], fin[3], res=residual, relu=relu)
-        # the ReLU mask of a unit without residual is recomputed from y in backward: `out` is not kept for it
-        ctx.save_for_backward(x, w, y, out if (relu and residual is not None) else None, fin)
-        ctx.geom, ctx.stride, ctx.pad, ctx.relu, ctx.count = geom, stride, pad, relu, count
-        ctx.has_res = residual is not None
+        out, saved, meta = _cba_train_fwd(x, w, gamma, beta, running_mean, running_var, residual, stride, pad, relu)
+        ctx.save_for_backward(*saved)
+        ctx.meta = meta
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        x, w, y, out, fin = ctx.saved_tensors
-        dout = dout.contiguous()
-        mean, invstd, scale = fin[0], fin[1], fin[2]
-        relu = ctx.relu
-        need_dz = ctx.has_res and relu
-        sums, dz = raw.bn_bwd_reduce(dout, out, y, mean, invstd, relu, need_dz, scale=scale, shift=fin[3])
-        dy = raw.bn_bwd_apply(dout, out, y, mean, invstd, scale, sums, ctx.count, relu, shift=fin[3])
-        dres = None
-        if ctx.has_res:
-            dres = dz if relu else dout
-        dgamma, dbeta = sums[1], sums[0]
-        # weight gradient
-        dwp = raw.conv_wgrad(x, dy, ctx.geom)
-        dw = raw.unpack_filter_grad(dwp, tuple(w.shape))
-        # data gradient
-        dx = None
-        if ctx.needs_input_grad[0]:
-            dx = conv2d_dgrad(dy, w, x.shape, ctx.stride, ctx.pad)
+        dx, dw, dgamma, dbeta, dres = _cba_bwd(ctx.saved_tensors, ctx.meta, dout, ctx.needs_input_grad[0])
         return dx, dw, dgamma, dbeta, None, None, dres, None, None, None, None
+
+
+class BasicBlockFn(torch.autograd.Function):
+    """One train-mode BasicBlock (models/resnet.py:18-63: conv1-bn1-relu, conv2-bn2, (+downsample), add, relu) as a
+    single autograd node, so that the two gradients that meet at the block input are summed inside the dgrad
+    epilogue instead of by a separate pass: identity shortcut -> dX = dgrad(conv1) + dz (residual operand of the
+    dgrad kernel); 1x1/s2 downsample -> its data gradient accumulates in place into conv1's dX."""
+
+    @staticmethod
+    def forward(ctx, x, stride, w1, g1, b1, rm1, rv1, w2, g2, b2, rm2, rv2, wd, gd, bd, rmd, rvd):
+        h, s1, m1 = _cba_train_fwd(x, w1, g1, b1, rm1, rv1, None, stride, 1, True)
+        if wd is not None:
+            idt, sd, md = _cba_train_fwd(x, wd, gd, bd, rmd, rvd, None, stride, 0, False)
+        else:
+            idt, sd, md = x, (), None
+        out, s2, m2 = _cba_train_fwd(h, w2, g2, b2, rm2, rv2, idt, 1, 1, True)
+        ctx.save_for_backward(*s1, *s2, *sd)
+        ctx.metas = (m1, m2, md)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        t = ctx.saved_tensors
+        m1, m2, md = ctx.metas
+        s1, s2, sd = t[0:5], t[5:10], t[10:15]
+        need_dx = ctx.needs_input_grad[0]
+        dh, dw2, dg2, db2, dres = _cba_bwd(s2, m2, dout, True)
+        if md is None:
+            dx, dw1, dg1, db1, _ = _cba_bwd(s1, m1, dh, need_dx, dgrad_residual=dres)
+            if not need_dx:
+                dx = None
+            return (dx, None, dw1, dg1, db1, None, None, dw2, dg2, db2, None, None, None, None, None, None, None)
+        dx, dw1, dg1, db1, _ = _cba_bwd(s1, m1, dh, need_dx)
+        dx, dwd, dgd, dbd, _ = _cba_bwd(sd, md, dres, need_dx, dx_accum=dx)
+        return (dx, None, dw1, dg1, db1, None, None, dw2, dg2, db2, None, None, dwd, dgd, dbd, None, None)
 
 
 _PARITY_TAPS = {}
@@ -204,7 +251,7 @@ def _parity_taps(K, pad, ph, pw, device):
 DGRAD_S2_PARITY = True   # stride-2 data gradients as four parity sub-convolutions (False: zero-inserted dY)
 
 
-def _dgrad_s2_parity(dy, w, x_shape, pad):
+def _dgrad_s2_parity(dy, w, x_shape, pad, accum_into=None):
     N, H, W, Cin = x_shape
     Cout, _, K, _ = w.shape
     _, P, Q, _ = dy.shape
@@ -229,26 +276,34 @@ def _dgrad_s2_parity(dy, w, x_shape, pad):
 
     subs = _cached(w, "dgrad_s2", make)
     full = all(pl is not None for pl in plans)
-    dx = (torch.empty if full else torch.zeros)((N, H, W, Cin), device=dy.device, dtype=torch.bfloat16)
+    if accum_into is not None:
+        dx = accum_into
+    else:
+        dx = (torch.empty if full else torch.zeros)((N, H, W, Cin), device=dy.device, dtype=torch.bfloat16)
     flat = dx.view(-1)
     for pl, wsub in zip(plans, subs):
         if pl is None:
             continue
         ph, pw, _, nh, nw, plh, plw, phh, pwh = pl
         geom = _geom2d(dy.shape, Cin, (nh, nw), 1, (plh, plw), (phh, pwh))
-        raw.conv_fprop_scatter(dy, wsub, geom, flat[(ph * W + pw) * Cin:], H * W, 2 * W, 2)
+        raw.conv_fprop_scatter(dy, wsub, geom, flat[(ph * W + pw) * Cin:], H * W, 2 * W, 2,
+                               accumulate=accum_into is not None)
     return dx
 
 
-def conv2d_dgrad(dy, w, x_shape, stride, pad):
+def conv2d_dgrad(dy, w, x_shape, stride, pad, residual=None, accum_into=None):
     """dX of conv2d as stride-1 implicit-GEMM convolutions of dY with the flipped, transposed filter: one for
-    stride 1; one per output parity for stride 2 (fallback: a single one over zero-inserted dY)."""
+    stride 1; one per output parity for stride 2 (fallback: a single one over zero-inserted dY).
+    residual (stride 1): added in the epilogue.  accum_into: dX buffer to accumulate into (returned)."""
     N, H, W, Cin = x_shape
     Cout, _, kh, kw = w.shape
-    if stride == 2 and DGRAD_S2_PARITY and kh == kw and Cout % 64 == 0:
-        dx = _dgrad_s2_parity(dy, w, x_shape, pad)
+    if stride == 2 and DGRAD_S2_PARITY and kh == kw and Cout % 64 == 0 and residual is None:
+        dx = _dgrad_s2_parity(dy, w, x_shape, pad, accum_into)
         if dx is not None:
             return dx
+    if accum_into is not None:
+        assert residual is None
+        residual = accum_into
     _, wd = packed_filter(w, True)
     if stride == 1:
         src = dy
@@ -259,7 +314,7 @@ def conv2d_dgrad(dy, w, x_shape, stride, pad):
     hi = (pad, pad) if stride == 2 else lo
     geom = _geom2d(src.shape, Cin, (kh, kw), 1, lo, hi)
     flops = 2.0 * dy.shape[0] * dy.shape[1] * dy.shape[2] * Cout * Cin * kh * kw   # true dgrad work
-    dx = raw.conv_fprop(src, wd, geom, algo_flops=flops, tag="dgrad")
+    dx = raw.conv_fprop(src, wd, geom, residual=residual, algo_flops=flops, tag="dgrad")
     return dx.view(N, H, W, Cin)
 
 

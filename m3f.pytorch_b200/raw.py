@@ -133,17 +133,19 @@ def conv_fprop(x, w_packed, g, scale=None, shift=None, residual=None, relu=False
     return y
 
 
-def conv_fprop_scatter(x, w_packed, g, out_base, img_pitch, row_pitch, px_pitch, algo_flops=None, tag="dgrad-s2"):
+def conv_fprop_scatter(x, w_packed, g, out_base, img_pitch, row_pitch, px_pitch, accumulate=False, algo_flops=None,
+                       tag="dgrad-s2"):
     """conv_fprop (2-D, no epilogue arithmetic) storing output pixel (n,p,q) at out_base + (n*img_pitch + p*row_pitch +
-    q*px_pitch) * Cout elements.  out_base: bf16 tensor view whose data pointer is the address of pixel (0,0,0)."""
+    q*px_pitch) * Cout elements.  out_base: bf16 tensor view whose data pointer is the address of pixel (0,0,0).
+    accumulate: add to what is stored there instead of overwriting."""
     _chk_bf16(x, w_packed, out_base)
     Z, P, Q = conv_out_dims(g)
     N, Cout = g[1], g[6]
 
     def run():
         rc = L.load().m3t_conv_fprop_scatter_bf16(L.ptr(x), L.ptr(w_packed), L.ptr(out_base), L.int_array(g),
-                                                  L.i64(img_pitch), L.i64(row_pitch), L.i64(px_pitch), L.i32(0),
-                                                  L.stream_ptr())
+                                                  L.i64(img_pitch), L.i64(row_pitch), L.i64(px_pitch),
+                                                  L.i32(1 if accumulate else 0), L.i32(0), L.stream_ptr())
         L.check(rc, "m3t_conv_fprop_scatter_bf16")
 
     if _prof is not None and algo_flops is None:
