@@ -304,7 +304,7 @@ def run_b200(args, rank, local_rank, world):
                     "avg_launch_ms": d["ms_total"] / d["calls"], "launches_timed": d["calls"],
                     "all_conv_kernels": {"tflops": tot_fl / (tot_ms * 1e-3) / 1e12 if tot_ms else None,
                                          "share_of_step": tot_ms / ms if ms else None}}
-        top = sorted(conv.items(), key=lambda kv: -kv[1]["ms_total"])[:8]
+        top = sorted(conv.items(), key=lambda kv: -kv[1]["ms_total"])[:args.top]
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -336,6 +336,7 @@ def main():
     ap.add_argument("--clips", type=int, default=256, help="clips per GPU (x16 frames)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs)")
+    ap.add_argument("--top", type=int, default=8, help="how many tensor-core kernels to list under \"kernels\"")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3

@@ -75,6 +75,15 @@ int m3t_conv_fprop_scatter_bf16(const void* x, const void* w_packed, void* y, co
 int m3t_conv3x3_c64_halo(const void* x, const void* w_packed, void* y, int F, int H, int W, const float* scale,
                          const float* shift, const void* residual, int relu, float* stats, void* stream);
 
+/* 3x3 / stride 1 / pad 1 convolution for Cin = Cout = 128 with one whole image per tile (ResNet layer2 at 14x14; its
+ * dgrad with the flipped filter): 128 <= H*(W+2) <= 256 and (H+2)*(W+2) <= 256, a multiple of 8.  The image's halo is
+ * two 64-channel TMA boxes, the filter streams through a shared-memory ring as [128][64] blocks, taps are row-shifted
+ * views of the boxes, N = 128 MMAs into double-buffered TMEM.  Epilogue contract and replaced call sites as
+ * m3t_conv_fprop_bf16 (models/resnet.py layer2: 3 convs 128->128 at 14x14 and their data gradients).
+ * x, y: bf16 [F][H][W][128]; w_packed: bf16 [128][9*128]. */
+int m3t_conv3x3_c128_halo(const void* x, const void* w_packed, void* y, int F, int H, int W, const float* scale,
+                          const float* shift, const void* residual, int relu, float* stats, void* stream);
+
 /* Stem forward as a halo-tile kernel over the W-unrolled space-to-depth image xs [B][T][H2][W2][64] with the packed
  * (5,4,1)x64 filter [64][20*64]: per temporal tap one box of TR+3 rows plus that tap's filter slices, the 4 vertical
  * taps as row-shifted views; y bf16 [B*T][H2][W2][64]; epilogue contract as m3t_conv_fprop_bf16 (no residual).

@@ -151,7 +151,10 @@ def _cba_bwd(saved, meta, dout, need_dx, dgrad_residual=None, dx_accum=None):
     mean, invstd, scale = fin[0], fin[1], fin[2]
     need_dz = has_res and relu
     sums, dz = raw.bn_bwd_reduce(dout, out, y, mean, invstd, relu, need_dz, scale=scale, shift=fin[3])
-    dy = raw.bn_bwd_apply(dout, out, y, mean, invstd, scale, sums, count, relu, shift=fin[3])
+    if need_dz:   # dz = relu'(out) * dout is already materialised (exactly): two tensor reads instead of three
+        dy = raw.bn_bwd_apply(dz, None, y, mean, invstd, scale, sums, count, False)
+    else:
+        dy = raw.bn_bwd_apply(dout, out, y, mean, invstd, scale, sums, count, relu, shift=fin[3])
     dres = (dz if relu else dout) if has_res else None
     dwp = raw.conv_wgrad(x, dy, geom)
     dw = raw.unpack_filter_grad(dwp, tuple(w.shape))
@@ -314,6 +317,11 @@ def conv2d_dgrad(dy, w, x_shape, stride, pad, residual=None, accum_into=None):
     hi = (pad, pad) if stride == 2 else lo
     geom = _geom2d(src.shape, Cin, (kh, kw), 1, lo, hi)
     flops = 2.0 * dy.shape[0] * dy.shape[1] * dy.shape[2] * Cout * Cin * kh * kw   # true dgrad work
+    if residual is not None and raw.halo_route(geom):
+        # the persistent halo kernel has one CTA per SM and its epilogue is on the critical path: a residual read
+        # there costs more (+0.2 ms at 4096x28x28x64) than a separate, bandwidth-bound add (0.17 ms)
+        dx = raw.conv_fprop(src, wd, geom, algo_flops=flops, tag="dgrad").view(N, H, W, Cin)
+        return raw.add_bf16(dx, residual.view(N, H, W, Cin))
     dx = raw.conv_fprop(src, wd, geom, residual=residual, algo_flops=flops, tag="dgrad")
     return dx.view(N, H, W, Cin)
 

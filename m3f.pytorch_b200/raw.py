@@ -105,6 +105,42 @@ def conv_key(kind, g):
                                                         g[12])
 
 
+def halo_route(g, tile_hint=0):
+    """True if conv_fprop sends this geometry to the persistent halo-tile kernel (64->64 3x3/s1/p1, W+2 <= 48)."""
+    return (USE_HALO and tile_hint == 0 and g[0] == 2 and g[5] == 64 and g[6] == 64 and tuple(g[7:10]) == (1, 3, 3)
+            and tuple(g[10:13]) == (1, 1, 1) and tuple(g[13:19]) == (0, 0, 1, 1, 1, 1)
+            and tuple(g[19:22]) == (1, 1, 1) and g[4] + 2 <= 48)
+
+
+USE_HALO128 = True   # route 128->128 3x3/s1/p1 convolutions over 14x14-like images to the image-per-tile halo kernel
+
+
+def halo128_route(g, tile_hint=0):
+    H, W = g[3], g[4]
+    return (USE_HALO128 and tile_hint == 0 and g[0] == 2 and g[5] == 128 and g[6] == 128
+            and tuple(g[7:10]) == (1, 3, 3) and tuple(g[10:13]) == (1, 1, 1) and tuple(g[13:19]) == (0, 0, 1, 1, 1, 1)
+            and tuple(g[19:22]) == (1, 1, 1) and 128 <= H * (W + 2) <= 256 and (H + 2) * (W + 2) <= 256
+            and ((H + 2) * (W + 2)) % 8 == 0)
+
+
+def conv3x3_c128_halo(x, w_packed, scale=None, shift=None, residual=None, relu=False, stats=None, tag="fprop"):
+    """x: bf16 [F,H,W,128]; w_packed bf16 [128, 1152] -> bf16 [F,H,W,128]."""
+    _chk_bf16(x, w_packed, residual)
+    F_, H, W, C = x.shape
+    assert C == 128 and w_packed.shape == (128, 1152)
+    y = torch.empty((F_, H, W, 128), device=x.device, dtype=torch.bfloat16)
+
+    def run():
+        rc = L.load().m3t_conv3x3_c128_halo(L.ptr(x), L.ptr(w_packed), L.ptr(y), L.i32(F_), L.i32(H), L.i32(W),
+                                            L.ptr(scale), L.ptr(shift), L.ptr(residual), L.i32(relu), L.ptr(stats),
+                                            L.stream_ptr())
+        L.check(rc, "m3t_conv3x3_c128_halo")
+
+    g = conv_geom(2, F_, 1, H, W, 128, 128, (1, 3, 3), (1, 1, 1), (0, 1, 1), (0, 1, 1), (1, 1, 1))
+    _timed(conv_key(tag + "-halo", g), 2.0 * F_ * H * W * 128 * 128 * 9, run)
+    return y
+
+
 def conv_fprop(x, w_packed, g, scale=None, shift=None, residual=None, relu=False, stats=None, tile_hint=0,
                algo_flops=None, tag="fprop"):
     """x: bf16 [N,D,H,W,Cin] contiguous (any view with that element order), w_packed: bf16 [Cout, taps*Cin].
@@ -113,9 +149,11 @@ def conv_fprop(x, w_packed, g, scale=None, shift=None, residual=None, relu=False
     _chk_bf16(x, w_packed, residual)
     Z, P, Q = conv_out_dims(g)
     N, Cout = g[1], g[6]
-    if (USE_HALO and tile_hint == 0 and g[0] == 2 and g[5] == 64 and Cout == 64 and tuple(g[7:10]) == (1, 3, 3)
-            and tuple(g[10:13]) == (1, 1, 1) and tuple(g[13:19]) == (0, 0, 1, 1, 1, 1)
-            and tuple(g[19:22]) == (1, 1, 1) and g[4] + 2 <= 48):
+    if halo128_route(g, tile_hint):
+        y = conv3x3_c128_halo(x.view(N, g[3], g[4], 128), w_packed, scale, shift,
+                              residual.view(N, g[3], g[4], 128) if residual is not None else None, relu, stats, tag)
+        return y.view(N, 1, g[3], g[4], 128)
+    if halo_route(g, tile_hint):
         y = conv3x3_c64_halo(x.view(N, g[3], g[4], 64), w_packed, scale, shift,
                              residual.view(N, g[3], g[4], 64) if residual is not None else None, relu, stats, tag)
         return y.view(N, 1, g[3], g[4], 64)

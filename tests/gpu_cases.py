@@ -895,6 +895,16 @@ def case_stem_fprop_halo(seed=0):
 CASES["stem_fprop_halo"] = (case_stem_fprop_halo, _c())
 
 
+# 128 -> 128 at 14x14: the image-per-tile halo kernel (conv_halo128.cu); 5 images = one tile per CTA, 333 images =
+# persistent CTAs over three tiles each (A double buffer, filter ring and TMEM phases wrap)
+CASES["conv2d_c128_halo_stats"] = (case_conv, _c(nd=2, N=5, D=1, H=14, W=14, Cin=128, Cout=128, k=(1, 3, 3),
+                                                 stride=(1, 1, 1), pad_lo=(0, 1, 1), stats=True))
+CASES["conv2d_c128_halo_fused"] = (case_conv, _c(nd=2, N=5, D=1, H=14, W=14, Cin=128, Cout=128, k=(1, 3, 3),
+                                                 stride=(1, 1, 1), pad_lo=(0, 1, 1), fused=True))
+CASES["conv2d_c128_halo_many"] = (case_conv, _c(nd=2, N=333, D=1, H=14, W=14, Cin=128, Cout=128, k=(1, 3, 3),
+                                                stride=(1, 1, 1), pad_lo=(0, 1, 1), stats=True))
+
+
 def case_dgrad_s2(H, K, pad, Cin, Cout, N=5, seed=0):
     """Stride-2 data gradient by output parity (four small stride-1 convolutions of dY scattered into dX) vs the
     zero-inserted formulation and vs conv_transpose on the CPU."""
