@@ -87,6 +87,7 @@ int m3t_conv3x3_c128_halo(const void* x, const void* w_packed, void* y, int F, i
 /* Stem forward as a halo-tile kernel over the W-unrolled space-to-depth image xs [B][T][H2][W2][64] with the packed
  * (5,4,1)x64 filter [64][20*64]: per temporal tap one box of TR+3 rows plus that tap's filter slices, the 4 vertical
  * taps as row-shifted views; y bf16 [B*T][H2][W2][64]; epilogue contract as m3t_conv_fprop_bf16 (no residual).
+ * Channels 48..63 of every pixel of xs are structural zeros of that layout and are NOT multiplied (3 K steps per tap).
  * Replaces nn.Conv3d(3,64,(5,7,7),(1,2,2),(2,3,3)) at models/backbone.py:328. */
 int m3t_stem_fprop_halo(const void* xs, const void* w_packed, void* y, int B, int T, int H2, int W2,
                         const float* scale, const float* shift, int relu, float* stats, void* stream);
@@ -120,7 +121,8 @@ int m3t_video_prep_s2d(const void* video, int is_u8, void* out, int B, int T, in
                        void* stream);
 
 /* Same, additionally unrolled over the stem's four horizontal taps: out bf16 (B,T,H/2,W/2,64) with
- * out[..][w2][jw*16+ch] = s2d[..][w2+jw-2][ch] (zero outside).  Every pixel is then one 128-byte row, and the stem
+ * out[..][w2][jw*12+ch] = s2d[..][w2+jw-2][ch] for the 12 real channels ch = (ph*2+pw)*3+c (zero outside the image),
+ * channels 48..63 = 0.  Every pixel is then one 128-byte row, and the stem
  * Conv3d(3,64,(5,7,7),s(1,2,2),p(2,3,3)) (models/backbone.py:328) becomes a (5,4,1) filter over 64 channels. */
 int m3t_video_prep_s2d_w4(const void* video, int is_u8, void* out, int B, int T, int H, int W, float mul, float add,
                           void* stream);

@@ -350,8 +350,9 @@ stem_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
               const int sub_start = min(128 * j, p.npos - 128);
               const uint32_t a_tap = a_base + (uint32_t)(jh * p.W2 + sub_start) * 128u;
               const uint32_t b_tap = b_base + (uint32_t)jh * 8192u;
+              // channels 48..63 of every tap are structural zeros (m3t_video_prep_s2d_w4): three K steps, not four
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
+              for (int k = 0; k < 3; ++k) {
                 const uint64_t adesc = make_smem_desc(a_tap + k * 32, 16, 1024, SWZ_128B);
                 const uint64_t bdesc = make_smem_desc(b_tap + k * 32, 16, 1024, SWZ_128B);
                 umma_bf16(tmem_base + acc * 256 + j * 64, adesc, bdesc, idesc, (kt | jh | k) != 0 ? 1u : 0u);

@@ -83,11 +83,13 @@ __global__ void video_prep_s2d_kernel(const T* __restrict__ in, __nv_bfloat16* _
 }
 
 // Same normalised space-to-depth image, additionally unrolled over the 4 horizontal filter taps so that every pixel
-// carries 64 channels (one 128-byte swizzle row):  out[b][t][h2][w2][jw*16 + ch] = s2d[b][t][h2][w2 + jw - 2][ch]
-// (zero outside the image).  The stem conv then is a (5,4,1) filter over 64 channels: the standard CK=64 im2col path.
+// carries 64 channels (one 128-byte swizzle row):  out[b][t][h2][w2][jw*12 + ch] = s2d[b][t][h2][w2 + jw - 2][ch]
+// for the 12 real channels ch = (ph*2+pw)*3 + c (zero outside the image), channels 48..63 = 0.  The stem conv then is a (5,4,1) filter over 64 channels: the standard CK=64 im2col path.
 template <typename T>
 __global__ void video_prep_s2d_w4_kernel(const T* __restrict__ in, __nv_bfloat16* __restrict__ out, int B, int Tn,
                                          int H, int W, float mul, float add) {
+  // One thread writes one complete 128-byte destination row (eight 16-byte stores): 4 taps x 12 channels + 16 zeros.
+  // Each source pixel pair is read by the four destination pixels it is a tap of (L1-resident re-reads).
   const int H2 = H / 2, W2 = W / 2;
   const long long total = (long long)B * Tn * H2 * W2;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -98,51 +100,37 @@ __global__ void video_prep_s2d_w4_kernel(const T* __restrict__ in, __nv_bfloat16
     r /= H2;
     const int t = (int)(r % Tn);
     const int b = (int)(r / Tn);
-    float f[16];
-#pragma unroll
-    for (int j = 12; j < 16; ++j) f[j] = 0.f;
+    float f[48];
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
 #pragma unroll
       for (int ph = 0; ph < 2; ++ph) {
-        const T* p = in + ((((long long)b * 3 + c) * Tn + t) * H + (2 * h2 + ph)) * W + 2 * w2;
-        float x0, x1;
-        if constexpr (sizeof(T) == 4) {
-          const float2 v = __ldg(reinterpret_cast<const float2*>(p));
-          x0 = v.x; x1 = v.y;
-        } else {
-          const uchar2 v = *reinterpret_cast<const uchar2*>(p);
-          x0 = (float)v.x; x1 = (float)v.y;
+        const T* p = in + ((((long long)b * 3 + c) * Tn + t) * H + (2 * h2 + ph)) * W;
+#pragma unroll
+        for (int jw = 0; jw < 4; ++jw) {
+          const int ws = w2 + jw - 2;
+          float x0 = 0.f, x1 = 0.f;
+          if (ws >= 0 && ws < W2) {
+            if constexpr (sizeof(T) == 4) {
+              const float2 v = __ldg(reinterpret_cast<const float2*>(p + 2 * ws));
+              x0 = fmaf(v.x, mul, add); x1 = fmaf(v.y, mul, add);
+            } else {
+              const uchar2 v = *reinterpret_cast<const uchar2*>(p + 2 * ws);
+              x0 = fmaf((float)v.x, mul, add); x1 = fmaf((float)v.y, mul, add);
+            }
+          }
+          f[jw * 12 + (ph * 2 + 0) * 3 + c] = x0;
+          f[jw * 12 + (ph * 2 + 1) * 3 + c] = x1;
         }
-        f[(ph * 2 + 0) * 3 + c] = fmaf(x0, mul, add);
-        f[(ph * 2 + 1) * 3 + c] = fmaf(x1, mul, add);
       }
     }
-    float lo[8], hi[8];
+    uint4* o = reinterpret_cast<uint4*>(out + i * 64);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { lo[j] = f[j]; hi[j] = f[8 + j]; }
-    const uint4 vlo = pack8(lo), vhi = pack8(hi);
-    // source pixel w2 is tap jw of destination pixel wd = w2 - jw + 2
-    const long long rowbase = (i - w2) * 64;
-#pragma unroll
-    for (int jw = 0; jw < 4; ++jw) {
-      const int wd = w2 - jw + 2;
-      if (wd >= 0 && wd < W2) {
-        uint4* o = reinterpret_cast<uint4*>(out + rowbase + (long long)wd * 64 + jw * 16);
-        o[0] = vlo;
-        o[1] = vhi;
-      }
-    }
-    // taps that fall outside the image are zero: destination w2 has missing taps jw with w2 + jw - 2 outside [0,W2)
-#pragma unroll
-    for (int jw = 0; jw < 4; ++jw) {
-      const int ws = w2 + jw - 2;
-      if (ws < 0 || ws >= W2) {
-        uint4* o = reinterpret_cast<uint4*>(out + rowbase + (long long)w2 * 64 + jw * 16);
-        o[0] = make_uint4(0, 0, 0, 0);
-        o[1] = make_uint4(0, 0, 0, 0);
-      }
-    }
+    for (int g = 0; g < 6; ++g)
+      o[g] = make_uint4(pack_bf16x2(f[8 * g], f[8 * g + 1]), pack_bf16x2(f[8 * g + 2], f[8 * g + 3]),
+                        pack_bf16x2(f[8 * g + 4], f[8 * g + 5]), pack_bf16x2(f[8 * g + 6], f[8 * g + 7]));
+    o[6] = make_uint4(0, 0, 0, 0);   // channels 48..63 are structural zeros (the stem kernels never multiply them)
+    o[7] = make_uint4(0, 0, 0, 0);
   }
 }
 

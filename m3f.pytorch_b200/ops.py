@@ -383,11 +383,12 @@ _stem_idx = {}
 
 
 def stem_s2d_index(device):
-    """idx[(kt*16 + jh*4 + jw)*16 + (ph*2+pw)*3 + c] = flat offset of W[c, kt, kh, kw] inside one filter, with
-    kh = 2*jh + ph - 1, kw = 2*jw + pw - 1 (entries outside the 7x7 window and the 4 pad channels are -1)."""
+    """idx[(kt*4 + jh)*64 + jw*12 + (ph*2+pw)*3 + c] = flat offset of W[c, kt, kh, kw] inside one filter, with
+    kh = 2*jh + ph - 1, kw = 2*jw + pw - 1 (entries outside the 7x7 window and channels 48..63 of every tap are -1):
+    the channel order m3t_video_prep_s2d_w4 writes."""
     key = str(device)
     if key not in _stem_idx:
-        idx = torch.full((5, 4, 4, 16), -1, dtype=torch.int32)
+        idx = torch.full((5, 4, 64), -1, dtype=torch.int32)
         for kt in range(5):
             for jh in range(4):
                 for jw in range(4):
@@ -396,7 +397,7 @@ def stem_s2d_index(device):
                             kh, kw = 2 * jh + ph - 1, 2 * jw + pw - 1
                             if 0 <= kh < 7 and 0 <= kw < 7:
                                 for c in range(3):
-                                    idx[kt, jh, jw, (ph * 2 + pw) * 3 + c] = ((c * 5 + kt) * 7 + kh) * 7 + kw
+                                    idx[kt, jh, jw * 12 + (ph * 2 + pw) * 3 + c] = ((c * 5 + kt) * 7 + kh) * 7 + kw
         _stem_idx[key] = idx.view(-1).to(device)
     return _stem_idx[key]
 

@@ -243,7 +243,7 @@ def case_elementwise(seed=0):
         for w2 in range(10):
             ws = w2 + jw - 2
             if 0 <= ws < 10:
-                ref4[:, :, :, w2, jw * 16:(jw + 1) * 16] = ref[:, :, :, ws]
+                ref4[:, :, :, w2, jw * 12:(jw + 1) * 12] = ref[:, :, :, ws, :12]
     errs["prep_w4"] = _err(x4, ref4)
     # layout conversion round trip
     x = torch.randn(3, 70, 5, 9, generator=g)
@@ -876,7 +876,9 @@ def case_stem_fprop_halo(seed=0):
     from m3t_b200 import raw
     g = torch.Generator().manual_seed(seed)
     B, T, H2, W2 = 3, 5, 56, 56
-    xs = _rnd((B, T, H2, W2, 64), g).cuda()
+    xs = _rnd((B, T, H2, W2, 64), g)
+    xs[..., 48:] = 0            # structural zeros of the W-unrolled layout: the halo kernel never multiplies them
+    xs = xs.cuda()
     w = _rnd((64, 1280), g, scale=0.03).cuda()
     geom = raw.conv_geom(3, B, T, H2, W2, 64, 64, (5, 4, 1), (1, 1, 1), (2, 2, 0), (2, 1, 0), (1, 1, 1))
     st0 = torch.zeros((2, 64), device="cuda")
