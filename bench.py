@@ -23,15 +23,17 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 # dram__bytes_read.sum + dram__bytes_write.sum per call of the kernels that can be the dominant one, from the
-# `ncu --set full` capture at this workload (profiles/r1_ncu_full_summary.md; 256 clips x 16 frames per GPU)
+# `ncu --set full` capture at this workload (profiles/r1_ncu_full_summary.md, capture prof_r1c; 256 clips x 16 frames per GPU)
 NCU_DRAM_TRAFFIC_256 = {
-    "wgrad-halo stem 16x56x56": 15.85e9,        # sum over its 5 launches (one per temporal tap)
+    "wgrad-halo stem 16x56x56": 6.562e9,        # sum over its 2 passes (3 + 2 temporal taps, activation box resident)
     "stem-halo 16x56x56": 3.244e9,
     "stem nd3 16x56x56 c64->64 k5x4x1 s1": 3.248e9,
     "wgrad nd3 16x56x56 c64->64 k5x4x1 s1": 8.788e9,
     "fprop-halo nd2 1x28x28 c64->64 k1x3x3 s1": 0.772e9,
     "dgrad-halo nd2 1x28x28 c64->64 k1x3x3 s1": 0.772e9,
     "wgrad-halo nd2 1x28x28 c64->64 k1x3x3 s1": 0.826e9,
+    "fprop-halo nd2 1x14x14 c128->128 k1x3x3 s1": 0.3615e9,
+    "dgrad-halo nd2 1x14x14 c128->128 k1x3x3 s1": 0.3615e9,
 }
 
 METRIC = "av_m3t_train_frames_per_sec"

@@ -16,6 +16,7 @@ def main():
     rb = lambda *s: torch.randn(s, device=dev).bfloat16()    # noqa: E731
     # stem fprop + wgrad (W-unrolled space-to-depth input)
     xs = rb(B, T, 56, 56, 64)
+    xs[..., 48:] = 0
     w = (torch.randn(64, 1280, device=dev) * 0.03).bfloat16()
     g = raw.conv_geom(3, B, T, 56, 56, 64, 64, (5, 4, 1), (1, 1, 1), (2, 2, 0), (2, 1, 0), (1, 1, 1))
     st = torch.zeros(2, 64, device=dev)
@@ -47,8 +48,15 @@ def main():
     x = rb(F, 14, 14, 128)
     w2 = (torch.randn(128, 1152, device=dev) * 0.03).bfloat16()
     g2 = raw.conv_geom(2, F, 1, 14, 14, 128, 128, (1, 3, 3), (1, 1, 1), (0, 1, 1), (0, 1, 1), (1, 1, 1))
-    y2 = raw.conv_fprop(x, w2, g2, stats=torch.zeros(2, 128, device=dev))
+    y2 = raw.conv_fprop(x, w2, g2, stats=torch.zeros(2, 128, device=dev))          # image-per-tile halo kernel
+    raw.USE_HALO128 = False
+    raw.conv_fprop(x, w2, g2, stats=torch.zeros(2, 128, device=dev))               # generic im2col, for comparison
+    raw.USE_HALO128 = True
     raw.conv_wgrad(x, y2.view(F, 14, 14, 128), g2)
+    # stride-2 dgrad of layer2.0.conv1 by parity (4 launches) into a 28x28x64 dX
+    from m3t_b200 import ops
+    wfull = torch.randn(128, 64, 3, 3, device=dev) * 0.05
+    ops.conv2d_dgrad(y2.view(F, 14, 14, 128), wfull, (F, 28, 28, 64), 2, 1)
     # GRU layer H=512 forward/backward, x-projection GEMM
     xg = rb(B * T, 512)
     wih = (torch.randn(3072, 512, device=dev) * 0.03).bfloat16()
