@@ -180,7 +180,7 @@ def run_reference(args, rank, world):
                                    "pure Python/PyTorch and cannot travel, so its oracle port is timed" % (clips, T_FRAMES)},
         "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 # ----------------------------------------------------------------------------------------------------------
@@ -243,8 +243,8 @@ def run_b200(args, rank, local_rank, world):
     # ---------------- end-to-end timing (host batch -> device every step, loss read back) ----------------
     if args.no_e2e:
         if rank == 0:
-            print(json.dumps({"metric": METRIC, "value": value, "ms_per_step": ms / args.steps, "profiling": True,
-                              "gpu_launches": int(launches)}), flush=True)
+            _emit({"metric": METRIC, "value": value, "ms_per_step": ms / args.steps, "profiling": True,
+                   "gpu_launches": int(launches)})
         return
     copy_stream = torch.cuda.Stream()
     bufs = [{k: torch.empty_like(v, device=dev) for k, v in host.items()} for _ in range(2)]
@@ -324,7 +324,7 @@ def run_b200(args, rank, local_rank, world):
             line["cpu_baseline"] = {"value": fps, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": "%d clips x %d frames per step, 1 warm-up + 3 timed steps of the same "
                                               "training step through oracle/ref_torch.py" % (clips, T_FRAMES)}
-        print(json.dumps(line), flush=True)
+        _emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -351,5 +351,16 @@ def main():
         run_b200(args, rank, local_rank, world)
 
 
+def _emit(obj):
+    """The one JSON line goes to the process's ORIGINAL stdout; everything else written to fd 1 while the bench runs
+    (NCCL's version banner, library chatter) has been redirected to stderr so the line stays alone."""
+    os.write(_REAL_STDOUT, (json.dumps(obj) + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
 if __name__ == "__main__":
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     main()
