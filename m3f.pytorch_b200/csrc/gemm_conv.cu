@@ -221,7 +221,12 @@ extern "C" int m3t_conv_wgrad_bf16(const void* x, const void* dy, float* dw_pack
   const int ck = conv_ck(g);
   p.tiles_n = ceil_div(g.Cout, bn);
   // 256-row CTA tiles (two accumulators share every dY stage) whenever there are enough M atoms
-  const int mt = (ck == 64 && p.atoms >= 4 && bn == 64 && !(splits_hint & (1 << 30))) ? 2 : 1;
+  // (bit 30 of splits_hint forces 128-row tiles).  With 128 columns the 256-row tile is used when the M atoms pair
+  // up evenly (measured, 4096 frames: 14x14x128 0.357 -> 0.328 ms, 7x7x256 0.368 -> 0.305, 4x4x512 0.472 -> 0.386;
+  // 9 atoms (64 -> 128 stride 2) lose to the padding; 256x256 tiles and 3-stage / 1-CTA-per-SM variants were no faster)
+  const bool force_mt1 = (splits_hint & (1 << 30)) != 0;
+  int mt = (ck == 64 && p.atoms >= 4 && bn == 64 && !force_mt1) ? 2 : 1;
+  if (ck == 64 && bn == 128 && p.atoms % 4 == 0 && !force_mt1) mt = 2;
   splits_hint &= ~(1 << 30);
   const int tiles_m = ceil_div(p.atoms, mt * 128 / ck);
   const int kblocks = ceil_div(Mpix, kBlockK);
@@ -253,5 +258,6 @@ extern "C" int m3t_conv_wgrad_bf16(const void* x, const void* dy, float* dw_pack
   if (bn == 64 && mt == 2)
     return launch_umma<64, 2, 2, A_WGRAD, false, true, EPI_ATOMIC_T>(tmA, tmB, p, tiles_m, splits, st);
   if (bn == 64) return launch_umma<64, 1, 4, A_WGRAD, false, true, EPI_ATOMIC_T>(tmA, tmB, p, tiles_m, splits, st);
+  if (mt == 2) return launch_umma<128, 2, 2, A_WGRAD, false, true, EPI_ATOMIC_T>(tmA, tmB, p, tiles_m, splits, st);
   return launch_umma<128, 1, 3, A_WGRAD, false, true, EPI_ATOMIC_T>(tmA, tmB, p, tiles_m, splits, st);
 }
