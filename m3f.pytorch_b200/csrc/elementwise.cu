@@ -209,6 +209,46 @@ __global__ void bn_act_kernel(const __nv_bfloat16* __restrict__ y, const float* 
   }
 }
 
+// Same, for the common case that every thread keeps one channel group over its whole grid-stride loop (total threads
+// a multiple of C/8): the per-channel constants live in registers and two vectors are in flight per iteration.
+template <bool HAS_RES, bool RELU>
+__global__ void __launch_bounds__(256, 4)
+bn_act_fixed_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ scale,
+                    const float* __restrict__ shift, const __nv_bfloat16* __restrict__ res,
+                    __nv_bfloat16* __restrict__ out, long long nvec, int C) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const int c = (int)((i * 8) % C);
+  float s[8], b[8];
+  load8f(scale + c, s);
+  load8f(shift + c, b);
+  for (; i < nvec; i += 2 * stride) {
+    const long long i2 = i + stride;
+    const bool two = i2 < nvec;
+    uint4 ya = __ldg(reinterpret_cast<const uint4*>(y) + i), yb = make_uint4(0, 0, 0, 0);
+    uint4 ra = make_uint4(0, 0, 0, 0), rb = make_uint4(0, 0, 0, 0);
+    if (two) yb = __ldg(reinterpret_cast<const uint4*>(y) + i2);
+    if (HAS_RES) {
+      ra = __ldg(reinterpret_cast<const uint4*>(res) + i);
+      if (two) rb = __ldg(reinterpret_cast<const uint4*>(res) + i2);
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      if (h == 1 && !two) break;
+      float v[8], r[8];
+      unpack8(h ? yb : ya, v);
+      if (HAS_RES) unpack8(h ? rb : ra, r);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float x = fmaf(v[j], s[j], b[j]);
+        if (HAS_RES) x += r[j];
+        v[j] = RELU ? fmaxf(x, 0.f) : x;
+      }
+      reinterpret_cast<uint4*>(out)[h ? i2 : i] = pack8(v);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // Backward of  out = act(y*scale + shift + resid)  with train-mode BN (batch statistics).
 //   dz = dout * (out > 0)                                  (relu)   |  dz = dout   (no relu)
@@ -307,6 +347,68 @@ __global__ void bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout, cons
       d[j] = sc[j] * (d[j] - s0[j] * inv_count - xh * s1[j] * inv_count);
     }
     reinterpret_cast<uint4*>(dy)[i] = pack8(d);
+  }
+}
+
+// Fixed-channel-group variant (total threads a multiple of C/8): dy = kA*dz + kB*y + kC with the three per-channel
+// coefficients in registers, two vectors in flight per iteration.
+template <int RELU>
+__global__ void __launch_bounds__(256, 4)
+bn_bwd_apply_fixed_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ out,
+                          const __nv_bfloat16* __restrict__ y, const float* __restrict__ mean,
+                          const float* __restrict__ invstd, const float* __restrict__ scale,
+                          const float* __restrict__ shift, const float* __restrict__ sums, float inv_count,
+                          __nv_bfloat16* __restrict__ dy, long long nvec, int C) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const int c = (int)((i * 8) % C);
+  float kA[8], kB[8], kC[8], sh[8];
+  {
+    float mu[8], is[8], s0[8], s1[8];
+    load8f(scale + c, kA);
+    load8f(mean + c, mu);
+    load8f(invstd + c, is);
+    load8f(sums + c, s0);
+    load8f(sums + C + c, s1);
+    if (RELU == 2) load8f(shift + c, sh);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      kB[j] = -kA[j] * is[j] * s1[j] * inv_count;
+      kC[j] = -kA[j] * s0[j] * inv_count - kB[j] * mu[j];
+    }
+  }
+  for (; i < nvec; i += 2 * stride) {
+    const long long i2 = i + stride;
+    const bool two = i2 < nvec;
+    const uint4 z4 = make_uint4(0, 0, 0, 0);
+    const uint4 da = __ldg(reinterpret_cast<const uint4*>(dout) + i);
+    const uint4 ya = __ldg(reinterpret_cast<const uint4*>(y) + i);
+    const uint4 db = two ? __ldg(reinterpret_cast<const uint4*>(dout) + i2) : z4;
+    const uint4 yb = two ? __ldg(reinterpret_cast<const uint4*>(y) + i2) : z4;
+    uint4 oa = z4, ob = z4;
+    if (RELU == 1) {
+      oa = __ldg(reinterpret_cast<const uint4*>(out) + i);
+      if (two) ob = __ldg(reinterpret_cast<const uint4*>(out) + i2);
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      if (h == 1 && !two) break;
+      float d[8], yy[8];
+      unpack8(h ? db : da, d);
+      unpack8(h ? yb : ya, yy);
+      if (RELU == 1) {
+        float o[8];
+        unpack8(h ? ob : oa, o);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) d[j] = o[j] > 0.f ? d[j] : 0.f;
+      } else if (RELU == 2) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) d[j] = fmaf(yy[j], kA[j], sh[j]) > 0.f ? d[j] : 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) d[j] = fmaf(kA[j], d[j], fmaf(kB[j], yy[j], kC[j]));
+      reinterpret_cast<uint4*>(dy)[h ? i2 : i] = pack8(d);
+    }
   }
 }
 
@@ -967,6 +1069,18 @@ extern "C" int m3t_bn_act(const void* y, const float* scale, const float* shift,
                           void* stream) {
   if (C % 8) return -1;
   const long long nvec = rows * C / 8;
+  if (kEwThreads % (C / 8) == 0 && !res_scale) {
+    const int blocks = ew_blocks((nvec + 1) / 2);
+#define ACT_FIXED(HR, RL)                                                                                      \
+  bn_act_fixed_kernel<HR, RL><<<blocks, kEwThreads, 0, ST(stream)>>>(CBF(y), scale, shift, CBF(res), BF(out), nvec, C)
+    if (res && relu) ACT_FIXED(true, true);
+    else if (res) ACT_FIXED(true, false);
+    else if (relu) ACT_FIXED(false, true);
+    else ACT_FIXED(false, false);
+#undef ACT_FIXED
+    count_launch();
+    return launch_status();
+  }
   bn_act_kernel<<<ew_blocks(nvec), kEwThreads, 0, ST(stream)>>>(CBF(y), scale, shift, CBF(res), res_scale, res_shift,
                                                                 relu, BF(out), nvec, C);
   count_launch();
@@ -1000,6 +1114,19 @@ extern "C" int m3t_bn_bwd_apply(const void* dout, const void* out, const void* y
                                 double count, int relu, void* dy, long long rows, int C, void* stream) {
   if (C % 8) return -1;
   const long long nvec = rows * C / 8;
+  if (kEwThreads % (C / 8) == 0) {
+    const int blocks = ew_blocks((nvec + 1) / 2);
+    const float ic = (float)(1.0 / count);
+#define APPLY_FIXED(R)                                                                                              \
+  bn_bwd_apply_fixed_kernel<R><<<blocks, kEwThreads, 0, ST(stream)>>>(CBF(dout), CBF(out), CBF(y), mean, invstd,    \
+                                                                     scale, shift, sums, ic, BF(dy), nvec, C)
+    if (relu == 0) APPLY_FIXED(0);
+    else if (relu == 1) APPLY_FIXED(1);
+    else APPLY_FIXED(2);
+#undef APPLY_FIXED
+    count_launch();
+    return launch_status();
+  }
   bn_bwd_apply_kernel<<<ew_blocks(nvec), kEwThreads, 0, ST(stream)>>>(CBF(dout), CBF(out), CBF(y), mean, invstd, scale,
                                                                       shift, sums, (float)(1.0 / count), relu, BF(dy),
                                                                       nvec, C);
