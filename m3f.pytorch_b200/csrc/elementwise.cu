@@ -259,7 +259,7 @@ bn_act_fixed_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict
 // relu: 0 = none, 1 = mask from the stored activation (out > 0), 2 = mask recomputed from y*scale + shift > 0 (units
 // without a residual input: `out` is then neither stored for backward nor read here)
 template <int relu>
-__global__ void __launch_bounds__(256, relu == 2 ? 3 : 4)
+__global__ void __launch_bounds__(256, relu == 2 ? 2 : 3)
 bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ out,
                      const __nv_bfloat16* __restrict__ y, const float* __restrict__ mean,
                      const float* __restrict__ invstd, const float* __restrict__ scale,
@@ -283,31 +283,48 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16
     load8f(shift + cg * 8, sft);
   }
   if (rl < rows_per_iter) {
-    for (long long r = (long long)blockIdx.x * rows_per_iter + rl; r < rows; r += (long long)gridDim.x * rows_per_iter) {
+    // two rows in flight per iteration; a1 accumulates sum dz*y and is centred once at the end
+    const long long rstride = (long long)gridDim.x * rows_per_iter;
+    for (long long r = (long long)blockIdx.x * rows_per_iter + rl; r < rows; r += 2 * rstride) {
       const long long i = r * cgs + cg;
-      float d[8], yy[8];
-      unpack8(__ldg(reinterpret_cast<const uint4*>(dout) + i), d);
-      unpack8(__ldg(reinterpret_cast<const uint4*>(y) + i), yy);
+      const bool two = r + rstride < rows;
+      const long long i2 = two ? (r + rstride) * cgs + cg : i;
+      const uint4 da = __ldg(reinterpret_cast<const uint4*>(dout) + i);
+      const uint4 ya = __ldg(reinterpret_cast<const uint4*>(y) + i);
+      const uint4 db = __ldg(reinterpret_cast<const uint4*>(dout) + i2);
+      const uint4 yb = __ldg(reinterpret_cast<const uint4*>(y) + i2);
+      uint4 oa = make_uint4(0, 0, 0, 0), ob = oa;
       if (relu == 1) {
-        float o[8];
-        unpack8(__ldg(reinterpret_cast<const uint4*>(out) + i), o);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) d[j] = o[j] > 0.f ? d[j] : 0.f;
-      } else if (relu == 2) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) d[j] = fmaf(yy[j], sc[j], sft[j]) > 0.f ? d[j] : 0.f;
+        oa = __ldg(reinterpret_cast<const uint4*>(out) + i);
+        ob = __ldg(reinterpret_cast<const uint4*>(out) + i2);
       }
-      if (dz_out) reinterpret_cast<uint4*>(dz_out)[i] = pack8(d);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        a0[j] += d[j];
-        a1[j] += d[j] * (yy[j] - mu[j]) * is[j];
+      for (int h = 0; h < 2; ++h) {
+        if (h == 1 && !two) break;
+        float d[8], yy[8];
+        unpack8(h ? db : da, d);
+        unpack8(h ? yb : ya, yy);
+        if (relu == 1) {
+          float o[8];
+          unpack8(h ? ob : oa, o);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) d[j] = o[j] > 0.f ? d[j] : 0.f;
+        } else if (relu == 2) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) d[j] = fmaf(yy[j], sc[j], sft[j]) > 0.f ? d[j] : 0.f;
+        }
+        if (dz_out) reinterpret_cast<uint4*>(dz_out)[h ? i2 : i] = pack8(d);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          a0[j] += d[j];
+          a1[j] = fmaf(d[j], yy[j], a1[j]);
+        }
       }
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       atomicAdd(&sh[cg * 8 + j], a0[j]);
-      atomicAdd(&sh[C + cg * 8 + j], a1[j]);
+      atomicAdd(&sh[C + cg * 8 + j], (a1[j] - mu[j] * a0[j]) * is[j]);
     }
   }
   __syncthreads();
@@ -912,14 +929,29 @@ __global__ void zero_insert2_kernel(const __nv_bfloat16* __restrict__ dy, __nv_b
 // out = a + b (bf16, vectors of 8) — gradient fan-in at residual forks
 __global__ void add_bf16_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b,
                                 __nv_bfloat16* __restrict__ out, long long nvec) {
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec;
-       i += (long long)gridDim.x * blockDim.x) {
-    float x[8], y[8];
-    unpack8(__ldg(reinterpret_cast<const uint4*>(a) + i), x);
-    unpack8(__ldg(reinterpret_cast<const uint4*>(b) + i), y);
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec; i += 4 * stride) {
+    uint4 va[4], vb[4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) x[j] += y[j];
-    reinterpret_cast<uint4*>(out)[i] = pack8(x);
+    for (int h = 0; h < 4; ++h) {     // four vectors in flight
+      const long long ih = i + h * stride;
+      if (ih < nvec) {
+        va[h] = __ldg(reinterpret_cast<const uint4*>(a) + ih);
+        vb[h] = __ldg(reinterpret_cast<const uint4*>(b) + ih);
+      }
+    }
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {
+      const long long ih = i + h * stride;
+      if (ih < nvec) {
+        float x[8], y[8];
+        unpack8(va[h], x);
+        unpack8(vb[h], y);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[j] += y[j];
+        reinterpret_cast<uint4*>(out)[ih] = pack8(x);
+      }
+    }
   }
 }
 
@@ -1288,7 +1320,7 @@ extern "C" int m3t_zero_insert2(const void* dy, void* up, int N, int P, int Q, i
 
 extern "C" int m3t_add_bf16(const void* a, const void* b, void* out, long long n, void* stream) {
   if (n % 8) return -1;
-  add_bf16_kernel<<<ew_blocks(n / 8), kEwThreads, 0, ST(stream)>>>(CBF(a), CBF(b), BF(out), n / 8);
+  add_bf16_kernel<<<ew_blocks((n / 8 + 3) / 4), kEwThreads, 0, ST(stream)>>>(CBF(a), CBF(b), BF(out), n / 8);
   count_launch();
   return launch_status();
 }
