@@ -183,13 +183,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         }
         if (ok) {
           float o[32];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            float x = v[i];
-            if (p.scale) x *= __ldg(p.scale + c0 + i);
-            if (p.shift) x += __ldg(p.shift + c0 + i);
-            o[i] = x;
-          }
+          epi_scale_shift32(o, v, p.scale, p.shift, c0);
           if (p.residual) {
             const uint4* rp = reinterpret_cast<const uint4*>(p.residual + pix * 64 + c0);
 #pragma unroll
@@ -407,12 +401,10 @@ stem_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           }
           if (ok) {
             float o[32];
+            epi_scale_shift32(o, v, p.scale, p.shift, c0);
+            if (p.relu) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              float x = v[i];
-              if (p.scale) x *= __ldg(p.scale + c0 + i);
-              if (p.shift) x += __ldg(p.shift + c0 + i);
-              o[i] = p.relu ? fmaxf(x, 0.f) : x;
+              for (int i = 0; i < 32; ++i) o[i] = fmaxf(o[i], 0.f);
             }
             uint4* op = reinterpret_cast<uint4*>(p.y + pix * 64 + c0);
 #pragma unroll

@@ -191,13 +191,7 @@ conv3x3_c128_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
           }
           if (ok) {
             float o[32];
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              float x = v[i];
-              if (p.scale) x *= __ldg(p.scale + c0 + i);
-              if (p.shift) x += __ldg(p.shift + c0 + i);
-              o[i] = x;
-            }
+            epi_scale_shift32(o, v, p.scale, p.shift, c0);
             if (p.residual) {
               const uint4* rp = reinterpret_cast<const uint4*>(p.residual + pix * 128 + c0);
 #pragma unroll

@@ -4,6 +4,7 @@
 #include "common.cuh"
 #include "tmap.cuh"
 #include "umma_kernel.cuh"
+#include "umma_persist.cuh"
 
 namespace m3t {
 
@@ -25,6 +26,28 @@ static int launch_umma(const CUtensorMap& tmA, const CUtensorMap& tmB, const Umm
 }
 
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+template <int BN, int MT, int STAGES, int AKIND>
+static int launch_persist(const CUtensorMap& tmA, const CUtensorMap& tmB, const UmmaParams& p, int tiles_m,
+                          cudaStream_t st) {
+  auto kern = umma_persist_kernel<BN, MT, STAGES, AKIND>;
+  constexpr int smem = umma_persist_smem_bytes<BN, MT, STAGES>();
+  static_assert(smem <= 227 * 1024, "shared memory");
+  static bool attr_done = false;
+  if (!attr_done) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return -20;
+    attr_done = true;
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int num_tiles = tiles_m * p.tiles_n;
+  int grid = num_tiles < sms ? num_tiles : sms;
+  if (p.tiles_n <= grid) grid -= grid % p.tiles_n;   // a CTA then keeps one column block (register-resident BN stats)
+  kern<<<grid, kUmmaThreads, smem, st>>>(tmA, tmB, p, num_tiles);
+  count_launch();
+  return launch_status();
+}
 
 }  // namespace m3t
 
@@ -131,6 +154,15 @@ static int conv_fprop_impl(const void* x, const void* w_packed, void* y, const i
                            const float* shift, const void* residual, int relu, float* stats, int tile_hint,
                            const long long* out_map, void* stream);
 
+// When the persistent kernel is the default (tests/tune_conv.py, 4096 frames): it wins whenever a tile has at least
+// two k-iterations (28->14 64->128 s2 0.198 -> 0.166 ms, 7x7x256 0.214 -> 0.189, 4x4x512 0.255 -> 0.226 = 1367
+// TFLOP/s, parity sub-convolutions 0.078 -> 0.071); with a single k-iteration (1x1, 64 channels) two co-resident
+// one-tile CTAs hide the epilogue better (0.107 vs 0.146 ms).
+static bool conv_use_persist(const ConvGeom& g, const UmmaParams& p, int bn, int mt) {
+  (void)g; (void)bn; (void)mt;
+  return p.k_iters >= 2;
+}
+
 extern "C" int m3t_conv_fprop_bf16(const void* x, const void* w_packed, void* y, const int* geom, const float* scale,
                                    const float* shift, const void* residual, int relu, float* stats, int tile_hint,
                                    void* stream) {
@@ -193,6 +225,15 @@ static int conv_fprop_impl(const void* x, const void* w_packed, void* y, const i
     if (bn != 64) return -4;
     if (mt == 2) return launch_umma<64, 2, 2, A_IM2COL, false, false, EPI_STORE, 16>(tmA, tmB, p, tiles_m, 1, st);
     return launch_umma<64, 1, 4, A_IM2COL, false, false, EPI_STORE, 16>(tmA, tmB, p, tiles_m, 1, st);
+  }
+  // persistent tile walker (umma_persist.cuh): tile_hint bit4 forces it, bit5 forbids it
+  const bool persist = (tile_hint & 16) != 0 || (!(tile_hint & 32) && conv_use_persist(g, p, bn, mt));
+  if (persist) {
+    if (bn == 64 && mt == 1) return launch_persist<64, 1, 8, A_IM2COL>(tmA, tmB, p, tiles_m, st);
+    if (bn == 64 && mt == 2) return launch_persist<64, 2, 5, A_IM2COL>(tmA, tmB, p, tiles_m, st);
+    if (bn == 128 && mt == 1) return launch_persist<128, 1, 6, A_IM2COL>(tmA, tmB, p, tiles_m, st);
+    if (bn == 128 && mt == 2) return launch_persist<128, 2, 4, A_IM2COL>(tmA, tmB, p, tiles_m, st);
+    if (bn == 256) return launch_persist<256, 1, 4, A_IM2COL>(tmA, tmB, p, tiles_m, st);
   }
   if (bn == 64 && mt == 1) return launch_umma<64, 1, 4, A_IM2COL, false, false, EPI_STORE>(tmA, tmB, p, tiles_m, 1, st);
   if (bn == 64 && mt == 2) return launch_umma<64, 2, 2, A_IM2COL, false, false, EPI_STORE>(tmA, tmB, p, tiles_m, 1, st);

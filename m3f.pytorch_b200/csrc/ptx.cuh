@@ -53,6 +53,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(32);   // the spinning producer / MMA lanes share issue slots with the epilogue warps of their SMSP
     if (clock64() - t0 > 4000000000LL) {
       printf("m3t: mbarrier timeout code=%u block=(%d,%d,%d) thread=%d parity=%u\n", code, blockIdx.x, blockIdx.y,
              blockIdx.z, threadIdx.x, parity);
@@ -204,6 +205,29 @@ __device__ __forceinline__ float bf16hi(uint32_t v) { return __uint_as_float(v &
 
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// Epilogue helper of the halo kernels: o[i] = v[i] * scale[c0+i] + shift[c0+i] for one 32-column chunk, with the
+// null checks hoisted out of the element loop and the constants read as float4 (per-element guarded loads cost
+// ~4 issue slots per value even when both pointers are null).  scale/shift point at 16-byte aligned arrays.
+__device__ __forceinline__ void epi_scale_shift32(float (&o)[32], const float (&v)[32], const float* scale,
+                                                  const float* shift, int c0) {
+#pragma unroll
+  for (int i = 0; i < 32; ++i) o[i] = v[i];
+  if (scale) {
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      const float4 sv = __ldg(reinterpret_cast<const float4*>(scale + c0) + g);
+      o[4 * g] *= sv.x; o[4 * g + 1] *= sv.y; o[4 * g + 2] *= sv.z; o[4 * g + 3] *= sv.w;
+    }
+  }
+  if (shift) {
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      const float4 bv = __ldg(reinterpret_cast<const float4*>(shift + c0) + g);
+      o[4 * g] += bv.x; o[4 * g + 1] += bv.y; o[4 * g + 2] += bv.z; o[4 * g + 3] += bv.w;
+    }
+  }
 }
 
 }  // namespace m3t

@@ -120,6 +120,98 @@ __device__ __forceinline__ void butterfly_colsum(float (&v)[32], uint32_t lane) 
 template <>
 __device__ __forceinline__ void butterfly_colsum<0>(float (&)[32], uint32_t) {}
 
+// Epilogue output of one 32-column chunk of one accumulator row: v * scale + shift (+ residual) (ReLU) -> bf16 / fp32.
+// m = row of D, mo = output row (after the optional scatter map), nc0 = first global column of the chunk, cols_left =
+// columns of the CTA tile from this chunk on.
+__device__ __forceinline__ void epi_store_chunk(const UmmaParams& p, const float (&v)[32], long long m, long long mo,
+                                                int nc0, int cols_left) {
+    float o[32];
+    // whole chunk inside N and 16-byte aligned constants (parameters living in a flat arena are only 4-byte aligned):
+    // vector loads of the per-column constants, no per-element guards
+    const bool vec_ok = nc0 + 32 <= p.N &&
+                        ((reinterpret_cast<uintptr_t>(p.scale) | reinterpret_cast<uintptr_t>(p.shift)) & 15) == 0;
+    if (vec_ok) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) o[i] = v[i];
+      if (p.scale) {
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          const float4 sv = __ldg(reinterpret_cast<const float4*>(p.scale + nc0) + g);
+          o[4 * g] *= sv.x; o[4 * g + 1] *= sv.y; o[4 * g + 2] *= sv.z; o[4 * g + 3] *= sv.w;
+        }
+      }
+      if (p.shift) {
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          const float4 bv = __ldg(reinterpret_cast<const float4*>(p.shift + nc0) + g);
+          o[4 * g] += bv.x; o[4 * g + 1] += bv.y; o[4 * g + 2] += bv.z; o[4 * g + 3] += bv.w;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const int n = nc0 + i;
+        float x = v[i];
+        if (n < p.N) {
+          if (p.scale) x *= __ldg(p.scale + n);
+          if (p.shift) x += __ldg(p.shift + n);
+        }
+        o[i] = x;
+      }
+    }
+    const int ncols = min(32, min(cols_left, p.N - nc0));
+    if (p.residual) {
+      const __nv_bfloat16* rp = p.residual + (p.res_mapped ? mo : m) * p.ldr + nc0;
+      if (ncols == 32 && (p.ldr & 7) == 0) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const uint4 rv = __ldg(reinterpret_cast<const uint4*>(rp) + g);
+          const uint32_t w4[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            o[g * 8 + 2 * j] += bf16lo(w4[j]);
+            o[g * 8 + 2 * j + 1] += bf16hi(w4[j]);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (i < ncols) o[i] += __bfloat162float(rp[i]);
+      }
+    }
+    if (p.relu) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) o[i] = fmaxf(o[i], 0.f);
+    }
+    if (ncols > 0) {
+      if (p.out_f32) {
+        float* op = reinterpret_cast<float*>(p.out) + mo * p.ldc + nc0;
+        if (ncols == 32 && (p.ldc & 3) == 0) {
+#pragma unroll
+          for (int g = 0; g < 8; ++g)
+            reinterpret_cast<float4*>(op)[g] = make_float4(o[4 * g], o[4 * g + 1], o[4 * g + 2], o[4 * g + 3]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (i < ncols) op[i] = o[i];
+        }
+      } else {
+        __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + mo * p.ldc + nc0;
+        if (ncols == 32 && (p.ldc & 7) == 0) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+            reinterpret_cast<uint4*>(op)[g] =
+                make_uint4(pack_bf16x2(o[8 * g], o[8 * g + 1]), pack_bf16x2(o[8 * g + 2], o[8 * g + 3]),
+                           pack_bf16x2(o[8 * g + 4], o[8 * g + 5]), pack_bf16x2(o[8 * g + 6], o[8 * g + 7]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (i < ncols) op[i] = __float2bfloat16(o[i]);
+        }
+      }
+    }
+}
+
 // CK = channels per filter-tap chunk of the implicit-GEMM operand: 64 (one 128B swizzle row per pixel) for the
 // trunk, 16 (32B rows, SWIZZLE_32B, four taps per pipeline stage) for the space-to-depth stem whose Cin is 16.
 template <int BN, int MT, int STAGES, int AKIND, bool A_MN, bool B_MN, int EPI, int CK = 64>
@@ -322,70 +414,7 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             }
           }
           // ---- output ----
-          if (row_ok) {
-            float o[32];
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const int n = n0 + c0 + i;
-              float x = v[i];
-              if (n < p.N) {
-                if (p.scale) x *= __ldg(p.scale + n);
-                if (p.shift) x += __ldg(p.shift + n);
-              }
-              o[i] = x;
-            }
-            const int ncols = min(32, min(BN - c0, p.N - (n0 + c0)));
-            if (p.residual) {
-              const __nv_bfloat16* rp = p.residual + (p.res_mapped ? mo : m) * p.ldr + n0 + c0;
-              if (ncols == 32 && (p.ldr & 7) == 0) {
-#pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                  const uint4 rv = __ldg(reinterpret_cast<const uint4*>(rp) + g);
-                  const uint32_t w4[4] = {rv.x, rv.y, rv.z, rv.w};
-#pragma unroll
-                  for (int j = 0; j < 4; ++j) {
-                    o[g * 8 + 2 * j] += bf16lo(w4[j]);
-                    o[g * 8 + 2 * j + 1] += bf16hi(w4[j]);
-                  }
-                }
-              } else {
-#pragma unroll
-                for (int i = 0; i < 32; ++i)
-                  if (i < ncols) o[i] += __bfloat162float(rp[i]);
-              }
-            }
-            if (p.relu) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) o[i] = fmaxf(o[i], 0.f);
-            }
-            if (ncols > 0) {
-              if (p.out_f32) {
-                float* op = reinterpret_cast<float*>(p.out) + mo * p.ldc + n0 + c0;
-                if (ncols == 32 && (p.ldc & 3) == 0) {
-#pragma unroll
-                  for (int g = 0; g < 8; ++g)
-                    reinterpret_cast<float4*>(op)[g] = make_float4(o[4 * g], o[4 * g + 1], o[4 * g + 2], o[4 * g + 3]);
-                } else {
-#pragma unroll
-                  for (int i = 0; i < 32; ++i)
-                    if (i < ncols) op[i] = o[i];
-                }
-              } else {
-                __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + mo * p.ldc + n0 + c0;
-                if (ncols == 32 && (p.ldc & 7) == 0) {
-#pragma unroll
-                  for (int g = 0; g < 4; ++g)
-                    reinterpret_cast<uint4*>(op)[g] =
-                        make_uint4(pack_bf16x2(o[8 * g], o[8 * g + 1]), pack_bf16x2(o[8 * g + 2], o[8 * g + 3]),
-                                   pack_bf16x2(o[8 * g + 4], o[8 * g + 5]), pack_bf16x2(o[8 * g + 6], o[8 * g + 7]));
-                } else {
-#pragma unroll
-                  for (int i = 0; i < 32; ++i)
-                    if (i < ncols) op[i] = __float2bfloat16(o[i]);
-                }
-              }
-            }
-          }
+          if (row_ok) epi_store_chunk(p, v, m, mo, n0 + c0, BN - c0);
           // ---- per-column statistics of the raw accumulator (train-mode BatchNorm) ----
           if (want_stats) {
             float s1[32], s2[32];

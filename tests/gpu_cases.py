@@ -907,6 +907,20 @@ CASES["conv2d_c128_halo_many"] = (case_conv, _c(nd=2, N=333, D=1, H=14, W=14, Ci
                                                 stride=(1, 1, 1), pad_lo=(0, 1, 1), stats=True))
 
 
+# persistent tile walker (umma_persist.cuh), forced with tile_hint bit 4: many tiles per CTA (ring and TMEM phases wrap),
+# two column blocks, statistics in registers across tiles, fused epilogue, one k-iteration per tile
+CASES["conv2d_persist_stats"] = (case_conv, _c(nd=2, N=300, D=1, H=14, W=14, Cin=128, Cout=128, k=(1, 3, 3),
+                                               stride=(1, 1, 1), pad_lo=(0, 1, 1), stats=True, tile_hint=16))
+CASES["conv2d_persist_fused_512"] = (case_conv, _c(nd=2, N=700, D=1, H=7, W=7, Cin=256, Cout=512, k=(1, 3, 3),
+                                                   stride=(1, 1, 1), pad_lo=(0, 1, 1), fused=True, tile_hint=16))
+CASES["conv2d_persist_stats_512"] = (case_conv, _c(nd=2, N=700, D=1, H=7, W=7, Cin=256, Cout=512, k=(1, 3, 3),
+                                                   stride=(1, 1, 1), pad_lo=(0, 1, 1), stats=True, tile_hint=16))
+CASES["conv2d_persist_1x1_s2"] = (case_conv, _c(nd=2, N=40, D=1, H=28, W=28, Cin=64, Cout=128, k=(1, 1, 1),
+                                                stride=(1, 2, 2), pad_lo=(0, 0, 0), stats=True, tile_hint=16))
+CASES["conv2d_persist_mt1_64"] = (case_conv, _c(nd=2, N=30, D=1, H=28, W=28, Cin=64, Cout=64, k=(1, 3, 3),
+                                                stride=(1, 1, 1), pad_lo=(0, 1, 1), stats=True, tile_hint=17))
+
+
 def case_dgrad_s2(H, K, pad, Cin, Cout, N=5, seed=0):
     """Stride-2 data gradient by output parity (four small stride-1 convolutions of dY scattered into dX) vs the
     zero-inserted formulation and vs conv_transpose on the CPU."""
