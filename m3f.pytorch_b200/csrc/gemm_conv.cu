@@ -78,6 +78,12 @@ extern "C" int m3t_gemm_bf16(const void* A, long long lda, int a_mn, const void*
   if (!b_mn) rc = make_tmap_2d_bf16(&tmB, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, 64, (uint32_t)bn);
   else rc = make_tmap_2d_bf16(&tmB, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 64, 64);
   if (rc) return rc;
+  // K-major x K-major with more tiles than SMs: the persistent tile walker (epilogue of tile i overlaps tile i+1)
+  if (!a_mn && !b_mn && p.k_iters >= 2 && (long long)tiles_m * p.tiles_n > 148) {
+    if (bn == 32) return launch_persist<32, 1, 8, A_TILED>(tmA, tmB, p, tiles_m, st);
+    if (bn == 64) return launch_persist<64, 1, 8, A_TILED>(tmA, tmB, p, tiles_m, st);
+    return launch_persist<128, 1, 6, A_TILED>(tmA, tmB, p, tiles_m, st);
+  }
 #define GEMM_CASE(BN_, AMN_, BMN_)                                                                         \
   if (bn == BN_ && (bool)a_mn == AMN_ && (bool)b_mn == BMN_)                                               \
     return launch_umma<BN_, 1, (BN_ >= 128 ? 4 : 4), A_TILED, AMN_, BMN_, EPI_STORE>(tmA, tmB, p, tiles_m, 1, st);
