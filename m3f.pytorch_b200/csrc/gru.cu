@@ -62,10 +62,11 @@ __device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
   return v;
 }
 // all threads of the CTA call; thread 0 arrives / polls
+// Arrival = CTA barrier (orders every thread's global writes before thread 0) + ONE gpu-scope release reduction:
+// release is cumulative over what thread 0 observed through bar.sync, so no per-thread __threadfence is needed.
 __device__ __forceinline__ void group_arrive(unsigned* counter) {
-  __threadfence();
   __syncthreads();
-  if (threadIdx.x == 0) atomicAdd(counter, 1u);
+  if (threadIdx.x == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
 }
 __device__ __forceinline__ void group_wait(const unsigned* counter, unsigned target) {
   if (threadIdx.x == 0) {
@@ -77,9 +78,8 @@ __device__ __forceinline__ void group_wait(const unsigned* counter, unsigned tar
         __trap();
       }
     }
-    __threadfence();
   }
-  __syncthreads();
+  __syncthreads();   // the acquire load of thread 0 + this barrier order the other threads' reads after the arrivals
 }
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
 

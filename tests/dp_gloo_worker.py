@@ -50,6 +50,15 @@ def main():
     eng._allreduce_grads()
     for v, e in zip(eng.grad_views, exp):
         assert torch.allclose(v, e, atol=1e-6), (rank, (v - e).abs().max())
+    # the overlapped path (second step on): bucketed async all-reduce issued from post-accumulate hooks; with lr = 0 the
+    # parameters do not move, so every step must reproduce the same mean gradient in the arena
+    eng.num_buckets = 2
+    eng.want_overlap = True
+    for _ in range(3):
+        eng.step(batch)
+        assert eng.overlap and len(eng.buckets) == 2
+        for v, e in zip(eng.grad_views, exp):
+            assert torch.allclose(v, e, atol=1e-6), (rank, "overlap", (v - e).abs().max())
     print("DP_OK rank %d" % rank, flush=True)
     dist.destroy_process_group()
 
