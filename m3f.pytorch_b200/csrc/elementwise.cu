@@ -1126,7 +1126,10 @@ extern "C" int m3t_bn_bwd_reduce(const void* dout, const void* out, const void* 
   const int cgs = C / 8;
   const int rows_per_iter = kEwThreads / cgs;
   long long blocks = (rows + rows_per_iter - 1) / rows_per_iter;
-  if (blocks > 148 * 8) blocks = 148 * 8;
+  // exactly one resident wave (launch bounds: 3 CTAs per SM, 2 for the mask-from-y variant): every CTA gets the same
+  // share of the grid-stride loop, no partial last wave
+  const long long cap = 148LL * (relu == 2 ? 2 : 3);
+  if (blocks > cap) blocks = cap;
   const size_t sm = 2 * C * sizeof(float);
   if (relu == 0)
     bn_bwd_reduce_kernel<0><<<(int)blocks, kEwThreads, sm, ST(stream)>>>(CBF(dout), CBF(out), CBF(y), mean, invstd,
