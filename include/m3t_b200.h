@@ -246,6 +246,34 @@ int m3t_patch3x3_c1(const float* x, void* out, int N, int H, int W, void* stream
  * mode 1 additionally sets the descriptor base_offset to (addr >> 7) & 7. */
 int m3t_debug_rowshift(const void* A, const void* B, float* out, int shift_rows, int mode, void* stream);
 
+/* ---- evaluation post-processing on the device (csrc/postproc.cu) --------------------------------
+ * All videos at once as ragged sequences: seq_off[v]..seq_off[v+1] (V+1 int64, device) are the frames of video v in
+ * one flat [total_frames][C] array. */
+
+/* Overlap-add of window predictions into per-video frame tracks, then halving of frames >= window/2 of every video
+ * (the half-stride windows cover them twice).  pred f32 [S][L][C]; seg_start/seg_len int32 [S] (start frame inside
+ * the video, valid frames of the segment); seg_base int64 [S] = seq_off[video of segment]; out f32
+ * [total_frames][C] (zeroed here).  Replaces the Python loops of models/model.py:281-297 (validation_end) and
+ * :358-366 (test_end).  With at most two windows per frame the fp32 sums are order-independent (bit-exact). */
+int m3t_overlap_add_f32(const float* pred, const int* seg_start, const int* seg_len, const long long* seg_base,
+                        const long long* seq_off, float* out, long long S, int L, int C, int V,
+                        long long total_frames, int window, void* stream);
+
+/* scipy.signal.wiener(x, window) along the frames of every (video, channel) sequence, float64 arithmetic on the
+ * float32 tracks exactly as scipy promotes them (x**2 in float32, sums and the filter in float64).
+ * lmean, lvar: f64 [total_frames][C] workspaces; noise_sum: f64 [V][C] workspace; out f64 [total_frames][C];
+ * max_len = longest sequence.  Replaces models/utils.py:29-33 smooth_predictions(mode='wiener') as called with
+ * window 35 by get_smoothed_ccc.py:15-16. */
+int m3t_wiener1d_f64(const float* x, const long long* seq_off, int V, int C, int window, long long max_len,
+                     double* lmean, double* lvar, double* noise_sum, double* out, void* stream);
+
+/* Moments for the masked concordance correlation: moments f64 [V][C][6] = {n, sum a, sum b, sum a^2, sum b^2,
+ * sum ab} over the frames whose ground truth is >= -1 in EVERY channel (a = pred f64, b = gt f32).  Per-video CCC
+ * and, by adding the moments over videos, the global CCC follow in closed form.  Replaces
+ * models/utils.py:19-21 concordance_cc2_np + the mask / concatenation of get_smoothed_ccc.py:17-30. */
+int m3t_ccc_moments_f64(const double* pred, const float* gt, const long long* seq_off, int V, int C, double* moments,
+                        void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -29,6 +29,65 @@ def timed(fn, warm=3, iters=10):
     return e0.elapsed_time(e1) / iters, (lib.launch_count() - n0) // iters
 
 
+def postproc_line():
+    """overlap-add + Wiener(35) + masked CCC for a validation-set-sized problem (70 videos, 2000-9000
+    frames, window 32 at half stride, V/A) on the device, next to scipy.signal.wiener + numpy (what the reference
+    calls) on ONE host core for the same tracks."""
+    import time
+
+    import numpy as np
+    from m3t_b200.process import postproc as PP
+    rng = np.random.default_rng(0)
+    window, C = 32, 2
+    lengths = [int(x) for x in rng.integers(2000, 9000, size=70)]
+    segs = []
+    for v, n in enumerate(lengths):
+        st = 0
+        while True:
+            ln = min(window, n - st)
+            segs.append((v, st, ln))
+            if st + ln >= n:
+                break
+            st += window // 2
+    S = len(segs)
+    preds = np.tanh(rng.standard_normal((S, window, C)).cumsum(1) * 0.2).astype(np.float32)
+    gts = np.clip(preds * 0.8 + rng.standard_normal((S, window, C)) * 0.2, -1, 1).astype(np.float32)
+    vids, starts, lens = [s[0] for s in segs], [s[1] for s in segs], [s[2] for s in segs]
+    dp, dg = torch.from_numpy(preds).cuda(), torch.from_numpy(gts).cuda()
+
+    def run():
+        tp = PP.overlap_add(dp, starts, vids, lens, window, len(lengths))
+        tg = PP.overlap_add(dg, starts, vids, lens, window, len(lengths))
+        return PP.concordance_cc2_np(PP.smooth_predictions(tp, 35), tg)
+
+    ms, nl = timed(run)
+    total = sum(lengths)
+    algo_bytes = total * C * (4 + 2 * 8 + 8 + 4 + 8 + 8) + 2 * S * window * C * 4   # wiener in/out + workspaces + ccc reads
+    cpu_ms = None
+    try:
+        from scipy.signal import wiener
+        tp = PP.overlap_add(dp, starts, vids, lens, window, len(lengths))
+        tg = PP.overlap_add(dg, starts, vids, lens, window, len(lengths))
+        tps, tgs = [t.cpu().numpy() for t in tp.split()], [t.cpu().numpy() for t in tg.split()]
+        t0 = time.perf_counter()
+        allp, allg = [], []
+        for p_, g_ in zip(tps, tgs):
+            sm = np.stack([wiener(p_[:, c], 35) for c in range(C)], 1)
+            valid = np.all(g_ >= -1, axis=1)
+            allp.append(sm[valid])
+            allg.append(g_[valid])
+        P_, G_ = np.concatenate(allp), np.concatenate(allg)
+        for c in range(C):
+            mcp = ((P_[:, c] - P_[:, c].mean()) * (G_[:, c] - G_[:, c].mean())).mean()
+            _ = 2 * mcp / (P_[:, c].var() + G_[:, c].var() + (P_[:, c].mean() - G_[:, c].mean()) ** 2)
+        cpu_ms = (time.perf_counter() - t0) * 1e3
+    except ImportError:
+        pass
+    return {"config": "N3", "what": "eval post-processing: overlap-add + Wiener(35) + masked CCC, 70 videos / %d frames"
+            % total, "ms": ms, "frames_per_s": total / ms * 1e3, "launches": nl,
+            "achieved_GBps": algo_bytes / ms / 1e6, "cpu_scipy_numpy_ms_1core_smooth_and_ccc_only": cpu_ms}
+
+
 def hp(**kw):
     d = dict(backbone="resnet", backend="gru", modality="audiovisual", fusion_type="attention", window=32,
              loss="ccc_mtl", loss_lambda=0.5, num_hidden=512, split_layer=5, num_fc_layers=2, learning_rate=5e-5,
@@ -95,6 +154,7 @@ def main():
         out.append({"config": 5, "what": "AV attention eval 16 clips x T=%d (resnet backbone)" % T, "ms": ms,
                     "frames_per_s": 16 * T / ms * 1e3, "launches": nl})
         del m, b
+    out.append(postproc_line())
     for o in out:
         print(json.dumps(o), flush=True)
 

@@ -8,6 +8,7 @@ through the C ABI and compares with a plain fp32 PyTorch CPU evaluation of the s
 Metric: max|y - ref| / max|ref| (range-normalised).
 """
 import json
+import os
 import math
 import sys
 
@@ -946,6 +947,71 @@ CASES["dgrad_s2_3x3_28"] = (case_dgrad_s2, _c(H=28, K=3, pad=1, Cin=64, Cout=128
 CASES["dgrad_s2_3x3_7"] = (case_dgrad_s2, _c(H=7, K=3, pad=1, Cin=256, Cout=512))
 CASES["dgrad_s2_1x1_14"] = (case_dgrad_s2, _c(H=14, K=1, pad=0, Cin=128, Cout=256))
 CASES["dgrad_s2_1x1_7"] = (case_dgrad_s2, _c(H=7, K=1, pad=0, Cin=256, Cout=512))
+
+
+def case_postproc(seed=0):
+    """Device evaluation post-processing (overlap-add, Wiener window 35, masked CCC) vs the golden outputs of the
+    reference's validation_end / smooth_predictions / concordance_cc2_np, and vs the oracle on a larger ragged set."""
+    import numpy as np
+    from m3t_b200.process import postproc as PP
+    from oracle import postproc as O
+    fx = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "postproc.pt"))
+    segs = fx["segs"]
+    vids, starts, lens = [s[0] for s in segs], [s[1] for s in segs], [s[2] for s in segs]
+    V = len(fx["lengths"])
+    tp = PP.overlap_add(fx["preds"].cuda(), starts, vids, lens, fx["window"], V)
+    tg = PP.overlap_add(fx["gts"].cuda(), starts, vids, lens, fx["window"], V)
+    errs = {}
+    errs["oadd_exact"] = float(max((a.cpu() != b).sum() for a, b in zip(tp.split(), fx["track_pred"])) +
+                               max((a.cpu() != b).sum() for a, b in zip(tg.split(), fx["track_gt"])))
+    sm = PP.smooth_predictions(tp, 35, mode="wiener")
+    errs["wiener"] = max(float((a.cpu() - b).abs().max()) for a, b in zip(sm.split(), fx["smooth"]))
+    pv, ov = PP.concordance_cc2_np(sm, tg)
+    errs["ccc_video"] = float((pv.cpu() - fx["ccc_per_video"]).abs().max())
+    errs["ccc_all"] = float((ov.cpu() - fx["ccc_overall"]).abs().max())
+    # larger ragged set vs the oracle: 37 videos of 40..3000 frames, window 16, some invalid annotations
+    rng = np.random.default_rng(seed)
+    window, C = 16, 2
+    lengths = [int(x) for x in rng.integers(40, 3000, size=37)]
+    segs = []
+    for v, n in enumerate(lengths):
+        st = 0
+        while True:
+            ln = min(window, n - st)
+            segs.append((v, st, ln))
+            if st + ln >= n:
+                break
+            st += window // 2
+    S = len(segs)
+    preds = np.tanh(rng.standard_normal((S, window, C)).cumsum(1) * 0.2).astype(np.float32)
+    gts = np.clip(preds * 0.8 + rng.standard_normal((S, window, C)) * 0.2, -1, 1).astype(np.float32)
+    gts[rng.integers(0, S, size=50), rng.integers(0, window, size=50), rng.integers(0, C, size=50)] = -5.0
+    order = rng.permutation(S)
+    vids, starts, lens = [segs[i][0] for i in order], [segs[i][1] for i in order], [segs[i][2] for i in order]
+    tp = PP.overlap_add(torch.from_numpy(preds[order]).cuda(), starts, vids, lens, window, len(lengths))
+    tg = PP.overlap_add(torch.from_numpy(gts[order]).cuda(), starts, vids, lens, window, len(lengths))
+    otp = O.overlap_add(preds[order], starts, vids, lens, window, len(lengths))
+    otg = O.overlap_add(gts[order], starts, vids, lens, window, len(lengths))
+    errs["oadd_exact_big"] = float(sum(int((a.cpu().numpy() != b).sum()) for a, b in zip(tp.split(), otp)))
+    sm = PP.smooth_predictions(tp, 35, mode="wiener")
+    pv, ov = PP.concordance_cc2_np(sm, tg)
+    opv, oov = O.smoothed_ccc(otp, otg, 35)
+    errs["wiener_big"] = max(float(np.abs(a.cpu().numpy()[:, c] - O.wiener(b[:, c], 35)).max())
+                             for a, b in list(zip(sm.split(), otp))[:6] for c in range(C))
+    errs["ccc_video_big"] = float(np.abs(pv.cpu().numpy() - opv).max())
+    errs["ccc_all_big"] = float(np.abs(ov.cpu().numpy() - oov).max())
+    return errs
+
+
+CASES["postproc_eval"] = (case_postproc, _c())
+# overlap-add: bit-exact (count of differing elements must be 0 -> below any positive tolerance); Wiener in float64:
+# summation order only; CCC: the reference reduces the float32 ground truth in float32, the device in float64
+for _k in ("oadd_exact", "oadd_exact_big"):
+    TOLS[_k] = 0.5
+for _k in ("wiener", "wiener_big"):
+    TOLS[_k] = 1e-10
+for _k in ("ccc_video", "ccc_all", "ccc_video_big", "ccc_all_big"):
+    TOLS[_k] = 1e-6
 
 
 if __name__ == "__main__":

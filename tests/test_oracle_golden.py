@@ -1,6 +1,8 @@
 """CPU: pin oracle/ref_torch.py against the golden vectors produced by the unmodified reference modules
 (oracle/make_golden.py).  fp32 vs fp32 on the same ATen kernels: tolerance 2e-5 range-normalised on outputs,
 5e-4 on gradients (summation order differs between the explicit GRU loop and nn.GRU)."""
+import os
+
 import pytest
 import torch
 
@@ -134,3 +136,23 @@ def test_ccc():
     fx = load("ccc")
     out = torch.stack([R.concordance_cc2(fx["inputs"]["r1"][i], fx["inputs"]["r2"][i]) for i in range(3)])
     assert rel_err(out, fx["out"]) < 1e-6
+
+
+def test_postproc_oracle_vs_reference_golden():
+    """oracle/postproc.py against the outputs of the reference's validation_end / smooth_predictions (scipy.signal.wiener)
+    / concordance_cc2_np recorded in tests/golden/postproc.pt (oracle/make_golden_postproc.py)."""
+    import numpy as np
+    from oracle import postproc as O
+    fx = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "postproc.pt"))
+    segs = fx["segs"]
+    vids, starts, lens = [s[0] for s in segs], [s[1] for s in segs], [s[2] for s in segs]
+    tracks = O.overlap_add(fx["preds"].numpy(), starts, vids, lens, fx["window"], len(fx["lengths"]))
+    gtr = O.overlap_add(fx["gts"].numpy(), starts, vids, lens, fx["window"], len(fx["lengths"]))
+    for t, g, rt, rg in zip(tracks, gtr, fx["track_pred"], fx["track_gt"]):
+        assert np.array_equal(t, rt.numpy()) and np.array_equal(g, rg.numpy())          # fp32 sums of <= 2 terms: exact
+    for t, sm in zip(tracks, fx["smooth"]):
+        for c in range(2):
+            assert np.abs(O.wiener(t[:, c], 35) - sm[:, c].numpy()).max() < 1e-12
+    per_video, overall = O.smoothed_ccc(tracks, gtr, 35)
+    assert np.abs(per_video - fx["ccc_per_video"].numpy()).max() < 1e-12
+    assert np.abs(overall - fx["ccc_overall"].numpy()).max() < 1e-12
