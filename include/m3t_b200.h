@@ -127,6 +127,15 @@ int m3t_video_prep_s2d(const void* video, int is_u8, void* out, int B, int T, in
 int m3t_video_prep_s2d_w4(const void* video, int is_u8, void* out, int B, int T, int H, int W, float mul, float add,
                           void* stream);
 
+/* Input pipeline on the device: the tensor m3t_video_prep_s2d_w4 produces, straight from DECODED uint8
+ * frames [B][T][Hs][Ws][3] (HWC, channel order as decoded) with the reference's per-clip augmentations applied on the
+ * fly: params int32 [B][8] = {crop_x, crop_y, flip, cut_y1, cut_y2, cut_x1, cut_x2, 0}; clip pixel (y,x) = frame pixel
+ * (crop_y+y, crop_x+(flip ? W-1-x : x)); the cutout rectangle [cut_y1,cut_y2) x [cut_x1,cut_x2) of the clip is 127.5.
+ * Replaces the crop / cv2.flip / stack / sequence_cutout steps of models/dataset.py:46-80 (load_video, no-resize case
+ * crop_size == 112) and :16-31 (sequence_cutout), the float32 CTHW copy and the H2D transfer of 4-byte pixels. */
+int m3t_video_augment_prep_s2d_w4(const void* frames_u8, const int* params, void* out, int B, int T, int Hs, int Ws,
+                                  int H, int W, float mul, float add, void* stream);
+
 /* Train-mode BatchNorm statistics -> per-channel scale/shift (+ running-stat update, momentum, unbiased variance).
  * stats = [2][C] column (sum, sum of squares) produced by the conv epilogue.  Replaces the statistics half of
  * nn.BatchNorm2d/3d in training (models/resnet.py:25,28; models/backbone.py:329). */

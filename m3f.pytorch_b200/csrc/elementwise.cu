@@ -134,6 +134,70 @@ __global__ void video_prep_s2d_w4_kernel(const T* __restrict__ in, __nv_bfloat16
   }
 }
 
+// Input pipeline on the device: the same W-unrolled space-to-depth tensor straight from DECODED
+// uint8 frames [B][T][Hs][Ws][3] (HWC, channel order as decoded - the reference keeps cv2's BGR) with the reference's
+// per-clip augmentations applied on the fly (models/dataset.py:46-80 load_video, :16-31 sequence_cutout):
+//   crop   pixel (y,x) of the H x W clip = frame pixel (crop_y + y, crop_x + x)        (same window for every frame)
+//   mirror x -> W-1-x after the crop                                                     (cv2.flip(img, 1))
+//   cutout rectangle [cy1,cy2) x [cx1,cx2) of the (cropped, mirrored) clip := 127.5    (zero after normalisation)
+// params int32 [B][8] = {crop_x, crop_y, flip, cy1, cy2, cx1, cx2, 0}.
+__global__ void video_augment_prep_s2d_w4_kernel(const uint8_t* __restrict__ frames, const int* __restrict__ params,
+                                                 __nv_bfloat16* __restrict__ out, int B, int Tn, int Hs, int Ws, int H,
+                                                 int W, float mul, float add) {
+  const int H2 = H / 2, W2 = W / 2;
+  const long long total = (long long)B * Tn * H2 * W2;
+  const float fill = fmaf(127.5f, mul, add);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int w2 = (int)(i % W2);
+    long long r = i / W2;
+    const int h2 = (int)(r % H2);
+    r /= H2;
+    const int t = (int)(r % Tn);
+    const int b = (int)(r / Tn);
+    const int* pp = params + b * 8;
+    const int crop_x = __ldg(pp), crop_y = __ldg(pp + 1), flip = __ldg(pp + 2);
+    const int cy1 = __ldg(pp + 3), cy2 = __ldg(pp + 4), cx1 = __ldg(pp + 5), cx2 = __ldg(pp + 6);
+    const uint8_t* fr = frames + ((long long)b * Tn + t) * Hs * Ws * 3;
+    float f[48];
+#pragma unroll
+    for (int ph = 0; ph < 2; ++ph) {
+      const int y = 2 * h2 + ph;
+      const bool ycut = y >= cy1 && y < cy2;
+      const uint8_t* row = fr + (long long)(crop_y + y) * Ws * 3;
+#pragma unroll
+      for (int jw = 0; jw < 4; ++jw) {
+        const int ws = w2 + jw - 2;
+#pragma unroll
+        for (int pw = 0; pw < 2; ++pw) {
+          const int x = 2 * ws + pw;
+          float v0 = 0.f, v1 = 0.f, v2 = 0.f;
+          if (ws >= 0 && ws < W2) {
+            if (ycut && x >= cx1 && x < cx2) {
+              v0 = v1 = v2 = fill;
+            } else {
+              const uint8_t* px = row + (crop_x + (flip ? W - 1 - x : x)) * 3;
+              v0 = fmaf((float)px[0], mul, add);
+              v1 = fmaf((float)px[1], mul, add);
+              v2 = fmaf((float)px[2], mul, add);
+            }
+          }
+          f[jw * 12 + (ph * 2 + pw) * 3 + 0] = v0;
+          f[jw * 12 + (ph * 2 + pw) * 3 + 1] = v1;
+          f[jw * 12 + (ph * 2 + pw) * 3 + 2] = v2;
+        }
+      }
+    }
+    uint4* o = reinterpret_cast<uint4*>(out + i * 64);
+#pragma unroll
+    for (int g = 0; g < 6; ++g)
+      o[g] = make_uint4(pack_bf16x2(f[8 * g], f[8 * g + 1]), pack_bf16x2(f[8 * g + 2], f[8 * g + 3]),
+                        pack_bf16x2(f[8 * g + 4], f[8 * g + 5]), pack_bf16x2(f[8 * g + 6], f[8 * g + 7]));
+    o[6] = make_uint4(0, 0, 0, 0);
+    o[7] = make_uint4(0, 0, 0, 0);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // BatchNorm finalize: (sum, sumsq) -> mean, invstd, scale = gamma*invstd, shift = beta - mean*scale; running stats
 // ------------------------------------------------------------------------------------------------------------
@@ -1074,6 +1138,16 @@ extern "C" int m3t_video_prep_s2d_w4(const void* video, int is_u8, void* out, in
   else
     video_prep_s2d_w4_kernel<float><<<ew_blocks(items), kEwThreads, 0, ST(stream)>>>(
         reinterpret_cast<const float*>(video), BF(out), B, T, H, W, mul, add);
+  count_launch();
+  return launch_status();
+}
+
+extern "C" int m3t_video_augment_prep_s2d_w4(const void* frames_u8, const int* params, void* out, int B, int T, int Hs,
+                                             int Ws, int H, int W, float mul, float add, void* stream) {
+  if ((H | W) & 1 || H > Hs || W > Ws || B <= 0 || T <= 0) return -1;
+  const long long items = (long long)B * T * (H / 2) * (W / 2);
+  video_augment_prep_s2d_w4_kernel<<<ew_blocks(items), kEwThreads, 0, ST(stream)>>>(
+      reinterpret_cast<const uint8_t*>(frames_u8), params, BF(out), B, T, Hs, Ws, H, W, mul, add);
   count_launch();
   return launch_status();
 }

@@ -66,6 +66,10 @@ class AffWild2VA(_Base):
         hp = self.hparams
         if hp.backbone == 'resnet':
             # normalisation (video - 127.5) / 127.5 (reference :106) is folded into the stem's input pass
+            if 'video_u8' in batch:
+                # decoded uint8 HWC frames + augmentation parameters instead of the float32 clip tensor: crop, mirror
+                # and cutout (models/dataset.py:46-80) happen inside the same pass (process/video_input.py)
+                return self.visual.forward_bf16(ops.RawClips(batch['video_u8'], batch['video_aug']), normalise=True)
             return self.visual.forward_bf16(batch['video'], normalise=True)
         return self.visual.forward_bf16(batch['video'], batch['se_features'], batch['se_features'], normalise=True)
 

@@ -326,6 +326,17 @@ def conv2d_dgrad(dy, w, x_shape, stride, pad, residual=None, accum_into=None):
     return dx.view(N, H, W, Cin)
 
 
+class RawClips:
+    """Decoded uint8 frames + per-clip augmentation parameters as the stem's input: frames uint8
+    [B,T,Hs,Ws,3] (HWC as decoded) and params int32 [B,8] = {crop_x, crop_y, flip, cut_y1, cut_y2, cut_x1, cut_x2, 0}
+    on the device; `shape` is the (B,3,T,H,W) of the clip tensor the reference's load_video would have produced."""
+
+    def __init__(self, frames_u8, params, H=112, W=112):
+        self.frames, self.params, self.H, self.W = frames_u8, params, H, W
+        self.shape = (frames_u8.shape[0], 3, frames_u8.shape[1], H, W)
+        self.device = frames_u8.device
+
+
 class Stem3D(torch.autograd.Function):
     """Conv3d(3,64,(5,7,7),s(1,2,2),p(2,3,3)) -> BN3d -> ReLU -> MaxPool3d((1,3,3),s(1,2,2),p(0,1,1))
     (models/backbone.py:327-332) on raw video.  The stride-2 7x7 spatial filter is evaluated as a stride-1 4x4 filter
@@ -334,7 +345,10 @@ class Stem3D(torch.autograd.Function):
     @staticmethod
     def forward(ctx, video, w, gamma, beta, running_mean, running_var, normalise, training):
         B, _, T, H, W = video.shape
-        xs = raw.video_prep_s2d_w4(video.contiguous(), normalise)
+        if isinstance(video, RawClips):   # crop / mirror / cutout / normalise fused into the layout pass
+            xs = raw.video_augment_prep_s2d_w4(video.frames, video.params, H, W, normalise)
+        else:
+            xs = raw.video_prep_s2d_w4(video.contiguous(), normalise)
         idx = stem_s2d_index(w.device)
         wp = _cached(w, "stem", lambda: raw.gather_pack(w.detach().view(64, -1), idx, 80 * 16))
         # (5,4,1) filter over the 64 = 4 taps x 16 channels of the W-unrolled space-to-depth image; the packed

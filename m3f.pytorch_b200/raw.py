@@ -309,6 +309,20 @@ def video_prep_s2d_w4(video, normalise):
     return out
 
 
+def video_augment_prep_s2d_w4(frames_u8, params, H, W, normalise):
+    """frames_u8: uint8 [B,T,Hs,Ws,3] decoded frames; params: int32 [B,8] (include/m3t_b200.h) -> bf16 (B,T,H/2,W/2,64)."""
+    assert frames_u8.is_cuda and frames_u8.is_contiguous() and frames_u8.dtype == torch.uint8 and frames_u8.shape[-1] == 3
+    assert params.is_cuda and params.dtype == torch.int32 and params.is_contiguous()
+    B, T, Hs, Ws, _ = frames_u8.shape
+    assert params.shape == (B, 8)
+    out = torch.empty((B, T, H // 2, W // 2, 64), device=frames_u8.device, dtype=torch.bfloat16)
+    mul, add = (1.0 / 127.5, -1.0) if normalise else (1.0, 0.0)
+    L.check(_lib().m3t_video_augment_prep_s2d_w4(L.ptr(frames_u8), L.ptr(params), L.ptr(out), L.i32(B), L.i32(T),
+                                                 L.i32(Hs), L.i32(Ws), L.i32(H), L.i32(W), L.f32(mul), L.f32(add),
+                                                 L.stream_ptr()), "video_augment_prep_s2d_w4")
+    return out
+
+
 def bn_finalize(stats, count, gamma, beta, eps, momentum, running_mean, running_var):
     C = gamma.numel()
     buf = torch.empty((4, C), device=gamma.device, dtype=torch.float32)  # mean, invstd, scale, shift

@@ -1014,6 +1014,35 @@ for _k in ("ccc_video", "ccc_all", "ccc_video_big", "ccc_all_big"):
     TOLS[_k] = 1e-6
 
 
+def case_video_input(seed=0):
+    """On-device input pipeline: m3t_video_augment_prep_s2d_w4 on decoded uint8 frames + parameter rows vs the layout
+    pass applied to the clips the reference's load_video produced (golden), bit for bit; and the visual stream fed
+    either way gives identical features."""
+    from m3t_b200 import ops, raw
+    from m3t_b200.models.backbone import VA_3DResNet
+    clips = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "video_input.pt"))
+    frames = torch.stack([c["frames"] for c in clips]).cuda()                       # [B,T,128,128,3]
+    params = torch.tensor([c["params"] for c in clips], dtype=torch.int32).cuda()
+    seq = torch.stack([c["seq"].float() for c in clips]).cuda()                     # [B,3,T,112,112]
+    errs = {}
+    for norm in (True, False):
+        a = raw.video_augment_prep_s2d_w4(frames, params, 112, 112, norm)
+        b = raw.video_prep_s2d_w4(seq, norm)
+        errs["prep_exact_norm%d" % norm] = float((a.view(torch.int16) != b.view(torch.int16)).sum())
+    torch.manual_seed(seed)
+    m = VA_3DResNet(frameLen=2, nClasses=9, nFCs=2, resnet_ver="v1").cuda().eval()
+    with torch.no_grad():
+        f0 = m.features_cl(seq, True)
+        f1 = m.features_cl(ops.RawClips(frames, params), True)
+    errs["features_exact"] = float((f0.view(torch.int16) != f1.view(torch.int16)).sum())
+    return errs
+
+
+CASES["video_input_pipeline"] = (case_video_input, _c())
+for _k in ("prep_exact_norm1", "prep_exact_norm0", "features_exact"):
+    TOLS[_k] = 0.5
+
+
 if __name__ == "__main__":
     name = sys.argv[1]
     errs = run_case(name)

@@ -156,3 +156,15 @@ def test_postproc_oracle_vs_reference_golden():
     per_video, overall = O.smoothed_ccc(tracks, gtr, 35)
     assert np.abs(per_video - fx["ccc_per_video"].numpy()).max() < 1e-12
     assert np.abs(overall - fx["ccc_overall"].numpy()).max() < 1e-12
+
+
+def test_video_input_oracle_vs_reference_golden():
+    """oracle/video_input.assemble_clip + process/video_input.draw_params against the reference's load_video run on
+    JPEG files under the same seeds (tests/golden/video_input.pt, oracle/make_golden_video_input.py): bit-exact."""
+    import numpy as np
+    from oracle import video_input as VI
+    clips = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "video_input.pt"))
+    assert len(clips) == 3
+    for c in clips:
+        seq = VI.assemble_clip(c["frames"].numpy(), *c["params"][:7])
+        assert seq.dtype == np.float32 and np.array_equal(seq, c["seq"].float().numpy())
