@@ -247,40 +247,63 @@ def run_b200(args, rank, local_rank, world):
                    "gpu_launches": int(launches)})
         return
     copy_stream = torch.cuda.Stream()
-    bufs = [{k: torch.empty_like(v, device=dev) for k, v in host.items()} for _ in range(2)]
-    ready = [torch.cuda.Event(), torch.cuda.Event()]
-    done = [torch.cuda.Event(), torch.cuda.Event()]
     loss_host = torch.zeros(args.warmup + args.steps, dtype=torch.float32).pin_memory()
-    h2d = sum(v.numel() * v.element_size() for v in host.values())
 
-    def issue_copy(i):
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(done[i % 2])
-            for k, v in host.items():
-                bufs[i % 2][k].copy_(v, non_blocking=True)
-            ready[i % 2].record(copy_stream)
+    def run_e2e(host):
+        """The step through the public API with HOST buffers: H2D copy of every step's batch (pinned memory, side
+        stream, prefetch depth 1) and D2H read of the loss inside the timed region."""
+        bufs = [{k: torch.empty_like(v, device=dev) for k, v in host.items()} for _ in range(2)]
+        ready = [torch.cuda.Event(), torch.cuda.Event()]
+        done = [torch.cuda.Event(), torch.cuda.Event()]
 
-    for d in done:
-        d.record()
-    issue_copy(0)
-    main = torch.cuda.current_stream()
-    for i in range(args.warmup + args.steps):
-        if i == args.warmup:
-            barrier()
-            e0.record()
-        issue_copy(i + 1)
-        main.wait_event(ready[i % 2])
-        loss = engine.step(bufs[i % 2])
-        done[i % 2].record(main)
-        loss_host[i:i + 1].copy_(loss.reshape(1), non_blocking=True)
-    e1.record()
-    barrier()
-    ms_e2e = e0.elapsed_time(e1)
-    t = torch.tensor([ms_e2e], device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_e2e = float(t.item())
+        def issue_copy(i):
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(done[i % 2])
+                for k, v in host.items():
+                    bufs[i % 2][k].copy_(v, non_blocking=True)
+                ready[i % 2].record(copy_stream)
+
+        for d in done:
+            d.record()
+        issue_copy(0)
+        main = torch.cuda.current_stream()
+        for i in range(args.warmup + args.steps):
+            if i == args.warmup:
+                barrier()
+                e0.record()
+            issue_copy(i + 1)
+            main.wait_event(ready[i % 2])
+            loss = engine.step(bufs[i % 2])
+            done[i % 2].record(main)
+            loss_host[i:i + 1].copy_(loss.reshape(1), non_blocking=True)
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), sum(v.numel() * v.element_size() for v in host.values())
+
+    ms_e2e, h2d = run_e2e(host)
     e2e_value = frames_per_step * args.steps / (ms_e2e * 1e-3)
+    # same step fed with DECODED uint8 frames (128x128 HWC) + augmentation rows: crop / mirror / cutout / normalise
+    # happen inside the stem's layout pass on the device (SURVEY 8(f) N2), 3.1x fewer host->device bytes
+    e2e_u8 = None
+    if not args.no_u8:
+        from m3t_b200.process.video_input import draw_params
+        import random as _random
+        import numpy as _np
+        _random.seed(1234 + rank)
+        _np.random.seed(1234 + rank)
+        g8 = torch.Generator().manual_seed(4321 + rank)
+        host_u8 = {k: v for k, v in host.items() if k != "video"}
+        host_u8["video_u8"] = torch.randint(0, 256, (args.clips, T_FRAMES, 128, 128, 3), generator=g8,
+                                            dtype=torch.uint8).pin_memory()
+        host_u8["video_aug"] = torch.tensor([draw_params(True, bool(i & 1), True, True, 128, 112)
+                                             for i in range(args.clips)], dtype=torch.int32).pin_memory()
+        ms_u8, h2d_u8 = run_e2e(host_u8)
+        e2e_u8 = {"value": frames_per_step * args.steps / (ms_u8 * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d_u8,
+                  "d2h_bytes_per_step": 4, "ms_per_step": ms_u8 / args.steps,
+                  "input": "uint8 128x128x3 decoded frames + crop/mirror/cutout rows (models/dataset.py:46-80 on device)"}
 
     if rank == 0:
         peaks = {}
@@ -314,6 +337,7 @@ def run_b200(args, rank, local_rank, world):
             "clips_per_sec": value / T_FRAMES, "loss": final_loss, "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / args.steps},
+            "e2e_u8_frames": e2e_u8,
             "gpu_launches": int(launches), "roofline": roof,
             "kernels": [{"key": k, "calls": v["calls"], "ms_total": round(v["ms_total"], 3),
                          "tflops": round(v["tflops"], 1)} for k, v in top],
@@ -338,6 +362,7 @@ def main():
     ap.add_argument("--clips", type=int, default=256, help="clips per GPU (x16 frames)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs)")
+    ap.add_argument("--no-u8", action="store_true", help="skip the uint8-frames end-to-end leg")
     ap.add_argument("--top", type=int, default=8, help="how many tensor-core kernels to list under \"kernels\"")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
