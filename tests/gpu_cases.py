@@ -559,7 +559,8 @@ for _k in ("conv1.weight", "conv2.weight", "bn1.weight", "bn1.bias", "bn2.weight
 # backward chain is asserted tightly by the well-conditioned block_* / convnd_* / golden_{gru,attfusion,tcn} cases;
 # here the whole-network gradient only has to stay within that floor (all-parameter L2 < 0.3) and forward / loss
 # parity is asserted at the normal tolerances.
-CHAOTIC_GRADS = {"golden_resnet_trunk_train", "golden_va3dresnet_train", "golden_av_resnet_attention_train"}
+CHAOTIC_GRADS = {"golden_resnet_trunk_train", "golden_va3dresnet_train", "golden_av_resnet_attention_train",
+                 "va3dresnet_96px_train", "va3dresnet_15frames_train"}
 
 
 def failures(name, errs):
@@ -1012,6 +1013,48 @@ for _k in ("wiener", "wiener_big"):
     TOLS[_k] = 1e-10
 for _k in ("ccc_video", "ccc_all", "ccc_video_big", "ccc_all_big"):
     TOLS[_k] = 1e-6
+
+
+def case_va3dresnet_shapes(B, T, HW, train, seed=0):
+    """VA_3DResNet on shapes off the tuned path - frame counts that are not tile multiples, a 96x96 input (generic
+    im2col stem and stem weight gradient instead of the 56-wide halo kernels; 24/12/6/3-pixel trunk maps) - vs the
+    bf16-emulating oracle, forward and (train) all-parameter gradient L2."""
+    from m3t_b200.models.backbone import VA_3DResNet
+    from oracle import ref_torch as R
+    torch.manual_seed(seed)
+    m = VA_3DResNet(frameLen=T, nClasses=9, nFCs=2, resnet_ver="v1")
+    spec = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    sd = R.synth_state_dict(spec, 77 + seed)
+    m.load_state_dict(sd)
+    m = m.cuda().train(train)
+    g = torch.Generator().manual_seed(seed + 5)
+    x = torch.rand((B, 3, T, HW, HW), generator=g) * 2 - 1
+    cot = torch.randn((B, T, 9), generator=g)
+    with torch.set_grad_enabled(train):
+        out = m(x.cuda())
+        if train:
+            (out * cot.cuda()).sum().backward()
+    sdr = {k: v.clone().requires_grad_(train and v.is_floating_point() and not k.endswith(("running_mean", "running_var")))
+           for k, v in sd.items()}
+    with R.bf16_emulation(), torch.set_grad_enabled(train):
+        ref = R.va_3dresnet(x, sdr, T, train=train)
+        if train:
+            (ref * cot).sum().backward()
+    errs = {"out_emu": _err(out, ref)}
+    if train:
+        num = den = 0.0
+        for k, p in m.named_parameters():
+            if p.grad is None or sdr[k].grad is None:
+                continue
+            num += float((p.grad.float().cpu() - sdr[k].grad).pow(2).sum())
+            den += float(sdr[k].grad.pow(2).sum())
+        errs["grad_all_l2"] = (num / max(den, 1e-30)) ** 0.5
+    return errs
+
+
+CASES["va3dresnet_96px_eval"] = (case_va3dresnet_shapes, _c(B=2, T=3, HW=96, train=False))
+CASES["va3dresnet_96px_train"] = (case_va3dresnet_shapes, _c(B=2, T=3, HW=96, train=True))
+CASES["va3dresnet_15frames_train"] = (case_va3dresnet_shapes, _c(B=3, T=5, HW=112, train=True))
 
 
 def case_video_input(seed=0):
