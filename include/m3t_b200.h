@@ -48,7 +48,8 @@ int m3t_gemm_bf16(const void* A, long long lda, int a_mn, const void* B, long lo
  *   w_packed bf16 [Cout][kd*kh*kw*Cin]                 (tap-major, channel-minor)
  *   y        bf16 channels-last [N][Z][P][Q][Cout]
  *   y = act( conv(x,w) * scale[c] + shift[c] + residual ), all optional; stats as in m3t_gemm_bf16.
- *   tile_hint: 0 = auto; bit0 force 128-row tiles, bit1 force 256-row tiles, bit3 force 128-column tiles.
+ *   tile_hint: 0 = auto; bit0 force 128-row tiles, bit1 force 256-row tiles, bit3 force 128-column tiles,
+ *     bit4 / bit5 force / forbid the persistent tile walker, bit6: y is float32 (no residual; fp32-parity mode).
  * Replaces: nn.Conv2d 3x3 / 1x1 in BasicBlock (models/resnet.py:7-15,24-27,40-54,98-101), nn.Conv3d 3x3x3 in
  * VA_3DVGGM(_Split) (models/backbone.py:73-103,179-195,243-271), weight-normed dilated causal nn.Conv1d in
  * TemporalBlock (models/tcn.py:19-33) and Conv1d k5 in tcn_simple (models/backbone.py:214-231), with the
@@ -282,6 +283,36 @@ int m3t_wiener1d_f64(const float* x, const long long* seq_off, int V, int C, int
  * models/utils.py:19-21 concordance_cc2_np + the mask / concatenation of get_smoothed_ccc.py:17-30. */
 int m3t_ccc_moments_f64(const double* pred, const float* gt, const long long* seq_off, int V, int C, double* moments,
                         void* stream);
+
+/* ---- fp32-parity inference mode (csrc/fp32mode.cu) ----------------------------------------------------------------
+ * North-star tolerance "fp32 max error <= 1e-4 on the per-frame V/A predictions".  Activations stay float32; the
+ * tensor-core launches are the SAME bf16 kernels (m3t_gemm_bf16 / m3t_conv_fprop_bf16 with fp32 output) over 3x the
+ * contraction: x = hi + lo with hi = bf16(x), lo = bf16(x - hi), and a.b ~= a_hi.b_hi + a_hi.b_lo + a_lo.b_hi is
+ * obtained by concatenating A' = [a_hi | a_hi | a_lo], B' = [b_hi | b_lo | b_hi] along K (per channel block); bf16
+ * products are exact in fp32 and accumulate in the fp32 TMEM accumulator.  Forward / eval only. */
+
+/* y = x (+ res) (ReLU);  out_f32 = y (optional, may alias x);  out3 bf16 [rows][3C] = [hi | hi | lo] of y.
+ * Replaces, in this mode, the residual add + ReLU of BasicBlock.forward (models/resnet.py:52-54) and feeds the next
+ * convolution / Linear. */
+int m3t_split3_bf16(const float* x, const float* res, int relu, float* out_f32, void* out3, long long rows, int C,
+                    void* stream);
+/* Weights: f32 [N][G][C] (tap_minor 0) or [N][C][G] (tap_minor 1, nn.Conv layout, G = taps) -> bf16 [N][G][3C] =
+ * [hi | lo | hi] per group (nn.Linear: G = 1). */
+int m3t_pack_split3_bf16(const float* w, void* out, long long N, int G, int C, int tap_minor, void* stream);
+/* m3t_video_prep_s2d_w4 with split output: bf16 (B,T,H/2,W/2,192) = [hi 64 | hi 64 | lo 64] per pixel. */
+int m3t_video_prep_s2d_w4_split3(const void* video, int is_u8, void* out, int B, int T, int H, int W, float mul,
+                                 float add, void* stream);
+/* nn.MaxPool3d((1,3,3),(1,2,2),(0,1,1)) (models/backbone.py:331) / AdaptiveAvgPool2d(1) (models/resnet.py:117) on
+ * float32 channels-last tensors. */
+int m3t_maxpool3s2_f32(const float* x, float* out, int F, int H, int W, int C, void* stream);
+int m3t_avgpool_f32(const float* x, float* out, int F, int HW, int C, void* stream);
+/* models/att_fusion.py:21-25 in float32: f = softmax(sigmoid(s_v), sigmoid(s_a)) . (x_v, x_a). */
+int m3t_att_mix_f32(const float* x_a, const float* x_v, const float* s_a, const float* s_v, float* f, long long rows,
+                    int C, void* stream);
+/* Bidirectional GRU layer recurrence in float32 FFMA (one launch per time step; gi f32 [B*T][2][3H] from the split
+ * GEMM, w_hh f32 [2][3H][H], b_hh f32 [2][3H], out f32 [B][T][2H]).  Replaces nn.GRU (models/rnn.py:17,72-75). */
+int m3t_gru_fwd_f32(const float* gi, const float* w_hh, const float* b_hh, float* out, int B, int T, int H,
+                    void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,7 +1,7 @@
 """Attention fusion of the audio and visual streams (reference: models/att_fusion.py:8-27)."""
 import torch.nn as nn
 
-from .. import ops
+from .. import fp32, ops
 from .rnn import GRU
 
 
@@ -15,6 +15,9 @@ class AttFusion(nn.Module):
         self.scorer_v = GRU(input_dim[0], hidden_dim, 1, 1, 1)
 
     def forward_bf16(self, x_a, x_v):
+        if fp32.enabled():
+            fp32.require_eval(self)
+            return fp32.att_fusion(self, ops.as_f32(x_a), ops.as_f32(x_v))
         x_a, x_v = ops.as_bf16(x_a), ops.as_bf16(x_v)
         if self.use_proj:
             x_v = ops.linear(x_v, self.proj_v.weight, self.proj_v.bias)

@@ -9,7 +9,7 @@ import math
 import torch
 import torch.nn as nn
 
-from .. import ops
+from .. import fp32, ops
 from .resnet import BasicBlock, ResNet
 from .rnn import GRU
 
@@ -65,6 +65,9 @@ class VA_3DResNet(nn.Module):
         return f.view(B, T, -1)
 
     def forward_bf16(self, x, normalise=False):
+        if fp32.enabled():       # fp32-parity inference mode: float32 activations, split-operand tensor-core launches
+            fp32.require_eval(self)
+            return fp32.va_3dresnet(self, x, normalise)
         f = self.features_cl(x, normalise)
         if f.shape[1] != self.frameLen:
             raise RuntimeError("VA_3DResNet: T (%d) must equal frameLen (%d)" % (f.shape[1], self.frameLen))

@@ -9,7 +9,7 @@ import torch
 import torch.nn as nn
 from torch.nn import functional as F
 
-from .. import ops
+from .. import fp32, ops
 from .att_fusion import AttFusion
 from .backbone import VA_3DResNet
 from .rnn import GRU
@@ -81,7 +81,10 @@ class AffWild2VA(_Base):
             return ops.as_f32(self._visual(batch))
         a = self.audio.forward_bf16(batch['audio'])
         v = self._visual(batch)
-        v = ops.linear(v, self.proj_v.weight, self.proj_v.bias)
+        if fp32.enabled():
+            v = fp32.linear(v, self.proj_v.weight, self.proj_v.bias)
+        else:
+            v = ops.linear(v, self.proj_v.weight, self.proj_v.bias)
         if hp.fusion_type == 'concat':
             f = torch.cat((a, v), dim=-1)
         else:

@@ -7,7 +7,7 @@ arithmetic runs as fused conv+BN(+residual)+ReLU units on channels-last bf16 act
 import torch
 import torch.nn as nn
 
-from .. import ops
+from .. import fp32, ops
 
 
 def _conv_bn_act(x, conv, bn, residual, relu):
@@ -101,6 +101,9 @@ class ResNet(nn.Module):
         return x
 
     def forward(self, x):
+        if fp32.enabled():
+            fp32.require_eval(self)
+            return fp32.resnet_trunk(self, x.permute(0, 2, 3, 1).contiguous().float())
         out = self.forward_cl(ops.ToCL.apply(x))
         if out.dim() == 2:
             return ops.as_f32(out)

@@ -9,7 +9,7 @@ import math
 import torch
 import torch.nn as nn
 
-from .. import ops
+from .. import fp32, ops
 
 
 class GRU(nn.Module):
@@ -64,6 +64,9 @@ class GRU(nn.Module):
 
     def forward_bf16(self, x):
         """x: [B,T,I] (fp32 or bf16) -> head output (fp32) or raw BiGRU features (bf16) when num_classes <= 0."""
+        if fp32.enabled():
+            fp32.require_eval(self)
+            return fp32.gru_module(self, ops.as_f32(x))
         h = ops.as_bf16(x)
         g = self.gru
         for l in range(self.num_layers):

@@ -1057,6 +1057,38 @@ CASES["va3dresnet_96px_train"] = (case_va3dresnet_shapes, _c(B=2, T=3, HW=96, tr
 CASES["va3dresnet_15frames_train"] = (case_va3dresnet_shapes, _c(B=3, T=5, HW=112, train=True))
 
 
+def case_golden_fp32(name):
+    """fp32-parity inference mode (m3t_b200.fp32.parity_mode: float32 activations, split-operand bf16 tensor-core
+    launches) on a golden fixture, against the fp32 output of the UNMODIFIED reference module.  North-star bar:
+    1e-4 range-normalised on the outputs / the V-A predictions."""
+    from m3t_b200 import fp32
+    from tests.golden_util import load, ref_batch
+    fx = load(name)
+    m = _build(fx).eval()
+    kind, inp = fx["kind"], fx["inputs"]
+    with torch.no_grad(), fp32.parity_mode():
+        if kind in ("GRU", "ResNet"):
+            out = m(inp["x"].cuda())
+        elif kind == "AttFusion":
+            out = m(inp["x_a"].cuda(), inp["x_v"].cuda())
+        elif kind == "VA_3DResNet":
+            out = m((inp["video_u8"].float().cuda() - 127.5) / 127.5)
+        else:
+            out = m(ref_batch(inp, "cuda"))
+    errs = {"out_ref32": _err(out, fx["out"])}
+    if kind == "AffWild2VA":
+        sl = slice(7, None) if "mtl" in fx["hparams"]["loss"] else slice(-2, None)
+        errs["va_ref32"] = _err(out[..., sl], fx["out"][..., sl])
+    return errs
+
+
+for _n in ("gru_audio", "gru_scorer", "gru_nohead", "attfusion", "resnet_trunk_eval", "va3dresnet_eval",
+           "av_resnet_attention_eval"):
+    CASES["fp32_" + _n] = (case_golden_fp32, _c(name=_n))
+TOLS["out_ref32"] = 1e-4
+TOLS["va_ref32"] = 1e-4
+
+
 def case_video_input(seed=0):
     """On-device input pipeline: m3t_video_augment_prep_s2d_w4 on decoded uint8 frames + parameter rows vs the layout
     pass applied to the clips the reference's load_video produced (golden), bit for bit; and the visual stream fed
