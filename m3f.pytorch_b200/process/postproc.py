@@ -4,6 +4,7 @@ Mirrors the reference's host-side steps after the model (models/model.py:281-297
 get_smoothed_ccc.py) with the same function names where the reference has one, on ragged per-video tracks kept in
 ONE flat device tensor.  All arithmetic runs in csrc/postproc.cu through the C ABI; there is no host fallback.
 """
+import numpy as np
 import torch
 
 from .. import lib as L
@@ -29,17 +30,21 @@ def overlap_add(preds, starts, vid_of_seg, seg_lens, window, n_videos):
     (models/model.py:281-297: nframes = start of the last window + its length; frames >= window//2 are halved.)"""
     assert preds.is_cuda and preds.dtype == torch.float32 and preds.dim() == 3
     S, Lw, C = preds.shape
-    lengths = [0] * n_videos
-    for st, v, n in zip(starts, vid_of_seg, seg_lens):
-        lengths[v] = max(lengths[v], int(st) + int(n))
-    off = [0]
-    for n in lengths:
-        off.append(off[-1] + n)
+    # per-segment bookkeeping is vectorised numpy on the host (tens of thousands of windows per validation set)
+    starts = np.asarray(starts, dtype=np.int64)
+    vids = np.asarray(vid_of_seg, dtype=np.int64)
+    lens = np.asarray(seg_lens, dtype=np.int64)
+    lengths = np.zeros(n_videos, dtype=np.int64)
+    np.maximum.at(lengths, vids, starts + lens)
+    off = np.concatenate([[0], np.cumsum(lengths)])
     dev = preds.device
-    seq_off = torch.tensor(off, dtype=torch.int64, device=dev)
-    seg_base = torch.tensor([off[v] for v in vid_of_seg], dtype=torch.int64, device=dev)
-    seg_start = torch.tensor([int(s) for s in starts], dtype=torch.int32, device=dev)
-    seg_len = torch.tensor([int(n) for n in seg_lens], dtype=torch.int32, device=dev)
+    host = torch.from_numpy(np.concatenate([off, off[vids]]))                      # one H2D copy for both int64 arrays
+    dev64 = host.to(dev)
+    seq_off, seg_base = dev64[:n_videos + 1], dev64[n_videos + 1:]
+    dev32 = torch.from_numpy(np.concatenate([starts, lens]).astype(np.int32)).to(dev)
+    seg_start, seg_len = dev32[:S], dev32[S:]
+    lengths = [int(x) for x in lengths]
+    off = [int(x) for x in off]
     out = torch.empty((off[-1], C), dtype=torch.float32, device=dev)
     L.check(_lib().m3t_overlap_add_f32(L.ptr(preds.contiguous()), L.ptr(seg_start), L.ptr(seg_len), L.ptr(seg_base),
                                        L.ptr(seq_off), L.ptr(out), L.i64(S), L.i32(Lw), L.i32(C), L.i32(n_videos),

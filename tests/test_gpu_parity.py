@@ -54,3 +54,28 @@ def test_ccc_three_decimals():
         c_gpu = float(concordance_cc2(out[..., ch].reshape(-1), y, "none"))
         assert abs(c_emu - c_gpu) < 1e-3, (ch, c_ref, c_emu, c_gpu)
         assert abs(c_ref - c_gpu) < 5e-3, (ch, c_ref, c_emu, c_gpu)
+
+
+def test_ccc_three_decimals_fp32_mode():
+    """North-star criterion in the fp32-parity mode: CCC of the V/A predictions vs the synthetic labels equals the
+    reference's to 3 decimals (here: within 5e-4), AV-ResNet attention fixture."""
+    from tests.golden_util import load, ref_batch
+    from m3t_b200 import fp32
+    from m3t_b200.models.utils import concordance_cc2
+    fx = load("av_resnet_attention_eval")
+    m = G._build(fx).eval()
+    with torch.no_grad(), fp32.parity_mode():
+        out = m(ref_batch(fx["inputs"], "cuda")).float().cpu()
+    for ch, lab in ((7, "label_valence"), (8, "label_arousal")):
+        y = fx["inputs"][lab].reshape(-1)
+        c_ref = float(concordance_cc2(fx["out"][..., ch].reshape(-1), y, "none"))
+        c_gpu = float(concordance_cc2(out[..., ch].reshape(-1), y, "none"))
+        assert abs(c_ref - c_gpu) < 5e-4, (ch, c_ref, c_gpu)
+
+
+def test_fp32_mode_refuses_training():
+    from m3t_b200 import fp32
+    from m3t_b200.models.rnn import GRU
+    m = GRU(64, 32, 1, 2, 1).cuda().train()
+    with fp32.parity_mode(), pytest.raises(NotImplementedError):
+        m(torch.randn(2, 4, 64, device="cuda"))
