@@ -57,6 +57,13 @@ def main():
     from m3t_b200 import ops
     wfull = torch.randn(128, 64, 3, 3, device=dev) * 0.05
     ops.conv2d_dgrad(y2.view(F, 14, 14, 128), wfull, (F, 28, 28, 64), 2, 1)
+    # layer3 / layer4 3x3 on the persistent tile walker, and their weight gradients (256-row tiles)
+    for HW, C in ((7, 256), (4, 512)):
+        x = rb(F, HW, HW, C)
+        w = (torch.randn(C, 9 * C, device=dev) * 0.02).bfloat16()
+        g = raw.conv_geom(2, F, 1, HW, HW, C, C, (1, 3, 3), (1, 1, 1), (0, 1, 1), (0, 1, 1), (1, 1, 1))
+        y = raw.conv_fprop(x, w, g, stats=torch.zeros(2, C, device=dev))
+        raw.conv_wgrad(x, y.view(F, HW, HW, C), g)
     # GRU layer H=512 forward/backward, x-projection GEMM
     xg = rb(B * T, 512)
     wih = (torch.randn(3072, 512, device=dev) * 0.03).bfloat16()
