@@ -155,6 +155,9 @@ class TrainEngine:
                                        L.i64(self.n), L.f32(self.lr), L.f32(self.betas[0]), L.f32(self.betas[1]),
                                        L.f32(self.eps), L.f32(self.wd), L.i32(self.steps), L.f32(self.clip),
                                        L.f32(1.0 / self.world), L.ptr(self.gnorm_sq), st), "adam_clip_step")
+        # the kernel rewrote every parameter through the arena pointer: PyTorch's per-tensor version counters did not
+        # move, so the packed / bf16 copies derived from the old values must be dropped explicitly
+        ops.clear_caches()
 
     def step(self, batch):
         """One optimisation step on this rank's shard; returns the (detached) loss tensor, no host sync."""

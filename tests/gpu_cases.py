@@ -1089,6 +1089,52 @@ TOLS["out_ref32"] = 1e-4
 TOLS["va_ref32"] = 1e-4
 
 
+def case_train_trajectory(steps=4, clips=4, lr=2e-4, seed=0):
+    """Several optimisation steps end to end (TrainEngine: forward, ccc_mtl loss, backward, clip 1.0, Adam with weight
+    decay 1e-4 through the flat arenas) vs the same loop on the oracle with bf16 storage emulation and
+    torch.optim.Adam: the loss trajectory must agree step by step."""
+    import bench as BN
+    from m3t_b200.engine import TrainEngine
+    from m3t_b200.models.model import AffWild2VA
+    from oracle import ref_torch as R
+    hp = BN.hparams()
+    torch.manual_seed(12345 + seed)
+    m = AffWild2VA(hp)
+    BN.randomise_bn(m, 7)
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    batch = BN.synth_batch(clips, 99 + seed, pin=False)
+    # oracle loop
+    params = []
+    for k, v in sd.items():
+        if v.is_floating_point() and not k.endswith(("running_mean", "running_var")):
+            v.requires_grad_(True)
+            params.append(v)
+    opt = torch.optim.Adam(params, lr=lr, weight_decay=1e-4)
+    ref_losses = []
+    for _ in range(steps):
+        with R.bf16_emulation():
+            y = R.affwild2va_forward(batch, sd, hp, train=True)
+            loss = R.training_loss(y, batch, hp.loss, hp.loss_lambda)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(params, 1.0)
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+        ref_losses.append(float(loss))
+    # device loop
+    m = m.cuda().train()
+    eng = TrainEngine(m, lr=lr, weight_decay=1e-4, clip=1.0)
+    dbatch = {k: v.cuda() for k, v in batch.items()}
+    losses = [float(eng.step(dbatch)) for _ in range(steps)]
+    errs = {"loss_step%d" % i: abs(a - b) / max(abs(b), 1e-6) for i, (a, b) in enumerate(zip(losses, ref_losses))}
+    errs["info"] = {"gpu": [round(x, 5) for x in losses], "oracle": [round(x, 5) for x in ref_losses]}
+    return errs
+
+
+CASES["train_trajectory_4steps"] = (case_train_trajectory, _c())
+for _i in range(4):
+    TOLS["loss_step%d" % _i] = 1e-2
+
+
 def case_video_input(seed=0):
     """On-device input pipeline: m3t_video_augment_prep_s2d_w4 on decoded uint8 frames + parameter rows vs the layout
     pass applied to the clips the reference's load_video produced (golden), bit for bit; and the visual stream fed
