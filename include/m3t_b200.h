@@ -207,6 +207,11 @@ int m3t_relu_bwd_bf16(const void* dy, const void* out, void* dz, long long n, vo
  * Replaces nn.GRU(batch_first=True, bidirectional=True) (models/rnn.py:17,72-75) = cuDNN RNN in the reference. */
 int m3t_gru_fwd(const float* gi, const void* w_hh_bf16, const float* b_hh, void* out_bf16, float* out_f32,
                 float* saved, unsigned* counters, int B, int T, int H, void* stream);
+/* The bf16 weight copies of one bidirectional layer in one launch (rebuilt after every optimizer step):
+ * wih bf16 [6H][Ipad] = [W_ih ; W_ih_reverse] zero-padded to Ipad columns, whh bf16 [2][3H][H], whht bf16 [2][H][3H]
+ * (W_hh transposed, for m3t_gru_bwd; may be NULL).  Inputs are the nn.GRU parameters (models/rnn.py:17). */
+int m3t_gru_pack_weights(const float* w_ih, const float* w_ih_r, const float* w_hh, const float* w_hh_r, void* wih,
+                         void* whh, void* whht, int I, int Ipad, int H, void* stream);
 /* BPTT: dgi, dgh bf16 [B*T][2][3H] (gradients wrt the input / hidden pre-activations) and hprev bf16 [B*T][2][H]
  * (h_{t-1}, zero at the sequence start); w_hh_t_bf16 = bf16 [2][H][3H] (W_hh transposed).  The weight / bias /
  * input gradients follow as GEMMs and column sums over these. */

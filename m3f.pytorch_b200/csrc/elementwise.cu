@@ -1107,6 +1107,37 @@ __global__ void patch3x3_c1_kernel(const float* __restrict__ x, __nv_bfloat16* _
   }
 }
 
+// All bf16 copies one bidirectional GRU layer needs, in ONE launch (they are rebuilt after every optimizer step):
+//   wih  [6H][Ipad]   = [W_ih ; W_ih_reverse] (columns >= I zero)      input projection, both directions
+//   whh  [2][3H][H]   = W_hh per direction                               forward recurrence
+//   whht [2][H][3H]   = W_hh^T per direction                             BPTT recurrence
+__global__ void gru_pack_weights_kernel(const float* __restrict__ w_ih, const float* __restrict__ w_ih_r,
+                                        const float* __restrict__ w_hh, const float* __restrict__ w_hh_r,
+                                        __nv_bfloat16* __restrict__ wih, __nv_bfloat16* __restrict__ whh,
+                                        __nv_bfloat16* __restrict__ whht, int I, int Ipad, int H) {
+  const long long n_ih = 6LL * H * Ipad, n_hh = 6LL * H * H;
+  const long long total = n_ih + n_hh;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    if (i < n_ih) {
+      const int c = (int)(i % Ipad);
+      const long long r = i / Ipad;
+      float v = 0.f;
+      if (c < I) v = r < 3 * H ? w_ih[r * I + c] : w_ih_r[(r - 3 * H) * I + c];
+      wih[i] = __float2bfloat16(v);
+    } else {
+      const long long j = i - n_ih;                 // index into [2][3H][H]
+      const int k = (int)(j % H);
+      const long long r = j / H;
+      const int d = (int)(r / (3 * H));
+      const int g = (int)(r - (long long)d * 3 * H);
+      const __nv_bfloat16 v = __float2bfloat16(d == 0 ? w_hh[(long long)g * H + k] : w_hh_r[(long long)g * H + k]);
+      whh[j] = v;
+      if (whht) whht[((long long)d * H + k) * 3 * H + g] = v;
+    }
+  }
+}
+
 }  // namespace m3t
 
 using namespace m3t;
@@ -1366,6 +1397,16 @@ extern "C" int m3t_cast_f32_bf16(const float* in, long long ld_in, void* out, lo
 extern "C" int m3t_cast_bf16_f32(const void* in, long long ld_in, float* out, long long ld_out, long long rows,
                                  int cols, void* stream) {
   cast_bf16_f32_kernel<<<ew_blocks(rows * cols), kEwThreads, 0, ST(stream)>>>(CBF(in), ld_in, out, ld_out, rows, cols);
+  count_launch();
+  return launch_status();
+}
+
+extern "C" int m3t_gru_pack_weights(const float* w_ih, const float* w_ih_r, const float* w_hh, const float* w_hh_r,
+                                    void* wih, void* whh, void* whht, int I, int Ipad, int H, void* stream) {
+  if (I <= 0 || H <= 0 || Ipad < I) return -1;
+  const long long total = 6LL * H * Ipad + 6LL * H * H;
+  gru_pack_weights_kernel<<<ew_blocks(total), kEwThreads, 0, ST(stream)>>>(w_ih, w_ih_r, w_hh, w_hh_r, BF(wih), BF(whh),
+                                                                          BF(whht), I, Ipad, H);
   count_launch();
   return launch_status();
 }

@@ -483,6 +483,20 @@ def linear(x, w, b, relu=False, out_f32=False):
     return LinearFn.apply(as_bf16(x), w, b, relu, out_f32)
 
 
+def _gru_packed(w_ih, w_ih_r, w_hh, w_hh_r, I, H):
+    """(wih [6H, Ipad], whh [2,3H,H], whht [2,H,3H]) bf16 copies of one bidirectional layer, one launch, cached until
+    the parameters change."""
+    def make():
+        Ipad = (I + 7) // 8 * 8
+        dev = w_ih.device
+        wih = torch.empty((6 * H, Ipad), device=dev, dtype=torch.bfloat16)
+        whh = torch.empty((2, 3 * H, H), device=dev, dtype=torch.bfloat16)
+        whht = torch.empty((2, H, 3 * H), device=dev, dtype=torch.bfloat16)
+        raw.gru_pack_weights(w_ih.detach(), w_ih_r.detach(), w_hh.detach(), w_hh_r.detach(), wih, whh, whht, I, Ipad, H)
+        return wih, whh, whht
+    return _cached_multi((w_ih, w_ih_r, w_hh, w_hh_r), "gru_w", make)
+
+
 class GRULayerFn(torch.autograd.Function):
     """One bidirectional nn.GRU layer (models/rnn.py:17,75): x bf16 [B,T,I] -> bf16 [B,T,2H].
     Parameters in nn.GRU layout: w_ih/w_hh/b_ih/b_hh for the forward and the reverse direction."""
@@ -493,20 +507,7 @@ class GRULayerFn(torch.autograd.Function):
         H = w_hh.shape[1]
         x2 = x.contiguous().view(B * T, I)
 
-        def make_ih():
-            buf = torch.empty((6 * H, (I + 7) // 8 * 8), device=x.device, dtype=torch.bfloat16)
-            raw.cast_bf16(w_ih.detach(), out=buf[:3 * H])
-            raw.cast_bf16(w_ih_r.detach(), out=buf[3 * H:])
-            return buf
-
-        def make_hh():
-            buf = torch.empty((2, 3 * H, H), device=x.device, dtype=torch.bfloat16)
-            raw.cast_bf16(w_hh.detach(), out=buf[0])
-            raw.cast_bf16(w_hh_r.detach(), out=buf[1])
-            return buf
-
-        wih = _cached_multi((w_ih, w_ih_r), "gru_ih", make_ih)
-        whh = _cached_multi((w_hh, w_hh_r), "gru_hh", make_hh)
+        wih, whh, _ = _gru_packed(w_ih, w_ih_r, w_hh, w_hh_r, I, H)
         bih = torch.cat((b_ih.detach(), b_ih_r.detach()))
         bhh = torch.cat((b_hh.detach(), b_hh_r.detach()))
         gi = raw.gemm(x2, wih, shift=bih, out_dtype=torch.float32)
@@ -521,19 +522,7 @@ class GRULayerFn(torch.autograd.Function):
         x2, out, saved, w_ih, w_hh, w_ih_r, w_hh_r = ctx.saved_tensors
         B, T, I, H = ctx.dims
 
-        def make_hht():
-            # W_hh^T per direction: [2][H][3H] bf16 (the backward recurrence contracts over the 3H gate rows)
-            t = torch.stack((w_hh.detach().t().contiguous(), w_hh_r.detach().t().contiguous()))
-            return raw.cast_bf16(t.view(2 * H, 3 * H)).view(2, H, 3 * H)
-
-        def make_ih():
-            buf = torch.empty((6 * H, (I + 7) // 8 * 8), device=dout.device, dtype=torch.bfloat16)
-            raw.cast_bf16(w_ih.detach(), out=buf[:3 * H])
-            raw.cast_bf16(w_ih_r.detach(), out=buf[3 * H:])
-            return buf
-
-        whht = _cached_multi((w_hh, w_hh_r), "gru_hht", make_hht)
-        wih = _cached_multi((w_ih, w_ih_r), "gru_ih", make_ih)
+        wih, _, whht = _gru_packed(w_ih, w_ih_r, w_hh, w_hh_r, I, H)
         dgi, dgh, hprev = raw.gru_bwd(dout.contiguous(), out, saved, whht, B, T, H)
         dx = None
         if ctx.needs_input_grad[0]:

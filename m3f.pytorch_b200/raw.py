@@ -488,6 +488,14 @@ def pack_filter(w, want_dgrad):
     return wf, wd
 
 
+def gru_pack_weights(w_ih, w_ih_r, w_hh, w_hh_r, wih, whh, whht, I, Ipad, H):
+    for t in (w_ih, w_ih_r, w_hh, w_hh_r):
+        assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()
+    L.check(_lib().m3t_gru_pack_weights(L.ptr(w_ih), L.ptr(w_ih_r), L.ptr(w_hh), L.ptr(w_hh_r), L.ptr(wih), L.ptr(whh),
+                                        L.ptr(whht), L.i32(I), L.i32(Ipad), L.i32(H), L.stream_ptr()),
+            "m3t_gru_pack_weights")
+
+
 def unpack_filter_grad(dwp, shape):
     Cout, Cin = shape[:2]
     taps = 1
