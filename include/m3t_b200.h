@@ -303,7 +303,13 @@ int m3t_split3_bf16(const float* x, const float* res, int relu, float* out_f32, 
                     void* stream);
 /* Weights: f32 [N][G][C] (tap_minor 0) or [N][C][G] (tap_minor 1, nn.Conv layout, G = taps) -> bf16 [N][G][3C] =
  * [hi | lo | hi] per group (nn.Linear: G = 1). */
-int m3t_pack_split3_bf16(const float* w, void* out, long long N, int G, int C, int tap_minor, void* stream);
+int m3t_pack_split3_bf16(const float* w, void* out, long long N, int G, int C, int tap_minor, int cpad, void* stream);
+/* cpad (0 = 3C): elements per group in `out`; a tail beyond 3C is zero-filled (first VGG-M conv: 3*16 -> 64).
+ * m3t_video_prep_s2d with split output for that conv: bf16 (B,T,H/2,W/2,64) = [hi 16 | hi 16 | lo 16 | 0 16]. */
+int m3t_video_prep_s2d_split3(const void* video, int is_u8, void* out, int B, int T, int H, int W, float mul, float add,
+                              void* stream);
+/* nn.MaxPool3d((1,2,2),(1,2,2)) of the VGG-M groups (models/backbone.py:76-96) on float32 channels-last tensors. */
+int m3t_maxpool2x2_f32(const float* x, float* out, int F, int H, int W, int C, void* stream);
 /* m3t_video_prep_s2d_w4 with split output: bf16 (B,T,H/2,W/2,192) = [hi 64 | hi 64 | lo 64] per pixel. */
 int m3t_video_prep_s2d_w4_split3(const void* video, int is_u8, void* out, int B, int T, int H, int W, float mul,
                                  float add, void* stream);

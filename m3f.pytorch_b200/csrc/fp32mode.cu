@@ -54,7 +54,7 @@ __global__ void split3_kernel(const float* __restrict__ x, const float* __restri
 // w f32 [N][G][C] (tap_minor == 0) or [N][C][G] (tap_minor == 1, the nn.Conv layout with G = taps)
 //   -> bf16 [N][G][3C] = [hi | lo | hi] per group
 __global__ void pack_split3_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, long long N, int G,
-                                   int C, int tap_minor) {
+                                   int C, int tap_minor, int cpad) {
   const long long total = N * G * C;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -65,10 +65,63 @@ __global__ void pack_split3_kernel(const float* __restrict__ w, __nv_bfloat16* _
     const float v = tap_minor ? w[(n * C + c) * G + g] : w[i];
     __nv_bfloat16 hi, lo;
     split_hi_lo(v, hi, lo);
-    __nv_bfloat16* o = out + (n * G + g) * 3 * C;
+    __nv_bfloat16* o = out + (n * G + g) * cpad;    // cpad >= 3C; the tail (if any) was zero-filled by the caller
     o[c] = hi;
     o[C + c] = lo;
     o[2 * C + c] = hi;
+  }
+}
+
+// video (B,3,T,H,W) -> 2x2 space-to-depth with split output for the first VGG-M conv: bf16 (B,T,H/2,W/2,64) =
+// [hi 16 | hi 16 | lo 16 | 0 16] per pixel, channel (ph*2+pw)*3 + c of each 16 (12 real).
+template <typename T>
+__global__ void video_prep_s2d_split3_kernel(const T* __restrict__ in, __nv_bfloat16* __restrict__ out, int B, int Tn,
+                                             int H, int W, float mul, float add) {
+  const int H2 = H / 2, W2 = W / 2;
+  const long long total = (long long)B * Tn * H2 * W2;
+  const __nv_bfloat16 z = __float2bfloat16(0.f);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int w2 = (int)(i % W2);
+    long long r = i / W2;
+    const int h2 = (int)(r % H2);
+    r /= H2;
+    const int t = (int)(r % Tn);
+    const int b = (int)(r / Tn);
+    __nv_bfloat16* o = out + i * 64;
+    for (int k = 0; k < 64; ++k) o[k] = z;
+#pragma unroll
+    for (int ph = 0; ph < 2; ++ph)
+#pragma unroll
+      for (int pw = 0; pw < 2; ++pw)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const T* p = in + ((((long long)b * 3 + c) * Tn + t) * H + (2 * h2 + ph)) * W + 2 * w2 + pw;
+          const float v = fmaf((float)(*p), mul, add);
+          __nv_bfloat16 hi, lo;
+          split_hi_lo(v, hi, lo);
+          const int ch = (ph * 2 + pw) * 3 + c;
+          o[ch] = hi;
+          o[16 + ch] = hi;
+          o[32 + ch] = lo;
+        }
+  }
+}
+
+// 2x2 / stride 2 max-pool over (H,W) of [F][H][W][C] float32 (nn.MaxPool3d((1,2,2),(1,2,2)), floor mode)
+__global__ void maxpool2x2_f32_kernel(const float* __restrict__ x, float* __restrict__ out, int F, int H, int W, int C) {
+  const int P = H / 2, Q = W / 2;
+  const long long total = (long long)F * P * Q * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    long long r = i / C;
+    const int q = (int)(r % Q);
+    r /= Q;
+    const int p = (int)(r % P);
+    const int f = (int)(r / P);
+    const float* b = x + (((long long)f * H + 2 * p) * W + 2 * q) * C + c;
+    out[i] = fmaxf(fmaxf(b[0], b[C]), fmaxf(b[(long long)W * C], b[(long long)W * C + C]));
   }
 }
 
@@ -250,10 +303,37 @@ extern "C" int m3t_split3_bf16(const float* x, const float* res, int relu, float
   return launch_status();
 }
 
-extern "C" int m3t_pack_split3_bf16(const float* w, void* out, long long N, int G, int C, int tap_minor, void* stream) {
+extern "C" int m3t_pack_split3_bf16(const float* w, void* out, long long N, int G, int C, int tap_minor, int cpad,
+                                    void* stream) {
   if (N <= 0 || G <= 0 || C <= 0) return -1;
-  pack_split3_kernel<<<fp_blocks(N * G * C), kFpThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      w, reinterpret_cast<__nv_bfloat16*>(out), N, G, C, tap_minor);
+  if (cpad <= 0) cpad = 3 * C;
+  if (cpad < 3 * C) return -1;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (cpad > 3 * C && cudaMemsetAsync(out, 0, (size_t)N * G * cpad * 2, st) != cudaSuccess) return -21;
+  pack_split3_kernel<<<fp_blocks(N * G * C), kFpThreads, 0, st>>>(w, reinterpret_cast<__nv_bfloat16*>(out), N, G, C,
+                                                                   tap_minor, cpad);
+  count_launch();
+  return launch_status();
+}
+
+extern "C" int m3t_video_prep_s2d_split3(const void* video, int is_u8, void* out, int B, int T, int H, int W, float mul,
+                                         float add, void* stream) {
+  if ((H | W) & 1) return -1;
+  const long long items = (long long)B * T * (H / 2) * (W / 2);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (is_u8)
+    video_prep_s2d_split3_kernel<uint8_t><<<fp_blocks(items), kFpThreads, 0, st>>>(
+        reinterpret_cast<const uint8_t*>(video), reinterpret_cast<__nv_bfloat16*>(out), B, T, H, W, mul, add);
+  else
+    video_prep_s2d_split3_kernel<float><<<fp_blocks(items), kFpThreads, 0, st>>>(
+        reinterpret_cast<const float*>(video), reinterpret_cast<__nv_bfloat16*>(out), B, T, H, W, mul, add);
+  count_launch();
+  return launch_status();
+}
+
+extern "C" int m3t_maxpool2x2_f32(const float* x, float* out, int F, int H, int W, int C, void* stream) {
+  maxpool2x2_f32_kernel<<<fp_blocks((long long)F * (H / 2) * (W / 2) * C), kFpThreads, 0,
+                          reinterpret_cast<cudaStream_t>(stream)>>>(x, out, F, H, W, C);
   count_launch();
   return launch_status();
 }

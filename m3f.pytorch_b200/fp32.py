@@ -55,14 +55,17 @@ def split3(x, res=None, relu=False, want_f32=False):
     return out3, y
 
 
-def _pack_w(w, tag, N, G, C, tap_minor, src=None):
+def _pack_raw(s, N, G, C, tap_minor, cpad=0):
+    out = torch.empty((N, G * (cpad or 3 * C)), device=s.device, dtype=torch.bfloat16)
+    L.check(_lib().m3t_pack_split3_bf16(L.ptr(s), L.ptr(out), L.i64(N), L.i32(G), L.i32(C), L.i32(tap_minor),
+                                        L.i32(cpad), L.stream_ptr()), "m3t_pack_split3_bf16")
+    return out
+
+
+def _pack_w(w, tag, N, G, C, tap_minor, src=None, cpad=0):
     """bf16 [N, G*3C] split copy of a float32 parameter, cached until the parameter changes."""
     def make():
-        s = (w.detach() if src is None else src()).contiguous().float()
-        out = torch.empty((N, G * 3 * C), device=w.device, dtype=torch.bfloat16)
-        L.check(_lib().m3t_pack_split3_bf16(L.ptr(s), L.ptr(out), L.i64(N), L.i32(G), L.i32(C), L.i32(tap_minor),
-                                            L.stream_ptr()), "m3t_pack_split3_bf16")
-        return out
+        return _pack_raw((w.detach() if src is None else src()).contiguous().float(), N, G, C, tap_minor, cpad)
     return ops._cached(w, "split3:" + tag, make)
 
 
@@ -166,9 +169,7 @@ def gru_module(m, x):
         # input projection of all steps, both directions: [B*T, 2*3H] = x . [W_ih ; W_ih_reverse]^T + b_ih
         K = h.shape[-1]
         x3, _ = split3(h.view(B * T, K))
-        w3 = torch.empty((6 * H, 3 * K), device=h.device, dtype=torch.bfloat16)
-        L.check(_lib().m3t_pack_split3_bf16(L.ptr(w_ih.contiguous().float()), L.ptr(w3), L.i64(6 * H), L.i32(1),
-                                            L.i32(K), L.i32(0), L.stream_ptr()), "m3t_pack_split3_bf16")
+        w3 = _pack_raw(w_ih.contiguous().float(), 6 * H, 1, K, 0)
         gi = raw.gemm(x3, w3, out_dtype=torch.float32, shift=b_ih.float().contiguous())
         out = torch.empty((B, T, 2 * H), device=h.device, dtype=torch.float32)
         L.check(_lib().m3t_gru_fwd_f32(L.ptr(gi), L.ptr(w_hh.contiguous().float()), L.ptr(b_hh.contiguous().float()),
@@ -207,6 +208,113 @@ def va_3dresnet(m, video, normalise=False):
     if f.shape[1] != m.frameLen:
         raise RuntimeError("VA_3DResNet: T (%d) must equal frameLen (%d)" % (f.shape[1], m.frameLen))
     return gru_module(m.gru, f) if m.backend == 'gru' else f
+
+
+def convnd_bias_bn(x3, x_shape, nd, w, w3, bias, bn, k, pad_lo, pad_hi, relu, cin3, dil=(1, 1, 1)):
+    """Generic N-d stride-1 conv on a split input with conv bias + eval BN folded into the epilogue -> f32."""
+    if nd == 3:
+        N, D, H, W = x_shape
+    else:
+        N, W = x_shape
+        D = H = 1
+    Cout = w.shape[0]
+    if bn is not None:
+        ss = raw.bn_fold(bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var,
+                         bias.detach() if bias is not None else None, ops.BN_EPS)
+        scale, shift = ss[0], ss[1]
+    else:
+        scale, shift = None, (bias.detach().float().contiguous() if bias is not None else None)
+    geom = raw.conv_geom(nd, N, D, H, W, cin3, Cout, k, (1, 1, 1), pad_lo, pad_hi, dil)
+    Z, P, Q = raw.conv_out_dims(geom)
+    y = torch.empty((N, Z, P, Q, Cout), device=x3.device, dtype=torch.float32)
+    rc = _lib().m3t_conv_fprop_bf16(L.ptr(x3), L.ptr(w3), L.ptr(y), L.int_array(geom), L.ptr(scale), L.ptr(shift),
+                                    L.ptr(None), L.i32(1 if relu else 0), L.ptr(None), L.i32(BF16_OUT_F32),
+                                    L.stream_ptr())
+    L.check(rc, "m3t_conv_fprop_bf16 (fp32 mode)")
+    return y
+
+
+def vggm_stack(seq, x, video_first, normalise=False):
+    """A Sequential of [Conv3d 3x3x3 pad(1,0,0) + BN3d + ReLU (+ MaxPool3d(1,2,2))] groups (models/backbone.py:73-103)
+    in float32.  x: the raw video (B,3,T,H,W) when video_first, else f32 [B,T,H,W,C]."""
+    mods = list(seq)
+    i = 0
+    while i < len(mods):
+        conv, bn = mods[i], mods[i + 1]
+        pool = i + 3 < len(mods) and isinstance(mods[i + 3], torch.nn.MaxPool3d)
+        w = conv.weight
+        Cout = w.shape[0]
+        if video_first and i == 0:
+            video = x.contiguous()
+            B, _, T, H, W = video.shape
+            xs3 = torch.empty((B, T, H // 2, W // 2, 64), device=video.device, dtype=torch.bfloat16)
+            mul, add = (1.0 / 127.5, -1.0) if normalise else (1.0, 0.0)
+            L.check(_lib().m3t_video_prep_s2d_split3(L.ptr(video), L.i32(video.dtype == torch.uint8), L.ptr(xs3),
+                                                     L.i32(B), L.i32(T), L.i32(H), L.i32(W), L.f32(mul), L.f32(add),
+                                                     L.stream_ptr()), "m3t_video_prep_s2d_split3")
+            idx = ops.vggm_s2d_index(w.device).long()
+
+            def gathered(w=w, idx=idx, Cout=Cout):
+                flat = w.detach().view(Cout, -1)
+                return (flat[:, idx.clamp(min=0)] * (idx >= 0).to(flat.dtype)).contiguous()
+
+            w3 = _pack_w(w, "vggm1", Cout, 12, 16, 0, src=gathered, cpad=64)
+            y = convnd_bias_bn(xs3, (B, T, H // 2, W // 2), 3, w, w3, conv.bias, bn, (3, 2, 2), (1, 0, 0), (1, 0, 0),
+                               True, 64)
+        else:
+            B, T, H, W, C = x.shape
+            x3, _ = split3(x)
+            w3 = _pack_w(w, "conv3d", Cout, 27, C, 1)
+            y = convnd_bias_bn(x3, (B, T, H, W), 3, w, w3, conv.bias, bn, (3, 3, 3), (1, 0, 0), (1, 0, 0), True, 3 * C)
+        if pool:
+            Bq, Z, P, Q, Cq = y.shape
+            out = torch.empty((Bq, Z, P // 2, Q // 2, Cq), device=y.device, dtype=torch.float32)
+            L.check(_lib().m3t_maxpool2x2_f32(L.ptr(y), L.ptr(out), L.i32(Bq * Z), L.i32(P), L.i32(Q), L.i32(Cq),
+                                              L.stream_ptr()), "m3t_maxpool2x2_f32")
+            y = out
+        x = y
+        i += 4 if pool else 3
+    return x
+
+
+def tcn_simple(mlist, x):
+    """[Conv1d(k, p=(k-1)/2) + BN1d + ReLU] x2 (+ Linear) on f32 (B,T,C) (models/backbone.py:214-231,284-289)."""
+    seq = mlist[0]
+    for ci in (0, 3):
+        conv, bn = seq[ci], seq[ci + 1]
+        k, p = conv.kernel_size[0], conv.padding[0]
+        B, T, C = x.shape
+        x3, _ = split3(x.contiguous())
+        w3 = _pack_w(conv.weight, "conv1d", conv.weight.shape[0], k, C, 1)
+        x = convnd_bias_bn(x3, (B, T), 1, conv.weight, w3, conv.bias, bn, (1, 1, k), (0, 0, p), (0, 0, p), True, 3 * C)
+        x = x.view(B, T, -1)
+    if len(mlist) > 1:
+        x = linear(x, mlist[1].weight, mlist[1].bias)
+    return x
+
+
+def temporal_conv_net(net, x):
+    """models/tcn.py:43-64 (eval, dropout off): weight-normed dilated causal Conv1d pairs + residual, f32 (B,T,C)."""
+    for blk in net.network:
+        B, T, C = x.shape
+        h = x
+        for conv in (blk.conv1, blk.conv2):
+            w = torch._weight_norm(conv.weight_v, conv.weight_g, 0).detach().contiguous()   # g * v / ||v|| per channel
+            k, Ci = w.shape[2], w.shape[1]
+            h3, _ = split3(h.contiguous())
+            w3 = _pack_raw(w.float(), w.shape[0], k, Ci, 1)
+            h = convnd_bias_bn(h3, (B, T), 1, w, w3, conv.bias, None, (1, 1, k), (0, 0, blk.padding), (0, 0, 0), True,
+                               3 * Ci, dil=(1, 1, blk.dilation)).view(B, T, -1)
+        if blk.downsample is None:
+            res = x.contiguous()
+        else:
+            x3, _ = split3(x.contiguous())
+            wd = blk.downsample.weight
+            w3 = _pack_w(wd, "conv1d", wd.shape[0], 1, C, 1)
+            res = convnd_bias_bn(x3, (B, T), 1, wd, w3, blk.downsample.bias, None, (1, 1, 1), (0, 0, 0), (0, 0, 0),
+                                 False, 3 * C).view(B, T, -1)
+        _, x = split3(h.contiguous(), res=res, relu=True, want_f32=True)
+    return x
 
 
 def require_eval(module):

@@ -11,7 +11,7 @@ import torch
 import torch.nn as nn
 from torch.nn.utils import weight_norm
 
-from .. import ops
+from .. import fp32, ops
 
 
 class Chomp1d(nn.Module):
@@ -81,9 +81,14 @@ class TemporalConvNet(nn.Module):
         self.network = nn.Sequential(*layers)
 
     def forward_cl(self, x):
+        if fp32.enabled():       # fp32-parity inference mode (m3t_b200.fp32)
+            fp32.require_eval(self)
+            return fp32.temporal_conv_net(self, ops.as_f32(x))
         for blk in self.network:
             x = blk.forward_cl(x)
         return x
 
     def forward(self, x):
+        if fp32.enabled():
+            return self.forward_cl(x.float().transpose(1, 2).contiguous()).transpose(1, 2).contiguous()
         return ops.FromCL.apply(self.forward_cl(ops.ToCL.apply(x)))

@@ -8,7 +8,7 @@ evaluated over the 2x2 space-to-depth image, like the ResNet stem.
 import torch
 import torch.nn as nn
 
-from .. import ops, raw
+from .. import fp32, ops, raw
 from .backbone import _init_like_reference
 from .rnn import GRU
 from .tcn import TemporalConvNet
@@ -105,6 +105,17 @@ class VA_3DVGGM(nn.Module):
         _init_like_reference(self)
 
     def forward_bf16(self, video, *unused, normalise=False):
+        if fp32.enabled():       # fp32-parity inference mode (m3t_b200.fp32)
+            fp32.require_eval(self)
+            f = _squeeze_features(fp32.vggm_stack(self.v2p, video, True, normalise))
+            if self.backend == 'gru':
+                return self.gru.forward_bf16(f)
+            if self.backend == 'tcn':
+                return fp32.linear(self.tcn[0].forward_cl(f), self.tcn[1].weight, self.tcn[1].bias)
+            if self.backend == 'tcn_simple':
+                return fp32.tcn_simple(self.tcn, f)
+            h = fp32.linear(f, self.fc[0].weight, self.fc[0].bias, relu=True)
+            return fp32.linear(h, self.fc[2].weight, self.fc[2].bias).mean(dim=1)
         xs = raw.video_prep_s2d(video.contiguous(), normalise)
         f = _squeeze_features(_run_stack(self.v2p, xs, True))           # (B,T,512)
         if self.backend == 'gru':
@@ -160,6 +171,20 @@ class VA_3DVGGM_Split(nn.Module):
         _init_like_reference(self)
 
     def forward_bf16(self, video, se, au, normalise=False):
+        if fp32.enabled():       # fp32-parity inference mode (m3t_b200.fp32)
+            fp32.require_eval(self)
+            cl = lambda f: f.float().transpose(1, 2).contiguous()        # noqa: E731  (B,C,T) -> (B,T,C)
+            x = fp32.vggm_stack(self.shared, video, True, normalise)
+            if self.split_layer == 5:
+                f = torch.cat((_squeeze_features(x), cl(se), cl(au)), dim=-1)
+                return self.gru.forward_bf16(f) if self.backend == 'gru' else f
+            x_v = torch.cat((_squeeze_features(fp32.vggm_stack(self.v_private, x, False)), cl(se)), dim=-1)
+            x_a = torch.cat((_squeeze_features(fp32.vggm_stack(self.a_private, x, False)), cl(au)), dim=-1)
+            if self.backend == 'gru':
+                o_v, o_a = self.gru_v.forward_bf16(x_v), self.gru_a.forward_bf16(x_a)
+            else:
+                o_v, o_a = fp32.tcn_simple(self.tcn_v, x_v), fp32.tcn_simple(self.tcn_a, x_a)
+            return torch.cat((o_v, o_a), dim=-1)
         xs = raw.video_prep_s2d(video.contiguous(), normalise)
         x = _run_stack(self.shared, xs, True)
         if self.split_layer == 5:

@@ -1067,12 +1067,15 @@ def case_golden_fp32(name):
     m = _build(fx).eval()
     kind, inp = fx["kind"], fx["inputs"]
     with torch.no_grad(), fp32.parity_mode():
-        if kind in ("GRU", "ResNet"):
+        if kind in ("GRU", "ResNet", "TemporalConvNet"):
             out = m(inp["x"].cuda())
         elif kind == "AttFusion":
             out = m(inp["x_a"].cuda(), inp["x_v"].cuda())
         elif kind == "VA_3DResNet":
             out = m((inp["video_u8"].float().cuda() - 127.5) / 127.5)
+        elif kind == "VA_3DVGGM_Split":
+            se = inp["se_features"].cuda()
+            out = m((inp["video_u8"].float().cuda() - 127.5) / 127.5, se, se)
         else:
             out = m(ref_batch(inp, "cuda"))
     errs = {"out_ref32": _err(out, fx["out"])}
@@ -1082,8 +1085,8 @@ def case_golden_fp32(name):
     return errs
 
 
-for _n in ("gru_audio", "gru_scorer", "gru_nohead", "attfusion", "resnet_trunk_eval", "va3dresnet_eval",
-           "av_resnet_attention_eval"):
+for _n in ("gru_audio", "gru_scorer", "gru_nohead", "attfusion", "tcn", "resnet_trunk_eval", "va3dresnet_eval",
+           "av_resnet_attention_eval", "vggm_split3_eval", "av_v2psplit_attention_eval"):
     CASES["fp32_" + _n] = (case_golden_fp32, _c(name=_n))
 TOLS["out_ref32"] = 1e-4
 TOLS["va_ref32"] = 1e-4
