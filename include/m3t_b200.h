@@ -49,7 +49,8 @@ int m3t_gemm_bf16(const void* A, long long lda, int a_mn, const void* B, long lo
  *   y        bf16 channels-last [N][Z][P][Q][Cout]
  *   y = act( conv(x,w) * scale[c] + shift[c] + residual ), all optional; stats as in m3t_gemm_bf16.
  *   tile_hint: 0 = auto; bit0 force 128-row tiles, bit1 force 256-row tiles, bit3 force 128-column tiles,
- *     bit4 / bit5 force / forbid the persistent tile walker, bit6: y is float32 (no residual; fp32-parity mode).
+ *     bit4 / bit5 force / forbid the persistent tile walker, bit6: y is float32 (no residual; fp32-parity mode),
+ *     bit7: contraction runs channel-block-major (all taps of block 0, then block 1, ...) instead of tap-major.
  * Replaces: nn.Conv2d 3x3 / 1x1 in BasicBlock (models/resnet.py:7-15,24-27,40-54,98-101), nn.Conv3d 3x3x3 in
  * VA_3DVGGM(_Split) (models/backbone.py:73-103,179-195,243-271), weight-normed dilated causal nn.Conv1d in
  * TemporalBlock (models/tcn.py:19-33) and Conv1d k5 in tcn_simple (models/backbone.py:214-231), with the
@@ -300,19 +301,22 @@ int m3t_ccc_moments_f64(const double* pred, const float* gt, const long long* se
  * Replaces, in this mode, the residual add + ReLU of BasicBlock.forward (models/resnet.py:52-54) and feeds the next
  * convolution / Linear. */
 int m3t_split3_bf16(const float* x, const float* res, int relu, float* out_f32, void* out3, long long rows, int C,
-                    void* stream);
+                    int nterms, void* stream);
+/* nterms = 3 (above, error 2^-16) or 6: three pieces per value, x = p0 + p1 + p2, and the products a0b0 + a0b1 + a1b0 +
+ * a0b2 + a1b1 + a2b0 (error 2^-24): activations [a0 a0 a1 a0 a1 a2], weights [b0 b1 b0 b2 b1 b0], 6x the contraction. */
 /* Weights: f32 [N][G][C] (tap_minor 0) or [N][C][G] (tap_minor 1, nn.Conv layout, G = taps) -> bf16 [N][G][3C] =
  * [hi | lo | hi] per group (nn.Linear: G = 1). */
-int m3t_pack_split3_bf16(const float* w, void* out, long long N, int G, int C, int tap_minor, int cpad, void* stream);
-/* cpad (0 = 3C): elements per group in `out`; a tail beyond 3C is zero-filled (first VGG-M conv: 3*16 -> 64).
- * m3t_video_prep_s2d with split output for that conv: bf16 (B,T,H/2,W/2,64) = [hi 16 | hi 16 | lo 16 | 0 16]. */
+int m3t_pack_split3_bf16(const float* w, void* out, long long N, int G, int C, int tap_minor, int cpad, int nterms,
+                         void* stream);
+/* cpad (0 = nterms*C): elements per group in `out`; a tail beyond nterms*C is zero-filled (first VGG-M conv: 3*16 -> 64).
+ * m3t_video_prep_s2d with split output for that conv: bf16 (B,T,H/2,W/2,cpad) = nterms blocks of 16 channels + zeros. */
 int m3t_video_prep_s2d_split3(const void* video, int is_u8, void* out, int B, int T, int H, int W, float mul, float add,
-                              void* stream);
+                              int nterms, int cpad, void* stream);
 /* nn.MaxPool3d((1,2,2),(1,2,2)) of the VGG-M groups (models/backbone.py:76-96) on float32 channels-last tensors. */
 int m3t_maxpool2x2_f32(const float* x, float* out, int F, int H, int W, int C, void* stream);
-/* m3t_video_prep_s2d_w4 with split output: bf16 (B,T,H/2,W/2,192) = [hi 64 | hi 64 | lo 64] per pixel. */
+/* m3t_video_prep_s2d_w4 with split output: bf16 (B,T,H/2,W/2,64*nterms), nterms blocks of 64 channels per pixel. */
 int m3t_video_prep_s2d_w4_split3(const void* video, int is_u8, void* out, int B, int T, int H, int W, float mul,
-                                 float add, void* stream);
+                                 float add, int nterms, void* stream);
 /* nn.MaxPool3d((1,3,3),(1,2,2),(0,1,1)) (models/backbone.py:331) / AdaptiveAvgPool2d(1) (models/resnet.py:117) on
  * float32 channels-last tensors. */
 int m3t_maxpool3s2_f32(const float* x, float* out, int F, int H, int W, int C, void* stream);

@@ -29,10 +29,31 @@ __device__ __forceinline__ void split_hi_lo(float x, __nv_bfloat16& hi, __nv_bfl
   hi = __float2bfloat16_rn(x);
   lo = __float2bfloat16_rn(x - __bfloat162float(hi));
 }
+// three pieces: x = p0 + p1 + p2 up to 2^-25 |x| (8 + 8 + 8 mantissa bits)
+__device__ __forceinline__ void split_3(float x, __nv_bfloat16 (&p)[3]) {
+  p[0] = __float2bfloat16_rn(x);
+  const float r1 = x - __bfloat162float(p[0]);
+  p[1] = __float2bfloat16_rn(r1);
+  p[2] = __float2bfloat16_rn(r1 - __bfloat162float(p[1]));
+}
+// Term tables, smallest products first and the main term a0 b0 LAST (the consumers run the contraction
+// channel-block-major): the tensor core truncates the fp32 accumulator after every MMA, and that error is proportional
+// to the accumulator's magnitude, so the corrections are summed while it is still small.
+//   nt = 3: a.b ~= a0 b1 + a1 b0 + a0 b0 (error 2^-16): activation blocks [a0 a1 a0], weight blocks [b1 b0 b0]
+//   nt = 6: adds a0 b2 + a1 b1 + a2 b0 in front (error 2^-24): [a0 a1 a2 a0 a1 a0] x [b2 b1 b0 b1 b0 b0]
+__device__ __forceinline__ int act_piece(int nt, int k) {
+  constexpr int t3[3] = {0, 1, 0}, t6[6] = {0, 1, 2, 0, 1, 0};
+  return nt == 3 ? t3[k] : t6[k];
+}
+__device__ __forceinline__ int wgt_piece(int nt, int k) {
+  constexpr int t3[3] = {1, 0, 0}, t6[6] = {2, 1, 0, 1, 0, 0};
+  return nt == 3 ? t3[k] : t6[k];
+}
 
 // y = x (+ res) (relu);  out_f32 = y (optional);  out3[row] = [hi(C) | hi(C) | lo(C)]
 __global__ void split3_kernel(const float* __restrict__ x, const float* __restrict__ res, int relu,
-                              float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out3, long long rows, int C) {
+                              float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out3, long long rows, int C,
+                              int nt) {
   const long long total = rows * C;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -42,19 +63,17 @@ __global__ void split3_kernel(const float* __restrict__ x, const float* __restri
     if (res) y += res[i];
     if (relu) y = fmaxf(y, 0.f);
     if (out_f32) out_f32[i] = y;
-    __nv_bfloat16 hi, lo;
-    split_hi_lo(y, hi, lo);
-    __nv_bfloat16* o = out3 + r * 3 * C;
-    o[c] = hi;
-    o[C + c] = hi;
-    o[2 * C + c] = lo;
+    __nv_bfloat16 pc[3];
+    split_3(y, pc);
+    __nv_bfloat16* o = out3 + r * nt * C;
+    for (int k = 0; k < nt; ++k) o[k * C + c] = pc[act_piece(nt, k)];
   }
 }
 
 // w f32 [N][G][C] (tap_minor == 0) or [N][C][G] (tap_minor == 1, the nn.Conv layout with G = taps)
 //   -> bf16 [N][G][3C] = [hi | lo | hi] per group
 __global__ void pack_split3_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, long long N, int G,
-                                   int C, int tap_minor, int cpad) {
+                                   int C, int tap_minor, int cpad, int nt) {
   const long long total = N * G * C;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -63,12 +82,10 @@ __global__ void pack_split3_kernel(const float* __restrict__ w, __nv_bfloat16* _
     const int g = (int)(r % G);
     const long long n = r / G;
     const float v = tap_minor ? w[(n * C + c) * G + g] : w[i];
-    __nv_bfloat16 hi, lo;
-    split_hi_lo(v, hi, lo);
-    __nv_bfloat16* o = out + (n * G + g) * cpad;    // cpad >= 3C; the tail (if any) was zero-filled by the caller
-    o[c] = hi;
-    o[C + c] = lo;
-    o[2 * C + c] = hi;
+    __nv_bfloat16 pc[3];
+    split_3(v, pc);
+    __nv_bfloat16* o = out + (n * G + g) * cpad;    // cpad >= nt*C; the tail (if any) was zero-filled by the caller
+    for (int k = 0; k < nt; ++k) o[k * C + c] = pc[wgt_piece(nt, k)];
   }
 }
 
@@ -76,7 +93,7 @@ __global__ void pack_split3_kernel(const float* __restrict__ w, __nv_bfloat16* _
 // [hi 16 | hi 16 | lo 16 | 0 16] per pixel, channel (ph*2+pw)*3 + c of each 16 (12 real).
 template <typename T>
 __global__ void video_prep_s2d_split3_kernel(const T* __restrict__ in, __nv_bfloat16* __restrict__ out, int B, int Tn,
-                                             int H, int W, float mul, float add) {
+                                             int H, int W, float mul, float add, int nt, int cpad) {
   const int H2 = H / 2, W2 = W / 2;
   const long long total = (long long)B * Tn * H2 * W2;
   const __nv_bfloat16 z = __float2bfloat16(0.f);
@@ -88,8 +105,8 @@ __global__ void video_prep_s2d_split3_kernel(const T* __restrict__ in, __nv_bflo
     r /= H2;
     const int t = (int)(r % Tn);
     const int b = (int)(r / Tn);
-    __nv_bfloat16* o = out + i * 64;
-    for (int k = 0; k < 64; ++k) o[k] = z;
+    __nv_bfloat16* o = out + i * cpad;
+    for (int k = 0; k < cpad; ++k) o[k] = z;
 #pragma unroll
     for (int ph = 0; ph < 2; ++ph)
 #pragma unroll
@@ -98,12 +115,10 @@ __global__ void video_prep_s2d_split3_kernel(const T* __restrict__ in, __nv_bflo
         for (int c = 0; c < 3; ++c) {
           const T* p = in + ((((long long)b * 3 + c) * Tn + t) * H + (2 * h2 + ph)) * W + 2 * w2 + pw;
           const float v = fmaf((float)(*p), mul, add);
-          __nv_bfloat16 hi, lo;
-          split_hi_lo(v, hi, lo);
+          __nv_bfloat16 pc[3];
+          split_3(v, pc);
           const int ch = (ph * 2 + pw) * 3 + c;
-          o[ch] = hi;
-          o[16 + ch] = hi;
-          o[32 + ch] = lo;
+          for (int k = 0; k < nt; ++k) o[k * 16 + ch] = pc[act_piece(nt, k)];
         }
   }
 }
@@ -129,7 +144,7 @@ __global__ void maxpool2x2_f32_kernel(const float* __restrict__ x, float* __rest
 // channels + 16 zeros.
 template <typename T>
 __global__ void video_prep_s2d_w4_split3_kernel(const T* __restrict__ in, __nv_bfloat16* __restrict__ out, int B, int Tn,
-                                                int H, int W, float mul, float add) {
+                                                int H, int W, float mul, float add, int nt) {
   const int H2 = H / 2, W2 = W / 2;
   const long long total = (long long)B * Tn * H2 * W2 * 4;   // one thread per (pixel, tap jw)
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -143,7 +158,7 @@ __global__ void video_prep_s2d_w4_split3_kernel(const T* __restrict__ in, __nv_b
     const int t = (int)(r % Tn);
     const int b = (int)(r / Tn);
     const int ws = w2 + jw - 2;
-    __nv_bfloat16* o = out + pix * 192;
+    __nv_bfloat16* o = out + pix * (64 * nt);
 #pragma unroll
     for (int ph = 0; ph < 2; ++ph)
 #pragma unroll
@@ -155,17 +170,14 @@ __global__ void video_prep_s2d_w4_split3_kernel(const T* __restrict__ in, __nv_b
             const T* p = in + ((((long long)b * 3 + c) * Tn + t) * H + (2 * h2 + ph)) * W + 2 * ws + pw;
             v = fmaf((float)(*p), mul, add);
           }
-          __nv_bfloat16 hi, lo;
-          split_hi_lo(v, hi, lo);
+          __nv_bfloat16 pc[3];
+          split_3(v, pc);
           const int ch = jw * 12 + (ph * 2 + pw) * 3 + c;
-          o[ch] = hi;
-          o[64 + ch] = hi;
-          o[128 + ch] = lo;
+          for (int k = 0; k < nt; ++k) o[k * 64 + ch] = pc[act_piece(nt, k)];
         }
     if (jw == 0) {
       const __nv_bfloat16 z = __float2bfloat16(0.f);
-#pragma unroll
-      for (int k = 0; k < 3; ++k)
+      for (int k = 0; k < nt; ++k)
         for (int c = 48; c < 64; ++c) o[k * 64 + c] = z;
     }
   }
@@ -295,38 +307,38 @@ __global__ void __launch_bounds__(256) gru_step_f32_kernel(const float* __restri
 using namespace m3t;
 
 extern "C" int m3t_split3_bf16(const float* x, const float* res, int relu, float* out_f32, void* out3, long long rows,
-                               int C, void* stream) {
-  if (rows <= 0 || C <= 0) return -1;
+                               int C, int nterms, void* stream) {
+  if (rows <= 0 || C <= 0 || (nterms != 3 && nterms != 6)) return -1;
   split3_kernel<<<fp_blocks(rows * C), kFpThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      x, res, relu, out_f32, reinterpret_cast<__nv_bfloat16*>(out3), rows, C);
+      x, res, relu, out_f32, reinterpret_cast<__nv_bfloat16*>(out3), rows, C, nterms);
   count_launch();
   return launch_status();
 }
 
 extern "C" int m3t_pack_split3_bf16(const float* w, void* out, long long N, int G, int C, int tap_minor, int cpad,
-                                    void* stream) {
-  if (N <= 0 || G <= 0 || C <= 0) return -1;
-  if (cpad <= 0) cpad = 3 * C;
-  if (cpad < 3 * C) return -1;
+                                    int nterms, void* stream) {
+  if (N <= 0 || G <= 0 || C <= 0 || (nterms != 3 && nterms != 6)) return -1;
+  if (cpad <= 0) cpad = nterms * C;
+  if (cpad < nterms * C) return -1;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (cpad > 3 * C && cudaMemsetAsync(out, 0, (size_t)N * G * cpad * 2, st) != cudaSuccess) return -21;
+  if (cpad > nterms * C && cudaMemsetAsync(out, 0, (size_t)N * G * cpad * 2, st) != cudaSuccess) return -21;
   pack_split3_kernel<<<fp_blocks(N * G * C), kFpThreads, 0, st>>>(w, reinterpret_cast<__nv_bfloat16*>(out), N, G, C,
-                                                                   tap_minor, cpad);
+                                                                   tap_minor, cpad, nterms);
   count_launch();
   return launch_status();
 }
 
 extern "C" int m3t_video_prep_s2d_split3(const void* video, int is_u8, void* out, int B, int T, int H, int W, float mul,
-                                         float add, void* stream) {
-  if ((H | W) & 1) return -1;
+                                         float add, int nterms, int cpad, void* stream) {
+  if ((H | W) & 1 || (nterms != 3 && nterms != 6) || cpad < 16 * nterms) return -1;
   const long long items = (long long)B * T * (H / 2) * (W / 2);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (is_u8)
     video_prep_s2d_split3_kernel<uint8_t><<<fp_blocks(items), kFpThreads, 0, st>>>(
-        reinterpret_cast<const uint8_t*>(video), reinterpret_cast<__nv_bfloat16*>(out), B, T, H, W, mul, add);
+        reinterpret_cast<const uint8_t*>(video), reinterpret_cast<__nv_bfloat16*>(out), B, T, H, W, mul, add, nterms, cpad);
   else
     video_prep_s2d_split3_kernel<float><<<fp_blocks(items), kFpThreads, 0, st>>>(
-        reinterpret_cast<const float*>(video), reinterpret_cast<__nv_bfloat16*>(out), B, T, H, W, mul, add);
+        reinterpret_cast<const float*>(video), reinterpret_cast<__nv_bfloat16*>(out), B, T, H, W, mul, add, nterms, cpad);
   count_launch();
   return launch_status();
 }
@@ -339,16 +351,16 @@ extern "C" int m3t_maxpool2x2_f32(const float* x, float* out, int F, int H, int 
 }
 
 extern "C" int m3t_video_prep_s2d_w4_split3(const void* video, int is_u8, void* out, int B, int T, int H, int W,
-                                            float mul, float add, void* stream) {
-  if ((H | W) & 1) return -1;
+                                            float mul, float add, int nterms, void* stream) {
+  if ((H | W) & 1 || (nterms != 3 && nterms != 6)) return -1;
   const long long items = (long long)B * T * (H / 2) * (W / 2) * 4;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (is_u8)
     video_prep_s2d_w4_split3_kernel<uint8_t><<<fp_blocks(items), kFpThreads, 0, st>>>(
-        reinterpret_cast<const uint8_t*>(video), reinterpret_cast<__nv_bfloat16*>(out), B, T, H, W, mul, add);
+        reinterpret_cast<const uint8_t*>(video), reinterpret_cast<__nv_bfloat16*>(out), B, T, H, W, mul, add, nterms);
   else
     video_prep_s2d_w4_split3_kernel<float><<<fp_blocks(items), kFpThreads, 0, st>>>(
-        reinterpret_cast<const float*>(video), reinterpret_cast<__nv_bfloat16*>(out), B, T, H, W, mul, add);
+        reinterpret_cast<const float*>(video), reinterpret_cast<__nv_bfloat16*>(out), B, T, H, W, mul, add, nterms);
   count_launch();
   return launch_status();
 }

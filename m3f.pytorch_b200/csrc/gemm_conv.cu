@@ -201,6 +201,7 @@ static int conv_fprop_impl(const void* x, const void* w_packed, void* y, const i
   p.k_iters = taps * g.Cin / kBlockK;
   p.out = y; p.ldc = g.Cout; p.out_f32 = (tile_hint & 64) ? 1 : 0;
   if (p.out_f32 && residual) return -1;
+  p.cb_major = (tile_hint & 128) ? 1 : 0;
   p.scale = scale; p.shift = shift;
   p.residual = reinterpret_cast<const __nv_bfloat16*>(residual); p.ldr = g.Cout;
   p.relu = relu; p.stats = stats;

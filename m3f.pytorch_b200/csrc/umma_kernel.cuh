@@ -49,6 +49,10 @@ struct UmmaParams {
   int oq, op;
   long long o_img, o_row, o_px;
   int res_mapped;     // residual rows follow the same map (in-place accumulation)
+  // K order of the implicit GEMM: 0 = tap-major (tap, channel block), 1 = channel-block-major (all taps of block 0, then
+  // block 1, ...).  The fp32-parity mode puts the small correction terms in the first channel blocks and the main term
+  // last, so the tensor core's per-MMA accumulator truncation acts on the full magnitude for 1/3 of the K steps only.
+  int cb_major;
 };
 
 __device__ __forceinline__ long long out_row(const UmmaParams& p, long long m) {
@@ -306,8 +310,13 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           }
         } else if constexpr (AKIND == A_IM2COL) {
           if constexpr (CK == 64) {
-            const int tap = kglob / p.cblocks;
-            const int cb = kglob - tap * p.cblocks;
+            int tap = kglob / p.cblocks;
+            int cb = kglob - tap * p.cblocks;
+            if (p.cb_major) {
+              const int taps = p.T * p.R * p.S;
+              cb = kglob / taps;
+              tap = kglob - cb * taps;
+            }
 #pragma unroll
             for (int mt = 0; mt < MT; ++mt)
               im2col_load(&tmA, &full_bar[stage], sA + mt * 16384, p, pc[mt], cb * 64, tap);

@@ -80,8 +80,13 @@ umma_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               tma_load_2d(&tmA, &full_bar[stage], sA + mt * 16384, it * kBlockK, (m_tile * MT + mt) * 128);
             tma_load_2d(&tmB, &full_bar[stage], sB, it * kBlockK, n_tile * BN);
           } else {
-            const int tap = it / p.cblocks;
-            const int cb = it - tap * p.cblocks;
+            int tap = it / p.cblocks;
+            int cb = it - tap * p.cblocks;
+            if (p.cb_major) {
+              const int taps = p.T * p.R * p.S;
+              cb = it / taps;
+              tap = it - cb * taps;
+            }
 #pragma unroll
             for (int mt = 0; mt < MT; ++mt)
               im2col_load(&tmA, &full_bar[stage], sA + mt * 16384, p, pc[mt], cb * 64, tap);

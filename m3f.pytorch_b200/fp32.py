@@ -17,7 +17,8 @@ from . import lib as L
 from . import ops, raw
 
 _ON = False
-BF16_OUT_F32 = 64      # tile_hint bit 6 of m3t_conv_fprop_bf16: float32 output
+NT = 3                 # product terms per contraction: 3 (two bf16 pieces per value, 2^-16) or 6 (three pieces, 2^-24)
+BF16_OUT_F32 = 64 | 128   # tile_hint bits 6, 7 of m3t_conv_fprop_bf16: float32 output, channel-block-major K order
 
 
 def enabled():
@@ -25,13 +26,16 @@ def enabled():
 
 
 @contextlib.contextmanager
-def parity_mode(on=True):
-    global _ON
-    old, _ON = _ON, bool(on)
+def parity_mode(on=True, terms=3):
+    """terms=3: x = hi + lo, three bf16 products per fp32 product (2^-16 relative; 3x the tensor work).
+    terms=6: three pieces per value and the six leading products (2^-24, fp32-grade; 6x the tensor work)."""
+    global _ON, NT
+    assert terms in (3, 6)
+    old, _ON, NT = (_ON, NT), bool(on), terms
     try:
         yield
     finally:
-        _ON = old
+        _ON, NT = old
 
 
 def _lib():
@@ -46,19 +50,19 @@ def split3(x, res=None, relu=False, want_f32=False):
     assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()
     C = x.shape[-1]
     rows = x.numel() // C
-    out3 = torch.empty(x.shape[:-1] + (3 * C,), device=x.device, dtype=torch.bfloat16)
+    out3 = torch.empty(x.shape[:-1] + (NT * C,), device=x.device, dtype=torch.bfloat16)
     y = torch.empty_like(x) if want_f32 else None
     if res is not None:
         assert res.shape == x.shape and res.dtype == torch.float32 and res.is_contiguous()
     L.check(_lib().m3t_split3_bf16(L.ptr(x), L.ptr(res), L.i32(1 if relu else 0), L.ptr(y), L.ptr(out3), L.i64(rows),
-                                   L.i32(C), L.stream_ptr()), "m3t_split3_bf16")
+                                   L.i32(C), L.i32(NT), L.stream_ptr()), "m3t_split3_bf16")
     return out3, y
 
 
 def _pack_raw(s, N, G, C, tap_minor, cpad=0):
-    out = torch.empty((N, G * (cpad or 3 * C)), device=s.device, dtype=torch.bfloat16)
+    out = torch.empty((N, G * (cpad or NT * C)), device=s.device, dtype=torch.bfloat16)
     L.check(_lib().m3t_pack_split3_bf16(L.ptr(s), L.ptr(out), L.i64(N), L.i32(G), L.i32(C), L.i32(tap_minor),
-                                        L.i32(cpad), L.stream_ptr()), "m3t_pack_split3_bf16")
+                                        L.i32(cpad), L.i32(NT), L.stream_ptr()), "m3t_pack_split3_bf16")
     return out
 
 
@@ -66,7 +70,7 @@ def _pack_w(w, tag, N, G, C, tap_minor, src=None, cpad=0):
     """bf16 [N, G*3C] split copy of a float32 parameter, cached until the parameter changes."""
     def make():
         return _pack_raw((w.detach() if src is None else src()).contiguous().float(), N, G, C, tap_minor, cpad)
-    return ops._cached(w, "split3:" + tag, make)
+    return ops._cached(w, "split%d:%s" % (NT, tag), make)
 
 
 def linear(x, weight, bias, relu=False):
@@ -88,7 +92,7 @@ def conv2d_bn(x3, x_shape, conv, bn, relu):
     stride, pad = conv.stride[0], conv.padding[0]
     w3 = _pack_w(w, "conv", Cout, kh * kw, Cin, 1)
     ss = raw.bn_fold(bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var, None, ops.BN_EPS)
-    geom = raw.conv_geom(2, N, 1, H, W, 3 * Cin, Cout, (1, kh, kw), (1, stride, stride), (0, pad, pad), (0, pad, pad),
+    geom = raw.conv_geom(2, N, 1, H, W, NT * Cin, Cout, (1, kh, kw), (1, stride, stride), (0, pad, pad), (0, pad, pad),
                          (1, 1, 1))
     Z, P, Q = raw.conv_out_dims(geom)
     y = torch.empty((N, P, Q, Cout), device=x3.device, dtype=torch.float32)
@@ -128,10 +132,11 @@ def stem3d(video, conv, bn, normalise):
     """models/backbone.py:327-332 (eval): video (B,3,T,H,W) f32/u8 -> f32 [B*T, H/4, W/4, 64]."""
     video = video.contiguous()
     B, _, T, H, W = video.shape
-    xs3 = torch.empty((B, T, H // 2, W // 2, 192), device=video.device, dtype=torch.bfloat16)
+    xs3 = torch.empty((B, T, H // 2, W // 2, 64 * NT), device=video.device, dtype=torch.bfloat16)
     mul, add = (1.0 / 127.5, -1.0) if normalise else (1.0, 0.0)
     L.check(_lib().m3t_video_prep_s2d_w4_split3(L.ptr(video), L.i32(video.dtype == torch.uint8), L.ptr(xs3), L.i32(B),
-                                                L.i32(T), L.i32(H), L.i32(W), L.f32(mul), L.f32(add), L.stream_ptr()),
+                                                L.i32(T), L.i32(H), L.i32(W), L.f32(mul), L.f32(add), L.i32(NT),
+                                                L.stream_ptr()),
             "m3t_video_prep_s2d_w4_split3")
     w = conv.weight
     idx = ops.stem_s2d_index(w.device).long()
@@ -142,7 +147,7 @@ def stem3d(video, conv, bn, normalise):
 
     w3 = _pack_w(w, "stem", 64, 20, 64, 0, src=gathered)
     ss = raw.bn_fold(bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var, None, ops.BN_EPS)
-    geom = raw.conv_geom(3, B, T, H // 2, W // 2, 192, 64, (5, 4, 1), (1, 1, 1), (2, 2, 0), (2, 1, 0), (1, 1, 1))
+    geom = raw.conv_geom(3, B, T, H // 2, W // 2, 64 * NT, 64, (5, 4, 1), (1, 1, 1), (2, 2, 0), (2, 1, 0), (1, 1, 1))
     y = torch.empty((B * T, H // 2, W // 2, 64), device=video.device, dtype=torch.float32)
     rc = _lib().m3t_conv_fprop_bf16(L.ptr(xs3), L.ptr(w3), L.ptr(y), L.int_array(geom), L.ptr(ss[0]), L.ptr(ss[1]),
                                     L.ptr(None), L.i32(1), L.ptr(None), L.i32(BF16_OUT_F32), L.stream_ptr())
@@ -247,25 +252,26 @@ def vggm_stack(seq, x, video_first, normalise=False):
         if video_first and i == 0:
             video = x.contiguous()
             B, _, T, H, W = video.shape
-            xs3 = torch.empty((B, T, H // 2, W // 2, 64), device=video.device, dtype=torch.bfloat16)
+            cpad = (16 * NT + 63) // 64 * 64
+            xs3 = torch.empty((B, T, H // 2, W // 2, cpad), device=video.device, dtype=torch.bfloat16)
             mul, add = (1.0 / 127.5, -1.0) if normalise else (1.0, 0.0)
             L.check(_lib().m3t_video_prep_s2d_split3(L.ptr(video), L.i32(video.dtype == torch.uint8), L.ptr(xs3),
                                                      L.i32(B), L.i32(T), L.i32(H), L.i32(W), L.f32(mul), L.f32(add),
-                                                     L.stream_ptr()), "m3t_video_prep_s2d_split3")
+                                                     L.i32(NT), L.i32(cpad), L.stream_ptr()), "m3t_video_prep_s2d_split3")
             idx = ops.vggm_s2d_index(w.device).long()
 
             def gathered(w=w, idx=idx, Cout=Cout):
                 flat = w.detach().view(Cout, -1)
                 return (flat[:, idx.clamp(min=0)] * (idx >= 0).to(flat.dtype)).contiguous()
 
-            w3 = _pack_w(w, "vggm1", Cout, 12, 16, 0, src=gathered, cpad=64)
+            w3 = _pack_w(w, "vggm1", Cout, 12, 16, 0, src=gathered, cpad=cpad)
             y = convnd_bias_bn(xs3, (B, T, H // 2, W // 2), 3, w, w3, conv.bias, bn, (3, 2, 2), (1, 0, 0), (1, 0, 0),
-                               True, 64)
+                               True, cpad)
         else:
             B, T, H, W, C = x.shape
             x3, _ = split3(x)
             w3 = _pack_w(w, "conv3d", Cout, 27, C, 1)
-            y = convnd_bias_bn(x3, (B, T, H, W), 3, w, w3, conv.bias, bn, (3, 3, 3), (1, 0, 0), (1, 0, 0), True, 3 * C)
+            y = convnd_bias_bn(x3, (B, T, H, W), 3, w, w3, conv.bias, bn, (3, 3, 3), (1, 0, 0), (1, 0, 0), True, NT * C)
         if pool:
             Bq, Z, P, Q, Cq = y.shape
             out = torch.empty((Bq, Z, P // 2, Q // 2, Cq), device=y.device, dtype=torch.float32)
@@ -286,7 +292,7 @@ def tcn_simple(mlist, x):
         B, T, C = x.shape
         x3, _ = split3(x.contiguous())
         w3 = _pack_w(conv.weight, "conv1d", conv.weight.shape[0], k, C, 1)
-        x = convnd_bias_bn(x3, (B, T), 1, conv.weight, w3, conv.bias, bn, (1, 1, k), (0, 0, p), (0, 0, p), True, 3 * C)
+        x = convnd_bias_bn(x3, (B, T), 1, conv.weight, w3, conv.bias, bn, (1, 1, k), (0, 0, p), (0, 0, p), True, NT * C)
         x = x.view(B, T, -1)
     if len(mlist) > 1:
         x = linear(x, mlist[1].weight, mlist[1].bias)
@@ -304,7 +310,7 @@ def temporal_conv_net(net, x):
             h3, _ = split3(h.contiguous())
             w3 = _pack_raw(w.float(), w.shape[0], k, Ci, 1)
             h = convnd_bias_bn(h3, (B, T), 1, w, w3, conv.bias, None, (1, 1, k), (0, 0, blk.padding), (0, 0, 0), True,
-                               3 * Ci, dil=(1, 1, blk.dilation)).view(B, T, -1)
+                               NT * Ci, dil=(1, 1, blk.dilation)).view(B, T, -1)
         if blk.downsample is None:
             res = x.contiguous()
         else:
@@ -312,7 +318,7 @@ def temporal_conv_net(net, x):
             wd = blk.downsample.weight
             w3 = _pack_w(wd, "conv1d", wd.shape[0], 1, C, 1)
             res = convnd_bias_bn(x3, (B, T), 1, wd, w3, blk.downsample.bias, None, (1, 1, 1), (0, 0, 0), (0, 0, 0),
-                                 False, 3 * C).view(B, T, -1)
+                                 False, NT * C).view(B, T, -1)
         _, x = split3(h.contiguous(), res=res, relu=True, want_f32=True)
     return x
 

@@ -1057,7 +1057,7 @@ CASES["va3dresnet_96px_train"] = (case_va3dresnet_shapes, _c(B=2, T=3, HW=96, tr
 CASES["va3dresnet_15frames_train"] = (case_va3dresnet_shapes, _c(B=3, T=5, HW=112, train=True))
 
 
-def case_golden_fp32(name):
+def case_golden_fp32(name, terms=3):
     """fp32-parity inference mode (m3t_b200.fp32.parity_mode: float32 activations, split-operand bf16 tensor-core
     launches) on a golden fixture, against the fp32 output of the UNMODIFIED reference module.  North-star bar:
     1e-4 range-normalised on the outputs / the V-A predictions."""
@@ -1066,7 +1066,7 @@ def case_golden_fp32(name):
     fx = load(name)
     m = _build(fx).eval()
     kind, inp = fx["kind"], fx["inputs"]
-    with torch.no_grad(), fp32.parity_mode():
+    with torch.no_grad(), fp32.parity_mode(terms=terms):
         if kind in ("GRU", "ResNet", "TemporalConvNet"):
             out = m(inp["x"].cuda())
         elif kind == "AttFusion":
@@ -1078,18 +1078,26 @@ def case_golden_fp32(name):
             out = m((inp["video_u8"].float().cuda() - 127.5) / 127.5, se, se)
         else:
             out = m(ref_batch(inp, "cuda"))
-    errs = {"out_ref32": _err(out, fx["out"])}
+    sfx = "" if terms == 3 else "x6"
+    errs = {"out_ref32" + sfx: _err(out, fx["out"])}
     if kind == "AffWild2VA":
         sl = slice(7, None) if "mtl" in fx["hparams"]["loss"] else slice(-2, None)
-        errs["va_ref32"] = _err(out[..., sl], fx["out"][..., sl])
+        errs["va_ref32" + sfx] = _err(out[..., sl], fx["out"][..., sl])
     return errs
 
 
 for _n in ("gru_audio", "gru_scorer", "gru_nohead", "attfusion", "tcn", "resnet_trunk_eval", "va3dresnet_eval",
            "av_resnet_attention_eval", "vggm_split3_eval", "av_v2psplit_attention_eval"):
     CASES["fp32_" + _n] = (case_golden_fp32, _c(name=_n))
+# six-term variant (three bf16 pieces per value): removes the 2^-16 representation / dropped-term error; what remains is
+# the tensor core's per-MMA truncation of the fp32 accumulator on the main term (measured: V/A 5.0e-5 -> 1.1e-5 on the
+# AV-ResNet fixture, no change on the K = 13824 VGG-M convolutions)
+for _n in ("vggm_split3_eval", "av_resnet_attention_eval", "av_v2psplit_attention_eval"):
+    CASES["fp32x6_" + _n] = (case_golden_fp32, _c(name=_n, terms=6))
 TOLS["out_ref32"] = 1e-4
 TOLS["va_ref32"] = 1e-4
+TOLS["out_ref32x6"] = 5e-5
+TOLS["va_ref32x6"] = 3e-5
 
 
 def case_train_trajectory(steps=4, clips=4, lr=2e-4, seed=0):
