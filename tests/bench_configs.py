@@ -154,6 +154,27 @@ def main():
         out.append({"config": 5, "what": "AV attention eval 16 clips x T=%d (resnet backbone)" % T, "ms": ms,
                     "frames_per_s": 16 * T / ms * 1e3, "launches": nl})
         del m, b
+    # CUDA-graph replay of the launch-bound small-batch forwards (m3t_b200.graphs)
+    from m3t_b200.graphs import GraphedInference
+    torch.manual_seed(12345)
+    m = VA_3DResNet(hiddenDim=512, frameLen=16, backend='gru', resnet_ver='v1', nClasses=9, nFCs=2)
+    randomise_bn(m, 7)
+    m = m.cuda().eval()
+    x = (torch.randint(0, 256, (2, 3, 16, 112, 112)).float().cuda() - 127.5) / 127.5
+    g = GraphedInference(m, x)
+    ms, nl = timed(lambda: g(x))
+    out.append({"config": 1, "what": "VA_3DResNet eval fwd 2x16, CUDA-graph replay", "ms": ms,
+                "frames_per_s": 32 / ms * 1e3, "launches": nl})
+    torch.manual_seed(12345)
+    m = AffWild2VA(hp())
+    randomise_bn(m, 7)
+    m = m.cuda().eval()
+    b = av_batch(32, 32)
+    g = GraphedInference(m, b)
+    ms, nl = timed(lambda: g(b))
+    out.append({"config": 3, "what": "AV attention inference 32x32, backbone resnet, CUDA-graph replay", "ms": ms,
+                "frames_per_s": 1024 / ms * 1e3, "launches": nl})
+    del m, b, g
     # fp32-parity mode (m3t_b200.fp32): configs 1 and 3 (resnet backbone) again with float32 activations and
     # split-operand tensor-core launches
     from m3t_b200 import fp32

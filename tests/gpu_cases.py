@@ -1146,6 +1146,41 @@ for _i in range(4):
     TOLS["loss_step%d" % _i] = 1e-2
 
 
+def case_cuda_graph(seed=0):
+    """graphs.GraphedInference: the eval forward captured into a CUDA graph (tcgen05 / TMA / cooperative GRU launches
+    included) replays bit-identically to the eager path, also on inputs it was not captured with; AV model (dict
+    batch) and VA_3DResNet (tensor)."""
+    import bench as BN
+    from m3t_b200.graphs import GraphedInference
+    from m3t_b200.models.backbone import VA_3DResNet
+    from m3t_b200.models.model import AffWild2VA
+    errs = {}
+    torch.manual_seed(seed)
+    m = VA_3DResNet(hiddenDim=512, frameLen=16, backend="gru", resnet_ver="v1", nClasses=9, nFCs=2).cuda().eval()
+    BN.randomise_bn(m, 3)
+    x = (torch.randint(0, 256, (2, 3, 16, 112, 112)).float().cuda() - 127.5) / 127.5
+    x2 = torch.flip(x, dims=[0, 2]).contiguous()
+    with torch.no_grad():
+        y, y2 = m(x).clone(), m(x2).clone()
+    g = GraphedInference(m, x)
+    errs["graph_exact"] = float((g(x) != y).sum() + (g(x2) != y2).sum())
+    hp = BN.hparams()
+    m = AffWild2VA(hp).cuda().eval()
+    BN.randomise_bn(m, 5)
+    b1 = {k: v.cuda() for k, v in BN.synth_batch(2, 11, pin=False).items()}
+    b2 = {k: v.cuda() for k, v in BN.synth_batch(2, 12, pin=False).items()}
+    with torch.no_grad():
+        y, y2 = m(b1).clone(), m(b2).clone()
+    g = GraphedInference(m, b1)
+    errs["graph_exact_av"] = float((g(b1) != y).sum() + (g(b2) != y2).sum())
+    return errs
+
+
+CASES["cuda_graph_inference"] = (case_cuda_graph, _c())
+TOLS["graph_exact"] = 0.5
+TOLS["graph_exact_av"] = 0.5
+
+
 def case_video_input(seed=0):
     """On-device input pipeline: m3t_video_augment_prep_s2d_w4 on decoded uint8 frames + parameter rows vs the layout
     pass applied to the clips the reference's load_video produced (golden), bit for bit; and the visual stream fed
