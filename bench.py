@@ -322,7 +322,7 @@ def run_b200(args, rank, local_rank, world):
         roof = None
         if dom_key:
             d = conv[dom_key]
-            roof = {"bound": "tensor", "kernel": "umma_kernel (tcgen05 implicit GEMM): " + dom_key,
+            roof = {"bound": "tensor", "kernel": "tcgen05 implicit GEMM: " + dom_key,
                     "achieved": d["tflops"], "peak": peak, "unit": "TFLOP/s", "frac": d["tflops"] / peak,
                     "traffic": NCU_DRAM_TRAFFIC_256.get(dom_key) if args.clips == 256 else None,
                     "peak_source": peak_src,
