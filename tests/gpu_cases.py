@@ -1183,6 +1183,49 @@ TOLS["graph_exact"] = 0.5
 TOLS["graph_exact_av"] = 0.5
 
 
+def case_fullsize_properties(clips=256, seed=0):
+    """Size-independent properties at the BASELINE config-4 size (256 clips x 16 frames, too large for the CPU oracle):
+      * batch independence (eval): the predictions of the first 4 clips inside the 256-clip batch equal, bit for bit,
+        those of the same 4 clips run alone (every output element has a fixed summation order; no cross-clip op);
+      * determinism: two runs of the 256-clip forward are bit-identical;
+      * exact power-of-two linearity of the tensor-core stem at full size: conv(2x) == 2 conv(x) in bf16;
+      * training step: the loss of the 256-clip batch is finite and the gradient arena has no NaN / Inf."""
+    import bench as BN
+    from m3t_b200 import raw
+    from m3t_b200.engine import TrainEngine
+    from m3t_b200.models.model import AffWild2VA
+    hp = BN.hparams()
+    torch.manual_seed(12345 + seed)
+    m = AffWild2VA(hp)
+    BN.randomise_bn(m, 7)
+    m = m.cuda().eval()
+    batch = {k: v.cuda() for k, v in BN.synth_batch(clips, 77 + seed, pin=False).items()}
+    small = {k: v[:4].contiguous() for k, v in batch.items()}
+    errs = {}
+    with torch.no_grad():
+        big = m(batch)
+        big2 = m(batch)
+        sub = m(small)
+    errs["batch_indep_exact"] = float((big[:4] != sub).sum())
+    errs["determinism_exact"] = float((big != big2).sum())
+    xs = raw.video_prep_s2d_w4(batch["video"], True)
+    w = (torch.randn(64, 1280, device="cuda") * 0.03).bfloat16()
+    y1 = raw.stem_fprop_halo(xs, w)
+    y2 = raw.stem_fprop_halo((xs.float() * 2).bfloat16(), w)
+    errs["pow2_linearity_exact"] = float(((y1.float() * 2).bfloat16().view(torch.int16) != y2.view(torch.int16)).sum())
+    del xs, y1, y2, big, big2
+    m.train()
+    eng = TrainEngine(m, lr=5e-5, weight_decay=1e-4, clip=1.0)
+    loss = eng.step(batch)
+    errs["train_nonfinite"] = float((~torch.isfinite(eng.flat_g)).sum() + (~torch.isfinite(loss)).sum())
+    return errs
+
+
+CASES["fullsize_256clips_properties"] = (case_fullsize_properties, _c())
+for _k in ("batch_indep_exact", "determinism_exact", "pow2_linearity_exact", "train_nonfinite"):
+    TOLS[_k] = 0.5
+
+
 def case_video_input(seed=0):
     """On-device input pipeline: m3t_video_augment_prep_s2d_w4 on decoded uint8 frames + parameter rows vs the layout
     pass applied to the clips the reference's load_video produced (golden), bit for bit; and the visual stream fed
