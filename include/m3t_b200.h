@@ -99,7 +99,9 @@ int m3t_stem_fprop_halo(const void* xs, const void* w_packed, void* y, int B, in
  * TMEM, one atomic flush.  dw_packed is fp32, caller-zeroed, same packed layout as m3t_conv_wgrad_bf16.
  *   m3t_wgrad3x3_c64_halo : 3x3/s1/p1, 64->64, x/dy bf16 [F][H][W][64], dw_packed [64][9*64]   (ResNet layer1)
  *   m3t_wgrad_stem_halo   : stem over the W-unrolled s2d image xs [B][T][H2][W2][64], dy [B*T][H2][W2][64],
- *                           dw_packed [64][20*64] with tap = kt*4 + jh                         (models/backbone.py:328) */
+ *                           dw_packed [64][20*64] with tap = kt*4 + jh                         (models/backbone.py:328);
+ *                           the activation box of an input frame stays in shared memory while the dY boxes of every
+ *                           output frame that reads it stream through (two passes over the temporal taps) */
 int m3t_wgrad3x3_c64_halo(const void* x, const void* dy, float* dw_packed, int F, int H, int W, void* stream);
 int m3t_wgrad_stem_halo(const void* xs, const void* dy, float* dw_packed, int B, int T, int H2, int W2, void* stream);
 

@@ -1,7 +1,7 @@
 // Weight gradient of the 64-channel convolutions as a persistent, halo-tile tcgen05 kernel:
 //   * ResNet layer1  3x3/s1/p1  64 -> 64  over [F][H][W][64]                      (9 taps, one launch)
-//   * the stem over the W-unrolled space-to-depth image  (5,4,1) x 64 -> 64        (5 launches: one per temporal tap,
-//     4 vertical taps each)
+//   * the stem over the W-unrolled space-to-depth image  (5,4,1) x 64 -> 64        (activation box resident over the
+//     temporal taps, two passes: wgrad_stem_xres_kernel; fallback: one launch per temporal tap)
 // The generic wgrad (umma_kernel.cuh, A_WGRAD) re-reads a 64-pixel activation tile from L2 once per filter tap: 200 KB
 // of L2->SM traffic per 64 pixels for the stem, i.e. L2-bound at ~150 TFLOP/s.  Here a K-block is TR whole image rows;
 // ONE TMA box brings the activation halo (TR+3 rows, zero padding by out-of-bounds fill) and ONE box brings dY in the
@@ -378,7 +378,8 @@ extern "C" int m3t_wgrad3x3_c64_halo(const void* x, const void* dy, float* dw_pa
 }
 
 // Stem: xs bf16 [B][T][H2][W2][64] (W-unrolled space-to-depth), dy bf16 [B*T][H2][W2][64];
-// dw_packed fp32 [64][20*64] (tap = kt*4 + jh) += .  Five launches, one per temporal tap kt.
+// dw_packed fp32 [64][20*64] (tap = kt*4 + jh) += .  Two activation-resident passes (M3T_STEM_WGRAD_SPLIT taps each,
+// default 3 + 2); falls back to five launches, one per temporal tap kt, when the boxes do not fit.
 extern "C" int m3t_wgrad_stem_halo(const void* xs, const void* dy, float* dw_packed, int B, int T, int H2, int W2,
                                    void* stream) {
   if (B <= 0 || T <= 0 || H2 <= 0 || W2 <= 0 || W2 > 256) return -1;
