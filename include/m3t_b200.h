@@ -216,10 +216,11 @@ int m3t_gru_fwd(const float* gi, const void* w_hh_bf16, const float* b_hh, void*
 int m3t_gru_pack_weights(const float* w_ih, const float* w_ih_r, const float* w_hh, const float* w_hh_r, void* wih,
                          void* whh, void* whht, int I, int Ipad, int H, void* stream);
 /* BPTT: dgi, dgh bf16 [B*T][2][3H] (gradients wrt the input / hidden pre-activations) and hprev bf16 [B*T][2][H]
- * (h_{t-1}, zero at the sequence start); w_hh_t_bf16 = bf16 [2][H][3H] (W_hh transposed).  The weight / bias /
- * input gradients follow as GEMMs and column sums over these. */
+ * (h_{t-1}, zero at the sequence start); w_hh_t_bf16 = bf16 [2][H][3H] (W_hh transposed).  dbias (optional, caller-
+ * zeroed) fp32 [2][2][3H] += the bias gradients (b_ih | b_hh) x direction = column sums of the fp32 gate gradients over
+ * (b, t).  The weight / input gradients follow as GEMMs over dgi / dgh. */
 int m3t_gru_bwd(const void* dout_bf16, const void* out_bf16, const float* saved, const void* w_hh_t_bf16,
-                void* dgi_bf16, void* dgh_bf16, void* hprev_bf16, unsigned* counters, int B, int T, int H,
+                void* dgi_bf16, void* dgh_bf16, void* hprev_bf16, unsigned* counters, float* dbias, int B, int T, int H,
                 void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------

@@ -98,6 +98,7 @@ struct GruParams {
   __nv_bfloat16* hprev;         // [B*T][2][H]   h_{t-1} copy (zero at sequence start) for the dW_hh GEMM
   unsigned* counters;           // [2][nslices_b] zero-initialised
   int nbslices;                 // number of batch slices
+  float* dbias;                 // bwd, optional: [2 (ih, hh)][2 dirs][3H] fp32 += column sums of dgi / dgh (bias grads)
 };
 
 // ------------------------------------------------------------------------------------------------------------
@@ -264,6 +265,10 @@ __global__ void __launch_bounds__(kGruThreads, 1) gru_bwd_kernel(const GruParams
     for (int e = 0; e < 4; ++e) dhrec[s][e] = 0.f;
   __syncthreads();
 
+  // bias gradients = column sums of the gate gradients over (b, t): per-thread partials for the two hidden units this
+  // thread owns (e & 1), reduced over the warp's rows and added atomically once, after the last step
+  float sb_r[2] = {0.f, 0.f}, sb_z[2] = {0.f, 0.f}, sb_n[2] = {0.f, 0.f}, sb_nr[2] = {0.f, 0.f};
+
   for (int step = 0; step < T; ++step) {
     const int t = dir == 0 ? T - 1 - step : step;       // reverse of the forward order
     const int tprev = dir == 0 ? t - 1 : t + 1;         // time index of h_{prev} in forward order
@@ -294,6 +299,10 @@ __global__ void __launch_bounds__(kGruThreads, 1) gru_bwd_kernel(const GruParams
           const float daz = dz * z * (1.f - z);
           const float dar = dan * hn * r * (1.f - r);
           const long long g0 = row * 6 * H + dir * 3 * H + j;
+          sb_r[e & 1] += dar;
+          sb_z[e & 1] += daz;
+          sb_n[e & 1] += dan;
+          sb_nr[e & 1] += dan * r;
           p.dgi[g0] = __float2bfloat16(dar);
           p.dgi[g0 + H] = __float2bfloat16(daz);
           p.dgi[g0 + 2 * H] = __float2bfloat16(dan);
@@ -335,6 +344,33 @@ __global__ void __launch_bounds__(kGruThreads, 1) gru_bwd_kernel(const GruParams
 #pragma unroll
       for (int e = 0; e < 4; ++e) dhrec[si][e] = dh_direct[si][e] + acc[e];
       __syncthreads();  // gsm is rewritten by the next slice / step
+    }
+  }
+  if (p.dbias) {
+    // lanes with equal (lane & 3) own the same two hidden units on different rows: butterfly over lane bits 2..4
+#pragma unroll
+    for (int jj = 0; jj < 2; ++jj) {
+#pragma unroll
+      for (int o = 4; o < 32; o <<= 1) {
+        sb_r[jj] += __shfl_xor_sync(0xffffffffu, sb_r[jj], o);
+        sb_z[jj] += __shfl_xor_sync(0xffffffffu, sb_z[jj], o);
+        sb_n[jj] += __shfl_xor_sync(0xffffffffu, sb_n[jj], o);
+        sb_nr[jj] += __shfl_xor_sync(0xffffffffu, sb_nr[jj], o);
+      }
+    }
+    if (lane < 4) {
+      float* bih = p.dbias + (long long)dir * 3 * H;            // [ih][dir][3H]
+      float* bhh = p.dbias + (long long)(2 + dir) * 3 * H;      // [hh][dir][3H]
+#pragma unroll
+      for (int jj = 0; jj < 2; ++jj) {
+        const int j = js * kJS + ncol + lane * 2 + jj;
+        atomicAdd(bih + j, sb_r[jj]);
+        atomicAdd(bih + H + j, sb_z[jj]);
+        atomicAdd(bih + 2 * H + j, sb_n[jj]);
+        atomicAdd(bhh + j, sb_r[jj]);
+        atomicAdd(bhh + H + j, sb_z[jj]);
+        atomicAdd(bhh + 2 * H + j, sb_nr[jj]);
+      }
     }
   }
 }
@@ -384,8 +420,8 @@ extern "C" int m3t_gru_fwd(const float* gi, const void* w_hh_bf16, const float* 
 }
 
 extern "C" int m3t_gru_bwd(const void* dout_bf16, const void* out_bf16, const float* saved, const void* w_hh_t_bf16,
-                           void* dgi_bf16, void* dgh_bf16, void* hprev_bf16, unsigned* counters, int B, int T, int H,
-                           void* stream) {
+                           void* dgi_bf16, void* dgh_bf16, void* hprev_bf16, unsigned* counters, float* dbias, int B,
+                           int T, int H, void* stream) {
   GruParams p;
   memset(&p, 0, sizeof(p));
   p.B = B; p.T = T; p.H = H;
@@ -397,5 +433,6 @@ extern "C" int m3t_gru_bwd(const void* dout_bf16, const void* out_bf16, const fl
   p.dgh = reinterpret_cast<__nv_bfloat16*>(dgh_bf16);
   p.hprev = reinterpret_cast<__nv_bfloat16*>(hprev_bf16);
   p.counters = counters;
+  p.dbias = dbias;
   return gru_launch(false, p, stream);
 }

@@ -523,14 +523,13 @@ class GRULayerFn(torch.autograd.Function):
         B, T, I, H = ctx.dims
 
         wih, _, whht = _gru_packed(w_ih, w_ih_r, w_hh, w_hh_r, I, H)
-        dgi, dgh, hprev = raw.gru_bwd(dout.contiguous(), out, saved, whht, B, T, H)
+        dgi, dgh, hprev, dbias = raw.gru_bwd(dout.contiguous(), out, saved, whht, B, T, H)
         dx = None
         if ctx.needs_input_grad[0]:
             dxp = raw.gemm(dgi, wih, b_mn=True, out_dtype=torch.bfloat16)              # [B*T, Ipad]
             dx = (dxp if dxp.shape[1] == I else dxp[:, :I].contiguous()).view(B, T, I)
         dwih = raw.gemm(dgi, x2, a_mn=True, b_mn=True, out_dtype=torch.float32)      # [6H, I]
-        dbih = raw.colsum(dgi)
-        dbhh = raw.colsum(dgh)
+        dbih, dbhh = dbias[0], dbias[1]      # reduced inside the BPTT kernel from the fp32 gate gradients
         dwhh = []
         for d in range(2):
             dwhh.append(raw.gemm(dgh[:, d * 3 * H:(d + 1) * 3 * H], hprev[:, d * H:(d + 1) * H], a_mn=True, b_mn=True,

@@ -569,9 +569,11 @@ def gru_bwd(dout, out, saved, w_hh_t_bf16, B, T, H):
     dgh = torch.empty((B * T, 6 * H), device=dev, dtype=torch.bfloat16)
     hprev = torch.empty((B * T, 2 * H), device=dev, dtype=torch.bfloat16)
     counters = torch.empty((2 * ((B + 31) // 32) + 2,), device=dev, dtype=torch.int32)
+    dbias = torch.zeros((2, 6 * H), device=dev, dtype=torch.float32)     # [b_ih | b_hh] x [dir0 3H | dir1 3H]
     L.check(_lib().m3t_gru_bwd(L.ptr(dout), L.ptr(out), L.ptr(saved), L.ptr(w_hh_t_bf16), L.ptr(dgi), L.ptr(dgh),
-                               L.ptr(hprev), L.ptr(counters), L.i32(B), L.i32(T), L.i32(H), L.stream_ptr()), "gru_bwd")
-    return dgi, dgh, hprev
+                               L.ptr(hprev), L.ptr(counters), L.ptr(dbias), L.i32(B), L.i32(T), L.i32(H),
+                               L.stream_ptr()), "gru_bwd")
+    return dgi, dgh, hprev, dbias
 
 
 def att_mix_fwd(x_a, x_v, s_a, s_v):
