@@ -212,9 +212,11 @@ int m3t_gru_fwd(const float* gi, const void* w_hh_bf16, const float* b_hh, void*
                 float* saved, unsigned* counters, int B, int T, int H, void* stream);
 /* The bf16 weight copies of one bidirectional layer in one launch (rebuilt after every optimizer step):
  * wih bf16 [6H][Ipad] = [W_ih ; W_ih_reverse] zero-padded to Ipad columns, whh bf16 [2][3H][H], whht bf16 [2][H][3H]
- * (W_hh transposed, for m3t_gru_bwd; may be NULL).  Inputs are the nn.GRU parameters (models/rnn.py:17). */
+ * (W_hh transposed, for m3t_gru_bwd; may be NULL); bias fp32 [2][6H] = [b_ih ; b_ih_reverse], [b_hh ; b_hh_reverse]
+ * (optional, with the four bias vectors).  Inputs are the nn.GRU parameters (models/rnn.py:17). */
 int m3t_gru_pack_weights(const float* w_ih, const float* w_ih_r, const float* w_hh, const float* w_hh_r, void* wih,
-                         void* whh, void* whht, int I, int Ipad, int H, void* stream);
+                         void* whh, void* whht, int I, int Ipad, int H, const float* b_ih, const float* b_ih_r,
+                         const float* b_hh, const float* b_hh_r, float* bias, void* stream);
 /* BPTT: dgi, dgh bf16 [B*T][2][3H] (gradients wrt the input / hidden pre-activations) and hprev bf16 [B*T][2][H]
  * (h_{t-1}, zero at the sequence start); w_hh_t_bf16 = bf16 [2][H][3H] (W_hh transposed).  dbias (optional, caller-
  * zeroed) fp32 [2][2][3H] += the bias gradients (b_ih | b_hh) x direction = column sums of the fp32 gate gradients over

@@ -1111,12 +1111,23 @@ __global__ void patch3x3_c1_kernel(const float* __restrict__ x, __nv_bfloat16* _
 //   wih  [6H][Ipad]   = [W_ih ; W_ih_reverse] (columns >= I zero)      input projection, both directions
 //   whh  [2][3H][H]   = W_hh per direction                               forward recurrence
 //   whht [2][H][3H]   = W_hh^T per direction                             BPTT recurrence
+//   bias [2][6H] fp32 = [b_ih ; b_ih_reverse], [b_hh ; b_hh_reverse] (optional)
 __global__ void gru_pack_weights_kernel(const float* __restrict__ w_ih, const float* __restrict__ w_ih_r,
                                         const float* __restrict__ w_hh, const float* __restrict__ w_hh_r,
                                         __nv_bfloat16* __restrict__ wih, __nv_bfloat16* __restrict__ whh,
-                                        __nv_bfloat16* __restrict__ whht, int I, int Ipad, int H) {
+                                        __nv_bfloat16* __restrict__ whht, int I, int Ipad, int H,
+                                        const float* __restrict__ b_ih, const float* __restrict__ b_ih_r,
+                                        const float* __restrict__ b_hh, const float* __restrict__ b_hh_r,
+                                        float* __restrict__ bias) {
   const long long n_ih = 6LL * H * Ipad, n_hh = 6LL * H * H;
   const long long total = n_ih + n_hh;
+  if (bias) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 12 * H; i += gridDim.x * blockDim.x) {
+      const int which = i / (6 * H), r = i - which * 6 * H;
+      const float* src = which == 0 ? (r < 3 * H ? b_ih : b_ih_r) : (r < 3 * H ? b_hh : b_hh_r);
+      bias[i] = src[r < 3 * H ? r : r - 3 * H];
+    }
+  }
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     if (i < n_ih) {
@@ -1402,11 +1413,15 @@ extern "C" int m3t_cast_bf16_f32(const void* in, long long ld_in, float* out, lo
 }
 
 extern "C" int m3t_gru_pack_weights(const float* w_ih, const float* w_ih_r, const float* w_hh, const float* w_hh_r,
-                                    void* wih, void* whh, void* whht, int I, int Ipad, int H, void* stream) {
+                                    void* wih, void* whh, void* whht, int I, int Ipad, int H, const float* b_ih,
+                                    const float* b_ih_r, const float* b_hh, const float* b_hh_r, float* bias,
+                                    void* stream) {
   if (I <= 0 || H <= 0 || Ipad < I) return -1;
+  if (bias && !(b_ih && b_ih_r && b_hh && b_hh_r)) return -1;
   const long long total = 6LL * H * Ipad + 6LL * H * H;
   gru_pack_weights_kernel<<<ew_blocks(total), kEwThreads, 0, ST(stream)>>>(w_ih, w_ih_r, w_hh, w_hh_r, BF(wih), BF(whh),
-                                                                          BF(whht), I, Ipad, H);
+                                                                          BF(whht), I, Ipad, H, b_ih, b_ih_r, b_hh,
+                                                                          b_hh_r, bias);
   count_launch();
   return launch_status();
 }

@@ -483,18 +483,20 @@ def linear(x, w, b, relu=False, out_f32=False):
     return LinearFn.apply(as_bf16(x), w, b, relu, out_f32)
 
 
-def _gru_packed(w_ih, w_ih_r, w_hh, w_hh_r, I, H):
-    """(wih [6H, Ipad], whh [2,3H,H], whht [2,H,3H]) bf16 copies of one bidirectional layer, one launch, cached until
-    the parameters change."""
+def _gru_packed(w_ih, w_ih_r, w_hh, w_hh_r, I, H, biases):
+    """(wih [6H, Ipad], whh [2,3H,H], whht [2,H,3H]) bf16 copies of one bidirectional layer and, given the four bias
+    vectors, bias fp32 [2, 6H] = ([b_ih ; b_ih_r], [b_hh ; b_hh_r]): one launch, cached until the parameters change."""
     def make():
         Ipad = (I + 7) // 8 * 8
         dev = w_ih.device
         wih = torch.empty((6 * H, Ipad), device=dev, dtype=torch.bfloat16)
         whh = torch.empty((2, 3 * H, H), device=dev, dtype=torch.bfloat16)
         whht = torch.empty((2, H, 3 * H), device=dev, dtype=torch.bfloat16)
-        raw.gru_pack_weights(w_ih.detach(), w_ih_r.detach(), w_hh.detach(), w_hh_r.detach(), wih, whh, whht, I, Ipad, H)
-        return wih, whh, whht
-    return _cached_multi((w_ih, w_ih_r, w_hh, w_hh_r), "gru_w", make)
+        bias = torch.empty((2, 6 * H), device=dev, dtype=torch.float32)
+        raw.gru_pack_weights(w_ih.detach(), w_ih_r.detach(), w_hh.detach(), w_hh_r.detach(), wih, whh, whht, I, Ipad, H,
+                             [b.detach() for b in biases], bias)
+        return wih, whh, whht, bias
+    return _cached_multi((w_ih, w_ih_r, w_hh, w_hh_r) + tuple(biases), "gru_w", make)
 
 
 class GRULayerFn(torch.autograd.Function):
@@ -507,22 +509,21 @@ class GRULayerFn(torch.autograd.Function):
         H = w_hh.shape[1]
         x2 = x.contiguous().view(B * T, I)
 
-        wih, whh, _ = _gru_packed(w_ih, w_ih_r, w_hh, w_hh_r, I, H)
-        bih = torch.cat((b_ih.detach(), b_ih_r.detach()))
-        bhh = torch.cat((b_hh.detach(), b_hh_r.detach()))
+        wih, whh, _, bias = _gru_packed(w_ih, w_ih_r, w_hh, w_hh_r, I, H, (b_ih, b_ih_r, b_hh, b_hh_r))
+        bih, bhh = bias[0], bias[1]
         gi = raw.gemm(x2, wih, shift=bih, out_dtype=torch.float32)
         out, _, saved = raw.gru_fwd(gi, whh, bhh, B, T, H, training)
         if training:
-            ctx.save_for_backward(x2, out, saved, w_ih, w_hh, w_ih_r, w_hh_r)
+            ctx.save_for_backward(x2, out, saved, w_ih, w_hh, w_ih_r, w_hh_r, b_ih, b_ih_r, b_hh, b_hh_r)
             ctx.dims = (B, T, I, H)
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        x2, out, saved, w_ih, w_hh, w_ih_r, w_hh_r = ctx.saved_tensors
+        x2, out, saved, w_ih, w_hh, w_ih_r, w_hh_r, b_ih, b_ih_r, b_hh, b_hh_r = ctx.saved_tensors
         B, T, I, H = ctx.dims
 
-        wih, _, whht = _gru_packed(w_ih, w_ih_r, w_hh, w_hh_r, I, H)
+        wih, _, whht, _ = _gru_packed(w_ih, w_ih_r, w_hh, w_hh_r, I, H, (b_ih, b_ih_r, b_hh, b_hh_r))   # cache hit
         dgi, dgh, hprev, dbias = raw.gru_bwd(dout.contiguous(), out, saved, whht, B, T, H)
         dx = None
         if ctx.needs_input_grad[0]:

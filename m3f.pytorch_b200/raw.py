@@ -488,11 +488,13 @@ def pack_filter(w, want_dgrad):
     return wf, wd
 
 
-def gru_pack_weights(w_ih, w_ih_r, w_hh, w_hh_r, wih, whh, whht, I, Ipad, H):
-    for t in (w_ih, w_ih_r, w_hh, w_hh_r):
+def gru_pack_weights(w_ih, w_ih_r, w_hh, w_hh_r, wih, whh, whht, I, Ipad, H, biases=None, bias_out=None):
+    for t in (w_ih, w_ih_r, w_hh, w_hh_r) + tuple(biases or ()):
         assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()
+    b = list(biases) if biases else [None] * 4
     L.check(_lib().m3t_gru_pack_weights(L.ptr(w_ih), L.ptr(w_ih_r), L.ptr(w_hh), L.ptr(w_hh_r), L.ptr(wih), L.ptr(whh),
-                                        L.ptr(whht), L.i32(I), L.i32(Ipad), L.i32(H), L.stream_ptr()),
+                                        L.ptr(whht), L.i32(I), L.i32(Ipad), L.i32(H), L.ptr(b[0]), L.ptr(b[1]),
+                                        L.ptr(b[2]), L.ptr(b[3]), L.ptr(bias_out), L.stream_ptr()),
             "m3t_gru_pack_weights")
 
 
