@@ -130,7 +130,7 @@ class TrainEngine:
             self.flat_g.mul_(1.0 / self.world)
 
     def _allreduce_grads(self):
-        if self.world > 1:
+        if self.world > 1 and os.environ.get("M3T_DEBUG_SKIP_ALLREDUCE") != "1":   # debug knob: time a step without it
             dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM)
             if not self.on_gpu:
                 self.flat_g.mul_(1.0 / self.world)
