@@ -10,7 +10,6 @@ names, and its parity oracle is the same composition in plain PyTorch (tests/gpu
       -> TemporalConvNet(512,[512,512],3) over time   (models/tcn.py:49)          -> (B, T, 512)
       -> Linear(512, 2)                                                            -> (B, T, 2)  valence / arousal
 """
-import torch
 import torch.nn as nn
 
 from .. import ops

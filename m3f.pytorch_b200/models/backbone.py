@@ -6,7 +6,6 @@ channels-last (B*T, 28, 28, 64) bf16, which *is* the trunk's input layout.
 """
 import math
 
-import torch
 import torch.nn as nn
 
 from .. import fp32, ops
