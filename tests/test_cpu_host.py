@@ -126,3 +126,61 @@ def test_data_parallel_gradient_allreduce_gloo():
                        text=True, timeout=300)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert r.stdout.count("DP_OK") == 2, r.stdout[-2000:]
+
+
+def test_stride2_dgrad_parity_decomposition_host_logic():
+    """ops._parity_taps (which filter taps / paddings each output parity of a stride-2 data gradient uses) replayed with
+    plain CPU convolutions: the four scattered sub-convolutions must equal conv_transpose2d."""
+    import torch.nn.functional as F
+    from m3t_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    for (H, K, pad) in ((28, 3, 1), (7, 3, 1), (14, 1, 0), (7, 1, 0), (12, 7, 3)):
+        Cin, Cout, N = 3, 4, 2
+        P = (H + 2 * pad - K) // 2 + 1
+        w = torch.randn((Cout, Cin, K, K), generator=g)
+        dy = torch.randn((N, Cout, P, P), generator=g)
+        ref = F.conv_transpose2d(dy, w, stride=2, padding=pad, output_padding=H - ((P - 1) * 2 - 2 * pad + K))
+        # flipped dgrad pack [Cin][taps (flipped)][Cout], as m3t_pack_filter lays it out
+        wd = w.permute(1, 2, 3, 0).reshape(Cin, K * K, Cout).flip(1)
+        dx = torch.zeros((N, Cin, H, H))
+        for ph in range(2):
+            for pw in range(2):
+                tp = ops._parity_taps(K, pad, ph, pw, "cpu")
+                Ha, Wa = (H - ph + 1) // 2, (H - pw + 1) // 2
+                if tp is None or Ha == 0 or Wa == 0:
+                    continue
+                idx, nh, nw, plh, plw = tp
+                phh, pwh = Ha - P - plh + nh - 1, Wa - P - plw + nw - 1
+                assert min(phh, pwh, plh, plw) >= 0
+                wsub = wd.index_select(1, idx).reshape(Cin, nh, nw, Cout).permute(0, 3, 1, 2)   # [Cin][Cout][nh][nw]
+                sub = F.conv2d(F.pad(dy, (plw, pwh, plh, phh)), wsub)
+                assert sub.shape[-2:] == (Ha, Wa)
+                dx[:, :, ph::2, pw::2] = sub
+        assert (dx - ref).abs().max() < 1e-4, (H, K, pad, float((dx - ref).abs().max()))
+
+
+def test_split_operand_arithmetic_host_model():
+    """The arithmetic the fp32-parity mode relies on, modelled on the CPU: x = hi + lo with bf16 pieces, and
+    a.b ~= a_hi.b_hi + a_hi.b_lo + a_lo.b_hi with exact fp32 products - relative error ~2^-16 (three terms) and ~2^-23
+    (three pieces, six terms), against float64."""
+    g = torch.Generator().manual_seed(0)
+    a = torch.randn(64, 2048, generator=g)
+    b = torch.randn(32, 2048, generator=g)
+    ref = a.double() @ b.double().t()
+
+    def pieces(x, n):
+        out, r = [], x.clone()
+        for _ in range(n):
+            p = r.bfloat16().float()
+            out.append(p)
+            r = r - p
+        return out
+
+    a2, b2 = pieces(a, 2), pieces(b, 2)
+    assert (a - a2[0] - a2[1]).abs().max() <= a.abs().max() * 2.0 ** -16
+    three = sum((x.double() @ y.double().t()) for x, y in ((a2[0], b2[1]), (a2[1], b2[0]), (a2[0], b2[0])))
+    a3, b3 = pieces(a, 3), pieces(b, 3)
+    six = sum((a3[i].double() @ b3[j].double().t()) for i, j in ((0, 2), (1, 1), (2, 0), (0, 1), (1, 0), (0, 0)))
+    scale = ref.abs().max()
+    assert (three - ref).abs().max() / scale < 2.0 ** -14
+    assert (six - ref).abs().max() / scale < 2.0 ** -21
