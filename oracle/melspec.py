@@ -6,8 +6,10 @@ reference ships no vectors for it).  This file restates librosa's published algo
 reference makes -
     melspectrogram(y, sr=16000, n_fft=512, hop_length=hop, win_length=400, n_mels=40)   [center=True, hann,
     power=2.0, filters.mel(htk=False, norm='slaney', fmin=0, fmax=sr/2)] ;  power_to_db(ref=1.0, amin=1e-10, top_db=80)
-- in float64 numpy; `pad_mode` is 'constant' for librosa >= 0.10 and 'reflect' before.  tests/ cross-check it
-against torchaudio's MelSpectrogram(norm='slaney', mel_scale='slaney') + AmplitudeToDB where torchaudio imports.
+- in float64 numpy; `pad_mode` is 'constant' for librosa >= 0.10 and 'reflect' before.  Pinned on the second-best
+anchor available: features recorded from torchaudio's MelSpectrogram(norm='slaney', mel_scale='slaney') +
+AmplitudeToDB (tests/golden/logmel_torchaudio.pt, oracle/make_golden_logmel.py; agreement < 1e-3 dB), an independent
+implementation of the same published algorithm - not librosa itself, hence still "unpinned" in the strict sense.
 """
 import math
 

@@ -710,7 +710,22 @@ def case_logmel(seed=0):
     return errs
 
 
+def case_logmel_golden():
+    """Fused log-Mel kernel vs features recorded from torchaudio (tests/golden/logmel_torchaudio.pt)."""
+    from m3t_b200.process import extract_melspec as P
+    fx = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "logmel_torchaudio.pt"))
+    errs = {}
+    for c in fx:
+        got = P.melspectrogram_db(c["wave"].cuda(), c["fps"], pad_mode=c["pad_mode"]).cpu()
+        assert got.shape == c["logmel_db"].shape
+        errs["ta_%s_db_abs" % c["pad_mode"]] = float((got - c["logmel_db"]).abs().max())
+    return errs
+
+
 CASES["logmel"] = (case_logmel, _c())
+CASES["logmel_torchaudio_golden"] = (case_logmel_golden, _c())
+TOLS["ta_constant_db_abs"] = 2e-2      # dB
+TOLS["ta_reflect_db_abs"] = 2e-2
 for _k in ("fps30_db_abs", "fps25_reflect_db_abs"):
     TOLS[_k] = 2e-2      # dB
 

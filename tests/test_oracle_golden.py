@@ -168,3 +168,15 @@ def test_video_input_oracle_vs_reference_golden():
     for c in clips:
         seq = VI.assemble_clip(c["frames"].numpy(), *c["params"][:7])
         assert seq.dtype == np.float32 and np.array_equal(seq, c["seq"].float().numpy())
+
+
+def test_logmel_oracle_vs_torchaudio_golden():
+    """oracle/melspec.py against log-Mel features recorded from torchaudio (tests/golden/logmel_torchaudio.pt,
+    oracle/make_golden_logmel.py) - an independent implementation of the librosa call the reference makes."""
+    import numpy as np
+    from oracle import melspec as OM
+    fx = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "logmel_torchaudio.pt"))
+    for c in fx:
+        got = OM.logmel(c["wave"].numpy(), c["fps"], pad_mode=c["pad_mode"])
+        assert got.shape == tuple(c["logmel_db"].shape)
+        assert np.abs(got - c["logmel_db"].numpy()).max() < 1e-3       # dB
