@@ -73,12 +73,16 @@ def gemm(A, B, a_mn=False, b_mn=False, out_dtype=torch.bfloat16, scale=None, shi
     if out is None:
         out = torch.empty((M, N), device=A.device, dtype=out_dtype)
     assert out.dtype in (torch.bfloat16, torch.float32) and out.stride(1) == 1
-    rc = L.load().m3t_gemm_bf16(
-        L.ptr(A), L.i64(A.stride(0)), L.i32(a_mn), L.ptr(B), L.i64(B.stride(0)), L.i32(b_mn), L.ptr(out),
-        L.i64(out.stride(0)), L.i32(out.dtype == torch.float32), L.i32(M), L.i32(N), L.i32(K), L.ptr(scale),
-        L.ptr(shift), L.ptr(residual), L.i64(residual.stride(0) if residual is not None else 0), L.i32(relu),
-        L.ptr(stats), L.stream_ptr())
-    L.check(rc, "m3t_gemm_bf16")
+    def run():
+        rc = L.load().m3t_gemm_bf16(
+            L.ptr(A), L.i64(A.stride(0)), L.i32(a_mn), L.ptr(B), L.i64(B.stride(0)), L.i32(b_mn), L.ptr(out),
+            L.i64(out.stride(0)), L.i32(out.dtype == torch.float32), L.i32(M), L.i32(N), L.i32(K), L.ptr(scale),
+            L.ptr(shift), L.ptr(residual), L.i64(residual.stride(0) if residual is not None else 0), L.i32(relu),
+            L.ptr(stats), L.stream_ptr())
+        L.check(rc, "m3t_gemm_bf16")
+
+    # GEMM launches are recorded without a FLOP credit: bench.py's roofline / conv aggregate stay convolution-only
+    _timed("gemm %dx%dx%d" % (M, N, K), 0.0, run)
     return out
 
 
@@ -560,8 +564,9 @@ def gru_fwd(gi, w_hh_bf16, b_hh, B, T, H, want_saved, want_f32=False):
     out32 = torch.empty((B, T, 2 * H), device=dev, dtype=torch.float32) if want_f32 else None
     saved = torch.empty((B * T, 2, 4, H), device=dev, dtype=torch.float32) if want_saved else None
     counters = torch.empty((2 * ((B + 31) // 32) + 2,), device=dev, dtype=torch.int32)
-    L.check(_lib().m3t_gru_fwd(L.ptr(gi), L.ptr(w_hh_bf16), L.ptr(b_hh), L.ptr(out), L.ptr(out32), L.ptr(saved),
-                               L.ptr(counters), L.i32(B), L.i32(T), L.i32(H), L.stream_ptr()), "gru_fwd")
+    _timed("gru_fwd B%d T%d H%d" % (B, T, H), 0.0, lambda: L.check(
+        _lib().m3t_gru_fwd(L.ptr(gi), L.ptr(w_hh_bf16), L.ptr(b_hh), L.ptr(out), L.ptr(out32), L.ptr(saved),
+                           L.ptr(counters), L.i32(B), L.i32(T), L.i32(H), L.stream_ptr()), "gru_fwd"))
     return out, out32, saved
 
 
@@ -572,9 +577,10 @@ def gru_bwd(dout, out, saved, w_hh_t_bf16, B, T, H):
     hprev = torch.empty((B * T, 2 * H), device=dev, dtype=torch.bfloat16)
     counters = torch.empty((2 * ((B + 31) // 32) + 2,), device=dev, dtype=torch.int32)
     dbias = torch.zeros((2, 6 * H), device=dev, dtype=torch.float32)     # [b_ih | b_hh] x [dir0 3H | dir1 3H]
-    L.check(_lib().m3t_gru_bwd(L.ptr(dout), L.ptr(out), L.ptr(saved), L.ptr(w_hh_t_bf16), L.ptr(dgi), L.ptr(dgh),
-                               L.ptr(hprev), L.ptr(counters), L.ptr(dbias), L.i32(B), L.i32(T), L.i32(H),
-                               L.stream_ptr()), "gru_bwd")
+    _timed("gru_bwd B%d T%d H%d" % (B, T, H), 0.0, lambda: L.check(
+        _lib().m3t_gru_bwd(L.ptr(dout), L.ptr(out), L.ptr(saved), L.ptr(w_hh_t_bf16), L.ptr(dgi), L.ptr(dgh),
+                           L.ptr(hprev), L.ptr(counters), L.ptr(dbias), L.i32(B), L.i32(T), L.i32(H),
+                           L.stream_ptr()), "gru_bwd"))
     return dgi, dgh, hprev, dbias
 
 
@@ -582,8 +588,9 @@ def att_mix_fwd(x_a, x_v, s_a, s_v):
     C = x_a.shape[-1]
     rows = x_a.numel() // C
     f = torch.empty_like(x_a)
-    L.check(_lib().m3t_att_mix_fwd(L.ptr(x_a), L.ptr(x_v), L.ptr(s_a), L.ptr(s_v), L.ptr(f), L.ptr(None), L.i64(rows),
-                                   L.i32(C), L.stream_ptr()), "att_mix_fwd")
+    _timed("att_mix_fwd %dx%d" % (rows, C), 0.0, lambda: L.check(
+        _lib().m3t_att_mix_fwd(L.ptr(x_a), L.ptr(x_v), L.ptr(s_a), L.ptr(s_v), L.ptr(f), L.ptr(None), L.i64(rows),
+                               L.i32(C), L.stream_ptr()), "att_mix_fwd"))
     return f
 
 

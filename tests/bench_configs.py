@@ -151,8 +151,22 @@ def main():
         b = av_batch(16, T)
         with torch.no_grad():
             ms, nl = timed(lambda: m(b), iters=5)
+            # per-class breakdown of one forward (temporal / fusion kernels reported separately)
+            from m3t_b200 import raw
+            prof = raw.KernelProfiler()
+            raw.set_profiler(prof)
+            m(b)
+            torch.cuda.synchronize()
+            raw.set_profiler(None)
+        cls = {"conv": 0.0, "gemm": 0.0, "gru_fwd": 0.0, "att_mix": 0.0}
+        for k, v in prof.summary().items():
+            key = "gru_fwd" if k.startswith("gru_fwd") else "att_mix" if k.startswith("att_mix") else \
+                "gemm" if k.startswith("gemm") else "conv"
+            cls[key] += v["ms_total"]
         out.append({"config": 5, "what": "AV attention eval 16 clips x T=%d (resnet backbone)" % T, "ms": ms,
-                    "frames_per_s": 16 * T / ms * 1e3, "launches": nl})
+                    "frames_per_s": 16 * T / ms * 1e3, "launches": nl,
+                    "ms_by_class": {k: round(v, 3) for k, v in cls.items()},
+                    "gru_us_per_step": round(cls["gru_fwd"] * 1e3 / (8 * T), 2)})
         del m, b
     # CUDA-graph replay of the launch-bound small-batch forwards (m3t_b200.graphs)
     from m3t_b200.graphs import GraphedInference
