@@ -1,34 +1,41 @@
-"""Task module (reference: models/model.py `AffWild2VA`): stream construction, forward, losses, training_step,
-optimiser.  It keeps the LightningModule hook names but does not need pytorch_lightning (absent in this image; if it
-is importable the class derives from it so the reference's train.py/eval.py can drive it).
+"""Task module (reference: models/model.py `AffWild2VA`): stream construction, forward, losses, the Lightning-0.6
+hooks (training / validation / test steps and their `*_end` aggregation, optimiser + scheduler configuration,
+dataloaders, argparse surface), so the reference's train.py / eval.py drive it unchanged through `m3t_b200.run`
+(SURVEY 8(f) N1).  The base class is `m3t_b200.lightning.LightningModule` (pytorch_lightning 0.6 is not installable).
 
-Only the hot-path configurations are built: modality in {audio, visual, audiovisual}, backbone in {resnet,
-v2p_split(*)}, fusion_type in {concat, attention}.   (*) when models.vggm is available.
+Only the hot-path configurations are built: modality in {audio, visual, audiovisual}, backbone in {resnet, v2p,
+v2p_split}, fusion_type in {concat, attention}.
 """
+import sys
+from argparse import ArgumentParser
+
 import torch
 import torch.nn as nn
 from torch.nn import functional as F
+from torch.utils.data import DataLoader
 
 from .. import fp32, ops
+from .. import lightning as pl
 from .att_fusion import AttFusion
 from .backbone import VA_3DResNet
 from .rnn import GRU
-from .utils import concordance_cc2
+from .utils import concordance_cc2, mse
 
-try:  # pragma: no cover - not installed here
-    import pytorch_lightning as _pl
-    _Base = _pl.LightningModule
-except Exception:  # noqa: BLE001
-    _Base = nn.Module
+LR_TEST_MAX_LR = 0.01
+LR_TEST_STEPS = 1096 * 3
+
+_Base = pl.LightningModule
+
+
+def _hp(hparams, name, default):
+    """Callers outside train.py (tests, bench) pass a partial Namespace; absent switches read as the argparse default."""
+    return getattr(hparams, name, default)
 
 
 class AffWild2VA(_Base):
     def __init__(self, hparams):
         super().__init__()
-        try:
-            self.hparams = hparams
-        except AttributeError:  # newer Lightning makes hparams read-only
-            self.save_hyperparameters(vars(hparams))
+        self.hparams = hparams
         hp = hparams
         use_mtl = 'mtl' in hp.loss
         fc_outputs = 7 + 2 if use_mtl else 2
@@ -127,20 +134,208 @@ class AffWild2VA(_Base):
         logs['loss'] = loss
         return loss, logs
 
+
+    # ------------------------------------------------------------------ Lightning hooks (reference :146-373)
     def training_step(self, batch, batch_idx):
         y_hat = self.forward(batch)
         loss, logs = self.compute_loss(y_hat, batch)
-        return {'loss': loss, 'progress_bar': dict(logs), 'log': dict(logs)}
+        progress = dict(logs)
+        if 'loss_expr' in logs:
+            # expression accuracy over the frames that carry a label (reference :178-180)
+            keep = batch['expr_valid'].view(-1)
+            hit = (y_hat[..., :7].argmax(dim=-1).view(-1)[keep] == batch['class_expr'].view(-1)[keep]).sum().item()
+            progress['acc_expr'] = hit / int(keep.long().sum().item())
+        if _hp(self.hparams, 'test_lr', False):
+            self._lr_range_test_record(loss, batch_idx)
+        return {'loss': loss, 'progress_bar': progress, 'log': dict(logs)}
+
+    def _lr_range_test_record(self, loss, batch_idx):
+        """Learning-rate range test bookkeeping (reference :198-209): exponentially smoothed loss against the
+        BatchExponentialLR schedule; plots and exits after LR_TEST_STEPS batches."""
+        from .lr_finder import plot_lr
+        hist = self.history
+        if len(hist['lr']) == LR_TEST_STEPS:
+            plot_lr(hist)
+            print('Saved LR-loss plot.')
+            sys.exit(0)
+        hist['lr'].append(self.lr_test.get_lr()[0])
+        value = loss.item()
+        hist['loss'].append(value if batch_idx == 0 else 0.05 * value + 0.95 * hist['loss'][-1])
+
+    def on_batch_end(self):
+        if _hp(self.hparams, 'test_lr', False):
+            self.lr_test.step()
+        if _hp(self.hparams, 'scheduler', 'plateau') == 'cyclic':
+            self.cyclic_scheduler.step()
+
+    @staticmethod
+    def _valid_prefixes(track, lens):
+        return [track[i, :int(lens[i])] for i in range(track.size(0))]
 
     def validation_step(self, batch, batch_idx):
-        y_hat = self.forward(batch).cpu()
-        return {'valence_hat': y_hat[..., -2], 'arousal_hat': y_hat[..., -1]}
+        """Per clip: the first `length` frames of prediction and ground truth, plus the bookkeeping that lets
+        validation_end put the windows back on their videos (reference :220-242).  One device->host copy per batch."""
+        lens = batch['length'].cpu()
+        va_hat = self.forward(batch)[..., -2:].cpu()
+        return {'v_gt': self._valid_prefixes(batch['label_valence'].cpu(), lens),
+                'a_gt': self._valid_prefixes(batch['label_arousal'].cpu(), lens),
+                'v_pred': self._valid_prefixes(va_hat[..., 0], lens),
+                'a_pred': self._valid_prefixes(va_hat[..., 1], lens),
+                'vid_names': batch['vid_name'], 'start_frames': batch['start'].cpu()}
+
+    def test_step(self, batch, batch_idx):
+        if _hp(self.hparams, 'test_on_val', False):
+            return self.validation_step(batch, batch_idx)
+        lens = batch['length'].cpu()
+        va_hat = self.forward(batch)[..., -2:].cpu()
+        return {'v_pred': self._valid_prefixes(va_hat[..., 0], lens),
+                'a_pred': self._valid_prefixes(va_hat[..., 1], lens),
+                'vid_names': batch['vid_name'], 'start_frames': batch['start'].cpu()}
+
+    def _per_video(self, outputs, keys, overlapped):
+        """Windows -> per-video tracks.  keys: the per-clip lists to carry (e.g. v_gt, a_gt, v_pred, a_pred).
+        overlapped=False: windows tile the video, tracks are their concatenation in start order (reference :274-278);
+        overlapped=True: half-stride windows are summed on their frames and every frame from window//2 on is halved
+        (reference :279-297, :352-366) — `m3t_overlap_add_f32`, all videos in one launch."""
+        names, vid_of, starts, segs = [], {}, [], []
+        order = []
+        for out in outputs:
+            for j, name in enumerate(out['vid_names']):
+                vid_of.setdefault(name, len(vid_of))
+                names.append(name)
+                starts.append(int(out['start_frames'][j]))
+                segs.append(torch.stack([out[k][j].float() for k in keys], dim=-1))      # (len, C)
+        order = sorted(range(len(segs)), key=lambda i: (vid_of[names[i]], starts[i]))
+        videos = list(vid_of)
+        if not overlapped:
+            tracks = {k: {} for k in keys}
+            for v in videos:
+                whole = torch.cat([segs[i] for i in order if names[i] == v])
+                for c, k in enumerate(keys):
+                    tracks[k][v] = whole[:, c].contiguous()
+            return tracks
+        from ..process import postproc
+        dev = next(self.parameters()).device
+        if dev.type != 'cuda':
+            raise RuntimeError("overlap-add of half-stride windows runs on the device (m3t_overlap_add_f32); "
+                               "the module is on %s" % dev)
+        lens = [segs[i].size(0) for i in order]
+        stacked = torch.nn.utils.rnn.pad_sequence([segs[i] for i in order], batch_first=True)
+        if stacked.size(1) < self.hparams.window:
+            stacked = F.pad(stacked, (0, 0, 0, self.hparams.window - stacked.size(1)))
+        t = postproc.overlap_add(stacked.to(dev).contiguous(), [starts[i] for i in order],
+                                 [vid_of[names[i]] for i in order], lens, self.hparams.window, len(videos))
+        per_video = [x.cpu() for x in t.split()]
+        return {k: {v: per_video[n][:, c].contiguous() for n, v in enumerate(videos)} for c, k in enumerate(keys)}
+
+    def validation_end(self, outputs):
+        """Global CCC / MSE over every valid frame, `val_loss` = 1 - mean CCC, and predictions_val.pt with the
+        per-video tracks (reference :244-318)."""
+        flat = {k: torch.cat([torch.cat(o[k]) for o in outputs]) for k in ('v_gt', 'a_gt', 'v_pred', 'a_pred')}
+        ok = (flat['v_gt'].abs() <= 1) & (flat['a_gt'].abs() <= 1)
+        ccc_v = concordance_cc2(flat['v_gt'][ok], flat['v_pred'][ok])
+        ccc_a = concordance_cc2(flat['a_gt'][ok], flat['a_pred'][ok])
+        mse_v = mse(flat['v_pred'][ok], flat['v_gt'][ok])
+        mse_a = mse(flat['a_pred'][ok], flat['a_gt'][ok])
+        val_loss = 1 - 0.5 * (ccc_v + ccc_a)
+        tracks = self._per_video(outputs, ('v_gt', 'a_gt', 'v_pred', 'a_pred'),
+                                 overlapped=_hp(self.hparams, 'test_on_val', False))
+        torch.save({'valence_gt': tracks['v_gt'], 'arousal_gt': tracks['a_gt'],
+                    'valence_pred': tracks['v_pred'], 'arousal_pred': tracks['a_pred']}, 'predictions_val.pt')
+        bar = {'val_ccc_v': ccc_v, 'val_ccc_a': ccc_a}
+        return {'val_loss': val_loss, 'progress_bar': bar,
+                'log': dict(bar, val_mse_v=mse_v, val_mse_a=mse_a, val_loss=val_loss)}
+
+    def test_end(self, outputs):
+        """predictions_test.pt: per-video overlap-added valence / arousal tracks (reference :340-373)."""
+        if _hp(self.hparams, 'test_on_val', False):
+            return self.validation_end(outputs)
+        tracks = self._per_video(outputs, ('v_pred', 'a_pred'), overlapped=True)
+        torch.save({'valence_pred': tracks['v_pred'], 'arousal_pred': tracks['a_pred']}, 'predictions_test.pt')
+        return {}
 
     # ------------------------------------------------------------------ optimiser (reference :375-407)
     def configure_optimizers(self):
         hp = self.hparams
+        if _hp(hp, 'freeze_enc', False):
+            # only the fusion stage trains: projection, attention scorers, fusion GRU
+            trainable = [self.fusion, self.proj_v] + ([self.att_fuse] if hp.fusion_type == 'attention' else [])
+            self.requires_grad_(False)
+            for part in trainable:
+                part.requires_grad_(True)
+        params = [p for p in self.parameters() if p.requires_grad]
         if hp.optimizer == 'adam':
-            opt = torch.optim.Adam(self.parameters(), lr=hp.learning_rate, weight_decay=1e-4)
+            opt = torch.optim.Adam(params, lr=hp.learning_rate, weight_decay=1e-4)
+        elif hp.optimizer == 'sgd':
+            opt = torch.optim.SGD(params, lr=hp.learning_rate, momentum=0.9, weight_decay=5e-4)
         else:
-            opt = torch.optim.SGD(self.parameters(), lr=hp.learning_rate, momentum=0.9, weight_decay=5e-4)
+            raise ValueError("optimizer must be 'adam' or 'sgd', got %r" % (hp.optimizer,))
+        if _hp(hp, 'test_lr', False):
+            from .lr_finder import BatchExponentialLR
+            self.lr_test = BatchExponentialLR(opt, LR_TEST_MAX_LR, LR_TEST_STEPS)
+            return opt
+        kind = _hp(hp, 'scheduler', None)
+        if kind == 'cyclic':
+            self.cyclic_scheduler = torch.optim.lr_scheduler.CyclicLR(
+                opt, hp.min_lr, hp.learning_rate, step_size_up=5000, cycle_momentum=hp.optimizer == 'sgd')
+            return opt
+        if kind == 'exp':
+            return [opt], [torch.optim.lr_scheduler.ExponentialLR(opt, hp.decay_factor)]
+        if kind == 'plateau':
+            return [opt], [torch.optim.lr_scheduler.ReduceLROnPlateau(opt, factor=hp.decay_factor, patience=3,
+                                                                      min_lr=1e-6)]
         return opt
+
+    # ------------------------------------------------------------------ data (reference :409-446)
+    def _loader(self, split, inv_test_stride=1):
+        from .dataset import AffWild2SequenceDataset
+        hp = self.hparams
+        if hp.mode != 'video':
+            raise NotImplementedError("only mode='video' exists in the reference")
+        on_device_aug = _hp(hp, 'device_augment', False) and hp.backbone == 'resnet' and 'visual' in hp.modality
+        ds = AffWild2SequenceDataset(split, hp.dataset_path, hp.window, hp.windows_per_epoch, hp.cutout, hp.release,
+                                     hp.input_size, hp.modality, hp.resample, inv_test_stride, emit_u8=on_device_aug)
+        if hp.distributed:
+            return DataLoader(ds, batch_size=hp.batch_size, num_workers=hp.workers, pin_memory=True,
+                              sampler=torch.utils.data.distributed.DistributedSampler(ds))
+        return DataLoader(ds, batch_size=hp.batch_size, shuffle=split == 'train', num_workers=hp.workers,
+                          pin_memory=True)
+
+    @pl.data_loader
+    def train_dataloader(self):
+        return self._loader('train')
+
+    @pl.data_loader
+    def val_dataloader(self):
+        return self._loader('val', 2 if self.hparams.test_on_val else 1)
+
+    @pl.data_loader
+    def test_dataloader(self):
+        if self.hparams.test_on_val:
+            return self.val_dataloader()
+        return self._loader('test', 2)
+
+    @staticmethod
+    def add_model_specific_args(parent_parser):
+        """The reference's command line (models/model.py:448-493), plus --device_augment (crop / mirror / cutout /
+        normalise inside the stem's input kernel from uint8 frames; resnet backbone)."""
+        parser = ArgumentParser(parents=[parent_parser])
+        flag = dict(action='store_true', default=False)
+        for name, kw in (
+                ('--backbone', dict(default='v2p_split', type=str)), ('--backend', dict(default='gru', type=str)),
+                ('--modality', dict(default='visual', type=str)), ('--fusion_type', dict(default='concat', type=str)),
+                ('--freeze_enc', flag), ('--resample', flag), ('--mode', dict(default='video', type=str)),
+                ('--window', dict(default=32, type=int)), ('--windows_per_epoch', dict(default=200, type=int)),
+                ('--learning_rate', dict(default=5e-5, type=float)), ('--min_lr', dict(default=1e-8, type=float)),
+                ('--decay_factor', dict(default=0.5, type=float)), ('--batch_size', dict(default=96, type=int)),
+                ('--optimizer', dict(default='adam', type=str)), ('--scheduler', dict(default='plateau', type=str)),
+                ('--test_lr', flag), ('--test_on_val', flag), ('--loss', dict(default='ccc_mtl', type=str)),
+                ('--loss_lambda', dict(default=0.5, type=float)), ('--num_hidden', dict(default=512, type=int)),
+                ('--split_layer', dict(default=3, type=int)), ('--num_fc_layers', dict(default=2, type=int)),
+                ('--cutout', flag), ('--distributed', flag),
+                ('--dataset_path', dict(default='/.data/zhangyuanhang/Aff-Wild2', type=str)),
+                ('--release', dict(default='vipl', type=str)), ('--input_size', dict(default=256, type=int)),
+                ('--checkpoint_path', dict(default='.', type=str)), ('--workers', dict(default=8, type=int)),
+                ('--max_nb_epochs', dict(default=30, type=int)), ('--device_augment', flag)):
+            parser.add_argument(name, **kw)
+        return parser

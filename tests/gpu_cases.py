@@ -1270,6 +1270,109 @@ for _k in ("prep_exact_norm1", "prep_exact_norm0", "features_exact"):
     TOLS[_k] = 0.5
 
 
+# ----------------------------------------------------------------------------------------------------------
+# the scripts' call surface end to end — Trainer.fit / Trainer.test on a synthetic Aff-Wild2 tree
+# ----------------------------------------------------------------------------------------------------------
+def case_trainer_scripts(seed=0):
+    """`python -m m3t_b200.run <script> ...` (tests/scripts/fit_script.py has the imports and calls of the reference's
+    train.py / eval.py; on the build box the reference's own files are used instead when present): 2 epochs of
+    audio-visual training on the synthetic tree of tests/synth_affwild.py (uint8 frames + on-device augmentation), the
+    checkpoint it leaves, `--test_on_val` evaluation from that checkpoint, and the hooks run in-process on the same
+    weights: validation_end's overlap-added tracks vs the oracle's overlap-add (bit-exact) and vs the file the
+    evaluation script wrote (bit-exact: the eval forward is deterministic)."""
+    import argparse
+    import glob
+    import subprocess
+    import tempfile
+
+    import numpy as np
+    from oracle import postproc as O
+    from tests import synth_affwild
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    tmp = tempfile.mkdtemp(prefix="m3t_trainer_")
+    data = os.path.join(tmp, "data")
+    videos = synth_affwild.build(data, tmp, input_size=128, seed=seed)
+    ref_root = os.environ.get("M3T_REFERENCE", "/root/reference")
+    have_ref = os.path.isfile(os.path.join(ref_root, "train.py"))
+    own = os.path.join(root, "tests", "scripts", "fit_script.py")
+    common = ["--gpus", "0", "--modality", "audiovisual", "--backbone", "resnet", "--fusion_type", "attention",
+              "--split_layer", "5", "--window", "8", "--windows_per_epoch", "4", "--batch_size", "4",
+              "--dataset_path", data, "--release", "vipl", "--input_size", "128", "--workers", "0",
+              "--checkpoint_path", tmp, "--device_augment"]
+    env = dict(os.environ, PYTHONPATH=root)
+
+    def run(script, extra):
+        r = subprocess.run([sys.executable, "-m", "m3t_b200.run", script] + common + extra, cwd=tmp, env=env,
+                           capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, (script, r.stdout[-1500:], r.stderr[-3000:])
+        return r.stdout + r.stderr
+
+    errs = {}
+    fit_log = run(os.path.join(ref_root, "train.py") if have_ref else own, ["--max_nb_epochs", "2", "--cutout"])
+    ck = glob.glob(os.path.join(tmp, "lightning_logs", "version_0", "checkpoints", "_ckpt_epoch_*.ckpt"))
+    errs["one_checkpoint"] = float(len(ck) != 1)
+    errs["val_logged"] = float("val_ccc_v" not in fit_log or "fused flat-arena Adam" not in fit_log)
+    run(os.path.join(ref_root, "eval.py") if have_ref else own,
+        ["--checkpoint", ck[0], "--test_on_val"] + ([] if have_ref else ["--evaluate"]))
+    by_script = torch.load(os.path.join(tmp, "predictions_val.pt"))
+    val_videos = [v for v, d in videos.items() if d["split"] == "val"]
+    errs["track_lengths"] = float(any(len(by_script["valence_pred"][v]) != videos[v]["frames"] for v in val_videos))
+    errs["nonfinite"] = float(sum(int((~torch.isfinite(t)).sum()) for d in by_script.values() for t in d.values()))
+
+    # the same weights in-process: hooks vs the oracle's overlap-add and vs the script's file
+    from m3t_b200.models.model import AffWild2VA
+    cwd = os.getcwd()
+    os.chdir(tmp)
+    try:
+        model = AffWild2VA.load_from_checkpoint(ck[0])
+        model.hparams.test_on_val = True
+        model = model.cuda().eval()
+        outputs = []
+        with torch.no_grad():
+            for bi, batch in enumerate(model.val_dataloader()[0]):
+                batch = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in batch.items()}
+                outputs.append(model.validation_step(batch, bi))
+            res = model.validation_end(outputs)
+            in_proc = torch.load("predictions_val.pt")
+            model.hparams.test_on_val = False
+            test_out = [model.test_step({k: (v.cuda() if torch.is_tensor(v) else v) for k, v in b.items()}, i)
+                        for i, b in enumerate(model.test_dataloader()[0])]
+            model.test_end(test_out)
+            test_file = torch.load("predictions_test.pt")
+    finally:
+        os.chdir(cwd)
+    errs["val_loss_nonfinite"] = float(not bool(torch.isfinite(res["val_loss"])))
+    diff = 0
+    for key in by_script:
+        for v in val_videos:
+            diff += int((by_script[key][v] != in_proc[key][v]).sum())
+    errs["script_vs_inproc_exact"] = float(diff)
+    names = [n for o in outputs for n in o["vid_names"]]
+    starts = [int(s) for o in outputs for s in o["start_frames"]]
+    vid_ix = {v: i for i, v in enumerate(dict.fromkeys(names))}
+    segs = [torch.stack([o[k][j] for k in ("v_gt", "a_gt", "v_pred", "a_pred")], -1) for o in outputs
+            for j in range(len(o["vid_names"]))]
+    lens = [len(s) for s in segs]
+    padded = np.zeros((len(segs), 8, 4), dtype=np.float32)
+    for i, s in enumerate(segs):
+        padded[i, :len(s)] = s.numpy()
+    want = O.overlap_add(padded, starts, [vid_ix[n] for n in names], lens, 8, len(vid_ix))
+    diff = 0
+    for v, i in vid_ix.items():
+        for c, key in enumerate(("valence_gt", "arousal_gt", "valence_pred", "arousal_pred")):
+            diff += int((in_proc[key][v].numpy() != want[i][:, c]).sum())
+    errs["val_tracks_exact"] = float(diff)
+    tv = [v for v, d in videos.items() if d["split"] == "test"][0]
+    errs["test_track_length"] = float(len(test_file["valence_pred"][tv]) != videos[tv]["frames"])
+    return errs
+
+
+CASES["trainer_scripts_fit_eval"] = (case_trainer_scripts, _c())
+for _k in ("one_checkpoint", "val_logged", "track_lengths", "nonfinite", "val_loss_nonfinite",
+           "script_vs_inproc_exact", "val_tracks_exact", "test_track_length"):
+    TOLS[_k] = 0.5
+
+
 if __name__ == "__main__":
     name = sys.argv[1]
     errs = run_case(name)
