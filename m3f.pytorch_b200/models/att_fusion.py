@@ -1,7 +1,7 @@
 """Attention fusion of the audio and visual streams (reference: models/att_fusion.py:8-27)."""
 import torch.nn as nn
 
-from .. import fp32, ops
+from .. import fp32, ops, streams
 from .rnn import GRU
 
 
@@ -21,8 +21,14 @@ class AttFusion(nn.Module):
         x_a, x_v = ops.as_bf16(x_a), ops.as_bf16(x_v)
         if self.use_proj:
             x_v = ops.linear(x_v, self.proj_v.weight, self.proj_v.bias)
-        s_v = self.scorer_v.forward_bf16(x_v)     # (B,T,1) fp32 logits
-        s_a = self.scorer_a.forward_bf16(x_a)
+        if streams.overlap_ok(x_a):
+            # inference: the two scorers are independent -> one of them runs on a side stream (streams.py)
+            s_a = streams.run_on_side(0, x_a.device, self.scorer_a.forward_bf16, x_a)
+            s_v = self.scorer_v.forward_bf16(x_v)
+            streams.join(x_a.device, 0)
+        else:
+            s_v = self.scorer_v.forward_bf16(x_v)     # (B,T,1) fp32 logits
+            s_a = self.scorer_a.forward_bf16(x_a)
         return ops.AttMixFn.apply(x_a, x_v, s_a, s_v)
 
     def forward(self, x_a, x_v):

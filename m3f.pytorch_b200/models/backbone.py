@@ -63,11 +63,15 @@ class VA_3DResNet(nn.Module):
         f = self.resnet.forward_cl(x)                     # (B*T, 512)
         return f.view(B, T, -1)
 
-    def forward_bf16(self, x, normalise=False):
+    def forward_bf16(self, x, normalise=False, after_features=None):
+        """after_features: optional callable invoked once the convolutions are enqueued and before the recurrent head
+        (AffWild2VA forks the audio stream there, streams.py)."""
         if fp32.enabled():       # fp32-parity inference mode: float32 activations, split-operand tensor-core launches
             fp32.require_eval(self)
             return fp32.va_3dresnet(self, x, normalise)
         f = self.features_cl(x, normalise)
+        if after_features is not None:
+            after_features()
         if f.shape[1] != self.frameLen:
             raise RuntimeError("VA_3DResNet: T (%d) must equal frameLen (%d)" % (f.shape[1], self.frameLen))
         if self.backend == 'gru':

@@ -14,7 +14,7 @@ import torch.nn as nn
 from torch.nn import functional as F
 from torch.utils.data import DataLoader
 
-from .. import fp32, ops
+from .. import fp32, ops, streams
 from .. import lightning as pl
 from .att_fusion import AttFusion
 from .backbone import VA_3DResNet
@@ -69,16 +69,19 @@ class AffWild2VA(_Base):
         self.history = {'lr': [], 'loss': []}
 
     # ------------------------------------------------------------------ forward
-    def _visual(self, batch):
+    def _visual(self, batch, after_features=None):
         hp = self.hparams
         if hp.backbone == 'resnet':
             # normalisation (video - 127.5) / 127.5 (reference :106) is folded into the stem's input pass
             if 'video_u8' in batch:
                 # decoded uint8 HWC frames + augmentation parameters instead of the float32 clip tensor: crop, mirror
                 # and cutout (models/dataset.py:46-80) happen inside the same pass (process/video_input.py)
-                return self.visual.forward_bf16(ops.RawClips(batch['video_u8'], batch['video_aug']), normalise=True)
-            return self.visual.forward_bf16(batch['video'], normalise=True)
-        return self.visual.forward_bf16(batch['video'], batch['se_features'], batch['se_features'], normalise=True)
+                video = ops.RawClips(batch['video_u8'], batch['video_aug'])
+            else:
+                video = batch['video']
+            return self.visual.forward_bf16(video, normalise=True, after_features=after_features)
+        return self.visual.forward_bf16(batch['video'], batch['se_features'], batch['se_features'], normalise=True,
+                                        after_features=after_features)
 
     def forward(self, batch):
         hp = self.hparams
@@ -86,12 +89,24 @@ class AffWild2VA(_Base):
             return ops.as_f32(self.audio.forward_bf16(batch['audio']))
         if hp.modality == 'visual':
             return ops.as_f32(self._visual(batch))
-        a = self.audio.forward_bf16(batch['audio'])
-        v = self._visual(batch)
-        if fp32.enabled():
-            v = fp32.linear(v, self.proj_v.weight, self.proj_v.bias)
-        else:
+        audio = batch['audio']
+        if streams.overlap_ok(audio):
+            # inference: the audio BiGRU runs on a side stream next to the visual stream's recurrent head; it is
+            # forked by the backbone right after its convolutions (streams.py)
+            box = []
+            v = self._visual(batch, lambda: box.append(streams.run_on_side(0, audio.device, self.audio.forward_bf16,
+                                                                           audio)))
+            a = box[0] if box else self.audio.forward_bf16(audio)
             v = ops.linear(v, self.proj_v.weight, self.proj_v.bias)
+            if box:
+                streams.join(audio.device, 0)
+        else:
+            a = self.audio.forward_bf16(audio)
+            v = self._visual(batch)
+            if fp32.enabled():
+                v = fp32.linear(v, self.proj_v.weight, self.proj_v.bias)
+            else:
+                v = ops.linear(v, self.proj_v.weight, self.proj_v.bias)
         if hp.fusion_type == 'concat':
             f = torch.cat((a, v), dim=-1)
         else:

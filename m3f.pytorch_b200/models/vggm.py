@@ -8,7 +8,7 @@ evaluated over the 2x2 space-to-depth image, like the ResNet stem.
 import torch
 import torch.nn as nn
 
-from .. import fp32, ops, raw
+from .. import fp32, ops, raw, streams
 from .backbone import _init_like_reference
 from .rnn import GRU
 from .tcn import TemporalConvNet
@@ -104,7 +104,7 @@ class VA_3DVGGM(nn.Module):
             self.fc = nn.Sequential(nn.Linear(512, hiddenDim), nn.ReLU(True), nn.Linear(hiddenDim, nClasses))
         _init_like_reference(self)
 
-    def forward_bf16(self, video, *unused, normalise=False):
+    def forward_bf16(self, video, *unused, normalise=False, after_features=None):
         if fp32.enabled():       # fp32-parity inference mode (m3t_b200.fp32)
             fp32.require_eval(self)
             f = _squeeze_features(fp32.vggm_stack(self.v2p, video, True, normalise))
@@ -118,6 +118,8 @@ class VA_3DVGGM(nn.Module):
             return fp32.linear(h, self.fc[2].weight, self.fc[2].bias).mean(dim=1)
         xs = raw.video_prep_s2d(video.contiguous(), normalise)
         f = _squeeze_features(_run_stack(self.v2p, xs, True))           # (B,T,512)
+        if after_features is not None:
+            after_features()
         if self.backend == 'gru':
             return self.gru.forward_bf16(f)
         if self.backend == 'tcn':
@@ -170,7 +172,7 @@ class VA_3DVGGM_Split(nn.Module):
                 self.tcn_a.append(nn.Linear(hiddenDim, 1))
         _init_like_reference(self)
 
-    def forward_bf16(self, video, se, au, normalise=False):
+    def forward_bf16(self, video, se, au, normalise=False, after_features=None):
         if fp32.enabled():       # fp32-parity inference mode (m3t_b200.fp32)
             fp32.require_eval(self)
             cl = lambda f: f.float().transpose(1, 2).contiguous()        # noqa: E731  (B,C,T) -> (B,T,C)
@@ -189,10 +191,19 @@ class VA_3DVGGM_Split(nn.Module):
         x = _run_stack(self.shared, xs, True)
         if self.split_layer == 5:
             f = torch.cat((_squeeze_features(x), ops.ToCL.apply(se), ops.ToCL.apply(au)), dim=-1)
+            if after_features is not None:
+                after_features()
             return self.gru.forward_bf16(f) if self.backend == 'gru' else f
         x_v = _cat_cl(_squeeze_features(_run_stack(self.v_private, x, False)), se)
         x_a = _cat_cl(_squeeze_features(_run_stack(self.a_private, x, False)), au)
-        if self.backend == 'gru':
+        if after_features is not None:
+            after_features()
+        if self.backend == 'gru' and streams.overlap_ok(x_a):
+            # inference: the two private BiGRU heads are independent -> the arousal head runs on a side stream
+            o_a = streams.run_on_side(1, x_a.device, self.gru_a.forward_bf16, x_a)
+            o_v = self.gru_v.forward_bf16(x_v)
+            streams.join(x_a.device, 1)
+        elif self.backend == 'gru':
             o_v, o_a = self.gru_v.forward_bf16(x_v), self.gru_a.forward_bf16(x_a)
         else:
             o_v, o_a = _tcn_simple(self.tcn_v, x_v), _tcn_simple(self.tcn_a, x_a)

@@ -1373,6 +1373,93 @@ for _k in ("one_checkpoint", "val_logged", "track_lengths", "nonfinite", "val_lo
     TOLS[_k] = 0.5
 
 
+# ----------------------------------------------------------------------------------------------------------
+# Inference forward with its independent recurrent branches forked onto side streams (m3t_b200.streams)
+# ----------------------------------------------------------------------------------------------------------
+def case_streams(seed=0):
+    """The multi-stream inference forward is bit-identical to the single-stream one (attention / concat fusion,
+    ResNet and VGG-M split backbones, repeated calls, CUDA-graph capture of the forked forward); `info` reports the
+    latency of a BASELINE config-5 shaped forward (16 clips x T=64) both ways."""
+    import argparse
+
+    import bench as BN
+    from m3t_b200 import streams
+    from m3t_b200.graphs import GraphedInference
+    from m3t_b200.models.model import AffWild2VA
+    errs, info = {}, {}
+
+    def hp(**kw):
+        d = dict(backbone="resnet", backend="gru", modality="audiovisual", fusion_type="attention", window=8,
+                 loss="ccc_mtl", loss_lambda=0.5, num_hidden=512, split_layer=5, num_fc_layers=2, learning_rate=5e-5,
+                 optimizer="adam")
+        d.update(kw)
+        return argparse.Namespace(**d)
+
+    def batch(B, T, s):
+        g = torch.Generator().manual_seed(s)
+        return {"video": torch.randint(0, 256, (B, 3, T, 112, 112), generator=g, dtype=torch.uint8).float().cuda(),
+                "audio": (torch.randn((B, T, 200), generator=g) * 20 - 40).cuda(),
+                "se_features": torch.randn((B, 512, T), generator=g).cuda()}
+
+    prev = streams.set_enabled(True)
+    try:
+        for tag, h in (("resnet_att", hp()), ("resnet_concat", hp(fusion_type="concat")),
+                       ("v2psplit_att", hp(backbone="v2p_split", split_layer=3))):
+            torch.manual_seed(seed)
+            m = AffWild2VA(h)
+            BN.randomise_bn(m, 5)
+            m = m.cuda().eval()
+            diff = 0
+            with torch.no_grad():
+                for s in (1, 2, 3):
+                    b = batch(4, 8, s)
+                    streams.set_enabled(False)
+                    y0 = m(b).clone()
+                    streams.set_enabled(True)
+                    y1 = m(b).clone()
+                    diff += int((y0 != y1).sum()) + int((~torch.isfinite(y1)).sum())
+            errs["streams_exact_" + tag] = float(diff)
+            if tag == "resnet_att":
+                b = batch(4, 8, 9)
+                streams.set_enabled(False)
+                with torch.no_grad():
+                    y0 = m(b).clone()
+                streams.set_enabled(True)
+                g = GraphedInference(m, batch(4, 8, 8))
+                errs["streams_graph_exact"] = float((g(b) != y0).sum())
+        # latency at BASELINE config-5 shapes (16 clips per GPU)
+        for T in (64, 256):
+            torch.manual_seed(seed)
+            m = AffWild2VA(hp(window=T))
+            BN.randomise_bn(m, 5)
+            m = m.cuda().eval()
+            b = batch(16, T, 4)
+            for flag in (False, True):
+                streams.set_enabled(flag)
+                with torch.no_grad():
+                    for _ in range(3):
+                        m(b)
+                    torch.cuda.synchronize()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    for _ in range(10):
+                        m(b)
+                    e1.record()
+                    torch.cuda.synchronize()
+                info["ms_16x%d_streams_%s" % (T, "on" if flag else "off")] = round(e0.elapsed_time(e1) / 10, 3)
+            del m, b
+    finally:
+        streams.set_enabled(prev)
+    errs["info"] = info
+    return errs
+
+
+CASES["streams_inference_exact"] = (case_streams, _c())
+for _k in ("streams_exact_resnet_att", "streams_exact_resnet_concat", "streams_exact_v2psplit_att",
+           "streams_graph_exact"):
+    TOLS[_k] = 0.5
+
+
 if __name__ == "__main__":
     name = sys.argv[1]
     errs = run_case(name)

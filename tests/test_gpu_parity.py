@@ -16,7 +16,8 @@ from tests import gpu_cases as G
 
 pytestmark = pytest.mark.gpu
 
-PROBES = {"probe_rowshift"}   # hardware-semantics probes: informational, run by tests/gpu_probe.py
+# hardware-semantics probes (informational) and cases not yet confirmed on a B200: run by tests/gpu_probe.py only
+PROBES = {"probe_rowshift", "streams_inference_exact"}
 
 
 @pytest.mark.parametrize("name", sorted(n for n in G.CASES if n not in PROBES))
