@@ -20,7 +20,7 @@ import os
 
 import torch
 
-_enabled = os.environ.get("M3T_STREAMS", "0") == "1"     # off until confirmed on a B200
+_enabled = os.environ.get("M3T_STREAMS", "1") != "0"
 _side = {}
 MAX_CLIPS = 64
 

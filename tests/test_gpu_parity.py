@@ -16,8 +16,7 @@ from tests import gpu_cases as G
 
 pytestmark = pytest.mark.gpu
 
-# hardware-semantics probes (informational) and cases not yet confirmed on a B200: run by tests/gpu_probe.py only
-PROBES = {"probe_rowshift", "streams_inference_exact"}
+PROBES = {"probe_rowshift"}   # hardware-semantics probes: informational, run by tests/gpu_probe.py
 
 
 @pytest.mark.parametrize("name", sorted(n for n in G.CASES if n not in PROBES))
@@ -80,3 +79,22 @@ def test_fp32_mode_refuses_training():
     m = GRU(64, 32, 1, 2, 1).cuda().train()
     with fp32.parity_mode(), pytest.raises(NotImplementedError):
         m(torch.randn(2, 4, 64, device="cuda"))
+
+
+def test_trainer_ddp_nccl_two_gpus(tmp_path):
+    """Trainer 'ddp' on NCCL with the real model (needs 2 GPUs; the single-GPU round-end box skips it — run once with
+    `gpurun --gpus 2`, log in profiles/)."""
+    import os
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, PYTHONPATH=root)
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT"):
+        env.pop(k, None)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29641", "-m", "m3t_b200.run",
+                        os.path.join(root, "tests", "trainer_nccl_worker.py"), str(tmp_path)],
+                       capture_output=True, text=True, timeout=600, env=env, cwd=root)
+    assert r.returncode == 0 and r.stdout.count("TRAINER_NCCL_OK") == 2, r.stdout[-2000:] + r.stderr[-4000:]
