@@ -248,11 +248,14 @@ int m3t_mel_stack(const float* mel, long long n_frames, int n_mels, long long st
 
 /* ------------------------------------------------------------------------------------------------------------
  * Optimiser pass over the flat fp32 parameter / gradient arena (optim.cu).
- * m3t_sumsq_f32: out[0] = sum g^2 (zeroed by the call).  m3t_adam_clip_step: g' = g*grad_scale*min(1, max_norm /
+ * m3t_sumsq_f32: out[0] = sum g^2, computed in two passes with a fixed summation order (block partials in
+ * `workspace`, m3t_sumsq_workspace_floats() floats, then one block): the result is bit-reproducible, so data-parallel
+ * replicas derive identical clip coefficients from their all-reduced gradients.  m3t_adam_clip_step: g' = g*grad_scale*min(1, max_norm /
  * (sqrt(gnorm_sq)*grad_scale + 1e-6)) (skipped when max_norm <= 0), then torch.optim.Adam semantics with coupled
  * weight decay.  Replaces clip_grad_norm_(1.0) (train.py:35 via Lightning) + Adam(lr, weight_decay=1e-4)
  * (models/model.py:388-390); grad_scale = 1/world_size folds the data-parallel mean. */
-int m3t_sumsq_f32(const float* g, long long n, float* out, void* stream);
+long long m3t_sumsq_workspace_floats(void);
+int m3t_sumsq_f32(const float* g, long long n, float* out, float* workspace, void* stream);
 int m3t_adam_clip_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
                        float eps, float weight_decay, int step, float max_norm, float grad_scale,
                        const float* gnorm_sq, void* stream);

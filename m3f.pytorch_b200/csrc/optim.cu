@@ -7,7 +7,25 @@
 
 namespace m3t {
 
-__global__ void sumsq_kernel(const float* __restrict__ g, long long n, float* __restrict__ out) {
+// Block-level sum with a fixed reduction tree (deterministic for a given blockDim).
+__device__ __forceinline__ float block_sum_fixed(float acc) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  __shared__ float red[32];
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  float s = 0.f;
+  if (threadIdx.x < 32) {
+    s = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  }
+  return s;   // valid in thread 0
+}
+
+// Two deterministic passes instead of float atomics: data-parallel replicas must compute bit-identical clip
+// coefficients from their (identical, all-reduced) gradients, or their parameters drift apart ulp by ulp.
+__global__ void sumsq_partial_kernel(const float* __restrict__ g, long long n, float* __restrict__ partial) {
   float acc = 0.f;
   const long long n4 = n / 4;
   const float4* g4 = reinterpret_cast<const float4*>(g);
@@ -17,17 +35,15 @@ __global__ void sumsq_kernel(const float* __restrict__ g, long long n, float* __
   }
   if (blockIdx.x == 0 && threadIdx.x == 0)
     for (long long i = n4 * 4; i < n; ++i) acc += g[i] * g[i];
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-  __shared__ float red[32];
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
-  __syncthreads();
-  if (threadIdx.x < 32) {
-    float s = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (threadIdx.x == 0) atomicAdd(out, s);
-  }
+  const float s = block_sum_fixed(acc);
+  if (threadIdx.x == 0) partial[blockIdx.x] = s;
+}
+
+__global__ void sumsq_final_kernel(const float* __restrict__ partial, int nblocks, float* __restrict__ out) {
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < nblocks; i += blockDim.x) acc += partial[i];
+  const float s = block_sum_fixed(acc);
+  if (threadIdx.x == 0) out[0] = s;
 }
 
 __global__ void adam_clip_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
@@ -55,13 +71,19 @@ __global__ void adam_clip_kernel(float* __restrict__ p, const float* __restrict_
 
 using namespace m3t;
 
-extern "C" int m3t_sumsq_f32(const float* g, long long n, float* out, void* stream) {
+static const int kSumsqMaxBlocks = 148 * 8;
+
+extern "C" long long m3t_sumsq_workspace_floats(void) { return kSumsqMaxBlocks; }
+
+extern "C" int m3t_sumsq_f32(const float* g, long long n, float* out, float* workspace, void* stream) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (cudaMemsetAsync(out, 0, sizeof(float), st) != cudaSuccess) return -22;
+  if (!workspace) return -1;
   long long blocks = (n / 4 + 255) / 256;
-  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks > kSumsqMaxBlocks) blocks = kSumsqMaxBlocks;
   if (blocks < 1) blocks = 1;
-  sumsq_kernel<<<(int)blocks, 256, 0, st>>>(g, n, out);
+  sumsq_partial_kernel<<<(int)blocks, 256, 0, st>>>(g, n, workspace);
+  count_launch();
+  sumsq_final_kernel<<<1, 256, 0, st>>>(workspace, (int)blocks, out);
   count_launch();
   return launch_status();
 }

@@ -17,6 +17,7 @@ default because it measured slower on 2 x B200 (31.9-32.0 ms vs 31.4 ms per step
 the conv kernels are persistent, one CTA per SM, so the SMs NCCL's kernels occupy while they overlap turn a
 one-wave launch into a two-wave one; the non-overlapped collective costs 0.2 ms.
 """
+import ctypes
 import os
 
 import torch
@@ -69,6 +70,8 @@ class TrainEngine:
             self.m = torch.zeros(n, device=dev, dtype=torch.float32)
             self.v = torch.zeros(n, device=dev, dtype=torch.float32)
             self.gnorm_sq = torch.zeros(1, device=dev, dtype=torch.float32)
+            L.load().m3t_sumsq_workspace_floats.restype = ctypes.c_longlong
+            self.sumsq_ws = torch.empty(int(L.load().m3t_sumsq_workspace_floats()), device=dev, dtype=torch.float32)
         else:  # host-side logic tests only (gloo); the product path is the CUDA one
             self.opt = torch.optim.Adam(self.params, lr=self.lr, weight_decay=self.wd, betas=self.betas,
                                         eps=self.eps)
@@ -150,7 +153,8 @@ class TrainEngine:
         lib = L.load()
         st = L.stream_ptr()
         if self.clip:
-            L.check(lib.m3t_sumsq_f32(L.ptr(self.flat_g), L.i64(self.n), L.ptr(self.gnorm_sq), st), "sumsq")
+            L.check(lib.m3t_sumsq_f32(L.ptr(self.flat_g), L.i64(self.n), L.ptr(self.gnorm_sq), L.ptr(self.sumsq_ws), st),
+                    "sumsq")
         L.check(lib.m3t_adam_clip_step(L.ptr(self.flat_p), L.ptr(self.flat_g), L.ptr(self.m), L.ptr(self.v),
                                        L.i64(self.n), L.f32(self.lr), L.f32(self.betas[0]), L.f32(self.betas[1]),
                                        L.f32(self.eps), L.f32(self.wd), L.i32(self.steps), L.f32(self.clip),

@@ -184,12 +184,20 @@ class AffWild2SequenceDataset(Dataset):
                          for i in range(len(self.labels_va[vid]))])
 
     def _cached(self, cache_path, scan):
+        """Window lists are cached in the working directory under the reference's file names.  Unlike the reference
+        the file is written atomically and an unreadable one is rescanned: with one process per GPU every rank
+        builds the dataset at the same moment, and a rank must never read another rank's half-written file."""
         if os.path.exists(cache_path):
-            with open(cache_path, 'rb') as f:
-                return pickle.load(f)
+            try:
+                with open(cache_path, 'rb') as f:
+                    return pickle.load(f)
+            except (EOFError, pickle.UnpicklingError):
+                pass
         windows = scan()
-        with open(cache_path, 'wb') as f:
+        part = '%s.%d.part' % (cache_path, os.getpid())
+        with open(part, 'wb') as f:
             pickle.dump(windows, f)
+        os.replace(part, cache_path)
         return windows
 
     def _run_starts(self, ok):

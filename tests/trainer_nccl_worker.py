@@ -31,21 +31,32 @@ if __name__ == "__main__":
                             "--dataset_path", data, "--release", "vipl", "--input_size", "128", "--workers", "0",
                             "--checkpoint_path", tmp, "--device_augment", "--cutout", "--distributed",
                             "--max_nb_epochs", "1"])
+    # M3T_TRAINER_BACKEND=gloo: both ranks on GPU 0 with gloo collectives (a one-GPU box) / on the CPU (dry run of the
+    # host logic up to the first kernel)
+    backend = os.environ.get("M3T_TRAINER_BACKEND", "nccl")
+    gpus = ("0,1" if backend == "nccl" else "0,0") if torch.cuda.is_available() else None
     torch.manual_seed(12345)
     model = AffWild2VA(hp)
     seen = []
     inner = model.validation_end
     model.validation_end = lambda outputs: (seen.append(sum(len(o["vid_names"]) for o in outputs)), inner(outputs))[1]
     tr = Trainer(early_stop_callback=None, check_val_every_n_epoch=1, gradient_clip_val=1.0, default_save_path=tmp,
-                 max_epochs=1, gpus="0,1", nb_gpu_nodes=1, distributed_backend="ddp", nb_sanity_val_steps=0)
+                 max_epochs=1, gpus=gpus, nb_gpu_nodes=1,
+                 distributed_backend="ddp", nb_sanity_val_steps=0)
     # rank 0 wrote the tree: nobody may read it before that is done.  Trainer joins torchrun's group in fit(); the
     # barrier here needs it earlier.
-    torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
-    dist.init_process_group("nccl")
+    if backend == "nccl":
+        torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
+    elif gpus:
+        torch.cuda.set_device(0)
+    dist.init_process_group(backend)
     dist.barrier()
     tr.fit(model)
-    assert tr.world == 2 and tr.device.index == int(os.environ["LOCAL_RANK"]) and tr.engine is not None
+    assert tr.world == 2 and tr.engine is not None
+    assert tr.device.index == (int(os.environ["LOCAL_RANK"]) if backend == "nccl" else 0)
     flat = torch.cat([p.detach().reshape(-1).float() for p in model.parameters()])
+    if backend != "nccl":
+        flat = flat.cpu()                          # gloo gathers host tensors only
     both = [torch.empty_like(flat) for _ in range(2)]
     dist.all_gather(both, flat)
     assert torch.equal(both[0], both[1]), "ranks diverged: %g" % float((both[0] - both[1]).abs().max())
