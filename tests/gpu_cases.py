@@ -1460,6 +1460,38 @@ for _k in ("streams_exact_resnet_att", "streams_exact_resnet_concat", "streams_e
     TOLS[_k] = 0.5
 
 
+def case_smooth_predictions_api(seed=0):
+    """models.utils.smooth_predictions with the reference's call conventions (get_smoothed_ccc.py:15-16: a float32
+    torch track, window 35; create_submission.py:35-36: a float32 ndarray, default window 13) against
+    scipy.signal.wiener applied the way the reference applies it, and the script's CCC lines on top."""
+    import numpy as np
+    from scipy.signal import wiener
+    from m3t_b200.models.utils import concordance_cc2_np, smooth_predictions
+    rng = np.random.default_rng(seed)
+    errs = {"wiener_api": 0.0, "ccc_api": 0.0}
+    for n in (37, 400, 5000):
+        pred = torch.from_numpy(np.tanh(rng.standard_normal(n).cumsum() * 0.1).astype(np.float32))
+        gt = np.clip(pred.numpy() * 0.7 + rng.standard_normal(n).astype(np.float32) * 0.2, -1, 1)
+        gt[rng.integers(0, n, 3)] = -5.0
+        for window in (35, 13):
+            got = smooth_predictions(pred, window, mode="wiener") if window == 35 else smooth_predictions(pred.numpy())
+            want = np.apply_along_axis(lambda x: wiener(x, window), 0, pred.numpy())
+            assert got.dtype == np.float64 and got.shape == want.shape
+            errs["wiener_api"] = max(errs["wiener_api"], float(np.abs(got - want).max()))
+            valid = gt >= -1
+            errs["ccc_api"] = max(errs["ccc_api"], abs(float(concordance_cc2_np(got[valid], gt[valid])) -
+                                                       float(concordance_cc2_np(want[valid], gt[valid]))))
+    two = np.tanh(rng.standard_normal((300, 2)).cumsum(0) * 0.1).astype(np.float32)
+    want = np.apply_along_axis(lambda x: wiener(x, 35), 0, two)
+    errs["wiener_api"] = max(errs["wiener_api"], float(np.abs(smooth_predictions(two, 35) - want).max()))
+    return errs
+
+
+CASES["smooth_predictions_api"] = (case_smooth_predictions_api, _c())
+TOLS["wiener_api"] = 1e-10
+TOLS["ccc_api"] = 1e-10
+
+
 if __name__ == "__main__":
     name = sys.argv[1]
     errs = run_case(name)

@@ -446,3 +446,18 @@ def test_fit_on_synthetic_tree_with_stub_forward(tmp_path, monkeypatch):
     hp.test_on_val = False
     with pytest.raises(RuntimeError, match="m3t_overlap_add_f32"):
         tr.test(m)
+
+
+@pytest.mark.skipif(not _refload.available() or torch.cuda.is_available(), reason="reference tree + no GPU")
+def test_reference_smoothing_script_resolves_its_imports(tmp_path):
+    """get_smoothed_ccc.py, unmodified, through the launcher: `models.utils.smooth_predictions / concordance_cc2_np`
+    resolve to this build and the script reaches the device filter, which refuses to run without a GPU (its numerics
+    are the `smooth_predictions_api` / `postproc_eval` GPU cases)."""
+    track = torch.linspace(-1, 1, 50)
+    torch.save({k: {"vid": track.clone()} for k in ("valence_gt", "arousal_gt", "valence_pred", "arousal_pred")},
+               tmp_path / "predictions_val.pt")
+    r = subprocess.run([sys.executable, "-m", "m3t_b200.run", os.path.join(_refload.REFERENCE_ROOT,
+                                                                           "get_smoothed_ccc.py")],
+                       capture_output=True, text=True, timeout=300, env=dict(os.environ, PYTHONPATH=ROOT),
+                       cwd=str(tmp_path))
+    assert r.returncode != 0 and "m3t_wiener1d_f64" in r.stderr, r.stderr[-1500:]
