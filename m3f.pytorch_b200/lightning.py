@@ -10,19 +10,24 @@ schedulers (ReduceLROnPlateau on `val_loss`), best-`val_loss` checkpoint under
 `<default_save_path>/lightning_logs/version_N/checkpoints/_ckpt_epoch_E.ckpt`.
 
 B200 design instead of Lightning's: ONE process per GPU.  `distributed_backend='ddp'` joins the process group that
-`torchrun` set up (or spawns one rank per listed GPU when started as a plain `python train.py`); the gradient exchange
-and the Adam update are `engine.TrainEngine`'s flat-arena all-reduce + fused clip/Adam kernels (generic torch
-optimizers — the reference's SGD option — take a flat-buffer all-reduce and `optimizer.step()`).  `'dp'` (Lightning:
+`torchrun` set up; the gradient exchange and the Adam update are `engine.TrainEngine`'s flat-arena all-reduce + fused clip/Adam kernels (generic torch
+optimizers — the reference's SGD option — take a flat-buffer all-reduce and `optimizer.step()`).  Started as a plain
+`python train.py --gpus 0,1 --distributed` (the reference's README usage; Lightning 0.6 used mp.spawn there), rank 0
+re-launches its own command line once per additional GPU with RANK / LOCAL_RANK / WORLD_SIZE / MASTER_* set — the
+children run the script from the top like torchrun workers and meet rank 0 in `fit` / `test`.  `'dp'` (Lightning:
 replicas in threads of one process) runs on the first listed GPU.  Validation outputs of all ranks are gathered and
 `validation_end` / `test_end` run once on rank 0 (Lightning 0.6 ran them per rank on partial data, which lets
 ReduceLROnPlateau diverge between ranks); the result is broadcast.
 """
 import argparse
+import atexit
 import functools
 import logging
 import os
 import re
 import socket
+import subprocess
+import sys
 import warnings
 
 import torch
@@ -167,10 +172,30 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _spawn_entry(local_rank, trainer, model, mode, world, port):
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(local_rank),
-                      LOCAL_RANK=str(local_rank), WORLD_SIZE=str(world))
-    trainer._run(model, mode)
+_children = []
+
+
+def _reap_children(grace=600):
+    """Rank 0 waits for the ranks it launched (atexit); after a failure on rank 0 they are stopped at once, since
+    they would otherwise sit in a collective until its timeout."""
+    for proc in _children:
+        try:
+            proc.wait(timeout=grace)
+        except subprocess.TimeoutExpired:
+            proc.terminate()
+    del _children[:]
+
+
+def relaunch_ranks(world):
+    """Make this process rank 0 of `world` and start ranks 1..world-1 as copies of its own command line
+    (`sys.orig_argv`), one process per GPU, rendezvous on 127.0.0.1."""
+    port = _free_port()
+    common = dict(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), WORLD_SIZE=str(world))
+    for rank in range(1, world):
+        env = dict(os.environ, RANK=str(rank), LOCAL_RANK=str(rank), **common)
+        _children.append(subprocess.Popen(list(sys.orig_argv), env=env))
+    os.environ.update(RANK="0", LOCAL_RANK="0", **common)
+    atexit.register(_reap_children)
 
 
 # ----------------------------------------------------------------------------------------------- trainer
@@ -184,7 +209,7 @@ class Trainer:
                  row_log_interval=10, add_row_log_interval=None, distributed_backend=None, use_amp=False,
                  print_nan_grads=False, weights_summary="full", weights_save_path=None, amp_level="O1",
                  nb_sanity_val_steps=5, num_sanity_val_steps=None, truncated_bptt_steps=None,
-                 resume_from_checkpoint=None, max_steps=None, **unused):
+                 resume_from_checkpoint=None, max_steps=None, num_processes=1, **unused):
         if unused:
             warnings.warn("Trainer: ignoring arguments %s" % sorted(unused))
         if use_amp:
@@ -209,6 +234,7 @@ class Trainer:
         if self.nb_gpu_nodes != 1:
             raise NotImplementedError("one node (8 GPUs over NVSwitch) is the scope; nb_gpu_nodes must be 1")
         self.gpus = gpus
+        self.num_processes = int(num_processes)     # CPU ranks (gloo) when gpus is empty: host-logic tests
         self.distributed_backend = distributed_backend
         self.resume_from_checkpoint = resume_from_checkpoint
         self.current_epoch = 0
@@ -234,12 +260,15 @@ class Trainer:
     # ------------------------------------------------------------------ process layout
     def _launch(self, model, mode):
         ids = parse_gpus(self.gpus)
+        world = len(ids) if ids else self.num_processes
         under_launcher = int(os.environ.get("WORLD_SIZE", "1")) > 1
-        if self.distributed_backend == "ddp" and not under_launcher and len(ids) > 1:
-            import torch.multiprocessing as mp
-            mp.spawn(_spawn_entry, nprocs=len(ids), args=(self, model, mode, len(ids), _free_port()))
-            return
-        self._run(model, mode)
+        if self.distributed_backend == "ddp" and not under_launcher and world > 1:
+            relaunch_ranks(world)
+        try:
+            self._run(model, mode)
+        except BaseException:
+            _reap_children(grace=0)
+            raise
 
     def _setup_process(self, model):
         ids = parse_gpus(self.gpus)

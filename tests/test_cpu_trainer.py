@@ -461,3 +461,20 @@ def test_reference_smoothing_script_resolves_its_imports(tmp_path):
                        capture_output=True, text=True, timeout=300, env=dict(os.environ, PYTHONPATH=ROOT),
                        cwd=str(tmp_path))
     assert r.returncode != 0 and "m3t_wiener1d_f64" in r.stderr, r.stderr[-1500:]
+
+
+def test_plain_python_start_relaunches_one_process_per_rank(tmp_path):
+    """`python script.py` with distributed_backend='ddp' and 2 ranks (the reference's README start, without torchrun):
+    rank 0 re-launches its own command line as rank 1; two processes in total, identical parameters, fit followed by
+    test in the same script does not launch again."""
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT"):
+        env.pop(k, None)
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "scripts", "relaunch_script.py"), str(tmp_path)],
+                       capture_output=True, text=True, timeout=300, env=env, cwd=str(tmp_path))
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-3000:]
+    started = sorted(open(f).read() for f in glob.glob(str(tmp_path / "started_*")))
+    assert started == ["1", "none"], started          # the launched copy saw RANK=1; the original had no RANK yet
+    ranks = [open(tmp_path / ("rank_%d" % i)).read().split() for i in (0, 1)]
+    assert ranks[0][0] == ranks[1][0] == "2" and ranks[0][1] == ranks[1][1], ranks
+    assert (tmp_path / "toy_test.pt").exists()
