@@ -216,6 +216,9 @@ class Trainer:
             raise NotImplementedError("use_amp: the kernels already run bf16 operands with fp32 accumulation")
         if accumulate_grad_batches != 1 or truncated_bptt_steps:
             raise NotImplementedError("accumulate_grad_batches / truncated_bptt_steps are not used by the reference")
+        if resume_from_checkpoint:
+            raise NotImplementedError("resume_from_checkpoint: the reference restores weights through "
+                                      "model.load_from_checkpoint / load_state_dict (train.py:26-30)")
         self.max_epochs = max_nb_epochs if max_nb_epochs is not None else max_epochs
         self.max_steps = max_steps
         self.gradient_clip_val = float(gradient_clip_val or 0)

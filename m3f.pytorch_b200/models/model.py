@@ -213,7 +213,6 @@ class AffWild2VA(_Base):
         overlapped=True: half-stride windows are summed on their frames and every frame from window//2 on is halved
         (reference :279-297, :352-366) — `m3t_overlap_add_f32`, all videos in one launch."""
         names, vid_of, starts, segs = [], {}, [], []
-        order = []
         for out in outputs:
             for j, name in enumerate(out['vid_names']):
                 vid_of.setdefault(name, len(vid_of))
