@@ -478,3 +478,95 @@ def test_plain_python_start_relaunches_one_process_per_rank(tmp_path):
     ranks = [open(tmp_path / ("rank_%d" % i)).read().split() for i in (0, 1)]
     assert ranks[0][0] == ranks[1][0] == "2" and ranks[0][1] == ranks[1][1], ranks
     assert (tmp_path / "toy_test.pt").exists()
+
+
+@pytest.mark.skipif(not _refload.available(), reason="reference tree not present")
+@pytest.mark.parametrize("loss,expr", [("ccc_mtl", "some"), ("ccc_mtl", "none"), ("mse_mtl", "some"), ("ccc", "some")])
+def test_step_hooks_match_reference_methods(loss, expr):
+    """training_step / validation_step / test_step of the task module against the reference's own methods, both fed the
+    same network output (`forward` replaced by a constant): loss, every logged term, expression accuracy, and the
+    per-clip lists handed to validation_end / test_end."""
+    ref_cls = _refload.load("model").AffWild2VA
+    from m3t_b200.models.model import AffWild2VA
+    hp = _refload.hparams(modality="audio", loss=loss, window=6)
+    g = torch.Generator().manual_seed(4)
+    B, T, C = 3, 6, 9 if "mtl" in loss else 2
+    y_hat = torch.randn(B, T, C, generator=g)
+    batch = {"audio": torch.zeros(B, T, 200),
+             "label_valence": torch.rand(B, T, generator=g) * 2 - 1, "label_arousal": torch.rand(B, T, generator=g) * 2 - 1,
+             "class_expr": torch.randint(0, 7, (B, T), generator=g),
+             "expr_valid": (torch.rand(B, T, generator=g) > 0.4) if expr == "some" else torch.zeros(B, T, dtype=torch.bool),
+             "length": torch.tensor([6, 4, 1]), "vid_name": ["a", "a", "b"], "start": torch.tensor([0, 6, 0])}
+    torch.manual_seed(0)
+    ref, mine = ref_cls(hp), AffWild2VA(hp)
+    for m in (ref, mine):
+        m.forward = lambda b: y_hat.clone().requires_grad_(True)
+    want, got = ref.training_step(batch, 0), mine.training_step(batch, 0)
+    assert want.keys() == got.keys()
+    assert torch.allclose(want["loss"], got["loss"], atol=1e-6)
+    for part in ("progress_bar", "log"):
+        assert want[part].keys() == got[part].keys(), part
+        for k in want[part]:
+            assert abs(float(want[part][k]) - float(got[part][k])) < 1e-6, (part, k)
+    got["loss"].backward()                                   # the returned loss carries the graph
+    for name in ("validation_step", "test_step"):
+        for flag in (False, True):
+            hp.test_on_val = flag
+            w, o = getattr(ref, name)(batch, 0), getattr(mine, name)(batch, 0)
+            assert w.keys() == o.keys(), (name, flag)
+            for k in w:
+                if k == "vid_names":
+                    assert w[k] == o[k]
+                elif k == "start_frames":
+                    assert torch.equal(w[k], o[k])
+                else:
+                    assert len(w[k]) == len(o[k]) and all(torch.equal(a, b) for a, b in zip(w[k], o[k])), (name, k)
+
+
+@pytest.mark.skipif(not _refload.available(), reason="reference tree not present")
+@pytest.mark.parametrize("optimizer,scheduler,freeze", [("adam", "plateau", False), ("adam", "exp", False),
+                                                        ("sgd", "cyclic", False), ("adam", "plateau", True)])
+def test_configure_optimizers_matches_reference(optimizer, scheduler, freeze):
+    """Same optimiser class and hyper-parameters, same scheduler class and settings, same set of trainable parameters
+    as the reference's configure_optimizers (models/model.py:375-407)."""
+    ref_cls = _refload.load("model").AffWild2VA
+    from m3t_b200.models.model import AffWild2VA
+    hp = _refload.hparams(modality="audiovisual", backbone="resnet", fusion_type="attention", split_layer=5, window=4,
+                          optimizer=optimizer, scheduler=scheduler, freeze_enc=freeze, learning_rate=3e-4)
+
+    def unpack(conf):
+        return (conf[0][0], conf[1][0]) if isinstance(conf, (list, tuple)) else (conf, None)
+
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        try:
+            ref = ref_cls(hp)
+            r_opt, r_sch = unpack(ref.configure_optimizers())
+        except TypeError:            # ReduceLROnPlateau(verbose=...) no longer exists in this torch: compare what can be
+            ref, r_opt, r_sch = None, None, None
+        mine = AffWild2VA(hp)
+        m_opt, m_sch = unpack(mine.configure_optimizers())
+    if scheduler == "cyclic":
+        r_sch, m_sch = (getattr(ref, "cyclic_scheduler", None) if ref is not None else None), mine.cyclic_scheduler
+    if ref is None:
+        assert scheduler == "plateau" and isinstance(m_sch, torch.optim.lr_scheduler.ReduceLROnPlateau)
+        assert (m_sch.factor, m_sch.patience, m_sch.min_lrs) == (hp.decay_factor, 3, [1e-6])
+        ref = ref_cls(hp)
+        if freeze:                   # the freezing happens before the optimiser is built: still comparable
+            try:
+                ref.configure_optimizers()
+            except TypeError:
+                pass
+    else:
+        assert type(r_opt) is type(m_opt) and type(r_sch) is type(m_sch)
+        keys = ("lr", "weight_decay", "betas", "eps", "momentum", "nesterov", "dampening")
+        a, b = r_opt.param_groups[0], m_opt.param_groups[0]
+        assert {k: a[k] for k in keys if k in a} == {k: b[k] for k in keys if k in b}
+        for k in ("gamma", "factor", "patience", "min_lrs", "base_lrs", "max_lrs", "total_size", "step_ratio"):
+            if hasattr(r_sch, k):
+                assert getattr(r_sch, k) == getattr(m_sch, k), k
+    assert [n for n, p in ref.named_parameters() if p.requires_grad] == \
+        [n for n, p in mine.named_parameters() if p.requires_grad]
+    assert sum(p.numel() for p in m_opt.param_groups[0]["params"]) == \
+        sum(p.numel() for p in mine.parameters() if p.requires_grad)
