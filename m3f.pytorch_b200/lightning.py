@@ -198,6 +198,37 @@ def relaunch_ranks(world):
     atexit.register(_reap_children)
 
 
+class EarlyStopping:
+    """Keras-style early stopping as Lightning 0.6 shipped it: stop when `monitor` has not improved by more than
+    `min_delta` for `patience` consecutive checks.  strict=False ignores a missing metric."""
+
+    def __init__(self, monitor="val_loss", min_delta=0.0, patience=3, verbose=False, mode="min", strict=True):
+        if mode not in ("min", "max"):
+            raise ValueError("mode must be 'min' or 'max'")
+        self.monitor, self.min_delta, self.patience, self.verbose, self.strict = monitor, min_delta, patience, verbose, \
+            strict
+        self.sign = 1.0 if mode == "min" else -1.0
+        self.wait, self.best, self.stopped_epoch = 0, float("inf"), 0
+
+    def on_epoch_end(self, epoch, metrics):
+        """True when training should stop."""
+        current = metrics.get(self.monitor)
+        if current is None:
+            if self.strict:
+                raise RuntimeError("early stopping is conditioned on %r, which validation_end did not return"
+                                   % self.monitor)
+            return False
+        score = self.sign * current
+        if score + self.min_delta < self.best:
+            self.best, self.wait = score, 0
+            return False
+        self.wait += 1
+        if self.wait >= self.patience:
+            self.stopped_epoch = epoch
+            return True
+        return False
+
+
 # ----------------------------------------------------------------------------------------------- trainer
 class Trainer:
     def __init__(self, logger=True, checkpoint_callback=True, early_stop_callback=None, default_save_path=None,
@@ -220,7 +251,18 @@ class Trainer:
             raise NotImplementedError("resume_from_checkpoint: the reference restores weights through "
                                       "model.load_from_checkpoint / load_state_dict (train.py:26-30)")
         self.max_epochs = max_nb_epochs if max_nb_epochs is not None else max_epochs
+        self.min_epochs = min_nb_epochs if min_nb_epochs is not None else min_epochs
         self.max_steps = max_steps
+        # Lightning 0.6: True -> stop on val_loss (patience 3), an error if it is missing; None (what train.py:33
+        # passes, and the default) -> the same callback but tolerant of a missing val_loss; False -> disabled
+        if early_stop_callback is True:
+            self.early_stop_callback = EarlyStopping("val_loss", patience=3, strict=True)
+        elif early_stop_callback is None:
+            self.early_stop_callback = EarlyStopping("val_loss", patience=3, strict=False)
+        elif not early_stop_callback:
+            self.early_stop_callback = None
+        else:
+            self.early_stop_callback = early_stop_callback
         self.gradient_clip_val = float(gradient_clip_val or 0)
         self.default_save_path = default_save_path or os.getcwd()
         self.weights_save_path = weights_save_path
@@ -430,6 +472,13 @@ class Trainer:
             if self.plateau is not None and "val_loss" in self.callback_metrics:
                 self.plateau.step(self.callback_metrics["val_loss"])
             self._maybe_checkpoint(model, epoch)
+            validated = val_loaders and (epoch + 1) % self.check_val_every_n_epoch == 0
+            if self.early_stop_callback is not None and validated and epoch >= self.min_epochs - 1 \
+                    and self.early_stop_callback.on_epoch_end(epoch, self.callback_metrics):
+                if self.rank == 0:
+                    log.info("early stopping after epoch %d (%s did not improve for %d checks)", epoch,
+                             self.early_stop_callback.monitor, self.early_stop_callback.patience)
+                stop = True
             if stop:
                 break
 

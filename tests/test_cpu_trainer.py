@@ -240,8 +240,9 @@ def test_trainer_plateau_scheduler_sees_val_loss(tmp_path, monkeypatch):
     Toy = _toy_module()
     m = Toy(_toy_hparams(scheduler="plateau", lr=0.5))         # lr far too high: val_loss stops improving at once
     tr = Trainer(gradient_clip_val=0, default_save_path=str(tmp_path), max_epochs=6, nb_sanity_val_steps=0,
-                 show_progress_bar=False)
+                 show_progress_bar=False, early_stop_callback=False)
     tr.fit(m)
+    assert tr.current_epoch == 5
     lr_now = tr.optimizers[0].param_groups[0]["lr"]
     assert lr_now < 0.5 and tr.engine.lr in (lr_now, lr_now * 2)   # engine.lr is refreshed at each step
     assert tr.plateau is not None and tr.lr_schedulers == []
@@ -570,3 +571,38 @@ def test_configure_optimizers_matches_reference(optimizer, scheduler, freeze):
         [n for n, p in mine.named_parameters() if p.requires_grad]
     assert sum(p.numel() for p in m_opt.param_groups[0]["params"]) == \
         sum(p.numel() for p in mine.parameters() if p.requires_grad)
+
+
+def test_early_stopping_as_lightning_06(tmp_path, monkeypatch):
+    """`early_stop_callback=None` (what train.py passes) is Lightning 0.6's default callback: val_loss, patience 3,
+    tolerant of a missing metric; False disables it; True insists on the metric."""
+    from m3t_b200 import lightning as pl
+    monkeypatch.chdir(tmp_path)
+    Toy = _toy_module()
+
+    class Stuck(Toy):
+        def validation_end(self, outputs):
+            self.ended.append(None)
+            return {"val_loss": torch.tensor(1.0 + 0.01 * len(self.ended))}       # never improves after the first
+
+    m = Stuck(_toy_hparams())
+    tr = pl.Trainer(early_stop_callback=None, max_epochs=20, nb_sanity_val_steps=0, default_save_path=str(tmp_path),
+                    show_progress_bar=False)
+    tr.fit(m)
+    assert tr.current_epoch == 3 and tr.early_stop_callback.stopped_epoch == 3      # best at 0, then 3 bad checks
+    assert len(glob.glob(str(tmp_path / "lightning_logs" / "version_0" / "checkpoints" / "*.ckpt"))) == 1
+
+    class Silent(Toy):
+        def validation_end(self, outputs):
+            return {}
+
+    tr = pl.Trainer(early_stop_callback=None, max_epochs=5, nb_sanity_val_steps=0, default_save_path=str(tmp_path),
+                    show_progress_bar=False, checkpoint_callback=False)
+    tr.fit(Silent(_toy_hparams()))
+    assert tr.current_epoch == 4                                                     # non-strict: keeps going
+    with pytest.raises(RuntimeError, match="val_loss"):
+        pl.Trainer(early_stop_callback=True, max_epochs=5, nb_sanity_val_steps=0, default_save_path=str(tmp_path),
+                   show_progress_bar=False, checkpoint_callback=False).fit(Silent(_toy_hparams()))
+    es = pl.EarlyStopping("acc", min_delta=0.1, patience=2, mode="max")
+    assert [es.on_epoch_end(i, {"acc": a}) for i, a in enumerate((0.5, 0.55, 0.7, 0.75, 0.6))] == \
+        [False, False, False, False, True]
