@@ -27,31 +27,37 @@ def _wn_weight(conv):
     return torch._weight_norm(conv.weight_v, conv.weight_g, 0)
 
 
+def _causal_conv(c_in, c_out, kernel_size, dilation, padding):
+    """Weight-normed Conv1d holding the reference's parameters (`bias`, `weight_g`, `weight_v`); never called as a
+    module here — forward_cl feeds its weights to the implicit-GEMM kernel."""
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")          # torch deprecates this weight_norm; the key names depend on it
+        return weight_norm(nn.Conv1d(c_in, c_out, kernel_size, stride=1, padding=padding, dilation=dilation))
+
+
 class TemporalBlock(nn.Module):
     def __init__(self, n_inputs, n_outputs, kernel_size, stride, dilation, padding, dropout=0.2):
         super().__init__()
         assert stride == 1, "the reference only builds stride-1 temporal blocks"
-        with warnings.catch_warnings():
-            warnings.simplefilter("ignore")
-            self.conv1 = weight_norm(nn.Conv1d(n_inputs, n_outputs, kernel_size, stride=stride, padding=padding,
-                                               dilation=dilation))
-            self.conv2 = weight_norm(nn.Conv1d(n_outputs, n_outputs, kernel_size, stride=stride, padding=padding,
-                                               dilation=dilation))
-        self.chomp1, self.relu1, self.dropout1 = Chomp1d(padding), nn.ReLU(), nn.Dropout(dropout)
-        self.chomp2, self.relu2, self.dropout2 = Chomp1d(padding), nn.ReLU(), nn.Dropout(dropout)
-        self.net = nn.Sequential(self.conv1, self.chomp1, self.relu1, self.dropout1,
-                                 self.conv2, self.chomp2, self.relu2, self.dropout2)
-        self.downsample = nn.Conv1d(n_inputs, n_outputs, 1) if n_inputs != n_outputs else None
-        self.relu = nn.ReLU()
         self.dilation, self.padding = dilation, padding
+        stages = []
+        for i, c_in in ((1, n_inputs), (2, n_outputs)):
+            stage = (("conv", _causal_conv(c_in, n_outputs, kernel_size, dilation, padding)),
+                     ("chomp", Chomp1d(padding)), ("relu", nn.ReLU()), ("dropout", nn.Dropout(dropout)))
+            for name, mod in stage:
+                setattr(self, "%s%d" % (name, i), mod)          # conv1, chomp1, relu1, dropout1, conv2, ...
+                stages.append(mod)
+        self.net = nn.Sequential(*stages)                       # the reference's `net.{0,4}` aliases of conv1 / conv2
+        self.downsample = None if n_inputs == n_outputs else nn.Conv1d(n_inputs, n_outputs, 1)
+        self.relu = nn.ReLU()
         self.init_weights()
 
     def init_weights(self):
-        # as in the reference, this writes the derived `.weight`, which weight_norm recomputes at the next forward
-        self.conv1.weight.data.normal_(0, 0.01)
-        self.conv2.weight.data.normal_(0, 0.01)
-        if self.downsample is not None:
-            self.downsample.weight.data.normal_(0, 0.01)
+        # N(0, 0.01) lands in the DERIVED `.weight` of the weight-normed convs, which weight_norm recomputes from
+        # weight_g / weight_v at the next forward (so only the plain 1x1 `downsample` really gets it, SURVEY app. A)
+        for conv in (self.conv1, self.conv2, self.downsample):
+            if conv is not None:
+                conv.weight.data.normal_(0, 0.01)
 
     def forward_cl(self, x):
         h = x
