@@ -606,3 +606,30 @@ def test_early_stopping_as_lightning_06(tmp_path, monkeypatch):
     es = pl.EarlyStopping("acc", min_delta=0.1, patience=2, mode="max")
     assert [es.on_epoch_end(i, {"acc": a}) for i, a in enumerate((0.5, 0.55, 0.7, 0.75, 0.6))] == \
         [False, False, False, False, True]
+
+
+def test_trainer_loop_controls(tmp_path, monkeypatch):
+    """check_val_every_n_epoch, fast_dev_run, train_percent_check and max_steps bound the loops as in Lightning 0.6."""
+    from m3t_b200.lightning import Trainer
+    monkeypatch.chdir(tmp_path)
+    Toy = _toy_module()
+    common = dict(default_save_path=str(tmp_path), show_progress_bar=False, nb_sanity_val_steps=0,
+                  early_stop_callback=False, checkpoint_callback=False)
+    m = Toy(_toy_hparams())
+    Trainer(max_epochs=4, check_val_every_n_epoch=2, **common).fit(m)
+    assert len(m.ended) == 2 and m.batch_ends == 4 * 8
+    m = Toy(_toy_hparams())
+    tr = Trainer(max_epochs=4, fast_dev_run=True, **common)
+    tr.fit(m)
+    assert m.batch_ends == 1 and len(m.ended) == 1 and len(m.ended[0]) == 8 and tr.current_epoch == 0
+    m = Toy(_toy_hparams())
+    Trainer(max_epochs=2, train_percent_check=0.5, val_percent_check=0.25, **common).fit(m)
+    assert m.batch_ends == 2 * 4 and all(len(e) == 2 * 8 for e in m.ended)
+    m = Toy(_toy_hparams())
+    tr = Trainer(max_epochs=10, max_steps=11, **common)
+    tr.fit(m)
+    assert tr.global_step == 11 and tr.current_epoch == 1
+    with pytest.raises(NotImplementedError):
+        Trainer(resume_from_checkpoint="x.ckpt")
+    with pytest.raises(NotImplementedError):
+        Trainer(use_amp=True)
