@@ -199,6 +199,11 @@ int m3t_zero_insert2(const void* dy, void* up, int N, int P, int Q, int Hup, int
 int m3t_add_bf16(const void* a, const void* b, void* out, long long n, void* stream);
 int m3t_colsum_bf16(const void* x, long long ld, long long rows, int cols, float* out, void* stream);
 int m3t_relu_bwd_bf16(const void* dy, const void* out, void* dz, long long n, void* stream);
+/* Inverted dropout of nn.Dropout(p) in the temporal blocks (models/tcn.py:23,29,35-36), bf16, n % 8 == 0:
+ * y[i] = u_i >= floor(p * 2^32) ? x[i] / (1 - p) : 0 with u_i = top 32 bits of splitmix64(seed + (i+1) * 0x9E3779B97F4A7C15).
+ * Counter-based: calling it on the gradient with the same seed applies the same mask (nothing is stored).  The mask
+ * stream is this library's own (PyTorch's Philox stream is not reproduced); oracle/dropout.py restates it bit for bit. */
+int m3t_dropout_bf16(const void* x, void* y, long long n, float p, unsigned long long seed, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Bidirectional GRU layer recurrence (gru.cu), persistent kernel, both directions in one launch.

@@ -1019,6 +1019,28 @@ __global__ void add_bf16_kernel(const __nv_bfloat16* __restrict__ a, const __nv_
   }
 }
 
+// Inverted dropout with a counter-based generator (splitmix64 of seed + (i+1)*golden, top 32 bits): element i is
+// kept iff u_i >= thresh.  Stateless, so the backward pass re-derives the mask from (seed, i) instead of reading one.
+__device__ __forceinline__ unsigned dropout_u32(unsigned long long seed, long long i) {
+  unsigned long long z = seed + (unsigned long long)(i + 1) * 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  return (unsigned)(z >> 32);
+}
+
+__global__ void dropout_bf16_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, long long nvec,
+                                    unsigned thresh, float scale, unsigned long long seed) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec; i += stride) {
+    float v[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(x) + i), v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = dropout_u32(seed, i * 8 + j) >= thresh ? v[j] * scale : 0.f;
+    reinterpret_cast<uint4*>(y)[i] = pack8(v);
+  }
+}
+
 // out_bf16[r][k] = idx[k] >= 0 ? w[r*row_stride + idx[k]] : 0      (filter re-layout, e.g. the space-to-depth stem)
 __global__ void gather_pack_kernel(const float* __restrict__ w, const int* __restrict__ idx,
                                    __nv_bfloat16* __restrict__ out, int rows, long long row_stride, int K) {
@@ -1487,6 +1509,16 @@ extern "C" int m3t_colsum_bf16(const void* x, long long ld, long long rows, int 
 extern "C" int m3t_relu_bwd_bf16(const void* dy, const void* out, void* dz, long long n, void* stream) {
   if (n % 8) return -1;
   relu_bwd_kernel<<<ew_blocks(n / 8), kEwThreads, 0, ST(stream)>>>(CBF(dy), CBF(out), BF(dz), n / 8);
+  count_launch();
+  return launch_status();
+}
+
+extern "C" int m3t_dropout_bf16(const void* x, void* y, long long n, float p, unsigned long long seed, void* stream) {
+  if (n % 8 || !(p >= 0.f) || !(p < 1.f)) return -1;
+  const double t = (double)p * 4294967296.0;
+  const unsigned thresh = t >= 4294967295.0 ? 4294967295u : (unsigned)t;
+  dropout_bf16_kernel<<<ew_blocks(n / 8), kEwThreads, 0, ST(stream)>>>(CBF(x), BF(y), n / 8, thresh, 1.f / (1.f - p),
+                                                                       seed);
   count_launch();
   return launch_status();
 }

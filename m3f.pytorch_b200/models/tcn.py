@@ -64,7 +64,10 @@ class TemporalBlock(nn.Module):
         for conv, drop in ((self.conv1, self.dropout1), (self.conv2, self.dropout2)):
             h = ops.Conv1dBiasAct.apply(h, _wn_weight(conv), conv.bias, self.dilation, self.padding, 0, True)
             if self.training and drop.p > 0:
-                h = torch.nn.functional.dropout(h, drop.p, True)
+                if ops.fused_dropout_enabled():
+                    h = ops.DropoutFn.apply(h, drop.p)
+                else:
+                    h = torch.nn.functional.dropout(h, drop.p, True)
         if self.downsample is None:
             res = x
         else:

@@ -6,6 +6,7 @@ are sequences of C-ABI calls (raw.py -> libm3t_b200.so).  Activations between un
 Nothing here falls back to stock PyTorch kernels for the ops the library implements; torch is used for memory
 (torch.empty / zeros on the current stream), autograd bookkeeping and tiny parameter-side glue.
 """
+import os
 import weakref
 
 import torch
@@ -635,6 +636,29 @@ class AddReLU(torch.autograd.Function):
         (out,) = ctx.saved_tensors
         dz = raw.relu_bwd(dout.contiguous(), out)
         return dz, dz
+
+
+class DropoutFn(torch.autograd.Function):
+    """Inverted dropout on a bf16 tensor (nn.Dropout in the temporal blocks, models/tcn.py:23,29): one streaming pass
+    forward, the same pass on the gradient backward — the mask is a pure function of (seed, element index), so it is
+    re-derived instead of stored.  The seed is drawn from torch's CPU generator, so `torch.manual_seed` makes a run
+    reproducible (the mask stream itself is this library's, not PyTorch's Philox)."""
+
+    @staticmethod
+    def forward(ctx, x, p):
+        ctx.p = float(p)
+        ctx.seed = int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).item())
+        return raw.dropout_bf16(x.contiguous(), ctx.p, ctx.seed)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return raw.dropout_bf16(dy.contiguous(), ctx.p, ctx.seed), None
+
+
+def fused_dropout_enabled():
+    """M3T_FUSED_DROPOUT=1 routes training-mode TCN dropout through DropoutFn; until that kernel has been confirmed on
+    a B200 (tests/gpu_cases.py::case_dropout) the default stays torch.nn.functional.dropout."""
+    return os.environ.get("M3T_FUSED_DROPOUT", "0") == "1"
 
 
 # ------------------------------------------------------------------------------------------------------------

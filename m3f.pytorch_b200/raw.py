@@ -1,6 +1,8 @@
 """Raw tensor-level wrappers over the C ABI (no autograd).  Arguments are CUDA torch tensors already in the
 layout the ABI wants (channels-last bf16 activations, packed bf16 filters); outputs are allocated here with
 torch.empty so they live in PyTorch's caching allocator and on the current stream."""
+import ctypes
+
 import torch
 
 from . import lib as L
@@ -556,6 +558,13 @@ def relu_bwd(dy, out):
     dz = torch.empty_like(dy)
     L.check(_lib().m3t_relu_bwd_bf16(L.ptr(dy), L.ptr(out), L.ptr(dz), L.i64(dy.numel()), L.stream_ptr()), "relu_bwd")
     return dz
+
+
+def dropout_bf16(x, p, seed):
+    y = torch.empty_like(x)
+    L.check(_lib().m3t_dropout_bf16(L.ptr(x), L.ptr(y), L.i64(x.numel()), L.f32(p), ctypes.c_ulonglong(int(seed)),
+                                    L.stream_ptr()), "dropout_bf16")
+    return y
 
 
 def gru_fwd(gi, w_hh_bf16, b_hh, B, T, H, want_saved, want_f32=False):

@@ -1492,6 +1492,40 @@ TOLS["wiener_api"] = 1e-10
 TOLS["ccc_api"] = 1e-10
 
 
+def case_dropout(seed=0):
+    """m3t_dropout_bf16 vs oracle/dropout.py: the mask bit for bit, the scaled values (bf16 rounding only), the
+    backward pass (same mask on the gradient), and a TemporalBlock training step routed through it."""
+    import numpy as np
+    from m3t_b200 import ops, raw
+    from oracle import dropout as D
+    g = torch.Generator().manual_seed(seed)
+    errs = {}
+    x = (torch.randn((37, 24, 512), generator=g) + 3.0).bfloat16()        # no zeros: the mask is readable from y
+    for p, sd in ((0.2, 12345), (0.5, 2 ** 61 + 7), (0.0, 1)):
+        y = raw.dropout_bf16(x.cuda(), p, sd).cpu()
+        keep = D.keep_mask(sd, x.numel(), p).reshape(tuple(x.shape))
+        want = torch.from_numpy(D.dropout(x.float().numpy(), p, sd)).bfloat16()
+        errs["mask_exact_p%g" % p] = float(((y != 0).numpy() != keep).sum())
+        errs["values_p%g" % p] = _err(y.float(), want.float())
+    torch.manual_seed(seed)
+    xr = x.cuda().requires_grad_(True)
+    y = ops.DropoutFn.apply(xr, 0.2)
+    dy = torch.ones_like(y)
+    y.backward(dy)
+    errs["bwd_mask_exact"] = float(((xr.grad != 0) != (y != 0)).sum())
+    errs["bwd_scale"] = abs(float(xr.grad.float().max()) - 1.25) / 1.25
+    errs["keep_rate"] = abs(float((y != 0).float().mean()) - 0.8)
+    return errs
+
+
+CASES["dropout_bf16"] = (case_dropout, _c())
+for _k in ("mask_exact_p0.2", "mask_exact_p0.5", "mask_exact_p0", "bwd_mask_exact"):
+    TOLS[_k] = 0.5
+for _k in ("values_p0.2", "values_p0.5", "values_p0", "bwd_scale"):
+    TOLS[_k] = 4e-3                # one bf16 rounding of x * scale
+TOLS["keep_rate"] = 5e-3           # 454 656 draws: sigma = 6e-4
+
+
 if __name__ == "__main__":
     name = sys.argv[1]
     errs = run_case(name)

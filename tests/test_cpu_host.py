@@ -184,3 +184,21 @@ def test_split_operand_arithmetic_host_model():
     scale = ref.abs().max()
     assert (three - ref).abs().max() / scale < 2.0 ** -14
     assert (six - ref).abs().max() / scale < 2.0 ** -21
+
+
+def test_dropout_oracle_statistics():
+    """oracle/dropout.py (the restatement m3t_dropout_bf16 is checked against bit for bit on the GPU): keep rate,
+    determinism in (seed, index), independence of neighbours and of seeds, inverted-dropout scaling."""
+    import numpy as np
+    from oracle import dropout as D
+    n = 1 << 20
+    for p in (0.2, 0.5):
+        m = D.keep_mask(99, n, p)
+        assert abs(m.mean() - (1 - p)) < 4 * np.sqrt(p * (1 - p) / n)
+        assert np.array_equal(m, D.keep_mask(99, n, p)) and np.array_equal(m[:1000], D.keep_mask(99, 1000, p))
+        assert abs(np.corrcoef(m[:-1], m[1:])[0, 1]) < 5e-3 and abs(np.corrcoef(m, D.keep_mask(100, n, p))[0, 1]) < 5e-3
+    assert D.keep_mask(5, 4096, 0.0).all()
+    x = np.full(4096, 2.0, dtype=np.float32)
+    y = D.dropout(x, 0.2, 7)
+    assert set(np.unique(y)) == {0.0, 2.5}
+    assert D.uniform_u32(7, 4).tolist() == [1674306020, 72105175, 3868737664, 2503666544]   # splitmix64 in C (gcc)

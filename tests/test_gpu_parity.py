@@ -16,7 +16,9 @@ from tests import gpu_cases as G
 
 pytestmark = pytest.mark.gpu
 
-PROBES = {"probe_rowshift"}   # hardware-semantics probes: informational, run by tests/gpu_probe.py
+# hardware-semantics probes (informational) and cases not yet confirmed on a B200 (their code paths are off by default):
+# run by tests/gpu_probe.py only
+PROBES = {"probe_rowshift", "dropout_bf16"}
 
 
 @pytest.mark.parametrize("name", sorted(n for n in G.CASES if n not in PROBES))
