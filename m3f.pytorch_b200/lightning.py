@@ -139,6 +139,64 @@ def move_to(obj, device):
     return obj
 
 
+def _record_stream(obj, stream):
+    if torch.is_tensor(obj):
+        if obj.is_cuda:
+            obj.record_stream(stream)
+    elif isinstance(obj, dict):
+        for v in obj.values():
+            _record_stream(v, stream)
+    elif isinstance(obj, (list, tuple)):
+        for v in obj:
+            _record_stream(v, stream)
+
+
+class Prefetcher:
+    """Iterates a DataLoader one batch ahead of the consumer: the host->device copy of batch i+1 (pinned memory,
+    non-blocking, its own CUDA stream) overlaps the training step of batch i — 617 MB of float32 video per 256-clip
+    step is ~12 ms of PCIe time that would otherwise sit in front of every step.  The consumer's stream waits on the
+    copy's event and the tensors are `record_stream`-ed to it, so the allocator cannot hand their blocks to the next
+    copy while the step still reads them.  On the CPU it degenerates to a plain look-ahead."""
+
+    def __init__(self, loader, device):
+        self.it = iter(loader)
+        self.device = device
+        self.stream = torch.cuda.Stream(device) if device.type == "cuda" else None
+        self._ahead = None
+        self._issue()
+
+    def _issue(self):
+        try:
+            batch = next(self.it)
+        except StopIteration:
+            self._ahead = None
+            return
+        if self.stream is None:
+            self._ahead = (move_to(batch, self.device), None)
+            return
+        with torch.cuda.stream(self.stream):
+            on_dev = move_to(batch, self.device)
+            ready = torch.cuda.Event()
+            ready.record(self.stream)
+        self._ahead = (on_dev, ready)
+
+    def __iter__(self):
+        while self._ahead is not None:
+            batch, ready = self._ahead
+            if ready is not None:
+                cur = torch.cuda.current_stream(self.device)
+                cur.wait_event(ready)
+                _record_stream(batch, cur)
+            self._issue()           # the next copy is in flight before the consumer starts on this batch
+            yield batch
+
+
+def prefetch_enabled():
+    """M3T_TRAINER_PREFETCH=1: Trainer.fit feeds training_step through `Prefetcher`.  Opt-in until it has been timed
+    on a B200 (tests/bench_trainer.py); the default is the plain copy in front of each step."""
+    return os.environ.get("M3T_TRAINER_PREFETCH", "0") == "1"
+
+
 def _scalar(v):
     if torch.is_tensor(v):
         return float(v.detach().float().mean().cpu()) if v.numel() else float("nan")
@@ -442,10 +500,11 @@ class Trainer:
             model.train()
             model.on_epoch_start()
             n_batches = self._limit(len(train_loader), self.train_percent_check)
-            for bi, batch in enumerate(train_loader):
+            feed = Prefetcher(train_loader, self.device) if prefetch_enabled() else \
+                (move_to(b, self.device) for b in train_loader)
+            for bi, batch in enumerate(feed):
                 if bi >= n_batches:
                     break
-                batch = move_to(batch, self.device)
                 model.on_batch_start(batch)
                 out = model.training_step(batch, bi)
                 loss = out["loss"] if isinstance(out, dict) else out

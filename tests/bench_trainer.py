@@ -56,16 +56,21 @@ def main():
         def val_dataloader(self):
             return None
 
-    torch.manual_seed(12345)
-    m = Timed(hp)
-    BN.randomise_bn(m, 7)
-    tr = pl.Trainer(gradient_clip_val=1.0, max_epochs=1, gpus="0", nb_sanity_val_steps=0, checkpoint_callback=False,
-                    early_stop_callback=False, show_progress_bar=False, distributed_backend="dp")
-    tr.fit(m)
-    torch.cuda.synchronize()
-    ms = m.events[2].elapsed_time(m.events[-1]) / (len(m.events) - 3)
-    print(json.dumps({"arm": "Trainer.fit (training_step + host syncs + H2D per step)", "ms_per_step": ms,
-                      "frames_per_s": frames / ms * 1e3, "clips": clips, "steps": len(m.events) - 3}), flush=True)
+    for prefetch in ("0", "1"):
+        os.environ["M3T_TRAINER_PREFETCH"] = prefetch
+        torch.manual_seed(12345)
+        m = Timed(hp)
+        BN.randomise_bn(m, 7)
+        tr = pl.Trainer(gradient_clip_val=1.0, max_epochs=1, gpus="0", nb_sanity_val_steps=0,
+                        checkpoint_callback=False, early_stop_callback=False, show_progress_bar=False,
+                        distributed_backend="dp")
+        tr.fit(m)
+        torch.cuda.synchronize()
+        ms = m.events[2].elapsed_time(m.events[-1]) / (len(m.events) - 3)
+        print(json.dumps({"arm": "Trainer.fit (training_step + host syncs + H2D per step), prefetch=" + prefetch,
+                          "ms_per_step": ms, "frames_per_s": frames / ms * 1e3, "clips": clips,
+                          "steps": len(m.events) - 3}), flush=True)
+        del m, tr
 
     torch.manual_seed(12345)
     m2 = AffWild2VA(hp)
