@@ -105,3 +105,34 @@ def extract_melspec(task):
     except Exception as e:  # noqa: BLE001
         print('Exception on {}: {}'.format(src_wav, e))
         return -1
+
+
+def build_tasks(src_dir, dst_dir, frames_fps_csv='splits/frames_fps.csv'):
+    """(fps, wav path, npy path) for every video of at least 15 fps listed in splits/frames_fps.csv
+    (reference :31-39; slower videos get all-zero audio features in models/dataset.py:277-278)."""
+    tasks = []
+    with open(frames_fps_csv) as f:
+        for line in f.read().splitlines():
+            vid_name, _, fps = line.split(',')
+            if float(fps) >= 15:
+                tasks.append((float(fps), os.path.join(src_dir, vid_name + '.wav'),
+                              os.path.join(dst_dir, vid_name + '.npy')))
+    return tasks
+
+
+def main(argv=None):
+    """`python -m m3t_b200.process.extract_melspec <wav dir> <npy dir>`: the reference script's command line
+    (:27-46).  One process feeds the GPU file by file instead of a 16-process librosa pool."""
+    import sys
+    argv = sys.argv[1:] if argv is None else argv
+    src_dir, dst_dir = argv[0], argv[1]
+    tasks = build_tasks(src_dir, dst_dir)
+    for done, task in enumerate(tasks, 1):
+        result = extract_melspec(task)
+        if result <= 0:
+            print('Finished {}, result: {}, progress: {}/{}'.format(task[1], result, done, len(tasks)))
+    return 0
+
+
+if __name__ == '__main__':
+    raise SystemExit(main())

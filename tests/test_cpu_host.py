@@ -202,3 +202,23 @@ def test_dropout_oracle_statistics():
     y = D.dropout(x, 0.2, 7)
     assert set(np.unique(y)) == {0.0, 2.5}
     assert D.uniform_u32(7, 4).tolist() == [1674306020, 72105175, 3868737664, 2503666544]   # splitmix64 in C (gcc)
+
+
+def test_extract_melspec_task_list_and_error_contract(tmp_path, monkeypatch, capsys):
+    """process/extract_melspec.py keeps the reference script's contract: tasks for videos of >= 15 fps only, `_left` /
+    `_right` crops share the source wav, existing outputs are skipped (1), failures are reported and counted (-1)."""
+    from m3t_b200.process import extract_melspec as E
+    monkeypatch.chdir(tmp_path)
+    os.makedirs("splits")
+    with open("splits/frames_fps.csv", "w") as f:
+        f.write("a,100,30.0\nb_left,50,25.0\nc,80,12.0\n")
+    tasks = E.build_tasks("wavs", "out")
+    assert tasks == [(30.0, os.path.join("wavs", "a.wav"), os.path.join("out", "a.npy")),
+                     (25.0, os.path.join("wavs", "b_left.wav"), os.path.join("out", "b_left.npy"))]
+    os.makedirs("out")
+    open(os.path.join("out", "a.npy"), "w").close()
+    assert E.extract_melspec(tasks[0]) == 1
+    assert E.extract_melspec(tasks[1]) == -1                       # wavs/b.wav does not exist
+    assert "wavs/b.wav" in capsys.readouterr().out.replace(os.sep, "/")
+    assert E.main(["wavs", "out"]) == 0
+    assert "progress: 2/2" in capsys.readouterr().out
