@@ -222,3 +222,55 @@ def test_extract_melspec_task_list_and_error_contract(tmp_path, monkeypatch, cap
     assert "wavs/b.wav" in capsys.readouterr().out.replace(os.sep, "/")
     assert E.main(["wavs", "out"]) == 0
     assert "progress: 2/2" in capsys.readouterr().out
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/process"), reason="reference tree not present")
+def test_checkpoint_surgery_scripts_meet_the_key_contract(tmp_path):
+    """The reference's two checkpoint-surgery scripts, run unmodified on state_dicts of THIS build's modules, produce
+    files this build's next-stage models load (they pin the state_dict key contract):
+    export_pretrained_ckpts.py  VGG-M `visual.v2p.*` (VoxCeleb pre-training, fc backend) -> `visual.shared.*` +
+                                `visual.{v,a}_private.*` of the split model;
+    merge_av_checkpoints.py     audio stream + visual stream -> the `--fusion_checkpoint` of the audio-visual model."""
+    import subprocess
+    import sys
+    from m3t_b200.models.model import AffWild2VA
+    from m3t_b200.models.vggm import VA_3DVGGM
+    ref = "/root/reference/process"
+
+    def hp(**kw):
+        d = dict(backbone="v2p_split", backend="gru", modality="visual", fusion_type="attention", window=8,
+                 loss="ccc_mtl", loss_lambda=0.5, num_hidden=512, split_layer=3, num_fc_layers=2, learning_rate=5e-5,
+                 optimizer="adam")
+        d.update(kw)
+        return argparse.Namespace(**d)
+
+    torch.manual_seed(0)
+    pre = VA_3DVGGM(frameLen=8, backend="fc", nClasses=1000)
+    torch.save({"state_dict": {"visual." + k: v for k, v in pre.state_dict().items()}}, tmp_path / "vox.ckpt")
+    r = subprocess.run([sys.executable, os.path.join(ref, "export_pretrained_ckpts.py"), "vox.ckpt"], cwd=tmp_path,
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-1500:]
+    video_sd = torch.load(tmp_path / "video_checkpoint.pt")["state_dict"]
+    visual = AffWild2VA(hp())
+    own = visual.state_dict()
+    assert set(video_sd) <= set(own) and all(video_sd[k].shape == own[k].shape for k in video_sd)
+    res = visual.load_state_dict(video_sd, strict=False)
+    assert not res.unexpected_keys
+    assert all(k.split(".")[1] in ("gru_v", "gru_a") for k in res.missing_keys), res.missing_keys   # only the heads
+    assert torch.equal(visual.visual.shared[0].weight, pre.v2p[0].weight)
+    assert torch.equal(visual.visual.a_private[0].weight, pre.v2p[12].weight)
+
+    audio = AffWild2VA(hp(modality="audio"))
+    torch.save({"state_dict": audio.state_dict()}, tmp_path / "audio.ckpt")
+    torch.save({"state_dict": visual.state_dict()}, tmp_path / "video.ckpt")
+    r = subprocess.run([sys.executable, os.path.join(ref, "merge_av_checkpoints.py"), "audio.ckpt", "video.ckpt"],
+                       cwd=tmp_path, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-1500:]
+    fused = torch.load(tmp_path / "fused_av.pt")["state_dict"]
+    av = AffWild2VA(hp(modality="audiovisual"))
+    own = av.state_dict()
+    assert set(fused) <= set(own) and all(fused[k].shape == own[k].shape for k in fused)
+    res = av.load_state_dict(fused, strict=False)          # train.py:26-28
+    assert not res.unexpected_keys
+    assert {k.split(".")[0] for k in res.missing_keys} == {"proj_v", "att_fuse", "fusion"}
+    assert torch.equal(av.audio.gru.weight_hh_l0, audio.audio.gru.weight_hh_l0)
