@@ -36,14 +36,15 @@ def _seed(s):
 
 
 @pytest.mark.skipif(not _refload.available(), reason="reference tree not present")
-@pytest.mark.parametrize("modality,input_size,balance", [("audiovisual", 128, False), ("visual", 256, False),
-                                                          ("audio", 128, False), ("audiovisual", 128, True),
-                                                          ("audio", 128, True)])
-def test_dataset_matches_reference_class(tmp_path, monkeypatch, modality, input_size, balance):
+@pytest.mark.parametrize("modality,input_size,balance,release",
+                         [("audiovisual", 128, False, "vipl"), ("visual", 256, False, "vipl"),
+                          ("audio", 128, False, "vipl"), ("audiovisual", 128, True, "vipl"),
+                          ("audio", 128, True, "vipl"), ("visual", 112, False, "ibug")])
+def test_dataset_matches_reference_class(tmp_path, monkeypatch, modality, input_size, balance, release):
     """Every sample of every split equals the reference dataset's bit for bit under the same seeds: window choice,
     crop / mirror / cutout draws, missing-frame rule, edge padding of the last window, feature padding, masks."""
     root = str(tmp_path / "data")
-    synth_affwild.build(root, str(tmp_path), input_size=input_size)
+    synth_affwild.build(root, str(tmp_path), input_size=input_size, release=release)
     monkeypatch.chdir(tmp_path)
     ref_ds = _refload.load("dataset").AffWild2SequenceDataset
     from m3t_b200.models.dataset import AffWild2SequenceDataset
@@ -53,7 +54,7 @@ def test_dataset_matches_reference_class(tmp_path, monkeypatch, modality, input_
             for f in glob.glob(str(tmp_path / "*.pkl")):       # each class must do its own window scan
                 os.remove(f)
             _seed(11)
-            sets.append(cls(split, root, 8, 3, True, "vipl", input_size, modality, balance, stride))
+            sets.append(cls(split, root, 8, 3, True, release, input_size, modality, balance, stride))
         r, m = sets
         assert len(r) == len(m) and r.sample_src == m.sample_src
         if split == "train":
