@@ -236,6 +236,166 @@ __global__ void __launch_bounds__(kGruThreads, 1) gru_fwd_kernel(const GruParams
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// Small-batch inference variant (B <= 16: long-sequence evaluation at 16 clips per GPU, BASELINE config 5; config 1).
+// There a step of gru_fwd_kernel is pure latency: an L2 round trip to publish h, a gpu-scope arrival counter to poll,
+// another L2 round trip to fetch h (5.7 us per step measured).  Here the CTAs of one direction form ONE thread-block
+// cluster and the hidden state never leaves the SMs:
+//   grid (H/64, 1, 2), cluster (H/64, 1, 1): CTA r owns hidden units [64r, 64r+64) of its direction; its W_hh slice
+//   (3 gates x 64 units x H, bf16, 196 KB at H = 512) stays in shared memory for the whole sequence;
+//   per step: h' slice (16 rows x 64 units, bf16) -> own shared memory (double-buffered) -> ONE hardware cluster
+//   barrier (release/acquire) -> every CTA pulls the H/64 slices over DSMEM (ld.shared::cluster, 16-byte vectors)
+//   into its h tile -> mma.sync m16n8k16 over K = H (one m16 tile = all batch rows; warp w owns units 8w..8w+7 of
+//   the three gates) -> gates on the 4 (b, j) elements a thread owns (fp32 state in registers).
+// Same operand values, same k order and same gate arithmetic as gru_fwd_kernel.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int kCJS = 64;         // hidden units per CTA (cluster variant)
+constexpr int kCRows = 16;       // batch rows (one m16 tile)
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint4 ld_dsmem_u4(uint32_t local_saddr, uint32_t rank) {
+  uint32_t ra;
+  uint4 v;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(local_saddr), "r"(rank));
+  asm volatile("ld.shared::cluster.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "r"(ra)
+               : "memory");
+  return v;
+}
+
+__global__ void __launch_bounds__(kGruThreads, 1) gru_fwd_cluster_kernel(const GruParams p) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int H = p.H, T = p.T, B = p.B;
+  const int ldk = H + 8;
+  __nv_bfloat16* Wsm = reinterpret_cast<__nv_bfloat16*>(smem);   // [192][ldk]  row g*64 + j
+  __nv_bfloat16* hsm = Wsm + 3 * kCJS * ldk;                     // [16][ldk]   h_{t-1}, all H units
+  __nv_bfloat16* sl = hsm + kCRows * ldk;                        // [2][16][64] own h' slice, double-buffered
+  const int js = (int)cluster_ctarank(), dir = blockIdx.z;
+  const int ncta = gridDim.x;                                    // = H / 64 = cluster size
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int vec_per_row = H / 8;
+
+  for (int i = tid; i < 3 * kCJS * vec_per_row; i += kGruThreads) {
+    const int row = i / vec_per_row, v = i - row * vec_per_row;
+    const int g = row / kCJS, j = row - g * kCJS;
+    const uint4 val =
+        __ldg(reinterpret_cast<const uint4*>(p.w + ((long long)dir * 3 * H + g * H + js * kCJS + j) * H) + v);
+    *reinterpret_cast<uint4*>(Wsm + row * ldk + v * 8) = val;
+  }
+  // owned elements: rows b = lane/4 + 8*rs (rs = 0, 1), hidden units j0 + q (q = 0, 1) of this CTA's 64
+  const int j0 = 8 * warp + (lane & 3) * 2;
+  float bhh[3][2];
+#pragma unroll
+  for (int g = 0; g < 3; ++g)
+#pragma unroll
+    for (int q = 0; q < 2; ++q) bhh[g][q] = p.b_hh[dir * 3 * H + g * H + js * kCJS + j0 + q];
+  float hreg[4] = {0.f, 0.f, 0.f, 0.f};     // [rs*2 + q]
+  __syncthreads();
+
+  const uint32_t a_base = smem_u32(hsm + ((lane & 7) + ((lane >> 3) & 1) * 8) * ldk + (lane >> 4) * 8);
+  // gates r and z in one ldmatrix.x4 (lanes 0-15: r rows, k lo / k hi; lanes 16-31: z rows), gate n in an x2
+  const uint32_t brz_base =
+      smem_u32(Wsm + ((lane >> 4) * kCJS + 8 * warp + (lane & 7)) * ldk + ((lane >> 3) & 1) * 8);
+  const uint32_t bn_base = smem_u32(Wsm + (2 * kCJS + 8 * warp + (lane & 7)) * ldk + ((lane >> 3) & 1) * 8);
+
+  for (int step = 0; step < T; ++step) {
+    const int t = dir == 0 ? step : T - 1 - step;
+    float acc[3][4];
+#pragma unroll
+    for (int g = 0; g < 3; ++g)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[g][e] = 0.f;
+    // this step's input projection does not depend on h: issue the loads before touching the peers
+    float2 gir[2], giz[2], gin[2];
+#pragma unroll
+    for (int rs = 0; rs < 2; ++rs) {
+      const int b = (lane >> 2) + rs * 8;
+      gir[rs] = giz[rs] = gin[rs] = make_float2(0.f, 0.f);
+      if (b < B) {
+        const float* gi = p.gi + ((long long)b * T + t) * 6 * H + dir * 3 * H + js * kCJS + j0;
+        gir[rs] = __ldg(reinterpret_cast<const float2*>(gi));
+        giz[rs] = __ldg(reinterpret_cast<const float2*>(gi + H));
+        gin[rs] = __ldg(reinterpret_cast<const float2*>(gi + 2 * H));
+      }
+    }
+    if (step > 0) {
+      // pull h_{t-1}: slice r of buffer (step-1)&1 from CTA r, for every r of the cluster (own slice included)
+      const uint32_t sl_local = smem_u32(sl + ((step - 1) & 1) * kCRows * kCJS);
+      const int nvec = kCRows * ncta * 8;                 // 16-byte vectors: 8 per (row, slice)
+      for (int v0 = tid; v0 < nvec; v0 += 4 * kGruThreads) {
+        uint4 val[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int v = v0 + u * kGruThreads;
+          if (v < nvec) {
+            const int peer = v >> 7, rem = v & 127;       // 128 vectors per slice
+            val[u] = ld_dsmem_u4(sl_local + (uint32_t)((rem >> 3) * kCJS + (rem & 7) * 8) * 2u, (uint32_t)peer);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int v = v0 + u * kGruThreads;
+          if (v < nvec) {
+            const int peer = v >> 7, rem = v & 127;
+            *reinterpret_cast<uint4*>(hsm + (rem >> 3) * ldk + peer * kCJS + (rem & 7) * 8) = val[u];
+          }
+        }
+      }
+      __syncthreads();
+      for (int kk = 0; kk < H / 16; ++kk) {
+        uint32_t a[4], brz[4], bn[2];
+        ldmatrix_x4(a, a_base + kk * 32);
+        ldmatrix_x4(brz, brz_base + kk * 32);
+        ldmatrix_x2(bn, bn_base + kk * 32);
+        mma_16816(acc[0], a, brz[0], brz[1]);
+        mma_16816(acc[1], a, brz[2], brz[3]);
+        mma_16816(acc[2], a, bn[0], bn[1]);
+      }
+    }
+    __nv_bfloat16* slw = sl + (step & 1) * kCRows * kCJS;
+#pragma unroll
+    for (int rs = 0; rs < 2; ++rs) {
+      const int b = (lane >> 2) + rs * 8;
+      uint32_t packed = 0u;
+      if (b < B) {
+        float hnew[2];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const int e = rs * 2 + q;
+          const float hp = hreg[e];
+          const float hr = acc[0][e] + bhh[0][q];
+          const float hz = acc[1][e] + bhh[1][q];
+          const float hn = acc[2][e] + bhh[2][q];
+          const float r = sigmoidf_((q ? gir[rs].y : gir[rs].x) + hr);
+          const float z = sigmoidf_((q ? giz[rs].y : giz[rs].x) + hz);
+          const float n = tanhf((q ? gin[rs].y : gin[rs].x) + r * hn);
+          hnew[q] = (1.f - z) * n + z * hp;
+          hreg[e] = hnew[q];
+        }
+        const long long row = (long long)b * T + t;
+        packed = pack_bf16x2(hnew[0], hnew[1]);
+        *reinterpret_cast<uint32_t*>(p.out + row * 2 * H + dir * H + js * kCJS + j0) = packed;
+        if (p.out_f32)
+          *reinterpret_cast<float2*>(p.out_f32 + row * 2 * H + dir * H + js * kCJS + j0) =
+              make_float2(hnew[0], hnew[1]);
+      }
+      *reinterpret_cast<uint32_t*>(slw + b * kCJS + j0) = packed;     // rows past the batch stay zero
+    }
+    // One barrier per step: buffer step&1 is complete in every CTA after it, and nobody still reads buffer
+    // (step+1)&1 (those pulls happened before the pullers' MMAs of this step).  The last one also keeps every
+    // CTA's shared memory alive until its peers are done with it.
+    cluster_sync_all();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // BPTT.  Per step and batch slice (32 rows):
 //   phase A (elementwise, owned (b, j)):  dh = dout_t + dh_rec ; gate gradients ; write dgi, dgh (bf16), hprev copy
 //   group barrier
@@ -417,6 +577,42 @@ extern "C" int m3t_gru_fwd(const float* gi, const void* w_hh_bf16, const float* 
   p.saved = saved;
   p.counters = counters;
   return gru_launch(true, p, stream);
+}
+
+extern "C" int m3t_gru_fwd_cluster(const float* gi, const void* w_hh_bf16, const float* b_hh, void* out_bf16,
+                                   float* out_f32, int B, int T, int H, void* stream) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (H % kCJS != 0 || H > 512 || B <= 0 || B > kCRows || T <= 0) return -1;
+  GruParams p;
+  memset(&p, 0, sizeof(p));
+  p.B = B; p.T = T; p.H = H;
+  p.gi = gi;
+  p.w = reinterpret_cast<const __nv_bfloat16*>(w_hh_bf16);
+  p.b_hh = b_hh;
+  p.out = reinterpret_cast<__nv_bfloat16*>(out_bf16);
+  p.out_f32 = out_f32;
+  const int ncta = H / kCJS;     // 2, 4 or 8: a portable cluster size
+  const size_t smem = (size_t)(3 * kCJS + kCRows) * (H + 8) * 2 + (size_t)2 * kCRows * kCJS * 2;
+  if (cudaFuncSetAttribute(gru_fwd_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
+      cudaSuccess)
+    return -20;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(ncta, 1, 2);
+  cfg.blockDim = dim3(kGruThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = ncta;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gru_fwd_cluster_kernel, p);
+  count_launch();
+  if (e != cudaSuccess) return -21;
+  return launch_status();
 }
 
 extern "C" int m3t_gru_bwd(const void* dout_bf16, const void* out_bf16, const float* saved, const void* w_hh_t_bf16,

@@ -1526,6 +1526,43 @@ for _k in ("values_p0.2", "values_p0.5", "values_p0", "bwd_scale"):
 TOLS["keep_rate"] = 5e-3           # 454 656 draws: sigma = 6e-4
 
 
+def case_gru_cluster(seed=0):
+    """m3t_gru_fwd_cluster (thread-block cluster + DSMEM exchange, B <= 16) against m3t_gru_fwd on the same operands:
+    bf16 and fp32 outputs bit for bit (same operand values, k order and gate arithmetic), all three hidden sizes of
+    the model, ragged batch / sequence sizes; `info` = microseconds per time step of both kernels."""
+    from m3t_b200 import raw
+    g = torch.Generator().manual_seed(seed)
+    errs, info = {"gru_cluster_exact": 0.0, "gru_cluster_f32_exact": 0.0, "gru_cluster_nonfinite": 0.0}, {}
+    for B, T, H in ((16, 64, 512), (2, 16, 512), (7, 33, 256), (16, 40, 128), (1, 5, 512), (16, 256, 512)):
+        gi = (torch.randn((B * T, 6 * H), generator=g) * 0.8).cuda()
+        w = (torch.randn((2, 3 * H, H), generator=g) / H ** 0.5).bfloat16().cuda()
+        bh = (torch.randn((2, 3 * H), generator=g) * 0.1).cuda()
+        a, a32, _ = raw.gru_fwd(gi, w, bh, B, T, H, False, want_f32=True, cluster=False)
+        c, c32, _ = raw.gru_fwd(gi, w, bh, B, T, H, False, want_f32=True, cluster=True)
+        torch.cuda.synchronize()
+        errs["gru_cluster_exact"] += float((a.view(torch.int16) != c.view(torch.int16)).sum())
+        errs["gru_cluster_f32_exact"] += float((a32 != c32).sum())
+        errs["gru_cluster_nonfinite"] += float((~torch.isfinite(c32)).sum())
+        for tag, flag in (("l2", False), ("cluster", True)):
+            for _ in range(2):
+                raw.gru_fwd(gi, w, bh, B, T, H, False, cluster=flag)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(5):
+                raw.gru_fwd(gi, w, bh, B, T, H, False, cluster=flag)
+            e1.record()
+            torch.cuda.synchronize()
+            info["us_per_step_%s_B%d_T%d_H%d" % (tag, B, T, H)] = round(e0.elapsed_time(e1) / 5 / T * 1e3, 2)
+    errs["info"] = info
+    return errs
+
+
+CASES["gru_cluster_exact"] = (case_gru_cluster, _c())
+for _k in ("gru_cluster_exact", "gru_cluster_f32_exact", "gru_cluster_nonfinite"):
+    TOLS[_k] = 0.5
+
+
 if __name__ == "__main__":
     name = sys.argv[1]
     errs = run_case(name)
