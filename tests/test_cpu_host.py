@@ -274,3 +274,45 @@ def test_checkpoint_surgery_scripts_meet_the_key_contract(tmp_path):
     assert not res.unexpected_keys
     assert {k.split(".")[0] for k in res.missing_keys} == {"proj_v", "att_fuse", "fusion"}
     assert torch.equal(av.audio.gru.weight_hh_l0, audio.audio.gru.weight_hh_l0)
+
+
+def test_gru_cluster_index_maps():
+    """Host model of gru_fwd_cluster_kernel's index arithmetic (csrc/gru.cu): the DSMEM pull writes every element of
+    the 16 x H hidden-state tile exactly once from the right (peer, row, column); the 256 threads own every (row, unit)
+    of the CTA's 16 x 64 slice exactly once; the ldmatrix row addresses of a warp cover its 8 units of each gate; the
+    shared-memory budget fits for every hidden size."""
+    import numpy as np
+    for H in (128, 256, 512):
+        ncta, ldk = H // 64, H + 8
+        smem = (3 * 64 + 16) * ldk * 2 + 2 * 16 * 64 * 2
+        assert smem + 1024 <= 227 * 1024, (H, smem)
+        # pull: vector v -> (peer, row, c8); destination element offset in the h tile
+        hits = np.zeros((16, H), dtype=int)
+        src = {}
+        nvec = 16 * ncta * 8
+        for tid in range(256):
+            for v0 in range(tid, nvec, 4 * 256):
+                for u in range(4):
+                    v = v0 + u * 256
+                    if v < nvec:
+                        peer, rem = v >> 7, v & 127
+                        row, c8 = rem >> 3, rem & 7
+                        hits[row, peer * 64 + c8 * 8: peer * 64 + c8 * 8 + 8] += 1
+                        src[(row, peer * 64 + c8 * 8)] = (peer, row * 64 + c8 * 8)      # (rank, element in its slice)
+        assert (hits == 1).all()
+        assert all(col // 64 == peer and off == row * 64 + col % 64 for (row, col), (peer, off) in src.items())
+    owned = np.zeros((16, 64), dtype=int)
+    for tid in range(256):
+        warp, lane = tid >> 5, tid & 31
+        j0 = 8 * warp + (lane & 3) * 2
+        for rs in range(2):
+            b = (lane >> 2) + rs * 8
+            owned[b, j0:j0 + 2] += 1
+    assert (owned == 1).all()
+    for warp in range(8):
+        rows_rz = {(lane >> 4) * 64 + 8 * warp + (lane & 7) for lane in range(32)}
+        rows_n = {2 * 64 + 8 * warp + (lane & 7) for lane in range(32)}
+        assert rows_rz == {g * 64 + 8 * warp + i for g in (0, 1) for i in range(8)}
+        assert rows_n == {128 + 8 * warp + i for i in range(8)}
+        # accumulator columns of m16n8: thread (lane) holds units (lane & 3) * 2 + {0, 1} of the warp's 8
+        assert {8 * warp + (lane & 3) * 2 + q for lane in range(32) for q in range(2)} == set(range(8 * warp, 8 * warp + 8))
