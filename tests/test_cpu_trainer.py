@@ -666,3 +666,62 @@ def test_prefetcher_iteration_and_opt_in(tmp_path, monkeypatch):
     b = Toy(_toy_hparams())
     pl.Trainer(**kw).fit(b)
     assert all(torch.equal(p, q) for p, q in zip(a.state_dict().values(), b.state_dict().values()))
+
+
+@pytest.mark.skipif(not _refload.available(), reason="reference tree not present")
+@pytest.mark.parametrize("trial", [0, 1, 2, 3])
+def test_dataset_fuzz_vs_reference(tmp_path, monkeypatch, trial):
+    """Random trees (video lengths, missing frames, unannotated labels, frame rates, 128 / 256-pixel tracks, window
+    4 / 8 / 16, plain / noisy-balanced windows): every sample bit-identical to the reference class, and where the
+    reference raises (e.g. a one-frame last window past the end of a short feature file) this one raises the same
+    exception type."""
+    ref_ds = _refload.load("dataset").AffWild2SequenceDataset
+    from m3t_b200.models.dataset import AffWild2SequenceDataset
+    rng = np.random.default_rng(trial)
+    monkeypatch.chdir(tmp_path)
+    vids = {}
+    for i, split in enumerate(["train", "train", "val", "val", "test"]):
+        n = int(rng.integers(20, 70))
+        vids["v%d" % i] = dict(split=split, frames=n, fps=float(rng.choice([12.0, 25.0, 30.0])),
+                               expr=bool(rng.integers(0, 2)), missing=[int(x) for x in rng.integers(0, n, 3)],
+                               bad=[int(x) for x in rng.integers(0, n, 4)])
+    size = int(rng.choice([128, 256]))
+    root = str(tmp_path / "data")
+    synth_affwild.build(root, str(tmp_path), videos=vids, input_size=size, seed=trial)
+    W = int(rng.choice([4, 8, 16]))
+    compared = 0
+    for modality in ("audiovisual", "audio"):
+        for split, stride in (("train", 1), ("val", 2), ("test", 2)):
+            sets, errs = [], []
+            for cls in (ref_ds, AffWild2SequenceDataset):
+                for f in glob.glob(str(tmp_path / "*.pkl")):
+                    os.remove(f)
+                _seed(trial)
+                try:
+                    sets.append(cls(split, root, W, 2, True, "vipl", size, modality, bool(trial % 2), stride))
+                    errs.append(None)
+                except Exception as e:  # noqa: BLE001
+                    sets.append(None)
+                    errs.append(type(e).__name__)
+            assert errs[0] == errs[1], (modality, split, errs)
+            if errs[0]:
+                continue
+            r, m = sets
+            assert r.sample_src == m.sample_src
+            for i in range(len(r)):
+                got = []
+                for ds in (r, m):
+                    _seed(7 * trial + i)
+                    try:
+                        got.append(ds[i])
+                    except Exception as e:  # noqa: BLE001
+                        got.append(type(e).__name__)
+                a, b = got
+                if isinstance(a, str) or isinstance(b, str):
+                    assert a == b, (modality, split, i, a, b)
+                    continue
+                assert a.keys() == b.keys()
+                for k in a:
+                    _same(a[k], b[k], "%s %s[%d].%s" % (modality, split, i, k))
+                compared += 1
+    assert compared > 20
