@@ -240,7 +240,8 @@ __global__ void __launch_bounds__(kGruThreads, 1) gru_fwd_kernel(const GruParams
 // There a step of gru_fwd_kernel is pure latency: an L2 round trip to publish h, a gpu-scope arrival counter to poll,
 // another L2 round trip to fetch h (5.7 us per step measured).  Here the CTAs of one direction form ONE thread-block
 // cluster and the hidden state never leaves the SMs:
-//   grid (H/64, 1, 2), cluster (H/64, 1, 1): CTA r owns hidden units [64r, 64r+64) of its direction; its W_hh slice
+//   grid (H/64, ceil(B/16), 2), cluster (H/64, 1, 1): a cluster serves 16 batch rows of one direction (rows are
+//   independent, so a larger batch is simply more clusters); CTA r owns hidden units [64r, 64r+64); its W_hh slice
 //   (3 gates x 64 units x H, bf16, 196 KB at H = 512) stays in shared memory for the whole sequence;
 //   per step: h' slice (16 rows x 64 units, bf16) -> own shared memory (double-buffered) -> ONE hardware cluster
 //   barrier (release/acquire) -> every CTA pulls the H/64 slices over DSMEM (ld.shared::cluster, 16-byte vectors)
@@ -279,6 +280,8 @@ __global__ void __launch_bounds__(kGruThreads, 1) gru_fwd_cluster_kernel(const G
   __nv_bfloat16* sl = hsm + kCRows * ldk;                        // [2][16][64] own h' slice, double-buffered
   const int js = (int)cluster_ctarank(), dir = blockIdx.z;
   const int ncta = gridDim.x;                                    // = H / 64 = cluster size
+  const int b0 = blockIdx.y * kCRows;                            // batch rows of this cluster (rows are independent:
+                                                                 // larger batches are more clusters, each with W_hh)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int vec_per_row = H / 8;
 
@@ -316,7 +319,7 @@ __global__ void __launch_bounds__(kGruThreads, 1) gru_fwd_cluster_kernel(const G
     float2 gir[2], giz[2], gin[2];
 #pragma unroll
     for (int rs = 0; rs < 2; ++rs) {
-      const int b = (lane >> 2) + rs * 8;
+      const int b = b0 + (lane >> 2) + rs * 8;
       gir[rs] = giz[rs] = gin[rs] = make_float2(0.f, 0.f);
       if (b < B) {
         const float* gi = p.gi + ((long long)b * T + t) * 6 * H + dir * 3 * H + js * kCJS + j0;
@@ -362,7 +365,8 @@ __global__ void __launch_bounds__(kGruThreads, 1) gru_fwd_cluster_kernel(const G
     __nv_bfloat16* slw = sl + (step & 1) * kCRows * kCJS;
 #pragma unroll
     for (int rs = 0; rs < 2; ++rs) {
-      const int b = (lane >> 2) + rs * 8;
+      const int lrow = (lane >> 2) + rs * 8;
+      const int b = b0 + lrow;
       uint32_t packed = 0u;
       if (b < B) {
         float hnew[2];
@@ -386,7 +390,7 @@ __global__ void __launch_bounds__(kGruThreads, 1) gru_fwd_cluster_kernel(const G
           *reinterpret_cast<float2*>(p.out_f32 + row * 2 * H + dir * H + js * kCJS + j0) =
               make_float2(hnew[0], hnew[1]);
       }
-      *reinterpret_cast<uint32_t*>(slw + b * kCJS + j0) = packed;     // rows past the batch stay zero
+      *reinterpret_cast<uint32_t*>(slw + lrow * kCJS + j0) = packed;  // rows past the batch stay zero
     }
     // One barrier per step: buffer step&1 is complete in every CTA after it, and nobody still reads buffer
     // (step+1)&1 (those pulls happened before the pullers' MMAs of this step).  The last one also keeps every
@@ -582,7 +586,7 @@ extern "C" int m3t_gru_fwd(const float* gi, const void* w_hh_bf16, const float* 
 extern "C" int m3t_gru_fwd_cluster(const float* gi, const void* w_hh_bf16, const float* b_hh, void* out_bf16,
                                    float* out_f32, int B, int T, int H, void* stream) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (H % kCJS != 0 || H > 512 || B <= 0 || B > kCRows || T <= 0) return -1;
+  if (H % kCJS != 0 || H > 512 || B <= 0 || B > 4 * kCRows || T <= 0) return -1;   // <= 64 CTAs: one wave
   GruParams p;
   memset(&p, 0, sizeof(p));
   p.B = B; p.T = T; p.H = H;
@@ -598,7 +602,7 @@ extern "C" int m3t_gru_fwd_cluster(const float* gi, const void* w_hh_bf16, const
     return -20;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3(ncta, 1, 2);
+  cfg.gridDim = dim3(ncta, (B + kCRows - 1) / kCRows, 2);
   cfg.blockDim = dim3(kGruThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;

@@ -569,7 +569,7 @@ def dropout_bf16(x, p, seed):
 
 
 def gru_cluster_default():
-    """M3T_GRU_CLUSTER=1 routes small-batch inference recurrences (B <= 16) to m3t_gru_fwd_cluster.  Off until that
+    """M3T_GRU_CLUSTER=1 routes small-batch inference recurrences (B <= 64) to m3t_gru_fwd_cluster.  Off until that
     kernel has run on a B200 (tests/gpu_cases.py::case_gru_cluster compares it bit for bit with m3t_gru_fwd)."""
     return os.environ.get("M3T_GRU_CLUSTER", "0") == "1"
 
@@ -580,7 +580,7 @@ def gru_fwd(gi, w_hh_bf16, b_hh, B, T, H, want_saved, want_f32=False, cluster=No
     out32 = torch.empty((B, T, 2 * H), device=dev, dtype=torch.float32) if want_f32 else None
     if cluster is None:
         cluster = gru_cluster_default()
-    if cluster and not want_saved and B <= 16 and H % 64 == 0 and H <= 512:
+    if cluster and not want_saved and B <= 64 and H % 64 == 0 and H <= 512:
         _timed("gru_fwd_cluster B%d T%d H%d" % (B, T, H), 0.0, lambda: L.check(
             _lib().m3t_gru_fwd_cluster(L.ptr(gi), L.ptr(w_hh_bf16), L.ptr(b_hh), L.ptr(out), L.ptr(out32), L.i32(B),
                                        L.i32(T), L.i32(H), L.stream_ptr()), "gru_fwd_cluster"))

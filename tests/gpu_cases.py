@@ -1527,13 +1527,14 @@ TOLS["keep_rate"] = 5e-3           # 454 656 draws: sigma = 6e-4
 
 
 def case_gru_cluster(seed=0):
-    """m3t_gru_fwd_cluster (thread-block cluster + DSMEM exchange, B <= 16) against m3t_gru_fwd on the same operands:
+    """m3t_gru_fwd_cluster (thread-block cluster + DSMEM exchange, B <= 64) against m3t_gru_fwd on the same operands:
     bf16 and fp32 outputs bit for bit (same operand values, k order and gate arithmetic), all three hidden sizes of
     the model, ragged batch / sequence sizes; `info` = microseconds per time step of both kernels."""
     from m3t_b200 import raw
     g = torch.Generator().manual_seed(seed)
     errs, info = {"gru_cluster_exact": 0.0, "gru_cluster_f32_exact": 0.0, "gru_cluster_nonfinite": 0.0}, {}
-    for B, T, H in ((16, 64, 512), (2, 16, 512), (7, 33, 256), (16, 40, 128), (1, 5, 512), (16, 256, 512)):
+    for B, T, H in ((16, 64, 512), (2, 16, 512), (7, 33, 256), (16, 40, 128), (1, 5, 512), (16, 256, 512),
+                    (32, 32, 512), (40, 9, 256), (64, 16, 128)):
         gi = (torch.randn((B * T, 6 * H), generator=g) * 0.8).cuda()
         w = (torch.randn((2, 3 * H, H), generator=g) / H ** 0.5).bfloat16().cuda()
         bh = (torch.randn((2, 3 * H), generator=g) * 0.1).cuda()
