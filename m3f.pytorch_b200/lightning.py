@@ -192,9 +192,66 @@ class Prefetcher:
 
 
 def prefetch_enabled():
-    """M3T_TRAINER_PREFETCH=1: Trainer.fit feeds training_step through `Prefetcher`.  Opt-in until it has been timed
-    on a B200 (tests/bench_trainer.py); the default is the plain copy in front of each step."""
-    return os.environ.get("M3T_TRAINER_PREFETCH", "0") == "1"
+    """Trainer.fit feeds training_step through `Prefetcher` (next batch copied on a side stream while the current
+    step runs): 32.6 vs 43.9 ms per 256-clip step on a B200 (tests/bench_trainer.py, profiles/r2_next_session.md).
+    M3T_TRAINER_PREFETCH=0 restores the plain copy in front of each step."""
+    return os.environ.get("M3T_TRAINER_PREFETCH", "1") == "1"
+
+
+class SequentialShardSampler(torch.utils.data.Sampler):
+    """Evaluation sampler for one-process-per-GPU runs: rank r reads dataset indices r, r+world, ... in order and the
+    shards are NOT padded to equal length.  `DistributedSampler` (what the reference's loaders use,
+    models/model.py:416-418) repeats samples whenever len(dataset) % world != 0; the gathered validation / test outputs
+    would then hold duplicated windows — summed twice by the overlap-add of half-stride windows, concatenated twice on
+    tiled tracks, counted twice in val_loss (which drives ReduceLROnPlateau, checkpointing and early stopping)."""
+
+    def __init__(self, dataset, num_replicas=None, rank=None):
+        if num_replicas is None:
+            num_replicas = dist.get_world_size() if dist.is_available() and dist.is_initialized() else \
+                int(os.environ.get("WORLD_SIZE", "1"))
+        if rank is None:
+            rank = dist.get_rank() if dist.is_available() and dist.is_initialized() else \
+                int(os.environ.get("RANK", "0"))
+        self.n, self.world, self.rank = len(dataset), int(num_replicas), int(rank)
+
+    def __iter__(self):
+        return iter(range(self.rank, self.n, self.world))
+
+    def __len__(self):
+        return len(range(self.rank, self.n, self.world))
+
+    def set_epoch(self, epoch):
+        pass
+
+
+def _dedup_eval_outputs(outputs):
+    """Drop windows that reached rank 0 more than once (a padding sampler handed to the Trainer by user code): a window
+    is identified by (vid_name, start_frame).  Only step outputs carrying that bookkeeping are touched."""
+    if not (isinstance(outputs, list) and outputs and all(
+            isinstance(o, dict) and "vid_names" in o and "start_frames" in o for o in outputs)):
+        return outputs
+    seen, kept = set(), []
+    for o in outputs:
+        n = len(o["vid_names"])
+        keep = []
+        for j in range(n):
+            key = (o["vid_names"][j], int(o["start_frames"][j]))
+            if key not in seen:
+                seen.add(key)
+                keep.append(j)
+        if len(keep) == n:
+            kept.append(o)
+        elif keep:
+            new = {}
+            for k, v in o.items():
+                if isinstance(v, torch.Tensor) and v.dim() > 0 and v.size(0) == n:
+                    new[k] = v[torch.tensor(keep)]
+                elif isinstance(v, (list, tuple)) and len(v) == n:
+                    new[k] = type(v)(v[j] for j in keep)
+                else:
+                    new[k] = v
+            kept.append(new)
+    return kept
 
 
 def _scalar(v):
@@ -406,7 +463,22 @@ class Trainer:
                 self._fit(model)
             else:
                 self._test(model)
-        finally:
+        except BaseException:
+            # A failure on one rank (rank 0's validation_end / checkpoint write, typically) must not enter a barrier
+            # the other ranks will never match: tear the group down and stop the ranks this process started, so the
+            # real exception surfaces at once instead of after the collective timeout.
+            if self.world > 1 and dist.is_initialized():
+                try:
+                    abort = getattr(dist.distributed_c10d, "_abort_process_group", None)
+                    if abort is not None and self.device.type == "cuda":
+                        abort()
+                    else:
+                        dist.destroy_process_group()
+                except Exception:
+                    pass
+            _reap_children(grace=0)
+            raise
+        else:
             if self.world > 1 and dist.is_initialized():
                 dist.barrier()
 
@@ -563,7 +635,7 @@ class Trainer:
         if self.world > 1:
             gathered = [None] * self.world
             dist.all_gather_object(gathered, move_to(outputs, torch.device("cpu")))
-            outputs = [o for part in gathered for o in part]
+            outputs = _dedup_eval_outputs([o for part in gathered for o in part])
         result = None
         if end is not None:
             if self.rank == 0:

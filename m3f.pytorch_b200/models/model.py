@@ -310,8 +310,11 @@ class AffWild2VA(_Base):
         ds = AffWild2SequenceDataset(split, hp.dataset_path, hp.window, hp.windows_per_epoch, hp.cutout, hp.release,
                                      hp.input_size, hp.modality, hp.resample, inv_test_stride, emit_u8=on_device_aug)
         if hp.distributed:
-            return DataLoader(ds, batch_size=hp.batch_size, num_workers=hp.workers, pin_memory=True,
-                              sampler=torch.utils.data.distributed.DistributedSampler(ds))
+            # training: the reference's DistributedSampler; evaluation: an un-padded, in-order shard per rank, so the
+            # outputs gathered on rank 0 hold every window exactly once (pl.SequentialShardSampler)
+            sampler = torch.utils.data.distributed.DistributedSampler(ds) if split == 'train' else \
+                pl.SequentialShardSampler(ds)
+            return DataLoader(ds, batch_size=hp.batch_size, num_workers=hp.workers, pin_memory=True, sampler=sampler)
         return DataLoader(ds, batch_size=hp.batch_size, shuffle=split == 'train', num_workers=hp.workers,
                           pin_memory=True)
 

@@ -656,9 +656,9 @@ class DropoutFn(torch.autograd.Function):
 
 
 def fused_dropout_enabled():
-    """M3T_FUSED_DROPOUT=1 routes training-mode TCN dropout through DropoutFn; until that kernel has been confirmed on
-    a B200 (tests/gpu_cases.py::case_dropout) the default stays torch.nn.functional.dropout."""
-    return os.environ.get("M3T_FUSED_DROPOUT", "0") == "1"
+    """Training-mode TCN dropout runs through DropoutFn / m3t_dropout_bf16 (mask bit-exact against oracle/dropout.py
+    on a B200, tests/gpu_cases.py::case_dropout).  M3T_FUSED_DROPOUT=0 falls back to torch.nn.functional.dropout."""
+    return os.environ.get("M3T_FUSED_DROPOUT", "1") == "1"
 
 
 # ------------------------------------------------------------------------------------------------------------

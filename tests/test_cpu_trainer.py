@@ -725,3 +725,31 @@ def test_dataset_fuzz_vs_reference(tmp_path, monkeypatch, trial):
                     _same(a[k], b[k], "%s %s[%d].%s" % (modality, split, i, k))
                 compared += 1
     assert compared > 20
+
+
+def test_eval_shards_cover_every_window_once():
+    """ADVICE r1 (lightning.py distributed evaluation): evaluation shards must not repeat samples when
+    len(dataset) % world != 0 (DistributedSampler pads), and gathered outputs are de-duplicated by
+    (vid_name, start_frame) if a padding sampler is used anyway."""
+    from m3t_b200.lightning import SequentialShardSampler, _dedup_eval_outputs
+    for n in (1, 7, 8, 13):
+        for world in (1, 2, 3, 8):
+            seen = []
+            for r in range(world):
+                s = SequentialShardSampler(list(range(n)), num_replicas=world, rank=r)
+                idx = list(s)
+                assert len(idx) == len(s)
+                seen += idx
+            assert sorted(seen) == list(range(n)), (n, world)
+    # a padded pair of shards: 5 windows over 2 ranks -> rank 1 repeats window 0
+    def out(ids):
+        return {"vid_names": ["v%d" % (i // 3) for i in ids], "start_frames": torch.tensor([(i % 3) * 8 for i in ids]),
+                "v_pred": [torch.full((4,), float(i)) for i in ids], "tag": "x"}
+    gathered = [out([0, 2]), out([4]), out([1, 3]), out([0])]
+    kept = _dedup_eval_outputs(gathered)
+    ids = [int(t[0]) for o in kept for t in o["v_pred"]]
+    assert ids == [0, 2, 4, 1, 3]
+    mixed = _dedup_eval_outputs([out([0, 1]), out([1, 2])])
+    assert [int(t[0]) for o in mixed for t in o["v_pred"]] == [0, 1, 2]
+    assert mixed[1]["start_frames"].tolist() == [16] and mixed[1]["vid_names"] == ["v0"] and mixed[1]["tag"] == "x"
+    assert _dedup_eval_outputs([{"loss": 1.0}]) == [{"loss": 1.0}]

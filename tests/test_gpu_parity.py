@@ -18,7 +18,7 @@ pytestmark = pytest.mark.gpu
 
 # hardware-semantics probes (informational) and cases not yet confirmed on a B200 (their code paths are off by default):
 # run by tests/gpu_probe.py only
-PROBES = {"probe_rowshift", "dropout_bf16", "gru_cluster_exact"}
+PROBES = {"probe_rowshift"}
 
 
 @pytest.mark.parametrize("name", sorted(n for n in G.CASES if n not in PROBES))
