@@ -52,13 +52,35 @@ class TrainEngine:
         """Lay out the flat arenas over the parameters that actually receive a gradient.  Parameters autograd never
         reaches (e.g. `resnet.fc`, present in the state_dict but unused with agg_mode 'ap', models/resnet.py:72,117)
         stay outside, exactly as torch.optim.Adam skips parameters whose .grad is None (no weight decay on them)."""
-        self.params = [p for p in self.all_params if p.grad is not None]
+        old = None
+        if self.params is not None:      # re-layout: a parameter outside the arena received its first gradient
+            old = {id(p): (o, p.numel()) for p, o in zip(self.params, self.offs)}
+            old_m, old_v = (self.m, self.v) if self.on_gpu else (None, None)
+            in_arena = set(old)
+            self.params = [p for p in self.all_params if id(p) in in_arena or p.grad is not None]
+        else:
+            self.params = [p for p in self.all_params if p.grad is not None]
         dev = self.params[0].device
         offs, n = [], 0
         for p in self.params:
             offs.append(n)
             n += (p.numel() + 3) // 4 * 4       # 16-byte aligned slots
-        self.n = n
+        self.n, self.offs = n, offs
+        self._in_arena = {id(p) for p in self.params}
+        self._outside = [p for p in self.all_params if id(p) not in self._in_arena]
+        if self.world > 1:
+            # every rank must have laid out the same arena (same parameters reached by its first backward), or the
+            # flat all-reduce would add misaligned buffers
+            names = {id(p): i for i, p in enumerate(self.all_params)}
+            sig = torch.tensor([len(self.params), n, sum((names[id(p)] + 1) * (o + 1) % 1000003
+                                                         for p, o in zip(self.params, offs))],
+                               dtype=torch.int64, device=dev)
+            lo, hi = sig.clone(), sig.clone()
+            dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+            dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+            if not torch.equal(lo, hi):
+                raise RuntimeError("TrainEngine: ranks built different gradient arenas (a parameter received a "
+                                   "gradient on some ranks only): %s vs %s" % (lo.tolist(), hi.tolist()))
         self.flat_p = torch.zeros(n, device=dev, dtype=torch.float32)
         self.flat_g = torch.zeros(n, device=dev, dtype=torch.float32)
         self.grad_views = []
@@ -69,17 +91,36 @@ class TrainEngine:
         if self.on_gpu:
             self.m = torch.zeros(n, device=dev, dtype=torch.float32)
             self.v = torch.zeros(n, device=dev, dtype=torch.float32)
+            if old is not None:          # carry the Adam moments of the parameters that were already there
+                for p, o in zip(self.params, offs):
+                    if id(p) in old:
+                        oo, k = old[id(p)]
+                        self.m[o:o + k].copy_(old_m[oo:oo + k])
+                        self.v[o:o + k].copy_(old_v[oo:oo + k])
             self.gnorm_sq = torch.zeros(1, device=dev, dtype=torch.float32)
             L.load().m3t_sumsq_workspace_floats.restype = ctypes.c_longlong
             self.sumsq_ws = torch.empty(int(L.load().m3t_sumsq_workspace_floats()), device=dev, dtype=torch.float32)
         else:  # host-side logic tests only (gloo); the product path is the CUDA one
+            prev = getattr(self, "opt", None)
             self.opt = torch.optim.Adam(self.params, lr=self.lr, weight_decay=self.wd, betas=self.betas,
                                         eps=self.eps)
+            if prev is not None:
+                for p_, st in prev.state.items():
+                    self.opt.state[p_] = st
 
     def _gather_grads(self):
         """autograd hands every parameter a fresh gradient tensor (p.grad is None before backward, so nothing is
         accumulated); one multi-tensor copy moves them into the flat arena."""
         if self.params is None:
+            self._build_arena()
+        elif any(p.grad is not None for p in self._outside):
+            # torch.optim.Adam decides per step which parameters it updates; the arena is laid out once, so a parameter
+            # that gets its first gradient later (conditional branch, requires_grad switched on) joins it now.
+            # NOTE the fused kernel keeps ONE step counter: a late joiner's bias correction starts at the engine's step
+            # count (its moments start at zero), torch.optim.Adam would start it at 1.
+            if self.overlap:
+                raise RuntimeError("TrainEngine: a parameter outside the gradient arena received a gradient while the "
+                                   "bucketed all-reduce is armed; construct the engine after the graph is final")
             self._build_arena()
         dst, src = [], []
         for p, v in zip(self.params, self.grad_views):

@@ -9,8 +9,17 @@ whole forward can be captured once into a CUDA graph and replayed with one launc
     y = g(batch)                                    # copies the inputs into the static buffers, replays, returns y
 
 `batch` is a tensor, a tuple of tensors, or the AffWild2VA batch dict; shapes must equal the example's.
+
+The captured graph holds raw addresses of the packed / bf16 weight copies in `ops._pack_cache`.  The instance therefore
+(1) keeps strong references to every cache value that existed at capture, so a later `ops.clear_caches()` (every
+TrainEngine step) cannot hand those buffers back to the allocator under the graph, and (2) records the parameters'
+version counters, storage pointers and the cache generation: if the weights were updated in place, re-seated (`load_state_dict`,
+`p.data = ...`) or rewritten through the optimizer arena (generation bump), the next call re-captures instead of
+replaying stale weights.
 """
 import torch
+
+from . import ops
 
 
 def _map(obj, fn):
@@ -40,6 +49,22 @@ class GraphedInference:
         self.model = model
         self.static_in = _map(example, lambda t: t.detach().clone())
         self._call = (lambda x: model(*x)) if isinstance(example, tuple) else model
+        self.warmup = warmup
+        self.captures = 0
+        self._capture()
+
+    def _weights_key(self):
+        # per replay: version counters only (~20 us for the AV model); storage pointers are compared as well whenever
+        # the tensor list itself is rebuilt (every 64 calls), which also catches `p.data = ...` re-seating
+        self._calls = getattr(self, "_calls", 0) + 1
+        if self._calls % 64 == 1 or not hasattr(self, "_tensors"):
+            self._tensors = list(self.model.parameters()) + list(self.model.buffers())
+            self._ptrs = tuple(t.data_ptr() for t in self._tensors)
+        return (ops.CACHE_GENERATION, self._ptrs, tuple([t._version for t in self._tensors]))
+
+    def _capture(self):
+        model, warmup = self.model, self.warmup
+        assert not model.training, "graph capture is for eval-mode inference"
         # warm-up on a side stream: one-time work (cudaFuncSetAttribute, weight packing caches, allocator pools)
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
@@ -50,8 +75,13 @@ class GraphedInference:
         self.graph = torch.cuda.CUDAGraph()
         with torch.no_grad(), torch.cuda.graph(self.graph):
             self.static_out = self._call(self.static_in)
+        self._held = [v[2] for v in ops._pack_cache.values()]     # the derived weight copies the graph reads
+        self._key = self._weights_key()
+        self.captures += 1
 
     def __call__(self, batch):
+        if self._weights_key() != self._key:
+            self._capture()
         _copy_into(self.static_in, batch)
         self.graph.replay()
         return self.static_out

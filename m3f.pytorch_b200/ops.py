@@ -35,7 +35,12 @@ def _cached(key_tensor, tag, fn):
     return _cached_multi((key_tensor,), tag, fn)
 
 
+CACHE_GENERATION = 0      # bumped by clear_caches(): consumers holding raw addresses (graphs.GraphedInference) watch it
+
+
 def clear_caches():
+    global CACHE_GENERATION
+    CACHE_GENERATION += 1
     _pack_cache.clear()
 
 

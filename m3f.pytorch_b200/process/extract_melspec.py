@@ -52,8 +52,17 @@ def mel_filterbank(sr=SR, n_fft=N_FFT, n_mels=N_MELS, fmin=0.0, fmax=None):
 _fb_cache = {}
 
 
-def melspectrogram_db(y, fps, pad_mode="constant", top_db=80.0):
-    """y: 1-D float32 CUDA tensor (16 kHz).  Returns (n_frames, 40) float32 dB log-Mel, n_frames = 1 + len(y)//hop."""
+# librosa.stft's centre padding changed from 'reflect' (< 0.10, the version the reference script ran on and the released
+# checkpoints' mel_spec/*.npy were made with: requirements.txt pins nothing, the script dates from early 2020 =
+# librosa 0.7) to 'constant' (>= 0.10).  'reflect' is therefore the default; only the first / last frames differ.
+DEFAULT_PAD_MODE = "reflect"
+
+
+def melspectrogram_db(y, fps, pad_mode=DEFAULT_PAD_MODE, top_db=80.0):
+    """y: 1-D float32 CUDA tensor (16 kHz).  Returns (n_frames, 40) float32 dB log-Mel, n_frames = 1 + len(y)//hop.
+    pad_mode: 'reflect' (librosa < 0.10, the reference's era) or 'constant' (librosa >= 0.10)."""
+    if pad_mode not in ("reflect", "constant"):
+        raise ValueError("pad_mode must be 'reflect' or 'constant', got %r" % (pad_mode,))
     assert y.is_cuda and y.dtype == torch.float32 and y.dim() == 1
     y = y.contiguous()
     hop = int(1 / 3 * 1 / fps * SR)
@@ -91,7 +100,7 @@ def _read_wav_16k(path):
     return data.astype(np.float32)
 
 
-def extract_melspec(task):
+def extract_melspec(task, pad_mode=DEFAULT_PAD_MODE):
     """Same contract as the reference: returns 1 if the output exists, 0 on success, -1 on error."""
     fps, src_wav, dst_npy = task
     src_wav = src_wav.replace('_left', '').replace('_right', '')
@@ -99,7 +108,7 @@ def extract_melspec(task):
         return 1
     try:
         y = torch.from_numpy(_read_wav_16k(src_wav)).cuda()
-        spec = melspectrogram_db(y, fps)
+        spec = melspectrogram_db(y, fps, pad_mode=pad_mode)
         np.save(dst_npy, spec.cpu().numpy())        # (time, channels), as the reference stores it
         return 0
     except Exception as e:  # noqa: BLE001
@@ -124,11 +133,16 @@ def main(argv=None):
     """`python -m m3t_b200.process.extract_melspec <wav dir> <npy dir>`: the reference script's command line
     (:27-46).  One process feeds the GPU file by file instead of a 16-process librosa pool."""
     import sys
-    argv = sys.argv[1:] if argv is None else argv
+    argv = list(sys.argv[1:] if argv is None else argv)
+    pad_mode = DEFAULT_PAD_MODE
+    for a in [a for a in argv if a.startswith('--pad_mode')]:      # optional; the reference's two positionals stay
+        i = argv.index(a)
+        pad_mode = a.split('=', 1)[1] if '=' in a else argv.pop(i + 1)
+        argv.remove(a)
     src_dir, dst_dir = argv[0], argv[1]
     tasks = build_tasks(src_dir, dst_dir)
     for done, task in enumerate(tasks, 1):
-        result = extract_melspec(task)
+        result = extract_melspec(task, pad_mode)
         if result <= 0:
             print('Finished {}, result: {}, progress: {}/{}'.format(task[1], result, done, len(tasks)))
     return 0

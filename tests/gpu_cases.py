@@ -1190,12 +1190,34 @@ def case_cuda_graph(seed=0):
         y, y2 = m(b1).clone(), m(b2).clone()
     g = GraphedInference(m, b1)
     errs["graph_exact_av"] = float((g(b1) != y).sum() + (g(b2) != y2).sum())
+    # ADVICE r1 (graphs.py): the graph reads the derived weight copies by address.  (a) dropping the cache and
+    # allocating over the freed blocks must not disturb a replay (the instance holds the copies); (b) an in-place
+    # weight update / an optimizer-arena rewrite must re-capture, not replay stale weights
+    from m3t_b200 import ops
+    ops._pack_cache.clear()
+    junk = [torch.full((1 << 20,), 7.0, device="cuda") for _ in range(64)]    # reuse whatever was freed
+    errs["graph_exact_after_cache_drop"] = float((g(b2) != y2).sum())
+    del junk
+    with torch.no_grad():
+        for p_ in m.parameters():
+            p_.mul_(1.01)
+        y3 = m(b1).clone()
+    n_cap = g.captures
+    errs["graph_exact_after_update"] = float((g(b1) != y3).sum()) + (0.0 if g.captures == n_cap + 1 else 1.0)
+    with torch.no_grad():
+        for p_ in m.parameters():
+            p_.data.mul_(0.99)               # no version bump ...
+        ops.clear_caches()                   # ... but the engine announces arena rewrites this way
+        y4 = m(b2).clone()
+    errs["graph_exact_after_arena_step"] = float((g(b2) != y4).sum())
     return errs
 
 
 CASES["cuda_graph_inference"] = (case_cuda_graph, _c())
 TOLS["graph_exact"] = 0.5
 TOLS["graph_exact_av"] = 0.5
+for _k in ("graph_exact_after_cache_drop", "graph_exact_after_update", "graph_exact_after_arena_step"):
+    TOLS[_k] = 0.5
 
 
 def case_fullsize_properties(clips=256, seed=0):

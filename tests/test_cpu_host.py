@@ -316,3 +316,40 @@ def test_gru_cluster_index_maps():
         assert rows_n == {128 + 8 * warp + i for i in range(8)}
         # accumulator columns of m16n8: thread (lane) holds units (lane & 3) * 2 + {0, 1} of the warp's 8
         assert {8 * warp + (lane & 3) * 2 + q for lane in range(32) for q in range(2)} == set(range(8 * warp, 8 * warp + 8))
+
+
+def test_engine_arena_admits_late_gradients():
+    """ADVICE r1 (engine.py arena membership): a parameter that first receives a gradient after the arena was laid
+    out joins it (with the moments of the others preserved) instead of being silently skipped."""
+    import torch.nn as nn
+    from m3t_b200.engine import TrainEngine
+
+    class Two(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.a, self.b = nn.Linear(4, 4), nn.Linear(4, 4)
+            self.use_b = False
+
+        def forward(self, batch):
+            y = self.a(batch["x"])
+            return self.b(y) if self.use_b else y
+
+        def compute_loss(self, y, batch, sync_free=False):
+            return (y ** 2).mean(), {}
+
+    torch.manual_seed(0)
+    m = Two()
+    ref = Two()
+    ref.load_state_dict(m.state_dict())
+    opt = torch.optim.Adam(ref.parameters(), lr=1e-2, weight_decay=1e-4)
+    eng = TrainEngine(m, lr=1e-2, weight_decay=1e-4, clip=None)
+    batch = {"x": torch.randn(8, 4)}
+    for step in range(4):
+        m.use_b = ref.use_b = step >= 2
+        eng.step(batch)
+        opt.zero_grad(set_to_none=True)
+        ref.compute_loss(ref(batch), batch)[0].backward()
+        opt.step()
+        assert len(eng.params) == (4 if step >= 2 else 2)
+    for (k, p), q in zip(m.state_dict().items(), ref.state_dict().values()):
+        assert torch.allclose(p, q, atol=1e-6), k
