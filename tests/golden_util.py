@@ -19,7 +19,27 @@ def load(name):
                 fx["inputs"][k] = torch.randint(0, 256, d["shape"], generator=g, dtype=torch.uint8)
             else:
                 raise KeyError(d["kind"])
+    if "inputs_recipe" in fx:   # fixtures at BASELINE sizes (oracle/make_golden_sizes.py): everything is re-drawn
+        fx["inputs"] = from_recipe(fx["inputs_recipe"])
     return fx
+
+
+def from_recipe(r):
+    g = torch.Generator().manual_seed(r["seed"])
+    B, T = r["B"], r["T"]
+    if r["kind"] == "video_u8":
+        return {"video_u8": torch.randint(0, 256, (B, 3, T, 112, 112), generator=g, dtype=torch.uint8)}
+    if r["kind"] == "av_batch":     # draw order of oracle/make_golden_sizes.py::av_batch
+        return {
+            "video_u8": torch.randint(0, 256, (B, 3, T, 112, 112), generator=g, dtype=torch.uint8),
+            "audio": torch.randn((B, T, 200), generator=g) * 20 - 40,
+            "se_features": torch.randn((B, 512, T), generator=g),
+            "label_valence": torch.rand((B, T), generator=g) * 2 - 1,
+            "label_arousal": torch.rand((B, T), generator=g) * 2 - 1,
+            "class_expr": torch.randint(0, 7, (B, T), generator=g),
+            "expr_valid": torch.ones((B, T), dtype=torch.bool),
+        }
+    raise KeyError(r["kind"])
 
 
 def rel_err(y, ref):

@@ -382,12 +382,21 @@ def _build(fx):
     elif kind == "VA_3DVGGM_Split":
         from m3t_b200.models.vggm import VA_3DVGGM_Split
         m = VA_3DVGGM_Split(**fx["ctor"])
+    elif kind == "VA_3DVGGM":
+        from m3t_b200.models.vggm import VA_3DVGGM
+        m = VA_3DVGGM(**fx["ctor"])
     elif kind == "AffWild2VA":
         from m3t_b200.models.model import AffWild2VA
         m = AffWild2VA(argparse.Namespace(**fx["hparams"]))
     else:
         raise KeyError(kind)
-    m.load_state_dict(synth_state_dict(fx["spec"], fx["seed"]), strict=True)
+    m.load_state_dict(synth_state_dict(fx["spec"], fx["seed"], **fx.get("synth_kw", {})), strict=True)
+    if "dropout_p" in fx:
+        for d in m.modules():
+            if hasattr(d, "dropout_p"):
+                d.dropout_p = fx["dropout_p"]
+            if isinstance(d, torch.nn.Dropout):
+                d.p = fx["dropout_p"]
     return m.cuda()
 
 
@@ -396,7 +405,7 @@ def _oracle_run(fx, emulate, want_grads):
     from oracle import ref_torch as R
     from tests.golden_util import hparams_ns, ref_batch
     import contextlib
-    sd = R.synth_state_dict(fx["spec"], fx["seed"])
+    sd = R.synth_state_dict(fx["spec"], fx["seed"], **fx.get("synth_kw", {}))
     if want_grads:
         for k, v in sd.items():
             if v.is_floating_point() and not k.endswith(("running_mean", "running_var")):
@@ -429,6 +438,8 @@ def _oracle_run(fx, emulate, want_grads):
         elif kind == "VA_3DVGGM_Split":
             out = R.va_3dvggm_split((inp["video_u8"].float() - 127.5) / 127.5, inp["se_features"], inp["se_features"],
                                     sd, "", fx["ctor"]["split_layer"], fx["ctor"]["backend"], train=train)
+        elif kind == "VA_3DVGGM":
+            out = R.va_3dvggm((inp["video_u8"].float() - 127.5) / 127.5, sd, fx["ctor"]["backend"], train=train)
         elif kind == "AffWild2VA":
             b = ref_batch(inp)
             hp = hparams_ns(fx["hparams"])
@@ -479,7 +490,7 @@ def case_golden(name, grads=True):
             xv = inp["x_v"].cuda().requires_grad_(want_grads)
             leaves.update(x_a=xa, x_v=xv)
             out = m(xa, xv)
-        elif kind == "VA_3DResNet":
+        elif kind in ("VA_3DResNet", "VA_3DVGGM"):
             out = m((inp["video_u8"].float().cuda() - 127.5) / 127.5)
         elif kind == "VA_3DVGGM_Split":
             se = inp["se_features"].cuda()
@@ -546,8 +557,77 @@ CASES.update({
     "golden_av_v2psplit_attention_eval": (case_golden, _c(name="av_v2psplit_attention_eval")),
 })
 
+def case_golden_size(name, chunk=None):
+    """Eval-mode parity AT BASELINE's configuration sizes (fixtures of oracle/make_golden_sizes.py: reference output and
+    bf16-emulating oracle output stored, inputs / weights re-drawn from seeds).  Reported:
+      out_ref / va_ref   CUDA vs the unmodified reference (range-normalised max; V/A channels: the 2e-2 north-star bar)
+      out_emu            CUDA vs the bf16-storage-emulating oracle (implementation error only)
+      floor / va_floor   emulating oracle vs reference = what bf16 storage itself costs on these weights (reported)
+      ccc_ref_diff       |CCC(cuda, labels) - CCC(reference, labels)|, worst of valence / arousal, over ALL frames of
+                         the fixture (>= 1024 for cfg3 / cfg4): the north star's "CCC equal to 3 decimals" (5e-4)
+      va_rms_ref         RMS (not max) V/A error relative to the reference's V/A RMS (reported)
+    """
+    from tests.golden_util import load, ref_batch
+    from m3t_b200.models.utils import concordance_cc2
+    fx = load(name)
+    m = _build(fx).eval()
+    inp = fx["inputs"]
+    with torch.no_grad():
+        if fx["kind"] == "AffWild2VA":
+            B = inp["video_u8"].shape[0]
+            step = chunk or B
+            outs = []
+            for lo in range(0, B, step):
+                outs.append(m(ref_batch({k: v[lo:lo + step] for k, v in inp.items()}, "cuda")).float().cpu())
+            out = torch.cat(outs)
+        else:
+            out = m((inp["video_u8"].float().cuda() - 127.5) / 127.5).float().cpu()
+    ref, emu = fx["out"], fx.get("out_emu")
+    errs = {"out_ref": _err(out, ref)}
+    nva = 2
+    if out.shape[-1] >= 2:
+        errs["va_ref"] = _err(out[..., -nva:], ref[..., -nva:])
+        errs["va_rms_ref"] = {"value": round(float((out[..., -nva:] - ref[..., -nva:]).pow(2).mean().sqrt() /
+                                                   ref[..., -nva:].pow(2).mean().sqrt()), 5)}
+    if emu is not None:
+        errs["out_emu"] = _err(out, emu)
+        errs["floor"] = _err(emu, ref)
+        errs["va_floor"] = {"value": round(_err(emu[..., -nva:], ref[..., -nva:]), 5)}
+    if "labels" in fx or out.shape[-1] >= 2:
+        if "labels" in fx:
+            labs = (fx["labels"]["label_valence"], fx["labels"]["label_arousal"])
+        else:
+            g = torch.Generator().manual_seed(99)
+            labs = tuple(torch.rand(out.shape[:-1], generator=g) * 2 - 1 for _ in range(2))
+        worst, info = 0.0, {}
+        for j, lab in enumerate(labs):
+            ch = out.shape[-1] - 2 + j
+            c_ref = float(concordance_cc2(ref[..., ch].reshape(-1), lab.reshape(-1), "none"))
+            c_gpu = float(concordance_cc2(out[..., ch].reshape(-1), lab.reshape(-1), "none"))
+            worst = max(worst, abs(c_ref - c_gpu))
+            info["ccc_ref_%d" % j], info["ccc_gpu_%d" % j] = round(c_ref, 6), round(c_gpu, 6)
+            # agreement of the two prediction tracks themselves (CCC between CUDA and reference predictions)
+            info["ccc_between_%d" % j] = round(float(concordance_cc2(out[..., ch].reshape(-1),
+                                                                     ref[..., ch].reshape(-1), "none")), 6)
+        info["frames"] = int(out.shape[0] * out.shape[1])
+        if info["frames"] >= 1024:      # "CCC equal to 3 decimals" is asserted where the CCC is a statistic, not 32 points
+            errs["ccc_ref_diff"] = worst
+        else:
+            info["ccc_ref_diff_small_sample"] = round(worst, 6)
+        errs["info"] = info
+    return errs
+
+
+for _n, _kw in (("cfg1_va3dresnet_eval", {}), ("cfg1_va3dresnet_eval_hard", {}), ("cfg3_av_resnet_eval", {}),
+                ("cfg3_av_resnet_eval_hard", {}), ("cfg3_av_v2psplit_eval", {}),
+                ("cfg4_av_resnet_eval_256x16", {"chunk": 64}), ("cfg4_av_resnet_eval_256x16_hard", {"chunk": 64}),
+                ("vggm_tcn_eval", {})):
+    CASES["size_" + _n] = (case_golden_size, _c(name=_n, **_kw))
+CASES["golden_vggm_tcn_train"] = (case_golden, _c(name="vggm_tcn_train"))
+CASES["golden_av_v2psplit_attention_train"] = (case_golden, _c(name="av_v2psplit_attention_train"))
+
 TOLS = {"out_ref": 3e-2, "va_ref": 2e-2, "floor": 1.0, "out_emu": 1.5e-2, "loss_ref": 2e-2, "loss_emu": 1e-2,
-        "grad_emu": 0.12, "grad_all_l2": 0.05, "dx": 3e-2}
+        "grad_emu": 0.12, "grad_all_l2": 0.05, "dx": 3e-2, "ccc_ref_diff": 5e-4}
 for _k in ("conv1.weight", "conv2.weight", "bn1.weight", "bn1.bias", "bn2.weight", "bn2.bias", "downsample.0.weight",
            "downsample.1.weight", "downsample.1.bias"):
     TOLS["d_" + _k] = 3e-2
@@ -1088,7 +1168,7 @@ def case_golden_fp32(name, terms=3):
             out = m(inp["x"].cuda())
         elif kind == "AttFusion":
             out = m(inp["x_a"].cuda(), inp["x_v"].cuda())
-        elif kind == "VA_3DResNet":
+        elif kind in ("VA_3DResNet", "VA_3DVGGM"):
             out = m((inp["video_u8"].float().cuda() - 127.5) / 127.5)
         elif kind == "VA_3DVGGM_Split":
             se = inp["se_features"].cuda()

@@ -15,7 +15,7 @@ TOL_GRAD = 5e-4
 
 
 def _sd(fx, requires_grad=False):
-    sd = synth_state_dict(fx["spec"], fx["seed"])
+    sd = synth_state_dict(fx["spec"], fx["seed"], **fx.get("synth_kw", {}))
     if requires_grad:
         for k, v in sd.items():
             if v.is_floating_point() and not k.endswith(("running_mean", "running_var")):
@@ -130,6 +130,69 @@ def test_affwild2va_training_step():
         name = k.split(".", 1)[1]
         worst = max(worst, grad_err(sd[name].grad, packed))
     assert worst < 2e-2, worst  # fp32-reference noise floor through 20 train-mode BN layers (see above)
+
+
+@pytest.mark.parametrize("name", ["cfg1_va3dresnet_eval", "cfg1_va3dresnet_eval_hard"])
+def test_config1_full_size(name):
+    """BASELINE config 1 at its real size (2 clips x 16 frames x 112 x 112, SURVEY 8(d) parity anchor): the oracle
+    against the unmodified reference's output, softened and as-written BatchNorm recipe."""
+    fx = load(name)
+    sd = _sd(fx)
+    x = (fx["inputs"]["video_u8"].float() - 127.5) / 127.5
+    with torch.no_grad():
+        out = R.va_3dresnet(x, sd, fx["ctor"]["frameLen"])
+    assert out.shape == (2, 16, 9)
+    assert rel_err(out, fx["out"]) < TOL_OUT
+    # the stored bf16-emulating output is this oracle's own (what the GPU cases compare with at sizes they do not re-run)
+    with torch.no_grad(), R.bf16_emulation():
+        emu = R.va_3dresnet(x, sd, fx["ctor"]["frameLen"])
+    assert rel_err(emu, fx["out_emu"]) < 1e-6
+
+
+def test_vggm_tcn_backend():
+    """VA_3DVGGM(backend='tcn'), the reference's only TemporalConvNet carrier (models/backbone.py:107-111,139-141):
+    eval output, train-mode output and gradients."""
+    fx = load("vggm_tcn_eval")
+    x = (fx["inputs"]["video_u8"].float() - 127.5) / 127.5
+    with torch.no_grad():
+        out = R.va_3dvggm(x, _sd(fx), "tcn")
+    assert rel_err(out, fx["out"]) < TOL_OUT
+    fx = load("vggm_tcn_train")
+    sd = _sd(fx, True)
+    x = (fx["inputs"]["video_u8"].float() - 127.5) / 127.5
+    out = R.va_3dvggm(x, sd, "tcn", train=True)
+    assert rel_err(out, fx["out"]) < TOL_OUT
+    (out * fx["cot"]).sum().backward()
+    worst = max(grad_err(sd[k.split(".", 1)[1]].grad, packed) for k, packed in fx["grads"].items()
+                if ".net." not in k             # `net.{0,4}` are aliases of conv1 / conv2 (one gradient)
+                and not (k.startswith("param.v2p.") and k.endswith(".bias") and packed["norm"] < 1e-3))
+    # (a Conv3d bias in front of a train-mode BatchNorm has an exactly-zero gradient: the reference holds rounding noise)
+    assert worst < 2e-3, worst
+
+
+def test_affwild2va_v2psplit_training_step():
+    fx = load("av_v2psplit_attention_train")
+    sd = _sd(fx, True)
+    b = ref_batch(fx["inputs"])
+    hp = hparams_ns(fx["hparams"])
+    y = R.affwild2va_forward(b, sd, hp, train=True)
+    loss = R.training_loss(y, b, hp.loss, hp.loss_lambda)
+    assert abs(float(loss) - fx["loss"]) < 1e-4 * max(1.0, abs(fx["loss"]))
+    loss.backward()
+    worst = max(grad_err(sd[k.split(".", 1)[1]].grad, packed) for k, packed in fx["grads"].items()
+                if packed["norm"] > 1e-3)       # conv biases in front of train-mode BN: exact zero, noise in the reference
+    assert worst < 2e-2, worst
+
+
+@pytest.mark.parametrize("name", ["cfg3_av_v2psplit_eval"])
+def test_config3_sample_of_clips(name):
+    """BASELINE config 3 fixture (32 clips x 32 frames): the oracle on the first 2 clips equals the reference's rows
+    (eval has no cross-clip operation), which also pins the seeded input recipe."""
+    fx = load(name)
+    b = {k: v[:2] for k, v in ref_batch(fx["inputs"]).items()}
+    with torch.no_grad():
+        out = R.affwild2va_forward(b, _sd(fx), hparams_ns(fx["hparams"]))
+    assert rel_err(out, fx["out"][:2]) < TOL_OUT
 
 
 def test_ccc():
