@@ -270,6 +270,14 @@ int m3t_sumsq_f32(const float* g, long long n, float* out, float* workspace, voi
 int m3t_adam_clip_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
                        float eps, float weight_decay, int step, float max_norm, float grad_scale,
                        const float* gnorm_sq, void* stream);
+/* The same step with the optimiser scalars resident on the device (CUDA-graph replays of the whole training step hold
+ * no host value that changes between steps): hyper = float[8] {lr, weight_decay, step, bc1, sqrt(bc2), -, -, -}; the
+ * call first advances hyper[2] by one and derives the two bias corrections on the device, then applies clip + Adam.
+ * The host rewrites hyper[0..1] when a scheduler changes them (models/model.py:393-407) and hyper[2] when a
+ * checkpoint restores the step count. */
+int m3t_adam_clip_step_dev(float* p, const float* g, float* m, float* v, long long n, float* hyper, float beta1,
+                           float beta2, float eps, float max_norm, float grad_scale, const float* gnorm_sq,
+                           void* stream);
 
 /* 3x3/pad-1 patches of a 1-channel fp32 image [N][H][W] as bf16 GEMM rows [N*H*W][16] (9 taps + 7 zero columns):
  * the 1->64 channel stem of the builder-declared audio ResNet composition (BASELINE config 2; no reference symbol,

@@ -67,6 +67,57 @@ __global__ void adam_clip_kernel(float* __restrict__ p, const float* __restrict_
   }
 }
 
+// Device-resident optimiser state (CUDA-graph replays of the training step): hyper = {lr, weight_decay, step, bc1,
+// sqrt(bc2)}.  adam_tick advances the step counter and derives the bias corrections on the device, so a captured step
+// holds no host scalar that changes between replays; lr / weight decay are rewritten by the host (schedulers) with
+// an ordinary copy into the same buffer.
+__global__ void adam_tick_kernel(float* __restrict__ hyper, float beta1, float beta2) {
+  const float s = hyper[2] + 1.f;
+  hyper[2] = s;
+  hyper[3] = 1.f - powf(beta1, s);
+  hyper[4] = sqrtf(1.f - powf(beta2, s));
+}
+
+__global__ void adam_clip_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                     float* __restrict__ v, long long n, const float* __restrict__ hyper, float beta1,
+                                     float beta2, float eps, float max_norm, float grad_scale,
+                                     const float* __restrict__ gnorm_sq) {
+  const float lr = __ldg(hyper), wd = __ldg(hyper + 1), bc1 = __ldg(hyper + 3), bc2_sqrt = __ldg(hyper + 4);
+  float coef = grad_scale;
+  if (max_norm > 0.f) {
+    const float total = sqrtf(__ldg(gnorm_sq)) * grad_scale;
+    coef *= fminf(1.f, max_norm / (total + 1e-6f));
+  }
+  const float step = lr / bc1;
+  const long long n4 = n / 4;
+  float4* p4 = reinterpret_cast<float4*>(p);
+  const float4* g4 = reinterpret_cast<const float4*>(g);
+  float4* m4 = reinterpret_cast<float4*>(m);
+  float4* v4 = reinterpret_cast<float4*>(v);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 pi = p4[i], gi = g4[i], mi = m4[i], vi = v4[i];
+#define M3T_ADAM1(c)                                                     \
+    {                                                                    \
+      const float gg = fmaf(wd, pi.c, gi.c * coef);                      \
+      mi.c = fmaf(beta1, mi.c, (1.f - beta1) * gg);                      \
+      vi.c = fmaf(beta2, vi.c, (1.f - beta2) * gg * gg);                 \
+      pi.c = pi.c - step * mi.c / (sqrtf(vi.c) / bc2_sqrt + eps);        \
+    }
+    M3T_ADAM1(x) M3T_ADAM1(y) M3T_ADAM1(z) M3T_ADAM1(w)
+#undef M3T_ADAM1
+    p4[i] = pi; m4[i] = mi; v4[i] = vi;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    for (long long i = n4 * 4; i < n; ++i) {
+      const float pi = p[i];
+      const float gg = fmaf(wd, pi, g[i] * coef);
+      const float mi = fmaf(beta1, m[i], (1.f - beta1) * gg);
+      const float vi = fmaf(beta2, v[i], (1.f - beta2) * gg * gg);
+      m[i] = mi; v[i] = vi;
+      p[i] = pi - step * mi / (sqrtf(vi) / bc2_sqrt + eps);
+    }
+}
+
 }  // namespace m3t
 
 using namespace m3t;
@@ -98,6 +149,22 @@ extern "C" int m3t_adam_clip_step(float* p, const float* g, float* m, float* v, 
   if (blocks > 148 * 16) blocks = 148 * 16;
   adam_clip_kernel<<<(int)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, bc1, bc2_sqrt, max_norm, grad_scale, gnorm_sq);
+  count_launch();
+  return launch_status();
+}
+
+extern "C" int m3t_adam_clip_step_dev(float* p, const float* g, float* m, float* v, long long n, float* hyper,
+                                      float beta1, float beta2, float eps, float max_norm, float grad_scale,
+                                      const float* gnorm_sq, void* stream) {
+  if (!hyper) return -1;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  adam_tick_kernel<<<1, 1, 0, st>>>(hyper, beta1, beta2);
+  count_launch();
+  long long blocks = (n / 4 + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks < 1) blocks = 1;
+  adam_clip_dev_kernel<<<(int)blocks, 256, 0, st>>>(p, g, m, v, n, hyper, beta1, beta2, eps, max_norm, grad_scale,
+                                                    gnorm_sq);
   count_launch();
   return launch_status();
 }

@@ -179,8 +179,9 @@ class TrainEngine:
             if not self.on_gpu:
                 self.flat_g.mul_(1.0 / self.world)
 
-    def _optimizer_step(self):
-        self.steps += 1
+    def _optimizer_step(self, count=True):
+        if count:
+            self.steps += 1
         if not self.on_gpu:
             for p, v in zip(self.params, self.grad_views):
                 p.grad = v
@@ -196,16 +197,94 @@ class TrainEngine:
         if self.clip:
             L.check(lib.m3t_sumsq_f32(L.ptr(self.flat_g), L.i64(self.n), L.ptr(self.gnorm_sq), L.ptr(self.sumsq_ws), st),
                     "sumsq")
-        L.check(lib.m3t_adam_clip_step(L.ptr(self.flat_p), L.ptr(self.flat_g), L.ptr(self.m), L.ptr(self.v),
-                                       L.i64(self.n), L.f32(self.lr), L.f32(self.betas[0]), L.f32(self.betas[1]),
-                                       L.f32(self.eps), L.f32(self.wd), L.i32(self.steps), L.f32(self.clip),
-                                       L.f32(1.0 / self.world), L.ptr(self.gnorm_sq), st), "adam_clip_step")
+        # lr / weight decay / step count live on the device (hyper): nothing a scheduler or the step counter changes is
+        # a kernel argument, so the same launch sequence can be replayed from a CUDA graph
+        self._sync_hyper()
+        L.check(lib.m3t_adam_clip_step_dev(L.ptr(self.flat_p), L.ptr(self.flat_g), L.ptr(self.m), L.ptr(self.v),
+                                           L.i64(self.n), L.ptr(self.hyper), L.f32(self.betas[0]),
+                                           L.f32(self.betas[1]), L.f32(self.eps), L.f32(self.clip),
+                                           L.f32(1.0 / self.world), L.ptr(self.gnorm_sq), st), "adam_clip_step_dev")
         # the kernel rewrote every parameter through the arena pointer: PyTorch's per-tensor version counters did not
         # move, so the packed / bf16 copies derived from the old values must be dropped explicitly
         ops.clear_caches()
 
+    def _sync_hyper(self, force=False):
+        """Mirror (lr, weight_decay[, step count]) into the device-resident optimiser state when they changed on the host
+        (schedulers, checkpoint restore).  The copy is stream-ordered and OUTSIDE any captured graph."""
+        if getattr(self, "hyper", None) is None:
+            self.hyper = torch.zeros(8, device=self.flat_p.device, dtype=torch.float32)
+            self._hyper_host = None
+            force = True
+        want = (float(self.lr), float(self.wd))
+        if force or self._hyper_host != want:
+            if torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("TrainEngine: lr / weight decay changed inside a graph capture")
+            if force:       # (re)seed the device step counter from the host's: steps already taken = self.steps - 1
+                self.hyper.copy_(torch.tensor([want[0], want[1], float(max(self.steps - 1, 0)), 0, 0, 0, 0, 0],
+                                              dtype=torch.float32), non_blocking=False)
+            else:
+                self.hyper[:2].copy_(torch.tensor(want, dtype=torch.float32), non_blocking=False)
+            self._hyper_host = want
+
+    def set_step_count(self, steps):
+        """Restore the optimiser's step count (checkpoint resume)."""
+        self.steps = int(steps)
+        if getattr(self, "hyper", None) is not None:
+            self.steps += 1
+            self._sync_hyper(force=True)
+            self.steps -= 1
+
+    # ---- the whole step as ONE CUDA-graph launch (launch-bound shards: strong scaling, small per-GPU batches) ----
+    def capture(self, example_batch, warmup=3):
+        """Capture forward + loss + backward + gradient all-reduce + clip + Adam for batches shaped like
+        `example_batch` into a CUDA graph; afterwards `step(batch)` with matching shapes copies the batch into the
+        static input buffers and replays.  At 32 clips per GPU (BASELINE config 4's global batch 256 on 8 GPUs) the
+        eager step is bound by ~600 Python / ctypes launches, not by the GPU.
+        What makes the step capturable: every kernel launches on the current stream and never synchronises; TMA
+        descriptors are by-value kernel parameters; the optimiser scalars are device-resident (`hyper`); weight
+        re-packing is part of the captured sequence (the derived-weight cache is empty at the start of every step);
+        NCCL all-reduce is capturable."""
+        if not self.on_gpu:
+            raise RuntimeError("graph capture needs the CUDA path")
+        if self.want_overlap:
+            raise RuntimeError("graph capture and the bucketed all-reduce are alternatives")
+        self.graph = None
+        self.static_in = {k: v.detach().clone() for k, v in example_batch.items()}
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(max(warmup, 1 if self.params is not None else 2)):
+                self._eager_step(self.static_in)      # also lays out the arena and allocates hyper
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self._sync_hyper()
+        g = torch.cuda.CUDAGraph()
+        ops.clear_caches()
+        with torch.cuda.graph(g, capture_error_mode="thread_local"):
+            self.static_loss = self._eager_step(self.static_in, count=False)
+        self.graph = g
+        self._graph_sig = {k: (tuple(v.shape), v.dtype) for k, v in self.static_in.items()}
+        return self
+
+    def _graph_matches(self, batch):
+        sig = self._graph_sig
+        return len(batch) == len(sig) and all(
+            k in sig and torch.is_tensor(v) and (tuple(v.shape), v.dtype) == sig[k] for k, v in batch.items())
+
     def step(self, batch):
         """One optimisation step on this rank's shard; returns the (detached) loss tensor, no host sync."""
+        if getattr(self, "graph", None) is not None and self._graph_matches(batch):
+            self._sync_hyper()
+            for k, v in batch.items():
+                if v.data_ptr() != self.static_in[k].data_ptr():
+                    self.static_in[k].copy_(v, non_blocking=True)
+            self.graph.replay()
+            self.steps += 1
+            ops.clear_caches()          # the replay rewrote the parameters through the arena
+            return self.static_loss
+        return self._eager_step(batch)
+
+    def _eager_step(self, batch, count=True):
         ops.DEFER_NUM_BATCHES_TRACKED = True
         try:
             y = self.model(batch)
@@ -220,7 +299,7 @@ class TrainEngine:
             loss.backward()
             self._gather_grads()
             self._allreduce_grads()
-        self._optimizer_step()
+        self._optimizer_step(count)
         if self.world > 1 and self.want_overlap and not self.overlap and self.params is not None:
             self._arm_overlap()
         return loss.detach()

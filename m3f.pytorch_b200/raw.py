@@ -16,21 +16,25 @@ _prof = None
 
 class KernelProfiler:
     def __init__(self):
-        self.records = []          # (key, algorithmic flops, start event, end event)
+        self.records = []          # (key, algorithmic flops, algorithmic HBM bytes, start event, end event)
 
-    def add(self, key, flops, e0, e1):
-        self.records.append((key, flops, e0, e1))
+    def add(self, key, flops, e0, e1, nbytes=0.0):
+        self.records.append((key, flops, nbytes, e0, e1))
 
     def summary(self):
-        """key -> dict(calls, ms_total, flops_total, tflops) (call after torch.cuda.synchronize())."""
+        """key -> dict(calls, ms_total, flops_total, bytes_total, tflops, gbps) (call after torch.cuda.synchronize()).
+        flops / bytes are ALGORITHMIC: unpadded 2*M*N*K for the tensor-core kernels; one read + one write
+        of each tensor a streaming pass must touch for the HBM-bound ones."""
         out = {}
-        for key, flops, e0, e1 in self.records:
-            d = out.setdefault(key, {"calls": 0, "ms_total": 0.0, "flops_total": 0.0})
+        for key, flops, nbytes, e0, e1 in self.records:
+            d = out.setdefault(key, {"calls": 0, "ms_total": 0.0, "flops_total": 0.0, "bytes_total": 0.0})
             d["calls"] += 1
             d["ms_total"] += e0.elapsed_time(e1)
             d["flops_total"] += flops
+            d["bytes_total"] += nbytes
         for d in out.values():
             d["tflops"] = d["flops_total"] / (d["ms_total"] * 1e-3) / 1e12 if d["ms_total"] > 0 else 0.0
+            d["gbps"] = d["bytes_total"] / (d["ms_total"] * 1e-3) / 1e9 if d["ms_total"] > 0 else 0.0
         return out
 
 
@@ -39,7 +43,7 @@ def set_profiler(p):
     _prof = p
 
 
-def _timed(key, flops, fn):
+def _timed(key, flops, fn, nbytes=0.0):
     if _prof is None:
         return fn()
     e0 = torch.cuda.Event(enable_timing=True)
@@ -47,8 +51,13 @@ def _timed(key, flops, fn):
     e0.record()
     r = fn()
     e1.record()
-    _prof.add(key, flops, e0, e1)
+    _prof.add(key, flops, e0, e1, nbytes)
     return r
+
+
+def _nb(*ts):
+    """Bytes of the given tensors (None skipped): algorithmic traffic of a streaming pass = each operand once."""
+    return float(sum(t.numel() * t.element_size() for t in ts if t is not None))
 
 
 def _chk_bf16(*ts):
@@ -356,8 +365,10 @@ def bn_act(y, scale, shift, res=None, res_scale=None, res_shift=None, relu=True)
     C = y.shape[-1]
     rows = y.numel() // C
     out = torch.empty_like(y)
-    L.check(_lib().m3t_bn_act(L.ptr(y), L.ptr(scale), L.ptr(shift), L.ptr(res), L.ptr(res_scale), L.ptr(res_shift),
-                              L.i32(relu), L.ptr(out), L.i64(rows), L.i32(C), L.stream_ptr()), "bn_act")
+    _timed("hbm bn_act C%d" % C, 0.0, lambda: L.check(
+        _lib().m3t_bn_act(L.ptr(y), L.ptr(scale), L.ptr(shift), L.ptr(res), L.ptr(res_scale), L.ptr(res_shift),
+                          L.i32(relu), L.ptr(out), L.i64(rows), L.i32(C), L.stream_ptr()), "bn_act"),
+           _nb(y, res, out))
     return out
 
 
@@ -375,9 +386,10 @@ def bn_bwd_reduce(dout, out, y, mean, invstd, relu, want_dz, scale=None, shift=N
     dz = torch.empty_like(y) if want_dz else None
     mode = _relu_mode(relu, out)
     assert mode != 2 or (scale is not None and shift is not None)
-    L.check(_lib().m3t_bn_bwd_reduce(L.ptr(dout), L.ptr(out), L.ptr(y), L.ptr(mean), L.ptr(invstd), L.ptr(scale),
-                                     L.ptr(shift), L.i32(mode), L.ptr(dz), L.ptr(sums), L.i64(rows), L.i32(C),
-                                     L.stream_ptr()), "bn_bwd_reduce")
+    _timed("hbm bn_bwd_reduce C%d" % C, 0.0, lambda: L.check(
+        _lib().m3t_bn_bwd_reduce(L.ptr(dout), L.ptr(out), L.ptr(y), L.ptr(mean), L.ptr(invstd), L.ptr(scale),
+                                 L.ptr(shift), L.i32(mode), L.ptr(dz), L.ptr(sums), L.i64(rows), L.i32(C),
+                                 L.stream_ptr()), "bn_bwd_reduce"), _nb(dout, out, y, dz))
     return sums, dz
 
 
@@ -387,9 +399,10 @@ def bn_bwd_apply(dout, out, y, mean, invstd, scale, sums, count, relu, shift=Non
     dy = torch.empty_like(y)
     mode = _relu_mode(relu, out)
     assert mode != 2 or shift is not None
-    L.check(_lib().m3t_bn_bwd_apply(L.ptr(dout), L.ptr(out), L.ptr(y), L.ptr(mean), L.ptr(invstd), L.ptr(scale),
-                                    L.ptr(shift), L.ptr(sums), ctypes_double(count), L.i32(mode), L.ptr(dy),
-                                    L.i64(rows), L.i32(C), L.stream_ptr()), "bn_bwd_apply")
+    _timed("hbm bn_bwd_apply C%d" % C, 0.0, lambda: L.check(
+        _lib().m3t_bn_bwd_apply(L.ptr(dout), L.ptr(out), L.ptr(y), L.ptr(mean), L.ptr(invstd), L.ptr(scale),
+                                L.ptr(shift), L.ptr(sums), ctypes_double(count), L.i32(mode), L.ptr(dy),
+                                L.i64(rows), L.i32(C), L.stream_ptr()), "bn_bwd_apply"), _nb(dout, out, y, dy))
     return dy
 
 
@@ -399,9 +412,10 @@ def bn_relu_maxpool(y, scale, shift, want_idx, pool=(3, 2, 1)):
     P, Q = (H + 2 * PAD - K) // S + 1, (W + 2 * PAD - K) // S + 1
     out = torch.empty((F_, P, Q, C), device=y.device, dtype=torch.bfloat16)
     idx = torch.empty((F_, P, Q, C), device=y.device, dtype=torch.uint8) if want_idx else None
-    L.check(_lib().m3t_bn_relu_maxpool(L.ptr(y), L.ptr(scale), L.ptr(shift), L.ptr(out), L.ptr(idx), L.i32(F_),
-                                       L.i32(H), L.i32(W), L.i32(C), L.i32(K), L.i32(S), L.i32(PAD), L.stream_ptr()),
-            "bn_relu_maxpool")
+    _timed("hbm bn_relu_maxpool %dx%d C%d" % (H, W, C), 0.0, lambda: L.check(
+        _lib().m3t_bn_relu_maxpool(L.ptr(y), L.ptr(scale), L.ptr(shift), L.ptr(out), L.ptr(idx), L.i32(F_),
+                                   L.i32(H), L.i32(W), L.i32(C), L.i32(K), L.i32(S), L.i32(PAD), L.stream_ptr()),
+        "bn_relu_maxpool"), _nb(y, out, idx))
     return out, idx
 
 
@@ -410,13 +424,15 @@ def maxpool_bn_bwd(dout, idx, y, mean, invstd, scale, shift, count, pool=(3, 2, 
     K, S, PAD = pool
     sums = torch.zeros((2, C), device=y.device, dtype=torch.float32)
     fn = _lib().m3t_maxpool_bn_bwd
-    L.check(fn(L.i32(0), L.ptr(dout), L.ptr(idx), L.ptr(y), L.ptr(mean), L.ptr(invstd), L.ptr(scale), L.ptr(shift),
-               L.ptr(sums), ctypes_double(count), L.ptr(None), L.i32(F_), L.i32(H), L.i32(W), L.i32(C), L.i32(K),
-               L.i32(S), L.i32(PAD), L.stream_ptr()), "maxpool_bn_bwd(reduce)")
+    _timed("hbm maxpool_bn_bwd(reduce) %dx%d C%d" % (H, W, C), 0.0, lambda: L.check(
+        fn(L.i32(0), L.ptr(dout), L.ptr(idx), L.ptr(y), L.ptr(mean), L.ptr(invstd), L.ptr(scale), L.ptr(shift),
+           L.ptr(sums), ctypes_double(count), L.ptr(None), L.i32(F_), L.i32(H), L.i32(W), L.i32(C), L.i32(K),
+           L.i32(S), L.i32(PAD), L.stream_ptr()), "maxpool_bn_bwd(reduce)"), _nb(dout, idx, y))
     dy = torch.empty_like(y)
-    L.check(fn(L.i32(1), L.ptr(dout), L.ptr(idx), L.ptr(y), L.ptr(mean), L.ptr(invstd), L.ptr(scale), L.ptr(shift),
-               L.ptr(sums), ctypes_double(count), L.ptr(dy), L.i32(F_), L.i32(H), L.i32(W), L.i32(C), L.i32(K),
-               L.i32(S), L.i32(PAD), L.stream_ptr()), "maxpool_bn_bwd(apply)")
+    _timed("hbm maxpool_bn_bwd(apply) %dx%d C%d" % (H, W, C), 0.0, lambda: L.check(
+        fn(L.i32(1), L.ptr(dout), L.ptr(idx), L.ptr(y), L.ptr(mean), L.ptr(invstd), L.ptr(scale), L.ptr(shift),
+           L.ptr(sums), ctypes_double(count), L.ptr(dy), L.i32(F_), L.i32(H), L.i32(W), L.i32(C), L.i32(K),
+           L.i32(S), L.i32(PAD), L.stream_ptr()), "maxpool_bn_bwd(apply)"), _nb(dout, idx, y, dy))
     return dy, sums
 
 
@@ -526,7 +542,9 @@ def zero_insert2(dy, H, W):
 
 def add_bf16(a, b):
     out = torch.empty_like(a)
-    L.check(_lib().m3t_add_bf16(L.ptr(a), L.ptr(b), L.ptr(out), L.i64(a.numel()), L.stream_ptr()), "add_bf16")
+    _timed("hbm add_bf16", 0.0, lambda: L.check(
+        _lib().m3t_add_bf16(L.ptr(a), L.ptr(b), L.ptr(out), L.i64(a.numel()), L.stream_ptr()), "add_bf16"),
+           _nb(a, b, out))
     return out
 
 
@@ -584,13 +602,15 @@ def gru_fwd(gi, w_hh_bf16, b_hh, B, T, H, want_saved, want_f32=False, cluster=No
     if cluster and not want_saved and B <= 64 and H % 64 == 0 and H <= 512:
         _timed("gru_fwd_cluster B%d T%d H%d" % (B, T, H), 0.0, lambda: L.check(
             _lib().m3t_gru_fwd_cluster(L.ptr(gi), L.ptr(w_hh_bf16), L.ptr(b_hh), L.ptr(out), L.ptr(out32), L.i32(B),
-                                       L.i32(T), L.i32(H), L.stream_ptr()), "gru_fwd_cluster"))
+                                       L.i32(T), L.i32(H), L.stream_ptr()), "gru_fwd_cluster"),
+               _nb(gi, w_hh_bf16, out, out32))
         return out, out32, None
     saved = torch.empty((B * T, 2, 4, H), device=dev, dtype=torch.float32) if want_saved else None
     counters = torch.empty((2 * ((B + 31) // 32) + 2,), device=dev, dtype=torch.int32)
     _timed("gru_fwd B%d T%d H%d" % (B, T, H), 0.0, lambda: L.check(
         _lib().m3t_gru_fwd(L.ptr(gi), L.ptr(w_hh_bf16), L.ptr(b_hh), L.ptr(out), L.ptr(out32), L.ptr(saved),
-                           L.ptr(counters), L.i32(B), L.i32(T), L.i32(H), L.stream_ptr()), "gru_fwd"))
+                           L.ptr(counters), L.i32(B), L.i32(T), L.i32(H), L.stream_ptr()), "gru_fwd"),
+           _nb(gi, w_hh_bf16, out, out32, saved))
     return out, out32, saved
 
 
@@ -604,7 +624,7 @@ def gru_bwd(dout, out, saved, w_hh_t_bf16, B, T, H):
     _timed("gru_bwd B%d T%d H%d" % (B, T, H), 0.0, lambda: L.check(
         _lib().m3t_gru_bwd(L.ptr(dout), L.ptr(out), L.ptr(saved), L.ptr(w_hh_t_bf16), L.ptr(dgi), L.ptr(dgh),
                            L.ptr(hprev), L.ptr(counters), L.ptr(dbias), L.i32(B), L.i32(T), L.i32(H),
-                           L.stream_ptr()), "gru_bwd"))
+                           L.stream_ptr()), "gru_bwd"), _nb(dout, out, saved, w_hh_t_bf16, dgi, dgh, hprev))
     return dgi, dgh, hprev, dbias
 
 
@@ -614,7 +634,7 @@ def att_mix_fwd(x_a, x_v, s_a, s_v):
     f = torch.empty_like(x_a)
     _timed("att_mix_fwd %dx%d" % (rows, C), 0.0, lambda: L.check(
         _lib().m3t_att_mix_fwd(L.ptr(x_a), L.ptr(x_v), L.ptr(s_a), L.ptr(s_v), L.ptr(f), L.ptr(None), L.i64(rows),
-                               L.i32(C), L.stream_ptr()), "att_mix_fwd"))
+                               L.i32(C), L.stream_ptr()), "att_mix_fwd"), _nb(x_a, x_v, s_a, s_v, f))
     return f
 
 
@@ -623,8 +643,10 @@ def att_mix_bwd(df, x_a, x_v, s_a, s_v):
     rows = x_a.numel() // C
     dxa, dxv = torch.empty_like(x_a), torch.empty_like(x_v)
     dsa, dsv = torch.empty_like(s_a), torch.empty_like(s_v)
-    L.check(_lib().m3t_att_mix_bwd(L.ptr(df), L.ptr(x_a), L.ptr(x_v), L.ptr(s_a), L.ptr(s_v), L.ptr(dxa), L.ptr(dxv),
-                                   L.ptr(dsa), L.ptr(dsv), L.i64(rows), L.i32(C), L.stream_ptr()), "att_mix_bwd")
+    _timed("att_mix_bwd %dx%d" % (rows, C), 0.0, lambda: L.check(
+        _lib().m3t_att_mix_bwd(L.ptr(df), L.ptr(x_a), L.ptr(x_v), L.ptr(s_a), L.ptr(s_v), L.ptr(dxa), L.ptr(dxv),
+                               L.ptr(dsa), L.ptr(dsv), L.i64(rows), L.i32(C), L.stream_ptr()), "att_mix_bwd"),
+           _nb(df, x_a, x_v, s_a, s_v, dxa, dxv, dsa, dsv))
     return dxa, dxv, dsa, dsv
 
 

@@ -1,6 +1,7 @@
 """ORACLE support (test infrastructure): import the UNMODIFIED reference modules from /root/reference.
 
-Only usable on the build box (the GPU box has no /root/reference).  `pytorch_lightning` and `matplotlib` are not
+On the build box this is /root/reference; on the GPU box (no /root/reference) it is the byte-for-byte vendored copy
+oracle/_ref written by oracle/make_ref.py (git-ignored build output that travels with the snapshot).  `pytorch_lightning` and `matplotlib` are not
 installed, so tiny stand-ins are registered before `models.model` / `models.utils` are imported;
 nothing in the reference tree is changed or copied.
 """
@@ -11,11 +12,20 @@ import types
 
 import torch.nn as nn
 
-REFERENCE_ROOT = os.environ.get("M3T_REFERENCE", "/root/reference")
+def _find_root():
+    """$M3T_REFERENCE, /root/reference (build box), else the vendored copy oracle/_ref (GPU box; oracle/make_ref.py)."""
+    here = os.path.dirname(os.path.abspath(__file__))
+    for cand in (os.environ.get("M3T_REFERENCE"), "/root/reference", os.path.join(here, "_ref")):
+        if cand and os.path.isfile(os.path.join(cand, "models", "model.py")):
+            return cand
+    return os.environ.get("M3T_REFERENCE", "/root/reference")
+
+
+REFERENCE_ROOT = _find_root()
 
 
 def available():
-    return os.path.isdir(os.path.join(REFERENCE_ROOT, "models"))
+    return os.path.isfile(os.path.join(REFERENCE_ROOT, "models", "model.py"))
 
 
 def _install_stubs():

@@ -1672,3 +1672,62 @@ if __name__ == "__main__":
     ok = not failures(name, errs)
     print("CASE_RESULT " + json.dumps({"case": name, "ok": ok, "errs": errs}))
     sys.exit(0 if ok else 1)
+
+
+# ----------------------------------------------------------------------------------------------------------
+# The whole training step as one CUDA-graph launch (engine.TrainEngine.capture): same trajectory as the eager step,
+# scheduler changes of lr reach the replays, launch count per replay = 0
+# ----------------------------------------------------------------------------------------------------------
+def case_train_graph(steps=5, clips=4, seed=0):
+    import bench as BN
+    from m3t_b200 import lib
+    from m3t_b200.engine import TrainEngine
+    from m3t_b200.models.model import AffWild2VA
+    hp = BN.hparams()
+    batches = [{k: v.cuda() for k, v in BN.synth_batch(clips, 100 + i, pin=False).items()} for i in range(steps)]
+    lrs = [2e-4, 2e-4, 1e-4, 1e-4, 5e-5][:steps]
+
+    def run(graph):
+        torch.manual_seed(seed)
+        m = AffWild2VA(hp)
+        BN.randomise_bn(m, 7)
+        m = m.cuda().train()
+        eng = TrainEngine(m, lr=lrs[0], weight_decay=1e-4, clip=1.0)
+        losses, launches = [], []
+        if graph:
+            # capture() runs warm-up steps on its example batch: rewind the model / optimiser state afterwards so both
+            # arms start from the same point
+            sd0 = {k: v.detach().clone() for k, v in m.state_dict().items()}
+            eng.capture(batches[0], warmup=2)
+            with torch.no_grad():
+                for k, v in m.state_dict().items():
+                    v.copy_(sd0[k])
+            eng.m.zero_()
+            eng.v.zero_()
+            eng.set_step_count(0)
+            from m3t_b200 import ops
+            ops.clear_caches()
+        for b, lr in zip(batches, lrs):
+            eng.lr = lr
+            n0 = lib.launch_count()
+            losses.append(float(eng.step(b)))
+            launches.append(lib.launch_count() - n0)
+        return losses, launches, {k: v.detach().float().cpu().clone() for k, v in m.state_dict().items()}
+
+    le, ne, sde = run(False)
+    lg, ng, sdg = run(True)
+    errs = {"graph_loss_step%d" % i: abs(a - b) / max(abs(b), 1e-6) for i, (a, b) in enumerate(zip(lg, le))}
+    num = sum(float((sdg[k] - sde[k]).pow(2).sum()) for k in sde if sde[k].is_floating_point())
+    den = sum(float((sde[k]).pow(2).sum()) for k in sde if sde[k].is_floating_point())
+    errs["graph_params_l2"] = (num / den) ** 0.5
+    errs["graph_replay_launches"] = float(max(ng))
+    errs["info"] = {"eager": [round(x, 5) for x in le], "graph": [round(x, 5) for x in lg],
+                    "eager_launches_per_step": ne[-1], "graph_launches_per_step": ng[-1]}
+    return errs
+
+
+CASES["train_graph_step"] = (case_train_graph, _c())
+for _i in range(5):
+    TOLS["graph_loss_step%d" % _i] = 2e-3
+TOLS["graph_params_l2"] = 1e-4
+TOLS["graph_replay_launches"] = 0.5
