@@ -639,7 +639,11 @@ for _k in ("conv1.weight", "conv2.weight", "bn1.weight", "bn1.bias", "bn2.weight
 # backward chain is asserted tightly by the well-conditioned block_* / convnd_* / golden_{gru,attfusion,tcn} cases;
 # here the whole-network gradient only has to stay within that floor (all-parameter L2 < 0.3) and forward / loss
 # parity is asserted at the normal tolerances.
+# The same holds for the VGG-M stacks (5 train-mode BN layers, 3 max-pools whose argmax routes flip under bf16 rounding):
+# on vggm_tcn_train / av_v2psplit_attention_train (128 frames) the emulated oracle is 18 % / 14 % (all-parameter L2)
+# from the fp32 oracle, the CUDA path 8.7 % / 7.4 % from the emulated oracle (measured).
 CHAOTIC_GRADS = {"golden_resnet_trunk_train", "golden_va3dresnet_train", "golden_av_resnet_attention_train",
+                 "golden_vggm_tcn_train", "golden_av_v2psplit_attention_train",
                  "va3dresnet_96px_train", "va3dresnet_15frames_train", "va3dresnet_1clip_2frames_train"}
 
 
@@ -1666,14 +1670,6 @@ for _k in ("gru_cluster_exact", "gru_cluster_f32_exact", "gru_cluster_nonfinite"
     TOLS[_k] = 0.5
 
 
-if __name__ == "__main__":
-    name = sys.argv[1]
-    errs = run_case(name)
-    ok = not failures(name, errs)
-    print("CASE_RESULT " + json.dumps({"case": name, "ok": ok, "errs": errs}))
-    sys.exit(0 if ok else 1)
-
-
 # ----------------------------------------------------------------------------------------------------------
 # The whole training step as one CUDA-graph launch (engine.TrainEngine.capture): same trajectory as the eager step,
 # scheduler changes of lr reach the replays, launch count per replay = 0
@@ -1731,3 +1727,11 @@ for _i in range(5):
     TOLS["graph_loss_step%d" % _i] = 2e-3
 TOLS["graph_params_l2"] = 1e-4
 TOLS["graph_replay_launches"] = 0.5
+
+
+if __name__ == "__main__":
+    name = sys.argv[1]
+    errs = run_case(name)
+    ok = not failures(name, errs)
+    print("CASE_RESULT " + json.dumps({"case": name, "ok": ok, "errs": errs}))
+    sys.exit(0 if ok else 1)
