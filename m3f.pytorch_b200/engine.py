@@ -286,10 +286,18 @@ class TrainEngine:
 
     def _eager_step(self, batch, count=True):
         ops.DEFER_NUM_BATCHES_TRACKED = True
+        if self.on_gpu:
+            from . import raw
+            raw.begin_step(self.all_params[0].device)     # one memset instead of ~90 zero-fill kernels (raw.StepPool)
         try:
-            y = self.model(batch)
+            return self._eager_step_body(batch, count)
         finally:
             ops.DEFER_NUM_BATCHES_TRACKED = False
+            if self.on_gpu:
+                raw.end_step(self.all_params[0].device)
+
+    def _eager_step_body(self, batch, count):
+        y = self.model(batch)
         if self.nbt and self.model.training:
             torch._foreach_add_(self.nbt, 1)
         loss, _ = self.model.compute_loss(y, batch, sync_free=True)

@@ -578,10 +578,18 @@ class Trainer:
                 if bi >= n_batches:
                     break
                 model.on_batch_start(batch)
-                out = model.training_step(batch, bi)
-                loss = out["loss"] if isinstance(out, dict) else out
-                loss.backward()
-                self._optimizer_step()
+                pooled = self.engine is not None and self.engine.on_gpu
+                if pooled:      # the step's zero-initialised accumulators come from one pre-cleared pool (raw.StepPool)
+                    from . import raw
+                    raw.begin_step(self.device)
+                try:
+                    out = model.training_step(batch, bi)
+                    loss = out["loss"] if isinstance(out, dict) else out
+                    loss.backward()
+                    self._optimizer_step()
+                finally:
+                    if pooled:
+                        raw.end_step(self.device)
                 self.global_step += 1
                 model.global_step = self.global_step
                 model.on_batch_end()

@@ -135,7 +135,7 @@ def _cba_train_fwd(x, w, gamma, beta, running_mean, running_var, residual, strid
     k = (w.shape[2], w.shape[3])
     geom = _geom2d(x.shape, Cout, k, stride, (pad, pad), (pad, pad))
     wf, _ = packed_filter(w, True)
-    stats = torch.zeros((2, Cout), device=x.device, dtype=torch.float32)
+    stats = raw.zeros_f32((2, Cout), x.device)
     y = raw.conv_fprop(x, wf, geom, stats=stats)
     y = y.view(y.shape[0], y.shape[2], y.shape[3], y.shape[4])
     count = y.numel() // Cout
@@ -364,7 +364,7 @@ class Stem3D(torch.autograd.Function):
         ctx.flops = flops
         halo = raw.USE_HALO_STEM and (H // 2) % 8 == 0 and (W // 2) == 56
         if training:
-            stats = torch.zeros((2, 64), device=video.device, dtype=torch.float32)
+            stats = raw.zeros_f32((2, 64), video.device)
             if halo:
                 y = raw.stem_fprop_halo(xs, wp, stats=stats, algo_flops=flops)
             else:
@@ -726,7 +726,7 @@ class ConvNdBNAct(torch.autograd.Function):
             else:
                 out = raw.conv_fprop(x, wf, geom, scale=ss[0], shift=ss[1], relu=relu, algo_flops=flops)
             return out if nd == 3 else out.view(N, Q, Cout)
-        stats = torch.zeros((2, Cout), device=x.device, dtype=torch.float32)
+        stats = raw.zeros_f32((2, Cout), x.device)
         y = raw.conv_fprop(x, wf, geom, stats=stats, algo_flops=flops)
         count = y.numel() // Cout
         fin = raw.bn_finalize(stats, count, gamma.detach(), beta.detach(), BN_EPS, BN_MOMENTUM, running_mean,
@@ -795,7 +795,7 @@ class Conv3x3C1BNReLU(torch.autograd.Function):
             ss = raw.bn_fold(gamma.detach(), beta.detach(), running_mean, running_var, None, BN_EPS)
             out = raw.gemm(patches, wb, scale=ss[0], shift=ss[1], relu=True)
             return out.view(N, H, W, Cout)
-        stats = torch.zeros((2, Cout), device=x.device, dtype=torch.float32)
+        stats = raw.zeros_f32((2, Cout), x.device)
         y = raw.gemm(patches, wb, stats=stats)
         fin = raw.bn_finalize(stats, y.shape[0], gamma.detach(), beta.detach(), BN_EPS, BN_MOMENTUM, running_mean,
                               running_var)

@@ -55,6 +55,69 @@ def _timed(key, flops, fn, nbytes=0.0):
     return r
 
 
+class StepPool:
+    """Zero-initialised fp32 scratch for ONE training step.  A step needs ~90 small zeroed accumulators (BatchNorm
+    statistics, split-K weight-gradient tiles, bias-gradient sums): as separate `torch.zeros` calls they were 51+ fill
+    kernels per step.  Here they are bump-allocated slices of one buffer that is cleared by ONE
+    memset at the start of the next step, over the part that was handed out (the rest has never been written).
+    Active only between begin_step() / end_step() (TrainEngine, Trainer.fit); elsewhere zeros_f32 is torch.zeros."""
+
+    def __init__(self, device, nbytes=96 << 20):
+        self.buf = torch.zeros(nbytes // 4, device=device, dtype=torch.float32)
+        self.used = 0          # floats handed out in the current step
+        self.dirty = 0         # high-water mark: everything ever handed out (a captured step graph clears exactly this
+        self.active = False    # range on every replay, whatever ran eagerly in between)
+
+    def begin(self):
+        if self.dirty:
+            self.buf[:self.dirty].zero_()
+        self.used = 0
+        self.active = True
+
+    def end(self):
+        self.active = False
+
+    def take(self, numel):
+        n = (numel + 63) // 64 * 64            # 256-byte slots
+        if not self.active or self.used + n > self.buf.numel():
+            return None
+        t = self.buf[self.used:self.used + numel]
+        self.used += n
+        self.dirty = max(self.dirty, self.used)
+        return t
+
+
+_pools = {}
+
+
+def begin_step(device):
+    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    pool = _pools.get(key)
+    if pool is None:
+        pool = _pools[key] = StepPool(torch.device("cuda", key))
+    pool.begin()
+    return pool
+
+
+def end_step(device):
+    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    if key in _pools:
+        _pools[key].end()
+
+
+def zeros_f32(shape, device):
+    """fp32 zeros: a slice of the active step pool, else torch.zeros."""
+    pool = _pools.get(torch.device(device).index)
+    if pool is not None and pool.active:
+        numel = 1
+        for d in shape:
+            numel *= int(d)
+        t = pool.take(numel)
+        if t is not None:
+            return t.view(shape)
+    return torch.zeros(shape, device=device, dtype=torch.float32)
+
+
 def _nb(*ts):
     """Bytes of the given tensors (None skipped): algorithmic traffic of a streaming pass = each operand once."""
     return float(sum(t.numel() * t.element_size() for t in ts if t is not None))
@@ -251,7 +314,7 @@ def wgrad_stem_halo(xs, dy, algo_flops=None):
     fp32 [64, 1280] (packed (kt,jh,jw,ch))."""
     _chk_bf16(xs, dy)
     B, T, H2, W2, _ = xs.shape
-    dw = torch.zeros((64, 1280), device=xs.device, dtype=torch.float32)
+    dw = zeros_f32((64, 1280), xs.device)
 
     def run():
         L.check(L.load().m3t_wgrad_stem_halo(L.ptr(xs), L.ptr(dy), L.ptr(dw), L.i32(B), L.i32(T), L.i32(H2),
@@ -266,7 +329,7 @@ def conv_wgrad(x, dy, g, splits=0, algo_flops=None):
     _chk_bf16(x, dy)
     Cin, Cout = g[5], g[6]
     taps = g[7] * g[8] * g[9]
-    dw = torch.zeros((Cout, taps * Cin), device=x.device, dtype=torch.float32)
+    dw = zeros_f32((Cout, taps * Cin), x.device)
     if (USE_HALO_WGRAD and splits == 0 and g[0] == 2 and Cin == 64 and Cout == 64 and tuple(g[7:10]) == (1, 3, 3)
             and tuple(g[10:13]) == (1, 1, 1) and tuple(g[13:19]) == (0, 0, 1, 1, 1, 1)
             and tuple(g[19:22]) == (1, 1, 1) and g[4] + 2 <= 48):
@@ -382,7 +445,7 @@ def _relu_mode(relu, out):
 def bn_bwd_reduce(dout, out, y, mean, invstd, relu, want_dz, scale=None, shift=None):
     C = y.shape[-1]
     rows = y.numel() // C
-    sums = torch.zeros((2, C), device=y.device, dtype=torch.float32)
+    sums = zeros_f32((2, C), y.device)
     dz = torch.empty_like(y) if want_dz else None
     mode = _relu_mode(relu, out)
     assert mode != 2 or (scale is not None and shift is not None)
@@ -422,7 +485,7 @@ def bn_relu_maxpool(y, scale, shift, want_idx, pool=(3, 2, 1)):
 def maxpool_bn_bwd(dout, idx, y, mean, invstd, scale, shift, count, pool=(3, 2, 1)):
     F_, H, W, C = y.shape
     K, S, PAD = pool
-    sums = torch.zeros((2, C), device=y.device, dtype=torch.float32)
+    sums = zeros_f32((2, C), y.device)
     fn = _lib().m3t_maxpool_bn_bwd
     _timed("hbm maxpool_bn_bwd(reduce) %dx%d C%d" % (H, W, C), 0.0, lambda: L.check(
         fn(L.i32(0), L.ptr(dout), L.ptr(idx), L.ptr(y), L.ptr(mean), L.ptr(invstd), L.ptr(scale), L.ptr(shift),
@@ -558,7 +621,7 @@ def gather_pack(w2d, idx, K):
 
 def scatter_unpack(dwp, idx, shape2d):
     rows, K = dwp.shape
-    dw = torch.zeros(shape2d, device=dwp.device, dtype=torch.float32)
+    dw = zeros_f32(shape2d, dwp.device)
     L.check(_lib().m3t_scatter_unpack_f32(L.ptr(dwp), L.ptr(idx), L.ptr(dw), L.i32(rows), L.i64(dw.stride(0)), L.i32(K),
                                           L.stream_ptr()), "scatter_unpack")
     return dw
@@ -567,7 +630,7 @@ def scatter_unpack(dwp, idx, shape2d):
 def colsum(x2d, cols=None):
     rows = x2d.shape[0]
     cols = cols or x2d.shape[1]
-    out = torch.zeros((cols,), device=x2d.device, dtype=torch.float32)
+    out = zeros_f32((cols,), x2d.device)
     L.check(_lib().m3t_colsum_bf16(L.ptr(x2d), L.i64(x2d.stride(0)), L.i64(rows), L.i32(cols), L.ptr(out),
                                    L.stream_ptr()), "colsum")
     return out
@@ -620,7 +683,7 @@ def gru_bwd(dout, out, saved, w_hh_t_bf16, B, T, H):
     dgh = torch.empty((B * T, 6 * H), device=dev, dtype=torch.bfloat16)
     hprev = torch.empty((B * T, 2 * H), device=dev, dtype=torch.bfloat16)
     counters = torch.empty((2 * ((B + 31) // 32) + 2,), device=dev, dtype=torch.int32)
-    dbias = torch.zeros((2, 6 * H), device=dev, dtype=torch.float32)     # [b_ih | b_hh] x [dir0 3H | dir1 3H]
+    dbias = zeros_f32((2, 6 * H), dev)     # [b_ih | b_hh] x [dir0 3H | dir1 3H]
     _timed("gru_bwd B%d T%d H%d" % (B, T, H), 0.0, lambda: L.check(
         _lib().m3t_gru_bwd(L.ptr(dout), L.ptr(out), L.ptr(saved), L.ptr(w_hh_t_bf16), L.ptr(dgi), L.ptr(dgh),
                            L.ptr(hprev), L.ptr(counters), L.ptr(dbias), L.i32(B), L.i32(T), L.i32(H),

@@ -1710,14 +1710,21 @@ def case_train_graph(steps=5, clips=4, seed=0):
             launches.append(lib.launch_count() - n0)
         return losses, launches, {k: v.detach().float().cpu().clone() for k, v in m.state_dict().items()}
 
+    def dist(a, b):
+        num = sum(float((a[k] - b[k]).pow(2).sum()) for k in b if b[k].is_floating_point())
+        den = sum(float((b[k]).pow(2).sum()) for k in b if b[k].is_floating_point())
+        return (num / den) ** 0.5
+
     le, ne, sde = run(False)
-    lg, ng, sdg = run(True)
+    le2, _, sde2 = run(False)     # a training step is not bit-reproducible (fp32 atomics): the
+    lg, ng, sdg = run(True)       # eager-vs-eager distance on this high-gain synthetic model is the yardstick
     errs = {"graph_loss_step%d" % i: abs(a - b) / max(abs(b), 1e-6) for i, (a, b) in enumerate(zip(lg, le))}
-    num = sum(float((sdg[k] - sde[k]).pow(2).sum()) for k in sde if sde[k].is_floating_point())
-    den = sum(float((sde[k]).pow(2).sum()) for k in sde if sde[k].is_floating_point())
-    errs["graph_params_l2"] = (num / den) ** 0.5
+    noise = dist(sde2, sde)
+    errs["graph_params_l2"] = dist(sdg, sde)
+    errs["graph_vs_noise"] = errs["graph_params_l2"] / max(noise, 1e-5)
     errs["graph_replay_launches"] = float(max(ng))
-    errs["info"] = {"eager": [round(x, 5) for x in le], "graph": [round(x, 5) for x in lg],
+    errs["info"] = {"eager": [round(x, 5) for x in le], "eager_again": [round(x, 5) for x in le2],
+                    "graph": [round(x, 5) for x in lg], "eager_vs_eager_params_l2": noise,
                     "eager_launches_per_step": ne[-1], "graph_launches_per_step": ng[-1]}
     return errs
 
@@ -1725,7 +1732,8 @@ def case_train_graph(steps=5, clips=4, seed=0):
 CASES["train_graph_step"] = (case_train_graph, _c())
 for _i in range(5):
     TOLS["graph_loss_step%d" % _i] = 2e-3
-TOLS["graph_params_l2"] = 1e-4
+TOLS["graph_params_l2"] = 1e-2
+TOLS["graph_vs_noise"] = 5.0
 TOLS["graph_replay_launches"] = 0.5
 
 
