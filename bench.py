@@ -546,8 +546,8 @@ def run_b200(args, rank, local_rank, world):
 
     # ---------------- BASELINE config 4 as written: GLOBAL batch 256 split over the N GPUs (strong scaling) ----------
     strong = None
-    if world > 1 and not args.no_strong and 256 % world == 0:
-        sc = 256 // world
+    if (world > 1 or args.shard_clips) and not args.no_strong and 256 % world == 0:
+        sc = args.shard_clips or 256 // world
         sh_host = {k: v[:sc].clone().pin_memory() for k, v in host.items()}
         sh_res = {k: v.to(dev) for k, v in sh_host.items()}
         graphed = not args.no_graph
@@ -568,9 +568,10 @@ def run_b200(args, rank, local_rank, world):
         if graphed:      # the uint8 batch has other keys than the float batch: capture that signature
             engine.capture({k: v.to(dev) for k, v in u8h.items()}, warmup=2)
         ms_su8, h2d_s = run_e2e(engine, u8h, args.warmup, args.steps)
-        strong = {"scaling": "strong", "global_clips": 256, "per_gpu_clips": sc,
-                  "value": 256 * T_FRAMES * args.steps / (ms_s * 1e-3), "unit": UNIT, "ms_per_step": ms_s / args.steps,
-                  "e2e": {"value": 256 * T_FRAMES * args.steps / (ms_su8 * 1e-3), "unit": UNIT,
+        gclips = sc * world
+        strong = {"scaling": "strong", "global_clips": gclips, "per_gpu_clips": sc,
+                  "value": gclips * T_FRAMES * args.steps / (ms_s * 1e-3), "unit": UNIT, "ms_per_step": ms_s / args.steps,
+                  "e2e": {"value": gclips * T_FRAMES * args.steps / (ms_su8 * 1e-3), "unit": UNIT,
                           "h2d_bytes_per_step": h2d_s, "d2h_bytes_per_step": 4, "ms_per_step": ms_su8 / args.steps},
                   "cuda_graph": graphed, "host_launches_per_step": l_s / args.steps,
                   "ideal_ms_per_step": (ms / args.steps) * sc / args.clips,
@@ -673,6 +674,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end legs (profiling runs)")
     ap.add_argument("--no-f32-e2e", action="store_true", help="skip the float32-clips end-to-end leg")
     ap.add_argument("--no-strong", action="store_true", help="N > 1: skip the global-batch-256 (strong scaling) block")
+    ap.add_argument("--shard-clips", type=int, default=0, help="diagnostic: time the strong-scaling shard of this many "
+                    "clips on the GPUs given (e.g. 32 = one rank's share at N = 8, without the all-reduce when N = 1)")
     ap.add_argument("--no-graph", action="store_true", help="strong block: eager step instead of the CUDA-graph replay")
     ap.add_argument("--no-trainer", action="store_true", help="N = 1: skip the Trainer.fit end-to-end leg")
     ap.add_argument("--no-secondary", action="store_true", help="N = 1: skip BASELINE configs 1, 2, 3, 5")

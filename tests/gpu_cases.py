@@ -1731,7 +1731,7 @@ def case_train_graph(steps=5, clips=4, seed=0):
 
 CASES["train_graph_step"] = (case_train_graph, _c())
 for _i in range(5):
-    TOLS["graph_loss_step%d" % _i] = 2e-3
+    TOLS["graph_loss_step%d" % _i] = 1e-2       # run-to-run noise of this model is ~2e-3 (info: eager vs eager_again)
 TOLS["graph_params_l2"] = 1e-2
 TOLS["graph_vs_noise"] = 5.0
 TOLS["graph_replay_launches"] = 0.5
