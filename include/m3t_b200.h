@@ -215,12 +215,12 @@ int m3t_dropout_bf16(const void* x, void* y, long long n, float p, unsigned long
  * Replaces nn.GRU(batch_first=True, bidirectional=True) (models/rnn.py:17,72-75) = cuDNN RNN in the reference. */
 int m3t_gru_fwd(const float* gi, const void* w_hh_bf16, const float* b_hh, void* out_bf16, float* out_f32,
                 float* saved, unsigned* counters, int B, int T, int H, void* stream);
-/* Small-batch inference variant of m3t_gru_fwd (B <= 64, H in {128, 256, 512}, no `saved`): per direction and group
+/* Small-batch variant of m3t_gru_fwd (B <= 64, H in {128, 256, 512}; `saved` as in m3t_gru_fwd or NULL): per direction and group
  * of 16 batch rows one thread-block cluster (H/64 CTAs), W_hh stays in shared memory and the hidden state is exchanged over
  * distributed shared memory behind one hardware cluster barrier per step instead of through L2 + an arrival counter.
  * Same operands, k order and gate arithmetic as m3t_gru_fwd.  Returns -1 for shapes it does not take. */
 int m3t_gru_fwd_cluster(const float* gi, const void* w_hh_bf16, const float* b_hh, void* out_bf16, float* out_f32,
-                        int B, int T, int H, void* stream);
+                        float* saved, int B, int T, int H, void* stream);
 /* The bf16 weight copies of one bidirectional layer in one launch (rebuilt after every optimizer step):
  * wih bf16 [6H][Ipad] = [W_ih ; W_ih_reverse] zero-padded to Ipad columns, whh bf16 [2][3H][H], whht bf16 [2][H][3H]
  * (W_hh transposed, for m3t_gru_bwd; may be NULL); bias fp32 [2][6H] = [b_ih ; b_ih_reverse], [b_hh ; b_hh_reverse]

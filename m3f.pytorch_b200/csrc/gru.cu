@@ -369,7 +369,7 @@ __global__ void __launch_bounds__(kGruThreads, 1) gru_fwd_cluster_kernel(const G
       const int b = b0 + lrow;
       uint32_t packed = 0u;
       if (b < B) {
-        float hnew[2];
+        float hnew[2], rr[2], zz[2], nn[2], hnn[2];
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
           const int e = rs * 2 + q;
@@ -382,8 +382,16 @@ __global__ void __launch_bounds__(kGruThreads, 1) gru_fwd_cluster_kernel(const G
           const float n = tanhf((q ? gin[rs].y : gin[rs].x) + r * hn);
           hnew[q] = (1.f - z) * n + z * hp;
           hreg[e] = hnew[q];
+          rr[q] = r; zz[q] = z; nn[q] = n; hnn[q] = hn;
         }
         const long long row = (long long)b * T + t;
+        if (p.saved) {      // training: gates for BPTT, same layout as gru_fwd_kernel
+          float* sv = p.saved + (row * 2 + dir) * 4 * H + js * kCJS + j0;
+          *reinterpret_cast<float2*>(sv) = make_float2(rr[0], rr[1]);
+          *reinterpret_cast<float2*>(sv + H) = make_float2(zz[0], zz[1]);
+          *reinterpret_cast<float2*>(sv + 2 * H) = make_float2(nn[0], nn[1]);
+          *reinterpret_cast<float2*>(sv + 3 * H) = make_float2(hnn[0], hnn[1]);
+        }
         packed = pack_bf16x2(hnew[0], hnew[1]);
         *reinterpret_cast<uint32_t*>(p.out + row * 2 * H + dir * H + js * kCJS + j0) = packed;
         if (p.out_f32)
@@ -584,7 +592,7 @@ extern "C" int m3t_gru_fwd(const float* gi, const void* w_hh_bf16, const float* 
 }
 
 extern "C" int m3t_gru_fwd_cluster(const float* gi, const void* w_hh_bf16, const float* b_hh, void* out_bf16,
-                                   float* out_f32, int B, int T, int H, void* stream) {
+                                   float* out_f32, float* saved, int B, int T, int H, void* stream) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (H % kCJS != 0 || H > 512 || B <= 0 || B > 4 * kCRows || T <= 0) return -1;   // <= 64 CTAs: one wave
   GruParams p;
@@ -595,6 +603,7 @@ extern "C" int m3t_gru_fwd_cluster(const float* gi, const void* w_hh_bf16, const
   p.b_hh = b_hh;
   p.out = reinterpret_cast<__nv_bfloat16*>(out_bf16);
   p.out_f32 = out_f32;
+  p.saved = saved;
   const int ncta = H / kCJS;     // 2, 4 or 8: a portable cluster size
   const size_t smem = (size_t)(3 * kCJS + kCRows) * (H + 8) * 2 + (size_t)2 * kCRows * kCJS * 2;
   if (cudaFuncSetAttribute(gru_fwd_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=

@@ -248,8 +248,18 @@ class TrainEngine:
             raise RuntimeError("graph capture needs the CUDA path")
         if self.want_overlap:
             raise RuntimeError("graph capture and the bucketed all-reduce are alternatives")
+        from . import streams
         self.graph = None
         self.static_in = {k: v.detach().clone() for k, v in example_batch.items()}
+        nclips = max(int(v.shape[0]) for v in self.static_in.values() if v.dim() > 0)
+        prev_overlap = streams.set_train_overlap(
+            nclips <= streams.MAX_CLIPS and os.environ.get("M3T_TRAIN_STREAMS", "1") != "0")
+        try:
+            return self._capture(warmup)
+        finally:
+            streams.set_train_overlap(prev_overlap)
+
+    def _capture(self, warmup):
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):

@@ -23,6 +23,17 @@ import torch
 _enabled = os.environ.get("M3T_STREAMS", "1") != "0"
 _side = {}
 MAX_CLIPS = 64
+# Training: the fork is allowed only while this flag is set — TrainEngine.capture sets it for small per-GPU shards
+# (<= MAX_CLIPS), where the step is latency-bound and is replayed as a CUDA graph: the forks / joins of the forward
+# become graph dependencies, and autograd runs each branch's backward on the stream its forward ran on, so the
+# recurrences of the audio stream and of one attention scorer overlap the other branch in both directions.
+_train_overlap = False
+
+
+def set_train_overlap(flag):
+    global _train_overlap
+    prev, _train_overlap = _train_overlap, bool(flag)
+    return prev
 
 
 def set_enabled(flag):
@@ -33,7 +44,9 @@ def set_enabled(flag):
 
 def overlap_ok(x):
     """x: a (B, ...) device tensor of the forward being run."""
-    if not _enabled or torch.is_grad_enabled() or not torch.is_tensor(x) or not x.is_cuda:
+    if not _enabled or not torch.is_tensor(x) or not x.is_cuda:
+        return False
+    if torch.is_grad_enabled() and not _train_overlap:
         return False
     from . import fp32
     return not fp32.enabled() and x.shape[0] <= MAX_CLIPS

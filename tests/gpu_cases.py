@@ -1644,9 +1644,10 @@ def case_gru_cluster(seed=0):
         gi = (torch.randn((B * T, 6 * H), generator=g) * 0.8).cuda()
         w = (torch.randn((2, 3 * H, H), generator=g) / H ** 0.5).bfloat16().cuda()
         bh = (torch.randn((2, 3 * H), generator=g) * 0.1).cuda()
-        a, a32, _ = raw.gru_fwd(gi, w, bh, B, T, H, False, want_f32=True, cluster=False)
-        c, c32, _ = raw.gru_fwd(gi, w, bh, B, T, H, False, want_f32=True, cluster=True)
+        a, a32, sa = raw.gru_fwd(gi, w, bh, B, T, H, True, want_f32=True, cluster=False)
+        c, c32, sc = raw.gru_fwd(gi, w, bh, B, T, H, True, want_f32=True, cluster=True)
         torch.cuda.synchronize()
+        errs["gru_cluster_saved_exact"] = errs.get("gru_cluster_saved_exact", 0.0) + float((sa != sc).sum())
         errs["gru_cluster_exact"] += float((a.view(torch.int16) != c.view(torch.int16)).sum())
         errs["gru_cluster_f32_exact"] += float((a32 != c32).sum())
         errs["gru_cluster_nonfinite"] += float((~torch.isfinite(c32)).sum())
@@ -1666,7 +1667,7 @@ def case_gru_cluster(seed=0):
 
 
 CASES["gru_cluster_exact"] = (case_gru_cluster, _c())
-for _k in ("gru_cluster_exact", "gru_cluster_f32_exact", "gru_cluster_nonfinite"):
+for _k in ("gru_cluster_exact", "gru_cluster_f32_exact", "gru_cluster_nonfinite", "gru_cluster_saved_exact"):
     TOLS[_k] = 0.5
 
 
