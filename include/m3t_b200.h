@@ -59,6 +59,22 @@ int m3t_conv_fprop_bf16(const void* x, const void* w_packed, void* y, const int*
                         const float* shift, const void* residual, int relu, float* stats, int tile_hint,
                         void* stream);
 
+/* One weight-normed dilated causal Conv1d of a TemporalBlock with everything that follows it in the block fused into
+ * the epilogue (models/tcn.py:19-33 conv -> Chomp1d -> ReLU -> Dropout, :43-46 relu(net(x) + res)):
+ *   t = dropout_p(relu(conv(x) * scale[c] + shift[c]))         scale = weight_g / ||weight_v|| (weight-norm), shift = bias
+ *   residual == NULL:  y = t                                    (first conv of the block)
+ *   residual != NULL:  y = relu(t + residual), t_out = t        (second conv; t_out may be NULL at inference)
+ * x channels-last bf16 [B,T,Cin], w_packed = bf16 pack of weight_v, geom as m3t_conv_fprop_bf16 (nd = 1, left-only
+ * padding (k-1)*dilation: Chomp1d is index math).  Dropout mask = the counter-based generator of m3t_dropout_bf16 over
+ * the element index of y (row * Cout + c).  Replaces cuDNN conv1d + 2 `.contiguous()` copies + ATen relu / dropout /
+ * add / relu per block in the reference. */
+int m3t_tcn_conv_bf16(const void* x, const void* w_packed, void* y, void* t_out, const int* geom, const float* scale,
+                      const float* shift, const void* residual, float drop_p, unsigned long long seed, void* stream);
+/* Backward of that epilogue in one pass: dsum = dy * [y > 0] (residual case: y, dsum non-NULL; dsum is also the
+ * residual's gradient), da = dsum * scale * [t > 0] (t = the stored pre-residual tensor, or y itself without residual;
+ * scale = 1 / (1 - p)). */
+int m3t_tcn_epilogue_bwd_bf16(const void* dy, const void* y, const void* t, void* dsum, void* da, float scale,
+                              long long n, void* stream);
 /* m3t_conv_fprop_bf16 (2-D, no epilogue arithmetic) whose output pixel (n, p, q) is stored at pixel offset
  * n*img_pitch + p*row_pitch + q*px_pitch (in units of Cout-element pixels) from y instead of densely: the data
  * gradient of a stride-2 convolution is evaluated as one small stride-1 convolution of dY per output parity

@@ -1019,16 +1019,8 @@ __global__ void add_bf16_kernel(const __nv_bfloat16* __restrict__ a, const __nv_
   }
 }
 
-// Inverted dropout with a counter-based generator (splitmix64 of seed + (i+1)*golden, top 32 bits): element i is
-// kept iff u_i >= thresh.  Stateless, so the backward pass re-derives the mask from (seed, i) instead of reading one.
-__device__ __forceinline__ unsigned dropout_u32(unsigned long long seed, long long i) {
-  unsigned long long z = seed + (unsigned long long)(i + 1) * 0x9E3779B97F4A7C15ull;
-  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-  z ^= z >> 31;
-  return (unsigned)(z >> 32);
-}
-
+// Inverted dropout with the counter-based generator of common.cuh (dropout_u32): the backward pass re-derives the
+// mask from (seed, i) instead of reading one.
 __global__ void dropout_bf16_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, long long nvec,
                                     unsigned thresh, float scale, unsigned long long seed) {
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -1097,6 +1089,30 @@ __global__ void relu_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv
 #pragma unroll
     for (int j = 0; j < 8; ++j) d[j] = o[j] > 0.f ? d[j] : 0.f;
     reinterpret_cast<uint4*>(dz)[i] = pack8(d);
+  }
+}
+
+// Backward of the fused TemporalBlock conv epilogue  y = [relu](drop(relu(a)) + res):
+//   dsum = dy * [y > 0]            (only when a residual joined; also the residual's gradient)
+//   da   = dsum * scale * [t > 0]  (t = drop(relu(a)): positive exactly where the ReLU passed AND dropout kept it)
+__global__ void tcn_epi_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ y,
+                                   const __nv_bfloat16* __restrict__ t, __nv_bfloat16* __restrict__ dsum,
+                                   __nv_bfloat16* __restrict__ da, float scale, long long nvec) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec;
+       i += (long long)gridDim.x * blockDim.x) {
+    float d[8], tv[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(dy) + i), d);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(t) + i), tv);
+    if (y) {
+      float yv[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(y) + i), yv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) d[j] = yv[j] > 0.f ? d[j] : 0.f;
+      reinterpret_cast<uint4*>(dsum)[i] = pack8(d);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) d[j] = tv[j] > 0.f ? d[j] * scale : 0.f;
+    reinterpret_cast<uint4*>(da)[i] = pack8(d);
   }
 }
 
@@ -1513,10 +1529,18 @@ extern "C" int m3t_relu_bwd_bf16(const void* dy, const void* out, void* dz, long
   return launch_status();
 }
 
+extern "C" int m3t_tcn_epilogue_bwd_bf16(const void* dy, const void* y, const void* t, void* dsum, void* da,
+                                         float scale, long long n, void* stream) {
+  if (n % 8 || !dy || !t || !da || ((y != nullptr) != (dsum != nullptr))) return -1;
+  tcn_epi_bwd_kernel<<<ew_blocks(n / 8), kEwThreads, 0, ST(stream)>>>(CBF(dy), CBF(y), CBF(t), BF(dsum), BF(da), scale,
+                                                                      n / 8);
+  count_launch();
+  return launch_status();
+}
+
 extern "C" int m3t_dropout_bf16(const void* x, void* y, long long n, float p, unsigned long long seed, void* stream) {
   if (n % 8 || !(p >= 0.f) || !(p < 1.f)) return -1;
-  const double t = (double)p * 4294967296.0;
-  const unsigned thresh = t >= 4294967295.0 ? 4294967295u : (unsigned)t;
+  const unsigned thresh = dropout_threshold(p);
   dropout_bf16_kernel<<<ew_blocks(n / 8), kEwThreads, 0, ST(stream)>>>(CBF(x), BF(y), n / 8, thresh, 1.f / (1.f - p),
                                                                        seed);
   count_launch();

@@ -156,9 +156,14 @@ void conv_fill_params(UmmaParams& p, const ConvGeom& g) {
 
 }  // namespace
 
+struct TcnEpilogue {      // fused TemporalBlock epilogue (UmmaParams::pre_act ...)
+  float drop_p;
+  unsigned long long seed;
+  void* t_out;
+};
 static int conv_fprop_impl(const void* x, const void* w_packed, void* y, const int* geom, const float* scale,
                            const float* shift, const void* residual, int relu, float* stats, int tile_hint,
-                           const long long* out_map, void* stream);
+                           const long long* out_map, void* stream, const TcnEpilogue* tcn = nullptr);
 
 // When the persistent kernel is the default (tests/tune_conv.py, 4096 frames): it wins whenever a tile has at least
 // two k-iterations (28->14 64->128 s2 0.198 -> 0.166 ms, 7x7x256 0.214 -> 0.189, 4x4x512 0.255 -> 0.226 = 1367
@@ -175,6 +180,15 @@ extern "C" int m3t_conv_fprop_bf16(const void* x, const void* w_packed, void* y,
   return conv_fprop_impl(x, w_packed, y, geom, scale, shift, residual, relu, stats, tile_hint, nullptr, stream);
 }
 
+extern "C" int m3t_tcn_conv_bf16(const void* x, const void* w_packed, void* y, void* t_out, const int* geom,
+                                 const float* scale, const float* shift, const void* residual, float drop_p,
+                                 unsigned long long seed, void* stream) {
+  if (!(drop_p >= 0.f) || !(drop_p < 1.f) || (t_out && !residual)) return -1;
+  TcnEpilogue e;
+  e.drop_p = drop_p; e.seed = seed; e.t_out = t_out;
+  return conv_fprop_impl(x, w_packed, y, geom, scale, shift, residual, residual ? 1 : 0, nullptr, 0, nullptr, stream, &e);
+}
+
 extern "C" int m3t_conv_fprop_scatter_bf16(const void* x, const void* w_packed, void* y, const int* geom,
                                            long long img_pitch, long long row_pitch, long long px_pitch,
                                            int accumulate, int tile_hint, void* stream) {
@@ -185,7 +199,7 @@ extern "C" int m3t_conv_fprop_scatter_bf16(const void* x, const void* w_packed, 
 
 static int conv_fprop_impl(const void* x, const void* w_packed, void* y, const int* geom, const float* scale,
                            const float* shift, const void* residual, int relu, float* stats, int tile_hint,
-                           const long long* out_map, void* stream) {
+                           const long long* out_map, void* stream, const TcnEpilogue* tcn) {
   ConvGeom g;
   int rc = conv_geom(g, geom);
   if (rc) return rc;
@@ -205,6 +219,15 @@ static int conv_fprop_impl(const void* x, const void* w_packed, void* y, const i
   p.scale = scale; p.shift = shift;
   p.residual = reinterpret_cast<const __nv_bfloat16*>(residual); p.ldr = g.Cout;
   p.relu = relu; p.stats = stats;
+  if (tcn) {
+    p.pre_act = 1;
+    if (tcn->drop_p > 0.f) {
+      p.drop_thresh = dropout_threshold(tcn->drop_p);
+      p.drop_scale = 1.f / (1.f - tcn->drop_p);
+      p.drop_seed = tcn->seed;
+    }
+    p.out2 = reinterpret_cast<__nv_bfloat16*>(tcn->t_out);
+  }
   if (out_map) {
     p.oq = g.Q; p.op = g.P;
     p.o_img = out_map[0]; p.o_row = out_map[1]; p.o_px = out_map[2];

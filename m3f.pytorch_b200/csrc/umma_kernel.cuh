@@ -7,6 +7,7 @@
 // co-reside per SM whenever shared memory and TMEM columns allow, so one CTA's epilogue overlaps the
 // other's main loop.  Accumulators live in TMEM (MT*BN fp32 columns).
 #pragma once
+#include "common.cuh"
 #include "ptx.cuh"
 
 namespace m3t {
@@ -53,6 +54,14 @@ struct UmmaParams {
   // block 1, ...).  The fp32-parity mode puts the small correction terms in the first channel blocks and the main term
   // last, so the tensor core's per-MMA accumulator truncation acts on the full magnitude for 1/3 of the K steps only.
   int cb_major;
+  // ---- fused TemporalBlock epilogue (models/tcn.py:19-33,43-46): t = drop(relu(acc*scale+shift)); out2 = t (saved for
+  //      backward when a residual follows); out = residual ? relu(t + residual) : t.  pre_act != 0 selects this order
+  //      (the activation BEFORE the residual); drop_thresh == 0: no dropout.
+  int pre_act;
+  unsigned drop_thresh;
+  float drop_scale;
+  unsigned long long drop_seed;
+  __nv_bfloat16* out2;
 };
 
 __device__ __forceinline__ long long out_row(const UmmaParams& p, long long m) {
@@ -164,6 +173,35 @@ __device__ __forceinline__ void epi_store_chunk(const UmmaParams& p, const float
       }
     }
     const int ncols = min(32, min(cols_left, p.N - nc0));
+    if (p.pre_act) {
+      // ReLU -> inverted dropout on the bf16-rounded activation (what the stand-alone pass m3t_dropout_bf16 sees) ->
+      // optional store of this pre-residual tensor
+#pragma unroll
+      for (int i = 0; i < 32; ++i) o[i] = fmaxf(o[i], 0.f);
+      if (p.drop_thresh) {
+        const long long e0 = mo * p.ldc + nc0;
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          o[i] = dropout_u32(p.drop_seed, e0 + i) >= p.drop_thresh
+                     ? __bfloat162float(__float2bfloat16(o[i])) * p.drop_scale : 0.f;
+      }
+      if (p.out2 && ncols > 0) {
+        __nv_bfloat16* op2 = p.out2 + mo * p.ldc + nc0;
+        if (ncols == 32 && (p.ldc & 7) == 0) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+            reinterpret_cast<uint4*>(op2)[g] =
+                make_uint4(pack_bf16x2(o[8 * g], o[8 * g + 1]), pack_bf16x2(o[8 * g + 2], o[8 * g + 3]),
+                           pack_bf16x2(o[8 * g + 4], o[8 * g + 5]), pack_bf16x2(o[8 * g + 6], o[8 * g + 7]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (i < ncols) op2[i] = __float2bfloat16(o[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[i] = __bfloat162float(__float2bfloat16(o[i]));   // the sum reads the stored t
+      }
+    }
     if (p.residual) {
       const __nv_bfloat16* rp = p.residual + (p.res_mapped ? mo : m) * p.ldr + nc0;
       if (ncols == 32 && (p.ldr & 7) == 0) {

@@ -2,9 +2,11 @@
 
 Same module tree and state_dict keys as the reference (`network.{i}.conv{1,2}.{bias,weight_g,weight_v}`, their
 aliases under `net.{0,4}`, `downsample.*`).  Each weight-normed dilated causal Conv1d runs as an implicit-GEMM
-conv over channels-last (B,T,C) with left-only zero padding -- Chomp1d becomes index math -- and bias + ReLU in the
-epilogue; the block's residual add + ReLU is one more streaming pass.
+conv over channels-last (B,T,C) with left-only zero padding -- Chomp1d becomes index math -- and the rest of the block
+rides in the conv epilogues (ops.TCNConvFn / m3t_tcn_conv_bf16): weight-norm scale, bias, ReLU, dropout, and for the
+second conv the residual add + final ReLU.  M3T_TCN_FUSED=0 keeps the round-1 path (conv + separate dropout / add).
 """
+import os
 import warnings
 
 import torch
@@ -60,6 +62,17 @@ class TemporalBlock(nn.Module):
                 conv.weight.data.normal_(0, 0.01)
 
     def forward_cl(self, x):
+        """Two launches per block (three when a 1x1 `downsample` exists): each conv carries weight-norm scale, bias,
+        ReLU, dropout and — the second one — the residual add + final ReLU in its epilogue (ops.TCNConvFn)."""
+        if os.environ.get("M3T_TCN_FUSED", "1") == "1":
+            if self.downsample is None:
+                res = x
+            else:
+                res = ops.Conv1dBiasAct.apply(x, self.downsample.weight, self.downsample.bias, 1, 0, 0, False)
+            h = ops.TCNConvFn.apply(x, self.conv1.weight_v, self.conv1.weight_g, self.conv1.bias, None, self.dilation,
+                                    self.padding, self.dropout1.p, self.training)
+            return ops.TCNConvFn.apply(h, self.conv2.weight_v, self.conv2.weight_g, self.conv2.bias, res,
+                                       self.dilation, self.padding, self.dropout2.p, self.training)
         h = x
         for conv, drop in ((self.conv1, self.dropout1), (self.conv2, self.dropout2)):
             h = ops.Conv1dBiasAct.apply(h, _wn_weight(conv), conv.bias, self.dilation, self.padding, 0, True)

@@ -616,6 +616,61 @@ class Conv1dBiasAct(torch.autograd.Function):
         return dx, dw, db, None, None, None, None
 
 
+class TCNConvFn(torch.autograd.Function):
+    """One weight-normed dilated causal Conv1d of a TemporalBlock together with everything that follows it inside the
+    block (models/tcn.py:19-33,43-46), ONE launch (m3t_tcn_conv_bf16):
+        t = dropout_p(relu(conv1d(x, g * v / ||v||, dilation) + b)) ;  y = t                   (residual is None)
+                                                                       y = relu(t + residual)  (second conv of the block)
+    Weight-norm is folded into the epilogue: the tensor-core operand is the bf16 pack of `weight_v`, the per-channel
+    factor g / ||v|| rides with the bias as the epilogue's scale.  The dropout mask is the counter-based generator of
+    m3t_dropout_bf16 over the element index of y (seed drawn from torch's CPU generator), applied in the epilogue.
+    Backward: ONE mask pass (m3t_tcn_epilogue_bwd_bf16: y > 0 selects the outer ReLU, t > 0 the inner ReLU AND the kept
+    elements, so no mask is stored or re-derived), bias column sums, wgrad, dgrad; the weight-norm chain rule
+    (dg = <dw, v> / ||v||, dv = (g / ||v||) (dw - <dw, v> v / ||v||^2)) runs on the parameter-sized tensors."""
+
+    @staticmethod
+    def forward(ctx, x, v, g, b, residual, dilation, pad_lo, drop_p, training):
+        Cout, Cin, k = v.shape
+        geom = _geom2d(x.shape, Cout, (k,), 1, (pad_lo,), (0,), dilation, nd=1)
+        norm = v.detach().flatten(1).norm(dim=1)
+        scale = (g.detach().flatten() / norm).contiguous()
+        wf, _ = packed_filter(v, True)
+        p = float(drop_p) if training else 0.0
+        if p > 0 and torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("TCNConvFn: the dropout seed is a host value; a captured step would replay one mask")
+        seed = int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).item()) if p > 0 else 0
+        y, t = raw.tcn_conv(x, wf, geom, scale, b.detach() if b is not None else None, residual=residual, drop_p=p,
+                            seed=seed, want_t=training)
+        ctx.save_for_backward(x, v, g, y, t, scale, norm)
+        ctx.cfg = (geom, dilation, pad_lo, p, b is not None, residual is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, v, g, y, t, scale, norm = ctx.saved_tensors
+        geom, dil, pad_lo, p, has_b, has_res = ctx.cfg
+        Cout, Cin, k = v.shape
+        dy = dy.contiguous()
+        if has_res:
+            dsum, da = raw.tcn_epilogue_bwd(dy, y, t, 1.0 / (1.0 - p))
+        else:
+            dsum, da = raw.tcn_epilogue_bwd(dy, None, y, 1.0 / (1.0 - p))
+        db = raw.colsum(da.view(-1, Cout)) if has_b else None
+        dw = raw.unpack_filter_grad(raw.conv_wgrad(x, da, geom), (Cout, Cin, k))      # gradient of the EFFECTIVE weight
+        # the operand was bf16(v) and the epilogue multiplied by scale = g / ||v||:  w_eff = scale * v
+        dot = (dw * v).flatten(1).sum(dim=1)                    # <dw, v> per output channel
+        dg = (dot / norm).view_as(g)
+        dv = scale.view(-1, 1, 1) * dw - (scale * dot / (norm * norm)).view(-1, 1, 1) * v
+        dx = None
+        if ctx.needs_input_grad[0]:
+            w_eff = (v.detach() * scale.view(-1, 1, 1)).contiguous()
+            _, wd = raw.pack_filter(w_eff, True)
+            span = dil * (k - 1)
+            g2 = _geom2d(da.shape, Cin, (k,), 1, (span - pad_lo,), (span,), dil, nd=1)
+            dx = raw.conv_fprop(da, wd, g2).view(x.shape)
+        return dx, dv, dg, db, dsum, None, None, None, None
+
+
 _unit_affine = {}
 
 

@@ -250,6 +250,35 @@ def conv_fprop(x, w_packed, g, scale=None, shift=None, residual=None, relu=False
     return y
 
 
+def tcn_conv(x, w_packed, g, scale, shift, residual=None, drop_p=0.0, seed=0, want_t=False):
+    """One TemporalBlock conv with its epilogue (m3t_tcn_conv_bf16): t = dropout(relu(conv * scale + shift));
+    y = relu(t + residual) (t also returned when want_t) or y = t.  x: CL bf16 [B,T,Cin]."""
+    _chk_bf16(x, w_packed, residual)
+    Z, P, Q = conv_out_dims(g)
+    N, Cout = x.shape[0], w_packed.shape[0]
+    y = torch.empty((N, Q, Cout), device=x.device, dtype=torch.bfloat16)
+    t = torch.empty_like(y) if (want_t and residual is not None) else None
+    flops = 2.0 * N * Q * Cout * w_packed.shape[1]
+
+    def run():
+        L.check(L.load().m3t_tcn_conv_bf16(L.ptr(x), L.ptr(w_packed), L.ptr(y), L.ptr(t), L.int_array(g), L.ptr(scale),
+                                           L.ptr(shift),
+                                           L.ptr(residual), L.f32(drop_p), ctypes.c_ulonglong(int(seed)),
+                                           L.stream_ptr()), "tcn_conv")
+    _timed(conv_key("tcn", g), flops, run)
+    return y, t
+
+
+def tcn_epilogue_bwd(dy, y, t, scale):
+    """(dsum, da) of tcn_conv's epilogue; y is None when no residual joined (then dsum is None and t is the output)."""
+    _chk_bf16(dy, y, t)
+    da = torch.empty_like(dy)
+    dsum = torch.empty_like(dy) if y is not None else None
+    L.check(_lib().m3t_tcn_epilogue_bwd_bf16(L.ptr(dy), L.ptr(y), L.ptr(t), L.ptr(dsum), L.ptr(da), L.f32(scale),
+                                             L.i64(dy.numel()), L.stream_ptr()), "tcn_epilogue_bwd")
+    return dsum, da
+
+
 def conv_fprop_scatter(x, w_packed, g, out_base, img_pitch, row_pitch, px_pitch, accumulate=False, algo_flops=None,
                        tag="dgrad-s2"):
     """conv_fprop (2-D, no epilogue arithmetic) storing output pixel (n,p,q) at out_base + (n*img_pitch + p*row_pitch +

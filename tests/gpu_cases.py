@@ -1738,6 +1738,52 @@ TOLS["graph_vs_noise"] = 5.0
 TOLS["graph_replay_launches"] = 0.5
 
 
+# ----------------------------------------------------------------------------------------------------------
+# Fused TemporalBlock (ops.TCNConvFn / m3t_tcn_conv_bf16) IN TRAINING MODE WITH DROPOUT against the oracle evaluated with
+# the same mask stream (oracle/dropout.py): forward, input gradient and every parameter gradient
+# ----------------------------------------------------------------------------------------------------------
+def case_tcn_block_dropout(cin=512, cout=512, dilation=2, p=0.2, B=6, T=40, seed=0):
+    from m3t_b200.models.tcn import TemporalBlock
+    from oracle import ref_torch as R
+    torch.manual_seed(seed)
+    blk = TemporalBlock(cin, cout, 3, stride=1, dilation=dilation, padding=2 * dilation, dropout=p)
+    spec = {k: tuple(v.shape) for k, v in blk.state_dict().items()}
+    sd = R.synth_state_dict(spec, 41)
+    blk.load_state_dict(sd)
+    blk = blk.cuda().train()
+    g = torch.Generator().manual_seed(seed + 1)
+    x = torch.randn((B, cin, T), generator=g)
+    cot = torch.randn((B, cout, T), generator=g)
+    torch.manual_seed(1234)            # the two dropout seeds are the next two draws of torch's CPU generator
+    xg = x.cuda().requires_grad_(True)
+    out = blk(xg)
+    (out * cot.cuda()).sum().backward()
+    torch.manual_seed(1234)
+    seeds = [int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).item()) for _ in range(2)]
+    sdo = {"b." + k: v.clone().requires_grad_(v.is_floating_point()) for k, v in sd.items()}
+    xo = x.clone().requires_grad_(True)
+    with R.bf16_emulation():
+        ref = R.temporal_block(xo, sdo, "b", dilation, dropout=(p, seeds[0], seeds[1]))
+        (ref * cot).sum().backward()
+    errs = {"out_emu": _err(out, ref), "dx": _l2(xg.grad, xo.grad)}
+    zeros_gpu = float((out.detach().float().cpu() == 0).float().mean())
+    zeros_ref = float((ref.detach() == 0).float().mean())
+    errs["zero_fraction_diff"] = abs(zeros_gpu - zeros_ref)
+    params = dict(blk.named_parameters())
+    for k in ("conv1.weight_v", "conv1.weight_g", "conv1.bias", "conv2.weight_v", "conv2.weight_g", "conv2.bias") + \
+            (("downsample.weight", "downsample.bias") if cin != cout else ()):
+        errs["d_" + k] = _l2(params[k].grad, sdo["b." + k].grad)
+    return errs
+
+
+CASES["tcn_block_dropout"] = (case_tcn_block_dropout, _c())
+CASES["tcn_block_dropout_downsample"] = (case_tcn_block_dropout, _c(cin=1024, cout=512, dilation=1, p=0.5, B=3, T=17))
+for _k in ("conv1.weight_v", "conv1.weight_g", "conv1.bias", "conv2.weight_v", "conv2.weight_g", "conv2.bias",
+           "downsample.weight", "downsample.bias"):
+    TOLS["d_" + _k] = 3e-2
+TOLS["zero_fraction_diff"] = 2e-3
+
+
 if __name__ == "__main__":
     name = sys.argv[1]
     errs = run_case(name)
