@@ -372,6 +372,30 @@ int m3t_att_mix_f32(const float* x_a, const float* x_v, const float* s_a, const 
 int m3t_gru_fwd_f32(const float* gi, const float* w_hh, const float* b_hh, float* out, int B, int T, int H,
                     void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * CBAM gates (cbam.cu) on channels-last bf16 feature maps x[F][S][C], S = H*W.  Replace the ATen mean / max / mul /
+ * expand_as chains of models/cbam.py:46-53 (ChannelGate), :62-66,82-87 (ChannelPool + SpatialGate) and its cuDNN
+ * Conv2d(2,1,5,padding=2) (:79).  The shared MLP on (F,C) and BatchNorm2d(1) on (F,1,H,W) stay on the host side.
+ *   pool_hw:       avg / max (first maximum) over S per (f,c);   _bwd: dx = davg/S + [s == arg] dmx
+ *   scale_c:       y = x * sc[f][c];                              _bwd: dx = dy * sc, dsc[f][c] = sum_s dy * x
+ *   pool_c:        comp[f][0][s] = max_c, comp[f][1][s] = mean_c; _bwd: dx = dcomp[1]/C + [c == carg] dcomp[0]
+ *   scale_s:       y = x * ss[f][s];                              _bwd: dx = dy * ss, dss[f][s] = sum_c dy * x
+ *   conv5:         out[f][y][x] = sum w[c][kh][kw] in[f][c][y+kh-2][x+kw-2] (fp32);  _bwd: din and dw[2][5][5] */
+int m3t_cbam_pool_hw(const void* x, float* avg, float* mx, int* arg, int F, int S, int C, void* stream);
+int m3t_cbam_pool_hw_bwd(const float* davg, const float* dmx, const int* arg, void* dx, int F, int S, int C,
+                         void* stream);
+int m3t_cbam_scale_c(const void* x, const float* sc, void* y, int F, int S, int C, void* stream);
+int m3t_cbam_scale_c_bwd(const void* dy, const void* x, const float* sc, void* dx, float* dsc, int F, int S, int C,
+                         void* stream);
+int m3t_cbam_pool_c(const void* x, float* comp, int* carg, int F, int S, int C, void* stream);
+int m3t_cbam_pool_c_bwd(const float* dcomp, const int* carg, void* dx, int F, int S, int C, void* stream);
+int m3t_cbam_scale_s(const void* x, const float* ss, void* y, long long rows, int C, void* stream);
+int m3t_cbam_scale_s_bwd(const void* dy, const void* x, const float* ss, void* dx, float* dss, long long rows, int C,
+                         void* stream);
+int m3t_cbam_conv5(const float* in, const float* w, float* out, int F, int H, int W, void* stream);
+int m3t_cbam_conv5_bwd(const float* dout, const float* in, const float* w, float* din, float* dw, int F, int H, int W,
+                       void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -9,7 +9,7 @@ import math
 import torch.nn as nn
 
 from .. import fp32, ops
-from .resnet import BasicBlock, ResNet
+from .resnet import BasicBlock, BasicBlockV2, ResNet, ResNetV2
 from .rnn import GRU
 
 
@@ -37,17 +37,18 @@ class VA_3DResNet(nn.Module):
         self.frameLen, self.nLayers, self.backend, self.nFCs = frameLen, nLayers, backend, nFCs
         assert resnet_depth in (18, 34) and resnet_ver in ('v1', 'v2'), \
             'unsupported ResNet configuration: {}, {}'.format(resnet_depth, resnet_ver)
-        if resnet_ver != 'v1':
-            raise NotImplementedError("pre-activation ResNetV2 is selected by no caller of the reference "
-                                      "(models/model.py:47, models/vox2_model.py:35 pass 'v1')")
         self.c3d = nn.Sequential(
             nn.Conv3d(3, 64, kernel_size=(5, 7, 7), stride=(1, 2, 2), padding=(2, 3, 3), bias=False),
             nn.BatchNorm3d(64),
             nn.ReLU(True),
             nn.MaxPool3d(kernel_size=(1, 3, 3), stride=(1, 2, 2), padding=(0, 1, 1)))
         blocks = [2, 2, 2, 2] if resnet_depth == 18 else [3, 4, 6, 3]
-        self.resnet = ResNet(BasicBlock, blocks, inputDim, zero_init_residual=True, agg_mode=frontend_agg_mode,
-                             fmap_out_size=3, use_cbam=use_cbam)
+        if resnet_ver == 'v2':      # reference :336-337 (the constructor's default; AffWild2VA passes 'v1')
+            self.resnet = ResNetV2(BasicBlockV2, blocks, inputDim, zero_init_residual=False,
+                                   agg_mode=frontend_agg_mode, fmap_out_size=3, use_cbam=use_cbam)
+        else:
+            self.resnet = ResNet(BasicBlock, blocks, inputDim, zero_init_residual=True, agg_mode=frontend_agg_mode,
+                                 fmap_out_size=3, use_cbam=use_cbam)
         if backend == 'gru':
             self.gru = GRU(inputDim, hiddenDim, nLayers, nClasses, nFCs)
         _init_like_reference(self)

@@ -18,7 +18,7 @@ from .. import fp32, ops, streams
 from .. import lightning as pl
 from .att_fusion import AttFusion
 from .backbone import VA_3DResNet
-from .rnn import GRU
+from .rnn import GRU, AttEncDec
 from .utils import concordance_cc2, mse
 
 LR_TEST_MAX_LR = 0.01
@@ -64,8 +64,10 @@ class AffWild2VA(_Base):
                 self.fusion = GRU(512, hp.num_hidden, 2, fc_outputs, hp.num_fc_layers)
             elif hp.fusion_type == 'concat':
                 self.fusion = GRU(512 * 2, hp.num_hidden, 2, fc_outputs, hp.num_fc_layers)
+            elif hp.fusion_type == 'att_dec':
+                self.fusion = AttEncDec()
             else:
-                raise NotImplementedError("fusion_type %r is outside the hot path" % hp.fusion_type)
+                raise ValueError("unknown fusion_type %r" % hp.fusion_type)
         self.history = {'lr': [], 'loss': []}
 
     # ------------------------------------------------------------------ forward
@@ -107,6 +109,12 @@ class AffWild2VA(_Base):
                 v = fp32.linear(v, self.proj_v.weight, self.proj_v.bias)
             else:
                 v = ops.linear(v, self.proj_v.weight, self.proj_v.bias)
+        if hp.fusion_type == 'att_dec':
+            # reference :119-125: teacher forcing when the batch carries 'valence' / 'arousal' tracks
+            f = torch.cat((ops.as_bf16(a), ops.as_bf16(v)), dim=-1)
+            if 'arousal' in batch:
+                return self.fusion(f, torch.stack((batch['valence'], batch['arousal']), dim=-1))
+            return self.fusion(f)
         if hp.fusion_type == 'concat':
             f = torch.cat((a, v), dim=-1)
         else:

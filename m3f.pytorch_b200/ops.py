@@ -232,6 +232,63 @@ class BasicBlockFn(torch.autograd.Function):
         return (dx, None, dw1, dg1, db1, None, None, dw2, dg2, db2, None, None, dwd, dgd, dbd, None, None)
 
 
+class BNActFn(torch.autograd.Function):
+    """out = [relu](BatchNorm(x)) on a channels-last bf16 tensor, as a stand-alone unit: the pre-activation of
+    BasicBlockV2 / ResNetV2's bn5 (models/resnet.py:163-165,214-215,248-249), DenseNet's norm layers.
+    train: batch statistics by one streaming pass (sum x, sum x^2 through m3t_bn_bwd_reduce with mean 0 / invstd 1),
+    m3t_bn_finalize (running statistics), one m3t_bn_act pass.  backward: m3t_bn_bwd_reduce + m3t_bn_bwd_apply, the
+    ReLU mask recomputed from x."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, running_mean, running_var, relu, training, momentum=BN_MOMENTUM):
+        C = x.shape[-1]
+        x = x.contiguous()
+        if not training:
+            ss = raw.bn_fold(gamma.detach(), beta.detach(), running_mean, running_var, None, BN_EPS)
+            return raw.bn_act(x, ss[0], ss[1], relu=relu)
+        zero, one = _unit(C, x.device)[1], _unit(C, x.device)[0]
+        stats, _ = raw.bn_bwd_reduce(x, None, x, zero, one, False, False)       # (sum x, sum x*x)
+        count = x.numel() // C
+        fin = raw.bn_finalize(stats, count, gamma.detach(), beta.detach(), BN_EPS, momentum, running_mean, running_var)
+        out = raw.bn_act(x, fin[2], fin[3], relu=relu)
+        ctx.save_for_backward(x, fin)
+        ctx.cfg = (relu, count)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, fin = ctx.saved_tensors
+        relu, count = ctx.cfg
+        dout = dout.contiguous()
+        sums, _ = raw.bn_bwd_reduce(dout, None, x, fin[0], fin[1], relu, False, scale=fin[2], shift=fin[3])
+        dx = raw.bn_bwd_apply(dout, None, x, fin[0], fin[1], fin[2], sums, count, relu, shift=fin[3])
+        return dx, sums[1], sums[0], None, None, None, None, None
+
+
+class ConvPlainFn(torch.autograd.Function):
+    """out = conv2d(x, w) (+ residual) without normalisation: conv2 and the bare 1x1 `downsample` of BasicBlockV2
+    (models/resnet.py:146-150,166-176), DenseNet's convolutions.  The residual add rides in the conv epilogue."""
+
+    @staticmethod
+    def forward(ctx, x, w, residual, stride, pad):
+        Cout = w.shape[0]
+        geom = _geom2d(x.shape, Cout, (w.shape[2], w.shape[3]), stride, (pad, pad), (pad, pad))
+        wf, _ = packed_filter(w, True)
+        out = raw.conv_fprop(x, wf, geom, residual=residual)
+        ctx.save_for_backward(x, w)
+        ctx.cfg = (geom, stride, pad, residual is not None)
+        return out.view(out.shape[0], out.shape[2], out.shape[3], out.shape[4])
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, w = ctx.saved_tensors
+        geom, stride, pad, has_res = ctx.cfg
+        dout = dout.contiguous()
+        dw = raw.unpack_filter_grad(raw.conv_wgrad(x, dout, geom), tuple(w.shape))
+        dx = conv2d_dgrad(dout, w, x.shape, stride, pad) if ctx.needs_input_grad[0] else None
+        return dx, dw, (dout if has_res else None), None, None
+
+
 _PARITY_TAPS = {}
 
 
@@ -634,13 +691,18 @@ class TCNConvFn(torch.autograd.Function):
         geom = _geom2d(x.shape, Cout, (k,), 1, (pad_lo,), (0,), dilation, nd=1)
         norm = v.detach().flatten(1).norm(dim=1)
         scale = (g.detach().flatten() / norm).contiguous()
-        wf, _ = packed_filter(v, True)
+        fold = os.environ.get("M3T_TCN_FOLD_WN", "1") == "1"
+        if fold:
+            wf, _ = packed_filter(v, True)
+        else:       # diagnostic: round the EFFECTIVE weight to bf16 (what the bf16-emulating oracle does)
+            wf, _ = raw.pack_filter((v.detach() * scale.view(-1, 1, 1)).contiguous(), False)
         p = float(drop_p) if training else 0.0
         if p > 0 and torch.cuda.is_current_stream_capturing():
             raise RuntimeError("TCNConvFn: the dropout seed is a host value; a captured step would replay one mask")
         seed = int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).item()) if p > 0 else 0
-        y, t = raw.tcn_conv(x, wf, geom, scale, b.detach() if b is not None else None, residual=residual, drop_p=p,
-                            seed=seed, want_t=training)
+        y, t = raw.tcn_conv(x, wf, geom, scale if fold else None, b.detach() if b is not None else None,
+                            residual=residual, drop_p=p, seed=seed, want_t=training)
+        ctx.seed = seed
         ctx.save_for_backward(x, v, g, y, t, scale, norm)
         ctx.cfg = (geom, dilation, pad_lo, p, b is not None, residual is not None)
         return y
@@ -679,6 +741,18 @@ def _unit(C, device):
     if key not in _unit_affine:
         _unit_affine[key] = (torch.ones(C, device=device), torch.zeros(C, device=device))
     return _unit_affine[key]
+
+
+class AddFn(torch.autograd.Function):
+    """a + b on bf16 tensors (BasicBlockV2's residual join when a CBAM sits between conv2 and the add)."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        return raw.add_bf16(a.contiguous(), b.contiguous())
+
+    @staticmethod
+    def backward(ctx, dout):
+        return dout, dout
 
 
 class AddReLU(torch.autograd.Function):

@@ -749,3 +749,104 @@ def patch3x3_c1(x):
     L.check(_lib().m3t_patch3x3_c1(L.ptr(x.contiguous()), L.ptr(out), L.i32(N), L.i32(H), L.i32(W), L.stream_ptr()),
             "patch3x3_c1")
     return out
+
+
+# ----------------------------------------------------------------------------------------------------------
+# CBAM gates (cbam.cu): x is channels-last bf16 (F,H,W,C)
+# ----------------------------------------------------------------------------------------------------------
+def _fsc(x):
+    F_, H, W, C = x.shape
+    return F_, H * W, C
+
+
+def cbam_pool_hw(x):
+    _chk_bf16(x)
+    F_, S, C = _fsc(x)
+    avg = torch.empty((F_, C), device=x.device, dtype=torch.float32)
+    mx = torch.empty_like(avg)
+    arg = torch.empty((F_, C), device=x.device, dtype=torch.int32)
+    L.check(_lib().m3t_cbam_pool_hw(L.ptr(x), L.ptr(avg), L.ptr(mx), L.ptr(arg), L.i32(F_), L.i32(S), L.i32(C),
+                                    L.stream_ptr()), "cbam_pool_hw")
+    return avg, mx, arg
+
+
+def cbam_pool_hw_bwd(davg, dmx, arg, shape):
+    F_, H, W, C = shape
+    dx = torch.empty(shape, device=davg.device, dtype=torch.bfloat16)
+    L.check(_lib().m3t_cbam_pool_hw_bwd(L.ptr(davg.float()), L.ptr(dmx.float()), L.ptr(arg), L.ptr(dx), L.i32(F_),
+                                        L.i32(H * W), L.i32(C), L.stream_ptr()), "cbam_pool_hw_bwd")
+    return dx
+
+
+def cbam_scale_c(x, sc):
+    _chk_bf16(x)
+    F_, S, C = _fsc(x)
+    assert sc.dtype == torch.float32 and sc.shape == (F_, C) and sc.is_contiguous()
+    y = torch.empty_like(x)
+    L.check(_lib().m3t_cbam_scale_c(L.ptr(x), L.ptr(sc), L.ptr(y), L.i32(F_), L.i32(S), L.i32(C), L.stream_ptr()),
+            "cbam_scale_c")
+    return y
+
+
+def cbam_scale_c_bwd(dy, x, sc):
+    F_, S, C = _fsc(x)
+    dx = torch.empty_like(x)
+    dsc = torch.empty_like(sc)
+    L.check(_lib().m3t_cbam_scale_c_bwd(L.ptr(dy), L.ptr(x), L.ptr(sc), L.ptr(dx), L.ptr(dsc), L.i32(F_), L.i32(S),
+                                        L.i32(C), L.stream_ptr()), "cbam_scale_c_bwd")
+    return dx, dsc
+
+
+def cbam_pool_c(x):
+    _chk_bf16(x)
+    F_, H, W, C = x.shape
+    comp = torch.empty((F_, 2, H, W), device=x.device, dtype=torch.float32)
+    carg = torch.empty((F_, H, W), device=x.device, dtype=torch.int32)
+    L.check(_lib().m3t_cbam_pool_c(L.ptr(x), L.ptr(comp), L.ptr(carg), L.i32(F_), L.i32(H * W), L.i32(C),
+                                   L.stream_ptr()), "cbam_pool_c")
+    return comp, carg
+
+
+def cbam_pool_c_bwd(dcomp, carg, shape):
+    F_, H, W, C = shape
+    dx = torch.empty(shape, device=dcomp.device, dtype=torch.bfloat16)
+    L.check(_lib().m3t_cbam_pool_c_bwd(L.ptr(dcomp.float()), L.ptr(carg), L.ptr(dx), L.i32(F_), L.i32(H * W), L.i32(C),
+                                       L.stream_ptr()), "cbam_pool_c_bwd")
+    return dx
+
+
+def cbam_scale_s(x, ss):
+    _chk_bf16(x)
+    F_, H, W, C = x.shape
+    assert ss.dtype == torch.float32 and ss.numel() == F_ * H * W and ss.is_contiguous()
+    y = torch.empty_like(x)
+    L.check(_lib().m3t_cbam_scale_s(L.ptr(x), L.ptr(ss), L.ptr(y), L.i64(F_ * H * W), L.i32(C), L.stream_ptr()),
+            "cbam_scale_s")
+    return y
+
+
+def cbam_scale_s_bwd(dy, x, ss):
+    F_, H, W, C = x.shape
+    dx = torch.empty_like(x)
+    dss = torch.empty_like(ss)
+    L.check(_lib().m3t_cbam_scale_s_bwd(L.ptr(dy), L.ptr(x), L.ptr(ss), L.ptr(dx), L.ptr(dss), L.i64(F_ * H * W),
+                                        L.i32(C), L.stream_ptr()), "cbam_scale_s_bwd")
+    return dx, dss
+
+
+def cbam_conv5(comp, w):
+    F_, two, H, W = comp.shape
+    assert two == 2 and comp.dtype == torch.float32 and comp.is_contiguous() and tuple(w.shape) == (1, 2, 5, 5)
+    out = torch.empty((F_, 1, H, W), device=comp.device, dtype=torch.float32)
+    L.check(_lib().m3t_cbam_conv5(L.ptr(comp), L.ptr(w.detach().contiguous()), L.ptr(out), L.i32(F_), L.i32(H),
+                                  L.i32(W), L.stream_ptr()), "cbam_conv5")
+    return out
+
+
+def cbam_conv5_bwd(dout, comp, w):
+    F_, _, H, W = comp.shape
+    din = torch.empty_like(comp)
+    dw = torch.empty((1, 2, 5, 5), device=comp.device, dtype=torch.float32)
+    L.check(_lib().m3t_cbam_conv5_bwd(L.ptr(dout.float()), L.ptr(comp), L.ptr(w.detach().contiguous()), L.ptr(din),
+                                      L.ptr(dw), L.i32(F_), L.i32(H), L.i32(W), L.stream_ptr()), "cbam_conv5_bwd")
+    return din, dw

@@ -195,6 +195,72 @@ def test_config3_sample_of_clips(name):
     assert rel_err(out, fx["out"][:2]) < TOL_OUT
 
 
+@pytest.mark.parametrize("mode", ["eval", "train"])
+def test_resnet_v2_trunk(mode):
+    """pre-activation ResNetV2 / BasicBlockV2 (models/resnet.py:127-251)."""
+    fx = load("resnetv2_trunk_" + mode)
+    sd = _sd(fx, mode == "train")
+    x = fx["inputs"]["x"].clone().requires_grad_(mode == "train")
+    with torch.set_grad_enabled(mode == "train"):
+        out = R.resnet_v2_trunk(x, {"resnet." + k: v for k, v in sd.items()}, train=mode == "train")
+    assert rel_err(out, fx["out"]) < TOL_OUT
+    if mode == "train":
+        (out * fx["cot"]).sum().backward()
+        worst = max(grad_err(sd[k.split(".", 1)[1]].grad if k.startswith("param.") else x.grad, packed)
+                    for k, packed in fx["grads"].items())
+        assert worst < 2e-2, worst          # fp32 noise floor through 17 train-mode BN layers
+
+
+def test_va3dresnet_v2_eval():
+    fx = load("va3dresnet_v2_eval")
+    sd = _sd(fx)
+    x = (fx["inputs"]["video_u8"].float() - 127.5) / 127.5
+    with torch.no_grad():
+        y = R.stem3d(x, sd, "c3d").transpose(1, 2).contiguous()
+        y = R.resnet_v2_trunk(y.view(-1, 64, y.size(3), y.size(4)), sd, "resnet").view(-1, 4, 512)
+        out = R.gru_module(y, sd, "gru")
+    assert rel_err(out, fx["out"]) < TOL_OUT
+
+
+@pytest.mark.parametrize("mode", ["eval", "train"])
+def test_att_enc_dec(mode):
+    """AttEncDec = BiGRU encoder + additive attention + step-wise GRU decoder (models/rnn.py:84-165)."""
+    fx = load("attencdec_" + mode)
+    sd = _sd(fx, mode == "train")
+    x = fx["inputs"]["x"].clone().requires_grad_(mode == "train")
+    with torch.set_grad_enabled(mode == "train"):
+        out = R.att_enc_dec(x, {"fusion." + k: v for k, v in sd.items()}, "fusion")
+    assert rel_err(out, fx["out"]) < TOL_OUT
+    if mode == "train":
+        (out * fx["cot"]).sum().backward()
+        worst = max(grad_err(sd[k.split(".", 1)[1]].grad if k.startswith("param.") else x.grad, packed)
+                    for k, packed in fx["grads"].items())
+        assert worst < TOL_GRAD, worst
+
+
+@pytest.mark.parametrize("mode", ["eval", "train"])
+def test_cbam(mode):
+    """CBAM = ChannelGate + SpatialGate (models/cbam.py:32-112), output and all gradients."""
+    fx = load("cbam_" + mode)
+    sd = _sd(fx, True)
+    x = fx["inputs"]["x"].clone().requires_grad_(True)
+    out = R.cbam(x, sd, "", train=mode == "train")
+    assert rel_err(out, fx["out"]) < TOL_OUT
+    _check_grads(fx, sd, out, {"x": x})
+
+
+def test_resnet_with_cbam_train():
+    fx = load("resnet_cbam_train")
+    sd = _sd(fx, True)
+    x = fx["inputs"]["x"].clone().requires_grad_(True)
+    out = R.resnet_trunk(x, {"resnet." + k: v for k, v in sd.items()}, layers=(1, 1, 1, 1), train=True)
+    assert rel_err(out, fx["out"]) < TOL_OUT
+    (out * fx["cot"]).sum().backward()
+    worst = max(grad_err(sd[k.split(".", 1)[1]].grad if k.startswith("param.") else x.grad, packed)
+                for k, packed in fx["grads"].items())
+    assert worst < 2e-2, worst
+
+
 def test_ccc():
     fx = load("ccc")
     out = torch.stack([R.concordance_cc2(fx["inputs"]["r1"][i], fx["inputs"]["r2"][i]) for i in range(3)])
