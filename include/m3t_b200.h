@@ -396,6 +396,11 @@ int m3t_cbam_conv5(const float* in, const float* w, float* out, int F, int H, in
 int m3t_cbam_conv5_bwd(const float* dout, const float* in, const float* w, float* din, float* dw, int F, int H, int W,
                        void* stream);
 
+/* AvgPool3d((1,2,2), stride (1,2,2)) of the DenseNet transitions (models/densenet.py:38) on channels-last bf16
+ * [F][H][W][C] -> [F][H/2][W/2][C] (floor), and its backward (dx = dy/4 inside the windows, 0 on an odd last row / column). */
+int m3t_avgpool2x2(const void* x, void* y, int F, int H, int W, int C, void* stream);
+int m3t_avgpool2x2_bwd(const void* dy, void* dx, int F, int H, int W, int C, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

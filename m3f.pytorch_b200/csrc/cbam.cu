@@ -306,6 +306,61 @@ __global__ void cbam_conv5_bwd_w_kernel(const float* __restrict__ dout, const fl
   }
 }
 
+// ---- AvgPool3d((1,2,2), stride (1,2,2)) on CL [F][H][W][C] -> [F][H/2][W/2][C] (floor; DenseNet transitions) -----------
+__global__ void avgpool2x2_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int F, int H,
+                                  int W, int C) {
+  const int cgs = C / 8, P = H / 2, Q = W / 2;
+  const long long total = (long long)F * P * Q * cgs;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % cgs);
+    long long r = i / cgs;
+    const int q = (int)(r % Q);
+    r /= Q;
+    const int p = (int)(r % P);
+    const long long f = r / P;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+    for (int dh = 0; dh < 2; ++dh)
+#pragma unroll
+      for (int dw = 0; dw < 2; ++dw) {
+        float v[8];
+        cb_unpack8(__ldg(reinterpret_cast<const uint4*>(x + ((f * H + 2 * p + dh) * W + 2 * q + dw) * C) + cg), v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += v[j];
+      }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] *= 0.25f;
+    reinterpret_cast<uint4*>(y)[i] = cb_pack8(acc);
+  }
+}
+
+__global__ void avgpool2x2_bwd_kernel(const __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__ dx, int F,
+                                      int H, int W, int C) {
+  const int cgs = C / 8, P = H / 2, Q = W / 2;
+  const long long total = (long long)F * H * W * cgs;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % cgs);
+    long long r = i / cgs;
+    const int w = (int)(r % W);
+    r /= W;
+    const int h = (int)(r % H);
+    const long long f = r / H;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = 0.f;
+    if (h / 2 < P && w / 2 < Q) {       // an odd last row / column is outside every window
+      cb_unpack8(__ldg(reinterpret_cast<const uint4*>(dy + ((f * P + h / 2) * Q + w / 2) * C) + cg), v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] *= 0.25f;
+    }
+    reinterpret_cast<uint4*>(dx)[i] = cb_pack8(v);
+  }
+}
+
 static inline int cb_blocks(long long items, int threads = 256) {
   long long b = (items + threads - 1) / threads;
   if (b > 148LL * 16) b = 148LL * 16;
@@ -382,6 +437,21 @@ extern "C" int m3t_cbam_conv5_bwd(const float* dout, const float* in, const floa
   cbam_conv5_bwd_data_kernel<<<cb_blocks((long long)F * 2 * H * W), 256, 0, CB_ST(stream)>>>(dout, w, din, F, H, W);
   count_launch();
   cbam_conv5_bwd_w_kernel<<<50, 1024, 0, CB_ST(stream)>>>(dout, in, dw, F, H, W);
+  count_launch();
+  return launch_status();
+}
+
+extern "C" int m3t_avgpool2x2(const void* x, void* y, int F, int H, int W, int C, void* stream) {
+  if (C % 8 || H < 2 || W < 2) return -1;
+  avgpool2x2_kernel<<<cb_blocks((long long)F * (H / 2) * (W / 2) * (C / 8)), 256, 0, CB_ST(stream)>>>(CB_CBF(x), CB_BF(y),
+                                                                                                     F, H, W, C);
+  count_launch();
+  return launch_status();
+}
+extern "C" int m3t_avgpool2x2_bwd(const void* dy, void* dx, int F, int H, int W, int C, void* stream) {
+  if (C % 8 || H < 2 || W < 2) return -1;
+  avgpool2x2_bwd_kernel<<<cb_blocks((long long)F * H * W * (C / 8)), 256, 0, CB_ST(stream)>>>(CB_CBF(dy), CB_BF(dx), F, H,
+                                                                                            W, C);
   count_launch();
   return launch_status();
 }

@@ -82,3 +82,72 @@ class VA_3DResNet(nn.Module):
     def forward(self, x, *unused):
         # `*unused` tolerates AffWild2VA.forward's 3-argument call (reference models/model.py:111,130)
         return ops.as_f32(self.forward_bf16(x))
+
+
+class VA_VGGFace(nn.Module):
+    """Per-frame VGG-Face descriptor + BiGRU head (reference models/backbone.py:16-58; `--backbone vggface`)."""
+
+    def __init__(self, inputDim=4096, hiddenDim=512, nLayers=2, nClasses=2, frameLen=16, backend='gru', nFCs=1):
+        super().__init__()
+        from .vggface import VGGFace
+        self.inputDim, self.hiddenDim, self.nClasses = inputDim, hiddenDim, nClasses
+        self.frameLen, self.nLayers, self.backend, self.nFCs = frameLen, nLayers, backend, nFCs
+        self.vgg = VGGFace()
+        if backend == 'gru':
+            self.gru = GRU(inputDim, hiddenDim, nLayers, nClasses, nFCs)
+        for m in self.modules():            # reference :45-58
+            if isinstance(m, nn.Conv2d):
+                nn.init.xavier_normal_(m.weight.data)
+                if m.bias is not None:
+                    nn.init.normal_(m.bias.data)
+            elif isinstance(m, nn.Linear):
+                nn.init.xavier_normal_(m.weight)
+                nn.init.constant_(m.bias, 0)
+
+    def forward_bf16(self, x, *unused, normalise=False, after_features=None):
+        B, T = x.shape[0], x.shape[2]
+        if normalise:
+            x = (x.float() - 127.5) / 127.5
+        frames = x.transpose(1, 2).contiguous().view(-1, x.shape[1], x.shape[3], x.shape[4])
+        f = self.vgg.forward_bf16(frames).view(B, T, -1)
+        if after_features is not None:
+            after_features()
+        return self.gru.forward_bf16(f) if self.backend == 'gru' else f
+
+    def forward(self, x, *unused):
+        return ops.as_f32(self.forward_bf16(x))
+
+
+class VA_3DDenseNet(nn.Module):
+    """Conv3d stem + 3-D DenseNet-52 + BiGRU head (reference models/backbone.py:375-420; `--backbone densenet`)."""
+
+    def __init__(self, inputDim=392, hiddenDim=512, nLayers=2, nClasses=2, frameLen=16, backend='gru',
+                 frontend_agg_mode='ap', nFCs=1):
+        super().__init__()
+        from .densenet import DenseNet52_3D
+        self.inputDim, self.hiddenDim, self.nClasses = inputDim, hiddenDim, nClasses
+        self.frameLen, self.nLayers, self.backend, self.nFCs = frameLen, nLayers, backend, nFCs
+        self.c3d = nn.Sequential(
+            nn.Conv3d(3, 64, kernel_size=(5, 7, 7), stride=(1, 2, 2), padding=(2, 3, 3), bias=False),
+            nn.BatchNorm3d(64),
+            nn.ReLU(True),
+            nn.MaxPool3d(kernel_size=(1, 3, 3), stride=(1, 2, 2), padding=(0, 1, 1)))
+        self.densenet = DenseNet52_3D(inputDim, agg_mode=frontend_agg_mode, fmap_out_size=3)
+        if backend == 'gru':
+            self.gru = GRU(inputDim, hiddenDim, nLayers, nClasses, nFCs)
+        _init_like_reference(self)
+
+    def forward_bf16(self, x, *unused, normalise=False, after_features=None):
+        conv, bn = self.c3d[0], self.c3d[1]
+        B, T = x.shape[0], x.shape[2]
+        h = ops.Stem3D.apply(x, conv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var, normalise,
+                             bn.training)
+        if bn.training:
+            ops.bump_num_batches_tracked(bn)
+        f = self.densenet.forward_cl(h.view(B, T, h.shape[1], h.shape[2], h.shape[3]))
+        if after_features is not None:
+            after_features()
+        return self.gru.forward_bf16(f) if self.backend == 'gru' else f
+
+    def forward(self, x, *unused):
+        return ops.as_f32(self.forward_bf16(x))

@@ -53,8 +53,16 @@ class AffWild2VA(_Base):
                     self.visual = VA_3DVGGM_Split(hiddenDim=hp.num_hidden, frameLen=hp.window, backend=hp.backend,
                                                   split_layer=hp.split_layer, nClasses=rnn_fc_classes,
                                                   nFCs=hp.num_fc_layers, use_mtl=use_mtl)
+            elif hp.backbone == 'vggface':
+                from .backbone import VA_VGGFace
+                self.visual = VA_VGGFace(hiddenDim=hp.num_hidden, frameLen=hp.window, backend=hp.backend,
+                                         nClasses=rnn_fc_classes, nFCs=hp.num_fc_layers)
+            elif hp.backbone == 'densenet':
+                from .backbone import VA_3DDenseNet
+                self.visual = VA_3DDenseNet(hiddenDim=hp.num_hidden, frameLen=hp.window, backend=hp.backend,
+                                            nClasses=rnn_fc_classes, nFCs=hp.num_fc_layers)
             else:
-                raise NotImplementedError("backbone %r is outside the hot path (SURVEY.md section 2)" % hp.backbone)
+                raise ValueError("unknown backbone %r" % hp.backbone)
         if 'audio' in hp.modality:
             self.audio = GRU(200, 256, 2, rnn_fc_classes, hp.num_fc_layers)
         if hp.modality == 'audiovisual':
@@ -73,6 +81,8 @@ class AffWild2VA(_Base):
     # ------------------------------------------------------------------ forward
     def _visual(self, batch, after_features=None):
         hp = self.hparams
+        if hp.backbone in ('vggface', 'densenet'):
+            return self.visual.forward_bf16(batch['video'], normalise=True, after_features=after_features)
         if hp.backbone == 'resnet':
             # normalisation (video - 127.5) / 127.5 (reference :106) is folded into the stem's input pass
             if 'video_u8' in batch:

@@ -67,6 +67,19 @@ class ToCL(torch.autograd.Function):
         return raw.nsc_to_ncs_f32(g.contiguous(), ctx.C)
 
 
+class ToCLPad(torch.autograd.Function):
+    """fp32 [N,C,*S] -> bf16 [N,*S,cpad] with zero channels C..cpad-1 (an image entering a 64-channel conv block)."""
+
+    @staticmethod
+    def forward(ctx, x, cpad):
+        ctx.C = x.shape[1]
+        return raw.ncs_to_nsc_bf16(x.contiguous(), cpad)
+
+    @staticmethod
+    def backward(ctx, g):
+        return raw.nsc_to_ncs_f32(g.contiguous(), ctx.C), None
+
+
 class FromCL(torch.autograd.Function):
     """bf16 [N,*S,C] -> fp32 [N,C,*S]."""
 
@@ -287,6 +300,52 @@ class ConvPlainFn(torch.autograd.Function):
         dw = raw.unpack_filter_grad(raw.conv_wgrad(x, dout, geom), tuple(w.shape))
         dx = conv2d_dgrad(dout, w, x.shape, stride, pad) if ctx.needs_input_grad[0] else None
         return dx, dw, (dout if has_res else None), None, None
+
+
+class Conv3dPlainFn(torch.autograd.Function):
+    """out = conv3d(x, w, padding=pad) without normalisation on CL bf16 (N,D,H,W,Cin), stride 1: the 3x3x3 growth
+    convolution of a DenseNet layer (models/densenet.py:13-15).  Cin and Cout must be multiples of 64 (the caller
+    zero-pads a narrower filter bank)."""
+
+    @staticmethod
+    def forward(ctx, x, w, pad):
+        N, D, H, W, Cin = x.shape
+        Cout = w.shape[0]
+        k = tuple(w.shape[2:])
+        geom = raw.conv_geom(3, N, D, H, W, Cin, Cout, k, (1, 1, 1), (pad,) * 3, (pad,) * 3, (1, 1, 1))
+        wf, wd = raw.pack_filter(w.detach().contiguous(), True)
+        out = raw.conv_fprop(x, wf, geom)
+        ctx.save_for_backward(x, w, wd)
+        ctx.cfg = (geom, pad, k)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, w, wd = ctx.saved_tensors
+        geom, pad, k = ctx.cfg
+        dout = dout.contiguous()
+        dw = raw.unpack_filter_grad(raw.conv_wgrad(x, dout, geom), tuple(w.shape))
+        dx = None
+        if ctx.needs_input_grad[0]:
+            N, D, H, W, Cin = x.shape
+            lo = tuple(k[i] - 1 - pad for i in range(3))
+            g2 = raw.conv_geom(3, N, dout.shape[1], dout.shape[2], dout.shape[3], w.shape[0], Cin, k, (1, 1, 1), lo, lo,
+                               (1, 1, 1))
+            dx = raw.conv_fprop(dout, wd, g2, tag="dgrad").view(x.shape)
+        return dx, dw, None
+
+
+class AvgPool2x2Fn(torch.autograd.Function):
+    """AvgPool3d((1,2,2), stride (1,2,2)) on CL bf16 (F,H,W,C) (models/densenet.py:38)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        ctx.shape = tuple(x.shape)
+        return raw.avgpool2x2(x.contiguous())
+
+    @staticmethod
+    def backward(ctx, dy):
+        return raw.avgpool2x2_bwd(dy.contiguous(), ctx.shape)
 
 
 _PARITY_TAPS = {}
@@ -731,6 +790,83 @@ class TCNConvFn(torch.autograd.Function):
             g2 = _geom2d(da.shape, Cin, (k,), 1, (span - pad_lo,), (span,), dil, nd=1)
             dx = raw.conv_fprop(da, wd, g2).view(x.shape)
         return dx, dv, dg, db, dsum, None, None, None, None
+
+
+class Conv2dBiasAct(torch.autograd.Function):
+    """y = act(conv2d(x, w, padding) + b) on CL bf16 (F,H,W,Cin) -> (F,H,W,Cout), stride 1: the conv + ReLU units of
+    VGGFace (reference models/vggface.py:41-50).  Bias and ReLU ride in the conv epilogue; backward = one mask pass,
+    bias column sums, wgrad, dgrad.  w may have fewer input channels than x (x zero-padded to a multiple of 64)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, pad, relu):
+        Cout, Cin_w, kh, kw = w.shape
+        Cin = x.shape[-1]
+        if Cin_w != Cin:        # zero filter planes for the padding channels of x
+            wp = torch.zeros((Cout, Cin, kh, kw), device=w.device, dtype=w.dtype)
+            wp[:, :Cin_w] = w.detach()
+        else:
+            wp = w.detach()
+        geom = _geom2d(x.shape, Cout, (kh, kw), 1, (pad, pad), (pad, pad))
+        wf, wd = raw.pack_filter(wp.contiguous(), True)
+        y = raw.conv_fprop(x, wf, geom, shift=b.detach() if b is not None else None, relu=relu)
+        y = y.view(y.shape[0], y.shape[2], y.shape[3], y.shape[4])
+        ctx.save_for_backward(x, w, y if relu else None, wd)
+        ctx.cfg = (geom, pad, relu, b is not None, Cin_w)
+        return y
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, w, y, wd = ctx.saved_tensors
+        geom, pad, relu, has_b, Cin_w = ctx.cfg
+        Cout, _, kh, kw = w.shape
+        Cin = x.shape[-1]
+        dz = dout.contiguous()
+        if relu:
+            dz = raw.relu_bwd(dz, y)
+        db = raw.colsum(dz.view(-1, Cout)) if has_b else None
+        dw = raw.unpack_filter_grad(raw.conv_wgrad(x, dz, geom), (Cout, Cin, kh, kw))
+        if Cin_w != Cin:
+            dw = dw[:, :Cin_w].contiguous()
+        dx = None
+        if ctx.needs_input_grad[0]:
+            g2 = _geom2d(dz.shape, Cin, (kh, kw), 1, (kh - 1 - pad, kw - 1 - pad), (kh - 1 - pad, kw - 1 - pad))
+            dx = raw.conv_fprop(dz, wd, g2, tag="dgrad")
+            dx = dx.view(x.shape)
+        return dx, dw, db, None, None
+
+
+class MaxPool2x2Ceil(torch.autograd.Function):
+    """F.max_pool2d(x, 2, 2, 0, ceil_mode=True) on a NON-NEGATIVE CL bf16 map (it follows a ReLU in VGGFace,
+    models/vggface.py:50): an odd extent is zero-padded by one row / column at the high end, which cannot change a
+    maximum of non-negative values, then the 2x2/s2 pooling kernel runs (m3t_bn_relu_maxpool with unit scale)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        F_, H, W, C = x.shape
+        ph, pw = H % 2, W % 2
+        if ph or pw:
+            x = torch.nn.functional.pad(x, (0, 0, 0, pw, 0, ph))
+        one, zero = _unit(C, x.device)
+        out, idx = raw.bn_relu_maxpool(x.contiguous(), one, zero, True, (2, 2, 0))
+        ctx.save_for_backward(x, idx)
+        ctx.crop = (H, W)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, idx = ctx.saved_tensors
+        F_, Hp, Wp, C = x.shape
+        one, zero = _unit(C, x.device)
+        sums = raw.zeros_f32((2, C), x.device)
+        fn = raw._lib().m3t_maxpool_bn_bwd
+        dx = torch.empty_like(x)
+        # mode 1 with zero statistics sums and unit scale: dx = route(dout) * relu'(x); x > 0 where a maximum was taken
+        raw.L.check(fn(raw.L.i32(1), raw.L.ptr(dout.contiguous()), raw.L.ptr(idx), raw.L.ptr(x), raw.L.ptr(zero),
+                       raw.L.ptr(one), raw.L.ptr(one), raw.L.ptr(zero), raw.L.ptr(sums), raw.ctypes_double(1.0),
+                       raw.L.ptr(dx), raw.L.i32(F_), raw.L.i32(Hp), raw.L.i32(Wp), raw.L.i32(C), raw.L.i32(2),
+                       raw.L.i32(2), raw.L.i32(0), raw.L.stream_ptr()), "maxpool_bwd")
+        H, W = ctx.crop
+        return dx[:, :H, :W].contiguous() if (H, W) != (Hp, Wp) else dx
 
 
 _unit_affine = {}

@@ -850,3 +850,21 @@ def cbam_conv5_bwd(dout, comp, w):
     L.check(_lib().m3t_cbam_conv5_bwd(L.ptr(dout.float()), L.ptr(comp), L.ptr(w.detach().contiguous()), L.ptr(din),
                                       L.ptr(dw), L.i32(F_), L.i32(H), L.i32(W), L.stream_ptr()), "cbam_conv5_bwd")
     return din, dw
+
+
+def avgpool2x2(x):
+    """CL bf16 (F,H,W,C) -> (F,H//2,W//2,C): mean over 2x2 windows (floor)."""
+    _chk_bf16(x)
+    F_, H, W, C = x.shape
+    y = torch.empty((F_, H // 2, W // 2, C), device=x.device, dtype=torch.bfloat16)
+    L.check(_lib().m3t_avgpool2x2(L.ptr(x), L.ptr(y), L.i32(F_), L.i32(H), L.i32(W), L.i32(C), L.stream_ptr()),
+            "avgpool2x2")
+    return y
+
+
+def avgpool2x2_bwd(dy, shape):
+    F_, H, W, C = shape
+    dx = torch.empty(shape, device=dy.device, dtype=torch.bfloat16)
+    L.check(_lib().m3t_avgpool2x2_bwd(L.ptr(dy), L.ptr(dx), L.i32(F_), L.i32(H), L.i32(W), L.i32(C), L.stream_ptr()),
+            "avgpool2x2_bwd")
+    return dx

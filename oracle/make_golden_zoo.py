@@ -6,6 +6,8 @@ from the UNMODIFIED reference modules.  Run on the build box only:   python -m o
   attencdec_{eval,train}        AttEncDec (Attention + Decoder, fusion_type 'att_dec')       models/rnn.py:84-165
   cbam_{eval,train}             CBAM(128) (ChannelGate + SpatialGate)                        models/cbam.py:1-112
   resnet_cbam_train             ResNet(BasicBlock, [1,1,1,1], use_cbam=True)                  models/resnet.py:32-35,48-49
+  vggface_{eval,train}          VGGFace (13 conv + ReLU, ceil-mode pooling, fc1)             models/vggface.py:7-50
+  densenet_{eval,train}         DenseNet52_3D(392, agg_mode='ap') on (2,64,4,28,28)          models/densenet.py:5-93
 """
 import os
 import sys
@@ -92,8 +94,40 @@ def gen_cbam():
                                    cot=cot, grads=grads))
 
 
+def gen_vggface():
+    vgg = _refload.load("vggface")
+    for mode in ("eval", "train"):
+        m = vgg.VGGFace()
+        spec = load_synth(m, 65)
+        m.train(mode == "train")
+        m.dropout.p = 0.0                      # Philox masks cannot be matched; the dropout kernel has its own case
+        v = video(2, 1, 66)[:, :, 0]           # (2,3,112,112) uint8
+        x = (v.float() - 127.5) / 127.5
+        fx = dict(kind="VGGFace", mode=mode, seed=65, spec=spec, inputs={"image_u8": v}, dropout_p=0.0)
+        if mode == "eval":
+            with torch.no_grad():
+                fx["out"] = m(x)
+        else:
+            out, cot, grads = run_with_grads(m, lambda: m(x), {}, 67)
+            fx.update(out=out, cot=cot, grads=grads)
+        save("vggface_" + mode, fx)
+
+
+def gen_densenet():
+    dn = _refload.load("densenet")
+    for mode in ("eval", "train"):
+        m = dn.DenseNet52_3D(392, agg_mode="ap", fmap_out_size=3)
+        spec = load_synth(m, 68)
+        m.train(mode == "train")
+        gen = {"x": dict(kind="randn_relu", shape=(2, 64, 4, 28, 28), seed=69)}
+        x = materialise(gen)["x"].requires_grad_(True)
+        out, cot, grads = run_with_grads(m, lambda: m(x), {"x": x}, 70)
+        save("densenet_" + mode, dict(kind="DenseNet52_3D", mode=mode, seed=68, spec=spec, inputs_gen=gen, out=out,
+                                      cot=cot, grads=grads))
+
+
 GENERATORS = {"resnetv2": gen_resnetv2, "va3dresnet_v2": gen_va3dresnet_v2, "attencdec": gen_attencdec,
-              "cbam": gen_cbam}
+              "cbam": gen_cbam, "vggface": gen_vggface, "densenet": gen_densenet}
 
 
 def main(argv):

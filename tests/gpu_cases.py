@@ -385,6 +385,12 @@ def _build(fx):
     elif kind == "CBAM":
         from m3t_b200.models.cbam import CBAM
         m = CBAM(**fx["ctor"])
+    elif kind == "VGGFace":
+        from m3t_b200.models.vggface import VGGFace
+        m = VGGFace()
+    elif kind == "DenseNet52_3D":
+        from m3t_b200.models.densenet import DenseNet52_3D
+        m = DenseNet52_3D(392, agg_mode="ap", fmap_out_size=3)
     elif kind == "ResNetCBAM":
         from m3t_b200.models.resnet import BasicBlock, ResNet
         m = ResNet(BasicBlock, [1, 1, 1, 1], 512, zero_init_residual=True, agg_mode="ap", fmap_out_size=3, use_cbam=True)
@@ -457,6 +463,12 @@ def _oracle_run(fx, emulate, want_grads):
             x = inp["x"].clone().requires_grad_(want_grads)
             leaves["x"] = x
             out = R.cbam(R.q(x), sd, "", train=train)
+        elif kind == "VGGFace":
+            out = R.vggface((inp["image_u8"].float() - 127.5) / 127.5, sd)
+        elif kind == "DenseNet52_3D":
+            x = inp["x"].clone().requires_grad_(want_grads)
+            leaves["x"] = x
+            out = R.densenet52_3d(R.q(x), {"densenet." + k: v for k, v in sd.items()}, train=train)
         elif kind == "ResNetCBAM":
             x = inp["x"].clone().requires_grad_(want_grads)
             leaves["x"] = x
@@ -509,7 +521,7 @@ def case_golden(name, grads=True):
     leaves = {}
     loss = None
     with torch.set_grad_enabled(want_grads):
-        if kind in ("GRU", "TemporalConvNet", "ResNet", "ResNetV2", "AttEncDec", "CBAM", "ResNetCBAM"):
+        if kind in ("GRU", "TemporalConvNet", "ResNet", "ResNetV2", "AttEncDec", "CBAM", "ResNetCBAM", "DenseNet52_3D"):
             x = inp["x"].cuda().requires_grad_(want_grads)
             leaves["x"] = x
             out = m(x)
@@ -520,6 +532,8 @@ def case_golden(name, grads=True):
             out = m(xa, xv)
         elif kind in ("VA_3DResNet", "VA_3DVGGM"):
             out = m((inp["video_u8"].float().cuda() - 127.5) / 127.5)
+        elif kind == "VGGFace":
+            out = m((inp["image_u8"].float().cuda() - 127.5) / 127.5)
         elif kind == "VA_3DVGGM_Split":
             se = inp["se_features"].cuda()
             out = m((inp["video_u8"].float().cuda() - 127.5) / 127.5, se, se)
@@ -658,6 +672,10 @@ CASES["golden_resnetv2_trunk_train"] = (case_golden, _c(name="resnetv2_trunk_tra
 CASES["golden_va3dresnet_v2_eval"] = (case_golden, _c(name="va3dresnet_v2_eval"))
 CASES["golden_attencdec_eval"] = (case_golden, _c(name="attencdec_eval", grads=False))
 CASES["golden_attencdec_train"] = (case_golden, _c(name="attencdec_train"))
+CASES["golden_vggface_eval"] = (case_golden, _c(name="vggface_eval"))
+CASES["golden_vggface_train"] = (case_golden, _c(name="vggface_train"))
+CASES["golden_densenet_eval"] = (case_golden, _c(name="densenet_eval", grads=False))
+CASES["golden_densenet_train"] = (case_golden, _c(name="densenet_train"))
 CASES["golden_cbam_eval"] = (case_golden, _c(name="cbam_eval"))
 CASES["golden_cbam_train"] = (case_golden, _c(name="cbam_train"))
 CASES["golden_resnet_cbam_train"] = (case_golden, _c(name="resnet_cbam_train"))
@@ -680,7 +698,8 @@ for _k in ("conv1.weight", "conv2.weight", "bn1.weight", "bn1.bias", "bn2.weight
 # on vggm_tcn_train / av_v2psplit_attention_train (128 frames) the emulated oracle is 18 % / 14 % (all-parameter L2)
 # from the fp32 oracle, the CUDA path 8.7 % / 7.4 % from the emulated oracle (measured).
 CHAOTIC_GRADS = {"golden_resnet_trunk_train", "golden_va3dresnet_train", "golden_av_resnet_attention_train",
-                 "golden_resnetv2_trunk_train",
+                 "golden_resnetv2_trunk_train", "golden_densenet_train", "golden_resnet_cbam_train",
+                 "golden_vggface_train",
                  "golden_vggm_tcn_train", "golden_av_v2psplit_attention_train",
                  "va3dresnet_96px_train", "va3dresnet_15frames_train", "va3dresnet_1clip_2frames_train"}
 
@@ -1807,7 +1826,9 @@ def case_tcn_block_dropout(cin=512, cout=512, dilation=2, p=0.2, B=6, T=40, seed
         raw.tcn_conv = orig
     (out * cot.cuda()).sum().backward()
     seeds = used[-2:]
-    sdo = {"b." + k: v.clone().requires_grad_(v.is_floating_point()) for k, v in sd.items()}
+    # the oracle reads the values the module really holds (`net.{0,4}.*` alias `conv{1,2}.*` inside one parameter)
+    sdo = {"b." + k: v.detach().float().cpu().clone().requires_grad_(v.is_floating_point())
+           for k, v in blk.state_dict().items()}
     xo = x.clone().requires_grad_(True)
     with R.bf16_emulation():
         ref = R.temporal_block(xo, sdo, "b", dilation, dropout=(p, seeds[0], seeds[1]))

