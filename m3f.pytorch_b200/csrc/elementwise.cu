@@ -1276,7 +1276,9 @@ extern "C" int m3t_bn_act(const void* y, const float* scale, const float* shift,
 extern "C" int m3t_bn_bwd_reduce(const void* dout, const void* out, const void* y, const float* mean,
                                  const float* invstd, const float* scale, const float* shift, int relu, void* dz_out,
                                  float* sums, long long rows, int C, void* stream) {
-  if (C % 8 || (kEwThreads % (C / 8)) != 0) return -1;
+  // any C % 8 == 0 up to 8 * kEwThreads: when C/8 does not divide the block, the last kEwThreads % (C/8) threads idle
+  // (DenseNet's 96 / 160 / 200 ... channel tensors); the trunk's power-of-two widths use every thread
+  if (C % 8 || C / 8 > kEwThreads) return -1;
   const int cgs = C / 8;
   const int rows_per_iter = kEwThreads / cgs;
   long long blocks = (rows + rows_per_iter - 1) / rows_per_iter;

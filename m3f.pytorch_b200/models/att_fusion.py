@@ -29,7 +29,7 @@ class AttFusion(nn.Module):
         else:
             s_v = self.scorer_v.forward_bf16(x_v)     # (B,T,1) fp32 logits
             s_a = self.scorer_a.forward_bf16(x_a)
-        return ops.AttMixFn.apply(x_a, x_v, s_a, s_v)
+        return ops.att_mix(x_a, x_v, s_a, s_v)
 
     def forward(self, x_a, x_v):
         return ops.as_f32(self.forward_bf16(x_a, x_v))

@@ -601,8 +601,24 @@ class LinearFn(torch.autograd.Function):
         return dx, dw, db, None, None
 
 
+def torch_ops_enabled():
+    """M3T_TORCH_OPS=1: Linear and the attention mix go through the dispatcher (torch.ops.m3t.*, custom_ops.py) instead
+    of the autograd.Functions; same kernels, same results."""
+    return os.environ.get("M3T_TORCH_OPS", "0") == "1"
+
+
 def linear(x, w, b, relu=False, out_f32=False):
+    if torch_ops_enabled():
+        from . import custom_ops  # noqa: F401  (registers torch.ops.m3t)
+        return torch.ops.m3t.linear(as_bf16(x), w, b, relu, out_f32)
     return LinearFn.apply(as_bf16(x), w, b, relu, out_f32)
+
+
+def att_mix(x_a, x_v, s_a, s_v):
+    if torch_ops_enabled():
+        from . import custom_ops  # noqa: F401
+        return torch.ops.m3t.att_mix(x_a.contiguous(), x_v.contiguous(), s_a.float(), s_v.float())
+    return AttMixFn.apply(x_a, x_v, s_a, s_v)
 
 
 def _gru_packed(w_ih, w_ih_r, w_hh, w_hh_r, I, H, biases):

@@ -704,12 +704,18 @@ CHAOTIC_GRADS = {"golden_resnet_trunk_train", "golden_va3dresnet_train", "golden
                  "va3dresnet_96px_train", "va3dresnet_15frames_train", "va3dresnet_1clip_2frames_train"}
 
 
+# measured floors (bf16-emulating oracle vs fp32 oracle, all-parameter gradient L2, CPU): vggface_train 0.131,
+# resnetv2_trunk_train 0.142, resnet_cbam_train 0.106, densenet_train 0.408 (49 train-mode BatchNorms on 8 frames whose
+# last stage is 3x3 pixels) -- the CUDA path has to stay inside the same band
+CHAOTIC_L2 = {"golden_densenet_train": 0.6}
+
+
 def failures(name, errs):
     """The error keys of `errs` that break their tolerance (shared by pytest and tests/gpu_probe.py)."""
     tols = dict(TOLS)
     if name in CHAOTIC_GRADS:
         errs = {k: v for k, v in errs.items() if k != "grad_emu"}
-        tols["grad_all_l2"] = 0.3
+        tols["grad_all_l2"] = CHAOTIC_L2.get(name, 0.3)
     return {k: v for k, v in errs.items() if not isinstance(v, dict) and (v != v or v >= tols.get(k, TOL))}
 
 
@@ -1850,6 +1856,86 @@ for _k in ("conv1.weight_v", "conv1.weight_g", "conv1.bias", "conv2.weight_v", "
            "downsample.weight", "downsample.bias"):
     TOLS["d_" + _k] = 3e-2
 TOLS["zero_fraction_diff"] = 2e-3
+
+
+# ----------------------------------------------------------------------------------------------------------
+# torch.library custom ops (m3t_b200/custom_ops.py): the dispatcher path gives the autograd.Function path's results
+# ----------------------------------------------------------------------------------------------------------
+def case_torch_library(seed=0):
+    import m3t_b200.custom_ops  # noqa: F401
+    from m3t_b200 import ops, raw
+    g = torch.Generator().manual_seed(seed)
+    errs = {}
+    x = _rnd((6, 10, 512), g).cuda()
+    w, b = _rnd((264, 512), g, 0.05).cuda(), _rnd((264,), g, 0.1).cuda()
+    cot = _rnd((6, 10, 264), g).cuda()
+
+    def run(fn):
+        xs, ws, bs = x.clone().requires_grad_(True), w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+        y = fn(xs, ws, bs)
+        (y.float() * cot).sum().backward()
+        return y.detach().float(), xs.grad, ws.grad, bs.grad
+
+    ref = run(lambda a, ww, bb: ops.LinearFn.apply(ops.as_bf16(a), ww, bb, True, False))
+    got = run(lambda a, ww, bb: torch.ops.m3t.linear(ops.as_bf16(a), ww, bb, True, False))
+    errs["lib_linear_exact"] = float(sum((r.float() != t.float()).sum() for r, t in zip(ref, got)))
+    xa, xv = _rnd((4, 9, 512), g).cuda().bfloat16(), _rnd((4, 9, 512), g).cuda().bfloat16()
+    sa, sv = _rnd((4, 9, 1), g).cuda(), _rnd((4, 9, 1), g).cuda()
+
+    def run_mix(fn):
+        leaves = [t.clone().requires_grad_(True) for t in (xa, xv, sa, sv)]
+        f = fn(*leaves)
+        f.float().square().sum().backward()
+        return [f.detach()] + [t.grad for t in leaves]
+
+    ref = run_mix(ops.AttMixFn.apply)
+    got = run_mix(torch.ops.m3t.att_mix)
+    errs["lib_att_mix_exact"] = float(sum((r.float() != t.float()).sum() for r, t in zip(ref, got)))
+    H = 128
+    prm = [(_rnd(s, g, 0.05)).cuda() for s in ((3 * H, 512), (3 * H, H), (3 * H,), (3 * H,)) * 2]
+    xg = _rnd((3, 7, 512), g).cuda().bfloat16()
+
+    def run_gru(fn):
+        leaves = [t.clone().requires_grad_(True) for t in [xg] + prm]
+        out = fn(*leaves)
+        out.float().square().sum().backward()
+        return [out.detach()] + [t.grad for t in leaves]
+
+    ref = run_gru(lambda *a: ops.GRULayerFn.apply(*a, True))
+    got = run_gru(torch.ops.m3t.gru_layer)
+    errs["lib_gru_out_exact"] = float((ref[0] != got[0]).sum())
+    errs["lib_gru_grads"] = max(_l2(t, r) for r, t in zip(ref[1:], got[1:]))
+    A, Bm = _rnd((200, 96), g).cuda().bfloat16(), _rnd((72, 96), g).cuda().bfloat16()
+    errs["lib_gemm_exact"] = float((torch.ops.m3t.gemm(A, Bm, False, False, True, None, None, None, False) !=
+                                    raw.gemm(A, Bm, out_dtype=torch.float32)).sum())
+    # the whole AV model through the dispatcher path (M3T_TORCH_OPS=1) equals the default path bit for bit
+    import bench as BN
+    from m3t_b200.models.model import AffWild2VA
+    torch.manual_seed(3)
+    m = AffWild2VA(BN.hparams()).cuda().eval()
+    BN.randomise_bn(m, 5)
+    bt = {k: v.cuda() for k, v in BN.synth_batch(2, 11, pin=False).items()}
+    with torch.no_grad():
+        y0 = m(bt).clone()
+        os.environ["M3T_TORCH_OPS"] = "1"
+        try:
+            y1 = m(bt).clone()
+        finally:
+            os.environ.pop("M3T_TORCH_OPS", None)
+    errs["lib_model_exact"] = float((y0 != y1).sum())
+    try:
+        torch.library.opcheck(torch.ops.m3t.att_mix, (xa, xv, sa, sv), test_utils=("test_schema", "test_faketensor"))
+        errs["lib_opcheck"] = 0.0
+    except Exception as e:  # noqa: BLE001
+        errs["lib_opcheck"] = 1.0
+        errs["info"] = {"opcheck": str(e)[:300]}
+    return errs
+
+
+CASES["torch_library_ops"] = (case_torch_library, _c())
+for _k in ("lib_linear_exact", "lib_att_mix_exact", "lib_gru_out_exact", "lib_gemm_exact", "lib_model_exact", "lib_opcheck"):
+    TOLS[_k] = 0.5
+TOLS["lib_gru_grads"] = 1e-5
 
 
 if __name__ == "__main__":

@@ -353,3 +353,33 @@ def test_engine_arena_admits_late_gradients():
         assert len(eng.params) == (4 if step >= 2 else 2)
     for (k, p), q in zip(m.state_dict().items(), ref.state_dict().values()):
         assert torch.allclose(p, q, atol=1e-6), k
+
+
+def test_torch_library_registration():
+    """north star: the kernels are torch custom ops.  Every op of custom_ops.OP_NAMES is registered under torch.ops.m3t
+    with a schema and a fake (meta) implementation whose output shapes / dtypes match the C-ABI wrappers'."""
+    import m3t_b200.custom_ops as C
+    for n in C.OP_NAMES:
+        assert hasattr(torch.ops.m3t, n), n
+        assert str(getattr(torch.ops.m3t, n).default._schema).startswith("m3t::" + n)
+    bf = dict(dtype=torch.bfloat16, device="meta")
+    f32 = dict(dtype=torch.float32, device="meta")
+    A, B = torch.empty(128, 64, **bf), torch.empty(32, 64, **bf)
+    assert torch.ops.m3t.gemm(A, B, False, False, True, None, None, None, False).shape == (128, 32)
+    assert torch.ops.m3t.gemm(A, torch.empty(128, 48, **bf), True, True, False, None, None, None, False).shape == (64, 48)
+    x = torch.empty(4, 10, 512, **bf)
+    y = torch.ops.m3t.linear(x, torch.empty(9, 512, **f32), torch.empty(9, **f32), False, True)
+    assert y.shape == (4, 10, 9) and y.dtype == torch.float32
+    s = torch.empty(4, 10, 1, **f32)
+    assert torch.ops.m3t.att_mix(x, x, s, s).shape == x.shape
+    H = 128
+    prm = [torch.empty(3 * H, 512, **f32), torch.empty(3 * H, H, **f32), torch.empty(3 * H, **f32),
+           torch.empty(3 * H, **f32)] * 2
+    assert torch.ops.m3t.gru_layer(x, *prm).shape == (4, 10, 2 * H)
+    from m3t_b200 import raw
+    geom = raw.conv_geom(2, 5, 1, 28, 28, 64, 128, (1, 3, 3), (1, 2, 2), (0, 1, 1), (0, 1, 1), (1, 1, 1))
+    out = torch.ops.m3t.conv_fprop(torch.empty(5, 28, 28, 64, **bf), torch.empty(128, 576, **bf), geom, None, None, None,
+                                   False)
+    assert out.shape == (5, 1, 14, 14, 128)
+    assert torch.ops.m3t.conv_wgrad(torch.empty(5, 28, 28, 64, **bf), out, geom).shape == (128, 576)
+    assert torch.ops.m3t.logmel(torch.empty(16000, **f32), 30.0, True, 80.0).shape == (1 + 16000 // 177, 40)
