@@ -7,7 +7,7 @@ from the UNMODIFIED reference modules.  Run on the build box only:   python -m o
   cbam_{eval,train}             CBAM(128) (ChannelGate + SpatialGate)                        models/cbam.py:1-112
   resnet_cbam_train             ResNet(BasicBlock, [1,1,1,1], use_cbam=True)                  models/resnet.py:32-35,48-49
   vggface_{eval,train}          VGGFace (13 conv + ReLU, ceil-mode pooling, fc1)             models/vggface.py:7-50
-  densenet_{eval,train}         DenseNet52_3D(392, agg_mode='ap') on (2,64,4,28,28)          models/densenet.py:5-93
+  densenet_{eval,train}         DenseNet52_3D(392, agg_mode='ap') on (4,64,8,28,28)          models/densenet.py:5-93
 """
 import os
 import sys
@@ -119,7 +119,7 @@ def gen_densenet():
         m = dn.DenseNet52_3D(392, agg_mode="ap", fmap_out_size=3)
         spec = load_synth(m, 68)
         m.train(mode == "train")
-        gen = {"x": dict(kind="randn_relu", shape=(2, 64, 4, 28, 28), seed=69)}
+        gen = {"x": dict(kind="randn_relu", shape=(4, 64, 8, 28, 28), seed=69)}     # 32 frames: 288 samples in the 3x3 stage
         x = materialise(gen)["x"].requires_grad_(True)
         out, cot, grads = run_with_grads(m, lambda: m(x), {"x": x}, 70)
         save("densenet_" + mode, dict(kind="DenseNet52_3D", mode=mode, seed=68, spec=spec, inputs_gen=gen, out=out,

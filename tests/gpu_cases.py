@@ -708,11 +708,15 @@ CHAOTIC_GRADS = {"golden_resnet_trunk_train", "golden_va3dresnet_train", "golden
 # resnetv2_trunk_train 0.142, resnet_cbam_train 0.106, densenet_train 0.408 (49 train-mode BatchNorms on 8 frames whose
 # last stage is 3x3 pixels) -- the CUDA path has to stay inside the same band
 CHAOTIC_L2 = {"golden_densenet_train": 0.6}
+# train-mode forward of the 49-BatchNorm DenseNet on synthetic high-gain weights: the bf16-emulating oracle itself is
+# 2.4e-2 from the reference (floor, 32-frame fixture); eval mode sits at 5e-3
+CASE_TOLS = {"golden_densenet_train": {"out_emu": 3e-2, "out_ref": 4e-2}}
 
 
 def failures(name, errs):
     """The error keys of `errs` that break their tolerance (shared by pytest and tests/gpu_probe.py)."""
     tols = dict(TOLS)
+    tols.update(CASE_TOLS.get(name, {}))
     if name in CHAOTIC_GRADS:
         errs = {k: v for k, v in errs.items() if k != "grad_emu"}
         tols["grad_all_l2"] = CHAOTIC_L2.get(name, 0.3)
@@ -1866,9 +1870,9 @@ def case_torch_library(seed=0):
     from m3t_b200 import ops, raw
     g = torch.Generator().manual_seed(seed)
     errs = {}
-    x = _rnd((6, 10, 512), g).cuda()
-    w, b = _rnd((264, 512), g, 0.05).cuda(), _rnd((264,), g, 0.1).cuda()
-    cot = _rnd((6, 10, 264), g).cuda()
+    x = _rnd((6, 10, 512), g).float().cuda()
+    w, b = _rnd((264, 512), g, 0.05).float().cuda(), _rnd((264,), g, 0.1).float().cuda()
+    cot = _rnd((6, 10, 264), g).float().cuda()
 
     def run(fn):
         xs, ws, bs = x.clone().requires_grad_(True), w.clone().requires_grad_(True), b.clone().requires_grad_(True)
@@ -1880,7 +1884,7 @@ def case_torch_library(seed=0):
     got = run(lambda a, ww, bb: torch.ops.m3t.linear(ops.as_bf16(a), ww, bb, True, False))
     errs["lib_linear_exact"] = float(sum((r.float() != t.float()).sum() for r, t in zip(ref, got)))
     xa, xv = _rnd((4, 9, 512), g).cuda().bfloat16(), _rnd((4, 9, 512), g).cuda().bfloat16()
-    sa, sv = _rnd((4, 9, 1), g).cuda(), _rnd((4, 9, 1), g).cuda()
+    sa, sv = _rnd((4, 9, 1), g).float().cuda(), _rnd((4, 9, 1), g).float().cuda()
 
     def run_mix(fn):
         leaves = [t.clone().requires_grad_(True) for t in (xa, xv, sa, sv)]
@@ -1892,7 +1896,7 @@ def case_torch_library(seed=0):
     got = run_mix(torch.ops.m3t.att_mix)
     errs["lib_att_mix_exact"] = float(sum((r.float() != t.float()).sum() for r, t in zip(ref, got)))
     H = 128
-    prm = [(_rnd(s, g, 0.05)).cuda() for s in ((3 * H, 512), (3 * H, H), (3 * H,), (3 * H,)) * 2]
+    prm = [(_rnd(s, g, 0.05)).float().cuda() for s in ((3 * H, 512), (3 * H, H), (3 * H,), (3 * H,)) * 2]
     xg = _rnd((3, 7, 512), g).cuda().bfloat16()
 
     def run_gru(fn):
