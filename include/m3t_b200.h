@@ -199,6 +199,23 @@ int m3t_cast_f32_bf16(const float* in, long long ld_in, void* out, long long ld_
                       void* stream);
 int m3t_cast_bf16_f32(const void* in, long long ld_in, float* out, long long ld_out, long long rows, int cols,
                       void* stream);
+/* Every convolution filter of a model re-packed by ONE launch after the optimizer step (the per-filter m3t_pack_filter
+ * calls were 19 launches + 15 index_select per step).  `table_dev` = n entries in device memory, ordered by `start`
+ * (prefix sum of Cout*Cin*taps); outputs as m3t_pack_filter, plus - when has_parity - the four parity sub-filters of
+ * a stride-2 convolution's data gradient: tap t goes to par[par_of_tap[t]] at position pos_of_tap[t] of its
+ * ntaps_par[.] taps, layout [Cin][ntaps][Cout] (par_of_tap[t] < 0: tap unused).  taps <= 27. */
+typedef struct m3t_pack_entry {
+  const void* src;      /* fp32 [Cout][Cin][taps] */
+  void* wf;             /* bf16 [Cout][taps][Cin] or NULL */
+  void* wd;             /* bf16 [Cin][taps flipped][Cout] or NULL */
+  void* par[4];         /* bf16 parity sub-filters or NULL */
+  long long start;
+  int Cout, Cin, taps, has_parity;
+  int ntaps_par[4];
+  int par_of_tap[27];
+  int pos_of_tap[27];
+} m3t_pack_entry;
+int m3t_pack_filters_batched(const m3t_pack_entry* table_dev, int n, long long total, void* stream);
 /* Filter packing fp32 [Cout][Cin][taps] -> bf16 [Cout][taps][Cin] (fprop) and [Cin][taps reversed][Cout] (dgrad);
  * and the inverse re-layout of a packed fp32 weight gradient. */
 int m3t_pack_filter(const float* w, void* w_fprop, void* w_dgrad, int Cout, int Cin, int taps, void* stream);
@@ -400,6 +417,16 @@ int m3t_cbam_conv5_bwd(const float* dout, const float* in, const float* w, float
  * [F][H][W][C] -> [F][H/2][W/2][C] (floor), and its backward (dx = dy/4 inside the windows, 0 on an odd last row / column). */
 int m3t_avgpool2x2(const void* x, void* y, int F, int H, int W, int C, void* stream);
 int m3t_avgpool2x2_bwd(const void* dy, void* dx, int F, int H, int W, int C, void* stream);
+
+/* Training loss of the task module and its gradient in one launch (fusion.cu): L = lambda (1 - CCC(v_hat, v)) +
+ * (1 - lambda)(1 - CCC(a_hat, a)) [+ w_ce * mean_i(valid_i * CE(logits_i, class_i)) when n_logits > 0], CCC with the
+ * reference's mixed estimators (biased covariance, unbiased variances; models/utils.py:6-17).  y_hat fp32 [N][C],
+ * idx_v / idx_a = columns of the valence / arousal predictions, n_logits = leading expression logits (0: none).
+ * out4 = {L, L_v, L_a, CE mean}; dy = dL/dy_hat [N][C].  One CTA, fixed-order reductions (bit-reproducible).  Replaces
+ * ~90 ATen launches of concordance_cc2 / cross_entropy forward + backward (models/model.py:132-144,162-182). */
+int m3t_av_loss(const float* y_hat, const float* label_v, const float* label_a, const long long* cls,
+                const unsigned char* valid, int N, int C, int idx_v, int idx_a, int n_logits, float lambda, float w_ce,
+                float* out4, float* dy, void* stream);
 
 #ifdef __cplusplus
 }

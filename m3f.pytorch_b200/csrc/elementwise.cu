@@ -957,6 +957,38 @@ __global__ void pack_filter_kernel(const float* __restrict__ w, __nv_bfloat16* _
     if (wd) wd[((long long)ci * taps + (taps - 1 - t)) * Cout + co] = v;
   }
 }
+// All convolution filters of a model in ONE launch (table-driven): for entry e and element (co, ci, t) of its fp32
+// master [Cout][Cin][taps] write the fprop pack, the flipped dgrad pack and - for stride-2 convolutions whose data
+// gradient runs as parity sub-convolutions - the sub-filter of the output parity that tap t belongs to.
+__global__ void pack_filters_batched_kernel(const m3t_pack_entry* __restrict__ tab, int n, long long total) {
+  __shared__ long long starts[129];
+  for (int i = threadIdx.x; i <= n && i <= 128; i += blockDim.x) starts[i] = i < n ? tab[i].start : total;
+  __syncthreads();
+  for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < total;
+       g += (long long)gridDim.x * blockDim.x) {
+    int lo = 0, hi = n - 1;
+    while (lo < hi) {                       // last entry with start <= g
+      const int mid = (lo + hi + 1) >> 1;
+      if (starts[mid] <= g) lo = mid; else hi = mid - 1;
+    }
+    const m3t_pack_entry& e = tab[lo];
+    const long long i = g - e.start;
+    const int taps = e.taps, Cin = e.Cin, Cout = e.Cout;
+    const int t = (int)(i % taps);
+    long long r = i / taps;
+    const int ci = (int)(r % Cin);
+    const int co = (int)(r / Cin);
+    const __nv_bfloat16 v = __float2bfloat16(reinterpret_cast<const float*>(e.src)[i]);
+    if (e.wf) reinterpret_cast<__nv_bfloat16*>(e.wf)[((long long)co * taps + t) * Cin + ci] = v;
+    if (e.wd) reinterpret_cast<__nv_bfloat16*>(e.wd)[((long long)ci * taps + (taps - 1 - t)) * Cout + co] = v;
+    if (e.has_parity) {
+      const int p = e.par_of_tap[t];
+      if (p >= 0)
+        reinterpret_cast<__nv_bfloat16*>(e.par[p])[((long long)ci * e.ntaps_par[p] + e.pos_of_tap[t]) * Cout + co] = v;
+    }
+  }
+}
+
 __global__ void unpack_filter_grad_kernel(const float* __restrict__ dwp, float* __restrict__ dw, int Cout, int Cin,
                                           int taps) {
   const long long total = (long long)Cout * Cin * taps;
@@ -1471,6 +1503,13 @@ extern "C" int m3t_pack_filter(const float* w, void* w_fprop, void* w_dgrad, int
   pack_filter_kernel<<<ew_blocks((long long)Cout * Cin * taps), kEwThreads, 0, ST(stream)>>>(w, BF(w_fprop),
                                                                                            BF(w_dgrad), Cout, Cin,
                                                                                            taps);
+  count_launch();
+  return launch_status();
+}
+
+extern "C" int m3t_pack_filters_batched(const m3t_pack_entry* table_dev, int n, long long total, void* stream) {
+  if (n <= 0 || n > 128 || total <= 0) return -1;
+  pack_filters_batched_kernel<<<ew_blocks(total), kEwThreads, 0, ST(stream)>>>(table_dev, n, total);
   count_launch();
   return launch_status();
 }

@@ -118,3 +118,125 @@ extern "C" int m3t_att_mix_bwd(const void* df, const void* x_a, const void* x_v,
   count_launch();
   return launch_status();
 }
+
+namespace m3t {
+
+// ------------------------------------------------------------------------------------------------------------
+// Training loss of the task module and its gradient in ONE launch (reference models/model.py:132-144,146-182;
+// models/utils.py:6-17):   L = lambda * (1 - CCC(v_hat, v)) + (1 - lambda) * (1 - CCC(a_hat, a))
+//                              [+ w_ce * mean_i( valid_i * CE(logits_i, class_i) )]          (loss 'ccc_mtl')
+// CCC over the flattened local batch with the reference's mixed estimators: biased covariance, UNBIASED variances.
+// y_hat [N][C] fp32 (C = 9: 7 expression logits, valence, arousal; C = 2: valence, arousal), labels fp32 [N],
+// classes int64 [N], valid uint8 [N].  One CTA (N = B*T <= a few thousand rows); every reduction is a fixed-order
+// shared-memory tree, so the loss and dL/dy_hat are bit-reproducible.  The eager PyTorch version of this was ~90
+// launches per step (5 % of the launches of the whole training step).
+// out[0] = L, out[1] = L_v, out[2] = L_a, out[3] = CE term (before w_ce); dy [N][C] = dL/dy_hat.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int kLossThreads = 1024;
+
+__device__ __forceinline__ double block_sum_d(double v, double* red) {
+  // fixed-order tree over the block; result broadcast to every thread
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double s = 0.0;
+  if (threadIdx.x < 32) {
+    s = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (threadIdx.x == 0) red[32] = s;
+  }
+  __syncthreads();
+  return red[32];
+}
+
+__global__ void __launch_bounds__(kLossThreads, 1)
+av_loss_kernel(const float* __restrict__ y, const float* __restrict__ lab_v, const float* __restrict__ lab_a,
+               const long long* __restrict__ cls, const unsigned char* __restrict__ valid, int N, int C, int iv, int ia,
+               int n_logits, float lambda, float w_ce, float* __restrict__ out, float* __restrict__ dy) {
+  __shared__ double red[33];
+  const int tid = threadIdx.x;
+  // ---- first moments ----
+  double sx[2] = {0, 0}, sy[2] = {0, 0};
+  for (int i = tid; i < N; i += kLossThreads) {
+    sx[0] += y[(long long)i * C + iv];
+    sx[1] += y[(long long)i * C + ia];
+    sy[0] += lab_v[i];
+    sy[1] += lab_a[i];
+  }
+  double mx[2], my[2];
+  for (int k = 0; k < 2; ++k) {
+    mx[k] = block_sum_d(sx[k], red) / N;
+    my[k] = block_sum_d(sy[k], red) / N;
+  }
+  // ---- centred second moments ----
+  double sxx[2] = {0, 0}, syy[2] = {0, 0}, sxy[2] = {0, 0};
+  for (int i = tid; i < N; i += kLossThreads) {
+    const double xv = y[(long long)i * C + iv] - mx[0], xa = y[(long long)i * C + ia] - mx[1];
+    const double yv = lab_v[i] - my[0], ya = lab_a[i] - my[1];
+    sxx[0] += xv * xv; syy[0] += yv * yv; sxy[0] += xv * yv;
+    sxx[1] += xa * xa; syy[1] += ya * ya; sxy[1] += xa * ya;
+  }
+  double cov[2], vx[2], vy[2], den[2], ccc[2];
+  for (int k = 0; k < 2; ++k) {
+    cov[k] = block_sum_d(sxy[k], red) / N;                 // biased
+    vx[k] = block_sum_d(sxx[k], red) / (N - 1);            // unbiased (torch.var)
+    vy[k] = block_sum_d(syy[k], red) / (N - 1);
+    den[k] = vx[k] + vy[k] + (mx[k] - my[k]) * (mx[k] - my[k]);
+    ccc[k] = 2.0 * cov[k] / den[k];
+  }
+  // ---- masked cross-entropy over the expression logits, and the whole gradient ----
+  const double wk[2] = {(double)lambda, 1.0 - (double)lambda};
+  double ce = 0.0;
+  for (int i = tid; i < N; i += kLossThreads) {
+    float* d = dy + (long long)i * C;
+    const float* yi = y + (long long)i * C;
+    for (int j = 0; j < C; ++j) d[j] = 0.f;
+    if (n_logits > 0) {
+      float m = -INFINITY;
+      for (int j = 0; j < n_logits; ++j) m = fmaxf(m, yi[j]);
+      float se = 0.f;
+      for (int j = 0; j < n_logits; ++j) se += expf(yi[j] - m);
+      const float lse = m + logf(se);
+      const int c = (int)cls[i];
+      const bool ok = valid[i] != 0 && c >= 0 && c < n_logits;
+      if (ok) {
+        ce += (double)(lse - yi[c]);
+        const float g = w_ce / (float)N;
+        for (int j = 0; j < n_logits; ++j) d[j] = g * (expf(yi[j] - lse) - (j == c ? 1.f : 0.f));
+      }
+    }
+    const int col[2] = {iv, ia};
+    const float* lab[2] = {lab_v, lab_a};
+    for (int k = 0; k < 2; ++k) {
+      const double xc = (double)yi[col[k]] - mx[k], yc = (double)lab[k][i] - my[k];
+      // d ccc / d x_i = 2 [ (y_i - my)/N * D - cov * (2 (x_i - mx)/(N-1) + 2 (mx - my)/N) ] / D^2
+      const double dccc = 2.0 * (yc / N * den[k] - cov[k] * (2.0 * xc / (N - 1) + 2.0 * (mx[k] - my[k]) / N)) /
+                          (den[k] * den[k]);
+      d[col[k]] += (float)(-wk[k] * dccc);
+    }
+  }
+  const double ce_mean = block_sum_d(ce, red) / N;
+  if (tid == 0) {
+    const double lv = 1.0 - ccc[0], la = 1.0 - ccc[1];
+    out[1] = (float)lv;
+    out[2] = (float)la;
+    out[3] = (float)ce_mean;
+    out[0] = (float)(wk[0] * lv + wk[1] * la + (n_logits > 0 ? (double)w_ce * ce_mean : 0.0));
+  }
+}
+
+}  // namespace m3t
+
+extern "C" int m3t_av_loss(const float* y_hat, const float* label_v, const float* label_a, const long long* cls,
+                           const unsigned char* valid, int N, int C, int idx_v, int idx_a, int n_logits, float lambda,
+                           float w_ce, float* out4, float* dy, void* stream) {
+  if (N < 2 || C < 2 || idx_v < 0 || idx_v >= C || idx_a < 0 || idx_a >= C || n_logits < 0 || n_logits > C) return -1;
+  if (n_logits > 0 && (!cls || !valid)) return -1;
+  m3t::av_loss_kernel<<<1, m3t::kLossThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      y_hat, label_v, label_a, cls, valid, N, C, idx_v, idx_a, n_logits, lambda, w_ce, out4, dy);
+  m3t::count_launch();
+  return m3t::launch_status();
+}

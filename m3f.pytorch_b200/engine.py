@@ -299,6 +299,10 @@ class TrainEngine:
         if self.on_gpu:
             from . import raw
             raw.begin_step(self.all_params[0].device)     # one memset instead of ~90 zero-fill kernels (raw.StepPool)
+            if self.steps >= 1 and os.environ.get("M3T_PREPACK", "1") == "1":
+                if not hasattr(self, "_param_ids"):
+                    self._param_ids = {id(p) for p in self.all_params}
+                ops.prepack(self._param_ids)              # every conv filter re-packed by one launch
         try:
             return self._eager_step_body(batch, count)
         finally:

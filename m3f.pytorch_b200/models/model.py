@@ -6,6 +6,7 @@ dataloaders, argparse surface), so the reference's train.py / eval.py drive it u
 Only the hot-path configurations are built: modality in {audio, visual, audiovisual}, backbone in {resnet, v2p,
 v2p_split}, fusion_type in {concat, attention}.
 """
+import os
 import sys
 from argparse import ArgumentParser
 
@@ -151,6 +152,16 @@ class AffWild2VA(_Base):
         else:
             v_hat, a_hat = y_hat[..., -2], y_hat[..., -1]
         v, a = batch['label_valence'], batch['label_arousal']
+        if sync_free and 'ccc' in hp.loss and y_hat.is_cuda and os.environ.get("M3T_FUSED_LOSS", "1") == "1":
+            # the engine's step: both CCC terms, the masked cross-entropy and dL/dy_hat in ONE launch (m3t_av_loss)
+            mtl = 'mtl' in hp.loss
+            out = ops.AVLossFn.apply(y_hat, v, a, batch['class_expr'] if mtl else None,
+                                     batch['expr_valid'] if mtl else None, 7 if mtl else -2, -1, 7 if mtl else 0,
+                                     hp.loss_lambda, 0.8)
+            logs = {'loss_v': out[1], 'loss_a': out[2], 'loss': out[0]}
+            if mtl:
+                logs['loss_expr'] = out[3]
+            return out[0], logs
         if 'mse' in hp.loss:
             loss_v, loss_a = self.mse_loss(v_hat, v), self.mse_loss(a_hat, a)
         else:

@@ -44,8 +44,110 @@ def clear_caches():
     _pack_cache.clear()
 
 
+# ------------------------------------------------------------------------------------------------------------
+# All convolution filters of the model re-packed by ONE launch per step (m3t_pack_filters_batched).  The first step
+# records which parameters ask for a pack (and which stride-2 convolutions ask for parity sub-filters); from the
+# second step on TrainEngine calls prepack() before the forward, which fills the derived-weight cache in one launch,
+# so packed_filter() / the parity lookup are cache hits (was: 19 pack launches + 15 index_select per step).
+# ------------------------------------------------------------------------------------------------------------
+_prepack_wish = {}      # id(w) -> [weakref(w), parity index lists (4 x list | None) or None]
+_prepack_plans = {}
+
+
+def _wish(w, parity=None):
+    e = _prepack_wish.get(id(w))
+    if e is None or e[0]() is not w:
+        e = _prepack_wish[id(w)] = [weakref.ref(w), None]
+    if parity is not None:
+        e[1] = parity
+
+
+def prepack(allowed=None):
+    """Fill the derived-weight cache for every recorded convolution filter with one launch; returns the number packed.
+    allowed: optional set of id(parameter) restricting the pack to one model's parameters."""
+    import ctypes
+    live = [(e[0](), e[1]) for e in _prepack_wish.values() if e[0]() is not None and e[0]().is_cuda]
+    if allowed is not None:
+        live = [(w, par) for w, par in live if id(w) in allowed]
+    live = [(w, par) for w, par in live if w.dim() >= 3 and w.dtype == torch.float32 and w.is_contiguous()]
+    if not live:
+        return 0
+    if len(live) > 128:
+        live = live[:128]
+    key = tuple((id(w), w.data_ptr(), tuple(w.shape), None if par is None else tuple(
+        None if p is None else tuple(p) for p in par)) for w, par in live)
+    plan = _prepack_plans.get("plan")
+    if plan is None or plan["key"] != key:
+        class Entry(ctypes.Structure):
+            _fields_ = [("src", ctypes.c_void_p), ("wf", ctypes.c_void_p), ("wd", ctypes.c_void_p),
+                        ("par", ctypes.c_void_p * 4), ("start", ctypes.c_longlong), ("Cout", ctypes.c_int),
+                        ("Cin", ctypes.c_int), ("taps", ctypes.c_int), ("has_parity", ctypes.c_int),
+                        ("ntaps_par", ctypes.c_int * 4), ("par_of_tap", ctypes.c_int * 27),
+                        ("pos_of_tap", ctypes.c_int * 27)]
+
+        dev = live[0][0].device
+        need = 0
+        for w, par in live:
+            n = w.numel()
+            need += 2 * n + (n if par is not None else 0) + 64
+        buf = torch.empty(need, device=dev, dtype=torch.bfloat16)
+        table = (Entry * len(live))()
+        views, off, start = [], 0, 0
+
+        def take(numel):
+            nonlocal off
+            t = buf[off:off + numel]
+            off += (numel + 7) // 8 * 8
+            return t
+
+        for i, (w, par) in enumerate(live):
+            Cout, Cin = w.shape[0], w.shape[1]
+            taps = w.numel() // (Cout * Cin)
+            if taps > 27:
+                return 0
+            wf = take(w.numel()).view(Cout, taps * Cin)
+            wd = take(w.numel()).view(Cin, taps * Cout)
+            e = table[i]
+            e.src, e.wf, e.wd = w.data_ptr(), wf.data_ptr(), wd.data_ptr()
+            e.start, e.Cout, e.Cin, e.taps = start, Cout, Cin, taps
+            subs = None
+            for t in range(27):
+                e.par_of_tap[t] = -1
+                e.pos_of_tap[t] = 0
+            if par is not None:
+                e.has_parity = 1
+                subs = []
+                for p, idx in enumerate(par):
+                    if idx is None:
+                        subs.append(None)
+                        continue
+                    sub = take(Cin * len(idx) * Cout).view(Cin, len(idx) * Cout)
+                    subs.append(sub)
+                    e.par[p] = sub.data_ptr()
+                    e.ntaps_par[p] = len(idx)
+                    for j, flipped in enumerate(idx):
+                        t = taps - 1 - int(flipped)
+                        e.par_of_tap[t], e.pos_of_tap[t] = p, j
+                subs = tuple(subs)
+            views.append((w, wf, wd, subs))
+            start += w.numel()
+        raw_bytes = bytes(table)
+        tab = torch.frombuffer(bytearray(raw_bytes), dtype=torch.uint8).to(dev)
+        plan = _prepack_plans["plan"] = dict(key=key, buf=buf, tab=tab, views=views, total=start, n=len(live))
+    raw.L.check(raw._lib().m3t_pack_filters_batched(raw.L.ptr(plan["tab"]), raw.L.i32(plan["n"]),
+                                                    raw.L.i64(plan["total"]), raw.L.stream_ptr()),
+                "pack_filters_batched")
+    for w, wf, wd, subs in plan["views"]:
+        ver = ((w._version, w.data_ptr()),)
+        _pack_cache[((id(w),), "filter")] = (ver, (weakref.ref(w),), (wf, wd))
+        if subs is not None:
+            _pack_cache[((id(w),), "dgrad_s2")] = (ver, (weakref.ref(w),), subs)
+    return plan["n"]
+
+
 def packed_filter(w, want_dgrad):
     def make():
+        _wish(w)
         return raw.pack_filter(w.detach(), True)
     wf, wd = _cached(w, "filter", make)
     return wf, wd
@@ -349,6 +451,7 @@ class AvgPool2x2Fn(torch.autograd.Function):
 
 
 _PARITY_TAPS = {}
+_PARITY_LISTS = {}
 
 
 def _parity_taps(K, pad, ph, pw, device):
@@ -368,6 +471,7 @@ def _parity_taps(K, pad, ph, pw, device):
             taps = K * K
             idx = [taps - 1 - ((ph + pad - 2 * dh) * K + (pw + pad - 2 * dw))
                    for dh in range(hlo, hhi + 1) for dw in range(wlo, whi + 1)]
+            _PARITY_LISTS[(K, pad, ph, pw)] = idx
             _PARITY_TAPS[key] = (torch.tensor(idx, device=device, dtype=torch.long), hhi - hlo + 1, whi - wlo + 1,
                                  -hlo, -wlo)
     return _PARITY_TAPS[key]
@@ -396,6 +500,7 @@ def _dgrad_s2_parity(dy, w, x_shape, pad, accum_into=None):
     _, wd = packed_filter(w, True)
 
     def make():
+        _wish(w, [None if pl is None else _PARITY_LISTS[(K, pad, pl[0], pl[1])] for pl in plans])
         wd3 = wd.view(Cin, K * K, Cout)
         return tuple(None if pl is None else wd3.index_select(1, pl[2]).reshape(Cin, -1).contiguous() for pl in plans)
 
@@ -691,6 +796,33 @@ def _cached_multi(tensors, tag, fn):
             del _pack_cache[k]
     _pack_cache[key] = (ver, tuple(weakref.ref(t) for t in tensors), val)
     return val
+
+
+class AVLossFn(torch.autograd.Function):
+    """ccc / ccc_mtl training loss of the task module and dL/dy_hat in one launch (m3t_av_loss); returns the fp32
+    vector (L, L_v, L_a, CE).  Only L is differentiable."""
+
+    @staticmethod
+    def forward(ctx, y_hat, label_v, label_a, cls, valid, idx_v, idx_a, n_logits, lam, w_ce):
+        y2 = y_hat.contiguous().view(-1, y_hat.shape[-1]).float()
+        N, C = y2.shape
+        out = torch.empty(4, device=y2.device, dtype=torch.float32)
+        dy = torch.empty_like(y2)
+        raw.L.check(raw._lib().m3t_av_loss(
+            raw.L.ptr(y2), raw.L.ptr(label_v.contiguous().view(-1).float()),
+            raw.L.ptr(label_a.contiguous().view(-1).float()),
+            raw.L.ptr(cls.contiguous().view(-1).long() if cls is not None else None),
+            raw.L.ptr(valid.contiguous().view(-1).to(torch.uint8) if valid is not None else None), raw.L.i32(N),
+            raw.L.i32(C), raw.L.i32(idx_v % C), raw.L.i32(idx_a % C), raw.L.i32(n_logits), raw.L.f32(lam),
+            raw.L.f32(w_ce), raw.L.ptr(out), raw.L.ptr(dy), raw.L.stream_ptr()), "av_loss")
+        ctx.save_for_backward(dy)
+        ctx.shape = tuple(y_hat.shape)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (dy,) = ctx.saved_tensors
+        return (dy * dout[0]).view(ctx.shape), None, None, None, None, None, None, None, None, None
 
 
 class AttMixFn(torch.autograd.Function):

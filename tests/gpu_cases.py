@@ -1942,6 +1942,107 @@ for _k in ("lib_linear_exact", "lib_att_mix_exact", "lib_gru_out_exact", "lib_ge
 TOLS["lib_gru_grads"] = 1e-5
 
 
+# ----------------------------------------------------------------------------------------------------------
+# One-launch re-pack of every convolution filter (ops.prepack / m3t_pack_filters_batched) == the per-filter packs
+# ----------------------------------------------------------------------------------------------------------
+def case_prepack(seed=0):
+    from m3t_b200 import ops, raw
+    from m3t_b200.models.resnet import BasicBlock, ResNet
+    torch.manual_seed(seed)
+    m = ResNet(BasicBlock, [2, 2, 2, 2], 512, zero_init_residual=False, agg_mode="ap", fmap_out_size=3).cuda().train()
+    x = torch.randn(4, 64, 28, 28, device="cuda")
+    ops.clear_caches()
+    ops._prepack_wish.clear()
+    m(x).square().mean().backward()              # records which filters / parity sub-filters the model asks for
+    ref = {}
+    for k, v in ops._pack_cache.items():
+        if k[1] in ("filter", "dgrad_s2"):
+            ref[k] = [None if t is None else t.clone() for t in v[2]]
+    ops.clear_caches()
+    n = ops.prepack({id(p) for p in m.parameters()})
+    bad = 0.0
+    seen = 0
+    for k, want in ref.items():
+        got = ops._pack_cache.get(k)
+        if got is None:
+            bad += 1
+            continue
+        for a, b in zip(got[2], want):
+            if (a is None) != (b is None):
+                bad += 1
+            elif a is not None:
+                seen += 1
+                bad += float((a.reshape(-1).view(torch.int16) != b.reshape(-1).view(torch.int16)).sum())
+    errs = {"prepack_exact": bad, "prepack_missing": 0.0 if (n == 19 and seen >= 40) else 1.0}
+    errs["info"] = {"filters": n, "tensors_compared": seen}
+    # and the model gives the same gradients with the pre-packed cache (cache hits) as without
+    g0 = [p.grad.clone() for p in m.parameters() if p.grad is not None]
+    m.zero_grad(set_to_none=True)
+    m(x).square().mean().backward()
+    g1 = [p.grad for p in m.parameters() if p.grad is not None]
+    errs["prepack_grad_l2"] = max(_l2(a, b) for a, b in zip(g1, g0))
+    return errs
+
+
+CASES["prepack_filters"] = (case_prepack, _c())
+TOLS["prepack_exact"] = 0.5
+TOLS["prepack_missing"] = 0.5
+TOLS["prepack_grad_l2"] = 1e-4
+
+
+# ----------------------------------------------------------------------------------------------------------
+# Fused training loss (m3t_av_loss: both CCC terms + masked CE + dL/dy_hat in one launch) vs the reference-shaped
+# PyTorch composition (models/model.py compute_loss) and vs the oracle's training_loss on the CPU
+# ----------------------------------------------------------------------------------------------------------
+def case_av_loss(seed=0):
+    import argparse
+    from m3t_b200.models.model import AffWild2VA
+    from oracle import ref_torch as R
+    g = torch.Generator().manual_seed(seed)
+    errs = {}
+    for tag, loss_name, C, B, T in (("mtl", "ccc_mtl", 9, 32, 16), ("va", "ccc", 2, 5, 7), ("big", "ccc_mtl", 9, 256, 16)):
+        y = torch.randn((B, T, C), generator=g)
+        batch = {"label_valence": torch.rand((B, T), generator=g) * 2 - 1,
+                 "label_arousal": torch.rand((B, T), generator=g) * 2 - 1,
+                 "class_expr": torch.randint(0, 7, (B, T), generator=g),
+                 "expr_valid": torch.rand((B, T), generator=g) > 0.3}
+        hp = argparse.Namespace(loss=loss_name, loss_lambda=0.3)
+        stub = argparse.Namespace(hparams=hp)
+        for k in ("ccc_loss", "ce_loss", "mse_loss"):
+            setattr(stub, k, getattr(AffWild2VA, k).__get__(stub))
+        cb = {k: v.cuda() for k, v in batch.items()}
+
+        def run(fused):
+            os.environ["M3T_FUSED_LOSS"] = "1" if fused else "0"
+            yc = y.cuda().requires_grad_(True)
+            loss, logs = AffWild2VA.compute_loss(stub, yc, cb, sync_free=True)
+            loss.backward()
+            return float(loss), yc.grad.cpu(), {k: float(v) for k, v in logs.items()}
+
+        try:
+            lf, gf, logs_f = run(True)
+            lt, gt, logs_t = run(False)
+        finally:
+            os.environ.pop("M3T_FUSED_LOSS", None)
+        yo = y.clone().requires_grad_(True)
+        lo = R.training_loss(yo, batch, loss_name, 0.3)
+        lo.backward()
+        errs["loss_%s_vs_torch" % tag] = abs(lf - lt) / max(abs(lt), 1e-6)
+        errs["loss_%s_vs_oracle" % tag] = abs(lf - float(lo)) / max(abs(float(lo)), 1e-6)
+        errs["dloss_%s_vs_torch" % tag] = _l2(gf, gt)
+        errs["dloss_%s_vs_oracle" % tag] = _l2(gf, yo.grad)
+        errs["logs_%s" % tag] = max(abs(logs_f[k] - logs_t[k]) for k in logs_f)
+    return errs
+
+
+CASES["av_loss_fused"] = (case_av_loss, _c())
+for _t in ("mtl", "va", "big"):
+    for _k in ("loss_%s_vs_torch", "loss_%s_vs_oracle", "logs_%s"):
+        TOLS[_k % _t] = 2e-5
+    TOLS["dloss_%s_vs_torch" % _t] = 2e-5
+    TOLS["dloss_%s_vs_oracle" % _t] = 2e-5
+
+
 if __name__ == "__main__":
     name = sys.argv[1]
     errs = run_case(name)
