@@ -27,10 +27,10 @@ static int launch_umma(const CUtensorMap& tmA, const CUtensorMap& tmB, const Umm
 
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
-template <int BN, int MT, int STAGES, int AKIND>
+template <int BN, int MT, int STAGES, int AKIND, bool TCN = false>
 static int launch_persist(const CUtensorMap& tmA, const CUtensorMap& tmB, const UmmaParams& p, int tiles_m,
                           cudaStream_t st) {
-  auto kern = umma_persist_kernel<BN, MT, STAGES, AKIND>;
+  auto kern = umma_persist_kernel<BN, MT, STAGES, AKIND, TCN>;
   constexpr int smem = umma_persist_smem_bytes<BN, MT, STAGES>();
   static_assert(smem <= 227 * 1024, "shared memory");
   static bool attr_done = false;
@@ -259,6 +259,12 @@ static int conv_fprop_impl(const void* x, const void* w_packed, void* y, const i
   }
   // persistent tile walker (umma_persist.cuh): tile_hint bit4 forces it, bit5 forbids it
   const bool persist = (tile_hint & 16) != 0 || (!(tile_hint & 32) && conv_use_persist(g, p, bn, mt));
+  if (tcn) {       // fused TemporalBlock epilogue: its own instantiations of the persistent kernel
+    if (!persist) return -5;
+    if (bn == 64) return launch_persist<64, 1, 8, A_IM2COL, true>(tmA, tmB, p, ceil_div(Mpix, 128), st);
+    if (bn == 128) return launch_persist<128, 1, 6, A_IM2COL, true>(tmA, tmB, p, ceil_div(Mpix, 128), st);
+    return launch_persist<256, 1, 4, A_IM2COL, true>(tmA, tmB, p, ceil_div(Mpix, 128), st);
+  }
   if (persist) {
     if (bn == 64 && mt == 1) return launch_persist<64, 1, 8, A_IM2COL>(tmA, tmB, p, tiles_m, st);
     if (bn == 64 && mt == 2) return launch_persist<64, 2, 5, A_IM2COL>(tmA, tmB, p, tiles_m, st);

@@ -136,6 +136,9 @@ __device__ __forceinline__ void butterfly_colsum<0>(float (&)[32], uint32_t) {}
 // Epilogue output of one 32-column chunk of one accumulator row: v * scale + shift (+ residual) (ReLU) -> bf16 / fp32.
 // m = row of D, mo = output row (after the optional scatter map), nc0 = first global column of the chunk, cols_left =
 // columns of the CTA tile from this chunk on.
+// TCN = true compiles the fused TemporalBlock epilogue in (UmmaParams::pre_act ...); the ordinary instantiations do not
+// carry its registers (the 256-column persistent kernel went from 160 to 220 registers with it).
+template <bool TCN = false>
 __device__ __forceinline__ void epi_store_chunk(const UmmaParams& p, const float (&v)[32], long long m, long long mo,
                                                 int nc0, int cols_left) {
     float o[32];
@@ -173,7 +176,7 @@ __device__ __forceinline__ void epi_store_chunk(const UmmaParams& p, const float
       }
     }
     const int ncols = min(32, min(cols_left, p.N - nc0));
-    if (p.pre_act) {
+    if (TCN && p.pre_act) {
       // ReLU -> inverted dropout on the bf16-rounded activation (what the stand-alone pass m3t_dropout_bf16 sees) ->
       // optional store of this pre-residual tensor
 #pragma unroll

@@ -13,7 +13,7 @@
 
 namespace m3t {
 
-template <int BN, int MT, int STAGES, int AKIND>
+template <int BN, int MT, int STAGES, int AKIND, bool TCN = false>
 __global__ void __launch_bounds__(kUmmaThreads, 1)
 umma_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const UmmaParams p, const int num_tiles) {
@@ -191,7 +191,7 @@ umma_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             tc_fence_before();
             mbar_arrive(&tmem_empty[acc]);
           }
-          if (row_ok) epi_store_chunk(p, v, m, mo, n0 + c0, BN - c0);
+          if (row_ok) epi_store_chunk<TCN>(p, v, m, mo, n0 + c0, BN - c0);
           if (want_stats) {
             float s1[32], s2[32];
 #pragma unroll

@@ -1950,7 +1950,7 @@ def case_prepack(seed=0):
     from m3t_b200.models.resnet import BasicBlock, ResNet
     torch.manual_seed(seed)
     m = ResNet(BasicBlock, [2, 2, 2, 2], 512, zero_init_residual=False, agg_mode="ap", fmap_out_size=3).cuda().train()
-    x = torch.randn(4, 64, 28, 28, device="cuda")
+    x = torch.randn(32, 64, 28, 28, device="cuda")
     ops.clear_caches()
     ops._prepack_wish.clear()
     m(x).square().mean().backward()              # records which filters / parity sub-filters the model asks for
@@ -1975,12 +1975,20 @@ def case_prepack(seed=0):
                 bad += float((a.reshape(-1).view(torch.int16) != b.reshape(-1).view(torch.int16)).sum())
     errs = {"prepack_exact": bad, "prepack_missing": 0.0 if (n == 19 and seen >= 40) else 1.0}
     errs["info"] = {"filters": n, "tensors_compared": seen}
-    # and the model gives the same gradients with the pre-packed cache (cache hits) as without
-    g0 = [p.grad.clone() for p in m.parameters() if p.grad is not None]
-    m.zero_grad(set_to_none=True)
-    m(x).square().mean().backward()
-    g1 = [p.grad for p in m.parameters() if p.grad is not None]
-    errs["prepack_grad_l2"] = max(_l2(a, b) for a, b in zip(g1, g0))
+    # and the model gives the same gradients with the pre-packed cache (cache hits) as with per-filter packs; the
+    # yardstick is the run-to-run distance of two per-filter runs (train-mode BN statistics use fp32 atomics)
+    def grads(prepacked):
+        ops.clear_caches()
+        if prepacked:
+            ops.prepack({id(p) for p in m.parameters()})
+        m.zero_grad(set_to_none=True)
+        m(x).square().mean().backward()
+        return [p.grad.clone() for p in m.parameters() if p.grad is not None]
+
+    g0, g0b, g1 = grads(False), grads(False), grads(True)
+    noise = max(_l2(a, b) for a, b in zip(g0b, g0))
+    errs["prepack_grad_l2"] = max(0.0, max(_l2(a, b) for a, b in zip(g1, g0)) - 3.0 * noise)
+    errs["info"]["run_to_run_grad_l2"] = noise
     return errs
 
 
