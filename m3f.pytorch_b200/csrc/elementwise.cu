@@ -961,11 +961,17 @@ __global__ void pack_filter_kernel(const float* __restrict__ w, __nv_bfloat16* _
 // master [Cout][Cin][taps] write the fprop pack, the flipped dgrad pack and - for stride-2 convolutions whose data
 // gradient runs as parity sub-convolutions - the sub-filter of the output parity that tap t belongs to.
 __global__ void pack_filters_batched_kernel(const m3t_pack_entry* __restrict__ tab, int n, long long total) {
+  // Work item g in [0, 2*total): the first half walks the FPROP pack in destination order (consecutive threads write
+  // consecutive input channels), the second half the DGRAD pack in destination order (consecutive output channels) and
+  // with it the parity sub-filter the tap belongs to: every store is coalesced, the gathers hit L1 / L2 (the fp32
+  // masters of a ResNet-18 are 45 MB, L2-resident).  The element-order version spent 0.19 ms on scattered 2-byte stores.
   __shared__ long long starts[129];
   for (int i = threadIdx.x; i <= n && i <= 128; i += blockDim.x) starts[i] = i < n ? tab[i].start : total;
   __syncthreads();
-  for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < total;
-       g += (long long)gridDim.x * blockDim.x) {
+  for (long long g2 = blockIdx.x * (long long)blockDim.x + threadIdx.x; g2 < 2 * total;
+       g2 += (long long)gridDim.x * blockDim.x) {
+    const bool second = g2 >= total;
+    const long long g = second ? g2 - total : g2;
     int lo = 0, hi = n - 1;
     while (lo < hi) {                       // last entry with start <= g
       const int mid = (lo + hi + 1) >> 1;
@@ -974,17 +980,27 @@ __global__ void pack_filters_batched_kernel(const m3t_pack_entry* __restrict__ t
     const m3t_pack_entry& e = tab[lo];
     const long long i = g - e.start;
     const int taps = e.taps, Cin = e.Cin, Cout = e.Cout;
-    const int t = (int)(i % taps);
-    long long r = i / taps;
-    const int ci = (int)(r % Cin);
-    const int co = (int)(r / Cin);
-    const __nv_bfloat16 v = __float2bfloat16(reinterpret_cast<const float*>(e.src)[i]);
-    if (e.wf) reinterpret_cast<__nv_bfloat16*>(e.wf)[((long long)co * taps + t) * Cin + ci] = v;
-    if (e.wd) reinterpret_cast<__nv_bfloat16*>(e.wd)[((long long)ci * taps + (taps - 1 - t)) * Cout + co] = v;
-    if (e.has_parity) {
-      const int p = e.par_of_tap[t];
-      if (p >= 0)
-        reinterpret_cast<__nv_bfloat16*>(e.par[p])[((long long)ci * e.ntaps_par[p] + e.pos_of_tap[t]) * Cout + co] = v;
+    const float* src = reinterpret_cast<const float*>(e.src);
+    if (!second) {
+      if (!e.wf) continue;
+      const int ci = (int)(i % Cin);
+      long long r = i / Cin;
+      const int t = (int)(r % taps);
+      const int co = (int)(r / taps);
+      reinterpret_cast<__nv_bfloat16*>(e.wf)[i] = __float2bfloat16(src[((long long)co * Cin + ci) * taps + t]);
+    } else {
+      const int co = (int)(i % Cout);
+      long long r = i / Cout;
+      const int tf = (int)(r % taps);       // flipped tap index of the dgrad pack
+      const int ci = (int)(r / taps);
+      const int t = taps - 1 - tf;
+      const __nv_bfloat16 v = __float2bfloat16(src[((long long)co * Cin + ci) * taps + t]);
+      if (e.wd) reinterpret_cast<__nv_bfloat16*>(e.wd)[i] = v;
+      if (e.has_parity) {
+        const int p = e.par_of_tap[t];
+        if (p >= 0)
+          reinterpret_cast<__nv_bfloat16*>(e.par[p])[((long long)ci * e.ntaps_par[p] + e.pos_of_tap[t]) * Cout + co] = v;
+      }
     }
   }
 }
@@ -1509,7 +1525,7 @@ extern "C" int m3t_pack_filter(const float* w, void* w_fprop, void* w_dgrad, int
 
 extern "C" int m3t_pack_filters_batched(const m3t_pack_entry* table_dev, int n, long long total, void* stream) {
   if (n <= 0 || n > 128 || total <= 0) return -1;
-  pack_filters_batched_kernel<<<ew_blocks(total), kEwThreads, 0, ST(stream)>>>(table_dev, n, total);
+  pack_filters_batched_kernel<<<ew_blocks(2 * total), kEwThreads, 0, ST(stream)>>>(table_dev, n, total);
   count_launch();
   return launch_status();
 }
