@@ -3,8 +3,9 @@ hooks (training / validation / test steps and their `*_end` aggregation, optimis
 dataloaders, argparse surface), so the reference's train.py / eval.py drive it unchanged through `m3t_b200.run`
 (SURVEY 8(f) N1).  The base class is `m3t_b200.lightning.LightningModule` (pytorch_lightning 0.6 is not installable).
 
-Only the hot-path configurations are built: modality in {audio, visual, audiovisual}, backbone in {resnet, v2p,
-v2p_split}, fusion_type in {concat, attention}.
+Every configuration of the reference's constructor is built: modality in {audio, visual, audiovisual}, backbone in
+{resnet, v2p, v2p_split, densenet, vggface}, fusion_type in {concat, attention, att_dec}; the hot path (BASELINE
+configs) is resnet / v2p_split + attention.
 """
 import os
 import sys
