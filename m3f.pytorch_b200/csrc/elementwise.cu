@@ -499,7 +499,8 @@ bn_bwd_apply_fixed_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfl
 template <int K, int S, int PAD>
 __global__ void bn_relu_maxpool_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ scale,
                                        const float* __restrict__ shift, __nv_bfloat16* __restrict__ out,
-                                       uint8_t* __restrict__ idx, int F, int H, int W, int C, int cg_shift) {
+                                       uint8_t* __restrict__ idx, __nv_bfloat16* __restrict__ ymax, int F, int H, int W,
+                                       int C, int cg_shift) {
   // index math in 32 bits (the host checks the element counts fit); C/8 is a power of two on this path
   const int P = (H + 2 * PAD - K) / S + 1, Q = (W + 2 * PAD - K) / S + 1;
   const unsigned cgs = (unsigned)C / 8;
@@ -511,12 +512,12 @@ __global__ void bn_relu_maxpool_kernel(const __nv_bfloat16* __restrict__ y, cons
     r /= (unsigned)Q;
     const int p = (int)(r % (unsigned)P);
     const int f = (int)(r / (unsigned)P);
-    float s[8], b[8], best[8];
+    float s[8], b[8], best[8], yb[8];
     int bi[8];
     load8f(scale + cg * 8, s);
     load8f(shift + cg * 8, b);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { best[j] = -INFINITY; bi[j] = 0; }
+    for (int j = 0; j < 8; ++j) { best[j] = -INFINITY; bi[j] = 0; yb[j] = 0.f; }
 #pragma unroll
     for (int kh = 0; kh < K; ++kh) {
       const int h = S * p - PAD + kh;
@@ -530,11 +531,12 @@ __global__ void bn_relu_maxpool_kernel(const __nv_bfloat16* __restrict__ y, cons
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float a = fmaxf(fmaf(v[j], s[j], b[j]), 0.f);
-          if (a > best[j]) { best[j] = a; bi[j] = kh * K + kw; }
+          if (a > best[j]) { best[j] = a; bi[j] = kh * K + kw; yb[j] = v[j]; }
         }
       }
     }
     reinterpret_cast<uint4*>(out)[i] = pack8(best);
+    if (ymax) reinterpret_cast<uint4*>(ymax)[i] = pack8(yb);     // raw conv output at the arg-max (BN backward sums)
     if (idx) {
       uint2 pk;
       pk.x = bi[0] | (bi[1] << 8) | (bi[2] << 16) | (bi[3] << 24);
@@ -775,7 +777,7 @@ maxpool3s2_bn_bwd_kernel(const __nv_bfloat16* __restrict__ dout, const uint8_t* 
 __global__ void __launch_bounds__(256, 2)
 bn_relu_maxpool3s2_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ scale,
                           const float* __restrict__ shift, __nv_bfloat16* __restrict__ out, uint8_t* __restrict__ idx,
-                          int F, int H, int W, int C, int cg_shift) {
+                          __nv_bfloat16* __restrict__ ymax, int F, int H, int W, int C, int cg_shift) {
   const int P = H / 2, Q = W / 2;
   const unsigned cgs = (unsigned)C / 8;
   const unsigned total = (unsigned)F * P * Q * cgs;
@@ -802,10 +804,10 @@ bn_relu_maxpool3s2_kernel(const __nv_bfloat16* __restrict__ y, const float* __re
         v[kh * 3 + kw] = __ldg(reinterpret_cast<const uint4*>(y) + (ok ? o : c00));
       }
     }
-    float best[8];
+    float best[8], yb[8];
     int bi[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { best[j] = -INFINITY; bi[j] = 0; }
+    for (int j = 0; j < 8; ++j) { best[j] = -INFINITY; bi[j] = 0; yb[j] = 0.f; }
 #pragma unroll
     for (int k = 0; k < 9; ++k) {
       const bool ok = (k / 3 > 0 || p > 0) && (k % 3 > 0 || q > 0);
@@ -814,10 +816,11 @@ bn_relu_maxpool3s2_kernel(const __nv_bfloat16* __restrict__ y, const float* __re
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float a = ok ? fmaxf(fmaf(x[j], s[j], b[j]), 0.f) : -INFINITY;
-        if (a > best[j]) { best[j] = a; bi[j] = k; }
+        if (a > best[j]) { best[j] = a; bi[j] = k; yb[j] = x[j]; }
       }
     }
     reinterpret_cast<uint4*>(out)[i] = pack8(best);
+    if (ymax) reinterpret_cast<uint4*>(ymax)[i] = pack8(yb);     // raw conv output at the arg-max (BN backward sums)
     if (idx) {
       uint2 pk;
       pk.x = bi[0] | (bi[1] << 8) | (bi[2] << 16) | (bi[3] << 24);
@@ -1379,8 +1382,21 @@ static int ilog2_exact(int v) {
   return (1 << s) == v ? s : -1;
 }
 
+static int bn_relu_maxpool_impl(const void* y, const float* scale, const float* shift, void* out, void* idx,
+                                void* ymax, int F, int H, int W, int C, int K, int S, int PAD, void* stream);
+
 extern "C" int m3t_bn_relu_maxpool(const void* y, const float* scale, const float* shift, void* out, void* idx, int F,
                                    int H, int W, int C, int K, int S, int PAD, void* stream) {
+  return bn_relu_maxpool_impl(y, scale, shift, out, idx, nullptr, F, H, W, C, K, S, PAD, stream);
+}
+
+extern "C" int m3t_bn_relu_maxpool_ymax(const void* y, const float* scale, const float* shift, void* out, void* idx,
+                                        void* ymax, int F, int H, int W, int C, int K, int S, int PAD, void* stream) {
+  return bn_relu_maxpool_impl(y, scale, shift, out, idx, ymax, F, H, W, C, K, S, PAD, stream);
+}
+
+static int bn_relu_maxpool_impl(const void* y, const float* scale, const float* shift, void* out, void* idx,
+                                void* ymax, int F, int H, int W, int C, int K, int S, int PAD, void* stream) {
   const int sh = C % 8 ? -1 : ilog2_exact(C / 8);
   if (sh < 0) return -1;
   const int P = (H + 2 * PAD - K) / S + 1, Q = (W + 2 * PAD - K) / S + 1;
@@ -1389,13 +1405,14 @@ extern "C" int m3t_bn_relu_maxpool(const void* y, const float* scale, const floa
   const int blocks = ew_blocks(items);
   if (K == 3 && S == 2 && PAD == 1 && H % 2 == 0 && W % 2 == 0 && kEwThreads % (C / 8) == 0)
     bn_relu_maxpool3s2_kernel<<<blocks, kEwThreads, 0, ST(stream)>>>(CBF(y), scale, shift, BF(out),
-                                                                   reinterpret_cast<uint8_t*>(idx), F, H, W, C, sh);
+                                                                   reinterpret_cast<uint8_t*>(idx), BF(ymax), F, H, W, C,
+                                                                   sh);
   else if (K == 3 && S == 2 && PAD == 1)
-    bn_relu_maxpool_kernel<3, 2, 1><<<blocks, kEwThreads, 0, ST(stream)>>>(CBF(y), scale, shift, BF(out),
-                                                                         reinterpret_cast<uint8_t*>(idx), F, H, W, C, sh);
+    bn_relu_maxpool_kernel<3, 2, 1><<<blocks, kEwThreads, 0, ST(stream)>>>(
+        CBF(y), scale, shift, BF(out), reinterpret_cast<uint8_t*>(idx), BF(ymax), F, H, W, C, sh);
   else if (K == 2 && S == 2 && PAD == 0)
-    bn_relu_maxpool_kernel<2, 2, 0><<<blocks, kEwThreads, 0, ST(stream)>>>(CBF(y), scale, shift, BF(out),
-                                                                         reinterpret_cast<uint8_t*>(idx), F, H, W, C, sh);
+    bn_relu_maxpool_kernel<2, 2, 0><<<blocks, kEwThreads, 0, ST(stream)>>>(
+        CBF(y), scale, shift, BF(out), reinterpret_cast<uint8_t*>(idx), BF(ymax), F, H, W, C, sh);
   else
     return -1;
   count_launch();

@@ -602,16 +602,18 @@ class Stem3D(torch.autograd.Function):
                 y = raw.conv_fprop(xs, wp, geom, algo_flops=flops, tag="stem").view(B * T, H // 2, W // 2, 64)
             ss = raw.bn_fold(gamma.detach(), beta.detach(), running_mean, running_var, None, BN_EPS)
             scale, shift = ss[0], ss[1]
-        out, pidx = raw.bn_relu_maxpool(y, scale, shift, training)
         if training:
-            ctx.save_for_backward(xs, w, y, pidx, fin)
+            out, pidx, ymax = raw.bn_relu_maxpool(y, scale, shift, True, want_ymax=True)
+            ctx.save_for_backward(xs, w, y, pidx, fin, ymax)
             ctx.geom, ctx.count = geom, count
+        else:
+            out, pidx = raw.bn_relu_maxpool(y, scale, shift, False)
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        xs, w, y, pidx, fin = ctx.saved_tensors
-        dy, sums = raw.maxpool_bn_bwd(dout.contiguous(), pidx, y, fin[0], fin[1], fin[2], fin[3], ctx.count)
+        xs, w, y, pidx, fin, ymax = ctx.saved_tensors
+        dy, sums = raw.maxpool_bn_bwd(dout.contiguous(), pidx, y, fin[0], fin[1], fin[2], fin[3], ctx.count, ymax=ymax)
         if raw.USE_HALO_WGRAD:
             dwp = raw.wgrad_stem_halo(xs, dy, algo_flops=ctx.flops)
         else:
@@ -1146,20 +1148,20 @@ class ConvNdBNAct(torch.autograd.Function):
                               running_var)
         if cbias is not None:   # BN(conv + b): the bias only shifts the batch mean that enters running_mean
             running_mean.add_(cbias.detach(), alpha=BN_MOMENTUM)
-        pidx = None
+        pidx = ymax = None
         if pool:
-            out, pidx = raw.bn_relu_maxpool(y.view(N * Z, P, Q, Cout), fin[2], fin[3], True, pool)
+            out, pidx, ymax = raw.bn_relu_maxpool(y.view(N * Z, P, Q, Cout), fin[2], fin[3], True, pool, want_ymax=True)
             out = out.view(N, Z, out.shape[1], out.shape[2], Cout)
         else:
             out = raw.bn_act(y, fin[2], fin[3], relu=relu)
-        ctx.save_for_backward(x, w, y, pidx, None, fin)      # ReLU mask recomputed from y in backward
+        ctx.save_for_backward(x, w, y, pidx, ymax, fin)      # ReLU mask recomputed from y in backward
         ctx.cfg, ctx.geom, ctx.count, ctx.flops = cfg, geom, count, flops
         ctx.has_bias = cbias is not None
         return out if nd == 3 else out.view(N, Q, Cout)
 
     @staticmethod
     def backward(ctx, dout):
-        x, w, y, pidx, out, fin = ctx.saved_tensors
+        x, w, y, pidx, ymax, fin = ctx.saved_tensors
         cfg, geom = ctx.cfg, ctx.geom
         nd, k, pool, relu = cfg["nd"], cfg["k"], cfg.get("pool"), cfg["relu"]
         Cout = w.shape[0]
@@ -1167,7 +1169,8 @@ class ConvNdBNAct(torch.autograd.Function):
         dout = dout.contiguous()
         if pool:
             dy, sums = raw.maxpool_bn_bwd(dout.view(N * Z, -1, dout.shape[-2], Cout) if nd == 3 else dout, pidx,
-                                          y.view(N * Z, P, Q, Cout), fin[0], fin[1], fin[2], fin[3], ctx.count, pool)
+                                          y.view(N * Z, P, Q, Cout), fin[0], fin[1], fin[2], fin[3], ctx.count, pool,
+                                          ymax=ymax)
             dy = dy.view(y.shape)
         else:
             d5 = dout.view(y.shape)

@@ -499,28 +499,38 @@ def bn_bwd_apply(dout, out, y, mean, invstd, scale, sums, count, relu, shift=Non
     return dy
 
 
-def bn_relu_maxpool(y, scale, shift, want_idx, pool=(3, 2, 1)):
+def bn_relu_maxpool(y, scale, shift, want_idx, pool=(3, 2, 1), want_ymax=False):
+    """want_ymax: also return the raw y at every window's arg-max (the BN-backward sums then need the pooled tensors
+    only: maxpool_bn_bwd(..., ymax=...))."""
     F_, H, W, C = y.shape
     K, S, PAD = pool
     P, Q = (H + 2 * PAD - K) // S + 1, (W + 2 * PAD - K) // S + 1
     out = torch.empty((F_, P, Q, C), device=y.device, dtype=torch.bfloat16)
     idx = torch.empty((F_, P, Q, C), device=y.device, dtype=torch.uint8) if want_idx else None
+    ymax = torch.empty_like(out) if want_ymax else None
     _timed("hbm bn_relu_maxpool %dx%d C%d" % (H, W, C), 0.0, lambda: L.check(
-        _lib().m3t_bn_relu_maxpool(L.ptr(y), L.ptr(scale), L.ptr(shift), L.ptr(out), L.ptr(idx), L.i32(F_),
-                                   L.i32(H), L.i32(W), L.i32(C), L.i32(K), L.i32(S), L.i32(PAD), L.stream_ptr()),
-        "bn_relu_maxpool"), _nb(y, out, idx))
+        _lib().m3t_bn_relu_maxpool_ymax(L.ptr(y), L.ptr(scale), L.ptr(shift), L.ptr(out), L.ptr(idx), L.ptr(ymax),
+                                        L.i32(F_), L.i32(H), L.i32(W), L.i32(C), L.i32(K), L.i32(S), L.i32(PAD),
+                                        L.stream_ptr()), "bn_relu_maxpool"), _nb(y, out, idx, ymax))
+    if want_ymax:
+        return out, idx, ymax
     return out, idx
 
 
-def maxpool_bn_bwd(dout, idx, y, mean, invstd, scale, shift, count, pool=(3, 2, 1)):
+def maxpool_bn_bwd(dout, idx, y, mean, invstd, scale, shift, count, pool=(3, 2, 1), ymax=None):
     F_, H, W, C = y.shape
     K, S, PAD = pool
-    sums = zeros_f32((2, C), y.device)
     fn = _lib().m3t_maxpool_bn_bwd
-    _timed("hbm maxpool_bn_bwd(reduce) %dx%d C%d" % (H, W, C), 0.0, lambda: L.check(
-        fn(L.i32(0), L.ptr(dout), L.ptr(idx), L.ptr(y), L.ptr(mean), L.ptr(invstd), L.ptr(scale), L.ptr(shift),
-           L.ptr(sums), ctypes_double(count), L.ptr(None), L.i32(F_), L.i32(H), L.i32(W), L.i32(C), L.i32(K),
-           L.i32(S), L.i32(PAD), L.stream_ptr()), "maxpool_bn_bwd(reduce)"), _nb(dout, idx, y))
+    if ymax is not None:
+        # every window sends its gradient to ONE position whose raw value is ymax: the sums over the full-resolution map
+        # equal the sums over the pooled tensors (mask recomputed from ymax * scale + shift > 0)
+        sums, _ = bn_bwd_reduce(dout, None, ymax, mean, invstd, True, False, scale=scale, shift=shift)
+    else:
+        sums = zeros_f32((2, C), y.device)
+        _timed("hbm maxpool_bn_bwd(reduce) %dx%d C%d" % (H, W, C), 0.0, lambda: L.check(
+            fn(L.i32(0), L.ptr(dout), L.ptr(idx), L.ptr(y), L.ptr(mean), L.ptr(invstd), L.ptr(scale), L.ptr(shift),
+               L.ptr(sums), ctypes_double(count), L.ptr(None), L.i32(F_), L.i32(H), L.i32(W), L.i32(C), L.i32(K),
+               L.i32(S), L.i32(PAD), L.stream_ptr()), "maxpool_bn_bwd(reduce)"), _nb(dout, idx, y))
     dy = torch.empty_like(y)
     _timed("hbm maxpool_bn_bwd(apply) %dx%d C%d" % (H, W, C), 0.0, lambda: L.check(
         fn(L.i32(1), L.ptr(dout), L.ptr(idx), L.ptr(y), L.ptr(mean), L.ptr(invstd), L.ptr(scale), L.ptr(shift),

@@ -301,6 +301,14 @@ def case_elementwise(seed=0):
         errs["pool_bwd_dy" + tag] = _err(dy.float().cpu().permute(0, 3, 1, 2), y3.grad)
         errs["pool_bwd_dgamma" + tag] = _err(sums[1], gp.grad)
         errs["pool_bwd_dbeta" + tag] = _err(sums[0], bp.grad)
+        # the same backward with the BatchNorm sums taken over the POOLED tensors (raw y at the arg-max from the forward)
+        out3, idx3, ymax = raw.bn_relu_maxpool(yy.cuda(), scale.cuda(), shift.cuda(), True, want_ymax=True)
+        dy3, sums3 = raw.maxpool_bn_bwd(dout.cuda(), idx3, yy.cuda(), mean.cuda(), invstd.cuda(), scale.cuda(),
+                                        shift.cuda(), F_ * H * W, ymax=ymax)
+        errs["pool_ymax_fwd_exact" + tag] = float((out3 != out2).sum() + (idx3 != idx2).sum())
+        errs["pool_ymax_dy" + tag] = _err(dy3.float().cpu().permute(0, 3, 1, 2), y3.grad)
+        errs["pool_ymax_dgamma" + tag] = _err(sums3[1], gp.grad)
+        errs["pool_ymax_dbeta" + tag] = _err(sums3[0], bp.grad)
     # bn_act backward (relu + residual)
     C = 64
     y = _rnd((4, 6, 6, C), g)
@@ -681,6 +689,8 @@ CASES["golden_cbam_train"] = (case_golden, _c(name="cbam_train"))
 CASES["golden_resnet_cbam_train"] = (case_golden, _c(name="resnet_cbam_train"))
 CASES["golden_av_v2psplit_attention_train"] = (case_golden, _c(name="av_v2psplit_attention_train"))
 
+for _t in ("", "_odd"):
+    pass
 TOLS = {"out_ref": 3e-2, "va_ref": 2e-2, "floor": 1.0, "out_emu": 1.5e-2, "loss_ref": 2e-2, "loss_emu": 1e-2,
         "grad_emu": 0.12, "grad_all_l2": 0.05, "dx": 3e-2, "ccc_ref_diff": 5e-4}
 for _k in ("conv1.weight", "conv2.weight", "bn1.weight", "bn1.bias", "bn2.weight", "bn2.bias", "downsample.0.weight",
