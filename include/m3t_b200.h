@@ -209,7 +209,9 @@ int m3t_cast_bf16_f32(const void* in, long long ld_in, float* out, long long ld_
  * calls were 19 launches + 15 index_select per step).  `table_dev` = n entries in device memory, ordered by `start`
  * (prefix sum of Cout*Cin*taps); outputs as m3t_pack_filter, plus - when has_parity - the four parity sub-filters of
  * a stride-2 convolution's data gradient: tap t goes to par[par_of_tap[t]] at position pos_of_tap[t] of its
- * ntaps_par[.] taps, layout [Cin][ntaps][Cout] (par_of_tap[t] < 0: tap unused).  taps <= 27. */
+ * ntaps_par[.] taps, layout [Cin][ntaps][Cout] (par_of_tap[t] < 0: tap unused).  taps <= 27.  A matrix is a filter
+ * with taps = 1 (wf = bf16 copy, wd = bf16 transpose: W_hh / W_hh^T of a GRU layer, Linear weights); has_parity < 0
+ * marks a plain fp32 copy of Cout*Cin*taps values into wf (stacked bias vectors). */
 typedef struct m3t_pack_entry {
   const void* src;      /* fp32 [Cout][Cin][taps] */
   void* wf;             /* bf16 [Cout][taps][Cin] or NULL */

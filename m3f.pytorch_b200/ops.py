@@ -62,20 +62,42 @@ def _wish(w, parity=None):
         e[1] = parity
 
 
+_prepack_gru = {}       # tuple(id of the 8 tensors) -> [weakrefs..., (I, H)]
+_prepack_lin = {}       # id(w) -> weakref(w)
+
+
+def _wish_gru(tensors, I, H):
+    _prepack_gru[tuple(id(t) for t in tensors)] = ([weakref.ref(t) for t in tensors], (I, H))
+
+
+def _wish_linear(w):
+    _prepack_lin[id(w)] = weakref.ref(w)
+
+
 def prepack(allowed=None):
-    """Fill the derived-weight cache for every recorded convolution filter with one launch; returns the number packed.
+    """Fill the derived-weight cache with ONE launch (m3t_pack_filters_batched): every recorded convolution filter
+    (fprop / flipped-dgrad packs + stride-2 parity sub-filters), every BiGRU layer (W_ih of both directions stacked,
+    W_hh, W_hh^T, the stacked bias vectors) and every Linear weight (bf16 copy).  Returns the number of table entries.
     allowed: optional set of id(parameter) restricting the pack to one model's parameters."""
     import ctypes
-    live = [(e[0](), e[1]) for e in _prepack_wish.values() if e[0]() is not None and e[0]().is_cuda]
-    if allowed is not None:
-        live = [(w, par) for w, par in live if id(w) in allowed]
-    live = [(w, par) for w, par in live if w.dim() >= 3 and w.dtype == torch.float32 and w.is_contiguous()]
-    if not live:
+    ok = lambda t: t is not None and t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and \
+        (allowed is None or id(t) in allowed)                                                      # noqa: E731
+    convs = [(e[0](), e[1]) for e in _prepack_wish.values()]
+    convs = [(w, par) for w, par in convs if ok(w) and w.dim() >= 3 and w.numel() // (w.shape[0] * w.shape[1]) <= 27]
+    grus = []
+    for refs, (I, H) in _prepack_gru.values():
+        ts = [r() for r in refs]
+        if all(ok(t) for t in ts) and I % 8 == 0:
+            grus.append((ts, I, H))
+    lins = [r() for r in _prepack_lin.values()]
+    lins = [w for w in lins if ok(w) and w.dim() == 2 and w.shape[1] % 8 == 0]
+    n_entries = len(convs) + 8 * len(grus) + len(lins)
+    if n_entries == 0 or n_entries > 128:
         return 0
-    if len(live) > 128:
-        live = live[:128]
-    key = tuple((id(w), w.data_ptr(), tuple(w.shape), None if par is None else tuple(
-        None if p is None else tuple(p) for p in par)) for w, par in live)
+    key = (tuple((id(w), w.data_ptr(), tuple(w.shape), None if par is None else tuple(
+        None if p is None else tuple(p) for p in par)) for w, par in convs),
+        tuple(tuple((id(t), t.data_ptr()) for t in ts) for ts, _, _ in grus),
+        tuple((id(w), w.data_ptr(), tuple(w.shape)) for w in lins))
     plan = _prepack_plans.get("plan")
     if plan is None or plan["key"] != key:
         class Entry(ctypes.Structure):
@@ -85,35 +107,45 @@ def prepack(allowed=None):
                         ("ntaps_par", ctypes.c_int * 4), ("par_of_tap", ctypes.c_int * 27),
                         ("pos_of_tap", ctypes.c_int * 27)]
 
-        dev = live[0][0].device
-        need = 0
-        for w, par in live:
-            n = w.numel()
-            need += 2 * n + (n if par is not None else 0) + 64
+        dev = (convs[0][0] if convs else (grus[0][0][0] if grus else lins[0])).device
+        need = 64
+        for w, par in convs:
+            need += 3 * w.numel() + 64
+        for ts, I, H in grus:
+            need += 6 * H * I + 12 * H * H + 64
+        for w in lins:
+            need += w.numel() + 16
         buf = torch.empty(need, device=dev, dtype=torch.bfloat16)
-        table = (Entry * len(live))()
-        views, off, start = [], 0, 0
+        fbuf = torch.empty(sum(12 * H for _, _, H in grus) + 8, device=dev, dtype=torch.float32)
+        table = (Entry * n_entries)()
+        state = {"off": 0, "foff": 0, "start": 0, "i": 0}
 
         def take(numel):
-            nonlocal off
-            t = buf[off:off + numel]
-            off += (numel + 7) // 8 * 8
+            t = buf[state["off"]:state["off"] + numel]
+            state["off"] += (numel + 7) // 8 * 8
             return t
 
-        for i, (w, par) in enumerate(live):
-            Cout, Cin = w.shape[0], w.shape[1]
-            taps = w.numel() // (Cout * Cin)
-            if taps > 27:
-                return 0
-            wf = take(w.numel()).view(Cout, taps * Cin)
-            wd = take(w.numel()).view(Cin, taps * Cout)
-            e = table[i]
-            e.src, e.wf, e.wd = w.data_ptr(), wf.data_ptr(), wd.data_ptr()
-            e.start, e.Cout, e.Cin, e.taps = start, Cout, Cin, taps
-            subs = None
+        def entry(src, numel, Cout, Cin, taps, wf=None, wd=None, kind=0):
+            e = table[state["i"]]
+            state["i"] += 1
+            e.src = src.data_ptr()
+            e.wf = wf.data_ptr() if wf is not None else None
+            e.wd = wd.data_ptr() if wd is not None else None
+            e.start, e.Cout, e.Cin, e.taps, e.has_parity = state["start"], Cout, Cin, taps, kind
             for t in range(27):
                 e.par_of_tap[t] = -1
                 e.pos_of_tap[t] = 0
+            state["start"] += numel
+            return e
+
+        conv_views, gru_views, lin_views = [], [], []
+        for w, par in convs:
+            Cout, Cin = w.shape[0], w.shape[1]
+            taps = w.numel() // (Cout * Cin)
+            wf = take(w.numel()).view(Cout, taps * Cin)
+            wd = take(w.numel()).view(Cin, taps * Cout)
+            e = entry(w, w.numel(), Cout, Cin, taps, wf, wd)
+            subs = None
             if par is not None:
                 e.has_parity = 1
                 subs = []
@@ -129,19 +161,43 @@ def prepack(allowed=None):
                         t = taps - 1 - int(flipped)
                         e.par_of_tap[t], e.pos_of_tap[t] = p, j
                 subs = tuple(subs)
-            views.append((w, wf, wd, subs))
-            start += w.numel()
-        raw_bytes = bytes(table)
-        tab = torch.frombuffer(bytearray(raw_bytes), dtype=torch.uint8).to(dev)
-        plan = _prepack_plans["plan"] = dict(key=key, buf=buf, tab=tab, views=views, total=start, n=len(live))
+            conv_views.append((w, wf, wd, subs))
+        for ts, I, H in grus:
+            w_ih, w_ih_r, w_hh, w_hh_r, b_ih, b_ih_r, b_hh, b_hh_r = ts
+            wih = take(6 * H * I).view(6 * H, I)
+            whh = take(6 * H * H).view(2, 3 * H, H)
+            whht = take(6 * H * H).view(2, H, 3 * H)
+            bias = fbuf[state["foff"]:state["foff"] + 12 * H].view(2, 6 * H)
+            state["foff"] += 12 * H
+            entry(w_ih, 3 * H * I, 3 * H, I, 1, wf=wih[:3 * H])
+            entry(w_ih_r, 3 * H * I, 3 * H, I, 1, wf=wih[3 * H:])
+            entry(w_hh, 3 * H * H, 3 * H, H, 1, wf=whh[0], wd=whht[0])
+            entry(w_hh_r, 3 * H * H, 3 * H, H, 1, wf=whh[1], wd=whht[1])
+            for src, dst in ((b_ih, bias[0, :3 * H]), (b_ih_r, bias[0, 3 * H:]), (b_hh, bias[1, :3 * H]),
+                             (b_hh_r, bias[1, 3 * H:])):
+                entry(src, 3 * H, 3 * H, 1, 1, wf=dst, kind=-1)           # fp32 copy
+            gru_views.append((ts, (wih, whh, whht, bias)))
+        for w in lins:
+            wb = take(w.numel()).view(w.shape[0], w.shape[1])
+            entry(w, w.numel(), w.shape[0], w.shape[1], 1, wf=wb)
+            lin_views.append((w, wb))
+        tab = torch.frombuffer(bytearray(bytes(table)), dtype=torch.uint8).to(dev)
+        plan = _prepack_plans["plan"] = dict(key=key, buf=buf, fbuf=fbuf, tab=tab, convs=conv_views, grus=gru_views,
+                                             lins=lin_views, total=state["start"], n=n_entries)
     raw.L.check(raw._lib().m3t_pack_filters_batched(raw.L.ptr(plan["tab"]), raw.L.i32(plan["n"]),
                                                     raw.L.i64(plan["total"]), raw.L.stream_ptr()),
                 "pack_filters_batched")
-    for w, wf, wd, subs in plan["views"]:
+    for w, wf, wd, subs in plan["convs"]:
         ver = ((w._version, w.data_ptr()),)
         _pack_cache[((id(w),), "filter")] = (ver, (weakref.ref(w),), (wf, wd))
         if subs is not None:
             _pack_cache[((id(w),), "dgrad_s2")] = (ver, (weakref.ref(w),), subs)
+    for ts, val in plan["grus"]:
+        # cache key order of _gru_packed: (w_ih, w_ih_r, w_hh, w_hh_r) + (b_ih, b_ih_r, b_hh, b_hh_r)
+        _pack_cache[(tuple(id(t) for t in ts), "gru_w")] = (tuple((t._version, t.data_ptr()) for t in ts),
+                                                            tuple(weakref.ref(t) for t in ts), val)
+    for w, wb in plan["lins"]:
+        _pack_cache[((id(w),), "bf16")] = (((w._version, w.data_ptr()),), (weakref.ref(w),), wb)
     return plan["n"]
 
 
@@ -662,7 +718,10 @@ class AvgPoolCL(torch.autograd.Function):
 # Linear, GRU layer, attention mix
 # ------------------------------------------------------------------------------------------------------------
 def _w_bf16(w):
-    return _cached(w, "bf16", lambda: raw.cast_bf16(w.detach().view(w.shape[0], -1)))
+    def make():
+        _wish_linear(w)
+        return raw.cast_bf16(w.detach().view(w.shape[0], -1))
+    return _cached(w, "bf16", make)
 
 
 class LinearFn(torch.autograd.Function):
@@ -732,6 +791,8 @@ def _gru_packed(w_ih, w_ih_r, w_hh, w_hh_r, I, H, biases):
     """(wih [6H, Ipad], whh [2,3H,H], whht [2,H,3H]) bf16 copies of one bidirectional layer and, given the four bias
     vectors, bias fp32 [2, 6H] = ([b_ih ; b_ih_r], [b_hh ; b_hh_r]): one launch, cached until the parameters change."""
     def make():
+        if biases and all(b is not None for b in biases):
+            _wish_gru((w_ih, w_ih_r, w_hh, w_hh_r) + tuple(biases), I, H)
         Ipad = (I + 7) // 8 * 8
         dev = w_ih.device
         wih = torch.empty((6 * H, Ipad), device=dev, dtype=torch.bfloat16)

@@ -1958,16 +1958,28 @@ TOLS["lib_gru_grads"] = 1e-5
 def case_prepack(seed=0):
     from m3t_b200 import ops, raw
     from m3t_b200.models.resnet import BasicBlock, ResNet
+    from m3t_b200.models.rnn import GRU
     torch.manual_seed(seed)
-    m = ResNet(BasicBlock, [2, 2, 2, 2], 512, zero_init_residual=False, agg_mode="ap", fmap_out_size=3).cuda().train()
+    trunk = ResNet(BasicBlock, [2, 2, 2, 2], 512, zero_init_residual=False, agg_mode="ap", fmap_out_size=3)
+    head = GRU(512, 256, 2, 9, 2)                 # 2 BiGRU layers + a 2-layer FC head (Linear weights)
+    m = torch.nn.ModuleDict({"trunk": trunk, "head": head}).cuda().train()
     x = torch.randn(32, 64, 28, 28, device="cuda")
+
+    def loss():
+        f = m["trunk"](x)
+        return m["head"](f.view(4, 8, 512)).square().mean()
+
+    tags = ("filter", "dgrad_s2", "gru_w", "bf16")
     ops.clear_caches()
     ops._prepack_wish.clear()
-    m(x).square().mean().backward()              # records which filters / parity sub-filters the model asks for
+    ops._prepack_gru.clear()
+    ops._prepack_lin.clear()
+    loss().backward()                             # records which packs the model asks for
     ref = {}
     for k, v in ops._pack_cache.items():
-        if k[1] in ("filter", "dgrad_s2"):
-            ref[k] = [None if t is None else t.clone() for t in v[2]]
+        if k[1] in tags:
+            val = v[2] if isinstance(v[2], tuple) else (v[2],)
+            ref[k] = [None if t is None else t.clone() for t in val]
     ops.clear_caches()
     n = ops.prepack({id(p) for p in m.parameters()})
     bad = 0.0
@@ -1977,14 +1989,21 @@ def case_prepack(seed=0):
         if got is None:
             bad += 1
             continue
-        for a, b in zip(got[2], want):
+        gval = got[2] if isinstance(got[2], tuple) else (got[2],)
+        for a, b in zip(gval, want):
             if (a is None) != (b is None):
                 bad += 1
             elif a is not None:
                 seen += 1
-                bad += float((a.reshape(-1).view(torch.int16) != b.reshape(-1).view(torch.int16)).sum())
-    errs = {"prepack_exact": bad, "prepack_missing": 0.0 if (n == 19 and seen >= 40) else 1.0}
-    errs["info"] = {"filters": n, "tensors_compared": seen}
+                if a.shape != b.shape:
+                    bad += 1
+                elif a.dtype == torch.bfloat16:
+                    bad += float((a.reshape(-1).view(torch.int16) != b.reshape(-1).view(torch.int16)).sum())
+                else:
+                    bad += float((a != b).sum())
+    # 19 conv filters + 2 GRU layers x 8 entries + 2 Linear weights
+    errs = {"prepack_exact": bad, "prepack_missing": 0.0 if (n == 19 + 16 + 2 and seen >= 53 + 8 + 2) else 1.0}
+    errs["info"] = {"entries": n, "tensors_compared": seen, "by_tag": {t: sum(1 for k in ref if k[1] == t) for t in tags}}
     # and the model gives the same gradients with the pre-packed cache (cache hits) as with per-filter packs; the
     # yardstick is the run-to-run distance of two per-filter runs (train-mode BN statistics use fp32 atomics)
     def grads(prepacked):
@@ -1992,7 +2011,7 @@ def case_prepack(seed=0):
         if prepacked:
             ops.prepack({id(p) for p in m.parameters()})
         m.zero_grad(set_to_none=True)
-        m(x).square().mean().backward()
+        loss().backward()
         return [p.grad.clone() for p in m.parameters() if p.grad is not None]
 
     g0, g0b, g1 = grads(False), grads(False), grads(True)
