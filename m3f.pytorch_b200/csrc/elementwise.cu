@@ -90,6 +90,9 @@ __global__ void video_prep_s2d_w4_kernel(const T* __restrict__ in, __nv_bfloat16
                                          int H, int W, float mul, float add) {
   // One thread writes one complete 128-byte destination row (eight 16-byte stores): 4 taps x 12 channels + 16 zeros.
   // Each source pixel pair is read by the four destination pixels it is a tap of (L1-resident re-reads).
+  // Measured at 4096 frames (2.26 GB): 0.69 ms = 3.3 TB/s.  Two "coalesced-store" rewrites were tried in round 2 and
+  // dropped: rows staged in shared memory (two block barriers per destination row, 2.4x slower) and one thread per
+  // 16-byte chunk with eight scalar gathers (2.04 ms, 3x slower) - the float2 loads + full-row stores of this form win.
   const int H2 = H / 2, W2 = W / 2;
   const long long total = (long long)B * Tn * H2 * W2;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -131,51 +134,6 @@ __global__ void video_prep_s2d_w4_kernel(const T* __restrict__ in, __nv_bfloat16
                         pack_bf16x2(f[8 * g + 4], f[8 * g + 5]), pack_bf16x2(f[8 * g + 6], f[8 * g + 7]));
     o[6] = make_uint4(0, 0, 0, 0);   // channels 48..63 are structural zeros (the stem kernels never multiply them)
     o[7] = make_uint4(0, 0, 0, 0);
-  }
-}
-
-// The same layout pass with coalesced stores: ONE thread per 16-byte destination chunk (8 channels of one pixel),
-// consecutive threads consecutive chunks; its eight source values are scalar loads that hit L1 (every source pixel is a
-// tap of four destination pixels).  The one-thread-per-pixel kernel above issues eight 16-byte stores per thread at a
-// 128-byte stride (0.69 ms for 2.26 GB at 4096 frames).  (A shared-memory staged variant with two block barriers per
-// destination row measured 2.4x SLOWER: 2.6 loads per thread between barriers leave the memory pipe idle.)
-template <typename T>
-__global__ void __launch_bounds__(256)
-video_prep_s2d_w4_chunks_kernel(const T* __restrict__ in, __nv_bfloat16* __restrict__ out, int B, int Tn, int H, int W,
-                                float mul, float add) {
-  const int H2 = H / 2, W2 = W / 2;
-  const long long total = (long long)B * Tn * H2 * W2 * 8;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int g = (int)(i & 7);
-    long long r = i >> 3;
-    uint4 o = make_uint4(0, 0, 0, 0);
-    if (g < 6) {
-      const int w2 = (int)(r % W2);
-      r /= W2;
-      const int h2 = (int)(r % H2);
-      r /= H2;
-      const int t = (int)(r % Tn);
-      const long long b = r / Tn;
-      const long long plane = (long long)Tn * H * W;                      // one colour plane of one clip
-      const T* base = in + (b * 3 * Tn + t) * (long long)H * W + (long long)(2 * h2) * W;
-      float f[8];
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const int ch = g * 8 + e;
-        const int jw = ch / 12;
-        const int rm = ch - jw * 12;
-        const int pp = rm / 3;
-        const int c = rm - pp * 3;
-        const int ws = w2 + jw - 2;
-        f[e] = 0.f;
-        if (ws >= 0 && ws < W2)
-          f[e] = fmaf((float)__ldg(base + c * plane + (pp >> 1) * W + 2 * ws + (pp & 1)), mul, add);
-      }
-      o = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
-                     pack_bf16x2(f[6], f[7]));
-    }
-    reinterpret_cast<uint4*>(out)[i] = o;
   }
 }
 
@@ -1312,24 +1270,6 @@ extern "C" int m3t_video_prep_s2d_w4(const void* video, int is_u8, void* out, in
                                      float add, void* stream) {
   if ((H | W) & 1) return -1;
   const long long items = (long long)B * T * (H / 2) * (W / 2);
-  {
-    static int mode = -1;           // M3T_VIDEO_PREP=0: the one-thread-per-pixel kernel
-    if (mode < 0) {
-      const char* e = getenv("M3T_VIDEO_PREP");
-      mode = e ? atoi(e) : 1;
-    }
-    if (mode == 1) {
-      const int blocks = ew_blocks(items * 8);
-      if (is_u8)
-        video_prep_s2d_w4_chunks_kernel<uint8_t><<<blocks, 256, 0, ST(stream)>>>(
-            reinterpret_cast<const uint8_t*>(video), BF(out), B, T, H, W, mul, add);
-      else
-        video_prep_s2d_w4_chunks_kernel<float><<<blocks, 256, 0, ST(stream)>>>(reinterpret_cast<const float*>(video),
-                                                                              BF(out), B, T, H, W, mul, add);
-      count_launch();
-      return launch_status();
-    }
-  }
   if (is_u8)
     video_prep_s2d_w4_kernel<uint8_t><<<ew_blocks(items), kEwThreads, 0, ST(stream)>>>(
         reinterpret_cast<const uint8_t*>(video), BF(out), B, T, H, W, mul, add);
