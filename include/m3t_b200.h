@@ -436,6 +436,30 @@ int m3t_av_loss(const float* y_hat, const float* label_v, const float* label_a, 
                 const unsigned char* valid, int N, int C, int idx_v, int idx_a, int n_logits, float lambda, float w_ce,
                 float* out4, float* dy, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Deterministic training (the reference asks cuDNN for deterministic algorithms, train.py:17).  Every fp32 atomic
+ * accumulation of the training step has a slotted form: the destination passed by the caller is the FIRST of
+ * (1 + nslots) consecutive copies (all zero-filled by the caller); CTA / warp / split s accumulates into copy 1 + s,
+ * where it is the only writer, and m3t_det_reduce(buf, len, nslots) adds the copies to copy 0 in index order.
+ *   BatchNorm statistics of the conv kernels   m3t_conv_fprop_bf16 with tile_hint bit 8 (forces the persistent kernel);
+ *                                              m3t_conv3x3_c64_halo / _c128_halo / m3t_stem_fprop_halo with relu bit 8
+ *                                              nslots = m3t_det_stats_slots(), len = 2 * Cout
+ *   split-K weight gradients                   m3t_conv_wgrad_bf16 with splits_hint bit 29,
+ *                                              nslots = m3t_conv_wgrad_splits(geom, splits_hint), len = Cout*taps*Cin
+ *   halo-tile weight gradients                 m3t_wgrad3x3_c64_halo_det / m3t_wgrad_stem_halo_det,
+ *                                              nslots = m3t_det_cta_slots(), len = 64*576 / 64*1280
+ *   BatchNorm-backward sums                    m3t_bn_bwd_reduce with relu bit 8 (fixed-order block reduction),
+ *                                              nslots = m3t_det_stats_slots(), len = 2 * C
+ *   bias-gradient column sums                  m3t_colsum_bf16 with cols bit 30 (one row block per column strip; no slots)
+ * The GRU bias gradients are taken as deterministic column sums of dgi / dgh (dbias = NULL in m3t_gru_bwd); the loss,
+ * the gradient norm, clip and Adam are fixed-order already. */
+int m3t_det_stats_slots(void);
+int m3t_det_cta_slots(void);
+int m3t_det_reduce(float* buf, long long len, int nslots, void* stream);
+int m3t_conv_wgrad_splits(const int* geom, int splits_hint);
+int m3t_wgrad3x3_c64_halo_det(const void* x, const void* dy, float* dw_packed, int F, int H, int W, void* stream);
+int m3t_wgrad_stem_halo_det(const void* xs, const void* dy, float* dw_packed, int B, int T, int H2, int W2, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

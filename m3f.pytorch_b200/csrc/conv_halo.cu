@@ -38,6 +38,7 @@ struct HaloParams {
   const __nv_bfloat16* residual;
   int relu;
   float* stats;    // [2][64] or null
+  long long det_stride;   // != 0: statistics of CTA b go to stats + (1 + b) * det_stride (UmmaParams::det_stride)
 };
 
 template <int N>
@@ -235,7 +236,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         const int which = i / 64, c = i - which * 64;
         const float s = stat_smem[(0 * 2 + which) * 64 + c] + stat_smem[(1 * 2 + which) * 64 + c] +
                         stat_smem[(2 * 2 + which) * 64 + c] + stat_smem[(3 * 2 + which) * 64 + c];
-        atomicAdd(p.stats + which * 64 + c, s);
+        atomicAdd(p.stats + (p.det_stride ? (1 + (long long)blockIdx.x) * p.det_stride : 0) + which * 64 + c, s);
       }
     }
     tc_fence_before();
@@ -266,6 +267,7 @@ struct StemHaloParams {
   const float* shift;
   int relu;
   float* stats;
+  long long det_stride;
 };
 
 __global__ void __launch_bounds__(kHaloThreads, 1)
@@ -441,7 +443,7 @@ stem_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         const int which = i / 64, c = i - which * 64;
         const float s = stat_smem[(0 * 2 + which) * 64 + c] + stat_smem[(1 * 2 + which) * 64 + c] +
                         stat_smem[(2 * 2 + which) * 64 + c] + stat_smem[(3 * 2 + which) * 64 + c];
-        atomicAdd(p.stats + which * 64 + c, s);
+        atomicAdd(p.stats + (p.det_stride ? (1 + (long long)blockIdx.x) * p.det_stride : 0) + which * 64 + c, s);
       }
     }
     tc_fence_before();
@@ -479,7 +481,8 @@ extern "C" int m3t_conv3x3_c64_halo(const void* x, const void* w_packed, void* y
   p.y = reinterpret_cast<__nv_bfloat16*>(y);
   p.scale = scale; p.shift = shift;
   p.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
-  p.relu = relu; p.stats = stats;
+  p.relu = relu & 1; p.stats = stats;
+  p.det_stride = (relu & 256) && stats ? 2 * 64 : 0;      // bit 8: deterministic statistics (m3t_det_reduce follows)
   CUtensorMap tmX, tmW;
   uint64_t dims[4] = {64, (uint64_t)W, (uint64_t)H, (uint64_t)F};
   uint64_t strides[3] = {128, (uint64_t)W * 128, (uint64_t)H * W * 128};
@@ -530,7 +533,8 @@ extern "C" int m3t_stem_fprop_halo(const void* xs, const void* w_packed, void* y
   p.a_bytes = ((TR + 3) * W2 * 128 + 1023) / 1024 * 1024;
   p.stage_bytes = p.a_bytes + 4 * 8192;
   p.y = reinterpret_cast<__nv_bfloat16*>(y);
-  p.scale = scale; p.shift = shift; p.relu = relu; p.stats = stats;
+  p.scale = scale; p.shift = shift; p.relu = relu & 1; p.stats = stats;
+  p.det_stride = (relu & 256) && stats ? 2 * 64 : 0;
   if ((TR + 3) * W2 * 128 != p.a_bytes) return -8;   // the box must fill the stage exactly (expect_tx accounting)
   CUtensorMap tmX, tmW;
   uint64_t xd[5] = {64, (uint64_t)W2, (uint64_t)H2, (uint64_t)T, (uint64_t)B};

@@ -35,6 +35,7 @@ struct Halo128Params {
   const __nv_bfloat16* residual;
   int relu;
   float* stats;        // [2][128] or null
+  long long det_stride;   // != 0: statistics of CTA b go to stats + (1 + b) * det_stride
 };
 
 template <int N>
@@ -242,7 +243,7 @@ conv3x3_c128_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
         const int which = i / 128, c = i - which * 128;
         const float s = stat_smem[(0 * 2 + which) * 128 + c] + stat_smem[(1 * 2 + which) * 128 + c] +
                         stat_smem[(2 * 2 + which) * 128 + c] + stat_smem[(3 * 2 + which) * 128 + c];
-        atomicAdd(p.stats + which * 128 + c, s);
+        atomicAdd(p.stats + (p.det_stride ? (1 + (long long)blockIdx.x) * p.det_stride : 0) + which * 128 + c, s);
       }
     }
     tc_fence_before();
@@ -277,7 +278,8 @@ extern "C" int m3t_conv3x3_c128_halo(const void* x, const void* w_packed, void* 
   p.y = reinterpret_cast<__nv_bfloat16*>(y);
   p.scale = scale; p.shift = shift;
   p.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
-  p.relu = relu; p.stats = stats;
+  p.relu = relu & 1; p.stats = stats;
+  p.det_stride = (relu & 256) && stats ? 2 * 128 : 0;
   CUtensorMap tmX, tmW;
   uint64_t dims[4] = {128, (uint64_t)W, (uint64_t)H, (uint64_t)F};
   uint64_t strides[3] = {256, (uint64_t)W * 256, (uint64_t)H * W * 256};

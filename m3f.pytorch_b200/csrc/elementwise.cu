@@ -325,7 +325,7 @@ bn_act_fixed_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict
 // ------------------------------------------------------------------------------------------------------------
 // relu: 0 = none, 1 = mask from the stored activation (out > 0), 2 = mask recomputed from y*scale + shift > 0 (units
 // without a residual input: `out` is then neither stored for backward nor read here)
-template <int relu>
+template <int relu, bool DET = false>
 __global__ void __launch_bounds__(256, relu == 2 ? 2 : 3)
 bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ out,
                      const __nv_bfloat16* __restrict__ y, const float* __restrict__ mean,
@@ -388,14 +388,34 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16
         }
       }
     }
+    if constexpr (DET) {
+      // deterministic: per-thread partials side by side in shared memory ([row lane][2C]), summed in row-lane order,
+      // stored (not added) into this block's private slot of `sums` (slot 1 + blockIdx.x; m3t_det_reduce follows).
+      // (the zero-fill of sh[0 .. 2C) above is separated from these writes by the barrier at the top)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      atomicAdd(&sh[cg * 8 + j], a0[j]);
-      atomicAdd(&sh[C + cg * 8 + j], (a1[j] - mu[j] * a0[j]) * is[j]);
+      for (int j = 0; j < 8; ++j) {
+        sh[rl * 2 * C + cg * 8 + j] = a0[j];
+        sh[rl * 2 * C + C + cg * 8 + j] = (a1[j] - mu[j] * a0[j]) * is[j];
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        atomicAdd(&sh[cg * 8 + j], a0[j]);
+        atomicAdd(&sh[C + cg * 8 + j], (a1[j] - mu[j] * a0[j]) * is[j]);
+      }
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(sums + i, sh[i]);
+  if constexpr (DET) {
+    float* slot = sums + (1 + (long long)blockIdx.x) * 2 * C;
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
+      float s = 0.f;
+      for (int r = 0; r < rows_per_iter; ++r) s += sh[r * 2 * C + i];
+      slot[i] = s;
+    }
+  } else {
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(sums + i, sh[i]);
+  }
 }
 
 __global__ void bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ out,
@@ -1337,6 +1357,8 @@ extern "C" int m3t_bn_bwd_reduce(const void* dout, const void* out, const void* 
   // any C % 8 == 0 up to 8 * kEwThreads: when C/8 does not divide the block, the last kEwThreads % (C/8) threads idle
   // (DenseNet's 96 / 160 / 200 ... channel tensors); the trunk's power-of-two widths use every thread
   if (C % 8 || C / 8 > kEwThreads) return -1;
+  const bool det = (relu & 256) != 0;
+  relu &= 255;
   const int cgs = C / 8;
   const int rows_per_iter = kEwThreads / cgs;
   long long blocks = (rows + rows_per_iter - 1) / rows_per_iter;
@@ -1345,6 +1367,19 @@ extern "C" int m3t_bn_bwd_reduce(const void* dout, const void* out, const void* 
   const long long cap = 148LL * (relu == 2 ? 2 : 3);
   if (blocks > cap) blocks = cap;
   const size_t sm = 2 * C * sizeof(float);
+  if (det) {       // bit 8 of `relu`: `sums` is the first of 1 + m3t_det_stats_slots() zero-filled copies
+    const size_t smd = (size_t)rows_per_iter * 2 * C * sizeof(float);
+#define M3T_RED_DET(R)                                                                                              \
+  bn_bwd_reduce_kernel<R, true><<<(int)blocks, kEwThreads, smd, ST(stream)>>>(CBF(dout), CBF(out), CBF(y), mean,    \
+                                                                             invstd, scale, shift, BF(dz_out), sums, \
+                                                                             rows, C)
+    if (relu == 0) M3T_RED_DET(0);
+    else if (relu == 1) M3T_RED_DET(1);
+    else M3T_RED_DET(2);
+#undef M3T_RED_DET
+    count_launch();
+    return launch_status();
+  }
   if (relu == 0)
     bn_bwd_reduce_kernel<0><<<(int)blocks, kEwThreads, sm, ST(stream)>>>(CBF(dout), CBF(out), CBF(y), mean, invstd,
                                                                         scale, shift, BF(dz_out), sums, rows, C);
@@ -1593,10 +1628,32 @@ extern "C" int m3t_scatter_unpack_f32(const float* dwp, const int* idx, float* d
   return launch_status();
 }
 
+// buf = (1 + nslots) consecutive copies of a `len`-float vector: copy 0 += copy 1 + copy 2 + ... in index order.
+__global__ void det_reduce_kernel(float* __restrict__ buf, long long len, int nslots) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < len;
+       i += (long long)gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int k = 1; k <= nslots; ++k) s += buf[(long long)k * len + i];
+    buf[i] += s;
+  }
+}
+
+extern "C" int m3t_det_stats_slots(void) { return 148 * 4; }
+extern "C" int m3t_det_cta_slots(void) { return 148; }
+
+extern "C" int m3t_det_reduce(float* buf, long long len, int nslots, void* stream) {
+  if (!buf || len <= 0 || nslots <= 0) return -1;
+  det_reduce_kernel<<<ew_blocks(len), kEwThreads, 0, ST(stream)>>>(buf, len, nslots);
+  count_launch();
+  return launch_status();
+}
+
 extern "C" int m3t_colsum_bf16(const void* x, long long ld, long long rows, int cols, float* out, void* stream) {
+  const bool det = (cols & (1 << 30)) != 0;      // bit 30: deterministic (one row-block per column strip, no atomics race)
+  cols &= ~(1 << 30);
   long long gy = (rows + 8 * 64 - 1) / (8 * 64);
   if (gy > 148) gy = 148;
-  if (gy < 1) gy = 1;
+  if (gy < 1 || det) gy = 1;
   dim3 grid((cols + 31) / 32, (unsigned)gy), block(32, 8);
   colsum_bf16_kernel<<<grid, block, 0, ST(stream)>>>(CBF(x), ld, rows, cols, out);
   count_launch();

@@ -219,6 +219,8 @@ static int conv_fprop_impl(const void* x, const void* w_packed, void* y, const i
   p.scale = scale; p.shift = shift;
   p.residual = reinterpret_cast<const __nv_bfloat16*>(residual); p.ldr = g.Cout;
   p.relu = relu; p.stats = stats;
+  const bool det = (tile_hint & 256) != 0 && stats != nullptr;   // deterministic BatchNorm statistics (slots + m3t_det_reduce)
+  if (det) p.det_stride = 2LL * g.Cout;
   if (tcn) {
     p.pre_act = 1;
     if (tcn->drop_p > 0.f) {
@@ -258,7 +260,8 @@ static int conv_fprop_impl(const void* x, const void* w_packed, void* y, const i
     return launch_umma<64, 1, 4, A_IM2COL, false, false, EPI_STORE, 16>(tmA, tmB, p, tiles_m, 1, st);
   }
   // persistent tile walker (umma_persist.cuh): tile_hint bit4 forces it, bit5 forbids it
-  const bool persist = (tile_hint & 16) != 0 || (!(tile_hint & 32) && conv_use_persist(g, p, bn, mt));
+  const bool persist = det || (tile_hint & 16) != 0 || (!(tile_hint & 32) && conv_use_persist(g, p, bn, mt));
+  if (det && ck == 16) return -9;      // the 16-channel im2col mode has no persistent variant
   if (tcn) {       // fused TemporalBlock epilogue: its own instantiations of the persistent kernel
     if (!persist) return -5;
     if (bn == 64) return launch_persist<64, 1, 8, A_IM2COL, true>(tmA, tmB, p, ceil_div(Mpix, 128), st);
@@ -280,8 +283,22 @@ static int conv_fprop_impl(const void* x, const void* w_packed, void* y, const i
   return -3;
 }
 
+static int conv_wgrad_impl(const void* x, const void* dy, float* dw_packed, const int* geom, int splits_hint,
+                           void* stream, int* query_splits);
+
 extern "C" int m3t_conv_wgrad_bf16(const void* x, const void* dy, float* dw_packed, const int* geom, int splits_hint,
                                    void* stream) {
+  return conv_wgrad_impl(x, dy, dw_packed, geom, splits_hint, stream, nullptr);
+}
+
+extern "C" int m3t_conv_wgrad_splits(const int* geom, int splits_hint) {
+  int splits = 0;
+  const int rc = conv_wgrad_impl(nullptr, nullptr, nullptr, geom, splits_hint, nullptr, &splits);
+  return rc ? rc : splits;
+}
+
+static int conv_wgrad_impl(const void* x, const void* dy, float* dw_packed, const int* geom, int splits_hint,
+                           void* stream, int* query_splits) {
   ConvGeom g;
   int rc = conv_geom(g, geom);
   if (rc) return rc;
@@ -303,6 +320,8 @@ extern "C" int m3t_conv_wgrad_bf16(const void* x, const void* dy, float* dw_pack
   // up evenly (measured, 4096 frames: 14x14x128 0.357 -> 0.328 ms, 7x7x256 0.368 -> 0.305, 4x4x512 0.472 -> 0.386;
   // 9 atoms (64 -> 128 stride 2) lose to the padding; 256x256 tiles and 3-stage / 1-CTA-per-SM variants were no faster)
   const bool force_mt1 = (splits_hint & (1 << 30)) != 0;
+  const bool det = (splits_hint & (1 << 29)) != 0;    // every split accumulates into its own copy of dw_packed
+  splits_hint &= ~(1 << 29);
   int mt = (ck == 64 && p.atoms >= 4 && bn == 64 && !force_mt1) ? 2 : 1;
   if (ck == 64 && bn == 128 && p.atoms % 4 == 0 && !force_mt1) mt = 2;
   splits_hint &= ~(1 << 30);
@@ -324,6 +343,8 @@ extern "C" int m3t_conv_wgrad_bf16(const void* x, const void* dy, float* dw_pack
   p.k_iters = ceil_div(kblocks, splits);
   splits = ceil_div(kblocks, p.k_iters);   // never more than asked for: the wave count is preserved
   p.out = dw_packed; p.ldc = (long long)taps * g.Cin; p.out_f32 = 1;
+  if (det) p.det_stride = (long long)g.Cout * taps * g.Cin;
+  if (query_splits) { *query_splits = splits; return 0; }
   CUtensorMap tmA, tmB;
   rc = conv_tmap(&tmA, x, g, 64);
   if (rc) return rc;

@@ -57,6 +57,11 @@ struct UmmaParams {
   // ---- fused TemporalBlock epilogue (models/tcn.py:19-33,43-46): t = drop(relu(acc*scale+shift)); out2 = t (saved for
   //      backward when a residual follows); out = residual ? relu(t + residual) : t.  pre_act != 0 selects this order
   //      (the activation BEFORE the residual); drop_thresh == 0: no dropout.
+  // ---- deterministic accumulation (train.py:17 asks for reproducible training): when det_stride != 0 the fp32 atomics
+  //      of this launch go to a PRIVATE copy of the destination - slot s at dst + (1 + s) * det_stride - so no two CTAs
+  //      (or warps) ever add to the same address; m3t_det_reduce then sums the slots in index order.  Slot = 4 *
+  //      blockIdx.x + epilogue warp for the BatchNorm statistics of the persistent kernel, the split index for wgrad.
+  long long det_stride;
   int pre_act;
   unsigned drop_thresh;
   float drop_scale;
@@ -495,7 +500,7 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
       }
     } else {  // EPI_ATOMIC_T : out_f32[n][m] += acc  (rows of D are contiguous in the output)
-      float* outp = reinterpret_cast<float*>(p.out);
+      float* outp = reinterpret_cast<float*>(p.out) + (p.det_stride ? (1 + split) * p.det_stride : 0);
 #pragma unroll 1
       for (int mt = 0; mt < MT; ++mt) {
         const long long m = (long long)(m_tile * MT + mt) * 128 + row;

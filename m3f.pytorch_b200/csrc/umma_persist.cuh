@@ -137,14 +137,15 @@ umma_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
     for (int ci = 0; ci < NCH; ++ci) st1[ci] = st2[ci] = 0.f;
     int cur_n = -1;
+    float* const stats_base = p.stats + (p.det_stride ? (1 + 4 * (long long)blockIdx.x + quad) * p.det_stride : 0);
     auto flush_stats = [&]() {
       if (cur_n < 0) return;
 #pragma unroll
       for (int ci = 0; ci < NCH; ++ci) {
         const int c = ci * 32 + (int)lane;
         if (c < BN && cur_n * BN + c < p.N) {
-          atomicAdd(p.stats + cur_n * BN + c, st1[ci]);
-          atomicAdd(p.stats + p.N + cur_n * BN + c, st2[ci]);
+          atomicAdd(stats_base + cur_n * BN + c, st1[ci]);
+          atomicAdd(stats_base + p.N + cur_n * BN + c, st2[ci]);
         }
         st1[ci] = st2[ci] = 0.f;
       }

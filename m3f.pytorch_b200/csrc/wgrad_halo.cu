@@ -33,6 +33,7 @@ struct WgHaloParams {
   int shiftA[kWgMaxAcc], shiftB[kWgMaxAcc];   // row shifts of the two 64-wide atoms of accumulator a
   int tapA[kWgMaxAcc], tapB[kWgMaxAcc];       // output tap index of each atom (-1: atom unused)
   float* out;           // fp32 [64][ldo], accumulated atomically
+  long long det_stride; // != 0: CTA b accumulates into out + (1 + b) * det_stride (deterministic mode)
   int ldo;
 };
 
@@ -117,6 +118,7 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     const int row = quad * 32 + (int)lane;
     mbar_wait(tmem_full, 0, 520);
     tc_fence_after();
+    float* const outp = p.out + (p.det_stride ? (1 + (long long)blockIdx.x) * p.det_stride : 0);
     for (int a = 0; a < p.n_acc; ++a) {
       const int tap = row < 64 ? p.tapA[a] : p.tapB[a];
       const long long m = (long long)tap * 64 + (row & 63);
@@ -128,7 +130,7 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         tmem_ld_wait();
         if (tap >= 0) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) atomicAdd(p.out + (long long)(c0 + i) * p.ldo + m, __uint_as_float(r[i]));
+          for (int i = 0; i < 16; ++i) atomicAdd(outp + (long long)(c0 + i) * p.ldo + m, __uint_as_float(r[i]));
         }
       }
     }
@@ -180,6 +182,7 @@ struct WgXresParams {
   int kt0, nkt;
   float* out;
   int ldo;
+  long long det_stride;
 };
 
 __global__ void __launch_bounds__(kWgThreads, 1)
@@ -285,6 +288,7 @@ wgrad_stem_xres_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
     const int row = quad * 32 + (int)lane;
     mbar_wait(tmem_full, 0, 640);
     tc_fence_after();
+    float* const outp = p.out + (p.det_stride ? (1 + (long long)blockIdx.x) * p.det_stride : 0);
     const uint32_t started = *reinterpret_cast<volatile uint32_t*>(started_slot);
     for (int a = 0; a < n_acc; ++a) {
       if (!((started >> (a >> 1)) & 1u)) continue;
@@ -297,7 +301,7 @@ wgrad_stem_xres_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
         tmem_ld16(t_lane + c0, r);
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 16; ++i) atomicAdd(p.out + (long long)(c0 + i) * p.ldo + m, __uint_as_float(r[i]));
+        for (int i = 0; i < 16; ++i) atomicAdd(outp + (long long)(c0 + i) * p.ldo + m, __uint_as_float(r[i]));
       }
     }
     tc_fence_before();
@@ -334,8 +338,22 @@ static int wg_xres_launch(const CUtensorMap& tmX, const CUtensorMap& tmDY, const
 using namespace m3t;
 
 // 3x3 / stride 1 / pad 1, Cin = Cout = 64.  x, dy: bf16 [F][H][W][64]; dw_packed: fp32 [64][9*64] += (caller zero-fills)
+static int wgrad3x3_c64_halo_impl(const void* x, const void* dy, float* dw_packed, int F, int H, int W, void* stream,
+                                  int det);
+
 extern "C" int m3t_wgrad3x3_c64_halo(const void* x, const void* dy, float* dw_packed, int F, int H, int W,
                                      void* stream) {
+  return wgrad3x3_c64_halo_impl(x, dy, dw_packed, F, H, W, stream, 0);
+}
+// Deterministic variant: dw_packed is the first of (1 + m3t_det_cta_slots()) consecutive zero-filled copies; CTA b
+// accumulates into copy 1 + b; the caller sums the copies in order with m3t_det_reduce.
+extern "C" int m3t_wgrad3x3_c64_halo_det(const void* x, const void* dy, float* dw_packed, int F, int H, int W,
+                                         void* stream) {
+  return wgrad3x3_c64_halo_impl(x, dy, dw_packed, F, H, W, stream, 1);
+}
+
+static int wgrad3x3_c64_halo_impl(const void* x, const void* dy, float* dw_packed, int F, int H, int W, void* stream,
+                                  int det) {
   const int Wp = W + 2;
   if (F <= 0 || H <= 0 || W <= 0 || Wp > 64) return -1;
   // rows per K-block: TR*Wp must be a multiple of 16 and the boxes must fit two pipeline stages
@@ -363,6 +381,7 @@ extern "C" int m3t_wgrad3x3_c64_halo(const void* x, const void* dy, float* dw_pa
     else { p.tapB[a] = -1; p.shiftB[a] = p.shiftA[a]; }
   }
   p.out = dw_packed; p.ldo = 576;
+  p.det_stride = det ? 64LL * 576 : 0;
   CUtensorMap tmX, tmDY;
   uint64_t xd[5] = {64, (uint64_t)W, (uint64_t)H, 1, (uint64_t)F};
   uint64_t xs[4] = {128, (uint64_t)W * 128, (uint64_t)H * W * 128, (uint64_t)H * W * 128};
@@ -380,8 +399,20 @@ extern "C" int m3t_wgrad3x3_c64_halo(const void* x, const void* dy, float* dw_pa
 // Stem: xs bf16 [B][T][H2][W2][64] (W-unrolled space-to-depth), dy bf16 [B*T][H2][W2][64];
 // dw_packed fp32 [64][20*64] (tap = kt*4 + jh) += .  Two activation-resident passes (M3T_STEM_WGRAD_SPLIT taps each,
 // default 3 + 2); falls back to five launches, one per temporal tap kt, when the boxes do not fit.
+static int wgrad_stem_halo_impl(const void* xs, const void* dy, float* dw_packed, int B, int T, int H2, int W2,
+                                void* stream, int det);
+
 extern "C" int m3t_wgrad_stem_halo(const void* xs, const void* dy, float* dw_packed, int B, int T, int H2, int W2,
                                    void* stream) {
+  return wgrad_stem_halo_impl(xs, dy, dw_packed, B, T, H2, W2, stream, 0);
+}
+extern "C" int m3t_wgrad_stem_halo_det(const void* xs, const void* dy, float* dw_packed, int B, int T, int H2, int W2,
+                                       void* stream) {
+  return wgrad_stem_halo_impl(xs, dy, dw_packed, B, T, H2, W2, stream, 1);
+}
+
+static int wgrad_stem_halo_impl(const void* xs, const void* dy, float* dw_packed, int B, int T, int H2, int W2,
+                                void* stream, int det) {
   if (B <= 0 || T <= 0 || H2 <= 0 || W2 <= 0 || W2 > 256) return -1;
   int TR = 0;
   for (int t = 8; t >= 1; --t)
@@ -432,6 +463,7 @@ extern "C" int m3t_wgrad_stem_halo(const void* xs, const void* dy, float* dw_pac
         q.dy_bytes = TX * W2 * 128;
         q.kt0 = kt0; q.nkt = 5 - kt0 < split ? 5 - kt0 : split;
         q.out = dw_packed; q.ldo = 20 * 64;
+        q.det_stride = det ? 64LL * 20 * 64 : 0;
         rc = wg_xres_launch(tmX, tmDY, q, reinterpret_cast<cudaStream_t>(stream));
         if (rc) return rc;
       }
@@ -455,6 +487,7 @@ extern "C" int m3t_wgrad_stem_halo(const void* xs, const void* dy, float* dw_pac
       p.tapB[a] = kt * 4 + 2 * a + 1; p.shiftB[a] = (2 * a + 1) * W2;
     }
     p.out = dw_packed; p.ldo = 20 * 64;
+    p.det_stride = det ? 64LL * 20 * 64 : 0;
     rc = wg_launch(tmX, tmDY, p, reinterpret_cast<cudaStream_t>(stream));
     if (rc) return rc;
   }

@@ -306,7 +306,7 @@ def _cba_train_fwd(x, w, gamma, beta, running_mean, running_var, residual, strid
     k = (w.shape[2], w.shape[3])
     geom = _geom2d(x.shape, Cout, k, stride, (pad, pad), (pad, pad))
     wf, _ = packed_filter(w, True)
-    stats = raw.zeros_f32((2, Cout), x.device)
+    stats = raw.new_stats(Cout, x.device)
     y = raw.conv_fprop(x, wf, geom, stats=stats)
     y = y.view(y.shape[0], y.shape[2], y.shape[3], y.shape[4])
     count = y.numel() // Cout
@@ -641,7 +641,7 @@ class Stem3D(torch.autograd.Function):
         ctx.flops = flops
         halo = raw.USE_HALO_STEM and (H // 2) % 8 == 0 and (W // 2) == 56
         if training:
-            stats = raw.zeros_f32((2, 64), video.device)
+            stats = raw.new_stats(64, video.device)
             if halo:
                 y = raw.stem_fprop_halo(xs, wp, stats=stats, algo_flops=flops)
             else:
@@ -1202,7 +1202,7 @@ class ConvNdBNAct(torch.autograd.Function):
             else:
                 out = raw.conv_fprop(x, wf, geom, scale=ss[0], shift=ss[1], relu=relu, algo_flops=flops)
             return out if nd == 3 else out.view(N, Q, Cout)
-        stats = raw.zeros_f32((2, Cout), x.device)
+        stats = raw.new_stats(Cout, x.device)
         y = raw.conv_fprop(x, wf, geom, stats=stats, algo_flops=flops)
         count = y.numel() // Cout
         fin = raw.bn_finalize(stats, count, gamma.detach(), beta.detach(), BN_EPS, BN_MOMENTUM, running_mean,
@@ -1272,8 +1272,13 @@ class Conv3x3C1BNReLU(torch.autograd.Function):
             ss = raw.bn_fold(gamma.detach(), beta.detach(), running_mean, running_var, None, BN_EPS)
             out = raw.gemm(patches, wb, scale=ss[0], shift=ss[1], relu=True)
             return out.view(N, H, W, Cout)
-        stats = raw.zeros_f32((2, Cout), x.device)
-        y = raw.gemm(patches, wb, stats=stats)
+        if raw.DETERMINISTIC:     # the GEMM epilogue's statistics have no slotted form: one deterministic streaming pass
+            y = raw.gemm(patches, wb)
+            zero, one = _unit(Cout, x.device)[1], _unit(Cout, x.device)[0]
+            stats, _ = raw.bn_bwd_reduce(y, None, y, zero, one, False, False)
+        else:
+            stats = raw.new_stats(Cout, x.device)
+            y = raw.gemm(patches, wb, stats=stats)
         fin = raw.bn_finalize(stats, y.shape[0], gamma.detach(), beta.detach(), BN_EPS, BN_MOMENTUM, running_mean,
                               running_var)
         out = raw.bn_act(y, fin[2], fin[3], relu=True)

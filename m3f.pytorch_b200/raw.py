@@ -119,6 +119,45 @@ def zeros_f32(shape, device):
     return torch.zeros(shape, device=device, dtype=torch.float32)
 
 
+# ----------------------------------------------------------------------------------------------------------
+# Deterministic training (reference train.py:17).  M3T_DETERMINISTIC=1 or set_deterministic(True): every fp32 atomic
+# accumulation of the step runs in its slotted form (include/m3t_b200.h "Deterministic training") - destinations are
+# the first of (1 + nslots) zero-filled copies, each CTA / warp / split owns one copy, m3t_det_reduce sums them in
+# index order - so two runs from the same state give bit-identical losses, gradients and parameters.
+# ----------------------------------------------------------------------------------------------------------
+DETERMINISTIC = os.environ.get("M3T_DETERMINISTIC", "0") == "1"
+
+
+def set_deterministic(flag):
+    global DETERMINISTIC
+    prev, DETERMINISTIC = DETERMINISTIC, bool(flag)
+    return prev
+
+
+def _det_slots(kind):
+    lib = _lib()
+    return int(lib.m3t_det_stats_slots() if kind == "stats" else lib.m3t_det_cta_slots())
+
+
+def _det_accum(shape, nslots, device):
+    """(1 + nslots) zero-filled copies of an fp32 accumulator; returns (copy 0, the whole buffer)."""
+    buf = torch.zeros((1 + nslots,) + tuple(shape), device=device, dtype=torch.float32)
+    return buf[0], buf
+
+
+def _det_reduce(dst, nslots):
+    """dst = copy 0 of a _det_accum buffer: dst += copy 1 + copy 2 + ... in order."""
+    L.check(_lib().m3t_det_reduce(L.ptr(dst), L.i64(dst.numel()), L.i32(nslots), L.stream_ptr()), "det_reduce")
+
+
+def new_stats(C, device):
+    """fp32 [2, C] accumulator for BatchNorm statistics / BatchNorm-backward sums (zero-initialised).  In deterministic
+    mode it is copy 0 of a slotted buffer (the view keeps the buffer alive)."""
+    if DETERMINISTIC:
+        return _det_accum((2, C), _det_slots("stats"), device)[0]
+    return zeros_f32((2, C), device)
+
+
 def _nb(*ts):
     """Bytes of the given tensors (None skipped): algorithmic traffic of a streaming pass = each operand once."""
     return float(sum(t.numel() * t.element_size() for t in ts if t is not None))
@@ -209,12 +248,15 @@ def conv3x3_c128_halo(x, w_packed, scale=None, shift=None, residual=None, relu=F
     F_, H, W, C = x.shape
     assert C == 128 and w_packed.shape == (128, 1152)
     y = torch.empty((F_, H, W, 128), device=x.device, dtype=torch.bfloat16)
+    det = DETERMINISTIC and stats is not None
 
     def run():
         rc = L.load().m3t_conv3x3_c128_halo(L.ptr(x), L.ptr(w_packed), L.ptr(y), L.i32(F_), L.i32(H), L.i32(W),
-                                            L.ptr(scale), L.ptr(shift), L.ptr(residual), L.i32(relu), L.ptr(stats),
-                                            L.stream_ptr())
+                                            L.ptr(scale), L.ptr(shift), L.ptr(residual), L.i32(int(bool(relu)) | (256 if det else 0)),
+                                            L.ptr(stats), L.stream_ptr())
         L.check(rc, "m3t_conv3x3_c128_halo")
+        if det:
+            _det_reduce(stats, _det_slots("stats"))
 
     g = conv_geom(2, F_, 1, H, W, 128, 128, (1, 3, 3), (1, 1, 1), (0, 1, 1), (0, 1, 1), (1, 1, 1))
     _timed(conv_key(tag + "-halo", g), 2.0 * F_ * H * W * 128 * 128 * 9, run)
@@ -240,10 +282,13 @@ def conv_fprop(x, w_packed, g, scale=None, shift=None, residual=None, relu=False
     y = torch.empty((N, Z, P, Q, Cout), device=x.device, dtype=torch.bfloat16)
 
     def run():
+        det = DETERMINISTIC and stats is not None
         rc = L.load().m3t_conv_fprop_bf16(L.ptr(x), L.ptr(w_packed), L.ptr(y), L.int_array(g), L.ptr(scale),
-                                          L.ptr(shift), L.ptr(residual), L.i32(relu), L.ptr(stats), L.i32(tile_hint),
-                                          L.stream_ptr())
+                                          L.ptr(shift), L.ptr(residual), L.i32(relu), L.ptr(stats),
+                                          L.i32(tile_hint | (256 if det else 0)), L.stream_ptr())
         L.check(rc, "m3t_conv_fprop_bf16")
+        if det:
+            _det_reduce(stats, _det_slots("stats"))
 
     if _prof is not None and algo_flops is None:
         algo_flops = 2.0 * N * Z * P * Q * Cout * g[5] * g[7] * g[8] * g[9]
@@ -309,12 +354,15 @@ def conv3x3_c64_halo(x, w_packed, scale=None, shift=None, residual=None, relu=Fa
     F_, H, W, C = x.shape
     assert C == 64 and w_packed.shape == (64, 576)
     y = torch.empty((F_, H, W, 64), device=x.device, dtype=torch.bfloat16)
+    det = DETERMINISTIC and stats is not None
 
     def run():
         rc = L.load().m3t_conv3x3_c64_halo(L.ptr(x), L.ptr(w_packed), L.ptr(y), L.i32(F_), L.i32(H), L.i32(W),
-                                           L.ptr(scale), L.ptr(shift), L.ptr(residual), L.i32(relu), L.ptr(stats),
-                                           L.stream_ptr())
+                                           L.ptr(scale), L.ptr(shift), L.ptr(residual), L.i32(int(bool(relu)) | (256 if det else 0)),
+                                           L.ptr(stats), L.stream_ptr())
         L.check(rc, "m3t_conv3x3_c64_halo")
+        if det:
+            _det_reduce(stats, _det_slots("stats"))
 
     _timed("%s-halo nd2 1x%dx%d c64->64 k1x3x3 s1" % (tag, H, W), 2.0 * F_ * H * W * 64 * 576, run)
     return y
@@ -332,8 +380,11 @@ def stem_fprop_halo(xs, w_packed, stats=None, algo_flops=None):
 
     def run():
         L.check(L.load().m3t_stem_fprop_halo(L.ptr(xs), L.ptr(w_packed), L.ptr(y), L.i32(B), L.i32(T), L.i32(H2),
-                                             L.i32(W2), L.ptr(None), L.ptr(None), L.i32(0), L.ptr(stats),
+                                             L.i32(W2), L.ptr(None), L.ptr(None),
+                                             L.i32(256 if (DETERMINISTIC and stats is not None) else 0), L.ptr(stats),
                                              L.stream_ptr()), "m3t_stem_fprop_halo")
+        if DETERMINISTIC and stats is not None:
+            _det_reduce(stats, _det_slots("stats"))
 
     _timed("stem-halo %dx%dx%d" % (T, H2, W2), algo_flops or 2.0 * B * T * H2 * W2 * 64 * 1280, run)
     return y
@@ -344,11 +395,17 @@ def wgrad_stem_halo(xs, dy, algo_flops=None):
     fp32 [64, 1280] (packed (kt,jh,jw,ch))."""
     _chk_bf16(xs, dy)
     B, T, H2, W2, _ = xs.shape
-    dw = zeros_f32((64, 1280), xs.device)
+    if DETERMINISTIC:
+        dw, _ = _det_accum((64, 1280), _det_slots("cta"), xs.device)
+    else:
+        dw = zeros_f32((64, 1280), xs.device)
 
     def run():
-        L.check(L.load().m3t_wgrad_stem_halo(L.ptr(xs), L.ptr(dy), L.ptr(dw), L.i32(B), L.i32(T), L.i32(H2),
-                                             L.i32(W2), L.stream_ptr()), "m3t_wgrad_stem_halo")
+        fn = L.load().m3t_wgrad_stem_halo_det if DETERMINISTIC else L.load().m3t_wgrad_stem_halo
+        L.check(fn(L.ptr(xs), L.ptr(dy), L.ptr(dw), L.i32(B), L.i32(T), L.i32(H2), L.i32(W2), L.stream_ptr()),
+                "m3t_wgrad_stem_halo")
+        if DETERMINISTIC:
+            _det_reduce(dw, _det_slots("cta"))
 
     _timed("wgrad-halo stem %dx%dx%d" % (T, H2, W2), algo_flops or 2.0 * B * T * H2 * W2 * 64 * 1280, run)
     return dw
@@ -359,23 +416,36 @@ def conv_wgrad(x, dy, g, splits=0, algo_flops=None):
     _chk_bf16(x, dy)
     Cin, Cout = g[5], g[6]
     taps = g[7] * g[8] * g[9]
-    dw = zeros_f32((Cout, taps * Cin), x.device)
-    if (USE_HALO_WGRAD and splits == 0 and g[0] == 2 and Cin == 64 and Cout == 64 and tuple(g[7:10]) == (1, 3, 3)
+    halo = (USE_HALO_WGRAD and splits == 0 and g[0] == 2 and Cin == 64 and Cout == 64 and tuple(g[7:10]) == (1, 3, 3)
             and tuple(g[10:13]) == (1, 1, 1) and tuple(g[13:19]) == (0, 0, 1, 1, 1, 1)
-            and tuple(g[19:22]) == (1, 1, 1) and g[4] + 2 <= 48):
+            and tuple(g[19:22]) == (1, 1, 1) and g[4] + 2 <= 48)
+    det_slots = 0
+    if DETERMINISTIC:
+        det_slots = _det_slots("cta") if halo else int(L.load().m3t_conv_wgrad_splits(L.int_array(g), L.i32(splits)))
+        if det_slots <= 0:
+            raise L.M3TError("m3t_conv_wgrad_splits -> %d" % det_slots)
+        dw, _ = _det_accum((Cout, taps * Cin), det_slots, x.device)
+    else:
+        dw = zeros_f32((Cout, taps * Cin), x.device)
+    if halo:
         N, H, W = g[1], g[3], g[4]
 
         def run_h():
-            L.check(L.load().m3t_wgrad3x3_c64_halo(L.ptr(x), L.ptr(dy), L.ptr(dw), L.i32(N), L.i32(H), L.i32(W),
-                                                   L.stream_ptr()), "m3t_wgrad3x3_c64_halo")
+            fn = L.load().m3t_wgrad3x3_c64_halo_det if DETERMINISTIC else L.load().m3t_wgrad3x3_c64_halo
+            L.check(fn(L.ptr(x), L.ptr(dy), L.ptr(dw), L.i32(N), L.i32(H), L.i32(W), L.stream_ptr()),
+                    "m3t_wgrad3x3_c64_halo")
+            if DETERMINISTIC:
+                _det_reduce(dw, det_slots)
 
         _timed("wgrad-halo nd2 1x%dx%d c64->64 k1x3x3 s1" % (H, W), 2.0 * N * H * W * 64 * 576, run_h)
         return dw
 
     def run():
-        rc = L.load().m3t_conv_wgrad_bf16(L.ptr(x), L.ptr(dy), L.ptr(dw), L.int_array(g), L.i32(splits),
-                                          L.stream_ptr())
+        rc = L.load().m3t_conv_wgrad_bf16(L.ptr(x), L.ptr(dy), L.ptr(dw), L.int_array(g),
+                                          L.i32(splits | ((1 << 29) if DETERMINISTIC else 0)), L.stream_ptr())
         L.check(rc, "m3t_conv_wgrad_bf16")
+        if DETERMINISTIC:
+            _det_reduce(dw, det_slots)
 
     flops = None
     if _prof is not None:
@@ -475,14 +545,17 @@ def _relu_mode(relu, out):
 def bn_bwd_reduce(dout, out, y, mean, invstd, relu, want_dz, scale=None, shift=None):
     C = y.shape[-1]
     rows = y.numel() // C
-    sums = zeros_f32((2, C), y.device)
+    sums = new_stats(C, y.device)
     dz = torch.empty_like(y) if want_dz else None
     mode = _relu_mode(relu, out)
     assert mode != 2 or (scale is not None and shift is not None)
+    det = DETERMINISTIC
     _timed("hbm bn_bwd_reduce C%d" % C, 0.0, lambda: L.check(
         _lib().m3t_bn_bwd_reduce(L.ptr(dout), L.ptr(out), L.ptr(y), L.ptr(mean), L.ptr(invstd), L.ptr(scale),
-                                 L.ptr(shift), L.i32(mode), L.ptr(dz), L.ptr(sums), L.i64(rows), L.i32(C),
-                                 L.stream_ptr()), "bn_bwd_reduce"), _nb(dout, out, y, dz))
+                                 L.ptr(shift), L.i32(mode | (256 if det else 0)), L.ptr(dz), L.ptr(sums), L.i64(rows),
+                                 L.i32(C), L.stream_ptr()), "bn_bwd_reduce"), _nb(dout, out, y, dz))
+    if det:
+        _det_reduce(sums, _det_slots("stats"))
     return sums, dz
 
 
@@ -526,6 +599,8 @@ def maxpool_bn_bwd(dout, idx, y, mean, invstd, scale, shift, count, pool=(3, 2, 
         # equal the sums over the pooled tensors (mask recomputed from ymax * scale + shift > 0)
         sums, _ = bn_bwd_reduce(dout, None, ymax, mean, invstd, True, False, scale=scale, shift=shift)
     else:
+        if DETERMINISTIC:
+            raise L.M3TError("deterministic mode: the pooled units take their BatchNorm sums from ymax (want_ymax=True)")
         sums = zeros_f32((2, C), y.device)
         _timed("hbm maxpool_bn_bwd(reduce) %dx%d C%d" % (H, W, C), 0.0, lambda: L.check(
             fn(L.i32(0), L.ptr(dout), L.ptr(idx), L.ptr(y), L.ptr(mean), L.ptr(invstd), L.ptr(scale), L.ptr(shift),
@@ -671,8 +746,9 @@ def colsum(x2d, cols=None):
     rows = x2d.shape[0]
     cols = cols or x2d.shape[1]
     out = zeros_f32((cols,), x2d.device)
-    L.check(_lib().m3t_colsum_bf16(L.ptr(x2d), L.i64(x2d.stride(0)), L.i64(rows), L.i32(cols), L.ptr(out),
-                                   L.stream_ptr()), "colsum")
+    L.check(_lib().m3t_colsum_bf16(L.ptr(x2d), L.i64(x2d.stride(0)), L.i64(rows),
+                                   L.i32(cols | ((1 << 30) if DETERMINISTIC else 0)), L.ptr(out), L.stream_ptr()),
+            "colsum")
     return out
 
 
@@ -723,11 +799,15 @@ def gru_bwd(dout, out, saved, w_hh_t_bf16, B, T, H):
     dgh = torch.empty((B * T, 6 * H), device=dev, dtype=torch.bfloat16)
     hprev = torch.empty((B * T, 2 * H), device=dev, dtype=torch.bfloat16)
     counters = torch.empty((2 * ((B + 31) // 32) + 2,), device=dev, dtype=torch.int32)
-    dbias = zeros_f32((2, 6 * H), dev)     # [b_ih | b_hh] x [dir0 3H | dir1 3H]
+    # deterministic mode: the kernel's bias sums are atomics over batch slices and warps; take them as (deterministic)
+    # column sums of the gate-gradient tensors instead
+    dbias = None if DETERMINISTIC else zeros_f32((2, 6 * H), dev)     # [b_ih | b_hh] x [dir0 3H | dir1 3H]
     _timed("gru_bwd B%d T%d H%d" % (B, T, H), 0.0, lambda: L.check(
         _lib().m3t_gru_bwd(L.ptr(dout), L.ptr(out), L.ptr(saved), L.ptr(w_hh_t_bf16), L.ptr(dgi), L.ptr(dgh),
                            L.ptr(hprev), L.ptr(counters), L.ptr(dbias), L.i32(B), L.i32(T), L.i32(H),
                            L.stream_ptr()), "gru_bwd"), _nb(dout, out, saved, w_hh_t_bf16, dgi, dgh, hprev))
+    if dbias is None:
+        dbias = torch.stack((colsum(dgi, 6 * H), colsum(dgh, 6 * H)))
     return dgi, dgh, hprev, dbias
 
 

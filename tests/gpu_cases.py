@@ -2080,6 +2080,63 @@ for _t in ("mtl", "va", "big"):
     TOLS["dloss_%s_vs_oracle" % _t] = 2e-5
 
 
+# ----------------------------------------------------------------------------------------------------------
+# Deterministic training (raw.set_deterministic / M3T_DETERMINISTIC=1; reference train.py:17): two runs from the same
+# state are BIT-identical (losses, every gradient, every parameter after 3 optimizer steps), for the ResNet-backbone
+# AV model and for the VGG-M split model; and the slotted accumulation computes the same gradients as the default path.
+# ----------------------------------------------------------------------------------------------------------
+def case_deterministic(seed=0, steps=3, clips=6):
+    import bench as BN
+    from m3t_b200 import ops, raw
+    from m3t_b200.engine import TrainEngine
+    from m3t_b200.models.model import AffWild2VA
+    errs, info = {}, {}
+    for tag, kw in (("resnet", {}), ("v2psplit", dict(backbone="v2p_split", split_layer=3))):
+        hp = BN.hparams()
+        for k, v in kw.items():
+            setattr(hp, k, v)
+        batches = [{k: v.cuda() for k, v in BN.synth_batch(clips, 200 + i, pin=False).items()} for i in range(steps)]
+
+        def run(det):
+            prev = raw.set_deterministic(det)
+            try:
+                ops.clear_caches()
+                torch.manual_seed(seed)
+                m = AffWild2VA(hp)
+                BN.randomise_bn(m, 7)
+                m = m.cuda().train()
+                eng = TrainEngine(m, lr=1e-4, weight_decay=1e-4, clip=1.0)
+                losses, g_first = [], None
+                for b in batches:
+                    losses.append(eng.step(b).clone())
+                    if g_first is None:
+                        g_first = eng.flat_g.clone()
+                torch.cuda.synchronize()
+                return torch.stack(losses), g_first, eng.flat_p.clone()
+            finally:
+                raw.set_deterministic(prev)
+
+        l1, g1, p1 = run(True)
+        l2, g2, p2 = run(True)
+        l0, g0, p0 = run(False)
+        errs["det_loss_bits_" + tag] = float((l1 != l2).sum())
+        errs["det_grad_bits_" + tag] = float((g1 != g2).sum())
+        errs["det_param_bits_" + tag] = float((p1 != p2).sum())
+        errs["det_vs_default_grad_" + tag] = _l2(g1, g0)
+        l0b, g0b, _ = run(False)
+        info[tag] = {"default_run_to_run_grad_bits_differ": int((g0 != g0b).sum()),
+                     "default_run_to_run_grad_l2": _l2(g0b, g0), "losses": [round(float(x), 5) for x in l1]}
+    errs["info"] = info
+    return errs
+
+
+CASES["deterministic_training"] = (case_deterministic, _c())
+for _t in ("resnet", "v2psplit"):
+    for _k in ("det_loss_bits_", "det_grad_bits_", "det_param_bits_"):
+        TOLS[_k + _t] = 0.5
+    TOLS["det_vs_default_grad_" + _t] = 0.3       # same math, other summation order, on a chaotic model (see info)
+
+
 if __name__ == "__main__":
     name = sys.argv[1]
     errs = run_case(name)
