@@ -256,12 +256,12 @@ static int conv_fprop_impl(const void* x, const void* w_packed, void* y, const i
   if (rc) return rc;
   if (ck == 16) {
     if (bn != 64) return -4;
+    if (det) return -9;      // the 16-channel im2col mode has no persistent variant, hence no slotted statistics
     if (mt == 2) return launch_umma<64, 2, 2, A_IM2COL, false, false, EPI_STORE, 16>(tmA, tmB, p, tiles_m, 1, st);
     return launch_umma<64, 1, 4, A_IM2COL, false, false, EPI_STORE, 16>(tmA, tmB, p, tiles_m, 1, st);
   }
   // persistent tile walker (umma_persist.cuh): tile_hint bit4 forces it, bit5 forbids it
   const bool persist = det || (tile_hint & 16) != 0 || (!(tile_hint & 32) && conv_use_persist(g, p, bn, mt));
-  if (det && ck == 16) return -9;      // the 16-channel im2col mode has no persistent variant
   if (tcn) {       // fused TemporalBlock epilogue: its own instantiations of the persistent kernel
     if (!persist) return -5;
     if (bn == 64) return launch_persist<64, 1, 8, A_IM2COL, true>(tmA, tmB, p, ceil_div(Mpix, 128), st);
