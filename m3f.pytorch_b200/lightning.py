@@ -455,6 +455,16 @@ class Trainer:
         model.to(self.device)
         model.trainer = self
         model.on_gpu = self.device.type == "cuda"
+        if self.device.type == "cuda" and torch.backends.cudnn.deterministic and \
+                os.environ.get("M3T_DETERMINISTIC") is None:
+            # the reference's train.py:17 asks cuDNN for deterministic algorithms: the equivalent here is the slotted
+            # accumulation mode (bit-reproducible training, ~12 % slower); M3T_DETERMINISTIC=0 keeps the atomics
+            from . import raw
+            if not raw.DETERMINISTIC:
+                raw.set_deterministic(True)
+                if self.rank == 0:
+                    log.info("torch.backends.cudnn.deterministic is set: deterministic accumulation mode on "
+                             "(M3T_DETERMINISTIC=0 to keep the faster atomics)")
 
     def _run(self, model, mode):
         self._setup_process(model)
