@@ -25,6 +25,12 @@ extern "C" {
 int m3t_abi_version(void);
 /* Number of kernels launched by this library since load (bench.py reports it as gpu_launches). */
 long long m3t_launch_count(void);
+/* Programmatic dependent launch (csrc/common.cuh): every kernel of the library is launched with
+ * cudaLaunchAttributeProgrammaticStreamSerialization and orders itself behind the previous kernel of its stream with
+ * griddepcontrol.wait, so launch latency and CTA scheduling overlap the previous kernel's tail.  on = 0 / 1 sets the
+ * switch (default: environment M3T_PDL == "1"; m3t_b200.engine turns it on while it captures a small-shard training
+ * step), on < 0 only queries; returns the previous setting. */
+int m3t_set_pdl(int on);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Tensor-core GEMM (tcgen05 / TMEM / TMA).  D[M,N] = act( (A . B^T) * scale[n] + shift[n] + residual[m,n] )

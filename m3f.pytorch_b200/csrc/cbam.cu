@@ -33,6 +33,8 @@ __device__ __forceinline__ uint4 cb_pack8(const float (&f)[8]) {
 // ---- pooling over S: avg[f][c], mx[f][c], arg[f][c] (first maximum, as torch.max) -------------------------------
 __global__ void cbam_pool_hw_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ avg,
                                     float* __restrict__ mx, int* __restrict__ arg, int F, int S, int C) {
+  m3t::pdl_wait();
+  m3t::pdl_launch();
   const int cgs = C / 8;
   const long long total = (long long)F * cgs;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -67,6 +69,8 @@ __global__ void cbam_pool_hw_kernel(const __nv_bfloat16* __restrict__ x, float* 
 __global__ void cbam_pool_hw_bwd_kernel(const float* __restrict__ davg, const float* __restrict__ dmx,
                                         const int* __restrict__ arg, __nv_bfloat16* __restrict__ dx, int F, int S,
                                         int C) {
+  m3t::pdl_wait();
+  m3t::pdl_launch();
   const int cgs = C / 8;
   const long long total = (long long)F * S * cgs;
   const float inv = 1.f / (float)S;
@@ -89,6 +93,8 @@ __global__ void cbam_pool_hw_bwd_kernel(const float* __restrict__ davg, const fl
 // ---- y = x * s_c[f][c] ; backward dx = dy * s_c, ds_c[f][c] = sum_s dy * x ----------------------------------------
 __global__ void cbam_scale_c_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ sc,
                                     __nv_bfloat16* __restrict__ y, int F, int S, int C) {
+  m3t::pdl_wait();
+  m3t::pdl_launch();
   const int cgs = C / 8;
   const long long total = (long long)F * S * cgs;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -106,6 +112,8 @@ __global__ void cbam_scale_c_kernel(const __nv_bfloat16* __restrict__ x, const f
 __global__ void cbam_scale_c_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
                                         const float* __restrict__ sc, __nv_bfloat16* __restrict__ dx,
                                         float* __restrict__ dsc, int F, int S, int C) {
+  m3t::pdl_wait();
+  m3t::pdl_launch();
   const int cgs = C / 8;
   const long long total = (long long)F * cgs;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -135,6 +143,8 @@ __global__ void cbam_scale_c_bwd_kernel(const __nv_bfloat16* __restrict__ dy, co
 // ---- pooling over C, one warp per pixel: comp[f][0][s] = max_c, comp[f][1][s] = mean_c, carg[f][s] ----------------
 __global__ void cbam_pool_c_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ comp,
                                    int* __restrict__ carg, int F, int S, int C) {
+  m3t::pdl_wait();
+  m3t::pdl_launch();
   const int lane = threadIdx.x & 31;
   const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -166,6 +176,8 @@ __global__ void cbam_pool_c_kernel(const __nv_bfloat16* __restrict__ x, float* _
 // dx[f][s][c] = dcomp[f][1][s] / C + (c == carg[f][s]) * dcomp[f][0][s]
 __global__ void cbam_pool_c_bwd_kernel(const float* __restrict__ dcomp, const int* __restrict__ carg,
                                        __nv_bfloat16* __restrict__ dx, int F, int S, int C) {
+  m3t::pdl_wait();
+  m3t::pdl_launch();
   const int cgs = C / 8;
   const long long total = (long long)F * S * cgs;
   const float inv = 1.f / (float)C;
@@ -186,6 +198,8 @@ __global__ void cbam_pool_c_bwd_kernel(const float* __restrict__ dcomp, const in
 // ---- y = x * s_s[f][s] ; backward dx = dy * s_s, ds_s[f][s] = sum_c dy * x (one warp per pixel) --------------------
 __global__ void cbam_scale_s_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ ss,
                                     __nv_bfloat16* __restrict__ y, long long rows, int C) {
+  m3t::pdl_wait();
+  m3t::pdl_launch();
   const int cgs = C / 8;
   const long long total = rows * cgs;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -202,6 +216,8 @@ __global__ void cbam_scale_s_kernel(const __nv_bfloat16* __restrict__ x, const f
 __global__ void cbam_scale_s_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
                                         const float* __restrict__ ss, __nv_bfloat16* __restrict__ dx,
                                         float* __restrict__ dss, long long rows, int C) {
+  m3t::pdl_wait();
+  m3t::pdl_launch();
   const int lane = threadIdx.x & 31;
   const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -222,6 +238,8 @@ __global__ void cbam_scale_s_bwd_kernel(const __nv_bfloat16* __restrict__ dy, co
 // ---- the SpatialGate's conv: in fp32 [F][2][H][W], w [1][2][5][5], pad 2, no bias -> out fp32 [F][1][H][W] ----------
 __global__ void cbam_conv5_kernel(const float* __restrict__ in, const float* __restrict__ w, float* __restrict__ out,
                                   int F, int H, int W) {
+  m3t::pdl_wait();
+  m3t::pdl_launch();
   __shared__ float ws[50];
   if (threadIdx.x < 50) ws[threadIdx.x] = w[threadIdx.x];
   __syncthreads();
@@ -252,6 +270,8 @@ __global__ void cbam_conv5_kernel(const float* __restrict__ in, const float* __r
 // din[f][c][y][x] = sum_{kh,kw} w[c][kh][kw] * dout[f][y - kh + 2][x - kw + 2]
 __global__ void cbam_conv5_bwd_data_kernel(const float* __restrict__ dout, const float* __restrict__ w,
                                            float* __restrict__ din, int F, int H, int W) {
+  m3t::pdl_wait();
+  m3t::pdl_launch();
   __shared__ float ws[50];
   if (threadIdx.x < 50) ws[threadIdx.x] = w[threadIdx.x];
   __syncthreads();
@@ -281,6 +301,8 @@ __global__ void cbam_conv5_bwd_data_kernel(const float* __restrict__ dout, const
 // dw[c][kh][kw] = sum_{f,y,x} dout[f][y][x] * in[f][c][y + kh - 2][x + kw - 2]   (block per tap, fixed-order tree)
 __global__ void cbam_conv5_bwd_w_kernel(const float* __restrict__ dout, const float* __restrict__ in,
                                         float* __restrict__ dw, int F, int H, int W) {
+  m3t::pdl_wait();
+  m3t::pdl_launch();
   const int tap = blockIdx.x;                 // 0 .. 49
   const int c = tap / 25, kh = (tap / 5) % 5, kw = tap % 5;
   const long long total = (long long)F * H * W;
@@ -309,6 +331,8 @@ __global__ void cbam_conv5_bwd_w_kernel(const float* __restrict__ dout, const fl
 // ---- AvgPool3d((1,2,2), stride (1,2,2)) on CL [F][H][W][C] -> [F][H/2][W/2][C] (floor; DenseNet transitions) -----------
 __global__ void avgpool2x2_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int F, int H,
                                   int W, int C) {
+  m3t::pdl_wait();
+  m3t::pdl_launch();
   const int cgs = C / 8, P = H / 2, Q = W / 2;
   const long long total = (long long)F * P * Q * cgs;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -339,6 +363,8 @@ __global__ void avgpool2x2_kernel(const __nv_bfloat16* __restrict__ x, __nv_bflo
 
 __global__ void avgpool2x2_bwd_kernel(const __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__ dx, int F,
                                       int H, int W, int C) {
+  m3t::pdl_wait();
+  m3t::pdl_launch();
   const int cgs = C / 8, P = H / 2, Q = W / 2;
   const long long total = (long long)F * H * W * cgs;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -376,81 +402,81 @@ using namespace m3t;
 
 extern "C" int m3t_cbam_pool_hw(const void* x, float* avg, float* mx, int* arg, int F, int S, int C, void* stream) {
   if (C % 8 || F <= 0 || S <= 0) return -1;
-  cbam_pool_hw_kernel<<<cb_blocks((long long)F * (C / 8), 128), 128, 0, CB_ST(stream)>>>(CB_CBF(x), avg, mx, arg, F, S, C);
+  m3t::launch_k(cbam_pool_hw_kernel, dim3(cb_blocks((long long)F * (C / 8), 128)), dim3(128), 0, CB_ST(stream), CB_CBF(x), avg, mx, arg, F, S, C);
   count_launch();
   return launch_status();
 }
 extern "C" int m3t_cbam_pool_hw_bwd(const float* davg, const float* dmx, const int* arg, void* dx, int F, int S, int C,
                                     void* stream) {
   if (C % 8) return -1;
-  cbam_pool_hw_bwd_kernel<<<cb_blocks((long long)F * S * (C / 8)), 256, 0, CB_ST(stream)>>>(davg, dmx, arg, CB_BF(dx), F,
+  m3t::launch_k(cbam_pool_hw_bwd_kernel, dim3(cb_blocks((long long)F * S * (C / 8))), dim3(256), 0, CB_ST(stream), davg, dmx, arg, CB_BF(dx), F,
                                                                                           S, C);
   count_launch();
   return launch_status();
 }
 extern "C" int m3t_cbam_scale_c(const void* x, const float* sc, void* y, int F, int S, int C, void* stream) {
   if (C % 8) return -1;
-  cbam_scale_c_kernel<<<cb_blocks((long long)F * S * (C / 8)), 256, 0, CB_ST(stream)>>>(CB_CBF(x), sc, CB_BF(y), F, S, C);
+  m3t::launch_k(cbam_scale_c_kernel, dim3(cb_blocks((long long)F * S * (C / 8))), dim3(256), 0, CB_ST(stream), CB_CBF(x), sc, CB_BF(y), F, S, C);
   count_launch();
   return launch_status();
 }
 extern "C" int m3t_cbam_scale_c_bwd(const void* dy, const void* x, const float* sc, void* dx, float* dsc, int F, int S,
                                     int C, void* stream) {
   if (C % 8) return -1;
-  cbam_scale_c_bwd_kernel<<<cb_blocks((long long)F * (C / 8), 128), 128, 0, CB_ST(stream)>>>(CB_CBF(dy), CB_CBF(x), sc,
+  m3t::launch_k(cbam_scale_c_bwd_kernel, dim3(cb_blocks((long long)F * (C / 8), 128)), dim3(128), 0, CB_ST(stream), CB_CBF(dy), CB_CBF(x), sc,
                                                                                            CB_BF(dx), dsc, F, S, C);
   count_launch();
   return launch_status();
 }
 extern "C" int m3t_cbam_pool_c(const void* x, float* comp, int* carg, int F, int S, int C, void* stream) {
-  cbam_pool_c_kernel<<<cb_blocks((long long)F * S * 32), 256, 0, CB_ST(stream)>>>(CB_CBF(x), comp, carg, F, S, C);
+  m3t::launch_k(cbam_pool_c_kernel, dim3(cb_blocks((long long)F * S * 32)), dim3(256), 0, CB_ST(stream), CB_CBF(x), comp, carg, F, S, C);
   count_launch();
   return launch_status();
 }
 extern "C" int m3t_cbam_pool_c_bwd(const float* dcomp, const int* carg, void* dx, int F, int S, int C, void* stream) {
   if (C % 8) return -1;
-  cbam_pool_c_bwd_kernel<<<cb_blocks((long long)F * S * (C / 8)), 256, 0, CB_ST(stream)>>>(dcomp, carg, CB_BF(dx), F, S,
+  m3t::launch_k(cbam_pool_c_bwd_kernel, dim3(cb_blocks((long long)F * S * (C / 8))), dim3(256), 0, CB_ST(stream), dcomp, carg, CB_BF(dx), F, S,
                                                                                          C);
   count_launch();
   return launch_status();
 }
 extern "C" int m3t_cbam_scale_s(const void* x, const float* ss, void* y, long long rows, int C, void* stream) {
   if (C % 8) return -1;
-  cbam_scale_s_kernel<<<cb_blocks(rows * (C / 8)), 256, 0, CB_ST(stream)>>>(CB_CBF(x), ss, CB_BF(y), rows, C);
+  m3t::launch_k(cbam_scale_s_kernel, dim3(cb_blocks(rows * (C / 8))), dim3(256), 0, CB_ST(stream), CB_CBF(x), ss, CB_BF(y), rows, C);
   count_launch();
   return launch_status();
 }
 extern "C" int m3t_cbam_scale_s_bwd(const void* dy, const void* x, const float* ss, void* dx, float* dss,
                                     long long rows, int C, void* stream) {
-  cbam_scale_s_bwd_kernel<<<cb_blocks(rows * 32), 256, 0, CB_ST(stream)>>>(CB_CBF(dy), CB_CBF(x), ss, CB_BF(dx), dss,
+  m3t::launch_k(cbam_scale_s_bwd_kernel, dim3(cb_blocks(rows * 32)), dim3(256), 0, CB_ST(stream), CB_CBF(dy), CB_CBF(x), ss, CB_BF(dx), dss,
                                                                           rows, C);
   count_launch();
   return launch_status();
 }
 extern "C" int m3t_cbam_conv5(const float* in, const float* w, float* out, int F, int H, int W, void* stream) {
-  cbam_conv5_kernel<<<cb_blocks((long long)F * H * W), 256, 0, CB_ST(stream)>>>(in, w, out, F, H, W);
+  m3t::launch_k(cbam_conv5_kernel, dim3(cb_blocks((long long)F * H * W)), dim3(256), 0, CB_ST(stream), in, w, out, F, H, W);
   count_launch();
   return launch_status();
 }
 extern "C" int m3t_cbam_conv5_bwd(const float* dout, const float* in, const float* w, float* din, float* dw, int F,
                                   int H, int W, void* stream) {
-  cbam_conv5_bwd_data_kernel<<<cb_blocks((long long)F * 2 * H * W), 256, 0, CB_ST(stream)>>>(dout, w, din, F, H, W);
+  m3t::launch_k(cbam_conv5_bwd_data_kernel, dim3(cb_blocks((long long)F * 2 * H * W)), dim3(256), 0, CB_ST(stream), dout, w, din, F, H, W);
   count_launch();
-  cbam_conv5_bwd_w_kernel<<<50, 1024, 0, CB_ST(stream)>>>(dout, in, dw, F, H, W);
+  m3t::launch_k(cbam_conv5_bwd_w_kernel, dim3(50), dim3(1024), 0, CB_ST(stream), dout, in, dw, F, H, W);
   count_launch();
   return launch_status();
 }
 
 extern "C" int m3t_avgpool2x2(const void* x, void* y, int F, int H, int W, int C, void* stream) {
   if (C % 8 || H < 2 || W < 2) return -1;
-  avgpool2x2_kernel<<<cb_blocks((long long)F * (H / 2) * (W / 2) * (C / 8)), 256, 0, CB_ST(stream)>>>(CB_CBF(x), CB_BF(y),
+  m3t::launch_k(avgpool2x2_kernel, dim3(cb_blocks((long long)F * (H / 2) * (W / 2) * (C / 8))), dim3(256), 0, CB_ST(stream), CB_CBF(x), CB_BF(y),
                                                                                                      F, H, W, C);
   count_launch();
   return launch_status();
 }
 extern "C" int m3t_avgpool2x2_bwd(const void* dy, void* dx, int F, int H, int W, int C, void* stream) {
   if (C % 8 || H < 2 || W < 2) return -1;
-  avgpool2x2_bwd_kernel<<<cb_blocks((long long)F * H * W * (C / 8)), 256, 0, CB_ST(stream)>>>(CB_CBF(dy), CB_BF(dx), F, H,
+  m3t::launch_k(avgpool2x2_bwd_kernel, dim3(cb_blocks((long long)F * H * W * (C / 8))), dim3(256), 0, CB_ST(stream), CB_CBF(dy), CB_BF(dx), F, H,
                                                                                             W, C);
   count_launch();
   return launch_status();

@@ -94,6 +94,9 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // barriers, TMEM and descriptor prefetch above touch nothing a previous kernel wrote: they overlap its tail
+  m3t::pdl_wait();
+  m3t::pdl_launch();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -303,6 +306,9 @@ stem_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // barriers, TMEM and descriptor prefetch above touch nothing a previous kernel wrote: they overlap its tail
+  m3t::pdl_wait();
+  m3t::pdl_launch();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -504,7 +510,7 @@ extern "C" int m3t_conv3x3_c64_halo(const void* x, const void* w_packed, void* y
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = p.num_tiles < sms ? p.num_tiles : sms;
-  conv3x3_halo_kernel<<<grid, kHaloThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(tmX, tmW, p);
+  m3t::launch_k(conv3x3_halo_kernel, dim3(grid), dim3(kHaloThreads), smem, reinterpret_cast<cudaStream_t>(stream), tmX, tmW, p);
   count_launch();
   return launch_status();
 }
@@ -556,7 +562,7 @@ extern "C" int m3t_stem_fprop_halo(const void* xs, const void* w_packed, void* y
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = p.num_tiles < sms ? p.num_tiles : sms;
-  stem_halo_kernel<<<grid, kHaloThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(tmX, tmW, p);
+  m3t::launch_k(stem_halo_kernel, dim3(grid), dim3(kHaloThreads), smem, reinterpret_cast<cudaStream_t>(stream), tmX, tmW, p);
   count_launch();
   return launch_status();
 }

@@ -96,6 +96,9 @@ conv3x3_c128_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // barriers, TMEM and descriptor prefetch above touch nothing a previous kernel wrote: they overlap its tail
+  m3t::pdl_wait();
+  m3t::pdl_launch();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -302,7 +305,7 @@ extern "C" int m3t_conv3x3_c128_halo(const void* x, const void* w_packed, void* 
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = F < sms ? F : sms;
-  conv3x3_c128_halo_kernel<<<grid, kH128Threads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(tmX, tmW, p);
+  m3t::launch_k(conv3x3_c128_halo_kernel, dim3(grid), dim3(kH128Threads), smem, reinterpret_cast<cudaStream_t>(stream), tmX, tmW, p);
   count_launch();
   return launch_status();
 }

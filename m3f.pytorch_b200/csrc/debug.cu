@@ -11,6 +11,8 @@ namespace m3t {
 __global__ void __launch_bounds__(128, 1)
 dbg_rowshift_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     float* __restrict__ out, int shift_rows, int mode) {
+  m3t::pdl_wait();
+  m3t::pdl_launch();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;                 // 256 rows x 128 B
@@ -79,7 +81,7 @@ extern "C" int m3t_debug_rowshift(const void* A /*[256][64] bf16*/, const void* 
   const int smem = 256 * 128 + 64 * 128 + 64 + 1024;
   if (cudaFuncSetAttribute(dbg_rowshift_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
     return -20;
-  dbg_rowshift_kernel<<<1, 128, smem, reinterpret_cast<cudaStream_t>(stream)>>>(tmA, tmB, out, shift_rows, mode);
+  m3t::launch_k(dbg_rowshift_kernel, dim3(1), dim3(128), smem, reinterpret_cast<cudaStream_t>(stream), tmA, tmB, out, shift_rows, mode);
   count_launch();
   return launch_status();
 }

@@ -43,6 +43,8 @@ __device__ __forceinline__ void load8f(const float* p, float (&f)[8]) {
 template <typename T>
 __global__ void video_prep_s2d_kernel(const T* __restrict__ in, __nv_bfloat16* __restrict__ out, int B, int Tn, int H,
                                       int W, float mul, float add) {
+  m3t::pdl_wait();
+  m3t::pdl_launch();
   const int H2 = H / 2, W2 = W / 2;
   const long long total = (long long)B * Tn * H2 * W2;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -88,6 +90,8 @@ __global__ void video_prep_s2d_kernel(const T* __restrict__ in, __nv_bfloat16* _
 template <typename T>
 __global__ void video_prep_s2d_w4_kernel(const T* __restrict__ in, __nv_bfloat16* __restrict__ out, int B, int Tn,
                                          int H, int W, float mul, float add) {
+  m3t::pdl_wait();
+  m3t::pdl_launch();
   // One thread writes one complete 128-byte destination row (eight 16-byte stores): 4 taps x 12 channels + 16 zeros.
   // Each source pixel pair is read by the four destination pixels it is a tap of (L1-resident re-reads).
   // Measured at 4096 frames (2.26 GB): 0.69 ms = 3.3 TB/s.  Two "coalesced-store" rewrites were tried in round 2 and
@@ -147,6 +151,8 @@ __global__ void video_prep_s2d_w4_kernel(const T* __restrict__ in, __nv_bfloat16
 __global__ void video_augment_prep_s2d_w4_kernel(const uint8_t* __restrict__ frames, const int* __restrict__ params,
                                                  __nv_bfloat16* __restrict__ out, int B, int Tn, int Hs, int Ws, int H,
                                                  int W, float mul, float add) {
+  m3t::pdl_wait();
+  m3t::pdl_launch();
   const int H2 = H / 2, W2 = W / 2;
   const long long total = (long long)B * Tn * H2 * W2;
   const float fill = fmaf(127.5f, mul, add);
@@ -209,6 +215,8 @@ __global__ void bn_finalize_kernel(const float* __restrict__ stats, int C, float
                                    float* __restrict__ running_mean, float* __restrict__ running_var,
                                    float* __restrict__ mean_out, float* __restrict__ invstd_out,
                                    float* __restrict__ scale_out, float* __restrict__ shift_out) {
+  m3t::pdl_wait();
+  m3t::pdl_launch();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const float mean = stats[c] / count;
@@ -232,6 +240,8 @@ __global__ void bn_fold_kernel(int C, const float* __restrict__ gamma, const flo
                                const float* __restrict__ running_mean, const float* __restrict__ running_var,
                                const float* __restrict__ conv_bias, float eps, float* __restrict__ scale_out,
                                float* __restrict__ shift_out) {
+  m3t::pdl_wait();
+  m3t::pdl_launch();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const float sc = gamma[c] * rsqrtf(running_var[c] + eps);
@@ -247,6 +257,8 @@ __global__ void bn_act_kernel(const __nv_bfloat16* __restrict__ y, const float* 
                               const float* __restrict__ shift, const __nv_bfloat16* __restrict__ res,
                               const float* __restrict__ res_scale, const float* __restrict__ res_shift, int relu,
                               __nv_bfloat16* __restrict__ out, long long nvec, int C) {
+  m3t::pdl_wait();
+  m3t::pdl_launch();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec;
        i += (long long)gridDim.x * blockDim.x) {
     const int c = (int)((i * 8) % C);
@@ -283,6 +295,8 @@ __global__ void __launch_bounds__(256, 4)
 bn_act_fixed_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ scale,
                     const float* __restrict__ shift, const __nv_bfloat16* __restrict__ res,
                     __nv_bfloat16* __restrict__ out, long long nvec, int C) {
+  m3t::pdl_wait();
+  m3t::pdl_launch();
   const long long stride = (long long)gridDim.x * blockDim.x;
   long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const int c = (int)((i * 8) % C);
@@ -332,6 +346,8 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16
                      const float* __restrict__ invstd, const float* __restrict__ scale,
                      const float* __restrict__ shift, __nv_bfloat16* __restrict__ dz_out, float* __restrict__ sums,
                      long long rows, int C) {
+  m3t::pdl_wait();
+  m3t::pdl_launch();
   // block handles a strip of rows for all channels: thread -> (channel group cg = tid % (C/8), row lane)
   extern __shared__ float sh[];  // [2][C]
   const int cgs = C / 8;
@@ -423,6 +439,8 @@ __global__ void bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout, cons
                                     const float* __restrict__ invstd, const float* __restrict__ scale,
                                     const float* __restrict__ shift, const float* __restrict__ sums, float inv_count,
                                     int relu, __nv_bfloat16* __restrict__ dy, long long nvec, int C) {
+  m3t::pdl_wait();
+  m3t::pdl_launch();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec;
        i += (long long)gridDim.x * blockDim.x) {
     const int c = (int)((i * 8) % C);
@@ -463,6 +481,8 @@ bn_bwd_apply_fixed_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfl
                           const float* __restrict__ invstd, const float* __restrict__ scale,
                           const float* __restrict__ shift, const float* __restrict__ sums, float inv_count,
                           __nv_bfloat16* __restrict__ dy, long long nvec, int C) {
+  m3t::pdl_wait();
+  m3t::pdl_launch();
   const long long stride = (long long)gridDim.x * blockDim.x;
   long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const int c = (int)((i * 8) % C);
@@ -524,6 +544,8 @@ __global__ void bn_relu_maxpool_kernel(const __nv_bfloat16* __restrict__ y, cons
                                        const float* __restrict__ shift, __nv_bfloat16* __restrict__ out,
                                        uint8_t* __restrict__ idx, __nv_bfloat16* __restrict__ ymax, int F, int H, int W,
                                        int C, int cg_shift) {
+  m3t::pdl_wait();
+  m3t::pdl_launch();
   // index math in 32 bits (the host checks the element counts fit); C/8 is a power of two on this path
   const int P = (H + 2 * PAD - K) / S + 1, Q = (W + 2 * PAD - K) / S + 1;
   const unsigned cgs = (unsigned)C / 8;
@@ -577,6 +599,8 @@ __global__ void __launch_bounds__(256, 2) maxpool_bn_bwd_kernel(const __nv_bfloa
                                       const float* __restrict__ invstd, const float* __restrict__ scale,
                                       const float* __restrict__ shift, float* __restrict__ sums, float inv_count,
                                       __nv_bfloat16* __restrict__ dy, int F, int H, int W, int C, int cg_shift) {
+  m3t::pdl_wait();
+  m3t::pdl_launch();
   const int P = (H + 2 * PAD - K) / S + 1, Q = (W + 2 * PAD - K) / S + 1;
   const int cgs = C / 8;
   extern __shared__ float sh[];  // MODE 0: [2][C]
@@ -684,6 +708,8 @@ maxpool3s2_bn_bwd_kernel(const __nv_bfloat16* __restrict__ dout, const uint8_t* 
                          const float* __restrict__ invstd, const float* __restrict__ scale,
                          const float* __restrict__ shift, float* __restrict__ sums, float inv_count,
                          __nv_bfloat16* __restrict__ dy, int F, int H, int W, int C, int cg_shift) {
+  m3t::pdl_wait();
+  m3t::pdl_launch();
   const int P = H / 2, Q = W / 2;
   const int cgs = C / 8;
   extern __shared__ float sh[];  // MODE 0: [2][C]
@@ -801,6 +827,8 @@ __global__ void __launch_bounds__(256, 2)
 bn_relu_maxpool3s2_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ scale,
                           const float* __restrict__ shift, __nv_bfloat16* __restrict__ out, uint8_t* __restrict__ idx,
                           __nv_bfloat16* __restrict__ ymax, int F, int H, int W, int C, int cg_shift) {
+  m3t::pdl_wait();
+  m3t::pdl_launch();
   const int P = H / 2, Q = W / 2;
   const unsigned cgs = (unsigned)C / 8;
   const unsigned total = (unsigned)F * P * Q * cgs;
@@ -858,6 +886,8 @@ bn_relu_maxpool3s2_kernel(const __nv_bfloat16* __restrict__ y, const float* __re
 // ------------------------------------------------------------------------------------------------------------
 __global__ void avgpool_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out_bf16,
                                float* __restrict__ out_f32, int F, int HW, int C) {
+  m3t::pdl_wait();
+  m3t::pdl_launch();
   const int cgs = C / 8;
   const long long total = (long long)F * cgs;
   const float inv = 1.f / HW;
@@ -887,6 +917,8 @@ __global__ void avgpool_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat1
 // dx[f][s][c] = dout[f][c] / HW   (dout fp32 or bf16 -> dx bf16)
 template <typename T>
 __global__ void avgpool_bwd_kernel(const T* __restrict__ dout, __nv_bfloat16* __restrict__ dx, int F, int HW, int C) {
+  m3t::pdl_wait();
+  m3t::pdl_launch();
   const int cgs = C / 8;
   const long long total = (long long)F * HW * cgs;
   const float inv = 1.f / HW;
@@ -908,6 +940,8 @@ __global__ void avgpool_bwd_kernel(const T* __restrict__ dout, __nv_bfloat16* __
 // ------------------------------------------------------------------------------------------------------------
 __global__ void ncs_f32_to_nsc_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int C, int S,
                                            int Cpad) {
+  m3t::pdl_wait();
+  m3t::pdl_launch();
   __shared__ float tile[32][33];
   const int n = blockIdx.z;
   const int c0 = blockIdx.y * 32, s0 = blockIdx.x * 32;
@@ -923,6 +957,8 @@ __global__ void ncs_f32_to_nsc_bf16_kernel(const float* __restrict__ in, __nv_bf
 }
 template <typename TIN>
 __global__ void nsc_to_ncs_f32_kernel(const TIN* __restrict__ in, float* __restrict__ out, int C, int S, int Cpad) {
+  m3t::pdl_wait();
+  m3t::pdl_launch();
   __shared__ float tile[32][33];
   const int n = blockIdx.z;
   const int c0 = blockIdx.y * 32, s0 = blockIdx.x * 32;
@@ -945,6 +981,8 @@ __global__ void nsc_to_ncs_f32_kernel(const TIN* __restrict__ in, float* __restr
 // rows x cols fp32 (row stride ld_in) -> bf16 (row stride ld_out >= cols, pad columns zero-filled)
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ in, long long ld_in, __nv_bfloat16* __restrict__ out,
                                      long long ld_out, long long rows, int cols) {
+  m3t::pdl_wait();
+  m3t::pdl_launch();
   const long long total = rows * ld_out;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -955,6 +993,8 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ in, long long ld_
 }
 __global__ void cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ in, long long ld_in, float* __restrict__ out,
                                      long long ld_out, long long rows, int cols) {
+  m3t::pdl_wait();
+  m3t::pdl_launch();
   const long long total = rows * cols;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -971,6 +1011,8 @@ __global__ void cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ in, long 
 // ------------------------------------------------------------------------------------------------------------
 __global__ void pack_filter_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wf,
                                    __nv_bfloat16* __restrict__ wd, int Cout, int Cin, int taps) {
+  m3t::pdl_wait();
+  m3t::pdl_launch();
   const long long total = (long long)Cout * Cin * taps;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -987,6 +1029,8 @@ __global__ void pack_filter_kernel(const float* __restrict__ w, __nv_bfloat16* _
 // master [Cout][Cin][taps] write the fprop pack, the flipped dgrad pack and - for stride-2 convolutions whose data
 // gradient runs as parity sub-convolutions - the sub-filter of the output parity that tap t belongs to.
 __global__ void pack_filters_batched_kernel(const m3t_pack_entry* __restrict__ tab, int n, long long total) {
+  m3t::pdl_wait();
+  m3t::pdl_launch();
   // Work item g in [0, 2*total): the first half walks the FPROP pack in destination order (consecutive threads write
   // consecutive input channels), the second half the DGRAD pack in destination order (consecutive output channels) and
   // with it the parity sub-filter the tap belongs to: every store is coalesced, the gathers hit L1 / L2 (the fp32
@@ -1037,6 +1081,8 @@ __global__ void pack_filters_batched_kernel(const m3t_pack_entry* __restrict__ t
 
 __global__ void unpack_filter_grad_kernel(const float* __restrict__ dwp, float* __restrict__ dw, int Cout, int Cin,
                                           int taps) {
+  m3t::pdl_wait();
+  m3t::pdl_launch();
   const long long total = (long long)Cout * Cin * taps;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -1051,6 +1097,8 @@ __global__ void unpack_filter_grad_kernel(const float* __restrict__ dwp, float* 
 // Stride-2 dgrad helper: dy_up[n][2p][2q][c] = dy[n][p][q][c], zero elsewhere (Hup x Wup spatial extent).
 __global__ void zero_insert2_kernel(const __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__ up, int N, int P,
                                     int Q, int Hup, int Wup, int C) {
+  m3t::pdl_wait();
+  m3t::pdl_launch();
   const int cgs = C / 8;
   const long long total = (long long)N * Hup * Wup * cgs;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -1071,6 +1119,8 @@ __global__ void zero_insert2_kernel(const __nv_bfloat16* __restrict__ dy, __nv_b
 // out = a + b (bf16, vectors of 8) — gradient fan-in at residual forks
 __global__ void add_bf16_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b,
                                 __nv_bfloat16* __restrict__ out, long long nvec) {
+  m3t::pdl_wait();
+  m3t::pdl_launch();
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec; i += 4 * stride) {
     uint4 va[4], vb[4];
@@ -1101,6 +1151,8 @@ __global__ void add_bf16_kernel(const __nv_bfloat16* __restrict__ a, const __nv_
 // mask from (seed, i) instead of reading one.
 __global__ void dropout_bf16_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, long long nvec,
                                     unsigned thresh, float scale, unsigned long long seed) {
+  m3t::pdl_wait();
+  m3t::pdl_launch();
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec; i += stride) {
     float v[8];
@@ -1114,6 +1166,8 @@ __global__ void dropout_bf16_kernel(const __nv_bfloat16* __restrict__ x, __nv_bf
 // out_bf16[r][k] = idx[k] >= 0 ? w[r*row_stride + idx[k]] : 0      (filter re-layout, e.g. the space-to-depth stem)
 __global__ void gather_pack_kernel(const float* __restrict__ w, const int* __restrict__ idx,
                                    __nv_bfloat16* __restrict__ out, int rows, long long row_stride, int K) {
+  m3t::pdl_wait();
+  m3t::pdl_launch();
   const long long total = (long long)rows * K;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -1126,6 +1180,8 @@ __global__ void gather_pack_kernel(const float* __restrict__ w, const int* __res
 // dw[r*row_stride + idx[k]] = dwp[r][k] for idx[k] >= 0 (each target written once; the caller zero-fills dw)
 __global__ void scatter_unpack_kernel(const float* __restrict__ dwp, const int* __restrict__ idx,
                                       float* __restrict__ dw, int rows, long long row_stride, int K) {
+  m3t::pdl_wait();
+  m3t::pdl_launch();
   const long long total = (long long)rows * K;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -1139,6 +1195,8 @@ __global__ void scatter_unpack_kernel(const float* __restrict__ dwp, const int* 
 // column sums of a [rows][ld] bf16 matrix (bias gradients): out[c] = sum_r x[r][c], c < cols
 __global__ void colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, long long ld, long long rows, int cols,
                                    float* __restrict__ out) {
+  m3t::pdl_wait();
+  m3t::pdl_launch();
   // block: 32 columns x 8 row lanes
   __shared__ float part[8][33];
   const int c = blockIdx.x * 32 + threadIdx.x;
@@ -1159,6 +1217,8 @@ __global__ void colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, long lon
 // dz = dy * (out > 0)   (ReLU backward on bf16 vectors of 8)
 __global__ void relu_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ out,
                                 __nv_bfloat16* __restrict__ dz, long long nvec) {
+  m3t::pdl_wait();
+  m3t::pdl_launch();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec;
        i += (long long)gridDim.x * blockDim.x) {
     float d[8], o[8];
@@ -1176,6 +1236,8 @@ __global__ void relu_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv
 __global__ void tcn_epi_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ y,
                                    const __nv_bfloat16* __restrict__ t, __nv_bfloat16* __restrict__ dsum,
                                    __nv_bfloat16* __restrict__ da, float scale, long long nvec) {
+  m3t::pdl_wait();
+  m3t::pdl_launch();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec;
        i += (long long)gridDim.x * blockDim.x) {
     float d[8], tv[8];
@@ -1197,6 +1259,8 @@ __global__ void tcn_epi_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const _
 // 3x3 / pad 1 patches of a single-channel image as GEMM rows: out[(n*H + h)*W + w][kh*3 + kw] (9 taps, zero padded
 // to 16 columns) in bf16.  Feeds the 1-channel stem of the audio ResNet composition (BASELINE config 2).
 __global__ void patch3x3_c1_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int N, int H, int W) {
+  m3t::pdl_wait();
+  m3t::pdl_launch();
   const long long total = (long long)N * H * W;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -1235,6 +1299,8 @@ __global__ void gru_pack_weights_kernel(const float* __restrict__ w_ih, const fl
                                         const float* __restrict__ b_ih, const float* __restrict__ b_ih_r,
                                         const float* __restrict__ b_hh, const float* __restrict__ b_hh_r,
                                         float* __restrict__ bias) {
+  m3t::pdl_wait();
+  m3t::pdl_launch();
   const long long n_ih = 6LL * H * Ipad, n_hh = 6LL * H * H;
   const long long total = n_ih + n_hh;
   if (bias) {
@@ -1277,10 +1343,10 @@ extern "C" int m3t_video_prep_s2d(const void* video, int is_u8, void* out, int B
   if ((H | W) & 1) return -1;
   const long long items = (long long)B * T * (H / 2) * (W / 2);
   if (is_u8)
-    video_prep_s2d_kernel<uint8_t><<<ew_blocks(items), kEwThreads, 0, ST(stream)>>>(
+    m3t::launch_k(video_prep_s2d_kernel<uint8_t>, dim3(ew_blocks(items)), dim3(kEwThreads), 0, ST(stream), 
         reinterpret_cast<const uint8_t*>(video), BF(out), B, T, H, W, mul, add);
   else
-    video_prep_s2d_kernel<float><<<ew_blocks(items), kEwThreads, 0, ST(stream)>>>(
+    m3t::launch_k(video_prep_s2d_kernel<float>, dim3(ew_blocks(items)), dim3(kEwThreads), 0, ST(stream), 
         reinterpret_cast<const float*>(video), BF(out), B, T, H, W, mul, add);
   count_launch();
   return launch_status();
@@ -1291,10 +1357,10 @@ extern "C" int m3t_video_prep_s2d_w4(const void* video, int is_u8, void* out, in
   if ((H | W) & 1) return -1;
   const long long items = (long long)B * T * (H / 2) * (W / 2);
   if (is_u8)
-    video_prep_s2d_w4_kernel<uint8_t><<<ew_blocks(items), kEwThreads, 0, ST(stream)>>>(
+    m3t::launch_k(video_prep_s2d_w4_kernel<uint8_t>, dim3(ew_blocks(items)), dim3(kEwThreads), 0, ST(stream), 
         reinterpret_cast<const uint8_t*>(video), BF(out), B, T, H, W, mul, add);
   else
-    video_prep_s2d_w4_kernel<float><<<ew_blocks(items), kEwThreads, 0, ST(stream)>>>(
+    m3t::launch_k(video_prep_s2d_w4_kernel<float>, dim3(ew_blocks(items)), dim3(kEwThreads), 0, ST(stream), 
         reinterpret_cast<const float*>(video), BF(out), B, T, H, W, mul, add);
   count_launch();
   return launch_status();
@@ -1304,7 +1370,7 @@ extern "C" int m3t_video_augment_prep_s2d_w4(const void* frames_u8, const int* p
                                              int Ws, int H, int W, float mul, float add, void* stream) {
   if ((H | W) & 1 || H > Hs || W > Ws || B <= 0 || T <= 0) return -1;
   const long long items = (long long)B * T * (H / 2) * (W / 2);
-  video_augment_prep_s2d_w4_kernel<<<ew_blocks(items), kEwThreads, 0, ST(stream)>>>(
+  m3t::launch_k(video_augment_prep_s2d_w4_kernel, dim3(ew_blocks(items)), dim3(kEwThreads), 0, ST(stream), 
       reinterpret_cast<const uint8_t*>(frames_u8), params, BF(out), B, T, Hs, Ws, H, W, mul, add);
   count_launch();
   return launch_status();
@@ -1313,7 +1379,7 @@ extern "C" int m3t_video_augment_prep_s2d_w4(const void* frames_u8, const int* p
 extern "C" int m3t_bn_finalize(const float* stats, int C, double count, const float* gamma, const float* beta,
                                float eps, float momentum, float* running_mean, float* running_var, float* mean,
                                float* invstd, float* scale, float* shift, void* stream) {
-  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, ST(stream)>>>(stats, C, (float)count, gamma, beta, eps, momentum,
+  m3t::launch_k(bn_finalize_kernel, dim3((C + 127) / 128), dim3(128), 0, ST(stream), stats, C, (float)count, gamma, beta, eps, momentum,
                                                               running_mean, running_var, mean, invstd, scale, shift);
   count_launch();
   return launch_status();
@@ -1322,7 +1388,7 @@ extern "C" int m3t_bn_finalize(const float* stats, int C, double count, const fl
 extern "C" int m3t_bn_fold(int C, const float* gamma, const float* beta, const float* running_mean,
                            const float* running_var, const float* conv_bias, float eps, float* scale, float* shift,
                            void* stream) {
-  bn_fold_kernel<<<(C + 127) / 128, 128, 0, ST(stream)>>>(C, gamma, beta, running_mean, running_var, conv_bias, eps,
+  m3t::launch_k(bn_fold_kernel, dim3((C + 127) / 128), dim3(128), 0, ST(stream), C, gamma, beta, running_mean, running_var, conv_bias, eps,
                                                           scale, shift);
   count_launch();
   return launch_status();
@@ -1336,7 +1402,7 @@ extern "C" int m3t_bn_act(const void* y, const float* scale, const float* shift,
   if (kEwThreads % (C / 8) == 0 && !res_scale) {
     const int blocks = ew_blocks((nvec + 1) / 2);
 #define ACT_FIXED(HR, RL)                                                                                      \
-  bn_act_fixed_kernel<HR, RL><<<blocks, kEwThreads, 0, ST(stream)>>>(CBF(y), scale, shift, CBF(res), BF(out), nvec, C)
+  m3t::launch_k(bn_act_fixed_kernel<HR, RL>, dim3(blocks), dim3(kEwThreads), 0, ST(stream), CBF(y), scale, shift, CBF(res), BF(out), nvec, C)
     if (res && relu) ACT_FIXED(true, true);
     else if (res) ACT_FIXED(true, false);
     else if (relu) ACT_FIXED(false, true);
@@ -1345,7 +1411,7 @@ extern "C" int m3t_bn_act(const void* y, const float* scale, const float* shift,
     count_launch();
     return launch_status();
   }
-  bn_act_kernel<<<ew_blocks(nvec), kEwThreads, 0, ST(stream)>>>(CBF(y), scale, shift, CBF(res), res_scale, res_shift,
+  m3t::launch_k(bn_act_kernel, dim3(ew_blocks(nvec)), dim3(kEwThreads), 0, ST(stream), CBF(y), scale, shift, CBF(res), res_scale, res_shift,
                                                                 relu, BF(out), nvec, C);
   count_launch();
   return launch_status();
@@ -1370,7 +1436,7 @@ extern "C" int m3t_bn_bwd_reduce(const void* dout, const void* out, const void* 
   if (det) {       // bit 8 of `relu`: `sums` is the first of 1 + m3t_det_stats_slots() zero-filled copies
     const size_t smd = (size_t)rows_per_iter * 2 * C * sizeof(float);
 #define M3T_RED_DET(R)                                                                                              \
-  bn_bwd_reduce_kernel<R, true><<<(int)blocks, kEwThreads, smd, ST(stream)>>>(CBF(dout), CBF(out), CBF(y), mean,    \
+  m3t::launch_k(bn_bwd_reduce_kernel<R, true>, dim3((int)blocks), dim3(kEwThreads), smd, ST(stream), CBF(dout), CBF(out), CBF(y), mean,    \
                                                                              invstd, scale, shift, BF(dz_out), sums, \
                                                                              rows, C)
     if (relu == 0) M3T_RED_DET(0);
@@ -1381,13 +1447,13 @@ extern "C" int m3t_bn_bwd_reduce(const void* dout, const void* out, const void* 
     return launch_status();
   }
   if (relu == 0)
-    bn_bwd_reduce_kernel<0><<<(int)blocks, kEwThreads, sm, ST(stream)>>>(CBF(dout), CBF(out), CBF(y), mean, invstd,
+    m3t::launch_k(bn_bwd_reduce_kernel<0>, dim3((int)blocks), dim3(kEwThreads), sm, ST(stream), CBF(dout), CBF(out), CBF(y), mean, invstd,
                                                                         scale, shift, BF(dz_out), sums, rows, C);
   else if (relu == 1)
-    bn_bwd_reduce_kernel<1><<<(int)blocks, kEwThreads, sm, ST(stream)>>>(CBF(dout), CBF(out), CBF(y), mean, invstd,
+    m3t::launch_k(bn_bwd_reduce_kernel<1>, dim3((int)blocks), dim3(kEwThreads), sm, ST(stream), CBF(dout), CBF(out), CBF(y), mean, invstd,
                                                                         scale, shift, BF(dz_out), sums, rows, C);
   else
-    bn_bwd_reduce_kernel<2><<<(int)blocks, kEwThreads, sm, ST(stream)>>>(CBF(dout), CBF(out), CBF(y), mean, invstd,
+    m3t::launch_k(bn_bwd_reduce_kernel<2>, dim3((int)blocks), dim3(kEwThreads), sm, ST(stream), CBF(dout), CBF(out), CBF(y), mean, invstd,
                                                                         scale, shift, BF(dz_out), sums, rows, C);
   count_launch();
   return launch_status();
@@ -1402,7 +1468,7 @@ extern "C" int m3t_bn_bwd_apply(const void* dout, const void* out, const void* y
     const int blocks = ew_blocks((nvec + 1) / 2);
     const float ic = (float)(1.0 / count);
 #define APPLY_FIXED(R)                                                                                              \
-  bn_bwd_apply_fixed_kernel<R><<<blocks, kEwThreads, 0, ST(stream)>>>(CBF(dout), CBF(out), CBF(y), mean, invstd,    \
+  m3t::launch_k(bn_bwd_apply_fixed_kernel<R>, dim3(blocks), dim3(kEwThreads), 0, ST(stream), CBF(dout), CBF(out), CBF(y), mean, invstd,    \
                                                                      scale, shift, sums, ic, BF(dy), nvec, C)
     if (relu == 0) APPLY_FIXED(0);
     else if (relu == 1) APPLY_FIXED(1);
@@ -1411,7 +1477,7 @@ extern "C" int m3t_bn_bwd_apply(const void* dout, const void* out, const void* y
     count_launch();
     return launch_status();
   }
-  bn_bwd_apply_kernel<<<ew_blocks(nvec), kEwThreads, 0, ST(stream)>>>(CBF(dout), CBF(out), CBF(y), mean, invstd, scale,
+  m3t::launch_k(bn_bwd_apply_kernel, dim3(ew_blocks(nvec)), dim3(kEwThreads), 0, ST(stream), CBF(dout), CBF(out), CBF(y), mean, invstd, scale,
                                                                       shift, sums, (float)(1.0 / count), relu, BF(dy),
                                                                       nvec, C);
   count_launch();
@@ -1446,14 +1512,14 @@ static int bn_relu_maxpool_impl(const void* y, const float* scale, const float* 
   if ((long long)F * H * W * (C / 8) >= (1LL << 31)) return -6;
   const int blocks = ew_blocks(items);
   if (K == 3 && S == 2 && PAD == 1 && H % 2 == 0 && W % 2 == 0 && kEwThreads % (C / 8) == 0)
-    bn_relu_maxpool3s2_kernel<<<blocks, kEwThreads, 0, ST(stream)>>>(CBF(y), scale, shift, BF(out),
+    m3t::launch_k(bn_relu_maxpool3s2_kernel, dim3(blocks), dim3(kEwThreads), 0, ST(stream), CBF(y), scale, shift, BF(out),
                                                                    reinterpret_cast<uint8_t*>(idx), BF(ymax), F, H, W, C,
                                                                    sh);
   else if (K == 3 && S == 2 && PAD == 1)
-    bn_relu_maxpool_kernel<3, 2, 1><<<blocks, kEwThreads, 0, ST(stream)>>>(
+    m3t::launch_k(bn_relu_maxpool_kernel<3, 2, 1>, dim3(blocks), dim3(kEwThreads), 0, ST(stream), 
         CBF(y), scale, shift, BF(out), reinterpret_cast<uint8_t*>(idx), BF(ymax), F, H, W, C, sh);
   else if (K == 2 && S == 2 && PAD == 0)
-    bn_relu_maxpool_kernel<2, 2, 0><<<blocks, kEwThreads, 0, ST(stream)>>>(
+    m3t::launch_k(bn_relu_maxpool_kernel<2, 2, 0>, dim3(blocks), dim3(kEwThreads), 0, ST(stream), 
         CBF(y), scale, shift, BF(out), reinterpret_cast<uint8_t*>(idx), BF(ymax), F, H, W, C, sh);
   else
     return -1;
@@ -1466,11 +1532,11 @@ static void launch_pool_bwd(int mode, const void* dout, const void* idx, const v
                             const float* invstd, const float* scale, const float* shift, float* sums, double count,
                             void* dy, int F, int H, int W, int C, int sh, int blocks, cudaStream_t st) {
   if (mode == 0)
-    maxpool_bn_bwd_kernel<0, K, S, PAD><<<blocks, kEwThreads, 2 * C * sizeof(float), st>>>(
+    m3t::launch_k(maxpool_bn_bwd_kernel<0, K, S, PAD>, dim3(blocks), dim3(kEwThreads), 2 * C * sizeof(float), st, 
         CBF(dout), reinterpret_cast<const uint8_t*>(idx), CBF(y), mean, invstd, scale, shift, sums, 0.f, nullptr, F, H,
         W, C, sh);
   else
-    maxpool_bn_bwd_kernel<1, K, S, PAD><<<blocks, kEwThreads, 0, st>>>(
+    m3t::launch_k(maxpool_bn_bwd_kernel<1, K, S, PAD>, dim3(blocks), dim3(kEwThreads), 0, st, 
         CBF(dout), reinterpret_cast<const uint8_t*>(idx), CBF(y), mean, invstd, scale, shift, sums,
         (float)(1.0 / count), BF(dy), F, H, W, C, sh);
 }
@@ -1487,11 +1553,11 @@ extern "C" int m3t_maxpool_bn_bwd(int mode, const void* dout, const void* idx, c
   if (K == 3 && S == 2 && PAD == 1 && H % 2 == 0 && W % 2 == 0) {
     const int blocks4 = ew_blocks(items / 4);
     if (mode == 0)
-      maxpool3s2_bn_bwd_kernel<0><<<blocks4, kEwThreads, 2 * C * sizeof(float), ST(stream)>>>(
+      m3t::launch_k(maxpool3s2_bn_bwd_kernel<0>, dim3(blocks4), dim3(kEwThreads), 2 * C * sizeof(float), ST(stream), 
           CBF(dout), reinterpret_cast<const uint8_t*>(idx), CBF(y), mean, invstd, scale, shift, sums, 0.f, nullptr, F,
           H, W, C, sh);
     else
-      maxpool3s2_bn_bwd_kernel<1><<<blocks4, kEwThreads, 0, ST(stream)>>>(
+      m3t::launch_k(maxpool3s2_bn_bwd_kernel<1>, dim3(blocks4), dim3(kEwThreads), 0, ST(stream), 
           CBF(dout), reinterpret_cast<const uint8_t*>(idx), CBF(y), mean, invstd, scale, shift, sums,
           (float)(1.0 / count), BF(dy), F, H, W, C, sh);
   } else if (K == 3 && S == 2 && PAD == 1)
@@ -1508,7 +1574,7 @@ extern "C" int m3t_maxpool_bn_bwd(int mode, const void* dout, const void* idx, c
 
 extern "C" int m3t_avgpool(const void* x, void* out_bf16, float* out_f32, int F, int HW, int C, void* stream) {
   if (C % 8) return -1;
-  avgpool_kernel<<<ew_blocks((long long)F * C / 8), kEwThreads, 0, ST(stream)>>>(CBF(x), BF(out_bf16), out_f32, F, HW,
+  m3t::launch_k(avgpool_kernel, dim3(ew_blocks((long long)F * C / 8)), dim3(kEwThreads), 0, ST(stream), CBF(x), BF(out_bf16), out_f32, F, HW,
                                                                                  C);
   count_launch();
   return launch_status();
@@ -1518,17 +1584,17 @@ extern "C" int m3t_avgpool_bwd(const void* dout, int dout_f32, void* dx, int F, 
   if (C % 8) return -1;
   const long long items = (long long)F * HW * C / 8;
   if (dout_f32)
-    avgpool_bwd_kernel<float><<<ew_blocks(items), kEwThreads, 0, ST(stream)>>>(reinterpret_cast<const float*>(dout),
+    m3t::launch_k(avgpool_bwd_kernel<float>, dim3(ew_blocks(items)), dim3(kEwThreads), 0, ST(stream), reinterpret_cast<const float*>(dout),
                                                                                BF(dx), F, HW, C);
   else
-    avgpool_bwd_kernel<__nv_bfloat16><<<ew_blocks(items), kEwThreads, 0, ST(stream)>>>(CBF(dout), BF(dx), F, HW, C);
+    m3t::launch_k(avgpool_bwd_kernel<__nv_bfloat16>, dim3(ew_blocks(items)), dim3(kEwThreads), 0, ST(stream), CBF(dout), BF(dx), F, HW, C);
   count_launch();
   return launch_status();
 }
 
 extern "C" int m3t_ncs_f32_to_nsc_bf16(const float* in, void* out, int N, int C, int S, int Cpad, void* stream) {
   dim3 grid((S + 31) / 32, (Cpad + 31) / 32, N), block(32, 8);
-  ncs_f32_to_nsc_bf16_kernel<<<grid, block, 0, ST(stream)>>>(in, BF(out), C, S, Cpad);
+  m3t::launch_k(ncs_f32_to_nsc_bf16_kernel, dim3(grid), dim3(block), 0, ST(stream), in, BF(out), C, S, Cpad);
   count_launch();
   return launch_status();
 }
@@ -1537,16 +1603,16 @@ extern "C" int m3t_nsc_to_ncs_f32(const void* in, int in_f32, float* out, int N,
                                   void* stream) {
   dim3 grid((S + 31) / 32, (C + 31) / 32, N), block(32, 8);
   if (in_f32)
-    nsc_to_ncs_f32_kernel<float><<<grid, block, 0, ST(stream)>>>(reinterpret_cast<const float*>(in), out, C, S, Cpad);
+    m3t::launch_k(nsc_to_ncs_f32_kernel<float>, dim3(grid), dim3(block), 0, ST(stream), reinterpret_cast<const float*>(in), out, C, S, Cpad);
   else
-    nsc_to_ncs_f32_kernel<__nv_bfloat16><<<grid, block, 0, ST(stream)>>>(CBF(in), out, C, S, Cpad);
+    m3t::launch_k(nsc_to_ncs_f32_kernel<__nv_bfloat16>, dim3(grid), dim3(block), 0, ST(stream), CBF(in), out, C, S, Cpad);
   count_launch();
   return launch_status();
 }
 
 extern "C" int m3t_cast_f32_bf16(const float* in, long long ld_in, void* out, long long ld_out, long long rows,
                                  int cols, void* stream) {
-  cast_f32_bf16_kernel<<<ew_blocks(rows * ld_out), kEwThreads, 0, ST(stream)>>>(in, ld_in, BF(out), ld_out, rows,
+  m3t::launch_k(cast_f32_bf16_kernel, dim3(ew_blocks(rows * ld_out)), dim3(kEwThreads), 0, ST(stream), in, ld_in, BF(out), ld_out, rows,
                                                                                 cols);
   count_launch();
   return launch_status();
@@ -1554,7 +1620,7 @@ extern "C" int m3t_cast_f32_bf16(const float* in, long long ld_in, void* out, lo
 
 extern "C" int m3t_cast_bf16_f32(const void* in, long long ld_in, float* out, long long ld_out, long long rows,
                                  int cols, void* stream) {
-  cast_bf16_f32_kernel<<<ew_blocks(rows * cols), kEwThreads, 0, ST(stream)>>>(CBF(in), ld_in, out, ld_out, rows, cols);
+  m3t::launch_k(cast_bf16_f32_kernel, dim3(ew_blocks(rows * cols)), dim3(kEwThreads), 0, ST(stream), CBF(in), ld_in, out, ld_out, rows, cols);
   count_launch();
   return launch_status();
 }
@@ -1566,7 +1632,7 @@ extern "C" int m3t_gru_pack_weights(const float* w_ih, const float* w_ih_r, cons
   if (I <= 0 || H <= 0 || Ipad < I) return -1;
   if (bias && !(b_ih && b_ih_r && b_hh && b_hh_r)) return -1;
   const long long total = 6LL * H * Ipad + 6LL * H * H;
-  gru_pack_weights_kernel<<<ew_blocks(total), kEwThreads, 0, ST(stream)>>>(w_ih, w_ih_r, w_hh, w_hh_r, BF(wih), BF(whh),
+  m3t::launch_k(gru_pack_weights_kernel, dim3(ew_blocks(total)), dim3(kEwThreads), 0, ST(stream), w_ih, w_ih_r, w_hh, w_hh_r, BF(wih), BF(whh),
                                                                           BF(whht), I, Ipad, H, b_ih, b_ih_r, b_hh,
                                                                           b_hh_r, bias);
   count_launch();
@@ -1575,7 +1641,7 @@ extern "C" int m3t_gru_pack_weights(const float* w_ih, const float* w_ih_r, cons
 
 extern "C" int m3t_pack_filter(const float* w, void* w_fprop, void* w_dgrad, int Cout, int Cin, int taps,
                                void* stream) {
-  pack_filter_kernel<<<ew_blocks((long long)Cout * Cin * taps), kEwThreads, 0, ST(stream)>>>(w, BF(w_fprop),
+  m3t::launch_k(pack_filter_kernel, dim3(ew_blocks((long long)Cout * Cin * taps)), dim3(kEwThreads), 0, ST(stream), w, BF(w_fprop),
                                                                                            BF(w_dgrad), Cout, Cin,
                                                                                            taps);
   count_launch();
@@ -1584,13 +1650,13 @@ extern "C" int m3t_pack_filter(const float* w, void* w_fprop, void* w_dgrad, int
 
 extern "C" int m3t_pack_filters_batched(const m3t_pack_entry* table_dev, int n, long long total, void* stream) {
   if (n <= 0 || n > 128 || total <= 0) return -1;
-  pack_filters_batched_kernel<<<ew_blocks(2 * total), kEwThreads, 0, ST(stream)>>>(table_dev, n, total);
+  m3t::launch_k(pack_filters_batched_kernel, dim3(ew_blocks(2 * total)), dim3(kEwThreads), 0, ST(stream), table_dev, n, total);
   count_launch();
   return launch_status();
 }
 
 extern "C" int m3t_unpack_filter_grad(const float* dw_packed, float* dw, int Cout, int Cin, int taps, void* stream) {
-  unpack_filter_grad_kernel<<<ew_blocks((long long)Cout * Cin * taps), kEwThreads, 0, ST(stream)>>>(dw_packed, dw,
+  m3t::launch_k(unpack_filter_grad_kernel, dim3(ew_blocks((long long)Cout * Cin * taps)), dim3(kEwThreads), 0, ST(stream), dw_packed, dw,
                                                                                                   Cout, Cin, taps);
   count_launch();
   return launch_status();
@@ -1599,7 +1665,7 @@ extern "C" int m3t_unpack_filter_grad(const float* dw_packed, float* dw, int Cou
 extern "C" int m3t_zero_insert2(const void* dy, void* up, int N, int P, int Q, int Hup, int Wup, int C,
                                 void* stream) {
   if (C % 8) return -1;
-  zero_insert2_kernel<<<ew_blocks((long long)N * Hup * Wup * C / 8), kEwThreads, 0, ST(stream)>>>(CBF(dy), BF(up), N,
+  m3t::launch_k(zero_insert2_kernel, dim3(ew_blocks((long long)N * Hup * Wup * C / 8)), dim3(kEwThreads), 0, ST(stream), CBF(dy), BF(up), N,
                                                                                                  P, Q, Hup, Wup, C);
   count_launch();
   return launch_status();
@@ -1607,14 +1673,14 @@ extern "C" int m3t_zero_insert2(const void* dy, void* up, int N, int P, int Q, i
 
 extern "C" int m3t_add_bf16(const void* a, const void* b, void* out, long long n, void* stream) {
   if (n % 8) return -1;
-  add_bf16_kernel<<<ew_blocks((n / 8 + 3) / 4), kEwThreads, 0, ST(stream)>>>(CBF(a), CBF(b), BF(out), n / 8);
+  m3t::launch_k(add_bf16_kernel, dim3(ew_blocks((n / 8 + 3) / 4)), dim3(kEwThreads), 0, ST(stream), CBF(a), CBF(b), BF(out), n / 8);
   count_launch();
   return launch_status();
 }
 
 extern "C" int m3t_gather_pack_bf16(const float* w, const int* idx, void* out, int rows, long long row_stride, int K,
                                     void* stream) {
-  gather_pack_kernel<<<ew_blocks((long long)rows * K), kEwThreads, 0, ST(stream)>>>(w, idx, BF(out), rows, row_stride,
+  m3t::launch_k(gather_pack_kernel, dim3(ew_blocks((long long)rows * K)), dim3(kEwThreads), 0, ST(stream), w, idx, BF(out), rows, row_stride,
                                                                                   K);
   count_launch();
   return launch_status();
@@ -1622,7 +1688,7 @@ extern "C" int m3t_gather_pack_bf16(const float* w, const int* idx, void* out, i
 
 extern "C" int m3t_scatter_unpack_f32(const float* dwp, const int* idx, float* dw, int rows, long long row_stride,
                                       int K, void* stream) {
-  scatter_unpack_kernel<<<ew_blocks((long long)rows * K), kEwThreads, 0, ST(stream)>>>(dwp, idx, dw, rows, row_stride,
+  m3t::launch_k(scatter_unpack_kernel, dim3(ew_blocks((long long)rows * K)), dim3(kEwThreads), 0, ST(stream), dwp, idx, dw, rows, row_stride,
                                                                                      K);
   count_launch();
   return launch_status();
@@ -1630,6 +1696,8 @@ extern "C" int m3t_scatter_unpack_f32(const float* dwp, const int* idx, float* d
 
 // buf = (1 + nslots) consecutive copies of a `len`-float vector: copy 0 += copy 1 + copy 2 + ... in index order.
 __global__ void det_reduce_kernel(float* __restrict__ buf, long long len, int nslots) {
+  m3t::pdl_wait();
+  m3t::pdl_launch();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < len;
        i += (long long)gridDim.x * blockDim.x) {
     float s = 0.f;
@@ -1643,7 +1711,7 @@ extern "C" int m3t_det_cta_slots(void) { return 148; }
 
 extern "C" int m3t_det_reduce(float* buf, long long len, int nslots, void* stream) {
   if (!buf || len <= 0 || nslots <= 0) return -1;
-  det_reduce_kernel<<<ew_blocks(len), kEwThreads, 0, ST(stream)>>>(buf, len, nslots);
+  m3t::launch_k(det_reduce_kernel, dim3(ew_blocks(len)), dim3(kEwThreads), 0, ST(stream), buf, len, nslots);
   count_launch();
   return launch_status();
 }
@@ -1655,14 +1723,14 @@ extern "C" int m3t_colsum_bf16(const void* x, long long ld, long long rows, int 
   if (gy > 148) gy = 148;
   if (gy < 1 || det) gy = 1;
   dim3 grid((cols + 31) / 32, (unsigned)gy), block(32, 8);
-  colsum_bf16_kernel<<<grid, block, 0, ST(stream)>>>(CBF(x), ld, rows, cols, out);
+  m3t::launch_k(colsum_bf16_kernel, dim3(grid), dim3(block), 0, ST(stream), CBF(x), ld, rows, cols, out);
   count_launch();
   return launch_status();
 }
 
 extern "C" int m3t_relu_bwd_bf16(const void* dy, const void* out, void* dz, long long n, void* stream) {
   if (n % 8) return -1;
-  relu_bwd_kernel<<<ew_blocks(n / 8), kEwThreads, 0, ST(stream)>>>(CBF(dy), CBF(out), BF(dz), n / 8);
+  m3t::launch_k(relu_bwd_kernel, dim3(ew_blocks(n / 8)), dim3(kEwThreads), 0, ST(stream), CBF(dy), CBF(out), BF(dz), n / 8);
   count_launch();
   return launch_status();
 }
@@ -1670,7 +1738,7 @@ extern "C" int m3t_relu_bwd_bf16(const void* dy, const void* out, void* dz, long
 extern "C" int m3t_tcn_epilogue_bwd_bf16(const void* dy, const void* y, const void* t, void* dsum, void* da,
                                          float scale, long long n, void* stream) {
   if (n % 8 || !dy || !t || !da || ((y != nullptr) != (dsum != nullptr))) return -1;
-  tcn_epi_bwd_kernel<<<ew_blocks(n / 8), kEwThreads, 0, ST(stream)>>>(CBF(dy), CBF(y), CBF(t), BF(dsum), BF(da), scale,
+  m3t::launch_k(tcn_epi_bwd_kernel, dim3(ew_blocks(n / 8)), dim3(kEwThreads), 0, ST(stream), CBF(dy), CBF(y), CBF(t), BF(dsum), BF(da), scale,
                                                                       n / 8);
   count_launch();
   return launch_status();
@@ -1679,14 +1747,14 @@ extern "C" int m3t_tcn_epilogue_bwd_bf16(const void* dy, const void* y, const vo
 extern "C" int m3t_dropout_bf16(const void* x, void* y, long long n, float p, unsigned long long seed, void* stream) {
   if (n % 8 || !(p >= 0.f) || !(p < 1.f)) return -1;
   const unsigned thresh = dropout_threshold(p);
-  dropout_bf16_kernel<<<ew_blocks(n / 8), kEwThreads, 0, ST(stream)>>>(CBF(x), BF(y), n / 8, thresh, 1.f / (1.f - p),
+  m3t::launch_k(dropout_bf16_kernel, dim3(ew_blocks(n / 8)), dim3(kEwThreads), 0, ST(stream), CBF(x), BF(y), n / 8, thresh, 1.f / (1.f - p),
                                                                        seed);
   count_launch();
   return launch_status();
 }
 
 extern "C" int m3t_patch3x3_c1(const float* x, void* out, int N, int H, int W, void* stream) {
-  patch3x3_c1_kernel<<<ew_blocks((long long)N * H * W), kEwThreads, 0, ST(stream)>>>(x, BF(out), N, H, W);
+  m3t::launch_k(patch3x3_c1_kernel, dim3(ew_blocks((long long)N * H * W)), dim3(kEwThreads), 0, ST(stream), x, BF(out), N, H, W);
   count_launch();
   return launch_status();
 }

@@ -54,6 +54,8 @@ __device__ __forceinline__ int wgt_piece(int nt, int k) {
 __global__ void split3_kernel(const float* __restrict__ x, const float* __restrict__ res, int relu,
                               float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out3, long long rows, int C,
                               int nt) {
+  m3t::pdl_wait();
+  m3t::pdl_launch();
   const long long total = rows * C;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -74,6 +76,8 @@ __global__ void split3_kernel(const float* __restrict__ x, const float* __restri
 //   -> bf16 [N][G][3C] = [hi | lo | hi] per group
 __global__ void pack_split3_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, long long N, int G,
                                    int C, int tap_minor, int cpad, int nt) {
+  m3t::pdl_wait();
+  m3t::pdl_launch();
   const long long total = N * G * C;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -94,6 +98,8 @@ __global__ void pack_split3_kernel(const float* __restrict__ w, __nv_bfloat16* _
 template <typename T>
 __global__ void video_prep_s2d_split3_kernel(const T* __restrict__ in, __nv_bfloat16* __restrict__ out, int B, int Tn,
                                              int H, int W, float mul, float add, int nt, int cpad) {
+  m3t::pdl_wait();
+  m3t::pdl_launch();
   const int H2 = H / 2, W2 = W / 2;
   const long long total = (long long)B * Tn * H2 * W2;
   const __nv_bfloat16 z = __float2bfloat16(0.f);
@@ -125,6 +131,8 @@ __global__ void video_prep_s2d_split3_kernel(const T* __restrict__ in, __nv_bflo
 
 // 2x2 / stride 2 max-pool over (H,W) of [F][H][W][C] float32 (nn.MaxPool3d((1,2,2),(1,2,2)), floor mode)
 __global__ void maxpool2x2_f32_kernel(const float* __restrict__ x, float* __restrict__ out, int F, int H, int W, int C) {
+  m3t::pdl_wait();
+  m3t::pdl_launch();
   const int P = H / 2, Q = W / 2;
   const long long total = (long long)F * P * Q * C;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -145,6 +153,8 @@ __global__ void maxpool2x2_f32_kernel(const float* __restrict__ x, float* __rest
 template <typename T>
 __global__ void video_prep_s2d_w4_split3_kernel(const T* __restrict__ in, __nv_bfloat16* __restrict__ out, int B, int Tn,
                                                 int H, int W, float mul, float add, int nt) {
+  m3t::pdl_wait();
+  m3t::pdl_launch();
   const int H2 = H / 2, W2 = W / 2;
   const long long total = (long long)B * Tn * H2 * W2 * 4;   // one thread per (pixel, tap jw)
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -185,6 +195,8 @@ __global__ void video_prep_s2d_w4_split3_kernel(const T* __restrict__ in, __nv_b
 
 // 3x3 / stride 2 / pad 1 max-pool over [F][H][W][C] float32 (-inf padding, as nn.MaxPool)
 __global__ void maxpool3s2_f32_kernel(const float* __restrict__ x, float* __restrict__ out, int F, int H, int W, int C) {
+  m3t::pdl_wait();
+  m3t::pdl_launch();
   const int P = (H + 2 - 3) / 2 + 1, Q = (W + 2 - 3) / 2 + 1;
   const long long total = (long long)F * P * Q * C;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -210,6 +222,8 @@ __global__ void maxpool3s2_f32_kernel(const float* __restrict__ x, float* __rest
 }
 
 __global__ void avgpool_f32_kernel(const float* __restrict__ x, float* __restrict__ out, int F, int HW, int C) {
+  m3t::pdl_wait();
+  m3t::pdl_launch();
   const long long total = (long long)F * C;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -225,6 +239,8 @@ __global__ void avgpool_f32_kernel(const float* __restrict__ x, float* __restric
 __global__ void att_mix_f32_kernel(const float* __restrict__ xa, const float* __restrict__ xv,
                                    const float* __restrict__ sa, const float* __restrict__ sv, float* __restrict__ f,
                                    long long rows, int C) {
+  m3t::pdl_wait();
+  m3t::pdl_launch();
   const long long total = rows * C;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -243,6 +259,8 @@ constexpr int kGruF32Rows = 8;
 __global__ void __launch_bounds__(256) gru_step_f32_kernel(const float* __restrict__ gi, const float* __restrict__ w,
                                                            const float* __restrict__ b_hh, float* __restrict__ out,
                                                            int B, int T, int H, int step) {
+  m3t::pdl_wait();
+  m3t::pdl_launch();
   extern __shared__ float hs[];   // [kGruF32Rows][H]
   const int dir = blockIdx.z;
   const int b0 = blockIdx.y * kGruF32Rows;
@@ -309,7 +327,7 @@ using namespace m3t;
 extern "C" int m3t_split3_bf16(const float* x, const float* res, int relu, float* out_f32, void* out3, long long rows,
                                int C, int nterms, void* stream) {
   if (rows <= 0 || C <= 0 || (nterms != 3 && nterms != 6)) return -1;
-  split3_kernel<<<fp_blocks(rows * C), kFpThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  m3t::launch_k(split3_kernel, dim3(fp_blocks(rows * C)), dim3(kFpThreads), 0, reinterpret_cast<cudaStream_t>(stream), 
       x, res, relu, out_f32, reinterpret_cast<__nv_bfloat16*>(out3), rows, C, nterms);
   count_launch();
   return launch_status();
@@ -322,7 +340,7 @@ extern "C" int m3t_pack_split3_bf16(const float* w, void* out, long long N, int 
   if (cpad < nterms * C) return -1;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (cpad > nterms * C && cudaMemsetAsync(out, 0, (size_t)N * G * cpad * 2, st) != cudaSuccess) return -21;
-  pack_split3_kernel<<<fp_blocks(N * G * C), kFpThreads, 0, st>>>(w, reinterpret_cast<__nv_bfloat16*>(out), N, G, C,
+  m3t::launch_k(pack_split3_kernel, dim3(fp_blocks(N * G * C)), dim3(kFpThreads), 0, st, w, reinterpret_cast<__nv_bfloat16*>(out), N, G, C,
                                                                    tap_minor, cpad, nterms);
   count_launch();
   return launch_status();
@@ -334,18 +352,17 @@ extern "C" int m3t_video_prep_s2d_split3(const void* video, int is_u8, void* out
   const long long items = (long long)B * T * (H / 2) * (W / 2);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (is_u8)
-    video_prep_s2d_split3_kernel<uint8_t><<<fp_blocks(items), kFpThreads, 0, st>>>(
+    m3t::launch_k(video_prep_s2d_split3_kernel<uint8_t>, dim3(fp_blocks(items)), dim3(kFpThreads), 0, st, 
         reinterpret_cast<const uint8_t*>(video), reinterpret_cast<__nv_bfloat16*>(out), B, T, H, W, mul, add, nterms, cpad);
   else
-    video_prep_s2d_split3_kernel<float><<<fp_blocks(items), kFpThreads, 0, st>>>(
+    m3t::launch_k(video_prep_s2d_split3_kernel<float>, dim3(fp_blocks(items)), dim3(kFpThreads), 0, st, 
         reinterpret_cast<const float*>(video), reinterpret_cast<__nv_bfloat16*>(out), B, T, H, W, mul, add, nterms, cpad);
   count_launch();
   return launch_status();
 }
 
 extern "C" int m3t_maxpool2x2_f32(const float* x, float* out, int F, int H, int W, int C, void* stream) {
-  maxpool2x2_f32_kernel<<<fp_blocks((long long)F * (H / 2) * (W / 2) * C), kFpThreads, 0,
-                          reinterpret_cast<cudaStream_t>(stream)>>>(x, out, F, H, W, C);
+  m3t::launch_k(maxpool2x2_f32_kernel, dim3(fp_blocks((long long)F * (H / 2) * (W / 2) * C)), dim3(kFpThreads), 0, reinterpret_cast<cudaStream_t>(stream), x, out, F, H, W, C);
   count_launch();
   return launch_status();
 }
@@ -356,10 +373,10 @@ extern "C" int m3t_video_prep_s2d_w4_split3(const void* video, int is_u8, void* 
   const long long items = (long long)B * T * (H / 2) * (W / 2) * 4;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (is_u8)
-    video_prep_s2d_w4_split3_kernel<uint8_t><<<fp_blocks(items), kFpThreads, 0, st>>>(
+    m3t::launch_k(video_prep_s2d_w4_split3_kernel<uint8_t>, dim3(fp_blocks(items)), dim3(kFpThreads), 0, st, 
         reinterpret_cast<const uint8_t*>(video), reinterpret_cast<__nv_bfloat16*>(out), B, T, H, W, mul, add, nterms);
   else
-    video_prep_s2d_w4_split3_kernel<float><<<fp_blocks(items), kFpThreads, 0, st>>>(
+    m3t::launch_k(video_prep_s2d_w4_split3_kernel<float>, dim3(fp_blocks(items)), dim3(kFpThreads), 0, st, 
         reinterpret_cast<const float*>(video), reinterpret_cast<__nv_bfloat16*>(out), B, T, H, W, mul, add, nterms);
   count_launch();
   return launch_status();
@@ -367,14 +384,14 @@ extern "C" int m3t_video_prep_s2d_w4_split3(const void* video, int is_u8, void* 
 
 extern "C" int m3t_maxpool3s2_f32(const float* x, float* out, int F, int H, int W, int C, void* stream) {
   const int P = (H - 1) / 2 + 1, Q = (W - 1) / 2 + 1;
-  maxpool3s2_f32_kernel<<<fp_blocks((long long)F * P * Q * C), kFpThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  m3t::launch_k(maxpool3s2_f32_kernel, dim3(fp_blocks((long long)F * P * Q * C)), dim3(kFpThreads), 0, reinterpret_cast<cudaStream_t>(stream), 
       x, out, F, H, W, C);
   count_launch();
   return launch_status();
 }
 
 extern "C" int m3t_avgpool_f32(const float* x, float* out, int F, int HW, int C, void* stream) {
-  avgpool_f32_kernel<<<fp_blocks((long long)F * C), kFpThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, out, F,
+  m3t::launch_k(avgpool_f32_kernel, dim3(fp_blocks((long long)F * C)), dim3(kFpThreads), 0, reinterpret_cast<cudaStream_t>(stream), x, out, F,
                                                                                                            HW, C);
   count_launch();
   return launch_status();
@@ -382,7 +399,7 @@ extern "C" int m3t_avgpool_f32(const float* x, float* out, int F, int HW, int C,
 
 extern "C" int m3t_att_mix_f32(const float* x_a, const float* x_v, const float* s_a, const float* s_v, float* f,
                                long long rows, int C, void* stream) {
-  att_mix_f32_kernel<<<fp_blocks(rows * C), kFpThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x_a, x_v, s_a, s_v,
+  m3t::launch_k(att_mix_f32_kernel, dim3(fp_blocks(rows * C)), dim3(kFpThreads), 0, reinterpret_cast<cudaStream_t>(stream), x_a, x_v, s_a, s_v,
                                                                                                     f, rows, C);
   count_launch();
   return launch_status();
@@ -402,7 +419,7 @@ extern "C" int m3t_gru_fwd_f32(const float* gi, const float* w_hh, const float* 
   const int gx = H >= 64 ? H / 64 : 1;   // 64 hidden units per block (8 warps x 8 passes)
   dim3 grid((unsigned)gx, (unsigned)((B + kGruF32Rows - 1) / kGruF32Rows), 2);
   for (int step = 0; step < T; ++step) {
-    gru_step_f32_kernel<<<grid, 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(gi, w_hh, b_hh, out, B, T, H, step);
+    m3t::launch_k(gru_step_f32_kernel, dim3(grid), dim3(256), smem, reinterpret_cast<cudaStream_t>(stream), gi, w_hh, b_hh, out, B, T, H, step);
     count_launch();
   }
   return launch_status();

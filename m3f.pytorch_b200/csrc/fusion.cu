@@ -25,6 +25,8 @@ __device__ __forceinline__ float sigm(float x) { return 1.f / (1.f + __expf(-x))
 __global__ void att_mix_fwd_kernel(const __nv_bfloat16* __restrict__ xa, const __nv_bfloat16* __restrict__ xv,
                                    const float* __restrict__ sa, const float* __restrict__ sv,
                                    __nv_bfloat16* __restrict__ f, float* __restrict__ wv_out, long long rows, int C) {
+  m3t::pdl_wait();
+  m3t::pdl_launch();
   const int lane = threadIdx.x & 31;
   const int nvec = C / 8;
   for (long long r = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5; r < rows;
@@ -51,6 +53,8 @@ __global__ void att_mix_bwd_kernel(const __nv_bfloat16* __restrict__ df, const _
                                    const float* __restrict__ sv, __nv_bfloat16* __restrict__ dxa,
                                    __nv_bfloat16* __restrict__ dxv, float* __restrict__ dsa, float* __restrict__ dsv,
                                    long long rows, int C) {
+  m3t::pdl_wait();
+  m3t::pdl_launch();
   const int lane = threadIdx.x & 31;
   const int nvec = C / 8;
   for (long long r = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5; r < rows;
@@ -98,7 +102,7 @@ extern "C" int m3t_att_mix_fwd(const void* x_a, const void* x_v, const float* s_
   if (C % 8) return -1;
   long long blocks = (rows * 32 + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
-  att_mix_fwd_kernel<<<(int)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  m3t::launch_k(att_mix_fwd_kernel, dim3((int)blocks), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), 
       reinterpret_cast<const __nv_bfloat16*>(x_a), reinterpret_cast<const __nv_bfloat16*>(x_v), s_a, s_v,
       reinterpret_cast<__nv_bfloat16*>(f), w_v, rows, C);
   count_launch();
@@ -111,7 +115,7 @@ extern "C" int m3t_att_mix_bwd(const void* df, const void* x_a, const void* x_v,
   if (C % 8) return -1;
   long long blocks = (rows * 32 + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
-  att_mix_bwd_kernel<<<(int)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  m3t::launch_k(att_mix_bwd_kernel, dim3((int)blocks), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), 
       reinterpret_cast<const __nv_bfloat16*>(df), reinterpret_cast<const __nv_bfloat16*>(x_a),
       reinterpret_cast<const __nv_bfloat16*>(x_v), s_a, s_v, reinterpret_cast<__nv_bfloat16*>(dx_a),
       reinterpret_cast<__nv_bfloat16*>(dx_v), ds_a, ds_v, rows, C);
@@ -156,6 +160,8 @@ __global__ void __launch_bounds__(kLossThreads, 1)
 av_loss_kernel(const float* __restrict__ y, const float* __restrict__ lab_v, const float* __restrict__ lab_a,
                const long long* __restrict__ cls, const unsigned char* __restrict__ valid, int N, int C, int iv, int ia,
                int n_logits, float lambda, float w_ce, float* __restrict__ out, float* __restrict__ dy) {
+  m3t::pdl_wait();
+  m3t::pdl_launch();
   __shared__ double red[33];
   const int tid = threadIdx.x;
   // ---- first moments ----
@@ -235,7 +241,7 @@ extern "C" int m3t_av_loss(const float* y_hat, const float* label_v, const float
                            float w_ce, float* out4, float* dy, void* stream) {
   if (N < 2 || C < 2 || idx_v < 0 || idx_v >= C || idx_a < 0 || idx_a >= C || n_logits < 0 || n_logits > C) return -1;
   if (n_logits > 0 && (!cls || !valid)) return -1;
-  m3t::av_loss_kernel<<<1, m3t::kLossThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  m3t::launch_k(m3t::av_loss_kernel, dim3(1), dim3(m3t::kLossThreads), 0, reinterpret_cast<cudaStream_t>(stream), 
       y_hat, label_v, label_a, cls, valid, N, C, idx_v, idx_a, n_logits, lambda, w_ce, out4, dy);
   m3t::count_launch();
   return m3t::launch_status();

@@ -20,7 +20,7 @@ static int launch_umma(const CUtensorMap& tmA, const CUtensorMap& tmB, const Umm
     attr_done = true;
   }
   dim3 grid((unsigned)(tiles_m * p.tiles_n), (unsigned)splits, 1);
-  kern<<<grid, kUmmaThreads, smem, st>>>(tmA, tmB, p);
+  m3t::launch_k(kern, dim3(grid), dim3(kUmmaThreads), smem, st, tmA, tmB, p);
   count_launch();
   return launch_status();
 }
@@ -44,7 +44,7 @@ static int launch_persist(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
   const int num_tiles = tiles_m * p.tiles_n;
   int grid = num_tiles < sms ? num_tiles : sms;
   if (p.tiles_n <= grid) grid -= grid % p.tiles_n;   // a CTA then keeps one column block (register-resident BN stats)
-  kern<<<grid, kUmmaThreads, smem, st>>>(tmA, tmB, p, num_tiles);
+  m3t::launch_k(kern, dim3(grid), dim3(kUmmaThreads), smem, st, tmA, tmB, p, num_tiles);
   count_launch();
   return launch_status();
 }

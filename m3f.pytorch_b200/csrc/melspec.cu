@@ -26,6 +26,8 @@ __global__ void __launch_bounds__(kMelThreads) melspec_kernel(const float* __res
                                                               const float* __restrict__ melfb /* [n_mels][257] */,
                                                               int pad_mode, float* __restrict__ out_db,
                                                               int* __restrict__ gmax_ordered, long long n_frames) {
+  m3t::pdl_wait();
+  m3t::pdl_launch();
   __shared__ float re[kNfft], im[kNfft];
   __shared__ float pw[kBins + 3];
   __shared__ float red[kMelThreads / 32];
@@ -93,6 +95,8 @@ __global__ void __launch_bounds__(kMelThreads) melspec_kernel(const float* __res
 
 __global__ void melspec_clip_kernel(float* __restrict__ db, long long n, const int* __restrict__ gmax_ordered,
                                     float top_db) {
+  m3t::pdl_wait();
+  m3t::pdl_launch();
   const float floor_db = ordered_to_float(*gmax_ordered) - top_db;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     db[i] = fmaxf(db[i], floor_db);
@@ -102,6 +106,8 @@ __global__ void melspec_clip_kernel(float* __restrict__ db, long long n, const i
 // j < 5, zero beyond the end of the spectrogram.
 __global__ void mel_stack_kernel(const float* __restrict__ mel, long long n_frames, int n_mels, long long start,
                                  int w_len, float* __restrict__ out) {
+  m3t::pdl_wait();
+  m3t::pdl_launch();
   const long long total = (long long)w_len * 5 * n_mels;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -126,14 +132,14 @@ extern "C" int m3t_logmel(const float* wav, long long n_samples, int hop, int wi
   const long long n_frames = 1 + n_samples / hop;
   // 0x80808080 orders below every finite dB value (it decodes to about -3e38)
   if (cudaMemsetAsync(scratch, 0x80, sizeof(int), st) != cudaSuccess) return -22;
-  melspec_kernel<<<(unsigned)n_frames, kMelThreads, 0, st>>>(wav, n_samples, hop, win_length, n_mels, mel_fb, pad_mode,
+  m3t::launch_k(melspec_kernel, dim3((unsigned)n_frames), dim3(kMelThreads), 0, st, wav, n_samples, hop, win_length, n_mels, mel_fb, pad_mode,
                                                            out_db, scratch, n_frames);
   count_launch();
   if (top_db > 0.f) {
     const long long n = n_frames * n_mels;
     long long blocks = (n + 255) / 256;
     if (blocks > 148 * 8) blocks = 148 * 8;
-    melspec_clip_kernel<<<(int)blocks, 256, 0, st>>>(out_db, n, scratch, top_db);
+    m3t::launch_k(melspec_clip_kernel, dim3((int)blocks), dim3(256), 0, st, out_db, n, scratch, top_db);
     count_launch();
   }
   return launch_status();
@@ -145,7 +151,7 @@ extern "C" int m3t_mel_stack(const float* mel, long long n_frames, int n_mels, l
   long long blocks = (total + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
   if (blocks < 1) blocks = 1;
-  mel_stack_kernel<<<(int)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(mel, n_frames, n_mels, start,
+  m3t::launch_k(mel_stack_kernel, dim3((int)blocks), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), mel, n_frames, n_mels, start,
                                                                                     w_len, out);
   count_launch();
   return launch_status();

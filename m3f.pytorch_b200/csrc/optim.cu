@@ -26,6 +26,8 @@ __device__ __forceinline__ float block_sum_fixed(float acc) {
 // Two deterministic passes instead of float atomics: data-parallel replicas must compute bit-identical clip
 // coefficients from their (identical, all-reduced) gradients, or their parameters drift apart ulp by ulp.
 __global__ void sumsq_partial_kernel(const float* __restrict__ g, long long n, float* __restrict__ partial) {
+  m3t::pdl_wait();
+  m3t::pdl_launch();
   float acc = 0.f;
   const long long n4 = n / 4;
   const float4* g4 = reinterpret_cast<const float4*>(g);
@@ -40,6 +42,8 @@ __global__ void sumsq_partial_kernel(const float* __restrict__ g, long long n, f
 }
 
 __global__ void sumsq_final_kernel(const float* __restrict__ partial, int nblocks, float* __restrict__ out) {
+  m3t::pdl_wait();
+  m3t::pdl_launch();
   float acc = 0.f;
   for (int i = threadIdx.x; i < nblocks; i += blockDim.x) acc += partial[i];
   const float s = block_sum_fixed(acc);
@@ -50,6 +54,8 @@ __global__ void adam_clip_kernel(float* __restrict__ p, const float* __restrict_
                                  float* __restrict__ v, long long n, float lr, float beta1, float beta2, float eps,
                                  float wd, float bc1, float bc2_sqrt, float max_norm, float grad_scale,
                                  const float* __restrict__ gnorm_sq) {
+  m3t::pdl_wait();
+  m3t::pdl_launch();
   float coef = grad_scale;
   if (max_norm > 0.f) {
     const float total = sqrtf(__ldg(gnorm_sq)) * grad_scale;
@@ -72,6 +78,8 @@ __global__ void adam_clip_kernel(float* __restrict__ p, const float* __restrict_
 // holds no host scalar that changes between replays; lr / weight decay are rewritten by the host (schedulers) with
 // an ordinary copy into the same buffer.
 __global__ void adam_tick_kernel(float* __restrict__ hyper, float beta1, float beta2) {
+  m3t::pdl_wait();
+  m3t::pdl_launch();
   const float s = hyper[2] + 1.f;
   hyper[2] = s;
   hyper[3] = 1.f - powf(beta1, s);
@@ -82,6 +90,8 @@ __global__ void adam_clip_dev_kernel(float* __restrict__ p, const float* __restr
                                      float* __restrict__ v, long long n, const float* __restrict__ hyper, float beta1,
                                      float beta2, float eps, float max_norm, float grad_scale,
                                      const float* __restrict__ gnorm_sq) {
+  m3t::pdl_wait();
+  m3t::pdl_launch();
   const float lr = __ldg(hyper), wd = __ldg(hyper + 1), bc1 = __ldg(hyper + 3), bc2_sqrt = __ldg(hyper + 4);
   float coef = grad_scale;
   if (max_norm > 0.f) {
@@ -132,9 +142,9 @@ extern "C" int m3t_sumsq_f32(const float* g, long long n, float* out, float* wor
   long long blocks = (n / 4 + 255) / 256;
   if (blocks > kSumsqMaxBlocks) blocks = kSumsqMaxBlocks;
   if (blocks < 1) blocks = 1;
-  sumsq_partial_kernel<<<(int)blocks, 256, 0, st>>>(g, n, workspace);
+  m3t::launch_k(sumsq_partial_kernel, dim3((int)blocks), dim3(256), 0, st, g, n, workspace);
   count_launch();
-  sumsq_final_kernel<<<1, 256, 0, st>>>(workspace, (int)blocks, out);
+  m3t::launch_k(sumsq_final_kernel, dim3(1), dim3(256), 0, st, workspace, (int)blocks, out);
   count_launch();
   return launch_status();
 }
@@ -147,7 +157,7 @@ extern "C" int m3t_adam_clip_step(float* p, const float* g, float* m, float* v, 
   const float bc2_sqrt = sqrtf(1.f - powf(beta2, (float)step));
   long long blocks = (n + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  adam_clip_kernel<<<(int)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  m3t::launch_k(adam_clip_kernel, dim3((int)blocks), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), 
       p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, bc1, bc2_sqrt, max_norm, grad_scale, gnorm_sq);
   count_launch();
   return launch_status();
@@ -158,12 +168,12 @@ extern "C" int m3t_adam_clip_step_dev(float* p, const float* g, float* m, float*
                                       const float* gnorm_sq, void* stream) {
   if (!hyper) return -1;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  adam_tick_kernel<<<1, 1, 0, st>>>(hyper, beta1, beta2);
+  m3t::launch_k(adam_tick_kernel, dim3(1), dim3(1), 0, st, hyper, beta1, beta2);
   count_launch();
   long long blocks = (n / 4 + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
   if (blocks < 1) blocks = 1;
-  adam_clip_dev_kernel<<<(int)blocks, 256, 0, st>>>(p, g, m, v, n, hyper, beta1, beta2, eps, max_norm, grad_scale,
+  m3t::launch_k(adam_clip_dev_kernel, dim3((int)blocks), dim3(256), 0, st, p, g, m, v, n, hyper, beta1, beta2, eps, max_norm, grad_scale,
                                                     gnorm_sq);
   count_launch();
   return launch_status();

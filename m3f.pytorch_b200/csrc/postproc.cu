@@ -24,6 +24,8 @@ static inline int pp_blocks(long long n) {
 __global__ void overlap_add_kernel(const float* __restrict__ pred, const int* __restrict__ seg_start,
                                    const int* __restrict__ seg_len, const long long* __restrict__ seg_base,
                                    float* __restrict__ out, long long S, int L, int C) {
+  m3t::pdl_wait();
+  m3t::pdl_launch();
   const long long total = S * L * C;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -38,6 +40,8 @@ __global__ void overlap_add_kernel(const float* __restrict__ pred, const int* __
 // frames [window/2, n) of every video were covered by two windows: halve them (models/model.py:295-298, :364-365)
 __global__ void overlap_halve_kernel(float* __restrict__ out, const long long* __restrict__ seq_off, int V, int C,
                                      int half) {
+  m3t::pdl_wait();
+  m3t::pdl_launch();
   const int v = blockIdx.x;
   if (v >= V) return;
   const long long lo = (seq_off[v] + half) * C, hi = seq_off[v + 1] * C;
@@ -49,6 +53,8 @@ __global__ void overlap_halve_kernel(float* __restrict__ out, const long long* _
 __global__ void wiener_stats_kernel(const float* __restrict__ x, const long long* __restrict__ seq_off, int V, int C,
                                     int W, double* __restrict__ lmean, double* __restrict__ lvar,
                                     double* __restrict__ noise_sum) {
+  m3t::pdl_wait();
+  m3t::pdl_launch();
   const int v = blockIdx.y;
   const long long lo = seq_off[v], hi = seq_off[v + 1];
   const long long n = hi - lo;
@@ -83,6 +89,8 @@ __global__ void wiener_stats_kernel(const float* __restrict__ x, const long long
 __global__ void wiener_apply_kernel(const float* __restrict__ x, const long long* __restrict__ seq_off, int V, int C,
                                     const double* __restrict__ lmean, const double* __restrict__ lvar,
                                     const double* __restrict__ noise_sum, double* __restrict__ out) {
+  m3t::pdl_wait();
+  m3t::pdl_launch();
   const int v = blockIdx.y;
   const long long lo = seq_off[v], hi = seq_off[v + 1];
   const long long n = hi - lo;
@@ -103,6 +111,8 @@ __global__ void wiener_apply_kernel(const float* __restrict__ x, const long long
 // (f64), b = ground truth (f32); valid = every ground-truth channel of the frame >= -1 (get_smoothed_ccc.py:21).
 __global__ void ccc_moments_kernel(const double* __restrict__ pred, const float* __restrict__ gt,
                                    const long long* __restrict__ seq_off, int C, double* __restrict__ mom) {
+  m3t::pdl_wait();
+  m3t::pdl_launch();
   const int v = blockIdx.x, c = blockIdx.y;
   const long long lo = seq_off[v], hi = seq_off[v + 1];
   double acc[6] = {0, 0, 0, 0, 0, 0};
@@ -136,10 +146,10 @@ extern "C" int m3t_overlap_add_f32(const float* pred, const int* seg_start, cons
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (cudaMemsetAsync(out, 0, (size_t)total_frames * C * sizeof(float), st) != cudaSuccess) return -21;
   if (S > 0) {
-    overlap_add_kernel<<<pp_blocks(S * L * C), kPpThreads, 0, st>>>(pred, seg_start, seg_len, seg_base, out, S, L, C);
+    m3t::launch_k(overlap_add_kernel, dim3(pp_blocks(S * L * C)), dim3(kPpThreads), 0, st, pred, seg_start, seg_len, seg_base, out, S, L, C);
     count_launch();
   }
-  overlap_halve_kernel<<<V, kPpThreads, 0, st>>>(out, seq_off, V, C, window / 2);
+  m3t::launch_k(overlap_halve_kernel, dim3(V), dim3(kPpThreads), 0, st, out, seq_off, V, C, window / 2);
   count_launch();
   return launch_status();
 }
@@ -153,8 +163,8 @@ extern "C" int m3t_wiener1d_f64(const float* x, const long long* seq_off, int V,
   long long bx = (max_len * C + kPpThreads - 1) / kPpThreads;
   if (bx > 64) bx = 64;
   dim3 grid((unsigned)bx, (unsigned)V);
-  wiener_stats_kernel<<<grid, kPpThreads, C * sizeof(double), st>>>(x, seq_off, V, C, window, lmean, lvar, noise_sum);
-  wiener_apply_kernel<<<grid, kPpThreads, 0, st>>>(x, seq_off, V, C, lmean, lvar, noise_sum, out);
+  m3t::launch_k(wiener_stats_kernel, dim3(grid), dim3(kPpThreads), C * sizeof(double), st, x, seq_off, V, C, window, lmean, lvar, noise_sum);
+  m3t::launch_k(wiener_apply_kernel, dim3(grid), dim3(kPpThreads), 0, st, x, seq_off, V, C, lmean, lvar, noise_sum, out);
   count_launch(2);
   return launch_status();
 }
@@ -163,7 +173,7 @@ extern "C" int m3t_ccc_moments_f64(const double* pred, const float* gt, const lo
                                    double* moments, void* stream) {
   if (V <= 0 || C <= 0) return -1;
   dim3 grid((unsigned)V, (unsigned)C);
-  ccc_moments_kernel<<<grid, kPpThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(pred, gt, seq_off, C, moments);
+  m3t::launch_k(ccc_moments_kernel, dim3(grid), dim3(kPpThreads), 0, reinterpret_cast<cudaStream_t>(stream), pred, gt, seq_off, C, moments);
   count_launch();
   return launch_status();
 }

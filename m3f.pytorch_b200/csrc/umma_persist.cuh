@@ -55,6 +55,9 @@ umma_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // barriers, TMEM and descriptor prefetch above touch nothing a previous kernel wrote: they overlap its tail
+  m3t::pdl_wait();
+  m3t::pdl_launch();
 
   if (warp == 0) {
     // ===================================== TMA producer =====================================

@@ -65,6 +65,9 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // barriers, TMEM and descriptor prefetch above touch nothing a previous kernel wrote: they overlap its tail
+  m3t::pdl_wait();
+  m3t::pdl_launch();
   const int x_stage_bytes = (p.x_bytes + 1023) / 1024 * 1024;
   int my_blocks = 0;
   for (int kb = blockIdx.x; kb < p.num_kblocks; kb += gridDim.x) ++my_blocks;
@@ -161,7 +164,7 @@ static int wg_launch(const CUtensorMap& tmX, const CUtensorMap& tmDY, WgHaloPara
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = p.num_kblocks < sms ? p.num_kblocks : sms;
-  wgrad_halo_kernel<STAGES><<<grid, kWgThreads, smem, st>>>(tmX, tmDY, p);
+  m3t::launch_k(wgrad_halo_kernel<STAGES>, dim3(grid), dim3(kWgThreads), smem, st, tmX, tmDY, p);
   count_launch();
   return launch_status();
 }
@@ -221,6 +224,9 @@ wgrad_stem_xres_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // barriers, TMEM and descriptor prefetch above touch nothing a previous kernel wrote: they overlap its tail
+  m3t::pdl_wait();
+  m3t::pdl_launch();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -328,7 +334,7 @@ static int wg_xres_launch(const CUtensorMap& tmX, const CUtensorMap& tmDY, const
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = p.num_xblocks < sms ? p.num_xblocks : sms;
-  wgrad_stem_xres_kernel<<<grid, kWgThreads, smem, st>>>(tmX, tmDY, p);
+  m3t::launch_k(wgrad_stem_xres_kernel, dim3(grid), dim3(kWgThreads), smem, st, tmX, tmDY, p);
   count_launch();
   return launch_status();
 }

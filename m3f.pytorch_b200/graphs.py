@@ -17,8 +17,11 @@ version counters, storage pointers and the cache generation: if the weights were
 `p.data = ...`) or rewritten through the optimizer arena (generation bump), the next call re-captures instead of
 replaying stale weights.
 """
+import os
+
 import torch
 
+from . import lib as L
 from . import ops
 
 
@@ -73,8 +76,16 @@ class GraphedInference:
                 self._call(self.static_in)
         torch.cuda.current_stream().wait_stream(s)
         self.graph = torch.cuda.CUDAGraph()
-        with torch.no_grad(), torch.cuda.graph(self.graph):
-            self.static_out = self._call(self.static_in)
+        # kernel -> kernel edges of the captured sequence become programmatic dependencies (csrc/common.cuh): a replay
+        # is launch-latency bound, the next kernel's scheduling and prologue overlap the previous kernel's tail
+        prev_pdl = L.set_pdl(None)
+        if "M3T_PDL" not in os.environ:
+            L.set_pdl(True)
+        try:
+            with torch.no_grad(), torch.cuda.graph(self.graph):
+                self.static_out = self._call(self.static_in)
+        finally:
+            L.set_pdl(prev_pdl)
         self._held = [v[2] for v in ops._pack_cache.values()]     # the derived weight copies the graph reads
         self._key = self._weights_key()
         self.captures += 1

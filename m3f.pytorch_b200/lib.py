@@ -42,6 +42,12 @@ def launch_count():
     return int(load().m3t_launch_count())
 
 
+def set_pdl(on):
+    """Programmatic dependent launch of the library's kernels (include/m3t_b200.h m3t_set_pdl); returns the previous
+    setting.  on=None only queries."""
+    return bool(load().m3t_set_pdl(-1 if on is None else int(bool(on))))
+
+
 def check(rc, what):
     if rc != 0:
         raise M3TError("%s failed with code %d" % (what, rc))

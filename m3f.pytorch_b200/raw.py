@@ -15,9 +15,10 @@ _prof = None
 
 
 class KernelProfiler:
-    def __init__(self, track_hbm=True):
+    def __init__(self, track_hbm=True, only=None):
         self.records = []          # (key, algorithmic flops, algorithmic HBM bytes, start event, end event)
         self.track_hbm = track_hbm  # False: the ~60 streaming passes per step ("hbm ..." keys) run un-timed
+        self.only = None if only is None else frozenset(only)   # a set of keys: every other launch runs un-timed
 
     def add(self, key, flops, e0, e1, nbytes=0.0):
         self.records.append((key, flops, nbytes, e0, e1))
@@ -45,7 +46,8 @@ def set_profiler(p):
 
 
 def _timed(key, flops, fn, nbytes=0.0):
-    if _prof is None or (not _prof.track_hbm and key.startswith("hbm ")):
+    if _prof is None or (not _prof.track_hbm and key.startswith("hbm ")) \
+            or (_prof.only is not None and key not in _prof.only):
         return fn()
     e0 = torch.cuda.Event(enable_timing=True)
     e1 = torch.cuda.Event(enable_timing=True)

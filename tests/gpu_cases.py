@@ -2137,6 +2137,71 @@ for _t in ("resnet", "v2psplit"):
     TOLS["det_vs_default_grad_" + _t] = 0.3       # same math, other summation order, on a chaotic model (see info)
 
 
+# ----------------------------------------------------------------------------------------------------------
+# Programmatic dependent launch (csrc/common.cuh, m3t_set_pdl): every kernel orders itself behind its predecessor with
+# griddepcontrol.wait instead of the stream's full serialisation.  A kernel that read its input BEFORE the wait would
+# see stale data; in deterministic mode the step is bit-reproducible, so PDL on vs off must agree to the last bit
+# (eager, 3 optimizer steps, both model families), and so must eval inference replayed from a graph captured with it.
+# ----------------------------------------------------------------------------------------------------------
+def case_pdl_exact(seed=0, steps=3, clips=6):
+    import bench as BN
+    from m3t_b200 import lib, ops, raw
+    from m3t_b200.engine import TrainEngine
+    from m3t_b200.graphs import GraphedInference
+    from m3t_b200.models.model import AffWild2VA
+    errs = {}
+    for tag, kw in (("resnet", {}), ("v2psplit", dict(backbone="v2p_split", split_layer=3))):
+        hp = BN.hparams()
+        for k, v in kw.items():
+            setattr(hp, k, v)
+        batches = [{k: v.cuda() for k, v in BN.synth_batch(clips, 300 + i, pin=False).items()} for i in range(steps)]
+
+        def run(pdl):
+            prev_d, prev_p = raw.set_deterministic(True), lib.set_pdl(pdl)
+            try:
+                ops.clear_caches()
+                torch.manual_seed(seed)
+                m = AffWild2VA(hp)
+                BN.randomise_bn(m, 7)
+                m = m.cuda().train()
+                eng = TrainEngine(m, lr=1e-4, weight_decay=1e-4, clip=1.0)
+                losses = [eng.step(b).clone() for b in batches]
+                torch.cuda.synchronize()
+                return torch.stack(losses), eng.flat_g.clone(), eng.flat_p.clone()
+            finally:
+                raw.set_deterministic(prev_d)
+                lib.set_pdl(prev_p)
+
+        l0, g0, p0 = run(False)
+        l1, g1, p1 = run(True)
+        errs["pdl_loss_bits_" + tag] = float((l0 != l1).sum())
+        errs["pdl_grad_bits_" + tag] = float((g0 != g1).sum())
+        errs["pdl_param_bits_" + tag] = float((p0 != p1).sum())
+    # eval inference: graph captured with PDL edges vs plain eager
+    from m3t_b200.models.backbone import VA_3DResNet
+    torch.manual_seed(seed)
+    net = VA_3DResNet(resnet_ver='v1').cuda().eval()
+    x = torch.randn(2, 3, 16, 112, 112, device="cuda")
+    with torch.no_grad():
+        ref = net(x).clone()
+    prev = lib.set_pdl(True)
+    try:
+        gi = GraphedInference(net, x)
+        out = gi(x).clone()
+        out2 = gi(x).clone()
+    finally:
+        lib.set_pdl(prev)
+    errs["pdl_graph_bits"] = float((out != ref).sum() + (out2 != ref).sum())
+    return errs
+
+
+CASES["pdl_exact"] = (case_pdl_exact, _c())
+for _t in ("resnet", "v2psplit"):
+    for _k in ("pdl_loss_bits_", "pdl_grad_bits_", "pdl_param_bits_"):
+        TOLS[_k + _t] = 0.5
+TOLS["pdl_graph_bits"] = 0.5
+
+
 if __name__ == "__main__":
     name = sys.argv[1]
     errs = run_case(name)
