@@ -282,6 +282,17 @@ int m3t_gru_pack_weights(const float* w_ih, const float* w_ih_r, const float* w_
 int m3t_gru_bwd(const void* dout_bf16, const void* out_bf16, const float* saved, const void* w_hh_t_bf16,
                 void* dgi_bf16, void* dgh_bf16, void* hprev_bf16, unsigned* counters, float* dbias, int B, int T, int H,
                 void* stream);
+/* BPTT on thread-block clusters of H/32 CTAs (H in {128, 256, 512}; 16-CTA clusters for H = 512): each CTA multiplies
+ * the gate gradients of ITS 32 hidden units (just computed, in its own shared memory) with its K-slice of W_hh^T and
+ * the partial products are reduce-scattered over distributed shared memory behind one hardware cluster barrier per
+ * step, added in rank order (deterministic).  Same operands and results as m3t_gru_bwd up to the fp32 summation
+ * order of the recurrent product; no arrival counters.  Returns -23 when the device cannot co-schedule such a cluster
+ * and -3 / -1 for batches / shapes it does not take: callers fall back to m3t_gru_bwd. */
+int m3t_gru_bwd_cluster(const void* dout_bf16, const void* out_bf16, const float* saved, const void* w_hh_t_bf16,
+                        void* dgi_bf16, void* dgh_bf16, void* hprev_bf16, float* dbias, int B, int T, int H,
+                        void* stream);
+/* Clusters of that kernel (hidden size H) the device keeps resident at once; <= 0: it cannot run here. */
+int m3t_gru_bwd_cluster_max(int H);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Attention-fusion mix (fusion.cu): f = softmax(sigmoid(s_v), sigmoid(s_a)) . (x_v, x_a) per (b,t) row of C

@@ -547,6 +547,253 @@ __global__ void __launch_bounds__(kGruThreads, 1) gru_bwd_kernel(const GruParams
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------
+// BPTT on a thread-block cluster (H = 32 * CS, CS = 4, 8 or 16 CTAs).  The kernel above gathers the whole (rows, 3H)
+// gate-gradient tile through L2 every step and multiplies it with a 32-column slice of W_hh^T: a 96 KB read and a
+// serial chain of 3H/16 MMAs behind a global-memory barrier (9.2 us per step at any batch).  Here the contraction
+// is split the other way: CTA js owns hidden units [32 js, 32 js + 32) both as the ELEMENT-WISE owner (its threads
+// hold dh for them in registers) and as a K-SLICE of the recurrent product, so the gate gradients it needs as MMA
+// input are the ones it has just computed (a 16 x 96 tile in its own shared memory, never re-read from L2):
+//     partial[b][k] = sum_{g, j in own 32} dgh[b][g][j] * W_hh[g][j][k]        (all H columns k, K = 96)
+// and the partials are reduce-scattered over distributed shared memory: after ONE cluster barrier every CTA reads
+// the 32 columns it owns from each peer's partial tile (CS x 2 KB) and adds them in rank order — a fixed order, so
+// the kernel is deterministic as it stands.  W_hh^T[:, own (g, j)] stays in shared memory (H x 96 bf16 = 98 KB) for
+// the whole sequence; partial tiles are double-buffered, which makes the one barrier per step sufficient (a tile is
+// rewritten two barriers after it was read).  Batch rows are independent: a cluster owns 16-row slices
+// (blockIdx.y, + gridDim.y, ...), more rows are more clusters.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int kClMaxSlices = 3;       // 16-row slices per cluster.  A slice-step costs 3.6 us at H = 512 (barrier + DSMEM
+                                      // pull, not overlapped between slices): beyond 3 slices per cluster (B = 256 at
+                                      // H = 512, where only 7 clusters of 16 CTAs are resident) the L2 kernel is as fast
+constexpr int kBRows = 16;             // batch rows per slice (one m16 tile)
+constexpr int kBLd = 3 * kJS + 8;      // padded K row (bf16 elements): 208 B, conflict-free ldmatrix
+
+__device__ __forceinline__ float2 ld_dsmem_f2(uint32_t local_saddr, uint32_t rank) {
+  uint32_t ra;
+  float2 v;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(local_saddr), "r"(rank));
+  asm volatile("ld.shared::cluster.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(ra) : "memory");
+  return v;
+}
+
+__device__ __forceinline__ float4 ld_dsmem_f4(uint32_t local_saddr, uint32_t rank) {
+  uint32_t ra;
+  float4 v;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(local_saddr), "r"(rank));
+  asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "r"(ra)
+               : "memory");
+  return v;
+}
+
+struct BwdIn {            // what phase A of one (slice, step) reads from global memory, for one (row, unit pair)
+  float2 r, z, n, hn;
+  uint32_t dout2, hp2;
+  bool ok;
+};
+
+template <int CS>
+__global__ void __launch_bounds__(kGruThreads, 1) gru_bwd_cluster_kernel(const GruParams p) {
+  pdl_wait();
+  pdl_launch();
+  constexpr int H = CS * kJS;
+  constexpr int K3 = 3 * H;
+  constexpr int PLD = H + 8;            // fp32 row of a partial tile
+  constexpr int NTW = CS / 2;           // 8-column n-tiles per warp (H / 8 tiles over 8 warps)
+  extern __shared__ __align__(16) uint8_t smem[];
+  __nv_bfloat16* Wsm = reinterpret_cast<__nv_bfloat16*>(smem);     // [H][kBLd]  row k, col g*32 + jl
+  __nv_bfloat16* Asm = Wsm + H * kBLd;                             // [16][kBLd] own gate gradients of this step
+  float* Psm = reinterpret_cast<float*>(Asm + kBRows * kBLd);      // [2][16][PLD] partial dh_rec, all H columns
+  const int T = p.T, B = p.B;
+  const int js = (int)cluster_ctarank(), dir = blockIdx.z;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  for (int i = tid; i < H * 12; i += kGruThreads) {
+    const int k = i / 12, rem = i - k * 12, g = rem >> 2, v = rem & 3;
+    const uint4 val =
+        __ldg(reinterpret_cast<const uint4*>(p.w + ((long long)dir * H + k) * K3 + g * H + js * kJS) + v);
+    *reinterpret_cast<uint4*>(Wsm + k * kBLd + g * kJS + v * 8) = val;
+  }
+  // element-wise ownership: row = tid / 16 of the slice, hidden units jl, jl + 1 of this CTA's 32
+  const int row = tid >> 4, jl = (tid & 15) * 2;
+  const int j = js * kJS + jl;
+  int nsl = 0;                                             // slices of this cluster
+  for (int bs = blockIdx.y; bs < p.nbslices; bs += gridDim.y) ++nsl;
+
+  auto load_in = [&](int step, int si) {
+    BwdIn in;
+    const int t = dir == 0 ? T - 1 - step : step;
+    const int tprev = dir == 0 ? t - 1 : t + 1;
+    const int b = (blockIdx.y + si * gridDim.y) * kBRows + row;
+    in.ok = b < B;
+    in.hp2 = 0u;
+    if (in.ok) {
+      const long long rw = (long long)b * T + t;
+      const float* sv = p.saved + (rw * 2 + dir) * 4 * H + j;
+      in.r = __ldg(reinterpret_cast<const float2*>(sv));
+      in.z = __ldg(reinterpret_cast<const float2*>(sv + H));
+      in.n = __ldg(reinterpret_cast<const float2*>(sv + 2 * H));
+      in.hn = __ldg(reinterpret_cast<const float2*>(sv + 3 * H));
+      in.dout2 = __ldg(reinterpret_cast<const uint32_t*>(p.dout + rw * 2 * H + dir * H + j));
+      if (tprev >= 0 && tprev < T)
+        in.hp2 = __ldg(reinterpret_cast<const uint32_t*>(p.out + ((long long)b * T + tprev) * 2 * H + dir * H + j));
+    }
+    return in;
+  };
+
+  float dhrec[kClMaxSlices][2];
+#pragma unroll
+  for (int si = 0; si < kClMaxSlices; ++si) dhrec[si][0] = dhrec[si][1] = 0.f;
+  float sb_r[2] = {0.f, 0.f}, sb_z[2] = {0.f, 0.f}, sb_n[2] = {0.f, 0.f}, sb_nr[2] = {0.f, 0.f};
+
+  const uint32_t a_base = smem_u32(Asm + ((lane & 7) + ((lane >> 3) & 1) * 8) * kBLd + (lane >> 4) * 8);
+  // B fragments of two k-steps per ldmatrix.x4: matrices (lane >> 3) = k offsets 0, 8, 16, 24
+  const uint32_t b_base = smem_u32(Wsm + (warp * NTW * 8 + (lane & 7)) * kBLd + (lane >> 3) * 8);
+
+  BwdIn nxt = load_in(0, 0);
+  __syncthreads();
+  int q = 0;                                               // running (step, slice) index: partial buffer q & 1
+  for (int step = 0; step < T; ++step) {
+    const int t = dir == 0 ? T - 1 - step : step;
+    const bool last = step + 1 == T;
+#pragma unroll
+    for (int si = 0; si < kClMaxSlices; ++si) {
+      if (si >= nsl) break;
+      const BwdIn in = nxt;
+      {   // the next (slice, step)'s inputs do not depend on the recurrence: their latency hides behind this one
+        const int si2 = si + 1 < nsl ? si + 1 : 0;
+        const int step2 = si + 1 < nsl ? step : step + 1;
+        if (step2 < T) nxt = load_in(step2, si2);
+      }
+      // ---- phase A: gate gradients of the owned (row, unit pair) ----
+      float dh_direct[2] = {0.f, 0.f};
+      uint32_t a_r = 0u, a_z = 0u, a_nr = 0u;
+      if (in.ok) {
+        const int b = (blockIdx.y + si * gridDim.y) * kBRows + row;
+        const long long rw = (long long)b * T + t;
+        const float rr[2] = {in.r.x, in.r.y}, zz[2] = {in.z.x, in.z.y}, nn[2] = {in.n.x, in.n.y};
+        const float hh[2] = {in.hn.x, in.hn.y};
+        const float dd[2] = {__uint_as_float(in.dout2 << 16), __uint_as_float(in.dout2 & 0xffff0000u)};
+        const float hp[2] = {__uint_as_float(in.hp2 << 16), __uint_as_float(in.hp2 & 0xffff0000u)};
+        float dar[2], daz[2], dan[2], danr[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const float dh = dd[e] + dhrec[si][e];
+          const float dn = dh * (1.f - zz[e]);
+          const float dz = dh * (hp[e] - nn[e]);
+          dan[e] = dn * (1.f - nn[e] * nn[e]);
+          daz[e] = dz * zz[e] * (1.f - zz[e]);
+          dar[e] = dan[e] * hh[e] * rr[e] * (1.f - rr[e]);
+          danr[e] = dan[e] * rr[e];
+          sb_r[e] += dar[e];
+          sb_z[e] += daz[e];
+          sb_n[e] += dan[e];
+          sb_nr[e] += danr[e];
+          dh_direct[e] = dh * zz[e];
+        }
+        a_r = pack_bf16x2(dar[0], dar[1]);
+        a_z = pack_bf16x2(daz[0], daz[1]);
+        a_nr = pack_bf16x2(danr[0], danr[1]);
+        const uint32_t a_n = pack_bf16x2(dan[0], dan[1]);
+        const long long g0 = rw * 6 * H + dir * 3 * H + j;
+        *reinterpret_cast<uint32_t*>(p.dgi + g0) = a_r;
+        *reinterpret_cast<uint32_t*>(p.dgi + g0 + H) = a_z;
+        *reinterpret_cast<uint32_t*>(p.dgi + g0 + 2 * H) = a_n;
+        *reinterpret_cast<uint32_t*>(p.dgh + g0) = a_r;
+        *reinterpret_cast<uint32_t*>(p.dgh + g0 + H) = a_z;
+        *reinterpret_cast<uint32_t*>(p.dgh + g0 + 2 * H) = a_nr;
+        *reinterpret_cast<uint32_t*>(p.hprev + (rw * 2 + dir) * H + j) = in.hp2;
+      }
+      if (last) continue;          // the gradient wrt h_0 is not needed
+      *reinterpret_cast<uint32_t*>(Asm + row * kBLd + jl) = a_r;            // rows past the batch: zeros
+      *reinterpret_cast<uint32_t*>(Asm + row * kBLd + kJS + jl) = a_z;
+      *reinterpret_cast<uint32_t*>(Asm + row * kBLd + 2 * kJS + jl) = a_nr;
+      __syncthreads();
+      // ---- phase B: partial[16][H] = Asm[16][96] . Wsm[H][96]^T, this warp's NTW column tiles ----
+      float acc[NTW][4];
+#pragma unroll
+      for (int nt = 0; nt < NTW; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[nt][e] = 0.f;
+      uint32_t a[6][4];
+#pragma unroll
+      for (int kk = 0; kk < 6; ++kk) ldmatrix_x4(a[kk], a_base + kk * 32);
+#pragma unroll
+      for (int nt = 0; nt < NTW; ++nt) {
+#pragma unroll
+        for (int k2 = 0; k2 < 3; ++k2) {
+          uint32_t bb[4];
+          ldmatrix_x4(bb, b_base + nt * 8 * kBLd * 2 + k2 * 64);
+          mma_16816(acc[nt], a[2 * k2], bb[0], bb[1]);
+          mma_16816(acc[nt], a[2 * k2 + 1], bb[2], bb[3]);
+        }
+      }
+      float* P = Psm + (q & 1) * kBRows * PLD;
+#pragma unroll
+      for (int nt = 0; nt < NTW; ++nt) {
+        const int col = (warp * NTW + nt) * 8 + (lane & 3) * 2;
+        *reinterpret_cast<float2*>(P + (lane >> 2) * PLD + col) = make_float2(acc[nt][0], acc[nt][1]);
+        *reinterpret_cast<float2*>(P + ((lane >> 2) + 8) * PLD + col) = make_float2(acc[nt][2], acc[nt][3]);
+      }
+      // every CTA's partial tile q is complete after this barrier (and nobody still reads tile q - 1's buffer)
+      cluster_sync_all();
+      // ---- reduce-scatter: own 32 columns of every peer's partial, added in rank order ----
+      // 16-byte requests: lanes l, l ^ 1 share a 4-unit group; each reads it from half of the ranks (even lane:
+      // ranks 0 .. CS/2-1, odd lane: the rest), the halves meet through one shuffle
+      const int hsel = tid & 1;
+      const uint32_t pl = smem_u32(P + row * PLD + js * kJS + ((tid & 15) >> 1) * 4);
+      float4 v[CS / 2];
+#pragma unroll
+      for (int s2 = 0; s2 < CS / 2; ++s2) v[s2] = ld_dsmem_f4(pl, (uint32_t)(hsel * (CS / 2) + s2));
+      float4 sm = v[0];
+#pragma unroll
+      for (int s2 = 1; s2 < CS / 2; ++s2) {
+        sm.x += v[s2].x;
+        sm.y += v[s2].y;
+        sm.z += v[s2].z;
+        sm.w += v[s2].w;
+      }
+      float4 ot;
+      ot.x = __shfl_xor_sync(0xffffffffu, sm.x, 1);
+      ot.y = __shfl_xor_sync(0xffffffffu, sm.y, 1);
+      ot.z = __shfl_xor_sync(0xffffffffu, sm.z, 1);
+      ot.w = __shfl_xor_sync(0xffffffffu, sm.w, 1);
+      // low ranks + high ranks, the same expression in both lanes
+      const float s0 = hsel ? ot.z + sm.z : sm.x + ot.x;
+      const float s1 = hsel ? ot.w + sm.w : sm.y + ot.y;
+      dhrec[si][0] = dh_direct[0] + s0;
+      dhrec[si][1] = dh_direct[1] + s1;
+      ++q;
+    }
+  }
+  if (p.dbias) {
+    // lanes l and l ^ 16 own the same unit pair on two rows; the 8 warps add their sums atomically
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      sb_r[e] += __shfl_xor_sync(0xffffffffu, sb_r[e], 16);
+      sb_z[e] += __shfl_xor_sync(0xffffffffu, sb_z[e], 16);
+      sb_n[e] += __shfl_xor_sync(0xffffffffu, sb_n[e], 16);
+      sb_nr[e] += __shfl_xor_sync(0xffffffffu, sb_nr[e], 16);
+    }
+    if (lane < 16) {
+      float* bih = p.dbias + (long long)dir * 3 * H;
+      float* bhh = p.dbias + (long long)(2 + dir) * 3 * H;
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        atomicAdd(bih + j + e, sb_r[e]);
+        atomicAdd(bih + H + j + e, sb_z[e]);
+        atomicAdd(bih + 2 * H + j + e, sb_n[e]);
+        atomicAdd(bhh + j + e, sb_r[e]);
+        atomicAdd(bhh + H + j + e, sb_z[e]);
+        atomicAdd(bhh + 2 * H + j + e, sb_nr[e]);
+      }
+    }
+  }
+  cluster_sync_all();      // a CTA's shared memory must outlive its peers' last reads
+}
+
 }  // namespace m3t
 
 using namespace m3t;
@@ -644,4 +891,93 @@ extern "C" int m3t_gru_bwd(const void* dout_bf16, const void* out_bf16, const fl
   p.counters = counters;
   p.dbias = dbias;
   return gru_launch(false, p, stream);
+}
+
+template <int CS>
+static int gru_bwd_cluster_launch(GruParams& p, cudaStream_t st, int* query_max) {
+  constexpr int H = CS * kJS;
+  const size_t smem = (size_t)(H + kBRows) * kBLd * 2 + (size_t)2 * kBRows * (H + 8) * 4;
+  auto kern = gru_bwd_cluster_kernel<CS>;
+  static int max_clusters = -1;        // co-resident clusters of this size on the device (0: cannot launch)
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.blockDim = dim3(kGruThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CS;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (max_clusters < 0) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -20;
+    if (CS > 8 && cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
+      cudaGetLastError();
+      max_clusters = 0;
+      return -23;
+    }
+    cfg.gridDim = dim3(CS, 8, 2);
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) {
+      cudaGetLastError();
+      n = 0;
+    }
+    max_clusters = n;
+  }
+  if (query_max) { *query_max = max_clusters; return 0; }
+  if (max_clusters < 2) return -23;
+  p.nbslices = (p.B + kBRows - 1) / kBRows;
+  int ncl = max_clusters / 2;          // per direction
+  if (ncl > p.nbslices) ncl = p.nbslices;
+  const int spc = (p.nbslices + ncl - 1) / ncl;
+  if (spc > kClMaxSlices) return -3;
+  ncl = (p.nbslices + spc - 1) / spc;
+  cfg.gridDim = dim3(CS, ncl, 2);
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, p);
+  count_launch();
+  if (e != cudaSuccess) return -21;
+  return launch_status();
+}
+
+// Cluster / DSMEM BPTT (see gru_bwd_cluster_kernel).  Same arguments and results as m3t_gru_bwd without the arrival
+// counters; H must be 128, 256 or 512.  Returns -23 when the device cannot co-schedule a cluster of H/32 CTAs with
+// this kernel's shared memory and -3 when the batch needs more than 4 slices per cluster (callers fall back to
+// m3t_gru_bwd).
+extern "C" int m3t_gru_bwd_cluster(const void* dout_bf16, const void* out_bf16, const float* saved,
+                                   const void* w_hh_t_bf16, void* dgi_bf16, void* dgh_bf16, void* hprev_bf16,
+                                   float* dbias, int B, int T, int H, void* stream) {
+  if (B <= 0 || T <= 0) return -1;
+  GruParams p;
+  memset(&p, 0, sizeof(p));
+  p.B = B; p.T = T; p.H = H;
+  p.dout = reinterpret_cast<const __nv_bfloat16*>(dout_bf16);
+  p.out = reinterpret_cast<__nv_bfloat16*>(const_cast<void*>(out_bf16));
+  p.saved = const_cast<float*>(saved);
+  p.w = reinterpret_cast<const __nv_bfloat16*>(w_hh_t_bf16);
+  p.dgi = reinterpret_cast<__nv_bfloat16*>(dgi_bf16);
+  p.dgh = reinterpret_cast<__nv_bfloat16*>(dgh_bf16);
+  p.hprev = reinterpret_cast<__nv_bfloat16*>(hprev_bf16);
+  p.dbias = dbias;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (H == 128) return gru_bwd_cluster_launch<4>(p, st, nullptr);
+  if (H == 256) return gru_bwd_cluster_launch<8>(p, st, nullptr);
+  if (H == 512) return gru_bwd_cluster_launch<16>(p, st, nullptr);
+  return -1;
+}
+
+// How many clusters of m3t_gru_bwd_cluster's kernel for hidden size H the device keeps resident at once
+// (cudaOccupancyMaxActiveClusters; 0 = none, negative = error / unsupported H).
+extern "C" int m3t_gru_bwd_cluster_max(int H) {
+  GruParams p;
+  memset(&p, 0, sizeof(p));
+  int n = 0, rc = -1;
+  if (H == 128) rc = gru_bwd_cluster_launch<4>(p, nullptr, &n);
+  if (H == 256) rc = gru_bwd_cluster_launch<8>(p, nullptr, &n);
+  if (H == 512) rc = gru_bwd_cluster_launch<16>(p, nullptr, &n);
+  return rc ? rc : n;
 }

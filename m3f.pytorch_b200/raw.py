@@ -795,7 +795,13 @@ def gru_fwd(gi, w_hh_bf16, b_hh, B, T, H, want_saved, want_f32=False, cluster=No
     return out, out32, saved
 
 
-def gru_bwd(dout, out, saved, w_hh_t_bf16, B, T, H):
+def gru_bwd_cluster_default():
+    """BPTT on the cluster / DSMEM kernel (m3t_gru_bwd_cluster) wherever it applies; M3T_GRU_BWD_CLUSTER=0 switches back
+    to the L2 / arrival-counter kernel."""
+    return os.environ.get("M3T_GRU_BWD_CLUSTER", "1") == "1"
+
+
+def gru_bwd(dout, out, saved, w_hh_t_bf16, B, T, H, cluster=None):
     dev = dout.device
     dgi = torch.empty((B * T, 6 * H), device=dev, dtype=torch.bfloat16)
     dgh = torch.empty((B * T, 6 * H), device=dev, dtype=torch.bfloat16)
@@ -804,10 +810,21 @@ def gru_bwd(dout, out, saved, w_hh_t_bf16, B, T, H):
     # deterministic mode: the kernel's bias sums are atomics over batch slices and warps; take them as (deterministic)
     # column sums of the gate-gradient tensors instead
     dbias = None if DETERMINISTIC else zeros_f32((2, 6 * H), dev)     # [b_ih | b_hh] x [dir0 3H | dir1 3H]
-    _timed("gru_bwd B%d T%d H%d" % (B, T, H), 0.0, lambda: L.check(
-        _lib().m3t_gru_bwd(L.ptr(dout), L.ptr(out), L.ptr(saved), L.ptr(w_hh_t_bf16), L.ptr(dgi), L.ptr(dgh),
-                           L.ptr(hprev), L.ptr(counters), L.ptr(dbias), L.i32(B), L.i32(T), L.i32(H),
-                           L.stream_ptr()), "gru_bwd"), _nb(dout, out, saved, w_hh_t_bf16, dgi, dgh, hprev))
+    if cluster is None:
+        cluster = gru_bwd_cluster_default()
+
+    def launch():
+        if cluster and H in (128, 256, 512):
+            rc = _lib().m3t_gru_bwd_cluster(L.ptr(dout), L.ptr(out), L.ptr(saved), L.ptr(w_hh_t_bf16), L.ptr(dgi),
+                                            L.ptr(dgh), L.ptr(hprev), L.ptr(dbias), L.i32(B), L.i32(T), L.i32(H),
+                                            L.stream_ptr())
+            if rc not in (-23, -3):      # -23: no room for the cluster on this device, -3: batch too large for it
+                return L.check(rc, "gru_bwd_cluster")
+        L.check(_lib().m3t_gru_bwd(L.ptr(dout), L.ptr(out), L.ptr(saved), L.ptr(w_hh_t_bf16), L.ptr(dgi), L.ptr(dgh),
+                                   L.ptr(hprev), L.ptr(counters), L.ptr(dbias), L.i32(B), L.i32(T), L.i32(H),
+                                   L.stream_ptr()), "gru_bwd")
+
+    _timed("gru_bwd B%d T%d H%d" % (B, T, H), 0.0, launch, _nb(dout, out, saved, w_hh_t_bf16, dgi, dgh, hprev))
     if dbias is None:
         dbias = torch.stack((colsum(dgi, 6 * H), colsum(dgh, 6 * H)))
     return dgi, dgh, hprev, dbias

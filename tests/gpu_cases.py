@@ -1748,6 +1748,60 @@ for _k in ("gru_cluster_exact", "gru_cluster_f32_exact", "gru_cluster_nonfinite"
     TOLS[_k] = 0.5
 
 
+def case_gru_bwd_cluster(seed=0):
+    """m3t_gru_bwd_cluster (K-split recurrent product, DSMEM reduce-scatter) against m3t_gru_bwd on the same operands:
+    hprev bit for bit, gate gradients / bias gradients to the fp32 summation-order noise of the recurrent product
+    (the bf16 outputs then differ by single roundings), run-to-run bit-identical (rank-order reduction), ragged batch /
+    sequence sizes incl. several 16-row slices per cluster; `info` = microseconds per time step of both kernels."""
+    from m3t_b200 import raw
+    g = torch.Generator().manual_seed(seed)
+    errs, info = {"gru_bwd_cluster_hprev_exact": 0.0, "gru_bwd_cluster_rerun_bits": 0.0, "gru_bwd_cluster_dgi": 0.0,
+                  "gru_bwd_cluster_dgh": 0.0, "gru_bwd_cluster_dbias": 0.0, "gru_bwd_cluster_nonfinite": 0.0}, {}
+    for B, T, H in ((16, 16, 512), (32, 16, 512), (2, 16, 512), (7, 33, 256), (16, 40, 128), (1, 5, 512), (3, 1, 256),
+                    (40, 9, 256), (64, 16, 128), (256, 16, 512), (256, 16, 128), (100, 7, 512)):
+        gi = (torch.randn((B * T, 6 * H), generator=g) * 0.8).cuda()
+        w = (torch.randn((2, 3 * H, H), generator=g) / H ** 0.5).bfloat16().cuda()
+        wt = w.transpose(1, 2).contiguous()
+        bh = (torch.randn((2, 3 * H), generator=g) * 0.1).cuda()
+        out, _, saved = raw.gru_fwd(gi, w, bh, B, T, H, True, want_f32=False, cluster=False)
+        dout = torch.randn((B, T, 2 * H), generator=g).bfloat16().cuda()
+        ref = raw.gru_bwd(dout, out, saved, wt, B, T, H, cluster=False)
+        got = raw.gru_bwd(dout, out, saved, wt, B, T, H, cluster=True)
+        got2 = raw.gru_bwd(dout, out, saved, wt, B, T, H, cluster=True)
+        torch.cuda.synchronize()
+        errs["gru_bwd_cluster_hprev_exact"] += float((ref[2].view(torch.int16) != got[2].view(torch.int16)).sum())
+        errs["gru_bwd_cluster_rerun_bits"] += float(sum((a.view(torch.int16) != b.view(torch.int16)).sum()
+                                                         for a, b in zip(got[:3], got2[:3])))
+        errs["gru_bwd_cluster_dgi"] = max(errs["gru_bwd_cluster_dgi"], _l2(got[0].float(), ref[0].float()))
+        errs["gru_bwd_cluster_dgh"] = max(errs["gru_bwd_cluster_dgh"], _l2(got[1].float(), ref[1].float()))
+        errs["gru_bwd_cluster_dbias"] = max(errs["gru_bwd_cluster_dbias"], _l2(got[3], ref[3]))
+        errs["gru_bwd_cluster_nonfinite"] += float(sum((~torch.isfinite(x.float())).sum() for x in got))
+        for tag, flag in (("l2", False), ("cluster", True)):
+            for _ in range(2):
+                raw.gru_bwd(dout, out, saved, wt, B, T, H, cluster=flag)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(5):
+                raw.gru_bwd(dout, out, saved, wt, B, T, H, cluster=flag)
+            e1.record()
+            torch.cuda.synchronize()
+            info["us_per_step_%s_B%d_T%d_H%d" % (tag, B, T, H)] = round(e0.elapsed_time(e1) / 5 / T * 1e3, 2)
+    from m3t_b200 import lib
+    info["max_resident_clusters"] = {H: int(lib.load().m3t_gru_bwd_cluster_max(H)) for H in (128, 256, 512)}
+    errs["info"] = info
+    return errs
+
+
+CASES["gru_bwd_cluster"] = (case_gru_bwd_cluster, _c())
+TOLS["gru_bwd_cluster_hprev_exact"] = 0.5
+TOLS["gru_bwd_cluster_rerun_bits"] = 0.5
+TOLS["gru_bwd_cluster_nonfinite"] = 0.5
+TOLS["gru_bwd_cluster_dgi"] = 2e-3        # bf16 outputs of fp32 values that differ in the last bits: single roundings
+TOLS["gru_bwd_cluster_dgh"] = 2e-3
+TOLS["gru_bwd_cluster_dbias"] = 5e-4
+
+
 # ----------------------------------------------------------------------------------------------------------
 # The whole training step as one CUDA-graph launch (engine.TrainEngine.capture): same trajectory as the eager step,
 # scheduler changes of lr reach the replays, launch count per replay = 0
