@@ -213,7 +213,7 @@ int m3t_cast_bf16_f32(const void* in, long long ld_in, float* out, long long ld_
                       void* stream);
 /* Every convolution filter of a model re-packed by ONE launch after the optimizer step (the per-filter m3t_pack_filter
  * calls were 19 launches + 15 index_select per step).  `table_dev` = n entries in device memory, ordered by `start`
- * (prefix sum of Cout*Cin*taps); outputs as m3t_pack_filter, plus - when has_parity - the four parity sub-filters of
+ * (prefix sum of the entries' tile counts, m3t_pack_entry_tiles); outputs as m3t_pack_filter, plus - when has_parity - the four parity sub-filters of
  * a stride-2 convolution's data gradient: tap t goes to par[par_of_tap[t]] at position pos_of_tap[t] of its
  * ntaps_par[.] taps, layout [Cin][ntaps][Cout] (par_of_tap[t] < 0: tap unused).  taps <= 27.  A matrix is a filter
  * with taps = 1 (wf = bf16 copy, wd = bf16 transpose: W_hh / W_hh^T of a GRU layer, Linear weights); has_parity < 0
@@ -223,13 +223,17 @@ typedef struct m3t_pack_entry {
   void* wf;             /* bf16 [Cout][taps][Cin] or NULL */
   void* wd;             /* bf16 [Cin][taps flipped][Cout] or NULL */
   void* par[4];         /* bf16 parity sub-filters or NULL */
-  long long start;
+  long long start;      /* index of the entry's first tile (m3t_pack_entry_tiles) */
   int Cout, Cin, taps, has_parity;
   int ntaps_par[4];
   int par_of_tap[27];
   int pos_of_tap[27];
 } m3t_pack_entry;
-int m3t_pack_filters_batched(const m3t_pack_entry* table_dev, int n, long long total, void* stream);
+int m3t_pack_filters_batched(const m3t_pack_entry* table_dev, int n, long long total_tiles, void* stream);
+/* Tiles (= thread blocks) one entry occupies: 32 output channels x min(64, 288 / taps) input channels x all taps per
+ * tile, 2048 values per tile for a plain copy.  entry.start = sum of the tiles of the entries before it,
+ * total_tiles = the sum over all entries. */
+long long m3t_pack_entry_tiles(int Cout, int Cin, int taps, int has_parity);
 /* Filter packing fp32 [Cout][Cin][taps] -> bf16 [Cout][taps][Cin] (fprop) and [Cin][taps reversed][Cout] (dgrad);
  * and the inverse re-layout of a packed fp32 weight gradient. */
 int m3t_pack_filter(const float* w, void* w_fprop, void* w_dgrad, int Cout, int Cin, int taps, void* stream);

@@ -120,6 +120,9 @@ def prepack(allowed=None):
         table = (Entry * n_entries)()
         state = {"off": 0, "foff": 0, "start": 0, "i": 0}
 
+        tiles_of = raw._lib().m3t_pack_entry_tiles
+        tiles_of.restype = ctypes.c_longlong
+
         def take(numel):
             t = buf[state["off"]:state["off"] + numel]
             state["off"] += (numel + 7) // 8 * 8
@@ -135,7 +138,7 @@ def prepack(allowed=None):
             for t in range(27):
                 e.par_of_tap[t] = -1
                 e.pos_of_tap[t] = 0
-            state["start"] += numel
+            state["start"] += int(tiles_of(Cout, Cin, taps, kind))      # entry.start counts tiles (= blocks)
             return e
 
         conv_views, gru_views, lin_views = [], [], []
