@@ -257,6 +257,15 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
   return r;
 }
+// The two halves of the cluster barrier.  Global stores issued BETWEEN them are not covered by this release (they are
+// by the next one, a whole step later, when they have long completed): a release with this step's global stores still
+// in flight showed up as the `membar` stall of both cluster kernels (15 % of their stall cycles).
+__device__ __forceinline__ void cluster_arrive_release() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void cluster_wait_acquire() {
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
@@ -363,13 +372,12 @@ __global__ void __launch_bounds__(kGruThreads, 1) gru_fwd_cluster_kernel(const G
       }
     }
     __nv_bfloat16* slw = sl + (step & 1) * kCRows * kCJS;
+    float hnew[2][2], rr[2][2], zz[2][2], nn[2][2], hnn[2][2];
+    uint32_t packed[2] = {0u, 0u};
 #pragma unroll
     for (int rs = 0; rs < 2; ++rs) {
       const int lrow = (lane >> 2) + rs * 8;
-      const int b = b0 + lrow;
-      uint32_t packed = 0u;
-      if (b < B) {
-        float hnew[2], rr[2], zz[2], nn[2], hnn[2];
+      if (b0 + lrow < B) {
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
           const int e = rs * 2 + q;
@@ -380,30 +388,38 @@ __global__ void __launch_bounds__(kGruThreads, 1) gru_fwd_cluster_kernel(const G
           const float r = sigmoidf_((q ? gir[rs].y : gir[rs].x) + hr);
           const float z = sigmoidf_((q ? giz[rs].y : giz[rs].x) + hz);
           const float n = tanhf((q ? gin[rs].y : gin[rs].x) + r * hn);
-          hnew[q] = (1.f - z) * n + z * hp;
-          hreg[e] = hnew[q];
-          rr[q] = r; zz[q] = z; nn[q] = n; hnn[q] = hn;
+          hnew[rs][q] = (1.f - z) * n + z * hp;
+          hreg[e] = hnew[rs][q];
+          rr[rs][q] = r; zz[rs][q] = z; nn[rs][q] = n; hnn[rs][q] = hn;
         }
-        const long long row = (long long)b * T + t;
-        if (p.saved) {      // training: gates for BPTT, same layout as gru_fwd_kernel
-          float* sv = p.saved + (row * 2 + dir) * 4 * H + js * kCJS + j0;
-          *reinterpret_cast<float2*>(sv) = make_float2(rr[0], rr[1]);
-          *reinterpret_cast<float2*>(sv + H) = make_float2(zz[0], zz[1]);
-          *reinterpret_cast<float2*>(sv + 2 * H) = make_float2(nn[0], nn[1]);
-          *reinterpret_cast<float2*>(sv + 3 * H) = make_float2(hnn[0], hnn[1]);
-        }
-        packed = pack_bf16x2(hnew[0], hnew[1]);
-        *reinterpret_cast<uint32_t*>(p.out + row * 2 * H + dir * H + js * kCJS + j0) = packed;
-        if (p.out_f32)
-          *reinterpret_cast<float2*>(p.out_f32 + row * 2 * H + dir * H + js * kCJS + j0) =
-              make_float2(hnew[0], hnew[1]);
+        packed[rs] = pack_bf16x2(hnew[rs][0], hnew[rs][1]);
       }
-      *reinterpret_cast<uint32_t*>(slw + lrow * kCJS + j0) = packed;  // rows past the batch stay zero
+      *reinterpret_cast<uint32_t*>(slw + lrow * kCJS + j0) = packed[rs];  // rows past the batch stay zero
     }
     // One barrier per step: buffer step&1 is complete in every CTA after it, and nobody still reads buffer
     // (step+1)&1 (those pulls happened before the pullers' MMAs of this step).  The last one also keeps every
-    // CTA's shared memory alive until its peers are done with it.
-    cluster_sync_all();
+    // CTA's shared memory alive until its peers are done with it.  The step's global stores go between the two
+    // halves: the peers only need the shared-memory slice.
+    cluster_arrive_release();
+#pragma unroll
+    for (int rs = 0; rs < 2; ++rs) {
+      const int b = b0 + (lane >> 2) + rs * 8;
+      if (b < B) {
+        const long long row = (long long)b * T + t;
+        if (p.saved) {      // training: gates for BPTT, same layout as gru_fwd_kernel
+          float* sv = p.saved + (row * 2 + dir) * 4 * H + js * kCJS + j0;
+          *reinterpret_cast<float2*>(sv) = make_float2(rr[rs][0], rr[rs][1]);
+          *reinterpret_cast<float2*>(sv + H) = make_float2(zz[rs][0], zz[rs][1]);
+          *reinterpret_cast<float2*>(sv + 2 * H) = make_float2(nn[rs][0], nn[rs][1]);
+          *reinterpret_cast<float2*>(sv + 3 * H) = make_float2(hnn[rs][0], hnn[rs][1]);
+        }
+        *reinterpret_cast<uint32_t*>(p.out + row * 2 * H + dir * H + js * kCJS + j0) = packed[rs];
+        if (p.out_f32)
+          *reinterpret_cast<float2*>(p.out_f32 + row * 2 * H + dir * H + js * kCJS + j0) =
+              make_float2(hnew[rs][0], hnew[rs][1]);
+      }
+    }
+    cluster_wait_acquire();
   }
 }
 
@@ -669,10 +685,8 @@ __global__ void __launch_bounds__(kGruThreads, 1) gru_bwd_cluster_kernel(const G
       }
       // ---- phase A: gate gradients of the owned (row, unit pair) ----
       float dh_direct[2] = {0.f, 0.f};
-      uint32_t a_r = 0u, a_z = 0u, a_nr = 0u;
+      uint32_t a_r = 0u, a_z = 0u, a_nr = 0u, a_n = 0u;
       if (in.ok) {
-        const int b = (blockIdx.y + si * gridDim.y) * kBRows + row;
-        const long long rw = (long long)b * T + t;
         const float rr[2] = {in.r.x, in.r.y}, zz[2] = {in.z.x, in.z.y}, nn[2] = {in.n.x, in.n.y};
         const float hh[2] = {in.hn.x, in.hn.y};
         const float dd[2] = {__uint_as_float(in.dout2 << 16), __uint_as_float(in.dout2 & 0xffff0000u)};
@@ -696,7 +710,14 @@ __global__ void __launch_bounds__(kGruThreads, 1) gru_bwd_cluster_kernel(const G
         a_r = pack_bf16x2(dar[0], dar[1]);
         a_z = pack_bf16x2(daz[0], daz[1]);
         a_nr = pack_bf16x2(danr[0], danr[1]);
-        const uint32_t a_n = pack_bf16x2(dan[0], dan[1]);
+        a_n = pack_bf16x2(dan[0], dan[1]);
+      }
+      // this (slice, step)'s results for the GEMMs that follow the recurrence; issued between the two halves of the
+      // cluster barrier (or right away on the last step, which has none)
+      auto store_out = [&]() {
+        if (!in.ok) return;
+        const int b = (blockIdx.y + si * gridDim.y) * kBRows + row;
+        const long long rw = (long long)b * T + t;
         const long long g0 = rw * 6 * H + dir * 3 * H + j;
         *reinterpret_cast<uint32_t*>(p.dgi + g0) = a_r;
         *reinterpret_cast<uint32_t*>(p.dgi + g0 + H) = a_z;
@@ -705,7 +726,8 @@ __global__ void __launch_bounds__(kGruThreads, 1) gru_bwd_cluster_kernel(const G
         *reinterpret_cast<uint32_t*>(p.dgh + g0 + H) = a_z;
         *reinterpret_cast<uint32_t*>(p.dgh + g0 + 2 * H) = a_nr;
         *reinterpret_cast<uint32_t*>(p.hprev + (rw * 2 + dir) * H + j) = in.hp2;
-      }
+      };
+      if (last) store_out();
       if (last) continue;          // the gradient wrt h_0 is not needed
       *reinterpret_cast<uint32_t*>(Asm + row * kBLd + jl) = a_r;            // rows past the batch: zeros
       *reinterpret_cast<uint32_t*>(Asm + row * kBLd + kJS + jl) = a_z;
@@ -738,7 +760,9 @@ __global__ void __launch_bounds__(kGruThreads, 1) gru_bwd_cluster_kernel(const G
         *reinterpret_cast<float2*>(P + ((lane >> 2) + 8) * PLD + col) = make_float2(acc[nt][2], acc[nt][3]);
       }
       // every CTA's partial tile q is complete after this barrier (and nobody still reads tile q - 1's buffer)
-      cluster_sync_all();
+      cluster_arrive_release();
+      store_out();
+      cluster_wait_acquire();
       // ---- reduce-scatter: own 32 columns of every peer's partial, added in rank order ----
       // 16-byte requests: lanes l, l ^ 1 share a 4-unit group; each reads it from half of the ranks (even lane:
       // ranks 0 .. CS/2-1, odd lane: the rest), the halves meet through one shuffle
