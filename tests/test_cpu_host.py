@@ -318,6 +318,77 @@ def test_gru_cluster_index_maps():
         assert {8 * warp + (lane & 3) * 2 + q for lane in range(32) for q in range(2)} == set(range(8 * warp, 8 * warp + 8))
 
 
+def test_gru_bwd_cluster_index_maps():
+    """Host model of gru_bwd_cluster_kernel's index arithmetic (csrc/gru.cu): the 256 threads own every (row, unit) of
+    the CTA's 16 x 32 slice once; the W_hh^T slice load fills every (k, gate, unit) of the [H][96] tile once from the
+    right source element; the warps' n-tiles cover all H columns of the partial once; the reduce-scatter reads every
+    (rank, row, own column) once, low ranks in the even lane and high ranks in the odd lane of a pair, and each thread
+    ends with the two units it owns; the shared-memory budget fits for every cluster size."""
+    import numpy as np
+    for CS in (4, 8, 16):
+        H, K3, bld = CS * 32, CS * 96, 3 * 32 + 8
+        smem = (H + 16) * bld * 2 + 2 * 16 * (H + 8) * 4
+        assert smem + 1024 <= 227 * 1024, (CS, smem)
+        own = np.zeros((16, 32), dtype=int)
+        for tid in range(256):
+            row, jl = tid >> 4, (tid & 15) * 2
+            own[row, jl:jl + 2] += 1
+        assert (own == 1).all()
+        for js in (0, CS - 1):
+            filled = np.zeros((H, 96), dtype=int)
+            for i in range(H * 12):
+                k, rem = divmod(i, 12)
+                g, v = rem >> 2, rem & 3
+                src0 = k * K3 + g * H + js * 32 + v * 8          # element of W_hh^T[dir] = [H k][3H (g, j)]
+                for e in range(8):
+                    col = g * 32 + v * 8 + e
+                    filled[k, col] += 1
+                    assert (src0 + e) % K3 == g * H + js * 32 + col % 32 and (src0 + e) // K3 == k
+            assert (filled == 1).all()
+        ntw = CS // 2
+        cols = np.zeros(H, dtype=int)
+        for warp in range(8):
+            for nt in range(ntw):
+                for lane in range(32):
+                    c = (warp * ntw + nt) * 8 + (lane & 3) * 2
+                    if lane >> 2 == 0:
+                        cols[c:c + 2] += 1
+        assert (cols == 1).all()
+        js = CS - 1
+        reads = np.zeros((CS, 16, 32), dtype=int)
+        for tid in range(256):
+            row, hsel, quad = tid >> 4, tid & 1, (tid & 15) >> 1
+            for s2 in range(CS // 2):
+                reads[hsel * (CS // 2) + s2, row, quad * 4: quad * 4 + 4] += 1
+            mine = {quad * 4 + (2 if hsel else 0), quad * 4 + (3 if hsel else 1)}
+            assert mine == {(tid & 15) * 2, (tid & 15) * 2 + 1}
+        assert (reads == 1).all()
+
+
+def test_pack_tiling_host_functions():
+    """m3t_pack_entry_tiles (host arithmetic of the one-launch weight re-pack): tiles of 32 output channels x
+    min(64, 288 / taps) input channels x all taps cover every element once and fit the kernel's shared-memory tile;
+    a plain copy is cut into 2048-value tiles."""
+    import ctypes
+    from m3t_b200 import lib
+    L = lib.load()
+    L.m3t_pack_entry_tiles.restype = ctypes.c_longlong
+    for Cout, Cin, taps in ((64, 64, 9), (128, 64, 9), (512, 512, 9), (96, 16, 27), (1536, 512, 1), (3072, 200, 1),
+                            (2, 1024, 1), (64, 3, 25), (33, 7, 4)):
+        tci = max(1, min(64, 288 // taps))
+        want = -(-Cout // 32) * -(-Cin // tci)
+        assert L.m3t_pack_entry_tiles(Cout, Cin, taps, 0) == want
+        assert L.m3t_pack_entry_tiles(Cout, Cin, taps, 1) == want
+        rp = tci * taps
+        pitch = (rp + 1) & ~1
+        pitch += 2 if pitch % 4 == 0 else 0
+        assert pitch <= 292 and (pitch // 2) % 2 == 1          # odd number of 4-byte words per row: conflict-free columns
+        assert want * 32 * tci >= Cout * Cin
+    assert L.m3t_pack_entry_tiles(1536, 1, 1, -1) == 1
+    assert L.m3t_pack_entry_tiles(4096, 1, 1, -1) == 2
+    assert L.m3t_pack_entry_tiles(0, 1, 1, 0) < 0
+
+
 def test_engine_arena_admits_late_gradients():
     """ADVICE r1 (engine.py arena membership): a parameter that first receives a gradient after the arena was laid
     out joins it (with the moments of the others preserved) instead of being silently skipped."""
