@@ -31,6 +31,11 @@ long long m3t_launch_count(void);
  * switch (default: environment M3T_PDL == "1"; m3t_b200.engine turns it on while it captures a small-shard training
  * step), on < 0 only queries; returns the previous setting. */
 int m3t_set_pdl(int on);
+/* The persistent one-CTA-per-SM kernels (conv / GEMM tile walkers, halo kernels) size their grids for the device's SM
+ * count minus this reserve (default 0).  m3t_b200.engine sets it while a bucket of the gradient all-reduce overlaps
+ * the backward pass, so that NCCL's CTAs find free SMs instead of turning one-wave launches into two-wave ones.
+ * n < 0 only queries; returns the previous value. */
+int m3t_set_sm_reserve(int n);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Tensor-core GEMM (tcgen05 / TMEM / TMA).  D[M,N] = act( (A . B^T) * scale[n] + shift[n] + residual[m,n] )

@@ -21,6 +21,11 @@ inline int launch_status() { return cudaGetLastError() == cudaSuccess ? 0 : -21;
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+// SMs the persistent (one CTA per SM) kernels size their grids for: the device's count minus m3t_set_sm_reserve(k).
+// The data-parallel engine reserves k SMs while a bucket of the gradient all-reduce overlaps the backward pass, so
+// that NCCL's CTAs find free SMs and a 148-CTA persistent launch does not become a two-wave one.
+int usable_sms();
+
 extern int g_pdl;   // capi_misc.cu: -1 = read M3T_PDL on first use
 bool pdl_enabled();
 

@@ -506,9 +506,7 @@ extern "C" int m3t_conv3x3_c64_halo(const void* x, const void* w_packed, void* y
       return -20;
     attr_done = true;
   }
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int sms = m3t::usable_sms();
   const int grid = p.num_tiles < sms ? p.num_tiles : sms;
   m3t::launch_k(conv3x3_halo_kernel, dim3(grid), dim3(kHaloThreads), smem, reinterpret_cast<cudaStream_t>(stream), tmX, tmW, p);
   count_launch();
@@ -558,9 +556,7 @@ extern "C" int m3t_stem_fprop_halo(const void* xs, const void* w_packed, void* y
       return -20;
     attr_done = true;
   }
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int sms = m3t::usable_sms();
   const int grid = p.num_tiles < sms ? p.num_tiles : sms;
   m3t::launch_k(stem_halo_kernel, dim3(grid), dim3(kHaloThreads), smem, reinterpret_cast<cudaStream_t>(stream), tmX, tmW, p);
   count_launch();

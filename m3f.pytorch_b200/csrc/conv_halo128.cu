@@ -301,9 +301,7 @@ extern "C" int m3t_conv3x3_c128_halo(const void* x, const void* w_packed, void* 
       return -20;
     attr_done = true;
   }
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int sms = m3t::usable_sms();
   const int grid = F < sms ? F : sms;
   m3t::launch_k(conv3x3_c128_halo_kernel, dim3(grid), dim3(kH128Threads), smem, reinterpret_cast<cudaStream_t>(stream), tmX, tmW, p);
   count_launch();

@@ -38,9 +38,7 @@ static int launch_persist(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return -20;
     attr_done = true;
   }
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int sms = m3t::usable_sms();
   const int num_tiles = tiles_m * p.tiles_n;
   int grid = num_tiles < sms ? num_tiles : sms;
   if (p.tiles_n <= grid) grid -= grid % p.tiles_n;   // a CTA then keeps one column block (register-resident BN stats)
@@ -331,9 +329,7 @@ static int conv_wgrad_impl(const void* x, const void* dy, float* dw_packed, cons
   if (splits <= 0) {
     // fill exactly two waves of CTAs (2 CTAs/SM resident): one CTA more than a wave costs a whole extra wave
     // (measured: 612 CTAs 0.504 ms vs 576 CTAs 0.366 ms on the 7x7x256 layer)
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int sms = m3t::usable_sms();
     const int tiles = tiles_m * p.tiles_n;
     splits = (2 * 2 * sms) / tiles;
     const int max_splits = kblocks / 4 > 0 ? kblocks / 4 : 1;

@@ -160,9 +160,7 @@ static int wg_launch(const CUtensorMap& tmX, const CUtensorMap& tmDY, WgHaloPara
       return -20;
     attr_done = true;
   }
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int sms = m3t::usable_sms();
   const int grid = p.num_kblocks < sms ? p.num_kblocks : sms;
   m3t::launch_k(wgrad_halo_kernel<STAGES>, dim3(grid), dim3(kWgThreads), smem, st, tmX, tmDY, p);
   count_launch();
@@ -330,9 +328,7 @@ static int wg_xres_launch(const CUtensorMap& tmX, const CUtensorMap& tmDY, const
       return -20;
     attr_done = true;
   }
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int sms = m3t::usable_sms();
   const int grid = p.num_xblocks < sms ? p.num_xblocks : sms;
   m3t::launch_k(wgrad_stem_xres_kernel, dim3(grid), dim3(kWgThreads), smem, st, tmX, tmDY, p);
   count_launch();

@@ -13,9 +13,10 @@ Optional (overlap_allreduce=True / M3T_OVERLAP_ALLREDUCE=1): the all-reduce spli
 the gradient arena and overlapped with backward: from the second step on every `p.grad` IS its arena
 view (autograd accumulates in place into the zeroed arena), a post-accumulate hook counts the parameters of each
 bucket, and the bucket's `all_reduce(async_op=True)` is issued the moment its last gradient lands.  It is OFF by
-default because it measured slower on 2 x B200 (31.9-32.0 ms vs 31.4 ms per step; the single-GPU step is 31.2 ms):
+default because it measured slower on 2 x B200 (31.9-32.0 ms vs 31.4 ms per step; the single-GPU step is 31.2 ms)
+and again on 8 x B200 in round 2 (31.15 vs 30.52 ms; with SMs reserved for NCCL, M3T_OVERLAP_SM_RESERVE, 31.5-31.8):
 the conv kernels are persistent, one CTA per SM, so the SMs NCCL's kernels occupy while they overlap turn a
-one-wave launch into a two-wave one; the non-overlapped collective costs 0.2 ms.
+one-wave launch into a two-wave one, and leaving SMs free for them costs more than the 0.85 ms collective.
 """
 import ctypes
 import os
@@ -43,7 +44,7 @@ class TrainEngine:
         self.nbt = [m.num_batches_tracked for m in model.modules()
                     if isinstance(m, torch.nn.modules.batchnorm._BatchNorm) and m.num_batches_tracked is not None]
         self.overlap = False        # armed after the arena exists (second step on) when world > 1
-        self.num_buckets = 4
+        self.num_buckets = int(os.environ.get("M3T_OVERLAP_BUCKETS", "4"))
         if overlap_allreduce is None:
             overlap_allreduce = os.environ.get("M3T_OVERLAP_ALLREDUCE", "0") == "1"
         self.want_overlap = bool(overlap_allreduce)
@@ -148,25 +149,55 @@ class TrainEngine:
         for i, (p, v) in enumerate(zip(self.params, self.grad_views)):
             p.grad = v
             p.register_post_accumulate_grad_hook(lambda _p, b=self.bucket_of[i]: self._on_grad(b))
+        # M3T_OVERLAP_SM_RESERVE=k: the overlapped buckets run on their own communicator capped at k CTAs and the
+        # library's persistent kernels leave k SMs free while a bucket is in flight (m3t_set_sm_reserve), so that
+        # NCCL's CTAs do not turn 148-CTA one-wave launches into two-wave ones.  Measured at N = 8 (round 2, ms per
+        # 256-clip step): blocking all-reduce 30.52; overlapped 31.15 (k = 0), 31.51 (k = 4), 31.82 (k = 8) - the
+        # reserve costs more compute than the contention it removes, and the overlapped path's in-place gradient
+        # accumulation into the zeroed arena costs more than the 0.85 ms collective it hides.  Off by default.
+        self.sm_reserve = int(os.environ.get("M3T_OVERLAP_SM_RESERVE", "0")) if self.on_gpu else 0
+        self._pg = None
+        if self.on_gpu and self.sm_reserve > 0 and dist.get_backend() == "nccl":
+            try:
+                opts = dist.ProcessGroupNCCL.Options()
+                opts.config.max_ctas = self.sm_reserve
+                opts.config.min_ctas = 1
+                self._pg = dist.new_group(backend="nccl", pg_options=opts)
+            except Exception:       # older bindings without per-communicator config: fall back to the default group
+                self._pg = None
         self.overlap = True
+
+    def _issue_bucket(self, b):
+        lo, hi, _ = self.buckets[b]
+        if self.on_gpu and self.sm_reserve > 0 and not self._reserved:
+            L.load().m3t_set_sm_reserve(self.sm_reserve)
+            self._reserved = True
+        self._works.append(dist.all_reduce(self.flat_g[lo:hi], op=dist.ReduceOp.SUM, async_op=True, group=self._pg))
 
     def _on_grad(self, b):
         if not self.overlap or self._pending is None:
             return
         self._pending[b] -= 1
         if self._pending[b] == 0:
-            lo, hi, _ = self.buckets[b]
-            self._works.append(dist.all_reduce(self.flat_g[lo:hi], op=dist.ReduceOp.SUM, async_op=True))
+            self._issue_bucket(b)
 
     def _backward_overlapped(self, loss):
         self.flat_g.zero_()
         self._pending = [n for _, _, n in self.buckets]
         self._works = []
-        loss.backward()
+        self._reserved = False
+        try:
+            loss.backward()
+        finally:
+            if self._reserved:
+                L.load().m3t_set_sm_reserve(0)
+                self._reserved = False
         for b, left in enumerate(self._pending):       # buckets holding a parameter that got no gradient this step
             if left > 0:
-                lo, hi, _ = self.buckets[b]
-                self._works.append(dist.all_reduce(self.flat_g[lo:hi], op=dist.ReduceOp.SUM, async_op=True))
+                self._issue_bucket(b)
+        if self._reserved:
+            L.load().m3t_set_sm_reserve(0)
+            self._reserved = False
         self._pending = None
         for w in self._works:
             w.wait()
