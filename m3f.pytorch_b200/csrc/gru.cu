@@ -1011,7 +1011,7 @@ static int gru_bwd_cluster_launch(GruParams& p, cudaStream_t st, int* query_max)
 
 // Cluster / DSMEM BPTT (see gru_bwd_cluster_kernel).  Same arguments and results as m3t_gru_bwd without the arrival
 // counters; H must be 128, 256 or 512.  Returns -23 when the device cannot co-schedule a cluster of H/32 CTAs with
-// this kernel's shared memory and -3 when the batch needs more than 4 slices per cluster (callers fall back to
+// this kernel's shared memory and -3 when the batch needs more than 6 slices per cluster (callers fall back to
 // m3t_gru_bwd).
 extern "C" int m3t_gru_bwd_cluster(const void* dout_bf16, const void* out_bf16, const float* saved,
                                    const void* w_hh_t_bf16, void* dgi_bf16, void* dgh_bf16, void* hprev_bf16,
