@@ -81,6 +81,12 @@ int m3t_conv_fprop_bf16(const void* x, const void* w_packed, void* y, const int*
  * add / relu per block in the reference. */
 int m3t_tcn_conv_bf16(const void* x, const void* w_packed, void* y, void* t_out, const int* geom, const float* scale,
                       const float* shift, const void* residual, float drop_p, unsigned long long seed, void* stream);
+/* The same with mask seed = seed + *seed_dev, seed_dev a 64-bit counter in device memory that the caller advances once
+ * per training step: a step captured into a CUDA graph then draws a new mask on every replay (the launch arguments,
+ * frozen by the capture, carry only the per-layer offset). */
+int m3t_tcn_conv_bf16_dseed(const void* x, const void* w_packed, void* y, void* t_out, const int* geom,
+                            const float* scale, const float* shift, const void* residual, float drop_p,
+                            unsigned long long seed, const unsigned long long* seed_dev, void* stream);
 /* Backward of that epilogue in one pass: dsum = dy * [y > 0] (residual case: y, dsum non-NULL; dsum is also the
  * residual's gradient), da = dsum * scale * [t > 0] (t = the stored pre-residual tensor, or y itself without residual;
  * scale = 1 / (1 - p)). */

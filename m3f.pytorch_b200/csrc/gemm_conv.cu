@@ -158,6 +158,7 @@ struct TcnEpilogue {      // fused TemporalBlock epilogue (UmmaParams::pre_act .
   float drop_p;
   unsigned long long seed;
   void* t_out;
+  const unsigned long long* seed_dev;
 };
 static int conv_fprop_impl(const void* x, const void* w_packed, void* y, const int* geom, const float* scale,
                            const float* shift, const void* residual, int relu, float* stats, int tile_hint,
@@ -183,7 +184,18 @@ extern "C" int m3t_tcn_conv_bf16(const void* x, const void* w_packed, void* y, v
                                  unsigned long long seed, void* stream) {
   if (!(drop_p >= 0.f) || !(drop_p < 1.f) || (t_out && !residual)) return -1;
   TcnEpilogue e;
-  e.drop_p = drop_p; e.seed = seed; e.t_out = t_out;
+  e.drop_p = drop_p; e.seed = seed; e.t_out = t_out; e.seed_dev = nullptr;
+  return conv_fprop_impl(x, w_packed, y, geom, scale, shift, residual, residual ? 1 : 0, nullptr, 0, nullptr, stream, &e);
+}
+
+// The same with the mask seed = seed + *seed_dev (a 64-bit device-resident counter the caller advances once per
+// training step): nothing about the mask is a launch argument that a captured CUDA graph would freeze.
+extern "C" int m3t_tcn_conv_bf16_dseed(const void* x, const void* w_packed, void* y, void* t_out, const int* geom,
+                                       const float* scale, const float* shift, const void* residual, float drop_p,
+                                       unsigned long long seed, const unsigned long long* seed_dev, void* stream) {
+  if (!(drop_p >= 0.f) || !(drop_p < 1.f) || (t_out && !residual)) return -1;
+  TcnEpilogue e;
+  e.drop_p = drop_p; e.seed = seed; e.t_out = t_out; e.seed_dev = seed_dev;
   return conv_fprop_impl(x, w_packed, y, geom, scale, shift, residual, residual ? 1 : 0, nullptr, 0, nullptr, stream, &e);
 }
 
@@ -225,6 +237,7 @@ static int conv_fprop_impl(const void* x, const void* w_packed, void* y, const i
       p.drop_thresh = dropout_threshold(tcn->drop_p);
       p.drop_scale = 1.f / (1.f - tcn->drop_p);
       p.drop_seed = tcn->seed;
+      p.drop_seed_dev = tcn->seed_dev;
     }
     p.out2 = reinterpret_cast<__nv_bfloat16*>(tcn->t_out);
   }

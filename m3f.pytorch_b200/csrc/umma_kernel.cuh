@@ -66,6 +66,8 @@ struct UmmaParams {
   unsigned drop_thresh;
   float drop_scale;
   unsigned long long drop_seed;
+  const unsigned long long* drop_seed_dev;   // optional: *drop_seed_dev is added to drop_seed (a device-resident
+                                             // step counter: a replayed CUDA graph draws a new mask every replay)
   __nv_bfloat16* out2;
 };
 
@@ -188,9 +190,10 @@ __device__ __forceinline__ void epi_store_chunk(const UmmaParams& p, const float
       for (int i = 0; i < 32; ++i) o[i] = fmaxf(o[i], 0.f);
       if (p.drop_thresh) {
         const long long e0 = mo * p.ldc + nc0;
+        const unsigned long long seed = p.drop_seed + (p.drop_seed_dev ? __ldg(p.drop_seed_dev) : 0ull);
 #pragma unroll
         for (int i = 0; i < 32; ++i)
-          o[i] = dropout_u32(p.drop_seed, e0 + i) >= p.drop_thresh
+          o[i] = dropout_u32(seed, e0 + i) >= p.drop_thresh
                      ? __bfloat162float(__float2bfloat16(o[i])) * p.drop_scale : 0.f;
       }
       if (p.out2 && ncols > 0) {

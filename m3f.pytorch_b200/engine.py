@@ -306,6 +306,8 @@ class TrainEngine:
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         self._sync_hyper()
+        from . import raw
+        raw.dropout_counter(self.all_params[0].device)      # allocated before the capture starts
         g = torch.cuda.CUDAGraph()
         ops.clear_caches()
         with torch.cuda.graph(g, capture_error_mode="thread_local"):
@@ -337,6 +339,8 @@ class TrainEngine:
         if self.on_gpu:
             from . import raw
             raw.begin_step(self.all_params[0].device)     # one memset instead of ~90 zero-fill kernels (raw.StepPool)
+            if torch.cuda.is_current_stream_capturing():   # part of the graph: fused dropout draws new masks per replay
+                raw.advance_dropout_counter(self.all_params[0].device)
             if self.steps >= 1 and os.environ.get("M3T_PREPACK", "1") == "1":
                 if not hasattr(self, "_param_ids"):
                     self._param_ids = {id(p) for p in self.all_params}

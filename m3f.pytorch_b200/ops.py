@@ -953,7 +953,8 @@ class TCNConvFn(torch.autograd.Function):
                                                                        y = relu(t + residual)  (second conv of the block)
     Weight-norm is folded into the epilogue: the tensor-core operand is the bf16 pack of `weight_v`, the per-channel
     factor g / ||v|| rides with the bias as the epilogue's scale.  The dropout mask is the counter-based generator of
-    m3t_dropout_bf16 over the element index of y (seed drawn from torch's CPU generator), applied in the epilogue.
+    m3t_dropout_bf16 over the element index of y (seed drawn from torch's CPU generator; inside a captured CUDA graph
+    plus a device-resident step counter, so that replays draw new masks), applied in the epilogue.
     Backward: ONE mask pass (m3t_tcn_epilogue_bwd_bf16: y > 0 selects the outer ReLU, t > 0 the inner ReLU AND the kept
     elements, so no mask is stored or re-derived), bias column sums, wgrad, dgrad; the weight-norm chain rule
     (dg = <dw, v> / ||v||, dv = (g / ||v||) (dw - <dw, v> v / ||v||^2)) runs on the parameter-sized tensors."""
@@ -970,11 +971,12 @@ class TCNConvFn(torch.autograd.Function):
         else:       # diagnostic: round the EFFECTIVE weight to bf16 (what the bf16-emulating oracle does)
             wf, _ = raw.pack_filter((v.detach() * scale.view(-1, 1, 1)).contiguous(), False)
         p = float(drop_p) if training else 0.0
-        if p > 0 and torch.cuda.is_current_stream_capturing():
-            raise RuntimeError("TCNConvFn: the dropout seed is a host value; a captured step would replay one mask")
         seed = int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).item()) if p > 0 else 0
+        # under stream capture the host seed is frozen into the graph: the device-resident step counter, advanced by
+        # the captured step itself, makes every replay draw a new mask (raw.dropout_counter)
+        seed_dev = raw.dropout_counter(x.device) if (p > 0 and torch.cuda.is_current_stream_capturing()) else None
         y, t = raw.tcn_conv(x, wf, geom, scale if fold else None, b.detach() if b is not None else None,
-                            residual=residual, drop_p=p, seed=seed, want_t=training)
+                            residual=residual, drop_p=p, seed=seed, want_t=training, seed_dev=seed_dev)
         ctx.seed = seed
         ctx.save_for_backward(x, v, g, y, t, scale, norm)
         ctx.cfg = (geom, dilation, pad_lo, p, b is not None, residual is not None)
@@ -1131,6 +1133,9 @@ class DropoutFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, p):
         ctx.p = float(p)
+        if torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("DropoutFn: the stand-alone dropout pass takes a host seed, a captured step would replay "
+                               "one mask; the fused TemporalBlock epilogue (M3T_TCN_FUSED=1, the default) does not")
         ctx.seed = int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).item())
         return raw.dropout_bf16(x.contiguous(), ctx.p, ctx.seed)
 

@@ -298,9 +298,30 @@ def conv_fprop(x, w_packed, g, scale=None, shift=None, residual=None, relu=False
     return y
 
 
-def tcn_conv(x, w_packed, g, scale, shift, residual=None, drop_p=0.0, seed=0, want_t=False):
+_DROPOUT_COUNTERS = {}
+_DROPOUT_STRIDE = 0x2545F4914F6CDD1D          # odd 63-bit constant: the counter walks all of Z / 2^64
+
+
+def dropout_counter(device):
+    """64-bit device-resident counter added to every fused-dropout seed drawn while a CUDA graph is being captured
+    (m3t_tcn_conv_bf16_dseed): a captured step freezes its launch arguments, so what changes between replays has to
+    live in device memory.  advance_dropout_counter() is part of the captured step (engine._eager_step)."""
+    dev = torch.device(device)
+    key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device())
+    t = _DROPOUT_COUNTERS.get(key)
+    if t is None:
+        t = _DROPOUT_COUNTERS[key] = torch.zeros(1, device=dev, dtype=torch.int64)
+    return t
+
+
+def advance_dropout_counter(device):
+    dropout_counter(device).add_(_DROPOUT_STRIDE)       # int64 wrap-around = arithmetic mod 2^64, as the kernel adds
+
+
+def tcn_conv(x, w_packed, g, scale, shift, residual=None, drop_p=0.0, seed=0, want_t=False, seed_dev=None):
     """One TemporalBlock conv with its epilogue (m3t_tcn_conv_bf16): t = dropout(relu(conv * scale + shift));
-    y = relu(t + residual) (t also returned when want_t) or y = t.  x: CL bf16 [B,T,Cin]."""
+    y = relu(t + residual) (t also returned when want_t) or y = t.  x: CL bf16 [B,T,Cin].
+    seed_dev: optional int64[1] device tensor added to `seed` on the device (dropout_counter)."""
     _chk_bf16(x, w_packed, residual)
     Z, P, Q = conv_out_dims(g)
     N, Cout = x.shape[0], w_packed.shape[0]
@@ -309,6 +330,12 @@ def tcn_conv(x, w_packed, g, scale, shift, residual=None, drop_p=0.0, seed=0, wa
     flops = 2.0 * N * Q * Cout * w_packed.shape[1]
 
     def run():
+        if seed_dev is not None:
+            L.check(L.load().m3t_tcn_conv_bf16_dseed(L.ptr(x), L.ptr(w_packed), L.ptr(y), L.ptr(t), L.int_array(g),
+                                                     L.ptr(scale), L.ptr(shift), L.ptr(residual), L.f32(drop_p),
+                                                     ctypes.c_ulonglong(int(seed)), L.ptr(seed_dev), L.stream_ptr()),
+                    "tcn_conv_dseed")
+            return
         L.check(L.load().m3t_tcn_conv_bf16(L.ptr(x), L.ptr(w_packed), L.ptr(y), L.ptr(t), L.int_array(g), L.ptr(scale),
                                            L.ptr(shift),
                                            L.ptr(residual), L.f32(drop_p), ctypes.c_ulonglong(int(seed)),

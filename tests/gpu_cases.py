@@ -2256,6 +2256,57 @@ for _t in ("resnet", "v2psplit"):
 TOLS["pdl_graph_bits"] = 0.5
 
 
+# ----------------------------------------------------------------------------------------------------------
+# A captured training step of a TCN-backend model with dropout (reference models/tcn.py:23,29; `--backend tcn`): the
+# launch arguments of a CUDA graph are frozen, so the fused-dropout seed is host seed + a device-resident counter the
+# captured step advances (raw.dropout_counter, m3t_tcn_conv_bf16_dseed).  With lr = 0 and one fixed batch the loss
+# changes from replay to replay only through the masks: every replay must draw a new one; with p = 0 the same replays
+# give one loss (BatchNorm running statistics do not enter a training-mode forward).
+# ----------------------------------------------------------------------------------------------------------
+def case_tcn_graph_dropout(seed=0, clips=4, replays=4):
+    import bench as BN
+    from m3t_b200 import ops, raw
+    from m3t_b200.engine import TrainEngine
+    from m3t_b200.models.model import AffWild2VA
+    hp = BN.hparams()
+    hp.modality, hp.backbone, hp.backend, hp.loss = "visual", "v2p", "tcn", "ccc"
+    batch = {k: v.cuda() for k, v in BN.synth_batch(clips, 77, pin=False).items()}
+    errs = {}
+
+    def losses(p_drop):
+        ops.clear_caches()
+        torch.manual_seed(seed)
+        m = AffWild2VA(hp).cuda()
+        m.train()
+        for mod in m.modules():
+            if isinstance(mod, torch.nn.Dropout):
+                mod.p = p_drop
+        eng = TrainEngine(m, lr=0.0, weight_decay=0.0, clip=1.0)
+        eng.capture(batch, warmup=2)
+        c0 = int(raw.dropout_counter("cuda").item())
+        out = [float(eng.step(batch)) for _ in range(replays)]
+        c1 = int(raw.dropout_counter("cuda").item())
+        return out, (c1 - c0) % (1 << 64)
+
+    prev = raw.set_deterministic(True)      # fixed-order accumulation: without dropout the replays are bit-identical,
+    try:                                    # so distinct losses can only come from distinct masks
+        with_drop, adv = losses(0.2)
+        without, _ = losses(0.0)
+    finally:
+        raw.set_deterministic(prev)
+    errs["tcn_graph_nodrop_differs"] = float(len(set(without)) != 1)       # control: lr = 0, no dropout -> one loss
+    errs["tcn_graph_counter_advances"] = 0.0 if adv == (replays * raw._DROPOUT_STRIDE) % (1 << 64) else 1.0
+    errs["tcn_graph_masks_repeat"] = float(len(set(with_drop)) != len(with_drop))
+    errs["tcn_graph_nonfinite"] = float(sum(1 for v in with_drop if not (v == v and abs(v) < 1e6)))
+    errs["info"] = {"losses_with_dropout": [round(v, 5) for v in with_drop], "losses_without": [round(v, 5) for v in without]}
+    return errs
+
+
+CASES["tcn_graph_dropout"] = (case_tcn_graph_dropout, _c())
+for _k in ("tcn_graph_counter_advances", "tcn_graph_masks_repeat", "tcn_graph_nonfinite", "tcn_graph_nodrop_differs"):
+    TOLS[_k] = 0.5
+
+
 if __name__ == "__main__":
     name = sys.argv[1]
     errs = run_case(name)
