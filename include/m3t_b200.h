@@ -277,7 +277,8 @@ int m3t_dropout_bf16(const void* x, void* y, long long n, float p, unsigned long
  * Replaces nn.GRU(batch_first=True, bidirectional=True) (models/rnn.py:17,72-75) = cuDNN RNN in the reference. */
 int m3t_gru_fwd(const float* gi, const void* w_hh_bf16, const float* b_hh, void* out_bf16, float* out_f32,
                 float* saved, unsigned* counters, int B, int T, int H, void* stream);
-/* Small-batch variant of m3t_gru_fwd (B <= 64, H in {128, 256, 512}; `saved` as in m3t_gru_fwd or NULL): per direction and group
+/* Small-batch variant of m3t_gru_fwd (B <= 64 always, up to the number of 16-row clusters the device keeps resident
+ * beyond that - returns -3 when they would not all be resident; H in {128, 256, 512}; `saved` as in m3t_gru_fwd or NULL): per direction and group
  * of 16 batch rows one thread-block cluster (H/64 CTAs), W_hh stays in shared memory and the hidden state is exchanged over
  * distributed shared memory behind one hardware cluster barrier per step instead of through L2 + an arrival counter.
  * Same operands, k order and gate arithmetic as m3t_gru_fwd.  Returns -1 for shapes it does not take. */

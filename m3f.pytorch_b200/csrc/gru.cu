@@ -905,7 +905,7 @@ extern "C" int m3t_gru_fwd(const float* gi, const void* w_hh_bf16, const float* 
 extern "C" int m3t_gru_fwd_cluster(const float* gi, const void* w_hh_bf16, const float* b_hh, void* out_bf16,
                                    float* out_f32, float* saved, int B, int T, int H, void* stream) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (H % kCJS != 0 || H > 512 || B <= 0 || B > 4 * kCRows || T <= 0) return -1;   // <= 64 CTAs: one wave
+  if (H % kCJS != 0 || H > 512 || B <= 0 || T <= 0) return -1;
   GruParams p;
   memset(&p, 0, sizeof(p));
   p.B = B; p.T = T; p.H = H;
@@ -933,6 +933,23 @@ extern "C" int m3t_gru_fwd_cluster(const float* gi, const void* w_hh_bf16, const
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  // every cluster must be resident at once (a second wave would double the sequence latency): 8 clusters (64 rows)
+  // always are; beyond that ask the occupancy calculator for this cluster size and shared-memory footprint
+  static int max_clusters[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};     // by cluster size, stored + 1 (0 = not asked yet)
+  const int need = 2 * ((B + kCRows - 1) / kCRows);
+  if (need > 8) {
+    if (!max_clusters[ncta]) {
+      cudaLaunchConfig_t q = cfg;
+      q.gridDim = dim3(ncta, 8, 2);
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, gru_fwd_cluster_kernel, &q) != cudaSuccess) {
+        cudaGetLastError();
+        n = 8;
+      }
+      max_clusters[ncta] = n + 1;
+    }
+    if (need > max_clusters[ncta] - 1) return -3;
+  }
   cudaError_t e = cudaLaunchKernelEx(&cfg, gru_fwd_cluster_kernel, p);
   count_launch();
   if (e != cudaSuccess) return -21;

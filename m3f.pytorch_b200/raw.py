@@ -808,12 +808,19 @@ def gru_fwd(gi, w_hh_bf16, b_hh, B, T, H, want_saved, want_f32=False, cluster=No
     if cluster is None:
         cluster = gru_cluster_default()
     saved = torch.empty((B * T, 2, 4, H), device=dev, dtype=torch.float32) if want_saved else None
-    if cluster and B <= 64 and H % 64 == 0 and H <= 512:
-        _timed("gru_fwd_cluster B%d T%d H%d" % (B, T, H), 0.0, lambda: L.check(
-            _lib().m3t_gru_fwd_cluster(L.ptr(gi), L.ptr(w_hh_bf16), L.ptr(b_hh), L.ptr(out), L.ptr(out32),
-                                       L.ptr(saved), L.i32(B), L.i32(T), L.i32(H), L.stream_ptr()),
-            "gru_fwd_cluster"), _nb(gi, w_hh_bf16, out, out32, saved))
-        return out, out32, saved
+    if cluster and B <= 128 and H % 64 == 0 and H <= 512:
+        # one cluster per 16 rows and direction, all resident at once: 64 rows always fit, up to 128 when the device
+        # keeps that many clusters of this size resident (the call returns -3 otherwise -> L2 kernel below)
+        box = [0]
+
+        def launch():
+            box[0] = _lib().m3t_gru_fwd_cluster(L.ptr(gi), L.ptr(w_hh_bf16), L.ptr(b_hh), L.ptr(out), L.ptr(out32),
+                                                L.ptr(saved), L.i32(B), L.i32(T), L.i32(H), L.stream_ptr())
+            if box[0] != -3:
+                L.check(box[0], "gru_fwd_cluster")
+        _timed("gru_fwd_cluster B%d T%d H%d" % (B, T, H), 0.0, launch, _nb(gi, w_hh_bf16, out, out32, saved))
+        if box[0] != -3:
+            return out, out32, saved
     counters = torch.empty((2 * ((B + 31) // 32) + 2,), device=dev, dtype=torch.int32)
     _timed("gru_fwd B%d T%d H%d" % (B, T, H), 0.0, lambda: L.check(
         _lib().m3t_gru_fwd(L.ptr(gi), L.ptr(w_hh_bf16), L.ptr(b_hh), L.ptr(out), L.ptr(out32), L.ptr(saved),

@@ -1717,7 +1717,8 @@ def case_gru_cluster(seed=0):
     g = torch.Generator().manual_seed(seed)
     errs, info = {"gru_cluster_exact": 0.0, "gru_cluster_f32_exact": 0.0, "gru_cluster_nonfinite": 0.0}, {}
     for B, T, H in ((16, 64, 512), (2, 16, 512), (7, 33, 256), (16, 40, 128), (1, 5, 512), (16, 256, 512),
-                    (32, 32, 512), (40, 9, 256), (64, 16, 128)):
+                    (32, 32, 512), (40, 9, 256), (64, 16, 128), (100, 7, 512), (128, 16, 512), (128, 16, 256),
+                    (112, 5, 128)):
         gi = (torch.randn((B * T, 6 * H), generator=g) * 0.8).cuda()
         w = (torch.randn((2, 3 * H, H), generator=g) / H ** 0.5).bfloat16().cuda()
         bh = (torch.randn((2, 3 * H), generator=g) * 0.1).cuda()
